@@ -1,0 +1,16 @@
+"""exomedepth_b200 — B200-native CNV-calling core behind ExomeDepth's .Call boundary.
+
+Host-side mirror of the reference's interface for ONE hot path (emission log-likelihood + HMM Viterbi):
+
+    get_loglike_matrix(phi, expected, total, observed, mixture)   src/CNV_estimate.cpp:52-85
+    C_hmm / viterbi_hmm(transitions, loglikelihood, positions, L)  src/hmm.cpp:18-167, R/tools.R:88-103
+    ExomeDepth(test, reference, phi, expected, ...)                R/class_definition.R:82-191 (likelihood step)
+    CallCNVs(x, chromosome, start, end, name, ...)                 R/class_definition.R:311-419
+    Cohort                                                         many samples × one bin set, device resident
+
+All numerics run in hand-written sm_100a CUDA kernels through the C ABI in include/exomedepth_b200.h.
+There is no CPU fallback.
+"""
+from ._lib import EDB200Error, device_info, init, launch_count  # noqa: F401
+from .api import C_hmm, CallCNVs, ExomeDepth, emission, get_loglike_matrix, viterbi_hmm  # noqa: F401
+from .cohort import Cohort  # noqa: F401

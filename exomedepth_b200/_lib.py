@@ -1,0 +1,115 @@
+"""ctypes binding of libexomedepth_b200.so (the C ABI of include/exomedepth_b200.h).
+
+The library is CUDA-only.  If it is missing, or no sm_100 device is usable, every entry point raises:
+there is no CPU fallback anywhere in this package.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libexomedepth_b200.so")
+
+OK, WARN_NAN, ERR_NSTATES, ERR_CUDA, ERR_ARG, WARN_CALLCAP = 0, 1, 2, 4, 8, 16
+MAX_STATES = 7
+EMISSION_AUTO, EMISSION_DIRECT, EMISSION_TABLE = 0, 1, 2
+
+EXPORTS = (
+    "edb200_init", "edb200_shutdown", "edb200_last_error", "edb200_device_info", "edb200_launch_count",
+    "edb200_host_alloc", "edb200_host_free", "edb200_get_loglike_matrix", "edb200_emission", "edb200_hmm",
+    "edb200_cohort_create", "edb200_cohort_destroy", "edb200_cohort_table", "edb200_cohort_table_copy",
+    "edb200_cohort_run_device",
+    "edb200_cohort_run_host", "edb200_status",
+)
+
+
+class EDB200Error(RuntimeError):
+    pass
+
+
+class CohortSpec(C.Structure):
+    _fields_ = [("n_bins", C.c_int64), ("n_chains", C.c_int32), ("chain_offsets", C.c_void_p),
+                ("start", C.c_void_p), ("end", C.c_void_p), ("n_states", C.c_int32), ("odds", C.c_void_p),
+                ("mixture", C.c_double), ("transitions", C.c_void_p), ("transition_probability", C.c_double),
+                ("expected_cnv_length", C.c_double), ("skip_table_build", C.c_int32)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("n_samples", C.c_int32), ("observed", C.c_void_p), ("obs_stride", C.c_int64),
+                ("reference", C.c_void_p), ("ref_stride", C.c_int64), ("phi", C.c_void_p),
+                ("expected", C.c_void_p), ("ll", C.c_void_p), ("ll_stride", C.c_int64), ("path", C.c_void_p),
+                ("path_stride", C.c_int64), ("calls", C.c_void_p), ("ncalls", C.c_void_p), ("call_cap", C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library and declare prototypes.  Does not touch the GPU."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EDB200Error(f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C exomedepth_b200/csrc`); exomedepth_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    L.edb200_init.restype = C.c_int
+    L.edb200_init.argtypes = [C.c_int]
+    L.edb200_shutdown.restype = None
+    L.edb200_last_error.restype = C.c_char_p
+    L.edb200_device_info.restype = C.c_int
+    L.edb200_device_info.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.edb200_launch_count.restype = i64
+    L.edb200_launch_count.argtypes = [C.c_int]
+    L.edb200_host_alloc.restype = vp
+    L.edb200_host_alloc.argtypes = [C.c_size_t]
+    L.edb200_host_free.restype = None
+    L.edb200_host_free.argtypes = [vp]
+    L.edb200_get_loglike_matrix.restype = C.c_int
+    L.edb200_get_loglike_matrix.argtypes = [vp, vp, vp, vp, dbl, i64, vp]
+    L.edb200_emission.restype = C.c_int
+    L.edb200_emission.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp]
+    L.edb200_hmm.restype = C.c_int
+    L.edb200_hmm.argtypes = [i32, i32, vp, vp, vp, dbl, vp, vp, i32, vp]
+    L.edb200_cohort_create.restype = C.c_int
+    L.edb200_cohort_create.argtypes = [C.POINTER(CohortSpec), C.POINTER(vp)]
+    L.edb200_cohort_destroy.restype = None
+    L.edb200_cohort_destroy.argtypes = [vp]
+    L.edb200_cohort_table.restype = C.c_int
+    L.edb200_cohort_table.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.edb200_cohort_table_copy.restype = C.c_int
+    L.edb200_cohort_table_copy.argtypes = [vp, vp, C.c_int, vp]
+    L.edb200_cohort_run_device.restype = C.c_int
+    L.edb200_cohort_run_device.argtypes = [vp, C.POINTER(Batch), C.c_int, C.c_int, vp]
+    L.edb200_cohort_run_host.restype = C.c_int
+    L.edb200_cohort_run_host.argtypes = [vp, C.POINTER(Batch), C.c_int]
+    L.edb200_status.restype = C.c_int
+    L.edb200_status.argtypes = [C.c_int]
+    _lib = L
+    return L
+
+
+def last_error():
+    return load().edb200_last_error().decode()
+
+
+def check(rc, what):
+    """Raise on failure codes; return the warning bits (WARN_NAN, WARN_CALLCAP)."""
+    if rc & (ERR_NSTATES | ERR_CUDA | ERR_ARG):
+        raise EDB200Error(f"{what}: {last_error()} (status {rc})")
+    return rc
+
+
+def init(device=-1):
+    check(load().edb200_init(int(device)), "edb200_init")
+
+
+def device_info():
+    buf = C.create_string_buffer(256)
+    sms, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+    check(load().edb200_device_info(buf, 256, C.byref(sms), C.byref(maj), C.byref(mnr)), "edb200_device_info")
+    return dict(name=buf.value.decode(), n_sms=sms.value, cc=(maj.value, mnr.value))
+
+
+def launch_count(reset=False):
+    return int(load().edb200_launch_count(1 if reset else 0))

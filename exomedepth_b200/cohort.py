@@ -1,0 +1,106 @@
+"""Cohort: many samples over one shared, ordered bin set — the batched form of
+`new('ExomeDepth')`'s likelihood step + `CallCNVs`' per-chromosome Viterbi (R/class_definition.R:184-189,
+342-374).  torch is used only for device memory, streams and torch.distributed plumbing; all arithmetic
+is in the CUDA kernels behind the C ABI."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+class Cohort:
+    def __init__(self, chain_offsets, start, end, n_states=3, mixture=1.0, odds=None, transitions=None,
+                 transition_probability=1e-4, expected_cnv_length=50000.0, build_table=True, device=-1):
+        _lib.init(device)
+        self.lib = _lib.load()
+        self.chain_offsets = np.ascontiguousarray(np.asarray(chain_offsets, np.int64))
+        self.start = np.ascontiguousarray(np.asarray(start, np.int32))
+        self.end = np.ascontiguousarray(np.asarray(end, np.int32))
+        self.n_bins = int(self.start.size)
+        self.n_chains = int(self.chain_offsets.size - 1)
+        self.n_states = int(n_states)
+        odds_a = None if odds is None else np.ascontiguousarray(np.asarray(odds, np.float64))
+        T_a = None if transitions is None else np.ascontiguousarray(np.asarray(transitions, np.float64).ravel(order="F"))
+        spec = _lib.CohortSpec(self.n_bins, self.n_chains, _ptr(self.chain_offsets), _ptr(self.start), _ptr(self.end),
+                               self.n_states, _ptr(odds_a), float(mixture), _ptr(T_a), float(transition_probability),
+                               float(expected_cnv_length), 0 if build_table else 1)
+        h = C.c_void_p()
+        _lib.check(self.lib.edb200_cohort_create(C.byref(spec), C.byref(h)), "edb200_cohort_create")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.edb200_cohort_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- shared metadata ------------------------------------------------------------------------
+    def table_bytes(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        _lib.check(self.lib.edb200_cohort_table(self.handle, C.byref(p), C.byref(n)), "edb200_cohort_table")
+        return int(n.value)
+
+    def table_to(self, tensor, stream=0):
+        """copy the log-transition table into a torch.float64 CUDA tensor (for dist.broadcast from rank 0)"""
+        assert tensor.is_cuda and tensor.numel() * tensor.element_size() >= self.table_bytes()
+        _lib.check(self.lib.edb200_cohort_table_copy(self.handle, tensor.data_ptr(), 0, stream), "table_copy")
+
+    def table_from(self, tensor, stream=0):
+        assert tensor.is_cuda and tensor.numel() * tensor.element_size() >= self.table_bytes()
+        _lib.check(self.lib.edb200_cohort_table_copy(self.handle, tensor.data_ptr(), 1, stream), "table_copy")
+
+    # ---- host buffers ---------------------------------------------------------------------------
+    def run_host(self, observed, reference, phi, expected, want_ll=True, want_path=True, call_cap=512,
+                 mode=_lib.EMISSION_AUTO, out=None):
+        """observed int32[n_samples, n_bins]; reference int32[n_bins] (shared) or [n_samples, n_bins];
+        phi, expected float64[n_samples].  Returns dict(ll [n,S,bins], path int8 [n,bins], calls, ncalls, status)."""
+        observed = np.ascontiguousarray(np.asarray(observed, np.int32))
+        reference = np.ascontiguousarray(np.asarray(reference, np.int32))
+        ns = observed.shape[0]
+        phi = np.ascontiguousarray(np.broadcast_to(np.asarray(phi, np.float64), (ns,)))
+        expected = np.ascontiguousarray(np.broadcast_to(np.asarray(expected, np.float64), (ns,)))
+        S, nb = self.n_states, self.n_bins
+        assert observed.shape == (ns, nb)
+        out = out or {}
+        ll = out.get("ll") if want_ll else None
+        if want_ll and ll is None:
+            ll = np.empty((ns, S, nb))
+        path = out.get("path") if want_path else None
+        if want_path and path is None:
+            path = np.empty((ns, nb), np.int8)
+        calls = out.get("calls")
+        if calls is None:
+            calls = np.zeros((ns, call_cap, 4), np.int32)
+        ncalls = out.get("ncalls")
+        if ncalls is None:
+            ncalls = np.zeros(ns, np.int32)
+        b = _lib.Batch(ns, _ptr(observed), nb, _ptr(reference), 0 if reference.ndim == 1 else nb, _ptr(phi),
+                       _ptr(expected), _ptr(ll), nb, _ptr(path), nb, _ptr(calls), _ptr(ncalls), call_cap)
+        rc = _lib.check(self.lib.edb200_cohort_run_host(self.handle, C.byref(b), mode), "edb200_cohort_run_host")
+        return dict(ll=ll, path=path, calls=calls, ncalls=ncalls, status=rc)
+
+    # ---- device tensors (torch) -----------------------------------------------------------------
+    def run_device(self, observed, reference, phi, expected, ll, path=None, calls=None, ncalls=None,
+                   what=3, mode=_lib.EMISSION_AUTO, stream=None):
+        """All arguments are CUDA tensors on this cohort's device; enqueues on `stream` (default: torch's
+        current stream) without synchronising."""
+        import torch
+        ns = observed.shape[0]
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        b = _lib.Batch(ns, observed.data_ptr(), observed.stride(0), reference.data_ptr(),
+                       0 if reference.dim() == 1 else reference.stride(0), phi.data_ptr(), expected.data_ptr(),
+                       ll.data_ptr(), ll.stride(1), path.data_ptr() if path is not None else None,
+                       path.stride(0) if path is not None else 0, calls.data_ptr() if calls is not None else None,
+                       ncalls.data_ptr() if ncalls is not None else None, calls.shape[1] if calls is not None else 0)
+        return _lib.check(self.lib.edb200_cohort_run_device(self.handle, C.byref(b), what, mode, st),
+                          "edb200_cohort_run_device")

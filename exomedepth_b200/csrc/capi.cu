@@ -1,0 +1,605 @@
+// capi.cu — the C ABI declared in include/exomedepth_b200.h: context, device workspaces, and the
+// host-/device-pointer entry points that stand in for the reference's two .Call routines
+// (src/ExomeDepth_init.c:14-24) and for the per-sample loop that R drives around them.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/exomedepth_b200.h"
+#include "host_tables.h"
+#include "kernels.cuh"
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Context {
+    bool ready = false;
+    int device = 0;
+    int n_sms = 148;
+    int cc_major = 0, cc_minor = 0;
+    size_t smem_optin = 0;
+    std::string name;
+    cudaStream_t stream = nullptr;       // used by the host-pointer entry points
+    unsigned* d_flags = nullptr;         // sticky device warning word
+    unsigned sticky = 0;
+    std::vector<DevBuf*> bufs;
+};
+
+Context g;
+std::mutex g_mu;
+thread_local std::string t_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(EDB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int ensure(DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return 0;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+
+void release(DevBuf& b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+int need_ctx()
+{
+    if (g.ready) return 0;
+    return edb200_init(-1);
+}
+
+int check_kernel(const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(EDB200_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+// scratch used by the single-call (reference-shaped) entry points
+struct CallScratch {
+    DevBuf phi, expected, total, observed, odds, ll, consts, lt, chains, bp, path, ccalls, cncalls, calls, ncalls;
+} cs;
+
+}  // namespace
+
+// =====================================================================================================
+struct edb200_cohort {
+    int64_t n_bins = 0;
+    int32_t n_chains = 0;
+    int32_t S = 3;
+    int64_t total_rows = 0;
+    double L = 50000.0;
+    double odds[EDB200_MAX_STATES];
+    double T[EDB200_MAX_STATES * EDB200_MAX_STATES];
+    int perm[EDB200_MAX_STATES];
+    std::vector<edb::ChainDesc> chains_h;
+    DevBuf chains, lt, odds_d;
+    // per-batch scratch
+    DevBuf consts, bp, ccalls, cncalls, maxima;
+    // host-mode staging
+    DevBuf h_obs, h_ref, h_phi, h_exp, h_ll, h_path, h_calls, h_ncalls;
+};
+
+extern "C" {
+
+int edb200_init(int device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.ready && (device < 0 || device == g.device)) return 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(EDB200_ERR_CUDA, "no CUDA device available (%s); exomedepth_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0) {
+        const char* lr = getenv("LOCAL_RANK");
+        device = lr ? atoi(lr) % count : 0;
+    }
+    if (device >= count) return fail(EDB200_ERR_ARG, "device %d out of range (%d devices)", device, count);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, device));
+    g.device = device;
+    g.n_sms = p.multiProcessorCount;
+    g.cc_major = p.major;
+    g.cc_minor = p.minor;
+    g.smem_optin = p.sharedMemPerBlockOptin;
+    g.name = p.name;
+    if (p.major < 10)
+        return fail(EDB200_ERR_CUDA, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 part; this library ships sm_100a code only",
+                    device, p.name, p.major, p.minor);
+    if (!g.stream) CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    if (!g.d_flags) {
+        CU(cudaMalloc(&g.d_flags, sizeof(unsigned)));
+        CU(cudaMemset(g.d_flags, 0, sizeof(unsigned)));
+    }
+    g.ready = true;
+    return 0;
+}
+
+void edb200_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.ready) return;
+    cudaDeviceSynchronize();
+    DevBuf* all[] = {&cs.phi, &cs.expected, &cs.total, &cs.observed, &cs.odds, &cs.ll, &cs.consts, &cs.lt,
+                     &cs.chains, &cs.bp, &cs.path, &cs.ccalls, &cs.cncalls, &cs.calls, &cs.ncalls};
+    for (DevBuf* b : all) release(*b);
+    if (g.d_flags) cudaFree(g.d_flags);
+    g.d_flags = nullptr;
+    if (g.stream) cudaStreamDestroy(g.stream);
+    g.stream = nullptr;
+    g.ready = false;
+}
+
+const char* edb200_last_error(void) { return t_err.c_str(); }
+
+int edb200_device_info(char* buf, int buflen, int* n_sms, int* cc_major, int* cc_minor)
+{
+    if (int rc = need_ctx()) return rc;
+    if (buf && buflen > 0) snprintf(buf, buflen, "%s sm_%d%d %d SMs", g.name.c_str(), g.cc_major, g.cc_minor, g.n_sms);
+    if (n_sms) *n_sms = g.n_sms;
+    if (cc_major) *cc_major = g.cc_major;
+    if (cc_minor) *cc_minor = g.cc_minor;
+    return 0;
+}
+
+int64_t edb200_launch_count(int reset)
+{
+    long long n = g_launches.load();
+    if (reset) g_launches.store(0);
+    return n;
+}
+
+void* edb200_host_alloc(size_t bytes)
+{
+    if (need_ctx()) return nullptr;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        fail(EDB200_ERR_CUDA, "cudaHostAlloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void edb200_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int edb200_status(int reset)
+{
+    if (int rc = need_ctx()) return rc;
+    unsigned f = 0;
+    CU(cudaMemcpy(&f, g.d_flags, sizeof f, cudaMemcpyDeviceToHost));
+    g.sticky |= f;
+    int out = (int)g.sticky;
+    if (reset) {
+        g.sticky = 0;
+        CU(cudaMemset(g.d_flags, 0, sizeof(unsigned)));
+    }
+    return out;
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+namespace {
+
+constexpr int kTableK = 2048, kTableRN = 12288;   // lattice caps: (2048 + 2*12288) * 8 B = 208 KB of shared memory
+
+int pull_flags(cudaStream_t st, int* warn)
+{
+    unsigned f = 0;
+    CU(cudaMemcpyAsync(&f, g.d_flags, sizeof f, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (f) {
+        CU(cudaMemsetAsync(g.d_flags, 0, sizeof(unsigned), st));
+        g.sticky |= f;
+    }
+    *warn = (f & edb::kFlagNaN) ? EDB200_WARN_NAN : 0;
+    return 0;
+}
+
+// emission for device-resident inputs; consts scratch must hold n_samples*S StateConst
+int run_emission_scalar(edb::CountsView cv, const double* d_phi, const double* d_expected, const double* d_odds,
+                        edb::StateConst* d_consts, int n_samples, int S, int64_t n_bins, edb::LLView out,
+                        int mode, cudaStream_t st)
+{
+    edb::launch_state_setup(n_samples, S, d_phi, d_expected, d_odds, d_consts, st);
+    g_launches++;
+    bool table = mode == EDB200_EMISSION_TABLE;
+    if (mode == EDB200_EMISSION_AUTO) table = n_bins >= 4 * (int64_t)(kTableK + 2 * kTableRN);
+    if (table) {
+        edb::TableDims d{kTableK, kTableRN, kTableRN};
+        if (edb::emission_table_smem_bytes(d) > g.smem_optin)
+            return fail(EDB200_ERR_CUDA, "device offers %zu B of shared memory per CTA; the lattice kernel needs %zu",
+                        g.smem_optin, edb::emission_table_smem_bytes(d));
+        edb::launch_emission_table(cv, d_consts, n_samples, S, n_bins, d, out, g.d_flags, g.n_sms, st);
+    } else {
+        edb::launch_emission_direct(cv, d_consts, n_samples, S, n_bins, out, g.d_flags, st);
+    }
+    g_launches++;
+    return check_kernel("emission");
+}
+
+}  // namespace
+
+extern "C" {
+
+int edb200_emission(const double* phi, const double* expected, const int32_t* total, const int32_t* observed,
+                    int64_t n, int32_t n_states, const double* odds, double* ll_out)
+{
+    if (int rc = need_ctx()) return rc;
+    if (n_states < 2 || n_states > EDB200_MAX_STATES) return fail(EDB200_ERR_NSTATES, "n_states=%d not in [2,%d]", n_states, EDB200_MAX_STATES);
+    if (n < 0 || (n > 0 && (!phi || !expected || !total || !observed || !ll_out)) || !odds) return fail(EDB200_ERR_ARG, "null argument");
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaStream_t st = g.stream;
+    const int S = n_states;
+    if (int rc = ensure(cs.total, n * 4)) return rc;
+    if (int rc = ensure(cs.observed, n * 4)) return rc;
+    if (int rc = ensure(cs.odds, S * 8)) return rc;
+    if (int rc = ensure(cs.ll, (size_t)n * S * 8)) return rc;
+    CU(cudaMemcpyAsync(cs.total.p, total, n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(cs.observed.p, observed, n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(cs.odds.p, odds, S * 8, cudaMemcpyHostToDevice, st));
+    edb::LLView out{(double*)cs.ll.p, 0, n};
+
+    // R hands over full-length vectors even when the fit is a single (phi, expected) pair
+    // (R/class_definition.R:119, 168); detect that and hoist the per-state constants.
+    bool constant = true;
+    for (int64_t i = 1; i < n && constant; i++) constant = phi[i] == phi[0] && expected[i] == expected[0];
+    if (constant) {
+        if (int rc = ensure(cs.phi, 8)) return rc;
+        if (int rc = ensure(cs.expected, 8)) return rc;
+        if (int rc = ensure(cs.consts, S * sizeof(edb::StateConst))) return rc;
+        CU(cudaMemcpyAsync(cs.phi.p, phi, 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(cs.expected.p, expected, 8, cudaMemcpyHostToDevice, st));
+        edb::CountsView cv{(const int32_t*)cs.observed.p, n, (const int32_t*)cs.total.p, 0, 1};
+        if (int rc = run_emission_scalar(cv, (double*)cs.phi.p, (double*)cs.expected.p, (double*)cs.odds.p,
+                                         (edb::StateConst*)cs.consts.p, 1, S, n, out, EDB200_EMISSION_AUTO, st))
+            return rc;
+    } else {
+        if (int rc = ensure(cs.phi, n * 8)) return rc;
+        if (int rc = ensure(cs.expected, n * 8)) return rc;
+        CU(cudaMemcpyAsync(cs.phi.p, phi, n * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(cs.expected.p, expected, n * 8, cudaMemcpyHostToDevice, st));
+        edb::launch_emission_bins((double*)cs.phi.p, (double*)cs.expected.p, (int32_t*)cs.total.p, (int32_t*)cs.observed.p,
+                                  n, S, (double*)cs.odds.p, out, g.d_flags, st);
+        g_launches++;
+        if (int rc = check_kernel("emission_bins")) return rc;
+    }
+    CU(cudaMemcpyAsync(ll_out, cs.ll.p, (size_t)n * S * 8, cudaMemcpyDeviceToHost, st));
+    int warn = 0;
+    if (int rc = pull_flags(st, &warn)) return rc;
+    return warn;
+}
+
+int edb200_get_loglike_matrix(const double* phi, const double* expected, const int32_t* total,
+                              const int32_t* observed, double mixture, int64_t n, double* ll_out)
+{
+    const double odds[3] = {1 - 0.5 * mixture, 1.0, 1 + 0.5 * mixture};   // src/CNV_estimate.cpp:65-66
+    return edb200_emission(phi, expected, total, observed, n, 3, odds, ll_out);
+}
+
+int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const double* probabilities,
+               const int32_t* positions, double expected_length, int32_t* path_out, int32_t* calls_out,
+               int32_t call_cap, int32_t* ncalls_out)
+{
+    if (int rc = need_ctx()) return rc;
+    if (nstates < 2 || nstates > EDB200_MAX_STATES) return fail(EDB200_ERR_NSTATES, "nstates=%d not in [2,%d]", nstates, EDB200_MAX_STATES);
+    if (nobs < 1 || !transitions || !probabilities || !positions || !path_out || !ncalls_out || call_cap < 0 || (call_cap && !calls_out))
+        return fail(EDB200_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaStream_t st = g.stream;
+    const int S = nstates;
+    const int cap = call_cap > 0 ? call_cap : 1;
+
+    std::vector<double> lt((size_t)nobs * S * S);
+    edb::build_log_transition_rows(S, transitions, positions, nobs, expected_length, lt.data());
+    edb::ChainDesc cd{};
+    cd.lt_row0 = 0;
+    cd.em_off = 0;
+    cd.out_off = 0;
+    cd.nobs = nobs;
+    cd.n_em = nobs - 1;
+    cd.out_first = 0;
+    cd.out_last = nobs - 1;
+    cd.call_shift = 0;
+
+    if (int rc = ensure(cs.lt, lt.size() * 8)) return rc;
+    if (int rc = ensure(cs.chains, sizeof cd)) return rc;
+    if (int rc = ensure(cs.ll, (size_t)nobs * S * 8)) return rc;
+    if (int rc = ensure(cs.bp, (size_t)nobs * 4)) return rc;
+    if (int rc = ensure(cs.path, (size_t)nobs)) return rc;
+    if (int rc = ensure(cs.ccalls, (size_t)cap * 16)) return rc;
+    if (int rc = ensure(cs.cncalls, 4)) return rc;
+    if (int rc = ensure(cs.calls, (size_t)cap * 16)) return rc;
+    if (int rc = ensure(cs.ncalls, 4)) return rc;
+    CU(cudaMemcpyAsync(cs.lt.p, lt.data(), lt.size() * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(cs.chains.p, &cd, sizeof cd, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(cs.ll.p, probabilities, (size_t)nobs * S * 8, cudaMemcpyHostToDevice, st));
+
+    edb::ViterbiArgs a{};
+    a.chains = (const edb::ChainDesc*)cs.chains.p;
+    a.n_chains = 1;
+    a.n_samples = 1;
+    a.n_states = S;
+    a.ll = (const double*)cs.ll.p;
+    a.ll_sample_stride = 0;
+    a.ll_state_stride = nobs;
+    for (int j = 0; j < S; j++) a.perm[j] = j;
+    a.lt = (const double*)cs.lt.p;
+    a.bp = (uint32_t*)cs.bp.p;
+    a.bp_stride = nobs;
+    a.tail_other = -100.0;
+    a.path = (int8_t*)cs.path.p;
+    a.path_stride = nobs;
+    a.chain_calls = (int32_t*)cs.ccalls.p;
+    a.chain_ncalls = (int32_t*)cs.cncalls.p;
+    a.chain_call_cap = cap;
+    a.calls = (int32_t*)cs.calls.p;
+    a.ncalls = (int32_t*)cs.ncalls.p;
+    a.call_cap = cap;
+    a.flags = g.d_flags;
+    edb::launch_viterbi(a, st);
+    g_launches += 3;
+    if (int rc = check_kernel("viterbi")) return rc;
+
+    std::vector<int8_t> p8(nobs);
+    int32_t nc = 0;
+    CU(cudaMemcpyAsync(p8.data(), cs.path.p, nobs, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&nc, cs.ncalls.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < nobs; i++) path_out[i] = p8[i];
+    *ncalls_out = nc;
+    const int have = nc < call_cap ? nc : call_cap;
+    if (have > 0) CU(cudaMemcpy(calls_out, cs.calls.p, (size_t)have * 16, cudaMemcpyDeviceToHost));
+    return nc > call_cap ? EDB200_WARN_CALLCAP : 0;
+}
+
+// ------------------------------------------------------------------------------------------------ cohort
+int edb200_cohort_create(const edb200_cohort_spec* sp, edb200_cohort** out)
+{
+    if (int rc = need_ctx()) return rc;
+    if (!sp || !out || sp->n_bins < 1 || sp->n_chains < 1 || !sp->chain_offsets || !sp->start || !sp->end)
+        return fail(EDB200_ERR_ARG, "bad cohort spec");
+    const int S = sp->n_states;
+    if (S != 3 && S != 5 && S != 7 && !(sp->odds && sp->transitions && S >= 2 && S <= EDB200_MAX_STATES))
+        return fail(EDB200_ERR_NSTATES, "n_states=%d: 3, 5, 7 have built-in tables; other values in [2,7] need explicit odds and transitions", S);
+    if (sp->chain_offsets[0] != 0 || sp->chain_offsets[sp->n_chains] != sp->n_bins)
+        return fail(EDB200_ERR_ARG, "chain_offsets must start at 0 and end at n_bins");
+    std::lock_guard<std::mutex> lk(g_mu);
+    edb200_cohort* c = new edb200_cohort();
+    c->n_bins = sp->n_bins;
+    c->n_chains = sp->n_chains;
+    c->S = S;
+    c->L = sp->expected_cnv_length;
+    // likelihood-column order is by copy number; the normal column is 1 for S=3 (CN 1,2,3) and 2 otherwise (CN 0..)
+    const int normal = S == 3 ? 1 : 2;
+    if (sp->odds) memcpy(c->odds, sp->odds, S * 8);
+    else {
+        for (int s = 0; s < S; s++) c->odds[s] = 1 + ((S == 3 ? s + 1 : s) - 2) / 2.0 * sp->mixture;
+        c->odds[normal] = 1.0;
+        if (S != 3 && c->odds[0] < 0.05) c->odds[0] = 0.05;
+    }
+    if (sp->transitions) memcpy(c->T, sp->transitions, S * S * 8);
+    else edb::callcnvs_transitions(S, sp->transition_probability, c->T);
+    c->perm[0] = normal;                                       // R/class_definition.R:364  c(2, 1, 3)
+    for (int s = 0, j = 1; s < S; s++) if (s != normal) c->perm[j++] = s;
+
+    // frame every chromosome and build its log-transition rows
+    c->chains_h.resize(c->n_chains);
+    int64_t rows = 0;
+    for (int ch = 0; ch < c->n_chains; ch++) {
+        const int64_t b0 = sp->chain_offsets[ch], b1 = sp->chain_offsets[ch + 1];
+        if (b1 <= b0) { delete c; return fail(EDB200_ERR_ARG, "empty chromosome %d", ch); }
+        edb::ChainDesc& cd = c->chains_h[ch];
+        cd.lt_row0 = rows;
+        cd.nobs = (int32_t)(b1 - b0 + 2);
+        cd.n_em = (int32_t)(b1 - b0);
+        cd.em_off = b0 - 1;
+        cd.out_off = b0 - 1;
+        cd.out_first = 1;
+        cd.out_last = (int32_t)(b1 - b0);
+        cd.call_shift = (int32_t)(b0 - 1);
+        cd.pad = 0;
+        rows += cd.nobs;
+    }
+    c->total_rows = rows;
+    std::vector<double> lt((size_t)rows * S * S);
+    std::vector<int32_t> pos;
+    for (int ch = 0; ch < c->n_chains; ch++) {
+        const int64_t b0 = sp->chain_offsets[ch], nb = sp->chain_offsets[ch + 1] - b0;
+        pos.resize(nb + 2);
+        if (edb::frame_positions(nb, sp->start + b0, sp->end + b0, c->L, pos.data())) {
+            delete c;
+            return fail(EDB200_ERR_ARG, "framed position of chromosome %d does not fit an R integer", ch);
+        }
+        if (!sp->skip_table_build)
+            edb::build_log_transition_rows(S, c->T, pos.data(), (int32_t)(nb + 2), c->L,
+                                           lt.data() + (size_t)c->chains_h[ch].lt_row0 * S * S);
+    }
+    int rc = 0;
+    if ((rc = ensure(c->lt, lt.size() * 8)) || (rc = ensure(c->chains, c->n_chains * sizeof(edb::ChainDesc))) ||
+        (rc = ensure(c->odds_d, S * 8))) {
+        delete c;
+        return rc;
+    }
+    CU(cudaMemcpy(c->lt.p, lt.data(), lt.size() * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->chains.p, c->chains_h.data(), c->n_chains * sizeof(edb::ChainDesc), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->odds_d.p, c->odds, S * 8, cudaMemcpyHostToDevice));
+    *out = c;
+    return 0;
+}
+
+void edb200_cohort_destroy(edb200_cohort* c)
+{
+    if (!c) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaDeviceSynchronize();
+    DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->maxima,
+                     &c->h_obs, &c->h_ref, &c->h_phi, &c->h_exp, &c->h_ll, &c->h_path, &c->h_calls, &c->h_ncalls};
+    for (DevBuf* b : all) release(*b);
+    delete c;
+}
+
+int edb200_cohort_table(edb200_cohort* c, void** device_ptr, size_t* bytes)
+{
+    if (!c) return fail(EDB200_ERR_ARG, "null cohort");
+    if (device_ptr) *device_ptr = c->lt.p;
+    if (bytes) *bytes = (size_t)c->total_rows * c->S * c->S * 8;
+    return 0;
+}
+
+int edb200_cohort_table_copy(edb200_cohort* c, void* device_buf, int direction, void* cuda_stream)
+{
+    if (!c || !device_buf) return fail(EDB200_ERR_ARG, "null argument");
+    const size_t bytes = (size_t)c->total_rows * c->S * c->S * 8;
+    if (direction == 0) CU(cudaMemcpyAsync(device_buf, c->lt.p, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
+    else CU(cudaMemcpyAsync(c->lt.p, device_buf, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
+    return 0;
+}
+
+int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, int emission_mode, void* cuda_stream)
+{
+    if (int rc = need_ctx()) return rc;
+    if (!c || !b) return fail(EDB200_ERR_ARG, "null argument");
+    if (b->n_samples <= 0) return 0;
+    if (!b->ll || !b->observed || !b->reference || !b->phi || !b->expected) return fail(EDB200_ERR_ARG, "null device pointer in batch");
+    if (b->obs_stride < c->n_bins || b->ll_stride < c->n_bins) return fail(EDB200_ERR_ARG, "stride smaller than n_bins");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int S = c->S, ns = b->n_samples;
+
+    if (what & 1) {
+        if (int rc = ensure(c->consts, (size_t)ns * S * sizeof(edb::StateConst))) return rc;
+        edb::CountsView cv{b->observed, b->obs_stride, b->reference, b->ref_stride, 0};
+        edb::LLView out{b->ll, (int64_t)S * b->ll_stride, b->ll_stride};
+        if (int rc = run_emission_scalar(cv, b->phi, b->expected, (const double*)c->odds_d.p, (edb::StateConst*)c->consts.p,
+                                         ns, S, c->n_bins, out, emission_mode, st))
+            return rc;
+    }
+    if (what & 2) {
+        if (!b->path || !b->calls || !b->ncalls || b->call_cap < 1 || b->path_stride < c->n_bins)
+            return fail(EDB200_ERR_ARG, "Viterbi outputs missing in batch");
+        const int ccap = b->call_cap;
+        if (int rc = ensure(c->bp, (size_t)ns * c->total_rows * 4)) return rc;
+        if (int rc = ensure(c->ccalls, (size_t)ns * c->n_chains * ccap * 16)) return rc;
+        if (int rc = ensure(c->cncalls, (size_t)ns * c->n_chains * 4)) return rc;
+        edb::ViterbiArgs a{};
+        a.chains = (const edb::ChainDesc*)c->chains.p;
+        a.n_chains = c->n_chains;
+        a.n_samples = ns;
+        a.n_states = S;
+        a.ll = b->ll;
+        a.ll_sample_stride = (int64_t)S * b->ll_stride;
+        a.ll_state_stride = b->ll_stride;
+        for (int j = 0; j < S; j++) a.perm[j] = c->perm[j];
+        a.lt = (const double*)c->lt.p;
+        a.bp = (uint32_t*)c->bp.p;
+        a.bp_stride = c->total_rows;
+        a.tail_other = -100.0;                                 // R/class_definition.R:364
+        a.path = b->path;
+        a.path_stride = b->path_stride;
+        a.chain_calls = (int32_t*)c->ccalls.p;
+        a.chain_ncalls = (int32_t*)c->cncalls.p;
+        a.chain_call_cap = ccap;
+        a.calls = b->calls;
+        a.ncalls = b->ncalls;
+        a.call_cap = b->call_cap;
+        a.flags = g.d_flags;
+        edb::launch_viterbi(a, st);
+        g_launches += 3;
+        if (int rc = check_kernel("viterbi")) return rc;
+    }
+    return 0;
+}
+
+int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission_mode)
+{
+    if (int rc = need_ctx()) return rc;
+    if (!c || !b) return fail(EDB200_ERR_ARG, "null argument");
+    if (b->n_samples <= 0) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaStream_t st = g.stream;
+    const int S = c->S, ns = b->n_samples;
+    const int64_t nb = c->n_bins;
+    const bool shared_ref = b->ref_stride == 0;
+    const int cap = b->call_cap > 0 ? b->call_cap : 1;
+    int rc = 0;
+    if ((rc = ensure(c->h_obs, (size_t)ns * nb * 4)) || (rc = ensure(c->h_ref, (size_t)(shared_ref ? 1 : ns) * nb * 4)) ||
+        (rc = ensure(c->h_phi, ns * 8)) || (rc = ensure(c->h_exp, ns * 8)) || (rc = ensure(c->h_ll, (size_t)ns * S * nb * 8)) ||
+        (rc = ensure(c->h_path, (size_t)ns * nb)) || (rc = ensure(c->h_calls, (size_t)ns * cap * 16)) ||
+        (rc = ensure(c->h_ncalls, ns * 4)))
+        return rc;
+    CU(cudaMemcpy2DAsync(c->h_obs.p, nb * 4, b->observed, b->obs_stride * 4, nb * 4, ns, cudaMemcpyHostToDevice, st));
+    if (shared_ref) CU(cudaMemcpyAsync(c->h_ref.p, b->reference, nb * 4, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemcpy2DAsync(c->h_ref.p, nb * 4, b->reference, b->ref_stride * 4, nb * 4, ns, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->h_phi.p, b->phi, ns * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->h_exp.p, b->expected, ns * 8, cudaMemcpyHostToDevice, st));
+
+    edb200_batch d = *b;
+    d.observed = (const int32_t*)c->h_obs.p;
+    d.obs_stride = nb;
+    d.reference = (const int32_t*)c->h_ref.p;
+    d.ref_stride = shared_ref ? 0 : nb;
+    d.phi = (const double*)c->h_phi.p;
+    d.expected = (const double*)c->h_exp.p;
+    d.ll = (double*)c->h_ll.p;
+    d.ll_stride = nb;
+    d.path = (int8_t*)c->h_path.p;
+    d.path_stride = nb;
+    d.calls = (int32_t*)c->h_calls.p;
+    d.ncalls = (int32_t*)c->h_ncalls.p;
+    d.call_cap = cap;
+    const bool want_vit = b->path || b->calls || b->ncalls;
+    if ((rc = edb200_cohort_run_device(c, &d, want_vit ? 3 : 1, emission_mode, st))) return rc;
+
+    if (b->ll) CU(cudaMemcpy2DAsync(b->ll, b->ll_stride * 8, c->h_ll.p, nb * 8, nb * 8, (size_t)ns * S, cudaMemcpyDeviceToHost, st));
+    if (b->path) CU(cudaMemcpy2DAsync(b->path, b->path_stride, c->h_path.p, nb, nb, ns, cudaMemcpyDeviceToHost, st));
+    if (b->calls && b->call_cap > 0) CU(cudaMemcpyAsync(b->calls, c->h_calls.p, (size_t)ns * cap * 16, cudaMemcpyDeviceToHost, st));
+    if (b->ncalls) CU(cudaMemcpyAsync(b->ncalls, c->h_ncalls.p, ns * 4, cudaMemcpyDeviceToHost, st));
+    int warn = 0;
+    if ((rc = pull_flags(st, &warn))) return rc;
+    if (b->ncalls && b->call_cap > 0)
+        for (int s = 0; s < ns; s++) if (b->ncalls[s] > b->call_cap) warn |= EDB200_WARN_CALLCAP;
+    return warn;
+}
+
+}  // extern "C"

@@ -1,0 +1,237 @@
+// emission.cu — beta-binomial emission log-likelihood kernels (sm_100a, FP64).
+//
+// Replaces get_loglike_matrix / myprob of the reference (src/CNV_estimate.cpp:44-50, 52-85) and the
+// vendored lnbeta chain under it (src/beta.c, src/VP_gamma.c, src/VP_log.c).
+//
+//   emission_bins_kernel    reference-API shape: one sample, per-bin phi / expected vectors.
+//   emission_direct_kernel  cohort shape: per-sample scalar phi / expected, constants hoisted per
+//                           (sample, state), lgamma differences in registers (FP64-pipe bound).
+//   emission_table_kernel   cohort shape, large bin counts: because the counts are integers, each
+//                           (sample, state) needs lgamma(a+j)-lgamma(a) only on an integer lattice.
+//                           One CTA per SM builds the three lattices in its 200+ KB of shared memory
+//                           and then streams the sample's bins through them with 128-bit loads/stores:
+//                           three 8-byte shared-memory gathers + two FP64 adds per cell instead of
+//                           ~150 FP64 instructions.  HBM traffic is the algorithmic 4 + 8S bytes per
+//                           bin·sample (the count vector is re-read once per state, from L2).
+#include "kernels.cuh"
+
+namespace edb {
+
+// ---------------------------------------------------------------------------------------------
+__global__ void state_setup_kernel(int n_samples, int n_states, const double* __restrict__ phi,
+                                   const double* __restrict__ expected, const double* __restrict__ odds,
+                                   StateConst* __restrict__ consts)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_samples * n_states) return;
+    const int sample = i / n_states, s = i % n_states;
+    const double e = expected[sample];
+    const double sd = best_sd(phi[sample], e);
+    consts[i] = make_state_const(state_expected(e, odds[s]), sd);
+}
+
+void launch_state_setup(int n_samples, int n_states, const double* phi, const double* expected,
+                        const double* odds, StateConst* consts, cudaStream_t st)
+{
+    const int n = n_samples * n_states;
+    if (n == 0) return;
+    state_setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(n_samples, n_states, phi, expected, odds, consts);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+emission_bins_kernel(const double* __restrict__ phi, const double* __restrict__ expected,
+                     const int32_t* __restrict__ total, const int32_t* __restrict__ observed, int64_t n_bins,
+                     int n_states, const double* __restrict__ odds, LLView out, unsigned* __restrict__ flags)
+{
+    unsigned f = 0;
+    for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < n_bins; b += (int64_t)gridDim.x * blockDim.x) {
+        const double e = expected[b];
+        const double sd = best_sd(phi[b], e);
+        const int tot = total[b], obs = observed[b];
+        for (int s = 0; s < n_states; s++) {
+            const StateConst sc = make_state_const(state_expected(e, odds[s]), sd);
+            out.ptr[s * out.state_stride + b] = cell_loglik(sc, tot, obs, f);
+        }
+    }
+    if (f) atomicOr(flags, f);
+}
+
+void launch_emission_bins(const double* phi, const double* expected, const int32_t* total,
+                          const int32_t* observed, int64_t n_bins, int n_states, const double* odds,
+                          LLView out, unsigned* flags, cudaStream_t st)
+{
+    if (n_bins == 0) return;
+    int64_t blocks = (n_bins + 127) / 128;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    emission_bins_kernel<<<(int)blocks, 128, 0, st>>>(phi, expected, total, observed, n_bins, n_states, odds, out, flags);
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_counts(const CountsView& c, int sample, int64_t b, int& tot, int& obs)
+{
+    obs = c.observed[sample * c.obs_stride + b];
+    const int o = c.other[sample * c.other_stride + b];
+    tot = c.other_is_total ? o : obs + o;
+}
+
+__global__ void __launch_bounds__(256)
+emission_direct_kernel(CountsView c, const StateConst* __restrict__ consts, int n_states, int64_t n_bins,
+                       LLView out, unsigned* __restrict__ flags)
+{
+    __shared__ StateConst sc[kMaxStates];
+    const int sample = blockIdx.y;
+    for (int i = threadIdx.x; i < n_states * (int)(sizeof(StateConst) / 8); i += blockDim.x)
+        reinterpret_cast<double*>(sc)[i] = reinterpret_cast<const double*>(consts + (int64_t)sample * n_states)[i];
+    __syncthreads();
+    unsigned f = 0;
+    double* o = out.ptr + sample * out.sample_stride;
+    for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < n_bins; b += (int64_t)gridDim.x * blockDim.x) {
+        int tot, obs;
+        load_counts(c, sample, b, tot, obs);
+        for (int s = 0; s < n_states; s++) o[s * out.state_stride + b] = cell_loglik(sc[s], tot, obs, f);
+    }
+    if (f) atomicOr(flags, f);
+}
+
+void launch_emission_direct(CountsView c, const StateConst* consts, int n_samples, int n_states,
+                            int64_t n_bins, LLView out, unsigned* flags, cudaStream_t st)
+{
+    if (n_bins == 0 || n_samples == 0) return;
+    int64_t bx = (n_bins + 255) / 256;
+    const int64_t want = (148 * 8 + n_samples - 1) / n_samples;   // ~8 CTAs per SM over the whole grid
+    if (bx > want) bx = want < 1 ? 1 : want;
+    dim3 grid((unsigned)bx, (unsigned)n_samples);
+    emission_direct_kernel<<<grid, 256, 0, st>>>(c, consts, n_states, n_bins, out, flags);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+count_maxima_kernel(CountsView c, int n_samples, int64_t n_bins, int32_t* __restrict__ maxima3)
+{
+    int mo = 0, mr = 0, mt = 0;
+    const int64_t total = (int64_t)n_samples * n_bins;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int sample = (int)(i / n_bins);
+        const int64_t b = i - sample * n_bins;
+        int tot, obs;
+        load_counts(c, sample, b, tot, obs);
+        mo = max(mo, obs);
+        mr = max(mr, tot - obs);
+        mt = max(mt, tot);
+    }
+    for (int d = 16; d; d >>= 1) {
+        mo = max(mo, __shfl_xor_sync(0xffffffffu, mo, d));
+        mr = max(mr, __shfl_xor_sync(0xffffffffu, mr, d));
+        mt = max(mt, __shfl_xor_sync(0xffffffffu, mt, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(maxima3 + 0, mo);
+        atomicMax(maxima3 + 1, mr);
+        atomicMax(maxima3 + 2, mt);
+    }
+}
+
+void launch_count_maxima(CountsView c, int n_samples, int64_t n_bins, int32_t* maxima3, cudaStream_t st)
+{
+    cudaMemsetAsync(maxima3, 0, 3 * sizeof(int32_t), st);
+    if (n_bins == 0 || n_samples == 0) return;
+    count_maxima_kernel<<<148 * 4, 256, 0, st>>>(c, n_samples, n_bins, maxima3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Table path.  One work item = (sample, state).  Lattices (see DESIGN.md "emission_table"):
+//   G1[k] = lgamma(fl(a1+k))            - lgamma(a1)          k = observed
+//   G2[r] = lgamma(fl(a2+r))            - lgamma(a2)          r = total - observed
+//   G3[n] = lgamma(fl(a1+fl(a2+n)))     - lgamma(fl(a1+a2))   n = total
+// ll = (G1[k] + G2[r]) - G3[n].  For k = 0 all three arguments coincide with the reference's own
+// roundings (CNV_estimate.cpp:49); for k > 0 they can differ from them by one rounding of a sum of
+// magnitude a1+a2+n, i.e. by <= ~4e-12 absolute on cells whose |ll| is then > 1.
+constexpr int kTableThreads = 1024;
+
+// out-of-lattice / pathological cells: kept out of line so the gather loop stays within 64 registers
+__device__ __noinline__ double cell_loglik_cold(const StateConst* sc, int total, int observed, unsigned* flags)
+{
+    unsigned f = 0;
+    const double v = cell_loglik(*sc, total, observed, f);
+    if (f) *flags |= f;
+    return v;
+}
+
+size_t emission_table_smem_bytes(TableDims d) { return sizeof(double) * ((size_t)d.K + d.R + d.N) + sizeof(StateConst); }
+
+__global__ void __launch_bounds__(kTableThreads, 1)
+emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n_states, int n_items,
+                      int64_t n_bins, TableDims dims, LLView out, unsigned* __restrict__ flags)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StateConst* scp = reinterpret_cast<StateConst*>(smem_raw);
+    double* G1 = reinterpret_cast<double*>(smem_raw + sizeof(StateConst));
+    double* G2 = G1 + dims.K;
+    double* G3 = G2 + dims.R;
+    unsigned f = 0;
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int sample = item / n_states, s = item - sample * n_states;
+        __syncthreads();     // previous item's gathers are done before the lattices are overwritten
+        for (int i = threadIdx.x; i < (int)(sizeof(StateConst) / 8); i += blockDim.x)
+            reinterpret_cast<double*>(scp)[i] = reinterpret_cast<const double*>(consts + item)[i];
+        __syncthreads();
+        const StateConst& sc = *scp;
+        const bool lattice = sc.ok;
+        if (lattice) {
+            for (int i = threadIdx.x; i < dims.K; i += blockDim.x) G1[i] = gdiff(sc.g1, __dadd_rn(sc.a1, (double)i));
+            for (int i = threadIdx.x; i < dims.R; i += blockDim.x) G2[i] = gdiff(sc.g2, __dadd_rn(sc.a2, (double)i));
+            for (int i = threadIdx.x; i < dims.N; i += blockDim.x)
+                G3[i] = gdiff(sc.g12, __dadd_rn(sc.a1, __dadd_rn(sc.a2, (double)i)));
+        }
+        __syncthreads();
+
+        const int32_t* __restrict__ obs_row = c.observed + sample * c.obs_stride;
+        const int32_t* __restrict__ oth_row = c.other + sample * c.other_stride;
+        double* __restrict__ o = out.ptr + sample * out.sample_stride + s * out.state_stride;
+        const bool vec = ((reinterpret_cast<uintptr_t>(obs_row) | reinterpret_cast<uintptr_t>(oth_row)) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(o) & 15) == 0;
+        const int64_t n4 = vec ? (n_bins & ~(int64_t)3) : 0;
+
+        auto cell = [&](int obs, int oth) -> double {
+            const int tot = c.other_is_total ? oth : obs + oth;
+            const int r = tot - obs;
+            if (lattice && obs >= 0 && r >= 0 && obs < dims.K && r < dims.R && tot < dims.N)
+                return (G1[obs] + G2[r]) - G3[tot];
+            return cell_loglik_cold(scp, tot, obs, &f);
+        };
+
+        for (int64_t b = (int64_t)threadIdx.x * 4; b < n4; b += (int64_t)blockDim.x * 4) {
+            const int4 ko = __ldg(reinterpret_cast<const int4*>(obs_row + b));
+            const int4 oo = __ldg(reinterpret_cast<const int4*>(oth_row + b));
+            double2 v0, v1;
+            v0.x = cell(ko.x, oo.x);
+            v0.y = cell(ko.y, oo.y);
+            v1.x = cell(ko.z, oo.z);
+            v1.y = cell(ko.w, oo.w);
+            __stcs(reinterpret_cast<double2*>(o + b), v0);        // streaming stores: ll is write-once
+            __stcs(reinterpret_cast<double2*>(o + b + 2), v1);
+        }
+        for (int64_t b = n4 + threadIdx.x; b < n_bins; b += blockDim.x) o[b] = cell(obs_row[b], oth_row[b]);
+    }
+    if (f) atomicOr(flags, f);
+}
+
+void launch_emission_table(CountsView c, const StateConst* consts, int n_samples, int n_states,
+                           int64_t n_bins, TableDims dims, LLView out, unsigned* flags, int n_sms,
+                           cudaStream_t st)
+{
+    const int n_items = n_samples * n_states;
+    if (n_items == 0 || n_bins == 0) return;
+    const size_t smem = emission_table_smem_bytes(dims);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(emission_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    const int grid = n_items < n_sms ? n_items : n_sms;
+    emission_table_kernel<<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, n_bins, dims, out, flags);
+}
+
+}  // namespace edb

@@ -1,0 +1,97 @@
+// host_tables.cpp — host-side construction of the shared per-bin HMM metadata.
+//
+// The distance-dependent transition terms of the reference depend on the bin, not on the sample
+// (src/hmm.cpp:62-76), yet the reference recomputes 1 exp + 9 log per observation for every sample.
+// Here they are computed ONCE per cohort, on the host, with the host libm — the same exp()/log() the
+// reference calls — so the table holds the reference's own bits (CUDA's log/exp are <= 1 ulp but not
+// bit-identical to glibc, which could flip a near-tie in the backtrace; SURVEY.md §7 hard part 2).
+// The table legitimately contains -Inf (log 0) and NaN (log of a negative term when bin starts are
+// not monotone, SURVEY.md §8c "NaN edge"); both are kept.  Compiled without FMA contraction.
+#include "host_tables.h"
+
+#include <cmath>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace edb {
+
+void callcnvs_transitions(int S, double tp, double* T)
+{
+    // R/class_definition.R:343-347 (byrow 3x3) generalised as SURVEY.md §8a H4; column-major T[k + S*j]
+    for (int k = 0; k < S; k++)
+        for (int j = 0; j < S; j++) {
+            double p;
+            if (k == 0) p = j == 0 ? 1. - tp : tp / (double)(S - 1);
+            else p = (j == 0 || j == k) ? 0.5 : 0.0;
+            T[k + S * j] = p;
+        }
+}
+
+static inline uint64_t bits_of(double x)
+{
+    uint64_t u;
+    std::memcpy(&u, &x, 8);
+    return u;
+}
+
+static void fill_rows(int S, const double* T, const int32_t* pos, double L, int64_t i0, int64_t i1, double* lt)
+{
+    double vals[64], logs[64];
+    uint64_t keys[64];
+    for (int64_t i = i0; i < i1; i++) {
+        const double dist = double(pos[i]) - double(pos[i - 1]);      // hmm.cpp:62
+        const double d = std::exp(-dist / L);                         // hmm.cpp:64
+        int nuniq = 0;
+        double* row = lt + i * S * S;
+        for (int j = 0; j < S; j++) {
+            const double t0 = T[j * S];
+            for (int k = 0; k < S; k++) {
+                const double t = k == 0 ? t0 : d * T[j * S + k] + (1.0 - d) * t0;   // hmm.cpp:74-76
+                const uint64_t key = bits_of(t);
+                int u = 0;
+                while (u < nuniq && keys[u] != key) u++;
+                if (u == nuniq) {                       // identical inputs give identical log(): memoise per row
+                    keys[u] = key;
+                    vals[u] = t;
+                    logs[u] = std::log(t);              // hmm.cpp:79
+                    nuniq++;
+                }
+                row[j * S + k] = logs[u];
+            }
+        }
+        (void)vals;
+    }
+}
+
+void build_log_transition_rows(int S, const double* T, const int32_t* pos, int32_t nobs, double L, double* lt)
+{
+    for (int q = 0; q < S * S; q++) lt[q] = 0.0;      // row 0 is never read (hmm.cpp:58 starts at i = 1)
+    if (nobs <= 1) return;
+    const int64_t n = nobs;
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)(hw ? (hw > 16 ? 16 : hw) : 1);
+    if (n < 20000) nt = 1;
+    if (nt == 1) { fill_rows(S, T, pos, L, 1, n, lt); return; }
+    std::vector<std::thread> th;
+    const int64_t per = (n - 1 + nt - 1) / nt;
+    for (int t = 0; t < nt; t++) {
+        const int64_t a = 1 + t * per, b = a + per < n ? a + per : n;
+        if (a >= b) break;
+        th.emplace_back(fill_rows, S, T, pos, L, a, b, lt);
+    }
+    for (auto& x : th) x.join();
+}
+
+int frame_positions(int64_t nb, const int32_t* start, const int32_t* end, double L, int32_t* pos)
+{
+    // R/class_definition.R:368: as.integer(c(start[1] - 2*L, start, end[last] + 2*L))
+    const double head = (double)start[0] - 2 * L, tail = (double)end[nb - 1] + 2 * L;
+    if (!(std::fabs(head) < 2147483647.0) || !(std::fabs(tail) < 2147483647.0)) return 1;   // R would give NA
+    pos[0] = (int32_t)head;                       // as.integer truncates toward zero
+    for (int64_t b = 0; b < nb; b++) pos[b + 1] = start[b];
+    pos[nb + 1] = (int32_t)tail;
+    return 0;
+}
+
+}  // namespace edb

@@ -1,0 +1,89 @@
+// kernels.cuh — host-callable launchers of the sm_100a kernels (internal; the public boundary is
+// include/exomedepth_b200.h).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "edb200_math.cuh"
+
+namespace edb {
+
+// ---- emission -----------------------------------------------------------------------------------
+struct CountsView {
+    const int32_t* observed;      // [n_samples][obs_stride]
+    int64_t obs_stride;
+    const int32_t* other;         // reference counts (total = observed + other) or totals
+    int64_t other_stride;         // 0: one vector shared by all samples
+    int other_is_total;           // 1: `other` already holds total = test + reference (reference API)
+};
+
+struct LLView {                   // ll[sample*sample_stride + state*state_stride + bin]
+    double* ptr;
+    int64_t sample_stride;
+    int64_t state_stride;
+};
+
+// per (sample, state) constants from per-sample scalar phi / expected
+void launch_state_setup(int n_samples, int n_states, const double* phi, const double* expected,
+                        const double* odds, StateConst* consts, cudaStream_t st);
+
+// reference-API shaped: per-bin phi / expected vectors of ONE sample (src/CNV_estimate.cpp:52-85)
+void launch_emission_bins(const double* phi, const double* expected, const int32_t* total,
+                          const int32_t* observed, int64_t n_bins, int n_states, const double* odds,
+                          LLView out, unsigned* flags, cudaStream_t st);
+
+// batched, per-sample scalar phi/expected, lgamma differences evaluated in registers
+void launch_emission_direct(CountsView c, const StateConst* consts, int n_samples, int n_states,
+                            int64_t n_bins, LLView out, unsigned* flags, cudaStream_t st);
+
+// batched, per (sample,state) lgamma-difference tables in shared memory + gather
+struct TableDims { int K, R, N; };    // entries for observed, other (=total-observed), total
+size_t emission_table_smem_bytes(TableDims d);
+void launch_emission_table(CountsView c, const StateConst* consts, int n_samples, int n_states,
+                           int64_t n_bins, TableDims dims, LLView out, unsigned* flags, int n_sms,
+                           cudaStream_t st);
+
+// per-launch maxima of observed / other / total over the batch -> int32[3]
+void launch_count_maxima(CountsView c, int n_samples, int64_t n_bins, int32_t* maxima3, cudaStream_t st);
+
+// ---- Viterbi ------------------------------------------------------------------------------------
+// One chain template per chromosome; shared by every sample of the batch.
+struct ChainDesc {
+    int64_t lt_row0;   // log-transition row of observation i is lt_row0 + i   (i = 1 .. nobs-1)
+    int64_t em_off;    // emission bin of observation i is em_off + i          (i = 1 .. n_em)
+    int64_t out_off;   // path_out index of observation i is out_off + i       (i = out_first .. out_last)
+    int32_t nobs;      // observations incl. the two CallCNVs dummies when framed
+    int32_t n_em;      // observations 1..n_em read the emission matrix; later ones use the tail constants
+    int32_t out_first; // first / last observation written to path_out
+    int32_t out_last;
+    int32_t call_shift;   // added to start.p / end.p (CallCNVs: -1 for the dummy + per-chromosome shift)
+    int32_t pad;
+};
+
+struct ViterbiArgs {
+    const ChainDesc* chains;      // [n_chains], longest first is best
+    int n_chains;
+    int n_samples;
+    int n_states;
+    const double* ll;             // emission matrix, see LLView strides
+    int64_t ll_sample_stride;
+    int64_t ll_state_stride;
+    int perm[kMaxStates];         // HMM state j reads emission column perm[j] (CallCNVs: c(2,1,3))
+    const double* lt;             // [rows][S(j)][S(k)] log-transition table (host libm)
+    uint32_t* bp;                 // [n_samples][bp_stride] packed back-pointers (scratch)
+    int64_t bp_stride;            // >= total rows
+    double tail_other;            // emission of the non-normal states at the dummy last observation (-100)
+    int8_t* path;                 // [n_samples][path_stride]
+    int64_t path_stride;
+    int32_t* chain_calls;         // scratch [n_samples][n_chains][chain_call_cap][4]
+    int32_t* chain_ncalls;        // scratch [n_samples][n_chains]
+    int chain_call_cap;
+    int32_t* calls;               // out [n_samples][call_cap][4]  (start.p, end.p, type, nexons)
+    int32_t* ncalls;              // out [n_samples]
+    int call_cap;
+    unsigned* flags;
+};
+
+void launch_viterbi(const ViterbiArgs& a, cudaStream_t st);
+
+}  // namespace edb

@@ -1,0 +1,146 @@
+/* exomedepth_b200.h — C ABI of the B200-native CNV-calling core for ExomeDepth.
+ *
+ * This is the drop-in boundary for ONE hot path of the reference (paths relative to /root/reference):
+ *   - the per-bin beta-binomial emission log-likelihood   src/CNV_estimate.cpp:52-85 (get_loglike_matrix)
+ *   - the HMM Viterbi sweep + traceback + segment summary  src/hmm.cpp:18-167        (C_hmm)
+ * as registered for .Call in src/ExomeDepth_init.c:14-24 and called from R/class_definition.R:184-189
+ * and R/tools.R:97.  Plain pointers and sizes only; no R, torch or CUDA types.
+ *
+ * Every entry point runs on the selected B200 (sm_100a).  There is NO CPU fallback: without a usable
+ * device the calls return EDB200_ERR_CUDA and edb200_last_error() says why.
+ *
+ * Return value of every int function: 0 on success, otherwise a bit mask of the EDB200_* codes.
+ * EDB200_WARN_NAN alone is not a failure: like the reference (src/error.c:35-52, error.h:9) a GSL-style
+ * domain error yields NaN in the affected cells, a message, and the computation continues.
+ */
+#ifndef EXOMEDEPTH_B200_H
+#define EXOMEDEPTH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define EDB200_API __attribute__((visibility("default")))
+#else
+#define EDB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDB200_OK            0
+#define EDB200_WARN_NAN      1   /* domain error(s): NaN cells produced, as src/beta.c:43-45 / error.h:9 */
+#define EDB200_ERR_NSTATES   2   /* unsupported number of states (cf. src/hmm.cpp:37-40)                  */
+#define EDB200_ERR_CUDA      4   /* no device / CUDA failure                                             */
+#define EDB200_ERR_ARG       8   /* bad argument                                                         */
+#define EDB200_WARN_CALLCAP 16   /* more CNV calls than the caller's buffer holds; ncalls has the count  */
+
+#define EDB200_MAX_STATES    7
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+/* Select the device and create the context (idempotent). device < 0: use LOCAL_RANK or 0. */
+EDB200_API int         edb200_init(int device);
+EDB200_API void        edb200_shutdown(void);
+EDB200_API const char *edb200_last_error(void);
+/* "NVIDIA B200 sm_100 148 SMs" style description of the selected device */
+EDB200_API int         edb200_device_info(char *buf, int buflen, int *n_sms, int *cc_major, int *cc_minor);
+/* count of kernels launched by this library since the last reset (bench.py's gpu_launches) */
+EDB200_API int64_t     edb200_launch_count(int reset);
+/* page-locked host buffers for the host-pointer entry points (optional, speeds up the copies) */
+EDB200_API void       *edb200_host_alloc(size_t bytes);
+EDB200_API void        edb200_host_free(void *p);
+
+/* ---- the two .Call routines, argument for argument --------------------------------------------- */
+
+/* Replaces get_loglike_matrix(phi, expected, total, observed, mixture)   src/CNV_estimate.cpp:52-85.
+ * phi, expected: double[n]; total, observed: int32[n]; ll_out: double[n*3] column-major
+ * (ll_out[c + n*s], s = 0 deletion, 1 normal, 2 duplication).  Host pointers. */
+EDB200_API int edb200_get_loglike_matrix(const double *phi, const double *expected, const int32_t *total,
+                              const int32_t *observed, double mixture, int64_t n, double *ll_out);
+
+/* S-state generalisation of the same routine (extension; n_states = 3 with odds = NULL or
+ * {1-mix/2, 1, 1+mix/2} is exactly the call above).  odds: double[n_states] multiplying the odds of the
+ * expected proportion per state; ll_out: double[n*n_states] column-major. */
+EDB200_API int edb200_emission(const double *phi, const double *expected, const int32_t *total,
+                    const int32_t *observed, int64_t n, int32_t n_states, const double *odds, double *ll_out);
+
+/* Replaces C_hmm(nstates, nobs, transitions, probabilities, positions, expectedLength)  src/hmm.cpp:18-167.
+ * transitions: double[S*S] column-major (R matrix; [k + S*j] = P(k -> j)); probabilities: double[nobs*S]
+ * column-major in HMM state order (0 = normal); positions: int32[nobs].
+ * path_out: int32[nobs]; calls_out: int32[4*call_cap] row-major (start.p, end.p, type, nexons), 1-based like
+ * hmm.cpp:114-115; *ncalls_out = number of calls found.  nstates 2..7 are accepted (the reference accepts
+ * only 3; the .Call glue keeps that check).  Host pointers. */
+EDB200_API int edb200_hmm(int32_t nstates, int32_t nobs, const double *transitions, const double *probabilities,
+               const int32_t *positions, double expected_length, int32_t *path_out, int32_t *calls_out,
+               int32_t call_cap, int32_t *ncalls_out);
+
+/* ---- cohort (batched) API: many samples over one shared bin set -------------------------------- */
+/* Implements, for every sample, `new('ExomeDepth')`'s likelihood step + CallCNVs' per-chromosome Viterbi
+ * with its framing (R/class_definition.R:342-374): dummy first/last observation, positions from bin starts,
+ * likelihood columns permuted normal-first, start.p/end.p shifted by -1 and by the chromosome offset. */
+typedef struct edb200_cohort edb200_cohort;
+
+typedef struct edb200_cohort_spec {
+    int64_t        n_bins;          /* bins, already ordered by (chromosome, midpoint) as CallCNVs orders them */
+    int32_t        n_chains;        /* chromosomes */
+    const int64_t *chain_offsets;   /* int64[n_chains+1], bins of chromosome c are [off[c], off[c+1]) */
+    const int32_t *start;           /* int32[n_bins] bin start coordinates */
+    const int32_t *end;             /* int32[n_bins] bin end coordinates   */
+    int32_t        n_states;        /* 3 (reference), 5 or 7 (extensions)  */
+    const double  *odds;            /* double[n_states] in likelihood-column (copy-number) order, or NULL = reference */
+    double         mixture;         /* prop.tumor; used when odds == NULL  */
+    const double  *transitions;     /* double[S*S] column-major in HMM order, or NULL = CallCNVs matrix from tp */
+    double         transition_probability;   /* CallCNVs default 1e-4 */
+    double         expected_cnv_length;      /* CallCNVs default 50000 */
+    int32_t        skip_table_build;         /* 1: leave the log-transition table empty; the caller fills it with
+                                                edb200_cohort_table_copy (ranks > 0 after an NCCL broadcast)     */
+} edb200_cohort_spec;
+
+/* Builds the framed positions and the log-transition table on the host (host libm, so that log/exp are the
+ * reference's own bits) and uploads them. */
+EDB200_API int  edb200_cohort_create(const edb200_cohort_spec *spec, edb200_cohort **out);
+EDB200_API void edb200_cohort_destroy(edb200_cohort *c);
+
+/* Size in bytes and device address of the shared log-transition table (for an NCCL broadcast from rank 0). */
+EDB200_API int  edb200_cohort_table(edb200_cohort *c, void **device_ptr, size_t *bytes);
+/* Device-to-device copy of the table: direction 0 = table -> buf, 1 = buf -> table; enqueued on cuda_stream. */
+EDB200_API int  edb200_cohort_table_copy(edb200_cohort *c, void *device_buf, int direction, void *cuda_stream);
+
+typedef struct edb200_batch {
+    int32_t        n_samples;
+    const int32_t *observed;        /* int32[n_samples][obs_stride]  test counts                           */
+    int64_t        obs_stride;      /* >= n_bins                                                           */
+    const int32_t *reference;       /* int32[n_bins] shared aggregate (ref_stride 0) or [n_samples][ref_stride] */
+    int64_t        ref_stride;
+    const double  *phi;             /* double[n_samples]  over-dispersion per sample                       */
+    const double  *expected;        /* double[n_samples]  expected proportion per sample                   */
+    double        *ll;              /* out double[n_samples][n_states][ll_stride] (likelihood-column order); may be NULL in host mode */
+    int64_t        ll_stride;       /* >= n_bins                                                           */
+    int8_t        *path;            /* out int8[n_samples][path_stride], HMM states (0 normal), may be NULL */
+    int64_t        path_stride;
+    int32_t       *calls;           /* out int32[n_samples][call_cap][4]  (start.p, end.p, type, nexons)   */
+    int32_t       *ncalls;          /* out int32[n_samples]                                                */
+    int32_t        call_cap;
+} edb200_batch;
+
+/* mode: 0 = auto, 1 = force in-register evaluation, 2 = force shared-memory lattice */
+#define EDB200_EMISSION_AUTO   0
+#define EDB200_EMISSION_DIRECT 1
+#define EDB200_EMISSION_TABLE  2
+
+/* All pointers in `b` are DEVICE pointers on the selected GPU; work is enqueued on `cuda_stream`
+ * (a cudaStream_t, 0 = default stream) and NOT synchronised.  ll must be non-NULL (the Viterbi reads it).
+ * what: bit 0 emission, bit 1 Viterbi. */
+EDB200_API int edb200_cohort_run_device(edb200_cohort *c, const edb200_batch *b, int what, int emission_mode, void *cuda_stream);
+
+/* Same, HOST pointers: copies in, runs, copies the non-NULL outputs back, synchronises. */
+EDB200_API int edb200_cohort_run_host(edb200_cohort *c, const edb200_batch *b, int emission_mode);
+
+/* sticky status word of device-side warnings since the last call with reset != 0 (EDB200_WARN_*) */
+EDB200_API int edb200_status(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXOMEDEPTH_B200_H */

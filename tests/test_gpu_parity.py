@@ -1,0 +1,151 @@
+"""Parity of the CUDA path (through the C ABI / its Python mirror) against the oracle and the committed
+reference outputs.  Tolerances: FP64 log-likelihoods within 1e-10 relative (absolute floor 1e-12 for the
+exact-zero rows); Viterbi path and call table bit-exact given identical emissions."""
+import numpy as np
+import pytest
+
+from conftest import hmm_cases
+from oracle import framing
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-10, 1e-12
+
+
+@pytest.fixture(scope="module")
+def edb():
+    import exomedepth_b200 as e
+    e.init()
+    info = e.device_info()
+    assert info["cc"][0] >= 10, info
+    return e
+
+
+def assert_ll_close(got, want, rtol=RTOL, atol=ATOL):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape
+    assert np.array_equal(np.isnan(got), np.isnan(want)), "NaN pattern differs from the reference"
+    ok = ~np.isnan(want)
+    err = np.abs(got[ok] - want[ok])
+    lim = rtol * np.abs(want[ok]) + atol
+    worst = np.argmax(err - lim)
+    assert np.all(err <= lim), f"max violation: got {got[ok][worst]!r} want {want[ok][worst]!r}"
+    return float(np.max(err / np.maximum(np.abs(want[ok]), 1e-300), initial=0.0))
+
+
+# ------------------------------------------------------------------------------------------------ KATs
+def test_kat1_viterbi_doc_example(edb, kat):
+    k = kat["kat1"]
+    res = edb.viterbi_hmm(np.array(k["T"]), np.array(k["loglik"], float), k["positions"], k["L"])
+    assert res["Viterbi_path"].tolist() == k["path"]
+    assert res["calls"].tolist() == k["calls"]
+    res = edb.viterbi_hmm(np.eye(3), np.array(k["loglik"], float), k["positions"], k["L"])
+    assert res["Viterbi_path"].tolist() == [0] * 10 and res["calls"].shape == (0, 4)
+
+
+def test_hmm_rejects_other_state_counts_like_the_reference(edb, capsys):
+    assert edb.C_hmm(5, 4, np.full((5, 5), .2), np.zeros((4, 5)), np.arange(4), 1.0) is None   # hmm.cpp:37-40
+    assert "must assume 3 states" in capsys.readouterr().err
+
+
+def test_kat3_loglike(edb, kat):
+    for tot, obs, mix, *vals in kat["kat3"]:
+        got = edb.get_loglike_matrix([kat["kat3_phi"]], [kat["kat3_expected"]], [tot], [obs], mix)[0]
+        assert_ll_close(got, vals)
+        if tot == 0:
+            assert got.tolist() == [0.0, 0.0, 0.0]
+
+
+# ------------------------------------------------------------------------------------------------ committed reference outputs
+def test_emission_per_bin_vectors_vs_reference(edb, refvec):
+    args = [refvec[k] for k in ("em_phi", "em_expected", "em_total", "em_observed")]
+    worst = assert_ll_close(edb.get_loglike_matrix(*args, 1.0), refvec["em_ll_mix1"])
+    assert_ll_close(edb.get_loglike_matrix(*args, 0.4), refvec["em_ll_mix04"])
+    zero = (refvec["em_total"] == 0) & ~np.isnan(refvec["em_ll_mix1"][:, 1])
+    got = edb.get_loglike_matrix(*args, 1.0)
+    assert np.all(got[zero] == 0.0)
+    print("worst relative deviation", worst)
+
+
+def test_hmm_vs_reference_bit_exact(edb, refvec):
+    for T, ll, pos, L, path, calls in hmm_cases(refvec):
+        p, c = edb.C_hmm(3, ll.shape[0], T, ll, pos, L)
+        assert np.array_equal(p, path)
+        assert np.array_equal(c, calls)
+
+
+def test_kat4_exomecount_end_to_end(edb, refvec, exomecount, kat):
+    ec = exomecount
+    test = ec["Exome4"].astype(float)
+    reference = (ec["Exome1"] + ec["Exome2"] + ec["Exome3"]).astype(float)
+    n = test.size
+    x = edb.ExomeDepth(test, reference, kat["kat3_phi"], kat["kat3_expected"])
+    assert_ll_close(x.likelihood, refvec["kat4_ll"])
+    np.testing.assert_allclose(x.likelihood.sum(0), kat["kat4"]["colsums"], rtol=1e-12)
+    x = edb.CallCNVs(x, ["chr1"] * n, ec["start"], ec["end"], [f"b{i}" for i in range(n)])
+    keys = ("start_p", "end_p", "nexons", "start", "end", "BF", "reads_expected", "reads_observed", "reads_ratio")
+    got = np.array([[c[k] for k in keys] for c in x.CNV_calls], float)
+    want = refvec["kat4_calls"][:, [0, 1, 3, 4, 5, 6, 7, 8, 9]]
+    assert np.array_equal(got, want)
+    types = [1 if c["type"] == "deletion" else 2 for c in x.CNV_calls]
+    assert types == refvec["kat4_calls"][:, 2].astype(int).tolist()
+    assert abs(x.cor_test_reference - refvec["kat4_cor"][0]) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ oracle, seeded inputs
+@pytest.mark.parametrize("S", [3, 5, 7])
+@pytest.mark.parametrize("mode", ["direct", "table"])
+def test_cohort_vs_oracle(edb, port, S, mode):
+    from exomedepth_b200 import _lib, synth
+    d = synth.cohort(7, n_bins=9000)
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=S)
+    res = co.run_host(d["observed"], d["reference"], d["phi"], d["expected"], call_cap=256,
+                      mode=_lib.EMISSION_DIRECT if mode == "direct" else _lib.EMISSION_TABLE)
+    odds = port.state_odds(S)
+    T = port.callcnvs_transitions(S, 1e-4)
+    cols = framing.hmm_column_order(S)
+    for s in range(d["observed"].shape[0]):
+        want = port.emission(d["phi"][s], d["expected"][s], d["observed"][s] + d["reference"], d["observed"][s], odds)
+        # the lattice path rounds a2+r and a1+a2+n once instead of following the reference's two-step sums:
+        # that moves cells with observed > 0 by up to a few 1e-12 absolute, still within 1e-10 relative
+        assert_ll_close(res["ll"][s].T, want)
+        # identical emissions -> bit-exact path and calls
+        n_calls, k = 0, 0
+        for c in range(len(d["offsets"]) - 1):
+            b0, b1 = d["offsets"][c], d["offsets"][c + 1]
+            loc, pos = framing.frame_chromosome(res["ll"][s][:, b0:b1].T, d["start"][b0:b1].astype(float),
+                                                d["end"][b0:b1].astype(float), 50000.0)
+            path, calls = port.c_hmm(T, loc, pos, 50000.0)
+            assert np.array_equal(res["path"][s, b0:b1], path[1:-1])
+            for (sp, ep, typ, nex) in calls:
+                assert res["calls"][s, k].tolist() == [sp - 1 + b0, ep - 1 + b0, typ, nex]
+                k += 1
+        assert res["ncalls"][s] == k
+    assert cols[0] == (1 if S == 3 else 2)
+
+
+def test_table_and_direct_paths_agree(edb):
+    from exomedepth_b200 import _lib, synth
+    d = synth.cohort(5, n_bins=20000)
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=5)
+    a = co.run_host(d["observed"], d["reference"], d["phi"], d["expected"], want_path=False, mode=_lib.EMISSION_DIRECT)["ll"]
+    b = co.run_host(d["observed"], d["reference"], d["phi"], d["expected"], want_path=False, mode=_lib.EMISSION_TABLE)["ll"]
+    zero_obs = np.broadcast_to((d["observed"] == 0)[:, None, :], a.shape)
+    assert np.array_equal(a[zero_obs], b[zero_obs])          # observed == 0: identical arguments, identical bits
+    assert_ll_close(b, a, rtol=2e-11, atol=0)
+    both_zero = np.broadcast_to(((d["observed"] == 0) & (d["reference"] == 0))[:, None, :], a.shape)
+    assert np.all(a[both_zero] == 0.0)
+
+
+def test_pathological_phi_nan_pattern(edb, port):
+    """a1 < 0: NaN cells exactly where the reference has them, others unaffected."""
+    rng = np.random.default_rng(5)
+    n = 4000
+    phi = rng.uniform(0.5, 0.99, n)
+    e = rng.uniform(0.05, 0.5, n)
+    tot = rng.poisson(200, n).astype(np.int32)
+    obs = rng.binomial(tot, e).astype(np.int32)
+    want = port.get_loglike_matrix(phi, e, tot, obs, 1.0)
+    got = edb.get_loglike_matrix(phi, e, tot, obs, 1.0)
+    assert np.isnan(want).sum() > 100
+    assert_ll_close(got, want, rtol=1e-9)
