@@ -68,7 +68,7 @@ def C_hmm(nstates, nobs, transitions, loglikelihood, positions, expected_length,
     ll = np.asfortranarray(np.asarray(loglikelihood, float))
     pos = _i32(positions)
     path = np.empty(nobs, np.int32)
-    cap = max(nobs // 2 + 1, 1)
+    cap = max(nobs, 1)          # every state change can close a call (hmm.cpp:110-121)
     calls = np.empty(4 * cap, np.int32)
     import ctypes as C
     nc = C.c_int32(0)

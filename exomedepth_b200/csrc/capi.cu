@@ -1,6 +1,7 @@
 // capi.cu — the C ABI declared in include/exomedepth_b200.h: context, device workspaces, and the
 // host-/device-pointer entry points that stand in for the reference's two .Call routines
 // (src/ExomeDepth_init.c:14-24) and for the per-sample loop that R drives around them.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -108,7 +109,9 @@ struct edb200_cohort {
     double T[EDB200_MAX_STATES * EDB200_MAX_STATES];
     int perm[EDB200_MAX_STATES];
     std::vector<edb::ChainDesc> chains_h;
-    DevBuf chains, lt, odds_d;
+    int64_t total_tiles = 0;
+    int lt_pitch = 0;
+    DevBuf chains, lt, odds_d, order, tile_base;
     // per-batch scratch
     DevBuf consts, bp, ccalls, cncalls, maxima;
     // host-mode staging
@@ -331,8 +334,9 @@ int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const d
     const int S = nstates;
     const int cap = call_cap > 0 ? call_cap : 1;
 
-    std::vector<double> lt((size_t)nobs * S * S);
-    edb::build_log_transition_rows(S, transitions, positions, nobs, expected_length, lt.data());
+    const int pitch = edb::viterbi_lt_pitch(S);
+    std::vector<double> lt(((size_t)nobs + edb::viterbi_tile()) * pitch, 0.0);
+    edb::build_log_transition_rows(S, transitions, positions, nobs, expected_length, lt.data(), pitch);
     edb::ChainDesc cd{};
     cd.lt_row0 = 0;
     cd.em_off = 0;
@@ -342,11 +346,14 @@ int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const d
     cd.out_first = 0;
     cd.out_last = nobs - 1;
     cd.call_shift = 0;
+    const int n_tiles = edb::viterbi_chain_tiles(cd);
+    const int32_t tile_base0 = 0;
+    const int64_t nobs_p = ((int64_t)nobs + 15) & ~(int64_t)15;     // emission rows padded to whole 128-byte lines
 
     if (int rc = ensure(cs.lt, lt.size() * 8)) return rc;
-    if (int rc = ensure(cs.chains, sizeof cd)) return rc;
-    if (int rc = ensure(cs.ll, (size_t)nobs * S * 8)) return rc;
-    if (int rc = ensure(cs.bp, (size_t)nobs * 4)) return rc;
+    if (int rc = ensure(cs.chains, sizeof cd + 16)) return rc;
+    if (int rc = ensure(cs.ll, (size_t)nobs_p * S * 8)) return rc;
+    if (int rc = ensure(cs.bp, (size_t)(n_tiles + 1) * 3 * edb::viterbi_tile() * 4)) return rc;
     if (int rc = ensure(cs.path, (size_t)nobs)) return rc;
     if (int rc = ensure(cs.ccalls, (size_t)cap * 16)) return rc;
     if (int rc = ensure(cs.cncalls, 4)) return rc;
@@ -354,7 +361,8 @@ int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const d
     if (int rc = ensure(cs.ncalls, 4)) return rc;
     CU(cudaMemcpyAsync(cs.lt.p, lt.data(), lt.size() * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(cs.chains.p, &cd, sizeof cd, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(cs.ll.p, probabilities, (size_t)nobs * S * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync((char*)cs.chains.p + sizeof cd, &tile_base0, 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpy2DAsync(cs.ll.p, nobs_p * 8, probabilities, (size_t)nobs * 8, (size_t)nobs * 8, S, cudaMemcpyHostToDevice, st));
 
     edb::ViterbiArgs a{};
     a.chains = (const edb::ChainDesc*)cs.chains.p;
@@ -363,11 +371,12 @@ int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const d
     a.n_states = S;
     a.ll = (const double*)cs.ll.p;
     a.ll_sample_stride = 0;
-    a.ll_state_stride = nobs;
+    a.ll_state_stride = nobs_p;
     for (int j = 0; j < S; j++) a.perm[j] = j;
+    a.order = nullptr;
     a.lt = (const double*)cs.lt.p;
     a.bp = (uint32_t*)cs.bp.p;
-    a.bp_stride = nobs;
+    a.bp_tile_base = (const int32_t*)((char*)cs.chains.p + sizeof cd);
     a.tail_other = -100.0;
     a.path = (int8_t*)cs.path.p;
     a.path_stride = nobs;
@@ -379,7 +388,7 @@ int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const d
     a.call_cap = cap;
     a.flags = g.d_flags;
     edb::launch_viterbi(a, st);
-    g_launches += 3;
+    g_launches += 2;
     if (int rc = check_kernel("viterbi")) return rc;
 
     std::vector<int8_t> p8(nobs);
@@ -443,7 +452,16 @@ int edb200_cohort_create(const edb200_cohort_spec* sp, edb200_cohort** out)
         rows += cd.nobs;
     }
     c->total_rows = rows;
-    std::vector<double> lt((size_t)rows * S * S);
+    const int pitch = edb::viterbi_lt_pitch(S);
+    c->lt_pitch = pitch;
+    std::vector<double> lt(((size_t)rows + edb::viterbi_tile()) * pitch, 0.0);
+    std::vector<int32_t> tile_base(c->n_chains), order(c->n_chains);
+    for (int ch = 0; ch < c->n_chains; ch++) {
+        tile_base[ch] = (int32_t)c->total_tiles;
+        c->total_tiles += edb::viterbi_chain_tiles(c->chains_h[ch]);
+        order[ch] = ch;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return c->chains_h[x].nobs > c->chains_h[y].nobs; });
     std::vector<int32_t> pos;
     for (int ch = 0; ch < c->n_chains; ch++) {
         const int64_t b0 = sp->chain_offsets[ch], nb = sp->chain_offsets[ch + 1] - b0;
@@ -454,14 +472,16 @@ int edb200_cohort_create(const edb200_cohort_spec* sp, edb200_cohort** out)
         }
         if (!sp->skip_table_build)
             edb::build_log_transition_rows(S, c->T, pos.data(), (int32_t)(nb + 2), c->L,
-                                           lt.data() + (size_t)c->chains_h[ch].lt_row0 * S * S);
+                                           lt.data() + (size_t)c->chains_h[ch].lt_row0 * pitch, pitch);
     }
     int rc = 0;
     if ((rc = ensure(c->lt, lt.size() * 8)) || (rc = ensure(c->chains, c->n_chains * sizeof(edb::ChainDesc))) ||
-        (rc = ensure(c->odds_d, S * 8))) {
+        (rc = ensure(c->odds_d, S * 8)) || (rc = ensure(c->order, c->n_chains * 4)) || (rc = ensure(c->tile_base, c->n_chains * 4))) {
         delete c;
         return rc;
     }
+    CU(cudaMemcpy(c->order.p, order.data(), c->n_chains * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->tile_base.p, tile_base.data(), c->n_chains * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->lt.p, lt.data(), lt.size() * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->chains.p, c->chains_h.data(), c->n_chains * sizeof(edb::ChainDesc), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->odds_d.p, c->odds, S * 8, cudaMemcpyHostToDevice));
@@ -474,7 +494,7 @@ void edb200_cohort_destroy(edb200_cohort* c)
     if (!c) return;
     std::lock_guard<std::mutex> lk(g_mu);
     cudaDeviceSynchronize();
-    DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->maxima,
+    DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->order, &c->tile_base, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->maxima,
                      &c->h_obs, &c->h_ref, &c->h_phi, &c->h_exp, &c->h_ll, &c->h_path, &c->h_calls, &c->h_ncalls};
     for (DevBuf* b : all) release(*b);
     delete c;
@@ -484,14 +504,14 @@ int edb200_cohort_table(edb200_cohort* c, void** device_ptr, size_t* bytes)
 {
     if (!c) return fail(EDB200_ERR_ARG, "null cohort");
     if (device_ptr) *device_ptr = c->lt.p;
-    if (bytes) *bytes = (size_t)c->total_rows * c->S * c->S * 8;
+    if (bytes) *bytes = ((size_t)c->total_rows + edb::viterbi_tile()) * c->lt_pitch * 8;
     return 0;
 }
 
 int edb200_cohort_table_copy(edb200_cohort* c, void* device_buf, int direction, void* cuda_stream)
 {
     if (!c || !device_buf) return fail(EDB200_ERR_ARG, "null argument");
-    const size_t bytes = (size_t)c->total_rows * c->S * c->S * 8;
+    const size_t bytes = ((size_t)c->total_rows + edb::viterbi_tile()) * c->lt_pitch * 8;
     if (direction == 0) CU(cudaMemcpyAsync(device_buf, c->lt.p, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
     else CU(cudaMemcpyAsync(c->lt.p, device_buf, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
     return 0;
@@ -518,8 +538,12 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
     if (what & 2) {
         if (!b->path || !b->calls || !b->ncalls || b->call_cap < 1 || b->path_stride < c->n_bins)
             return fail(EDB200_ERR_ARG, "Viterbi outputs missing in batch");
+        if ((b->ll_stride & 15) || (reinterpret_cast<uintptr_t>(b->ll) & 127))
+            return fail(EDB200_ERR_ARG, "Viterbi needs ll_stride to be a multiple of 16 and ll 128-byte aligned (whole 128-byte lines per row tile)");
         const int ccap = b->call_cap;
-        if (int rc = ensure(c->bp, (size_t)ns * c->total_rows * 4)) return rc;
+        const int G = 32 / S;
+        const int64_t groups = (ns + G - 1) / G;
+        if (int rc = ensure(c->bp, (size_t)groups * (c->total_tiles + 1) * 3 * edb::viterbi_tile() * 4)) return rc;
         if (int rc = ensure(c->ccalls, (size_t)ns * c->n_chains * ccap * 16)) return rc;
         if (int rc = ensure(c->cncalls, (size_t)ns * c->n_chains * 4)) return rc;
         edb::ViterbiArgs a{};
@@ -531,9 +555,10 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
         a.ll_sample_stride = (int64_t)S * b->ll_stride;
         a.ll_state_stride = b->ll_stride;
         for (int j = 0; j < S; j++) a.perm[j] = c->perm[j];
+        a.order = (const int32_t*)c->order.p;
         a.lt = (const double*)c->lt.p;
         a.bp = (uint32_t*)c->bp.p;
-        a.bp_stride = c->total_rows;
+        a.bp_tile_base = (const int32_t*)c->tile_base.p;
         a.tail_other = -100.0;                                 // R/class_definition.R:364
         a.path = b->path;
         a.path_stride = b->path_stride;
@@ -545,7 +570,7 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
         a.call_cap = b->call_cap;
         a.flags = g.d_flags;
         edb::launch_viterbi(a, st);
-        g_launches += 3;
+        g_launches += 2;
         if (int rc = check_kernel("viterbi")) return rc;
     }
     return 0;
@@ -562,9 +587,10 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     const int64_t nb = c->n_bins;
     const bool shared_ref = b->ref_stride == 0;
     const int cap = b->call_cap > 0 ? b->call_cap : 1;
+    const int64_t nbp = (nb + 15) & ~(int64_t)15;          // device rows padded to whole 128-byte lines
     int rc = 0;
     if ((rc = ensure(c->h_obs, (size_t)ns * nb * 4)) || (rc = ensure(c->h_ref, (size_t)(shared_ref ? 1 : ns) * nb * 4)) ||
-        (rc = ensure(c->h_phi, ns * 8)) || (rc = ensure(c->h_exp, ns * 8)) || (rc = ensure(c->h_ll, (size_t)ns * S * nb * 8)) ||
+        (rc = ensure(c->h_phi, ns * 8)) || (rc = ensure(c->h_exp, ns * 8)) || (rc = ensure(c->h_ll, (size_t)ns * S * nbp * 8)) ||
         (rc = ensure(c->h_path, (size_t)ns * nb)) || (rc = ensure(c->h_calls, (size_t)ns * cap * 16)) ||
         (rc = ensure(c->h_ncalls, ns * 4)))
         return rc;
@@ -582,7 +608,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     d.phi = (const double*)c->h_phi.p;
     d.expected = (const double*)c->h_exp.p;
     d.ll = (double*)c->h_ll.p;
-    d.ll_stride = nb;
+    d.ll_stride = nbp;
     d.path = (int8_t*)c->h_path.p;
     d.path_stride = nb;
     d.calls = (int32_t*)c->h_calls.p;
@@ -591,7 +617,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     const bool want_vit = b->path || b->calls || b->ncalls;
     if ((rc = edb200_cohort_run_device(c, &d, want_vit ? 3 : 1, emission_mode, st))) return rc;
 
-    if (b->ll) CU(cudaMemcpy2DAsync(b->ll, b->ll_stride * 8, c->h_ll.p, nb * 8, nb * 8, (size_t)ns * S, cudaMemcpyDeviceToHost, st));
+    if (b->ll) CU(cudaMemcpy2DAsync(b->ll, b->ll_stride * 8, c->h_ll.p, nbp * 8, nb * 8, (size_t)ns * S, cudaMemcpyDeviceToHost, st));
     if (b->path) CU(cudaMemcpy2DAsync(b->path, b->path_stride, c->h_path.p, nb, nb, ns, cudaMemcpyDeviceToHost, st));
     if (b->calls && b->call_cap > 0) CU(cudaMemcpyAsync(b->calls, c->h_calls.p, (size_t)ns * cap * 16, cudaMemcpyDeviceToHost, st));
     if (b->ncalls) CU(cudaMemcpyAsync(b->ncalls, c->h_ncalls.p, ns * 4, cudaMemcpyDeviceToHost, st));

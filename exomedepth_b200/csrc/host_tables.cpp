@@ -35,7 +35,7 @@ static inline uint64_t bits_of(double x)
     return u;
 }
 
-static void fill_rows(int S, const double* T, const int32_t* pos, double L, int64_t i0, int64_t i1, double* lt)
+static void fill_rows(int S, const double* T, const int32_t* pos, double L, int64_t i0, int64_t i1, double* lt, int pitch)
 {
     double vals[64], logs[64];
     uint64_t keys[64];
@@ -43,7 +43,8 @@ static void fill_rows(int S, const double* T, const int32_t* pos, double L, int6
         const double dist = double(pos[i]) - double(pos[i - 1]);      // hmm.cpp:62
         const double d = std::exp(-dist / L);                         // hmm.cpp:64
         int nuniq = 0;
-        double* row = lt + i * S * S;
+        double* row = lt + i * pitch;
+        for (int q = S * S; q < pitch; q++) row[q] = 0.0;
         for (int j = 0; j < S; j++) {
             const double t0 = T[j * S];
             for (int k = 0; k < S; k++) {
@@ -64,21 +65,21 @@ static void fill_rows(int S, const double* T, const int32_t* pos, double L, int6
     }
 }
 
-void build_log_transition_rows(int S, const double* T, const int32_t* pos, int32_t nobs, double L, double* lt)
+void build_log_transition_rows(int S, const double* T, const int32_t* pos, int32_t nobs, double L, double* lt, int pitch)
 {
-    for (int q = 0; q < S * S; q++) lt[q] = 0.0;      // row 0 is never read (hmm.cpp:58 starts at i = 1)
+    for (int q = 0; q < pitch; q++) lt[q] = 0.0;      // row 0 is never read (hmm.cpp:58 starts at i = 1)
     if (nobs <= 1) return;
     const int64_t n = nobs;
     unsigned hw = std::thread::hardware_concurrency();
     int nt = (int)(hw ? (hw > 16 ? 16 : hw) : 1);
     if (n < 20000) nt = 1;
-    if (nt == 1) { fill_rows(S, T, pos, L, 1, n, lt); return; }
+    if (nt == 1) { fill_rows(S, T, pos, L, 1, n, lt, pitch); return; }
     std::vector<std::thread> th;
     const int64_t per = (n - 1 + nt - 1) / nt;
     for (int t = 0; t < nt; t++) {
         const int64_t a = 1 + t * per, b = a + per < n ? a + per : n;
         if (a >= b) break;
-        th.emplace_back(fill_rows, S, T, pos, L, a, b, lt);
+        th.emplace_back(fill_rows, S, T, pos, L, a, b, lt, pitch);
     }
     for (auto& x : th) x.join();
 }

@@ -5,8 +5,8 @@
 namespace edb {
 // CallCNVs transition matrix for `tp` (R/class_definition.R:343-347), column-major T[k + S*j] = P(k -> j)
 void callcnvs_transitions(int S, double tp, double* T);
-// lt[(i*S + j)*S + k] = log(t_{k->j} at observation i), i = 1..nobs-1 (src/hmm.cpp:62-79); row 0 zeroed
-void build_log_transition_rows(int S, const double* T, const int32_t* pos, int32_t nobs, double L, double* lt);
+// lt[i*pitch + j*S + k] = log(t_{k->j} at observation i), i = 1..nobs-1 (src/hmm.cpp:62-79); row 0 zeroed
+void build_log_transition_rows(int S, const double* T, const int32_t* pos, int32_t nobs, double L, double* lt, int pitch);
 // CallCNVs framing of one chromosome's positions (R/class_definition.R:368); pos has nb+2 entries. 0 = ok
 int frame_positions(int64_t nb, const int32_t* start, const int32_t* end, double L, int32_t* pos);
 }  // namespace edb

@@ -69,9 +69,10 @@ struct ViterbiArgs {
     int64_t ll_sample_stride;
     int64_t ll_state_stride;
     int perm[kMaxStates];         // HMM state j reads emission column perm[j] (CallCNVs: c(2,1,3))
-    const double* lt;             // [rows][S(j)][S(k)] log-transition table (host libm)
-    uint32_t* bp;                 // [n_samples][bp_stride] packed back-pointers (scratch)
-    int64_t bp_stride;            // >= total rows
+    const int32_t* order;         // launch order of the chains (longest first), or null
+    const double* lt;             // [rows + tile][lt_pitch] log-transition table (host libm), row = S(j) x S(k)
+    uint32_t* bp;                 // back-pointer ballots: [chain tiles][group][tile][3*16] words (scratch)
+    const int32_t* bp_tile_base;  // [n_chains] prefix sum of the chains' tile counts
     double tail_other;            // emission of the non-normal states at the dummy last observation (-100)
     int8_t* path;                 // [n_samples][path_stride]
     int64_t path_stride;
@@ -85,5 +86,14 @@ struct ViterbiArgs {
 };
 
 void launch_viterbi(const ViterbiArgs& a, cudaStream_t st);
+size_t viterbi_smem_bytes(int n_states);
+int viterbi_lt_pitch(int n_states);      // doubles per table row (S*S rounded up to a 16-byte multiple)
+int viterbi_tile();                      // observations per tile; the table carries this many spare rows
+// tiles a chain spans (tiles follow the 128-byte lines of the emission rows)
+inline int viterbi_chain_tiles(const ChainDesc& cd)
+{
+    if (cd.nobs <= 1) return 0;
+    return (int)(((cd.em_off + cd.nobs - 1) >> 4) - ((cd.em_off + 1) >> 4) + 1);
+}
 
 }  // namespace edb

@@ -11,22 +11,106 @@
 //
 // Mapping: one lane per (chain, destination state).  A warp carries G = 32/S chains of the SAME
 // chromosome (so every lane runs the same number of steps) from G consecutive samples; the S lanes of
-// a chain exchange V[i-1][k] with warp shuffles.  Back-pointers leave the warp as three ballots per
-// step (one per bit), i.e. 4 bytes per chain·observation.
+// a chain exchange V[i-1][k] with warp shuffles.  Each warp is its own pipeline:
+//   * the shared log-transition rows stream through a per-warp shared-memory ring with TMA
+//     (cp.async.bulk + mbarrier complete_tx), 16 observations per tile;
+//   * every lane prefetches its own emission row one tile ahead with 128-bit loads (one full 128-byte
+//     line per lane and tile) into registers, so the sequential recurrence never waits on memory;
+//   * back-pointers leave the warp as three ballots per step (one per bit of the 3-bit pointer), i.e.
+//     12 bytes per warp·observation;
+//   * the same warp then walks the ballots backwards (traceback, hmm.cpp:95-100) and produces the
+//     reference's call table during that walk.
 #include "kernels.cuh"
 
 namespace edb {
 
+constexpr int kTile = 16;          // observations per tile (one 128-byte line of an emission row)
+constexpr int kStages = 4;         // TMA ring depth for the transition rows
+constexpr int kWarpsPerCta = 8;
+
+__host__ __device__ constexpr int lt_pitch(int S) { return S * S + ((S * S) & 1); }   // doubles per row, 16-byte multiple
+
+// ---- PTX helpers (mbarrier + 1-D bulk TMA) ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- call-table bookkeeping during the backward walk ------------------------------------------------
+// The reference scans forward (hmm.cpp:104-126): at every state change i it either records start = i (previous
+// state normal) or emits (start+1, i, previous state, run length).  Walking backwards the same calls appear
+// last-first; `start` of a call is the first observation of the enclosing block of non-normal states, known
+// only when the walk reaches it, so the calls of the open block are patched then.
+struct CallWriter {
+    int32_t* slots;     // per-chain scratch, filled from the end
+    int cap, n;         // n = calls written so far
+    int open_from;      // first (lowest slot index) call of the block still waiting for its start
+    int pending_end;    // end observation of the newest call, waiting for its run length
+    int shift;
+    __device__ void emit(int end_i, int type)
+    {
+        n++;
+        const int s = cap - n;
+        if (s >= 0) {
+            slots[4 * s + 1] = end_i + shift;
+            slots[4 * s + 2] = type;
+        }
+        pending_end = end_i;
+    }
+    __device__ void run_starts(int i2)      // the newest call's run is [i2 .. end-1]
+    {
+        const int s = cap - n;
+        if (n > 0 && s >= 0 && pending_end >= 0) slots[4 * s + 3] = pending_end - i2;
+        pending_end = -1;
+    }
+    __device__ void block_starts(int i3)    // start = i3 for every call of the open block
+    {
+        for (int q = open_from; q < n; q++) {
+            const int s = cap - 1 - q;
+            if (s >= 0) slots[4 * s + 0] = i3 + 1 + shift;
+        }
+        open_from = n;
+    }
+};
+
 template <int S>
-__global__ void __launch_bounds__(128)
-viterbi_forward_kernel(ViterbiArgs a, int groups_per_chain)
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+viterbi_chain_kernel(ViterbiArgs a, int groups_per_chain)
 {
     constexpr int G = 32 / S;
-    const int lane = threadIdx.x & 31;
-    const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int chain = warp_global / groups_per_chain;
-    const int grp = warp_global - chain * groups_per_chain;
-    if (chain >= a.n_chains) return;
+    constexpr int LTP = lt_pitch(S);
+    constexpr unsigned kTileBytes = kTile * LTP * 8;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* ring = reinterpret_cast<double*>(smem) + (size_t)warp * kStages * kTile * LTP;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWarpsPerCta * kStages * kTileBytes) + warp * kStages;
+
+    const int warp_global = blockIdx.x * kWarpsPerCta + warp;
+    const int slot = a.order ? a.order[warp_global / groups_per_chain] : warp_global / groups_per_chain;
+    const int grp = warp_global % groups_per_chain;
+    if (warp_global / groups_per_chain >= a.n_chains) return;
+    const int chain = slot;
 
     int g = lane / S;
     const int j = lane - g * S;
@@ -35,92 +119,156 @@ viterbi_forward_kernel(ViterbiArgs a, int groups_per_chain)
     int sample = grp * G + g;
     const bool valid = lane_ok && sample < a.n_samples;
     if (sample >= a.n_samples) sample = a.n_samples - 1;
-
-    const ChainDesc cd = a.chains[chain];
-    const double* __restrict__ em_row = a.ll + sample * a.ll_sample_stride + a.perm[j] * a.ll_state_stride + cd.em_off;
-    const double* __restrict__ lt_row = a.lt + cd.lt_row0 * (S * S) + j * S;
-    uint32_t* __restrict__ bp = a.bp + sample * a.bp_stride + cd.lt_row0;
-    const double ninf = -HUGE_VAL;
-    const double tail = j == 0 ? 0.0 : a.tail_other;
-    const unsigned fieldmask = (1u << S) - 1u;
     const int src0 = g * S;
 
-    double V = j == 0 ? 0.0 : ninf;                         // hmm.cpp:46-52
-    for (int i = 1; i < cd.nobs; i++) {
-        const double em = i <= cd.n_em ? em_row[i] : tail;
-        const double* __restrict__ lti = lt_row + (int64_t)i * (S * S);
-        double best = ninf;
-        int arg = 7;                                        // 7 encodes "from = -1" (hmm.cpp:60)
-#pragma unroll
-        for (int k = 0; k < S; k++) {
-            const double vk = __shfl_sync(0xffffffffu, V, src0 + k);
-            const double cand = __dadd_rn(__dadd_rn(em, vk), lti[k]);   // hmm.cpp:79
-            if (cand > best) { best = cand; arg = k; }                  // hmm.cpp:81
-        }
-        if (em == ninf) arg = 0;                            // hmm.cpp:87
-        V = best;
-        const unsigned b0 = __ballot_sync(0xffffffffu, arg & 1);
-        const unsigned b1 = __ballot_sync(0xffffffffu, arg & 2);
-        const unsigned b2 = __ballot_sync(0xffffffffu, arg & 4);
-        if (j == 0 && valid)
-            bp[i] = ((b0 >> src0) & fieldmask) | (((b1 >> src0) & fieldmask) << 8) | (((b2 >> src0) & fieldmask) << 16);
-    }
-}
-
-// One thread per (sample, chain): traceback (hmm.cpp:95-100), then the reference's forward segment
-// scan (hmm.cpp:104-126) over the states it just wrote.
-__global__ void __launch_bounds__(128)
-viterbi_traceback_kernel(ViterbiArgs a)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n_samples * a.n_chains) return;
-    const int chain = t % a.n_chains, sample = t / a.n_chains;
     const ChainDesc cd = a.chains[chain];
-    uint32_t* __restrict__ bp = a.bp + sample * a.bp_stride + cd.lt_row0;
-    int8_t* __restrict__ path = a.path + sample * a.path_stride + cd.out_off;
+    const int nobs = cd.nobs;
+    // tiles follow the 128-byte lines of the emission rows: tile t covers observations i with
+    // (em_off + i) / 16 == t_first + t
+    const int64_t e_first = cd.em_off + 1;
+    const int64_t t_first = e_first >> 4;
+    const int n_tiles = nobs > 1 ? (int)(((cd.em_off + nobs - 1) >> 4) - t_first + 1) : 0;
+    const double* __restrict__ em_row = a.ll + sample * a.ll_sample_stride + a.perm[j] * a.ll_state_stride;
+    const double* __restrict__ lt_base = a.lt + cd.lt_row0 * LTP;
+    uint32_t* __restrict__ bp = a.bp + ((int64_t)a.bp_tile_base[chain] * groups_per_chain + (int64_t)grp * n_tiles) * (3 * kTile);
 
-    int st = 0;                                             // hmm.cpp:96
-    for (int i = cd.nobs - 1; i >= 1; i--) {
-        const uint32_t w = bp[i];
-        bp[i] = (uint32_t)st;                               // slot reused for the decoded state
-        int prev;
-        if (st < 0) prev = 0;                               // reference reads out of bounds here; pinned to 0 like oracle.c
-        else {
-            prev = ((w >> st) & 1u) | (((w >> (8 + st)) & 1u) << 1) | (((w >> (16 + st)) & 1u) << 2);
-            if (prev == 7) prev = -1;
-        }
-        st = prev;
+    // ---------------------------------------------------------------- TMA ring for the transition rows
+    auto tile_i0 = [&](int t) -> int { return (int)(((t_first + t) << 4) - cd.em_off); };   // first obs of tile (may be < 1)
+    auto issue_lt = [&](int t) {
+        const int st = t % kStages;
+        int i0 = tile_i0(t);
+        int r0 = i0 < 0 ? 0 : i0;                       // rows before the chain's first row are never used
+        const unsigned bytes = (unsigned)(i0 + kTile - r0) * LTP * 8;
+        mbar_expect_tx(&bars[st], bytes);
+        tma_load_1d(ring + ((size_t)st * kTile + (r0 - i0)) * LTP, lt_base + (int64_t)r0 * LTP, bytes, &bars[st]);
+    };
+    if (lane == 0) {
+        for (int s = 0; s < kStages; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (cd.nobs > 0) bp[0] = (uint32_t)st;
+    __syncwarp();
+    if (lane == 0)
+        for (int t = 0; t < kStages && t < n_tiles; t++) issue_lt(t);
 
-    int32_t* __restrict__ calls = a.chain_calls + ((int64_t)t * a.chain_call_cap) * 4;
-    int n = 0, current = 0, start = -1, nex = 0;
-    int prev_state = cd.nobs > 0 ? (int)bp[0] : 0;
-    if (cd.out_first == 0 && cd.nobs > 0) path[0] = (int8_t)prev_state;
-    for (int i = 1; i < cd.nobs; i++) {
-        const int cur = (int)bp[i];
-        if (prev_state != cur) {
-            if (current == 0) start = i;
-            else {
-                if (n < a.chain_call_cap) {
-                    calls[4 * n + 0] = start + 1 + cd.call_shift;
-                    calls[4 * n + 1] = i + cd.call_shift;
-                    calls[4 * n + 2] = current;
-                    calls[4 * n + 3] = nex;
-                }
-                n++;
-                nex = 0;
+    // ---------------------------------------------------------------- emission prefetch (registers)
+    double em_nxt[kTile];
+    auto load_em = [&](int t) {
+        const int i0 = tile_i0(t);
+        // tiles holding only the dummy last observation have no emission row behind them
+        if (i0 <= cd.n_em && valid) {
+            const double2* p = reinterpret_cast<const double2*>(em_row + ((t_first + t) << 4));
+#pragma unroll
+            for (int q = 0; q < kTile / 2; q++) {
+                const double2 v = __ldcs(p + q);          // streamed once: evict-first
+                em_nxt[2 * q] = v.x;
+                em_nxt[2 * q + 1] = v.y;
             }
         }
-        if (cur != 0) nex++;
-        current = cur;
-        prev_state = cur;
-        if (i >= cd.out_first && i <= cd.out_last) path[i] = (int8_t)cur;
+    };
+    if (n_tiles > 0) load_em(0);
+
+    const double ninf = -HUGE_VAL;
+    const double tail = j == 0 ? 0.0 : a.tail_other;
+    double V = j == 0 ? 0.0 : ninf;                         // hmm.cpp:46-52
+
+    for (int t = 0; t < n_tiles; t++) {
+        double em_cur[kTile];
+#pragma unroll
+        for (int q = 0; q < kTile; q++) em_cur[q] = em_nxt[q];
+        if (t + 1 < n_tiles) load_em(t + 1);
+        const int st = t % kStages;
+        mbar_wait(&bars[st], (t / kStages) & 1);
+        const double* __restrict__ ltt = ring + (size_t)st * kTile * LTP + j * S;
+        const int i0 = tile_i0(t);
+        uint32_t cap0 = 0, cap1 = 0;
+#pragma unroll
+        for (int q = 0; q < kTile; q++) {
+            const int i = i0 + q;
+            if (i >= 1 && i < nobs) {                       // warp-uniform
+                const double em = i <= cd.n_em ? em_cur[q] : tail;
+                double best = ninf;
+                int arg = 7;                                // 7 encodes "from = -1" (hmm.cpp:60)
+#pragma unroll
+                for (int k = 0; k < S; k++) {
+                    const double vk = __shfl_sync(0xffffffffu, V, src0 + k);
+                    const double cand = __dadd_rn(__dadd_rn(em, vk), ltt[q * LTP + k]);   // hmm.cpp:79
+                    if (cand > best) { best = cand; arg = k; }                             // hmm.cpp:81
+                }
+                if (em == ninf) arg = 0;                    // hmm.cpp:87
+                V = best;
+                const unsigned b0 = __ballot_sync(0xffffffffu, arg & 1);
+                const unsigned b1 = __ballot_sync(0xffffffffu, arg & 2);
+                const unsigned b2 = __ballot_sync(0xffffffffu, arg & 4);
+                // word 3q+p of the tile is kept by lane (3q+p)%32
+                if (((3 * q + 0) & 31) == lane) { if (3 * q + 0 < 32) cap0 = b0; else cap1 = b0; }
+                if (((3 * q + 1) & 31) == lane) { if (3 * q + 1 < 32) cap0 = b1; else cap1 = b1; }
+                if (((3 * q + 2) & 31) == lane) { if (3 * q + 2 < 32) cap0 = b2; else cap1 = b2; }
+            }
+        }
+        uint32_t* bpt = bp + (int64_t)t * (3 * kTile);
+        bpt[lane] = cap0;
+        if (lane < 3 * kTile - 32) bpt[32 + lane] = cap1;
+        __syncwarp();
+        if (lane == 0 && t + kStages < n_tiles) issue_lt(t + kStages);
     }
-    a.chain_ncalls[t] = n;
+    __syncwarp();
+    __threadfence_block();
+
+    // ---------------------------------------------------------------- traceback + call table (leader lanes)
+    if (j != 0 || !valid) return;
+    const int64_t tcell = (int64_t)sample * a.n_chains + chain;
+    CallWriter cw;
+    cw.slots = a.chain_calls + tcell * a.chain_call_cap * 4;
+    cw.cap = a.chain_call_cap;
+    cw.n = 0;
+    cw.open_from = 0;
+    cw.pending_end = -1;
+    cw.shift = cd.call_shift;
+    int8_t* __restrict__ path = a.path + sample * a.path_stride + cd.out_off;
+
+    int st = 0;                                             // state at observation nobs-1 (hmm.cpp:96)
+    if (nobs - 1 >= cd.out_first && nobs - 1 <= cd.out_last && nobs >= 1) path[nobs - 1] = 0;
+    for (int t = n_tiles - 1; t >= 0; t--) {
+        const uint4* w4 = reinterpret_cast<const uint4*>(bp + (int64_t)t * (3 * kTile));
+        uint32_t w[3 * kTile];
+#pragma unroll
+        for (int q = 0; q < 3 * kTile / 4; q++) {
+            const uint4 v = w4[q];
+            w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+        }
+        const int i0 = tile_i0(t);
+#pragma unroll
+        for (int q = kTile - 1; q >= 0; q--) {
+            const int i = i0 + q;
+            if (i >= 1 && i < nobs) {
+                // state at i-1 from the back-pointer of (i, st)
+                int prev;
+                if (st == 7) prev = 0;                      // reference reads out of bounds here; pinned to 0 like oracle.c
+                else {
+                    const int pos = src0 + st;
+                    prev = ((w[3 * q] >> pos) & 1u) | (((w[3 * q + 1] >> pos) & 1u) << 1) | (((w[3 * q + 2] >> pos) & 1u) << 2);
+                }
+                if (prev != st) {                           // boundary at i (hmm.cpp:110), seen from above
+                    const int cur_state = st == 7 ? -1 : st, prev_state = prev == 7 ? -1 : prev;
+                    (void)cur_state;
+                    cw.run_starts(i);                       // a run that was open above starts at i
+                    const int current = i == 1 ? 0 : prev_state;   // hmm.cpp:108 starts with current = 0
+                    if (current == 0) cw.block_starts(i);   // hmm.cpp:111
+                    else cw.emit(i, current);               // hmm.cpp:112-120
+                }
+                st = prev;
+                if (i - 1 >= cd.out_first && i - 1 <= cd.out_last) path[i - 1] = (int8_t)(st == 7 ? -1 : st);
+            }
+        }
+    }
+    // observation 0 reached: a run still open extends to the start of the chain (counts from obs 1, hmm.cpp:124)
+    cw.run_starts(1);
+    cw.block_starts(-1);                                    // start keeps its initial -1 (hmm.cpp:106)
+    a.chain_ncalls[tcell] = cw.n;
 }
 
-// One thread per sample: concatenate the per-chain call lists in chromosome order.
+// One thread per sample: concatenate the per-chain call lists (stored last-first at the end of each
+// chain's scratch) in chromosome order.
 __global__ void viterbi_compact_kernel(ViterbiArgs a)
 {
     const int sample = blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,13 +278,30 @@ __global__ void viterbi_compact_kernel(ViterbiArgs a)
         const int64_t t = (int64_t)sample * a.n_chains + c;
         const int m = a.chain_ncalls[t];
         const int have = m < a.chain_call_cap ? m : a.chain_call_cap;
-        const int32_t* src = a.chain_calls + t * a.chain_call_cap * 4;
+        const int32_t* src = a.chain_calls + (t * a.chain_call_cap + (a.chain_call_cap - have)) * 4;
+        // when the chain overflowed its scratch, the EARLIEST calls were dropped; keep the count honest
+        n += m - have;
         for (int q = 0; q < have; q++, n++)
             if (n < a.call_cap)
                 for (int f = 0; f < 4; f++) a.calls[((int64_t)sample * a.call_cap + n) * 4 + f] = src[4 * q + f];
-        n += m - have;
     }
     a.ncalls[sample] = n;      // > call_cap signals truncation to the host
+}
+
+size_t viterbi_smem_bytes(int S) { return (size_t)kWarpsPerCta * kStages * (kTile * lt_pitch(S) * 8 + 8); }
+int viterbi_lt_pitch(int S) { return lt_pitch(S); }
+int viterbi_tile() { return kTile; }
+
+template <int S>
+static void launch_chain(const ViterbiArgs& a, int blocks, int groups, cudaStream_t st)
+{
+    const size_t smem = viterbi_smem_bytes(S);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(viterbi_chain_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    viterbi_chain_kernel<S><<<blocks, kWarpsPerCta * 32, smem, st>>>(a, groups);
 }
 
 void launch_viterbi(const ViterbiArgs& a, cudaStream_t st)
@@ -146,18 +311,16 @@ void launch_viterbi(const ViterbiArgs& a, cudaStream_t st)
     const int G = 32 / S;
     const int groups = (a.n_samples + G - 1) / G;
     const int warps = groups * a.n_chains;
-    const int blocks = (warps + 3) / 4;
+    const int blocks = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
     switch (S) {
-        case 2: viterbi_forward_kernel<2><<<blocks, 128, 0, st>>>(a, groups); break;
-        case 3: viterbi_forward_kernel<3><<<blocks, 128, 0, st>>>(a, groups); break;
-        case 4: viterbi_forward_kernel<4><<<blocks, 128, 0, st>>>(a, groups); break;
-        case 5: viterbi_forward_kernel<5><<<blocks, 128, 0, st>>>(a, groups); break;
-        case 6: viterbi_forward_kernel<6><<<blocks, 128, 0, st>>>(a, groups); break;
-        case 7: viterbi_forward_kernel<7><<<blocks, 128, 0, st>>>(a, groups); break;
+        case 2: launch_chain<2>(a, blocks, groups, st); break;
+        case 3: launch_chain<3>(a, blocks, groups, st); break;
+        case 4: launch_chain<4>(a, blocks, groups, st); break;
+        case 5: launch_chain<5>(a, blocks, groups, st); break;
+        case 6: launch_chain<6>(a, blocks, groups, st); break;
+        case 7: launch_chain<7>(a, blocks, groups, st); break;
         default: return;
     }
-    const int nt = a.n_samples * a.n_chains;
-    viterbi_traceback_kernel<<<(nt + 127) / 128, 128, 0, st>>>(a);
     viterbi_compact_kernel<<<(a.n_samples + 127) / 128, 128, 0, st>>>(a);
 }
 

@@ -61,9 +61,9 @@ def test_emission_per_bin_vectors_vs_reference(edb, refvec):
     args = [refvec[k] for k in ("em_phi", "em_expected", "em_total", "em_observed")]
     worst = assert_ll_close(edb.get_loglike_matrix(*args, 1.0), refvec["em_ll_mix1"])
     assert_ll_close(edb.get_loglike_matrix(*args, 0.4), refvec["em_ll_mix04"])
-    zero = (refvec["em_total"] == 0) & ~np.isnan(refvec["em_ll_mix1"][:, 1])
     got = edb.get_loglike_matrix(*args, 1.0)
-    assert np.all(got[zero] == 0.0)
+    zero = (refvec["em_total"] == 0)[:, None] & ~np.isnan(refvec["em_ll_mix1"])
+    assert zero.sum() > 1000 and np.all(got[zero] == 0.0)
     print("worst relative deviation", worst)
 
 

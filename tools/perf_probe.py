@@ -1,7 +1,11 @@
 """Quick device-resident timing of the individual stages at a cohort shape (development aid, not the bench)."""
 import argparse
 import json
+import os
+import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 import torch
