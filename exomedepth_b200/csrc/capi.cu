@@ -353,12 +353,13 @@ int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const d
     if (int rc = ensure(cs.lt, lt.size() * 8)) return rc;
     if (int rc = ensure(cs.chains, sizeof cd + 16)) return rc;
     if (int rc = ensure(cs.ll, (size_t)nobs_p * S * 8)) return rc;
-    if (int rc = ensure(cs.bp, (size_t)(n_tiles + 1) * 3 * edb::viterbi_tile() * 4)) return rc;
+    if (int rc = ensure(cs.bp, (size_t)(n_tiles + 1) * 256)) return rc;
     if (int rc = ensure(cs.path, (size_t)nobs)) return rc;
     if (int rc = ensure(cs.ccalls, (size_t)cap * 16)) return rc;
     if (int rc = ensure(cs.cncalls, 4)) return rc;
     if (int rc = ensure(cs.calls, (size_t)cap * 16)) return rc;
     if (int rc = ensure(cs.ncalls, 4)) return rc;
+    edb::nan_to_neg_inf(lt.data(), lt.size());     // device copy only: a NaN term is "never selected", like -Inf (hmm.cpp:81)
     CU(cudaMemcpyAsync(cs.lt.p, lt.data(), lt.size() * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(cs.chains.p, &cd, sizeof cd, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync((char*)cs.chains.p + sizeof cd, &tile_base0, 4, cudaMemcpyHostToDevice, st));
@@ -482,6 +483,7 @@ int edb200_cohort_create(const edb200_cohort_spec* sp, edb200_cohort** out)
     }
     CU(cudaMemcpy(c->order.p, order.data(), c->n_chains * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->tile_base.p, tile_base.data(), c->n_chains * 4, cudaMemcpyHostToDevice));
+    edb::nan_to_neg_inf(lt.data(), lt.size());     // device copy only: a NaN term is "never selected", like -Inf (hmm.cpp:81)
     CU(cudaMemcpy(c->lt.p, lt.data(), lt.size() * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->chains.p, c->chains_h.data(), c->n_chains * sizeof(edb::ChainDesc), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->odds_d.p, c->odds, S * 8, cudaMemcpyHostToDevice));
@@ -543,7 +545,7 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
         const int ccap = b->call_cap;
         const int G = 32 / S;
         const int64_t groups = (ns + G - 1) / G;
-        if (int rc = ensure(c->bp, (size_t)groups * (c->total_tiles + 1) * 3 * edb::viterbi_tile() * 4)) return rc;
+        if (int rc = ensure(c->bp, (size_t)groups * (c->total_tiles + 1) * 256)) return rc;
         if (int rc = ensure(c->ccalls, (size_t)ns * c->n_chains * ccap * 16)) return rc;
         if (int rc = ensure(c->cncalls, (size_t)ns * c->n_chains * 4)) return rc;
         edb::ViterbiArgs a{};

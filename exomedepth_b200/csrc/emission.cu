@@ -148,17 +148,55 @@ void launch_count_maxima(CountsView c, int n_samples, int64_t n_bins, int32_t* m
 // roundings (CNV_estimate.cpp:49); for k > 0 they can differ from them by one rounding of a sum of
 // magnitude a1+a2+n, i.e. by <= ~4e-12 absolute on cells whose |ll| is then > 1.
 constexpr int kTableThreads = 1024;
+constexpr int kColdCap = 2048;      // out-of-lattice cells parked per work item before they are drained
 
-// out-of-lattice / pathological cells: kept out of line so the gather loop stays within 64 registers
-__device__ __noinline__ double cell_loglik_cold(const StateConst* sc, int total, int observed, unsigned* flags)
+size_t emission_table_smem_bytes(TableDims d)
 {
-    unsigned f = 0;
-    const double v = cell_loglik(*sc, total, observed, f);
-    if (f) *flags |= f;
-    return v;
+    return sizeof(double) * ((size_t)d.K + d.R + d.N) + sizeof(StateConst) + sizeof(int) * (kColdCap + 4);
 }
 
-size_t emission_table_smem_bytes(TableDims d) { return sizeof(double) * ((size_t)d.K + d.R + d.N) + sizeof(StateConst); }
+// Out-of-lattice cells (counts beyond the lattice, inconsistent counts) and whole pathological
+// (sample, state) items are evaluated here, outside the gather loop, so that loop carries no call
+// and stays within the 64 registers a 1024-thread CTA allows.
+__device__ __noinline__ void drain_cold(const StateConst* sc, const CountsView& c, int sample, const int* list, int n,
+                                        double* o, unsigned* flags)
+{
+    unsigned f = 0;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        const int64_t b = list[q];
+        int tot, obs;
+        load_counts(c, sample, b, tot, obs);
+        o[b] = cell_loglik(*sc, tot, obs, f);
+    }
+    if (f) atomicOr(flags, f);
+}
+
+// more out-of-lattice cells than the parking list holds: walk the sample again and evaluate exactly those
+__device__ __noinline__ void rescan_cold(const StateConst* sc, const CountsView& c, int sample, int64_t n_bins,
+                                         TableDims dims, double* o, unsigned* flags)
+{
+    unsigned f = 0;
+    for (int64_t b = threadIdx.x; b < n_bins; b += blockDim.x) {
+        int tot, obs;
+        load_counts(c, sample, b, tot, obs);
+        const int r = tot - obs;
+        if (!((unsigned)obs < (unsigned)dims.K && (unsigned)r < (unsigned)dims.R && (unsigned)tot < (unsigned)dims.N))
+            o[b] = cell_loglik(*sc, tot, obs, f);
+    }
+    if (f) atomicOr(flags, f);
+}
+
+__device__ __noinline__ void whole_item_cold(const StateConst* sc, const CountsView& c, int sample, int64_t n_bins,
+                                             double* o, unsigned* flags)
+{
+    unsigned f = 0;
+    for (int64_t b = threadIdx.x; b < n_bins; b += blockDim.x) {
+        int tot, obs;
+        load_counts(c, sample, b, tot, obs);
+        o[b] = cell_loglik(*sc, tot, obs, f);
+    }
+    if (f) atomicOr(flags, f);
+}
 
 __global__ void __launch_bounds__(kTableThreads, 1)
 emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n_states, int n_items,
@@ -169,53 +207,71 @@ emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n
     double* G1 = reinterpret_cast<double*>(smem_raw + sizeof(StateConst));
     double* G2 = G1 + dims.K;
     double* G3 = G2 + dims.R;
-    unsigned f = 0;
+    int* cold_n = reinterpret_cast<int*>(G3 + dims.N);
+    int* cold = cold_n + 4;
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int sample = item / n_states, s = item - sample * n_states;
         __syncthreads();     // previous item's gathers are done before the lattices are overwritten
         for (int i = threadIdx.x; i < (int)(sizeof(StateConst) / 8); i += blockDim.x)
             reinterpret_cast<double*>(scp)[i] = reinterpret_cast<const double*>(consts + item)[i];
+        if (threadIdx.x == 0) *cold_n = 0;
         __syncthreads();
-        const StateConst& sc = *scp;
-        const bool lattice = sc.ok;
-        if (lattice) {
-            for (int i = threadIdx.x; i < dims.K; i += blockDim.x) G1[i] = gdiff(sc.g1, __dadd_rn(sc.a1, (double)i));
-            for (int i = threadIdx.x; i < dims.R; i += blockDim.x) G2[i] = gdiff(sc.g2, __dadd_rn(sc.a2, (double)i));
+        double* __restrict__ o = out.ptr + sample * out.sample_stride + s * out.state_stride;
+        if (!scp->ok) {      // pathological shape parameters: reference NaN/sign semantics, cell by cell
+            whole_item_cold(scp, c, sample, n_bins, o, flags);
+            continue;
+        }
+        {
+            const GConst g1 = scp->g1, g2 = scp->g2, g12 = scp->g12;
+            const double a1 = scp->a1, a2 = scp->a2;
+            for (int i = threadIdx.x; i < dims.K; i += blockDim.x) G1[i] = gdiff(g1, __dadd_rn(a1, (double)i));
+            for (int i = threadIdx.x; i < dims.R; i += blockDim.x) G2[i] = gdiff(g2, __dadd_rn(a2, (double)i));
             for (int i = threadIdx.x; i < dims.N; i += blockDim.x)
-                G3[i] = gdiff(sc.g12, __dadd_rn(sc.a1, __dadd_rn(sc.a2, (double)i)));
+                G3[i] = gdiff(g12, __dadd_rn(a1, __dadd_rn(a2, (double)i)));
         }
         __syncthreads();
 
         const int32_t* __restrict__ obs_row = c.observed + sample * c.obs_stride;
         const int32_t* __restrict__ oth_row = c.other + sample * c.other_stride;
-        double* __restrict__ o = out.ptr + sample * out.sample_stride + s * out.state_stride;
         const bool vec = ((reinterpret_cast<uintptr_t>(obs_row) | reinterpret_cast<uintptr_t>(oth_row)) & 15) == 0 &&
                          (reinterpret_cast<uintptr_t>(o) & 15) == 0;
         const int64_t n4 = vec ? (n_bins & ~(int64_t)3) : 0;
+        const int is_total = c.other_is_total;
+        const int K = dims.K, R = dims.R, N = dims.N;
 
-        auto cell = [&](int obs, int oth) -> double {
-            const int tot = c.other_is_total ? oth : obs + oth;
+        auto cell = [&](int obs, int oth, int64_t b) -> double {
+            const int tot = is_total ? oth : obs + oth;
             const int r = tot - obs;
-            if (lattice && obs >= 0 && r >= 0 && obs < dims.K && r < dims.R && tot < dims.N)
-                return (G1[obs] + G2[r]) - G3[tot];
-            return cell_loglik_cold(scp, tot, obs, &f);
+            // unsigned compares fold the >= 0 checks in; loads are clamped and unconditional so that the
+            // twelve gathers of a thread's four cells can be in flight together
+            const bool in = (unsigned)obs < (unsigned)K && (unsigned)r < (unsigned)R && (unsigned)tot < (unsigned)N;
+            const double v = (G1[min((unsigned)obs, (unsigned)K - 1)] + G2[min((unsigned)r, (unsigned)R - 1)]) -
+                             G3[min((unsigned)tot, (unsigned)N - 1)];
+            if (!in) {
+                const int q = atomicAdd(cold_n, 1);
+                if (q < kColdCap) cold[q] = (int)b;
+            }
+            return v;
         };
 
         for (int64_t b = (int64_t)threadIdx.x * 4; b < n4; b += (int64_t)blockDim.x * 4) {
             const int4 ko = __ldg(reinterpret_cast<const int4*>(obs_row + b));
             const int4 oo = __ldg(reinterpret_cast<const int4*>(oth_row + b));
             double2 v0, v1;
-            v0.x = cell(ko.x, oo.x);
-            v0.y = cell(ko.y, oo.y);
-            v1.x = cell(ko.z, oo.z);
-            v1.y = cell(ko.w, oo.w);
+            v0.x = cell(ko.x, oo.x, b);
+            v0.y = cell(ko.y, oo.y, b + 1);
+            v1.x = cell(ko.z, oo.z, b + 2);
+            v1.y = cell(ko.w, oo.w, b + 3);
             __stcs(reinterpret_cast<double2*>(o + b), v0);        // streaming stores: ll is write-once
             __stcs(reinterpret_cast<double2*>(o + b + 2), v1);
         }
-        for (int64_t b = n4 + threadIdx.x; b < n_bins; b += blockDim.x) o[b] = cell(obs_row[b], oth_row[b]);
+        for (int64_t b = n4 + threadIdx.x; b < n_bins; b += blockDim.x) o[b] = cell(obs_row[b], oth_row[b], b);
+        __syncthreads();
+        const int n_cold = *cold_n;
+        if (n_cold > kColdCap) rescan_cold(scp, c, sample, n_bins, dims, o, flags);     // lattice far too small for this sample
+        else if (n_cold > 0) drain_cold(scp, c, sample, cold, n_cold, o, flags);
     }
-    if (f) atomicOr(flags, f);
 }
 
 void launch_emission_table(CountsView c, const StateConst* consts, int n_samples, int n_states,

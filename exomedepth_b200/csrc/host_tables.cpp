@@ -84,6 +84,12 @@ void build_log_transition_rows(int S, const double* T, const int32_t* pos, int32
     for (auto& x : th) x.join();
 }
 
+void nan_to_neg_inf(double* v, size_t n)
+{
+    for (size_t i = 0; i < n; i++)
+        if (v[i] != v[i]) v[i] = -HUGE_VAL;
+}
+
 int frame_positions(int64_t nb, const int32_t* start, const int32_t* end, double L, int32_t* pos)
 {
     // R/class_definition.R:368: as.integer(c(start[1] - 2*L, start, end[last] + 2*L))

@@ -1,5 +1,6 @@
 // host_tables.h — host-side shared HMM metadata (see host_tables.cpp).
 #pragma once
+#include <cstddef>
 #include <cstdint>
 
 namespace edb {
@@ -9,4 +10,7 @@ void callcnvs_transitions(int S, double tp, double* T);
 void build_log_transition_rows(int S, const double* T, const int32_t* pos, int32_t nobs, double L, double* lt, int pitch);
 // CallCNVs framing of one chromosome's positions (R/class_definition.R:368); pos has nb+2 entries. 0 = ok
 int frame_positions(int64_t nb, const int32_t* start, const int32_t* end, double L, int32_t* pos);
+// in-place NaN -> -Inf for the device copy of the table: in the recurrence a NaN candidate and a -Inf candidate
+// behave identically (neither can satisfy the strict '>' of src/hmm.cpp:81)
+void nan_to_neg_inf(double* v, size_t n);
 }  // namespace edb

@@ -71,7 +71,7 @@ struct ViterbiArgs {
     int perm[kMaxStates];         // HMM state j reads emission column perm[j] (CallCNVs: c(2,1,3))
     const int32_t* order;         // launch order of the chains (longest first), or null
     const double* lt;             // [rows + tile][lt_pitch] log-transition table (host libm), row = S(j) x S(k)
-    uint32_t* bp;                 // back-pointer ballots: [chain tiles][group][tile][3*16] words (scratch)
+    uint32_t* bp;                 // back-pointers: [chain tiles][group][tile][32 lanes] x 8 bytes (scratch)
     const int32_t* bp_tile_base;  // [n_chains] prefix sum of the chains' tile counts
     double tail_other;            // emission of the non-normal states at the dummy last observation (-100)
     int8_t* path;                 // [n_samples][path_stride]

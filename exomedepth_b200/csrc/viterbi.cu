@@ -16,10 +16,10 @@
 //     (cp.async.bulk + mbarrier complete_tx), 16 observations per tile;
 //   * every lane prefetches its own emission row one tile ahead with 128-bit loads (one full 128-byte
 //     line per lane and tile) into registers, so the sequential recurrence never waits on memory;
-//   * back-pointers leave the warp as three ballots per step (one per bit of the 3-bit pointer), i.e.
-//     12 bytes per warp·observation;
-//   * the same warp then walks the ballots backwards (traceback, hmm.cpp:95-100) and produces the
-//     reference's call table during that walk.
+//   * every lane packs its 16 back-pointers of a tile into 64 bits (4 bits each) and stores them once
+//     per tile: 256 bytes per warp·tile, coalesced;
+//   * the same warp then walks them backwards (traceback, hmm.cpp:95-100) and produces the reference's
+//     call table during that walk.
 #include "kernels.cuh"
 
 namespace edb {
@@ -94,6 +94,57 @@ struct CallWriter {
     }
 };
 
+// ---- one step of the recurrence for this lane's destination state ---------------------------------
+// cand_k = (em + V[k]) + lt[k]  (hmm.cpp:79), winner = FIRST maximum (strict '>' of hmm.cpp:81).
+// The maximum is taken with an order-preserving tournament: a node keeps its left entry unless the right
+// one is strictly greater, which selects exactly the entry the reference's sequential scan selects.
+// NaN never reaches the tournament: NaN transition terms are stored as -Inf in the device copy of the
+// table (a NaN candidate and a -Inf candidate are both "never selected", hmm.cpp:81) and a NaN emission
+// is replaced by -Inf (all candidates lose, from stays -1, V stays -Inf, as in the reference).
+// SPECIAL = false is the hot variant for tiles whose emissions are all finite.
+template <int S, bool SPECIAL>
+__device__ __forceinline__ unsigned viterbi_step(double em, const double* __restrict__ lt_qj, int src0, double& V)
+{
+    const double ninf = -HUGE_VAL;
+    const double em_s = (SPECIAL && em != em) ? ninf : em;
+    double c[S];
+    int id[S];
+#pragma unroll
+    for (int k = 0; k < S; k++) {
+        const double vk = __shfl_sync(0xffffffffu, V, src0 + k);
+        c[k] = __dadd_rn(__dadd_rn(em_s, vk), lt_qj[k]);
+        id[k] = k;
+    }
+#pragma unroll
+    for (int n = S; n > 1; n = (n + 1) / 2) {
+#pragma unroll
+        for (int p = 0; p + 1 < n; p += 2) {
+            const bool right = c[p + 1] > c[p];
+            c[p / 2] = right ? c[p + 1] : c[p];
+            id[p / 2] = right ? id[p + 1] : id[p];
+        }
+        if (n & 1) { c[n / 2] = c[n - 1]; id[n / 2] = id[n - 1]; }
+    }
+    V = c[0];
+    unsigned arg = c[0] > ninf ? (unsigned)id[0] : 7u;      // 7 encodes "from = -1" (hmm.cpp:60)
+    if (SPECIAL && em == ninf) arg = 0u;                    // hmm.cpp:87
+    return arg;
+}
+
+// which sorted warp slot does warp `w` of CTA `c` run?  Slots are ordered longest chain first; lanes 0-3 of a
+// CTA take the front of the list and lanes 4-7 the back, so each SM sub-partition (warp id mod 4) hosts one
+// long and one short chain.
+__device__ __forceinline__ int warp_slot(int c, int w, int n_warps)
+{
+    const int half = (n_warps + 1) / 2;
+    if (w < 4) {
+        const int f = 4 * c + w;
+        return f < half ? f : -1;
+    }
+    const int b = n_warps - 1 - (4 * c + (w - 4));
+    return b >= half ? b : -1;
+}
+
 template <int S>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 viterbi_chain_kernel(ViterbiArgs a, int groups_per_chain)
@@ -106,11 +157,10 @@ viterbi_chain_kernel(ViterbiArgs a, int groups_per_chain)
     double* ring = reinterpret_cast<double*>(smem) + (size_t)warp * kStages * kTile * LTP;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWarpsPerCta * kStages * kTileBytes) + warp * kStages;
 
-    const int warp_global = blockIdx.x * kWarpsPerCta + warp;
-    const int slot = a.order ? a.order[warp_global / groups_per_chain] : warp_global / groups_per_chain;
+    const int warp_global = warp_slot(blockIdx.x, warp, a.n_chains * groups_per_chain);
+    if (warp_global < 0) return;                            // each warp is an independent pipeline: no CTA barrier below
+    const int chain = a.order ? a.order[warp_global / groups_per_chain] : warp_global / groups_per_chain;
     const int grp = warp_global % groups_per_chain;
-    if (warp_global / groups_per_chain >= a.n_chains) return;
-    const int chain = slot;
 
     int g = lane / S;
     const int j = lane - g * S;
@@ -125,19 +175,19 @@ viterbi_chain_kernel(ViterbiArgs a, int groups_per_chain)
     const int nobs = cd.nobs;
     // tiles follow the 128-byte lines of the emission rows: tile t covers observations i with
     // (em_off + i) / 16 == t_first + t
-    const int64_t e_first = cd.em_off + 1;
-    const int64_t t_first = e_first >> 4;
+    const int64_t t_first = (cd.em_off + 1) >> 4;
     const int n_tiles = nobs > 1 ? (int)(((cd.em_off + nobs - 1) >> 4) - t_first + 1) : 0;
     const double* __restrict__ em_row = a.ll + sample * a.ll_sample_stride + a.perm[j] * a.ll_state_stride;
     const double* __restrict__ lt_base = a.lt + cd.lt_row0 * LTP;
-    uint32_t* __restrict__ bp = a.bp + ((int64_t)a.bp_tile_base[chain] * groups_per_chain + (int64_t)grp * n_tiles) * (3 * kTile);
+    uint2* __restrict__ bp = reinterpret_cast<uint2*>(a.bp) +
+                             ((int64_t)a.bp_tile_base[chain] * groups_per_chain + (int64_t)grp * n_tiles) * 32;
 
     // ---------------------------------------------------------------- TMA ring for the transition rows
     auto tile_i0 = [&](int t) -> int { return (int)(((t_first + t) << 4) - cd.em_off); };   // first obs of tile (may be < 1)
     auto issue_lt = [&](int t) {
         const int st = t % kStages;
-        int i0 = tile_i0(t);
-        int r0 = i0 < 0 ? 0 : i0;                       // rows before the chain's first row are never used
+        const int i0 = tile_i0(t);
+        const int r0 = i0 < 0 ? 0 : i0;                 // rows before the chain's first row are never used
         const unsigned bytes = (unsigned)(i0 + kTile - r0) * LTP * 8;
         mbar_expect_tx(&bars[st], bytes);
         tma_load_1d(ring + ((size_t)st * kTile + (r0 - i0)) * LTP, lt_base + (int64_t)r0 * LTP, bytes, &bars[st]);
@@ -152,10 +202,11 @@ viterbi_chain_kernel(ViterbiArgs a, int groups_per_chain)
 
     // ---------------------------------------------------------------- emission prefetch (registers)
     double em_nxt[kTile];
+#pragma unroll
+    for (int q = 0; q < kTile; q++) em_nxt[q] = 0.0;
     auto load_em = [&](int t) {
-        const int i0 = tile_i0(t);
         // tiles holding only the dummy last observation have no emission row behind them
-        if (i0 <= cd.n_em && valid) {
+        if (tile_i0(t) <= cd.n_em) {
             const double2* p = reinterpret_cast<const double2*>(em_row + ((t_first + t) << 4));
 #pragma unroll
             for (int q = 0; q < kTile / 2; q++) {
@@ -167,47 +218,46 @@ viterbi_chain_kernel(ViterbiArgs a, int groups_per_chain)
     };
     if (n_tiles > 0) load_em(0);
 
-    const double ninf = -HUGE_VAL;
     const double tail = j == 0 ? 0.0 : a.tail_other;
-    double V = j == 0 ? 0.0 : ninf;                         // hmm.cpp:46-52
+    double V = j == 0 ? 0.0 : -HUGE_VAL;                    // hmm.cpp:46-52
 
     for (int t = 0; t < n_tiles; t++) {
         double em_cur[kTile];
+        bool special = false;
 #pragma unroll
-        for (int q = 0; q < kTile; q++) em_cur[q] = em_nxt[q];
+        for (int q = 0; q < kTile; q++) {
+            em_cur[q] = em_nxt[q];
+            special |= !(em_cur[q] > -HUGE_VAL);           // NaN or -Inf somewhere in the tile
+        }
         if (t + 1 < n_tiles) load_em(t + 1);
         const int st = t % kStages;
         mbar_wait(&bars[st], (t / kStages) & 1);
         const double* __restrict__ ltt = ring + (size_t)st * kTile * LTP + j * S;
         const int i0 = tile_i0(t);
-        uint32_t cap0 = 0, cap1 = 0;
+        unsigned lo = 0, hi = 0;                            // 16 back-pointers of this lane, 4 bits each
+        const bool whole = i0 >= 1 && i0 + kTile - 1 <= cd.n_em;   // tile entirely inside the real observations
+        if (whole && !__any_sync(0xffffffffu, special)) {
 #pragma unroll
-        for (int q = 0; q < kTile; q++) {
-            const int i = i0 + q;
-            if (i >= 1 && i < nobs) {                       // warp-uniform
-                const double em = i <= cd.n_em ? em_cur[q] : tail;
-                double best = ninf;
-                int arg = 7;                                // 7 encodes "from = -1" (hmm.cpp:60)
+            for (int q = 0; q < kTile; q++) {
+                const unsigned arg = viterbi_step<S, false>(em_cur[q], ltt + q * LTP, src0, V);
+                if (q < 8) lo |= arg << (4 * q);
+                else hi |= arg << (4 * (q - 8));
+            }
+        } else {
+#pragma unroll 1
+            for (int q = 0; q < kTile; q++) {
+                const int i = i0 + q;
+                if (i >= 1 && i < nobs) {                   // warp-uniform
+                    double em = tail;
 #pragma unroll
-                for (int k = 0; k < S; k++) {
-                    const double vk = __shfl_sync(0xffffffffu, V, src0 + k);
-                    const double cand = __dadd_rn(__dadd_rn(em, vk), ltt[q * LTP + k]);   // hmm.cpp:79
-                    if (cand > best) { best = cand; arg = k; }                             // hmm.cpp:81
+                    for (int r = 0; r < kTile; r++) em = (r == q && i <= cd.n_em) ? em_cur[r] : em;
+                    const unsigned arg = viterbi_step<S, true>(em, ltt + q * LTP, src0, V);
+                    if (q < 8) lo |= arg << (4 * q);
+                    else hi |= arg << (4 * (q - 8));
                 }
-                if (em == ninf) arg = 0;                    // hmm.cpp:87
-                V = best;
-                const unsigned b0 = __ballot_sync(0xffffffffu, arg & 1);
-                const unsigned b1 = __ballot_sync(0xffffffffu, arg & 2);
-                const unsigned b2 = __ballot_sync(0xffffffffu, arg & 4);
-                // word 3q+p of the tile is kept by lane (3q+p)%32
-                if (((3 * q + 0) & 31) == lane) { if (3 * q + 0 < 32) cap0 = b0; else cap1 = b0; }
-                if (((3 * q + 1) & 31) == lane) { if (3 * q + 1 < 32) cap0 = b1; else cap1 = b1; }
-                if (((3 * q + 2) & 31) == lane) { if (3 * q + 2 < 32) cap0 = b2; else cap1 = b2; }
             }
         }
-        uint32_t* bpt = bp + (int64_t)t * (3 * kTile);
-        bpt[lane] = cap0;
-        if (lane < 3 * kTile - 32) bpt[32 + lane] = cap1;
+        bp[(int64_t)t * 32 + lane] = make_uint2(lo, hi);
         __syncwarp();
         if (lane == 0 && t + kStages < n_tiles) issue_lt(t + kStages);
     }
@@ -224,45 +274,88 @@ viterbi_chain_kernel(ViterbiArgs a, int groups_per_chain)
     cw.open_from = 0;
     cw.pending_end = -1;
     cw.shift = cd.call_shift;
+    // path index of observation i is out_off + i, and out_off == em_off in both framings, so a tile's 16
+    // observations are one aligned 16-byte group of the path row
     int8_t* __restrict__ path = a.path + sample * a.path_stride + cd.out_off;
+    const bool vec_path = (((reinterpret_cast<uintptr_t>(a.path) | (uintptr_t)a.path_stride) & 15) == 0) && cd.out_off == cd.em_off;
 
-    int st = 0;                                             // state at observation nobs-1 (hmm.cpp:96)
-    if (nobs - 1 >= cd.out_first && nobs - 1 <= cd.out_last && nobs >= 1) path[nobs - 1] = 0;
+    // a state change between observation i-1 (state `below`) and i (hmm.cpp:110), met while walking down
+    auto boundary = [&](int i, int below) {
+        const int prev_state = below == 7 ? -1 : below;
+        cw.run_starts(i);                                   // a run that was open above starts at i
+        const int current = i == 1 ? 0 : prev_state;        // hmm.cpp:108 starts with current = 0
+        if (current == 0) cw.block_starts(i);               // hmm.cpp:111
+        else cw.emit(i, current);                           // hmm.cpp:112-120
+    };
+
+    unsigned st = 0;                                        // state at observation nobs-1 (hmm.cpp:96)
+    uint2 wn[S];
+    auto load_bp = [&](int t) {
+#pragma unroll
+        for (int s = 0; s < S; s++) wn[s] = bp[(int64_t)t * 32 + src0 + s];
+    };
+    if (n_tiles > 0) load_bp(n_tiles - 1);
     for (int t = n_tiles - 1; t >= 0; t--) {
-        const uint4* w4 = reinterpret_cast<const uint4*>(bp + (int64_t)t * (3 * kTile));
-        uint32_t w[3 * kTile];
+        uint2 w[S];
 #pragma unroll
-        for (int q = 0; q < 3 * kTile / 4; q++) {
-            const uint4 v = w4[q];
-            w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-        }
+        for (int s = 0; s < S; s++) w[s] = wn[s];
+        if (t > 0) load_bp(t - 1);
         const int i0 = tile_i0(t);
+        const bool whole = i0 >= 1 && i0 + kTile - 1 <= cd.out_last && i0 + kTile - 1 < nobs && i0 >= cd.out_first;
+        if (whole) {
+            unsigned pw[4] = {0, 0, 0, 0};                  // states at observations i0 .. i0+15, one byte each
+            unsigned bmask = 0;
+            const unsigned st_top = st;
 #pragma unroll
-        for (int q = kTile - 1; q >= 0; q--) {
-            const int i = i0 + q;
-            if (i >= 1 && i < nobs) {
-                // state at i-1 from the back-pointer of (i, st)
-                int prev;
-                if (st == 7) prev = 0;                      // reference reads out of bounds here; pinned to 0 like oracle.c
-                else {
-                    const int pos = src0 + st;
-                    prev = ((w[3 * q] >> pos) & 1u) | (((w[3 * q + 1] >> pos) & 1u) << 1) | (((w[3 * q + 2] >> pos) & 1u) << 2);
-                }
-                if (prev != st) {                           // boundary at i (hmm.cpp:110), seen from above
-                    const int cur_state = st == 7 ? -1 : st, prev_state = prev == 7 ? -1 : prev;
-                    (void)cur_state;
-                    cw.run_starts(i);                       // a run that was open above starts at i
-                    const int current = i == 1 ? 0 : prev_state;   // hmm.cpp:108 starts with current = 0
-                    if (current == 0) cw.block_starts(i);   // hmm.cpp:111
-                    else cw.emit(i, current);               // hmm.cpp:112-120
-                }
+            for (int q = kTile - 1; q >= 0; q--) {
+                pw[q >> 2] |= st << (8 * (q & 3));
+                unsigned word = q < 8 ? w[0].x : w[0].y;
+#pragma unroll
+                for (int s = 1; s < S; s++) word = st == (unsigned)s ? (q < 8 ? w[s].x : w[s].y) : word;
+                word = st == 7u ? 0u : word;                // reference reads out of bounds here; pinned to 0 like oracle.c
+                const unsigned prev = (word >> (4 * (q & 7))) & 7u;
+                bmask |= (prev != st ? 1u : 0u) << q;
                 st = prev;
-                if (i - 1 >= cd.out_first && i - 1 <= cd.out_last) path[i - 1] = (int8_t)(st == 7 ? -1 : st);
+            }
+            if (bmask) {                                    // rare: replay the tile's state changes top-down
+                unsigned above = st_top;
+                (void)above;
+                for (int q = kTile - 1; q >= 0; q--) {
+                    if ((bmask >> q) & 1u) {
+                        const unsigned below = q > 0 ? (pw[(q - 1) >> 2] >> (8 * ((q - 1) & 3))) & 0xffu : st;
+                        boundary(i0 + q, (int)below);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++) {                   // byte 7 -> 0xFF (-1)
+                const unsigned m = (pw[r] + 0x01010101u) & 0x08080808u;
+                pw[r] |= m * 31u;
+            }
+            if (vec_path) *reinterpret_cast<uint4*>(path + i0) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+            else {
+#pragma unroll
+                for (int q = 0; q < kTile; q++) path[i0 + q] = (int8_t)(pw[q >> 2] >> (8 * (q & 3)));
+            }
+        } else {
+#pragma unroll 1
+            for (int q = kTile - 1; q >= 0; q--) {
+                const int i = i0 + q;
+                if (i >= 1 && i < nobs) {
+                    if (i >= cd.out_first && i <= cd.out_last) path[i] = (int8_t)(st == 7u ? -1 : (int)st);
+                    unsigned word = 0;
+#pragma unroll
+                    for (int s = 0; s < S; s++) word = st == (unsigned)s ? (q < 8 ? w[s].x : w[s].y) : word;
+                    const unsigned prev = st == 7u ? 0u : (word >> (4 * (q & 7))) & 7u;
+                    if (prev != st) boundary(i, (int)prev);
+                    st = prev;
+                }
             }
         }
     }
-    // observation 0 reached: a run still open extends to the start of the chain (counts from obs 1, hmm.cpp:124)
-    cw.run_starts(1);
+    // observation 0 reached
+    if (nobs >= 1 && cd.out_first == 0) path[0] = (int8_t)(st == 7u ? -1 : (int)st);
+    cw.run_starts(1);                                       // a run still open extends to the chain start (hmm.cpp:124 counts from obs 1)
     cw.block_starts(-1);                                    // start keeps its initial -1 (hmm.cpp:106)
     a.chain_ncalls[tcell] = cw.n;
 }
@@ -311,7 +404,7 @@ void launch_viterbi(const ViterbiArgs& a, cudaStream_t st)
     const int G = 32 / S;
     const int groups = (a.n_samples + G - 1) / G;
     const int warps = groups * a.n_chains;
-    const int blocks = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int blocks = ((warps + 1) / 2 + 3) / 4;          // see warp_slot(): 4 front + 4 back slots per CTA
     switch (S) {
         case 2: launch_chain<2>(a, blocks, groups, st); break;
         case 3: launch_chain<3>(a, blocks, groups, st); break;
