@@ -113,3 +113,26 @@ def device_info():
 
 def launch_count(reset=False):
     return int(load().edb200_launch_count(1 if reset else 0))
+
+
+class PinnedPool:
+    """numpy views over page-locked host buffers from edb200_host_alloc (freed when the pool is closed)."""
+
+    def __init__(self):
+        self._ptrs = []
+
+    def empty(self, shape, dtype):
+        import numpy as np
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        p = load().edb200_host_alloc(max(n, 1))
+        if not p:
+            raise EDB200Error(f"edb200_host_alloc({n}): {last_error()}")
+        self._ptrs.append(p)
+        buf = (C.c_char * max(n, 1)).from_address(p)
+        return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        for p in self._ptrs:
+            load().edb200_host_free(p)
+        self._ptrs = []

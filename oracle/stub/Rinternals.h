@@ -40,6 +40,8 @@ SEXP    allocVector(int type, int n);
 SEXP    allocMatrix(int type, int nrow, int ncol);
 SEXP    SET_VECTOR_ELT(SEXP list, int i, SEXP v);
 SEXP    VECTOR_ELT(SEXP list, int i);
+/* transient storage R reclaims when .Call returns; the stand-in reclaims it in edb200_stub_free */
+char   *R_alloc(size_t n, int size);
 void    Rprintf(const char *fmt, ...);
 void    REprintf(const char *fmt, ...);
 void    Rf_error(const char *fmt, ...);

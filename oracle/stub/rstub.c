@@ -34,8 +34,29 @@ SEXP allocMatrix(int type, int nrow, int ncol)
 SEXP SET_VECTOR_ELT(SEXP list, int i, SEXP v) { ((SEXP *)list->data)[i] = v; return v; }
 SEXP VECTOR_ELT(SEXP list, int i)             { return ((SEXP *)list->data)[i]; }
 
+struct transient { struct transient *next; };
+static struct transient *g_transient = NULL;
+
+char *R_alloc(size_t n, int size)
+{
+    struct transient *t = (struct transient *)malloc(sizeof(*t) + 16 + n * (size_t)size);
+    t->next = g_transient;
+    g_transient = t;
+    return (char *)t + 16;
+}
+
+static void free_transient(void)
+{
+    while (g_transient) {
+        struct transient *t = g_transient;
+        g_transient = t->next;
+        free(t);
+    }
+}
+
 void edb200_stub_free(SEXP x)
 {
+    free_transient();
     if (!x) return;
     if (x->type == VECSXP)
         for (int i = 0; i < x->n; i++) edb200_stub_free(((SEXP *)x->data)[i]);
