@@ -93,8 +93,21 @@ int check_kernel(const char* what)
 
 // scratch used by the single-call (reference-shaped) entry points
 struct CallScratch {
-    DevBuf phi, expected, total, observed, odds, ll, consts, lt, chains, bp, path, ccalls, cncalls, calls, ncalls;
+    DevBuf phi, expected, total, observed, odds, ll, consts, lt, chains, bp, path, ccalls, cncalls, calls, ncalls, sched_begin, sched_items;
 } cs;
+
+// build and upload the sweep schedule (host_tables.cpp: viterbi_schedule)
+int upload_schedule(const std::vector<int32_t>& nobs, int groups, int n_ctas, DevBuf& d_begin, DevBuf& d_items, cudaStream_t st)
+{
+    std::vector<int32_t> begin, items;
+    edb::viterbi_schedule(nobs.data(), (int)nobs.size(), groups, n_ctas, edb::kViterbiWarpsPerCta, begin, items);
+    if (int rc = ensure(d_begin, begin.size() * 4)) return rc;
+    if (int rc = ensure(d_items, items.size() * 4 + 8)) return rc;
+    CU(cudaMemcpyAsync(d_begin.p, begin.data(), begin.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_items.p, items.data(), items.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));          // the vectors go out of scope
+    return 0;
+}
 
 }  // namespace
 
@@ -111,7 +124,9 @@ struct edb200_cohort {
     std::vector<edb::ChainDesc> chains_h;
     int64_t total_tiles = 0;
     int lt_pitch = 0;
-    DevBuf chains, lt, odds_d, order, tile_base;
+    DevBuf chains, lt, odds_d, tile_base;
+    DevBuf sched_begin, sched_items;     // sweep schedule for `sched_groups` groups of samples
+    int sched_groups = 0;
     // per-batch scratch
     DevBuf consts, bp, ccalls, cncalls, maxima;
     // host-mode staging
@@ -161,7 +176,7 @@ void edb200_shutdown(void)
     if (!g.ready) return;
     cudaDeviceSynchronize();
     DevBuf* all[] = {&cs.phi, &cs.expected, &cs.total, &cs.observed, &cs.odds, &cs.ll, &cs.consts, &cs.lt,
-                     &cs.chains, &cs.bp, &cs.path, &cs.ccalls, &cs.cncalls, &cs.calls, &cs.ncalls};
+                     &cs.chains, &cs.bp, &cs.path, &cs.ccalls, &cs.cncalls, &cs.calls, &cs.ncalls, &cs.sched_begin, &cs.sched_items};
     for (DevBuf* b : all) release(*b);
     if (g.d_flags) cudaFree(g.d_flags);
     g.d_flags = nullptr;
@@ -353,7 +368,7 @@ int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const d
     if (int rc = ensure(cs.lt, lt.size() * 8)) return rc;
     if (int rc = ensure(cs.chains, sizeof cd + 16)) return rc;
     if (int rc = ensure(cs.ll, (size_t)nobs_p * S * 8)) return rc;
-    if (int rc = ensure(cs.bp, (size_t)(n_tiles + 1) * 256)) return rc;
+    if (int rc = ensure(cs.bp, (size_t)(n_tiles + 1) * edb::viterbi_record_bytes())) return rc;
     if (int rc = ensure(cs.path, (size_t)nobs)) return rc;
     if (int rc = ensure(cs.ccalls, (size_t)cap * 16)) return rc;
     if (int rc = ensure(cs.cncalls, 4)) return rc;
@@ -374,7 +389,11 @@ int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const d
     a.ll_sample_stride = 0;
     a.ll_state_stride = nobs_p;
     for (int j = 0; j < S; j++) a.perm[j] = j;
-    a.order = nullptr;
+    if (int rc = upload_schedule(std::vector<int32_t>{nobs}, 1, 1, cs.sched_begin, cs.sched_items, st)) return rc;
+    a.groups = 1;
+    a.n_slots = edb::kViterbiWarpsPerCta;
+    a.sched_begin = (const int32_t*)cs.sched_begin.p;
+    a.sched_items = (const int32_t*)cs.sched_items.p;
     a.lt = (const double*)cs.lt.p;
     a.bp = (uint32_t*)cs.bp.p;
     a.bp_tile_base = (const int32_t*)((char*)cs.chains.p + sizeof cd);
@@ -388,8 +407,7 @@ int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const d
     a.ncalls = (int32_t*)cs.ncalls.p;
     a.call_cap = cap;
     a.flags = g.d_flags;
-    edb::launch_viterbi(a, st);
-    g_launches += 2;
+    g_launches += edb::launch_viterbi(a, n_tiles, st);
     if (int rc = check_kernel("viterbi")) return rc;
 
     std::vector<int8_t> p8(nobs);
@@ -456,13 +474,11 @@ int edb200_cohort_create(const edb200_cohort_spec* sp, edb200_cohort** out)
     const int pitch = edb::viterbi_lt_pitch(S);
     c->lt_pitch = pitch;
     std::vector<double> lt(((size_t)rows + edb::viterbi_tile()) * pitch, 0.0);
-    std::vector<int32_t> tile_base(c->n_chains), order(c->n_chains);
+    std::vector<int32_t> tile_base(c->n_chains);
     for (int ch = 0; ch < c->n_chains; ch++) {
         tile_base[ch] = (int32_t)c->total_tiles;
         c->total_tiles += edb::viterbi_chain_tiles(c->chains_h[ch]);
-        order[ch] = ch;
     }
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return c->chains_h[x].nobs > c->chains_h[y].nobs; });
     std::vector<int32_t> pos;
     for (int ch = 0; ch < c->n_chains; ch++) {
         const int64_t b0 = sp->chain_offsets[ch], nb = sp->chain_offsets[ch + 1] - b0;
@@ -477,11 +493,10 @@ int edb200_cohort_create(const edb200_cohort_spec* sp, edb200_cohort** out)
     }
     int rc = 0;
     if ((rc = ensure(c->lt, lt.size() * 8)) || (rc = ensure(c->chains, c->n_chains * sizeof(edb::ChainDesc))) ||
-        (rc = ensure(c->odds_d, S * 8)) || (rc = ensure(c->order, c->n_chains * 4)) || (rc = ensure(c->tile_base, c->n_chains * 4))) {
+        (rc = ensure(c->odds_d, S * 8)) || (rc = ensure(c->tile_base, c->n_chains * 4))) {
         delete c;
         return rc;
     }
-    CU(cudaMemcpy(c->order.p, order.data(), c->n_chains * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->tile_base.p, tile_base.data(), c->n_chains * 4, cudaMemcpyHostToDevice));
     edb::nan_to_neg_inf(lt.data(), lt.size());     // device copy only: a NaN term is "never selected", like -Inf (hmm.cpp:81)
     CU(cudaMemcpy(c->lt.p, lt.data(), lt.size() * 8, cudaMemcpyHostToDevice));
@@ -496,7 +511,7 @@ void edb200_cohort_destroy(edb200_cohort* c)
     if (!c) return;
     std::lock_guard<std::mutex> lk(g_mu);
     cudaDeviceSynchronize();
-    DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->order, &c->tile_base, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->maxima,
+    DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->tile_base, &c->sched_begin, &c->sched_items, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->maxima,
                      &c->h_obs, &c->h_ref, &c->h_phi, &c->h_exp, &c->h_ll, &c->h_path, &c->h_calls, &c->h_ncalls};
     for (DevBuf* b : all) release(*b);
     delete c;
@@ -545,7 +560,7 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
         const int ccap = b->call_cap;
         const int G = 32 / S;
         const int64_t groups = (ns + G - 1) / G;
-        if (int rc = ensure(c->bp, (size_t)groups * (c->total_tiles + 1) * 256)) return rc;
+        if (int rc = ensure(c->bp, (size_t)groups * (c->total_tiles + 1) * edb::viterbi_record_bytes())) return rc;
         if (int rc = ensure(c->ccalls, (size_t)ns * c->n_chains * ccap * 16)) return rc;
         if (int rc = ensure(c->cncalls, (size_t)ns * c->n_chains * 4)) return rc;
         edb::ViterbiArgs a{};
@@ -557,7 +572,16 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
         a.ll_sample_stride = (int64_t)S * b->ll_stride;
         a.ll_state_stride = b->ll_stride;
         for (int j = 0; j < S; j++) a.perm[j] = c->perm[j];
-        a.order = (const int32_t*)c->order.p;
+        if (c->sched_groups != (int)groups) {
+            std::vector<int32_t> nobs(c->n_chains);
+            for (int ch = 0; ch < c->n_chains; ch++) nobs[ch] = c->chains_h[ch].nobs;
+            if (int rc = upload_schedule(nobs, (int)groups, g.n_sms, c->sched_begin, c->sched_items, st)) return rc;
+            c->sched_groups = (int)groups;
+        }
+        a.groups = (int)groups;
+        a.n_slots = g.n_sms * edb::kViterbiWarpsPerCta;
+        a.sched_begin = (const int32_t*)c->sched_begin.p;
+        a.sched_items = (const int32_t*)c->sched_items.p;
         a.lt = (const double*)c->lt.p;
         a.bp = (uint32_t*)c->bp.p;
         a.bp_tile_base = (const int32_t*)c->tile_base.p;
@@ -571,8 +595,7 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
         a.ncalls = b->ncalls;
         a.call_cap = b->call_cap;
         a.flags = g.d_flags;
-        edb::launch_viterbi(a, st);
-        g_launches += 2;
+        g_launches += edb::launch_viterbi(a, groups * c->total_tiles, st);
         if (int rc = check_kernel("viterbi")) return rc;
     }
     return 0;

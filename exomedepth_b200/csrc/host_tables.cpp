@@ -9,7 +9,11 @@
 // not monotone, SURVEY.md §8c "NaN edge"); both are kept.  Compiled without FMA contraction.
 #include "host_tables.h"
 
+#include <algorithm>
 #include <cmath>
+#include <functional>
+#include <queue>
+#include <utility>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -44,7 +48,8 @@ static void fill_rows(int S, const double* T, const int32_t* pos, double L, int6
         const double d = std::exp(-dist / L);                         // hmm.cpp:64
         int nuniq = 0;
         double* row = lt + i * pitch;
-        for (int q = S * S; q < pitch; q++) row[q] = 0.0;
+        const int js = pitch / S;                        // doubles per destination state (S padded to an even count)
+        for (int q = 0; q < pitch; q++) row[q] = 0.0;
         for (int j = 0; j < S; j++) {
             const double t0 = T[j * S];
             for (int k = 0; k < S; k++) {
@@ -58,7 +63,7 @@ static void fill_rows(int S, const double* T, const int32_t* pos, double L, int6
                     logs[u] = std::log(t);              // hmm.cpp:79
                     nuniq++;
                 }
-                row[j * S + k] = logs[u];
+                row[j * js + k] = logs[u];
             }
         }
         (void)vals;
@@ -88,6 +93,46 @@ void nan_to_neg_inf(double* v, size_t n)
 {
     for (size_t i = 0; i < n; i++)
         if (v[i] != v[i]) v[i] = -HUGE_VAL;
+}
+
+void viterbi_schedule(const int32_t* chain_nobs, int n_chains, int groups, int n_ctas, int warps_per_cta,
+                      std::vector<int32_t>& begin, std::vector<int32_t>& items)
+{
+    const int n_slots = n_ctas * warps_per_cta, n_parts = n_ctas * 4;
+    std::vector<int> order(n_chains);
+    for (int c = 0; c < n_chains; c++) order[c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return chain_nobs[x] > chain_nobs[y]; });
+    std::vector<int64_t> part_load(n_parts, 0), slot_load(n_slots, 0);
+    std::vector<std::vector<int32_t>> per_slot(n_slots);
+    // min-heap of (load, partition)
+    using Key = std::pair<int64_t, int>;
+    std::priority_queue<Key, std::vector<Key>, std::greater<Key>> heap;
+    for (int p = 0; p < n_parts; p++) heap.push({0, p});
+    for (int oc = 0; oc < n_chains; oc++) {
+        const int c = order[oc];
+        for (int g = 0; g < groups; g++) {
+            Key k = heap.top();
+            heap.pop();
+            const int p = k.second, cta = p / 4, sub = p % 4;
+            int best = -1;
+            for (int w = sub; w < warps_per_cta; w += 4) {
+                const int s = cta * warps_per_cta + w;
+                if (best < 0 || slot_load[s] < slot_load[best]) best = s;
+            }
+            per_slot[best].push_back(c);
+            per_slot[best].push_back(g);
+            slot_load[best] += chain_nobs[c];
+            part_load[p] += chain_nobs[c];
+            heap.push({part_load[p], p});
+        }
+    }
+    begin.assign(n_slots + 1, 0);
+    items.clear();
+    for (int s = 0; s < n_slots; s++) {
+        begin[s] = (int32_t)(items.size() / 2);
+        items.insert(items.end(), per_slot[s].begin(), per_slot[s].end());
+    }
+    begin[n_slots] = (int32_t)(items.size() / 2);
 }
 
 int frame_positions(int64_t nb, const int32_t* start, const int32_t* end, double L, int32_t* pos)

@@ -2,15 +2,22 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <vector>
 
 namespace edb {
 // CallCNVs transition matrix for `tp` (R/class_definition.R:343-347), column-major T[k + S*j] = P(k -> j)
 void callcnvs_transitions(int S, double tp, double* T);
-// lt[i*pitch + j*S + k] = log(t_{k->j} at observation i), i = 1..nobs-1 (src/hmm.cpp:62-79); row 0 zeroed
+// lt[i*pitch + j*(pitch/S) + k] = log(t_{k->j} at observation i), i = 1..nobs-1 (src/hmm.cpp:62-79); row 0 and padding zeroed
 void build_log_transition_rows(int S, const double* T, const int32_t* pos, int32_t nobs, double L, double* lt, int pitch);
 // CallCNVs framing of one chromosome's positions (R/class_definition.R:368); pos has nb+2 entries. 0 = ok
 int frame_positions(int64_t nb, const int32_t* start, const int32_t* end, double L, int32_t* pos);
 // in-place NaN -> -Inf for the device copy of the table: in the recurrence a NaN candidate and a -Inf candidate
 // behave identically (neither can satisfy the strict '>' of src/hmm.cpp:81)
 void nan_to_neg_inf(double* v, size_t n);
+// Placement of the Viterbi sweep's work items (chromosome x group of samples) on the sweep warps: items are
+// dealt longest first to the least loaded SM sub-partition (warp slots w and w + 4 of a CTA share one), then to
+// its less loaded warp.  The sweep is a latency-bound dependent chain, so the longest chromosomes end up alone
+// on their sub-partition.  begin has n_slots + 1 entries, items 2 per work item (chain, group).
+void viterbi_schedule(const int32_t* chain_nobs, int n_chains, int groups, int n_ctas, int warps_per_cta,
+                      std::vector<int32_t>& begin, std::vector<int32_t>& items);
 }  // namespace edb

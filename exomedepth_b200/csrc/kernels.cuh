@@ -60,18 +60,23 @@ struct ChainDesc {
     int32_t pad;
 };
 
+constexpr int kViterbiWarpsPerCta = 8;   // two sweep warps per SM sub-partition
+
 struct ViterbiArgs {
-    const ChainDesc* chains;      // [n_chains], longest first is best
+    const ChainDesc* chains;      // [n_chains]
     int n_chains;
     int n_samples;
     int n_states;
+    int groups;                   // ceil(n_samples / (32 / n_states)): warps per chromosome
+    int n_slots;                  // sweep warps in the grid (a multiple of kViterbiWarpsPerCta)
+    const int32_t* sched_begin;   // [n_slots + 1] first work item of each sweep warp (viterbi_schedule)
+    const int32_t* sched_items;   // [2 * n_items] (chain, group) pairs
     const double* ll;             // emission matrix, see LLView strides
     int64_t ll_sample_stride;
     int64_t ll_state_stride;
     int perm[kMaxStates];         // HMM state j reads emission column perm[j] (CallCNVs: c(2,1,3))
-    const int32_t* order;         // launch order of the chains (longest first), or null
-    const double* lt;             // [rows + tile][lt_pitch] log-transition table (host libm), row = S(j) x S(k)
-    uint32_t* bp;                 // back-pointers: [chain tiles][group][tile][32 lanes] x 8 bytes (scratch)
+    const double* lt;             // [rows + tile][lt_pitch] log-transition table (host libm), row = S(j) x pitch/S (k, padded)
+    uint32_t* bp;                 // scratch records, viterbi_record_bytes() each: [chain tiles][group][tile]
     const int32_t* bp_tile_base;  // [n_chains] prefix sum of the chains' tile counts
     double tail_other;            // emission of the non-normal states at the dummy last observation (-100)
     int8_t* path;                 // [n_samples][path_stride]
@@ -85,10 +90,12 @@ struct ViterbiArgs {
     unsigned* flags;
 };
 
-void launch_viterbi(const ViterbiArgs& a, cudaStream_t st);
+// enqueues sweep, tilemap, trace, expand and compact; n_records = groups * (tiles of all chains); returns the number of launches
+int launch_viterbi(const ViterbiArgs& a, int64_t n_records, cudaStream_t st);
 size_t viterbi_smem_bytes(int n_states);
-int viterbi_lt_pitch(int n_states);      // doubles per table row (S*S rounded up to a 16-byte multiple)
+int viterbi_lt_pitch(int n_states);      // doubles per table row: S destination rows of S doubles padded to an even count
 int viterbi_tile();                      // observations per tile; the table carries this many spare rows
+size_t viterbi_record_bytes();           // scratch bytes per (warp, tile): packed back-pointers + tile maps
 // tiles a chain spans (tiles follow the 128-byte lines of the emission rows)
 inline int viterbi_chain_tiles(const ChainDesc& cd)
 {

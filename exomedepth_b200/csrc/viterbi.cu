@@ -9,38 +9,52 @@
 // the same emissions and the same log-transition table (built on the host with the host libm, see
 // host_tables.cpp) — no FMA contraction, no (max,+) re-association.
 //
-// Mapping: one lane per (chain, destination state).  A warp carries G = 32/S chains of the SAME
-// chromosome (so every lane runs the same number of steps) from G consecutive samples; the S lanes of
-// a chain exchange V[i-1][k] with warp shuffles.  Each warp is its own pipeline:
-//   * the shared log-transition rows stream through a per-warp shared-memory ring with TMA
-//     (cp.async.bulk + mbarrier complete_tx), 16 observations per tile;
-//   * every lane prefetches its own emission row one tile ahead with 128-bit loads (one full 128-byte
-//     line per lane and tile) into registers, so the sequential recurrence never waits on memory;
-//   * every lane packs its 16 back-pointers of a tile into 64 bits (4 bits each) and stores them once
-//     per tile: 256 bytes per warp·tile, coalesced;
-//   * the same warp then walks them backwards (traceback, hmm.cpp:95-100) and produces the reference's
-//     call table during that walk.
+// Five kernels (DESIGN.md "Viterbi"):
+//   sweep    one lane per (chain, destination state); a warp carries G = 32/S chains of the SAME
+//            chromosome from G consecutive samples.  The sweep is a chain of dependent FP64 operations
+//            (~20,000 steps for chromosome 1), so this kernel is about the latency of ONE step
+//            (tools/ubench/step.cu measures the variants on a B200): the S lanes of a chain exchange
+//            V[i-1][k] with SHFL.IDX issued back to back; the maximum is a tournament on VALUES only and
+//            the winning source state (the back-pointer) is derived afterwards as "first candidate equal
+//            to the maximum", in the shadow of the next step's exchange; the shared log-transition rows
+//            stream through a per-warp shared-memory ring with TMA (cp.async.bulk + mbarrier
+//            complete_tx), 16 observations per tile; every lane prefetches its own emission row one
+//            tile ahead with 128-bit loads; back-pointers leave as 64 bits per lane and tile.
+//            Work items (chromosome x group of samples) are placed on the SM sub-partitions by the
+//            host (longest-processing-time first), so the longest chains run alone on theirs.
+//            This file is compiled with ptxas -O1: at the default level ptxas interleaves the exchange
+//            with its consumers and the step takes 228 instead of 126 cycles.
+//   tilemap  composes the 16 back-pointer steps of every tile into a map end state -> state before
+//            the tile (fully parallel);
+//   trace    one thread per chain walks one map per tile instead of one back-pointer per observation
+//            (hmm.cpp:95-100);
+//   expand   one warp per chain fills in the per-observation states, the path bytes and the
+//            reference's call table, 32 tiles at a time;
+//   compact  concatenates the per-chromosome call tables per sample.
 #include "kernels.cuh"
 
 namespace edb {
 
 constexpr int kTile = 16;          // observations per tile (one 128-byte line of an emission row)
 constexpr int kStages = 4;         // TMA ring depth for the transition rows
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpsPerCta = kViterbiWarpsPerCta;
 
-__host__ __device__ constexpr int lt_pitch(int S) { return S * S + ((S * S) & 1); }   // doubles per row, 16-byte multiple
+// transition row of destination state j: S doubles padded to an even count, so that rows are 16-byte aligned
+__host__ __device__ constexpr int lt_jstride(int S) { return S + (S & 1); }
+__host__ __device__ constexpr int lt_pitch(int S) { return S * lt_jstride(S); }          // doubles per observation
 
 // ---- PTX helpers (mbarrier + 1-D bulk TMA) ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+// (all shared-memory operands are 32-bit shared-window addresses computed once per warp)
+__device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -48,264 +62,392 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar)
+__device__ __forceinline__ bool try_wait_once(uint32_t bar, unsigned parity)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src_gmem, unsigned bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src_gmem), "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int shfl_idx(int v, int src)
+{
+    int r;
+    asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(r) : "r"(v), "r"(src));
+    return r;
+}
 
-// ---- call-table bookkeeping during the backward walk ------------------------------------------------
-// The reference scans forward (hmm.cpp:104-126): at every state change i it either records start = i (previous
-// state normal) or emits (start+1, i, previous state, run length).  Walking backwards the same calls appear
-// last-first; `start` of a call is the first observation of the enclosing block of non-normal states, known
-// only when the walk reaches it, so the calls of the open block are patched then.
-struct CallWriter {
-    int32_t* slots;     // per-chain scratch, filled from the end
-    int cap, n;         // n = calls written so far
-    int open_from;      // first (lowest slot index) call of the block still waiting for its start
-    int pending_end;    // end observation of the newest call, waiting for its run length
-    int shift;
-    __device__ void emit(int end_i, int type)
-    {
-        n++;
-        const int s = cap - n;
-        if (s >= 0) {
-            slots[4 * s + 1] = end_i + shift;
-            slots[4 * s + 2] = type;
-        }
-        pending_end = end_i;
-    }
-    __device__ void run_starts(int i2)      // the newest call's run is [i2 .. end-1]
-    {
-        const int s = cap - n;
-        if (n > 0 && s >= 0 && pending_end >= 0) slots[4 * s + 3] = pending_end - i2;
-        pending_end = -1;
-    }
-    __device__ void block_starts(int i3)    // start = i3 for every call of the open block
-    {
-        for (int q = open_from; q < n; q++) {
-            const int s = cap - 1 - q;
-            if (s >= 0) slots[4 * s + 0] = i3 + 1 + shift;
-        }
-        open_from = n;
-    }
-};
-
-// ---- one step of the recurrence for this lane's destination state ---------------------------------
+// ---- the recurrence -----------------------------------------------------------------------------------
 // cand_k = (em + V[k]) + lt[k]  (hmm.cpp:79), winner = FIRST maximum (strict '>' of hmm.cpp:81).
-// The maximum is taken with an order-preserving tournament: a node keeps its left entry unless the right
-// one is strictly greater, which selects exactly the entry the reference's sequential scan selects.
+// The maximum is taken with an order-preserving tournament on the values: a node keeps its left entry
+// unless the right one is strictly greater, so the surviving VALUE is the one the reference's sequential
+// scan keeps, and the winning source state is the lowest k whose candidate equals it.
 // NaN never reaches the tournament: NaN transition terms are stored as -Inf in the device copy of the
 // table (a NaN candidate and a -Inf candidate are both "never selected", hmm.cpp:81) and a NaN emission
 // is replaced by -Inf (all candidates lose, from stays -1, V stays -Inf, as in the reference).
-// SPECIAL = false is the hot variant for tiles whose emissions are all finite.
-template <int S, bool SPECIAL>
-__device__ __forceinline__ unsigned viterbi_step(double em, const double* __restrict__ lt_qj, int src0, double& V)
-{
-    const double ninf = -HUGE_VAL;
-    const double em_s = (SPECIAL && em != em) ? ninf : em;
+template <int S>
+struct Cand {
     double c[S];
-    int id[S];
+};
+
+// exchange V between the chain's S lanes, form the candidates and reduce them to the new V
+template <int S, bool SPECIAL>
+__device__ __forceinline__ void sweep_step(double em, uint32_t lt_qj, int src0, double& V, Cand<S>& cd)
+{
+    double lt[S + 1];                                       // this lane's transition row: independent of V, issued first
+#pragma unroll
+    for (int k = 0; k + 1 < S; k += 2) {
+        const double2 x = lds_f64x2(lt_qj + 8u * k);
+        lt[k] = x.x;
+        lt[k + 1] = x.y;
+    }
+    if (S & 1) lt[S - 1] = lds_f64(lt_qj + 8u * (S - 1));
+    int lo[S], hi[S];
+    const int vlo = __double2loint(V), vhi = __double2hiint(V);
 #pragma unroll
     for (int k = 0; k < S; k++) {
-        const double vk = __shfl_sync(0xffffffffu, V, src0 + k);
-        c[k] = __dadd_rn(__dadd_rn(em_s, vk), lt_qj[k]);
-        id[k] = k;
+        lo[k] = shfl_idx(vlo, src0 + k);
+        hi[k] = shfl_idx(vhi, src0 + k);
     }
+    const double em_s = (SPECIAL && em != em) ? -HUGE_VAL : em;
+    double m[S];
 #pragma unroll
-    for (int n = S; n > 1; n = (n + 1) / 2) {
-#pragma unroll
-        for (int p = 0; p + 1 < n; p += 2) {
-            const bool right = c[p + 1] > c[p];
-            c[p / 2] = right ? c[p + 1] : c[p];
-            id[p / 2] = right ? id[p + 1] : id[p];
-        }
-        if (n & 1) { c[n / 2] = c[n - 1]; id[n / 2] = id[n - 1]; }
+    for (int k = 0; k < S; k++) {
+        cd.c[k] = __dadd_rn(__dadd_rn(em_s, __hiloint2double(hi[k], lo[k])), lt[k]);
+        m[k] = cd.c[k];
     }
-    V = c[0];
-    unsigned arg = c[0] > ninf ? (unsigned)id[0] : 7u;      // 7 encodes "from = -1" (hmm.cpp:60)
-    if (SPECIAL && em == ninf) arg = 0u;                    // hmm.cpp:87
+    // pairs first; the last three survivors are settled by independent compares
+    int n = S;
+#pragma unroll
+    for (; n > 3; n = (n + 1) / 2) {
+#pragma unroll
+        for (int p = 0; p + 1 < n; p += 2) m[p / 2] = m[p + 1] > m[p] ? m[p + 1] : m[p];
+        if (n & 1) m[n / 2] = m[n - 1];
+    }
+    if (n == 3) {
+        const bool p = m[1] > m[0], q2 = m[2] > m[0], r2 = m[2] > m[1];
+        const double t = p ? m[1] : m[0];
+        V = (q2 && r2) ? m[2] : t;
+    } else if (n == 2) {
+        V = m[1] > m[0] ? m[1] : m[0];
+    } else {
+        V = m[0];
+    }
+}
+
+// back-pointer of the step whose candidates are in `cd` and whose maximum is V
+template <int S, bool SPECIAL>
+__device__ __forceinline__ unsigned sweep_arg(const Cand<S>& cd, double V, double em)
+{
+    unsigned arg = S - 1;
+#pragma unroll
+    for (int k = S - 2; k >= 0; k--) arg = cd.c[k] == V ? (unsigned)k : arg;
+    if (!(V > -HUGE_VAL)) arg = 7u;                         // 7 encodes "from = -1" (hmm.cpp:60)
+    if (SPECIAL && em == -HUGE_VAL) arg = 0u;               // hmm.cpp:87
     return arg;
 }
 
-// which sorted warp slot does warp `w` of CTA `c` run?  Slots are ordered longest chain first; lanes 0-3 of a
-// CTA take the front of the list and lanes 4-7 the back, so each SM sub-partition (warp id mod 4) hosts one
-// long and one short chain.
-__device__ __forceinline__ int warp_slot(int c, int w, int n_warps)
+// ---- per-tile scratch record ---------------------------------------------------------------------------
+// One record per (work item, tile): 32 lanes x 8 bytes of packed back-pointers (16 observations x 4 bits),
+// then 16 x 4 bytes of tile maps, one per chain of the warp.  A tile map composes the tile's 16 back-pointer
+// steps: nibble e (e = 0..6, or 7 for the reference's "from = -1") holds the state at the observation just
+// BEFORE the tile given state e at the tile's last observation.
+constexpr int kRecU2 = 40;                 // uint2 per record (32 lanes + 64 bytes of maps)
+constexpr int kRecU32 = 2 * kRecU2;
+constexpr int kMapOff = 64;                // uint32 offset of the maps inside a record
+
+__device__ __forceinline__ unsigned bp_nibble(const uint2& w, int q) { return ((q < 8 ? w.x : w.y) >> (4 * (q & 7))) & 0xFu; }
+__device__ __forceinline__ int chain_tiles(const ChainDesc& cd)
 {
-    const int half = (n_warps + 1) / 2;
-    if (w < 4) {
-        const int f = 4 * c + w;
-        return f < half ? f : -1;
-    }
-    const int b = n_warps - 1 - (4 * c + (w - 4));
-    return b >= half ? b : -1;
+    return cd.nobs > 1 ? (int)(((cd.em_off + cd.nobs - 1) >> 4) - ((cd.em_off + 1) >> 4) + 1) : 0;
+}
+__device__ __forceinline__ int64_t record_base(const ViterbiArgs& a, int chain, int grp, int n_tiles)
+{
+    return (int64_t)a.bp_tile_base[chain] * a.groups + (int64_t)grp * n_tiles;
 }
 
+// =========================================================================================== sweep
 template <int S>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-viterbi_chain_kernel(ViterbiArgs a, int groups_per_chain)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 1)
+viterbi_sweep_kernel(ViterbiArgs a)
 {
     constexpr int G = 32 / S;
     constexpr int LTP = lt_pitch(S);
+    constexpr int LTJ = lt_jstride(S);
     constexpr unsigned kTileBytes = kTile * LTP * 8;
+    constexpr unsigned kFull = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* ring = reinterpret_cast<double*>(smem) + (size_t)warp * kStages * kTile * LTP;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWarpsPerCta * kStages * kTileBytes) + warp * kStages;
-
-    const int warp_global = warp_slot(blockIdx.x, warp, a.n_chains * groups_per_chain);
-    if (warp_global < 0) return;                            // each warp is an independent pipeline: no CTA barrier below
-    const int chain = a.order ? a.order[warp_global / groups_per_chain] : warp_global / groups_per_chain;
-    const int grp = warp_global % groups_per_chain;
+    const uint32_t ring = smem_u32(smem) + (uint32_t)warp * kStages * kTileBytes;                                   // [stage][obs][LTP] doubles
+    const uint32_t bars = smem_u32(smem) + (uint32_t)kWarpsPerCta * kStages * kTileBytes + (uint32_t)warp * kStages * 8;   // [stage] mbarriers
 
     int g = lane / S;
     const int j = lane - g * S;
-    const bool lane_ok = g < G;
-    if (!lane_ok) g = G - 1;
-    int sample = grp * G + g;
-    const bool valid = lane_ok && sample < a.n_samples;
-    if (sample >= a.n_samples) sample = a.n_samples - 1;
+    if (g >= G) g = G - 1;                                  // spare lanes shadow lanes of the last chain
     const int src0 = g * S;
+    const double tail = j == 0 ? 0.0 : a.tail_other;
 
-    const ChainDesc cd = a.chains[chain];
-    const int nobs = cd.nobs;
-    // tiles follow the 128-byte lines of the emission rows: tile t covers observations i with
-    // (em_off + i) / 16 == t_first + t
-    const int64_t t_first = (cd.em_off + 1) >> 4;
-    const int n_tiles = nobs > 1 ? (int)(((cd.em_off + nobs - 1) >> 4) - t_first + 1) : 0;
-    const double* __restrict__ em_row = a.ll + sample * a.ll_sample_stride + a.perm[j] * a.ll_state_stride;
-    const double* __restrict__ lt_base = a.lt + cd.lt_row0 * LTP;
-    uint2* __restrict__ bp = reinterpret_cast<uint2*>(a.bp) +
-                             ((int64_t)a.bp_tile_base[chain] * groups_per_chain + (int64_t)grp * n_tiles) * 32;
-
-    // ---------------------------------------------------------------- TMA ring for the transition rows
-    auto tile_i0 = [&](int t) -> int { return (int)(((t_first + t) << 4) - cd.em_off); };   // first obs of tile (may be < 1)
-    auto issue_lt = [&](int t) {
-        const int st = t % kStages;
-        const int i0 = tile_i0(t);
-        const int r0 = i0 < 0 ? 0 : i0;                 // rows before the chain's first row are never used
-        const unsigned bytes = (unsigned)(i0 + kTile - r0) * LTP * 8;
-        mbar_expect_tx(&bars[st], bytes);
-        tma_load_1d(ring + ((size_t)st * kTile + (r0 - i0)) * LTP, lt_base + (int64_t)r0 * LTP, bytes, &bars[st]);
-    };
     if (lane == 0) {
-        for (int s = 0; s < kStages; s++) mbar_init(&bars[s], 1);
+        for (int s = 0; s < kStages; s++) mbar_init(bars + 8u * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    if (lane == 0)
-        for (int t = 0; t < kStages && t < n_tiles; t++) issue_lt(t);
+    unsigned ring_seq = 0;                                  // tiles pushed through this warp's ring so far (stage / parity bookkeeping)
 
-    // ---------------------------------------------------------------- emission prefetch (registers)
-    double em_nxt[kTile];
+    // each warp is an independent pipeline over its own list of work items: no CTA barrier below
+    const int slot = blockIdx.x * kWarpsPerCta + warp;
+    for (int it = a.sched_begin[slot]; it < a.sched_begin[slot + 1]; it++) {
+        const int chain = a.sched_items[2 * it], grp = a.sched_items[2 * it + 1];
+        int sample = grp * G + g;
+        if (sample >= a.n_samples) sample = a.n_samples - 1;    // chains past the batch shadow the last sample
+
+        const ChainDesc cd = a.chains[chain];
+        const int nobs = cd.nobs;
+        // tiles follow the 128-byte lines of the emission rows: tile t covers observations i with
+        // (em_off + i) / 16 == t_first + t
+        const int64_t t_first = (cd.em_off + 1) >> 4;
+        const int n_tiles = chain_tiles(cd);
+        const double* __restrict__ em_row = a.ll + sample * a.ll_sample_stride + a.perm[j] * a.ll_state_stride;
+        const double* __restrict__ lt_base = a.lt + cd.lt_row0 * LTP;
+        uint2* bp = reinterpret_cast<uint2*>(a.bp) + record_base(a, chain, grp, n_tiles) * kRecU2;
+
+        auto tile_i0 = [&](int t) -> int { return (int)(((t_first + t) << 4) - cd.em_off); };   // first obs of tile (may be < 1)
+        auto issue_lt = [&](int t) {
+            const int st = (ring_seq + t) % kStages;
+            const int i0 = tile_i0(t);
+            const int r0 = i0 < 0 ? 0 : i0;             // rows before the chain's first row are never used
+            const unsigned bytes = (unsigned)(i0 + kTile - r0) * LTP * 8;
+            mbar_expect_tx(bars + 8u * st, bytes);
+            tma_load_1d(ring + (uint32_t)(st * kTile + (r0 - i0)) * LTP * 8, lt_base + (int64_t)r0 * LTP, bytes, bars + 8u * st);
+        };
+        if (lane == 0)
+            for (int t = 0; t < kStages && t < n_tiles; t++) issue_lt(t);
+
+        // ------------------------------------------------------------ emission prefetch (registers)
+        double em_nxt[kTile];
 #pragma unroll
-    for (int q = 0; q < kTile; q++) em_nxt[q] = 0.0;
-    auto load_em = [&](int t) {
-        // tiles holding only the dummy last observation have no emission row behind them
-        if (tile_i0(t) <= cd.n_em) {
-            const double2* p = reinterpret_cast<const double2*>(em_row + ((t_first + t) << 4));
+        for (int q = 0; q < kTile; q++) em_nxt[q] = 0.0;
+        auto load_em = [&](int t) {
+            // tiles holding only the dummy last observation have no emission row behind them
+            if (tile_i0(t) <= cd.n_em) {
+                const double2* p = reinterpret_cast<const double2*>(em_row + ((t_first + t) << 4));
 #pragma unroll
-            for (int q = 0; q < kTile / 2; q++) {
-                const double2 v = __ldcs(p + q);          // streamed once: evict-first
-                em_nxt[2 * q] = v.x;
-                em_nxt[2 * q + 1] = v.y;
+                for (int q = 0; q < kTile / 2; q++) {
+                    const double2 v = __ldcs(p + q);      // streamed once: evict-first
+                    em_nxt[2 * q] = v.x;
+                    em_nxt[2 * q + 1] = v.y;
+                }
             }
-        }
-    };
-    if (n_tiles > 0) load_em(0);
-
-    const double tail = j == 0 ? 0.0 : a.tail_other;
-    double V = j == 0 ? 0.0 : -HUGE_VAL;                    // hmm.cpp:46-52
-
-    for (int t = 0; t < n_tiles; t++) {
-        double em_cur[kTile];
-        bool special = false;
+        };
+        // NaN or +-Inf somewhere in the prefetched tile (integer test on the exponent field: off the FP64 pipe)
+        auto nonfinite_nxt = [&]() -> bool {
+            unsigned m = 0;
 #pragma unroll
-        for (int q = 0; q < kTile; q++) {
-            em_cur[q] = em_nxt[q];
-            special |= !(em_cur[q] > -HUGE_VAL);           // NaN or -Inf somewhere in the tile
-        }
-        if (t + 1 < n_tiles) load_em(t + 1);
-        const int st = t % kStages;
-        mbar_wait(&bars[st], (t / kStages) & 1);
-        const double* __restrict__ ltt = ring + (size_t)st * kTile * LTP + j * S;
-        const int i0 = tile_i0(t);
-        unsigned lo = 0, hi = 0;                            // 16 back-pointers of this lane, 4 bits each
-        const bool whole = i0 >= 1 && i0 + kTile - 1 <= cd.n_em;   // tile entirely inside the real observations
-        if (whole && !__any_sync(0xffffffffu, special)) {
+            for (int q = 0; q < kTile; q++) m = max(m, (unsigned)__double2hiint(em_nxt[q]) & 0x7fffffffu);
+            return m >= 0x7ff00000u;
+        };
+        if (n_tiles > 0) load_em(0);
+        bool special_nxt = n_tiles > 0 && nonfinite_nxt();
+        bool lt_ready = false;
+
+        double V = j == 0 ? 0.0 : -HUGE_VAL;                // hmm.cpp:46-52
+
+        for (int t = 0; t < n_tiles; t++) {
+            double em_cur[kTile];
 #pragma unroll
-            for (int q = 0; q < kTile; q++) {
-                const unsigned arg = viterbi_step<S, false>(em_cur[q], ltt + q * LTP, src0, V);
-                if (q < 8) lo |= arg << (4 * q);
-                else hi |= arg << (4 * (q - 8));
-            }
-        } else {
+            for (int q = 0; q < kTile; q++) em_cur[q] = em_nxt[q];
+            const bool special = special_nxt;
+            if (t + 1 < n_tiles) load_em(t + 1);
+            const unsigned seq = ring_seq + t;
+            const int st = seq % kStages;
+            if (!lt_ready) mbar_wait(bars + 8u * st, (seq / kStages) & 1);
+            const uint32_t ltt = ring + (uint32_t)(st * kTile * LTP + j * LTJ) * 8;
+            const int i0 = tile_i0(t);
+            unsigned lo = 0, hi = 0;                        // 16 back-pointers of this lane, 4 bits each
+            const bool whole = i0 >= 1 && i0 + kTile - 1 <= cd.n_em;   // tile entirely inside the real observations
+            if (whole && !__any_sync(kFull, special)) {
+                Cand<S> cnd;
+                double Vq = V;
+#pragma unroll
+                for (int q = 0; q < kTile; q++) {
+                    Cand<S> nxt;
+                    double Vn = Vq;
+                    sweep_step<S, false>(em_cur[q], ltt + q * LTP * 8, src0, Vn, nxt);
+                    if (q > 0) {                            // the previous step's back-pointer, in the shadow of this step's exchange
+                        const unsigned arg = sweep_arg<S, false>(cnd, Vq, 0.0);
+                        if (q - 1 < 8) lo |= arg << (4 * (q - 1));
+                        else hi |= arg << (4 * (q - 9));
+                    }
+                    cnd = nxt;
+                    Vq = Vn;
+                }
+                hi |= sweep_arg<S, false>(cnd, Vq, 0.0) << 28;
+                V = Vq;
+            } else {
 #pragma unroll 1
-            for (int q = 0; q < kTile; q++) {
-                const int i = i0 + q;
-                if (i >= 1 && i < nobs) {                   // warp-uniform
-                    double em = tail;
+                for (int q = 0; q < kTile; q++) {
+                    const int i = i0 + q;
+                    unsigned arg = (unsigned)j;             // observations outside the chain: identity step
+                    if (i >= 1 && i < nobs) {               // warp-uniform
+                        double em = tail;
 #pragma unroll
-                    for (int r = 0; r < kTile; r++) em = (r == q && i <= cd.n_em) ? em_cur[r] : em;
-                    const unsigned arg = viterbi_step<S, true>(em, ltt + q * LTP, src0, V);
+                        for (int r = 0; r < kTile; r++) em = (r == q && i <= cd.n_em) ? em_cur[r] : em;
+                        Cand<S> cnd;
+                        sweep_step<S, true>(em, ltt + q * LTP * 8, src0, V, cnd);
+                        arg = sweep_arg<S, true>(cnd, V, em);
+                    }
                     if (q < 8) lo |= arg << (4 * q);
                     else hi |= arg << (4 * (q - 8));
                 }
             }
+            bp[(int64_t)t * kRecU2 + lane] = make_uint2(lo, hi);
+            __syncwarp();
+            if (lane == 0 && t + kStages < n_tiles) issue_lt(t + kStages);
+            lt_ready = false;
+            if (t + 1 < n_tiles) {
+                special_nxt = nonfinite_nxt();
+                lt_ready = try_wait_once(bars + 8u * ((seq + 1) % kStages), ((seq + 1) / kStages) & 1);
+            }
         }
-        bp[(int64_t)t * 32 + lane] = make_uint2(lo, hi);
+        ring_seq += (unsigned)n_tiles;
         __syncwarp();
-        if (lane == 0 && t + kStages < n_tiles) issue_lt(t + kStages);
     }
-    __syncwarp();
-    __threadfence_block();
+}
 
-    // ---------------------------------------------------------------- traceback + call table (leader lanes)
-    if (j != 0 || !valid) return;
-    const int64_t tcell = (int64_t)sample * a.n_chains + chain;
-    CallWriter cw;
-    cw.slots = a.chain_calls + tcell * a.chain_call_cap * 4;
-    cw.cap = a.chain_call_cap;
-    cw.n = 0;
-    cw.open_from = 0;
-    cw.pending_end = -1;
-    cw.shift = cd.call_shift;
-    // path index of observation i is out_off + i, and out_off == em_off in both framings, so a tile's 16
-    // observations are one aligned 16-byte group of the path row
-    int8_t* __restrict__ path = a.path + sample * a.path_stride + cd.out_off;
+// =========================================================================================== tilemap
+// One thread per (record, chain of the record).  cur holds, for every end state e (nibble e; nibble 7 = the
+// pseudo-state "from = -1"), the state reached walking back from the tile's last observation.  As soon as all
+// tracked nibbles agree (the usual case: every state's best predecessor is "normal" somewhere in the tile) one
+// walk serves all of them.
+template <int S>
+__global__ void __launch_bounds__(256)
+viterbi_tilemap_kernel(ViterbiArgs a, int64_t n_records)
+{
+    constexpr int G = 32 / S;
+    constexpr unsigned kTracked = (S >= 7 ? 0x0FFFFFFFu : ((1u << (4 * S)) - 1u)) | 0xF0000000u;
+    constexpr unsigned kOnes = kTracked & 0x11111111u;
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= n_records * G) return;
+    const int64_t r = idx / G;
+    const int gg = (int)(idx - r * G);
+    const uint2* __restrict__ rec = reinterpret_cast<const uint2*>(a.bp) + r * kRecU2;
+    uint2 w[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) w[s] = rec[gg * S + s];
+    unsigned cur = 0x76543210u & kTracked;
+    int q = kTile - 1;
+    for (; q >= 0 && cur != (cur & 0xFu) * kOnes; q--) {
+        unsigned m = 0;                                     // step map: nibble s = predecessor of state s; nibble 7 = 0 (pinned like oracle.c)
+#pragma unroll
+        for (int s = 0; s < S; s++) m |= bp_nibble(w[s], q) << (4 * s);
+        unsigned nc = 0;
+#pragma unroll
+        for (int e = 0; e < 8; e++)
+            if ((kTracked >> (4 * e)) & 1u) nc |= ((m >> (4 * ((cur >> (4 * e)) & 0xFu))) & 0xFu) << (4 * e);
+        cur = nc;
+    }
+    if (q >= 0) {                                           // all end states share one walk from here
+        unsigned st1 = cur & 0xFu;
+        for (; q >= 0; q--) {
+            uint2 ws = w[0];
+#pragma unroll
+            for (int s = 1; s < S; s++) ws = st1 == (unsigned)s ? w[s] : ws;
+            st1 = st1 == 7u ? 0u : bp_nibble(ws, q);
+        }
+        cur = st1 * kOnes;
+    }
+    reinterpret_cast<unsigned*>(a.bp)[r * kRecU32 + kMapOff + gg] = cur;
+}
+
+// =========================================================================================== trace
+// One thread per chain: e = state at the tile's last observation; the chain ends in state 0 (hmm.cpp:96).
+// The map words are replaced by e as they are consumed.
+__global__ void __launch_bounds__(128)
+viterbi_trace_kernel(ViterbiArgs a, int G)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.n_samples * a.n_chains) return;
+    const int smp = idx % a.n_samples, chain = idx / a.n_samples;       // neighbouring threads: same chromosome, same length
+    const int grp = smp / G, gg = smp - grp * G;
+    const ChainDesc cd = a.chains[chain];
+    const int n_tiles = chain_tiles(cd);
+    unsigned* __restrict__ tmap = reinterpret_cast<unsigned*>(a.bp) + record_base(a, chain, grp, n_tiles) * kRecU32 + kMapOff + gg;
+    unsigned e = 0;
+    int t = n_tiles - 1;
+    while (t >= 0) {
+        unsigned w[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) w[r] = t - r >= 0 ? tmap[(int64_t)(t - r) * kRecU32] : 0u;
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            if (t - r >= 0) {
+                tmap[(int64_t)(t - r) * kRecU32] = e;
+                e = (w[r] >> (4 * e)) & 0xFu;
+            }
+        t -= 8;
+    }
+}
+
+// =========================================================================================== expand
+// One warp per (sample, chromosome), one lane per tile, 32 tiles at a time; state changes are rare and are
+// replayed in ascending order through the reference's own scan (hmm.cpp:104-126, including its stale `start`).
+template <int S>
+__global__ void __launch_bounds__(128)
+viterbi_expand_kernel(ViterbiArgs a)
+{
+    constexpr int G = 32 / S;
+    constexpr unsigned kFull = 0xffffffffu;
+    const int wid = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (wid >= a.n_samples * a.n_chains) return;
+    const int smp = wid % a.n_samples, chain = wid / a.n_samples;
+    const int grp = smp / G, gg = smp - grp * G;
+    const ChainDesc cd = a.chains[chain];
+    const int nobs = cd.nobs;
+    const int64_t t_first = (cd.em_off + 1) >> 4;
+    const int n_tiles = chain_tiles(cd);
+    auto tile_i0 = [&](int t) -> int { return (int)(((t_first + t) << 4) - cd.em_off); };
+    const uint2* __restrict__ bp = reinterpret_cast<const uint2*>(a.bp) + record_base(a, chain, grp, n_tiles) * kRecU2;
+    const unsigned* __restrict__ tmap = reinterpret_cast<const unsigned*>(bp) + kMapOff;
+
+    const int64_t tcell = (int64_t)smp * a.n_chains + chain;
+    int32_t* __restrict__ slots = a.chain_calls + tcell * a.chain_call_cap * 4;
+    int8_t* __restrict__ path = a.path + smp * a.path_stride + cd.out_off;
     const bool vec_path = (((reinterpret_cast<uintptr_t>(a.path) | (uintptr_t)a.path_stride) & 15) == 0) && cd.out_off == cd.em_off;
-
-    // a state change between observation i-1 (state `below`) and i (hmm.cpp:110), met while walking down
-    auto boundary = [&](int i, int below) {
-        const int prev_state = below == 7 ? -1 : below;
-        cw.run_starts(i);                                   // a run that was open above starts at i
-        const int current = i == 1 ? 0 : prev_state;        // hmm.cpp:108 starts with current = 0
-        if (current == 0) cw.block_starts(i);               // hmm.cpp:111
-        else cw.emit(i, current);                           // hmm.cpp:112-120
-    };
-
-    unsigned st = 0;                                        // state at observation nobs-1 (hmm.cpp:96)
-    uint2 wn[S];
-    auto load_bp = [&](int t) {
+    int n_calls = 0, start = -1, nex = 0, run_start = 1;          // hmm.cpp:106, :108
+    for (int base = 0; base < n_tiles; base += 32) {
+        const int t = base + lane;
+        const bool have = t < n_tiles;
+        unsigned pw[4] = {0, 0, 0, 0};                      // states at the tile's 16 observations, one byte each
+        unsigned bmask = 0, st = 0;
+        if (have) {
+            st = tmap[(int64_t)t * kRecU32 + gg] & 0xFu;
+            uint2 w[S];
 #pragma unroll
-        for (int s = 0; s < S; s++) wn[s] = bp[(int64_t)t * 32 + src0 + s];
-    };
-    if (n_tiles > 0) load_bp(n_tiles - 1);
-    for (int t = n_tiles - 1; t >= 0; t--) {
-        uint2 w[S];
-#pragma unroll
-        for (int s = 0; s < S; s++) w[s] = wn[s];
-        if (t > 0) load_bp(t - 1);
-        const int i0 = tile_i0(t);
-        const bool whole = i0 >= 1 && i0 + kTile - 1 <= cd.out_last && i0 + kTile - 1 < nobs && i0 >= cd.out_first;
-        if (whole) {
-            unsigned pw[4] = {0, 0, 0, 0};                  // states at observations i0 .. i0+15, one byte each
-            unsigned bmask = 0;
-            const unsigned st_top = st;
+            for (int s = 0; s < S; s++) w[s] = bp[(int64_t)t * kRecU2 + gg * S + s];
 #pragma unroll
             for (int q = kTile - 1; q >= 0; q--) {
                 pw[q >> 2] |= st << (8 * (q & 3));
@@ -317,104 +459,115 @@ viterbi_chain_kernel(ViterbiArgs a, int groups_per_chain)
                 bmask |= (prev != st ? 1u : 0u) << q;
                 st = prev;
             }
-            if (bmask) {                                    // rare: replay the tile's state changes top-down
-                unsigned above = st_top;
-                (void)above;
-                for (int q = kTile - 1; q >= 0; q--) {
-                    if ((bmask >> q) & 1u) {
-                        const unsigned below = q > 0 ? (pw[(q - 1) >> 2] >> (8 * ((q - 1) & 3))) & 0xffu : st;
-                        boundary(i0 + q, (int)below);
-                    }
-                }
-            }
+            // st is now the state just before the tile
+            const int i0 = tile_i0(t);
+            unsigned ob[4];
 #pragma unroll
-            for (int r = 0; r < 4; r++) {                   // byte 7 -> 0xFF (-1)
-                const unsigned m = (pw[r] + 0x01010101u) & 0x08080808u;
-                pw[r] |= m * 31u;
-            }
-            if (vec_path) *reinterpret_cast<uint4*>(path + i0) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+            for (int r = 0; r < 4; r++) ob[r] = pw[r] | (((pw[r] + 0x01010101u) & 0x08080808u) * 31u);   // byte 7 -> 0xFF (-1)
+            if (vec_path && i0 >= cd.out_first && i0 + kTile - 1 <= cd.out_last)
+                __stcs(reinterpret_cast<uint4*>(path + i0), make_uint4(ob[0], ob[1], ob[2], ob[3]));
             else {
 #pragma unroll
-                for (int q = 0; q < kTile; q++) path[i0 + q] = (int8_t)(pw[q >> 2] >> (8 * (q & 3)));
+                for (int q = 0; q < kTile; q++)
+                    if (i0 + q >= cd.out_first && i0 + q <= cd.out_last) path[i0 + q] = (int8_t)(ob[q >> 2] >> (8 * (q & 3)));
             }
-        } else {
-#pragma unroll 1
-            for (int q = kTile - 1; q >= 0; q--) {
-                const int i = i0 + q;
-                if (i >= 1 && i < nobs) {
-                    if (i >= cd.out_first && i <= cd.out_last) path[i] = (int8_t)(st == 7u ? -1 : (int)st);
-                    unsigned word = 0;
-#pragma unroll
-                    for (int s = 0; s < S; s++) word = st == (unsigned)s ? (q < 8 ? w[s].x : w[s].y) : word;
-                    const unsigned prev = st == 7u ? 0u : (word >> (4 * (q & 7))) & 7u;
-                    if (prev != st) boundary(i, (int)prev);
-                    st = prev;
+            if (t == 0 && i0 == 1 && cd.out_first == 0) path[0] = (int8_t)(st == 7u ? -1 : (int)st);
+        }
+        unsigned ev = __ballot_sync(kFull, have && bmask != 0);
+        while (ev) {                                        // warp-uniform replay, ascending tiles
+            const int L = __ffs(ev) - 1;
+            ev &= ev - 1;
+            unsigned bm = __shfl_sync(kFull, bmask, L);
+            const unsigned p0 = __shfl_sync(kFull, pw[0], L), p1 = __shfl_sync(kFull, pw[1], L);
+            const unsigned p2 = __shfl_sync(kFull, pw[2], L), p3 = __shfl_sync(kFull, pw[3], L);
+            const unsigned before = __shfl_sync(kFull, st, L);
+            const int i0 = tile_i0(base + L);
+            const unsigned long long plo = ((unsigned long long)p1 << 32) | p0, phi = ((unsigned long long)p3 << 32) | p2;
+            while (bm) {
+                const int q = __ffs(bm) - 1;
+                bm &= bm - 1;
+                const int i = i0 + q;                       // path[i-1] != path[i]   (hmm.cpp:110)
+                const unsigned below = q == 0 ? before : (unsigned)(((q - 1) < 8 ? plo >> (8 * (q - 1)) : phi >> (8 * (q - 9))) & 0xFFu);
+                const int below_state = below == 7u ? -1 : (int)below;
+                if (below_state != 0) nex += i - run_start;            // hmm.cpp:124 over the run that ends at i-1
+                run_start = i;
+                const int current = i == 1 ? 0 : below_state;          // hmm.cpp:108, :125
+                if (current == 0) start = i;                           // hmm.cpp:111
+                else {                                                 // hmm.cpp:112-120
+                    if (lane == 0 && n_calls < a.chain_call_cap) {
+                        slots[4 * n_calls + 0] = start + 1 + cd.call_shift;
+                        slots[4 * n_calls + 1] = i + cd.call_shift;
+                        slots[4 * n_calls + 2] = current;
+                        slots[4 * n_calls + 3] = nex;
+                    }
+                    n_calls++;
+                    nex = 0;
                 }
             }
         }
     }
-    // observation 0 reached
-    if (nobs >= 1 && cd.out_first == 0) path[0] = (int8_t)(st == 7u ? -1 : (int)st);
-    cw.run_starts(1);                                       // a run still open extends to the chain start (hmm.cpp:124 counts from obs 1)
-    cw.block_starts(-1);                                    // start keeps its initial -1 (hmm.cpp:106)
-    a.chain_ncalls[tcell] = cw.n;
+    if (n_tiles == 0 && nobs >= 1 && cd.out_first == 0 && lane == 0) path[0] = 0;          // hmm.cpp:96
+    if (lane == 0) a.chain_ncalls[tcell] = n_calls;
 }
 
-// One thread per sample: concatenate the per-chain call lists (stored last-first at the end of each
-// chain's scratch) in chromosome order.
+// =========================================================================================== compact
+// One warp per sample: concatenate the per-chain call lists in chromosome order.
 __global__ void viterbi_compact_kernel(ViterbiArgs a)
 {
-    const int sample = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sample = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (sample >= a.n_samples) return;
     int n = 0;
     for (int c = 0; c < a.n_chains; c++) {
         const int64_t t = (int64_t)sample * a.n_chains + c;
         const int m = a.chain_ncalls[t];
-        const int have = m < a.chain_call_cap ? m : a.chain_call_cap;
-        const int32_t* src = a.chain_calls + (t * a.chain_call_cap + (a.chain_call_cap - have)) * 4;
-        // when the chain overflowed its scratch, the EARLIEST calls were dropped; keep the count honest
-        n += m - have;
-        for (int q = 0; q < have; q++, n++)
-            if (n < a.call_cap)
-                for (int f = 0; f < 4; f++) a.calls[((int64_t)sample * a.call_cap + n) * 4 + f] = src[4 * q + f];
+        const int have = m < a.chain_call_cap ? m : a.chain_call_cap;      // a chain that overflowed its scratch lost its LAST calls
+        const int room = a.call_cap - n;
+        const int copy = have < room ? have : (room > 0 ? room : 0);
+        const int32_t* __restrict__ src = a.chain_calls + t * a.chain_call_cap * 4;
+        int32_t* __restrict__ dst = a.calls + ((int64_t)sample * a.call_cap + n) * 4;
+        for (int q = lane; q < copy * 4; q += 32) dst[q] = src[q];
+        n += m;                 // the count stays honest; > call_cap signals truncation to the host
     }
-    a.ncalls[sample] = n;      // > call_cap signals truncation to the host
+    if (lane == 0) a.ncalls[sample] = n;
 }
 
 size_t viterbi_smem_bytes(int S) { return (size_t)kWarpsPerCta * kStages * (kTile * lt_pitch(S) * 8 + 8); }
 int viterbi_lt_pitch(int S) { return lt_pitch(S); }
 int viterbi_tile() { return kTile; }
+size_t viterbi_record_bytes() { return (size_t)kRecU2 * 8; }
 
 template <int S>
-static void launch_chain(const ViterbiArgs& a, int blocks, int groups, cudaStream_t st)
+static void launch_all(const ViterbiArgs& a, int64_t n_records, cudaStream_t st)
 {
+    constexpr int G = 32 / S;
     const size_t smem = viterbi_smem_bytes(S);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(viterbi_chain_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(viterbi_sweep_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    viterbi_chain_kernel<S><<<blocks, kWarpsPerCta * 32, smem, st>>>(a, groups);
+    viterbi_sweep_kernel<S><<<a.n_slots / kWarpsPerCta, kWarpsPerCta * 32, smem, st>>>(a);
+    const int64_t map_threads = n_records * G;
+    if (map_threads > 0) viterbi_tilemap_kernel<S><<<(unsigned)((map_threads + 255) / 256), 256, 0, st>>>(a, n_records);
+    const int chains = a.n_samples * a.n_chains;
+    viterbi_trace_kernel<<<(chains + 127) / 128, 128, 0, st>>>(a, G);
+    viterbi_expand_kernel<S><<<(chains + 3) / 4, 128, 0, st>>>(a);
 }
 
-void launch_viterbi(const ViterbiArgs& a, cudaStream_t st)
+int launch_viterbi(const ViterbiArgs& a, int64_t n_records, cudaStream_t st)
 {
-    if (a.n_chains == 0 || a.n_samples == 0) return;
-    const int S = a.n_states;
-    const int G = 32 / S;
-    const int groups = (a.n_samples + G - 1) / G;
-    const int warps = groups * a.n_chains;
-    const int blocks = ((warps + 1) / 2 + 3) / 4;          // see warp_slot(): 4 front + 4 back slots per CTA
-    switch (S) {
-        case 2: launch_chain<2>(a, blocks, groups, st); break;
-        case 3: launch_chain<3>(a, blocks, groups, st); break;
-        case 4: launch_chain<4>(a, blocks, groups, st); break;
-        case 5: launch_chain<5>(a, blocks, groups, st); break;
-        case 6: launch_chain<6>(a, blocks, groups, st); break;
-        case 7: launch_chain<7>(a, blocks, groups, st); break;
-        default: return;
+    if (a.n_chains == 0 || a.n_samples == 0) return 0;
+    switch (a.n_states) {
+        case 2: launch_all<2>(a, n_records, st); break;
+        case 3: launch_all<3>(a, n_records, st); break;
+        case 4: launch_all<4>(a, n_records, st); break;
+        case 5: launch_all<5>(a, n_records, st); break;
+        case 6: launch_all<6>(a, n_records, st); break;
+        case 7: launch_all<7>(a, n_records, st); break;
+        default: return 0;
     }
-    viterbi_compact_kernel<<<(a.n_samples + 127) / 128, 128, 0, st>>>(a);
+    viterbi_compact_kernel<<<(a.n_samples + 3) / 4, 128, 0, st>>>(a);
+    return 5;
 }
 
 }  // namespace edb
