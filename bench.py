@@ -48,7 +48,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -230,6 +230,7 @@ def gpu_arm(a, rank, world):
         sampler.start()
         time.sleep(0.15)
     _lib.launch_count(reset=True)
+    _lib.profile(True)                  # one CUDA event before every kernel launch, on the launching stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -239,18 +240,9 @@ def gpu_arm(a, rank, world):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count()
-    # per-kernel device time for the roofline: CUDA events on the launching stream, same buffers, after the timed region
-    kt = {}
-    for name, what in (("emission", 1), ("viterbi", 2)):
-        ts = []
-        for _ in range(max(3, min(a.steps, 10))):
-            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            k0.record()
-            step(what)
-            k1.record()
-            torch.cuda.synchronize()
-            ts.append(k0.elapsed_time(k1))
-        kt[name] = float(np.mean(ts))
+    prof = _lib.profile_read()          # {kernel: (launches, total ms)} over exactly the timed region
+    _lib.profile(False)
+    kt = {k: v[1] / max(v[0], 1) for k, v in prof.items()}         # average device time per launch
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist:
@@ -282,8 +274,24 @@ def gpu_arm(a, rank, world):
         d2h = sum(v.nbytes for v in out.values())
         e2e = dict(value=world * ns * nb / float(t[0]), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                    ms_per_step=1e3 * float(t[0]),
-                   api="edb200_cohort_run_host (C ABI, pinned host buffers; returns ll matrix, Viterbi path and call table)")
+                   api="edb200_cohort_run_host (C ABI, pinned host buffers; returns ll matrix, Viterbi path and call table); "
+                       "bound by the device-to-host copy of the FP64 ll matrix (8*S bytes per bin*sample over PCIe)")
         assert int(out["ncalls"].sum()) == total_calls
+        # the same call when the caller leaves the likelihood matrix on the device (CallCNVs only needs path + calls)
+        out2 = dict(path=out["path"], calls=out["calls"], ncalls=out["ncalls"])
+        co.run_host(obs_p, ref, phi_h, exp_h, call_cap=cap, out=out2, want_ll=False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            co.run_host(obs_p, ref, phi_h, exp_h, call_cap=cap, out=out2, want_ll=False)
+        barrier()
+        dt2 = (time.perf_counter() - t0) / n_e2e
+        t2 = torch.tensor([dt2], dtype=torch.float64, device=dev)
+        if dist:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e["without_ll_copy"] = dict(value=world * ns * nb / float(t2[0]), unit=UNIT, ms_per_step=1e3 * float(t2[0]),
+                                      d2h_bytes_per_step=int(sum(v.nbytes for v in out2.values())),
+                                      note="same call, likelihood matrix left in HBM; path + call table returned")
 
     if rank != 0:
         if dist:
@@ -292,18 +300,21 @@ def gpu_arm(a, rank, world):
     cells = ns * nb
     value = world * cells * a.steps / (ms / 1e3)
     peak, peak_src = peaks()
-    dom = max(kt, key=kt.get)
-    alg = {"emission": 4 + 8 * S, "viterbi": 8 * S + 1}       # algorithmic bytes per bin*sample
+    # algorithmic bytes per bin*sample: emission reads the test count and writes S log-likelihoods;
+    # the Viterbi sweep reads them back and the path byte leaves downstream of it
+    alg = {"emission": 4 + 8 * S, "viterbi_sweep": 8 * S + 1}
+    dom = max(alg, key=lambda k: kt.get(k, 0.0))
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
 
     def roof(name):
         ach = cells * alg[name] / (kt[name] / 1e3) / 1e9
         return dict(kernel=name, bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
-                    traffic=traffic if name == dom else None, ms_per_launch=kt[name], bytes_per_unit=alg[name], peak_source=peak_src)
+                    traffic=(traffic or {}).get(name) if isinstance(traffic, dict) else None, ms_per_launch=kt[name],
+                    bytes_per_unit=alg[name], peak_source=peak_src)
 
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup, ms_per_step=ms / a.steps,
                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
@@ -313,7 +324,8 @@ def gpu_arm(a, rank, world):
                            shared_metadata="bin geometry, reference aggregate and host-libm log-transition table NCCL-broadcast from rank 0"
                            if world > 1 else "single rank", table_build_s=table_s, total_calls=total_calls, status=status),
                clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roof(dom),
-               roofline_other=roof([k for k in kt if k != dom][0]))
+               roofline_other=roof("emission" if dom != "emission" else "viterbi_sweep"),
+               kernel_ms_per_launch={k: round(v, 5) for k, v in sorted(kt.items(), key=lambda kv: -kv[1])})
     if world == 1 and not a.no_cpu:
         from oracle import ref as oref
         cores = os.cpu_count() or 1

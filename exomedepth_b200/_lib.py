@@ -18,7 +18,8 @@ EXPORTS = (
     "edb200_host_alloc", "edb200_host_free", "edb200_get_loglike_matrix", "edb200_emission", "edb200_hmm",
     "edb200_cohort_create", "edb200_cohort_destroy", "edb200_cohort_table", "edb200_cohort_table_copy",
     "edb200_cohort_run_device",
-    "edb200_cohort_run_host", "edb200_status",
+    "edb200_cohort_run_host", "edb200_status", "edb200_profile", "edb200_profile_read",
+    "edb200_cohort_forward_device", "edb200_cohort_forward_last",
 )
 
 
@@ -83,8 +84,16 @@ def load():
     L.edb200_cohort_run_device.argtypes = [vp, C.POINTER(Batch), C.c_int, C.c_int, vp]
     L.edb200_cohort_run_host.restype = C.c_int
     L.edb200_cohort_run_host.argtypes = [vp, C.POINTER(Batch), C.c_int]
+    L.edb200_cohort_forward_device.restype = C.c_int
+    L.edb200_cohort_forward_device.argtypes = [vp, C.POINTER(Batch), vp, i32, vp, vp, vp]
+    L.edb200_cohort_forward_last.restype = C.c_int
+    L.edb200_cohort_forward_last.argtypes = [vp, vp, i32, vp, vp]
     L.edb200_status.restype = C.c_int
     L.edb200_status.argtypes = [C.c_int]
+    L.edb200_profile.restype = C.c_int
+    L.edb200_profile.argtypes = [C.c_int]
+    L.edb200_profile_read.restype = C.c_int
+    L.edb200_profile_read.argtypes = [C.c_char_p, C.c_int]
     _lib = L
     return L
 
@@ -113,6 +122,23 @@ def device_info():
 
 def launch_count(reset=False):
     return int(load().edb200_launch_count(1 if reset else 0))
+
+
+def profile(enable):
+    """Bracket every kernel launch with CUDA events on its stream (bench.py's per-kernel roofline)."""
+    check(load().edb200_profile(1 if enable else 0), "edb200_profile")
+
+
+def profile_read():
+    """{kernel: (launches, total_ms)} since profiling was enabled or last read."""
+    buf = C.create_string_buffer(4096)
+    check(load().edb200_profile_read(buf, 4096), "edb200_profile_read")
+    out = {}
+    for item in buf.value.decode().split(";"):
+        if item:
+            name, n, ms = item.split(":")
+            out[name] = (int(n), float(ms))
+    return out
 
 
 class PinnedPool:

@@ -87,7 +87,24 @@ class Cohort:
         b = _lib.Batch(ns, _ptr(observed), nb, _ptr(reference), 0 if reference.ndim == 1 else nb, _ptr(phi),
                        _ptr(expected), _ptr(ll), nb, _ptr(path), nb, _ptr(calls), _ptr(ncalls), call_cap)
         rc = _lib.check(self.lib.edb200_cohort_run_host(self.handle, C.byref(b), mode), "edb200_cohort_run_host")
+        self._last_ns = ns
         return dict(ll=ll, path=path, calls=calls, ncalls=ncalls, status=rc)
+
+    def forward_last(self, tp_grid=None):
+        """Forward log-likelihood per sample and grid point over the likelihoods of the most recent run_host call
+        (still resident in HBM), and the index of the maximiser — the per-sample transition-probability MLE over the
+        grid.  tp_grid=None: one column for the cohort's own transition matrix.  Extension (no reference counterpart)."""
+        if tp_grid is None:
+            grid, ng = None, 1
+        else:
+            grid = np.ascontiguousarray(np.asarray(tp_grid, np.float64))
+            ng = grid.size
+        ns = self._last_ns
+        loglik = np.empty((ns, ng))
+        best = np.empty(ns, np.int32)
+        _lib.check(self.lib.edb200_cohort_forward_last(self.handle, _ptr(grid), ng, _ptr(loglik), _ptr(best)),
+                   "edb200_cohort_forward_last")
+        return loglik, best
 
     # ---- device tensors (torch) -----------------------------------------------------------------
     def run_device(self, observed, reference, phi, expected, ll, path=None, calls=None, ncalls=None,
@@ -104,3 +121,14 @@ class Cohort:
                        ncalls.data_ptr() if ncalls is not None else None, calls.shape[1] if calls is not None else 0)
         return _lib.check(self.lib.edb200_cohort_run_device(self.handle, C.byref(b), what, mode, st),
                           "edb200_cohort_run_device")
+
+    def forward_device(self, ll, loglik, best=None, tp_grid=None, stream=None):
+        """ll: CUDA float64 [n_samples, S, stride] as filled by run_device; loglik: CUDA float64 [n_samples, n_grid];
+        best: CUDA int32 [n_samples] or None.  Enqueues on `stream` (default: torch's current stream)."""
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        grid = None if tp_grid is None else np.ascontiguousarray(np.asarray(tp_grid, np.float64))
+        b = _lib.Batch(ll.shape[0], None, 0, None, 0, None, None, ll.data_ptr(), ll.stride(1), None, 0, None, None, 0)
+        return _lib.check(self.lib.edb200_cohort_forward_device(self.handle, C.byref(b), _ptr(grid), 1 if grid is None else grid.size,
+                                                                loglik.data_ptr(), best.data_ptr() if best is not None else None, st),
+                          "edb200_cohort_forward_device")

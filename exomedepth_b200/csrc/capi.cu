@@ -31,6 +31,8 @@ struct Context {
     size_t smem_optin = 0;
     std::string name;
     cudaStream_t stream = nullptr;       // used by the host-pointer entry points
+    cudaStream_t stream2 = nullptr;      // drains results to the host while `stream` computes the next chunk
+    cudaEvent_t chunk_done[16] = {};
     unsigned* d_flags = nullptr;         // sticky device warning word
     unsigned sticky = 0;
     std::vector<DevBuf*> bufs;
@@ -40,6 +42,56 @@ Context g;
 std::mutex g_mu;
 thread_local std::string t_err;
 std::atomic<long long> g_launches{0};
+
+// per-kernel timing: consecutive marks on a stream bracket the kernel launched between them
+struct EventTimer : edb::KernelTimer {
+    struct Interval { std::string name; cudaEvent_t e0, e1; };
+    std::vector<Interval> done;
+    std::vector<cudaEvent_t> pool;
+    std::string open_name;
+    cudaEvent_t open_ev = nullptr;
+    cudaEvent_t get()
+    {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void mark(const char* name, cudaStream_t st) override
+    {
+        cudaEvent_t e = get();
+        cudaEventRecord(e, st);
+        if (open_ev) done.push_back({open_name, open_ev, e});
+        if (name) { open_name = name; open_ev = e; }
+        else open_ev = nullptr;
+        // an event that only closes an interval is owned by that interval; one that opens the next is shared
+    }
+    std::string read()
+    {
+        cudaDeviceSynchronize();
+        std::vector<std::string> names;
+        std::vector<double> total;
+        std::vector<int> count;
+        for (auto& iv : done) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, iv.e0, iv.e1);
+            size_t k = 0;
+            while (k < names.size() && names[k] != iv.name) k++;
+            if (k == names.size()) { names.push_back(iv.name); total.push_back(0); count.push_back(0); }
+            total[k] += ms;
+            count[k]++;
+        }
+        done.clear();               // events are left to the driver: a profile run is short
+        std::string out;
+        char line[160];
+        for (size_t k = 0; k < names.size(); k++) {
+            snprintf(line, sizeof line, "%s%s:%d:%.6f", k ? ";" : "", names[k].c_str(), count[k], total[k]);
+            out += line;
+        }
+        return out;
+    }
+};
+EventTimer g_event_timer;
 
 int fail(int code, const char* fmt, ...)
 {
@@ -111,6 +163,8 @@ int upload_schedule(const std::vector<int32_t>& nobs, int groups, int n_ctas, De
 
 }  // namespace
 
+edb::KernelTimer* edb::g_timer = nullptr;
+
 // =====================================================================================================
 struct edb200_cohort {
     int64_t n_bins = 0;
@@ -124,11 +178,12 @@ struct edb200_cohort {
     std::vector<edb::ChainDesc> chains_h;
     int64_t total_tiles = 0;
     int lt_pitch = 0;
-    DevBuf chains, lt, odds_d, tile_base;
+    DevBuf chains, lt, odds_d, tile_base, decay;
     DevBuf sched_begin, sched_items;     // sweep schedule for `sched_groups` groups of samples
     int sched_groups = 0;
     // per-batch scratch
-    DevBuf consts, bp, ccalls, cncalls, maxima;
+    DevBuf consts, bp, ccalls, cncalls, maxima, fw_grid, fw_chain, fw_out, fw_best;
+    int last_host_samples = 0;           // samples whose likelihoods the last host-pointer run left in h_ll
     // host-mode staging
     DevBuf h_obs, h_ref, h_phi, h_exp, h_ll, h_path, h_calls, h_ncalls;
 };
@@ -162,6 +217,10 @@ int edb200_init(int device)
         return fail(EDB200_ERR_CUDA, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 part; this library ships sm_100a code only",
                     device, p.name, p.major, p.minor);
     if (!g.stream) CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    if (!g.stream2) {
+        CU(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
+        for (cudaEvent_t& e : g.chunk_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     if (!g.d_flags) {
         CU(cudaMalloc(&g.d_flags, sizeof(unsigned)));
         CU(cudaMemset(g.d_flags, 0, sizeof(unsigned)));
@@ -182,6 +241,11 @@ void edb200_shutdown(void)
     g.d_flags = nullptr;
     if (g.stream) cudaStreamDestroy(g.stream);
     g.stream = nullptr;
+    if (g.stream2) {
+        cudaStreamDestroy(g.stream2);
+        for (cudaEvent_t& e : g.chunk_done) cudaEventDestroy(e);
+    }
+    g.stream2 = nullptr;
     g.ready = false;
 }
 
@@ -220,6 +284,25 @@ void edb200_host_free(void* p)
     if (p) cudaFreeHost(p);
 }
 
+int edb200_profile(int enable)
+{
+    if (int rc = need_ctx()) return rc;
+    cudaDeviceSynchronize();
+    g_event_timer.done.clear();
+    g_event_timer.open_ev = nullptr;
+    edb::g_timer = enable ? &g_event_timer : nullptr;
+    return 0;
+}
+
+int edb200_profile_read(char* buf, int buflen)
+{
+    if (int rc = need_ctx()) return rc;
+    if (!buf || buflen < 1) return fail(EDB200_ERR_ARG, "null buffer");
+    const std::string s = g_event_timer.read();
+    snprintf(buf, buflen, "%s", s.c_str());
+    return (int)s.size() >= buflen ? EDB200_ERR_ARG : 0;
+}
+
 int edb200_status(int reset)
 {
     if (int rc = need_ctx()) return rc;
@@ -239,6 +322,7 @@ int edb200_status(int reset)
 // =====================================================================================================
 namespace {
 
+constexpr int kHostChunks = 8;                     // sample chunks of the host-pointer cohort call (<= 16 events)
 constexpr int kTableK = 2048, kTableRN = 12288;   // lattice caps: (2048 + 2*12288) * 8 B = 208 KB of shared memory
 
 int pull_flags(cudaStream_t st, int* warn)
@@ -259,7 +343,9 @@ int run_emission_scalar(edb::CountsView cv, const double* d_phi, const double* d
                         edb::StateConst* d_consts, int n_samples, int S, int64_t n_bins, edb::LLView out,
                         int mode, cudaStream_t st)
 {
+    edb::prof_mark("state_setup", st);
     edb::launch_state_setup(n_samples, S, d_phi, d_expected, d_odds, d_consts, st);
+    edb::prof_mark(mode == EDB200_EMISSION_DIRECT ? "emission_direct" : "emission", st);
     g_launches++;
     bool table = mode == EDB200_EMISSION_TABLE;
     if (mode == EDB200_EMISSION_AUTO) table = n_bins >= 4 * (int64_t)(kTableK + 2 * kTableRN);
@@ -272,6 +358,7 @@ int run_emission_scalar(edb::CountsView cv, const double* d_phi, const double* d
     } else {
         edb::launch_emission_direct(cv, d_consts, n_samples, S, n_bins, out, g.d_flags, st);
     }
+    edb::prof_mark(nullptr, st);
     g_launches++;
     return check_kernel("emission");
 }
@@ -480,6 +567,7 @@ int edb200_cohort_create(const edb200_cohort_spec* sp, edb200_cohort** out)
         c->total_tiles += edb::viterbi_chain_tiles(c->chains_h[ch]);
     }
     std::vector<int32_t> pos;
+    std::vector<double> decay((size_t)rows + edb::viterbi_tile(), 0.0);
     for (int ch = 0; ch < c->n_chains; ch++) {
         const int64_t b0 = sp->chain_offsets[ch], nb = sp->chain_offsets[ch + 1] - b0;
         pos.resize(nb + 2);
@@ -487,6 +575,7 @@ int edb200_cohort_create(const edb200_cohort_spec* sp, edb200_cohort** out)
             delete c;
             return fail(EDB200_ERR_ARG, "framed position of chromosome %d does not fit an R integer", ch);
         }
+        edb::build_decay_rows(pos.data(), (int32_t)(nb + 2), c->L, decay.data() + c->chains_h[ch].lt_row0);
         if (!sp->skip_table_build)
             edb::build_log_transition_rows(S, c->T, pos.data(), (int32_t)(nb + 2), c->L,
                                            lt.data() + (size_t)c->chains_h[ch].lt_row0 * pitch, pitch);
@@ -498,6 +587,11 @@ int edb200_cohort_create(const edb200_cohort_spec* sp, edb200_cohort** out)
         return rc;
     }
     CU(cudaMemcpy(c->tile_base.p, tile_base.data(), c->n_chains * 4, cudaMemcpyHostToDevice));
+    if ((rc = ensure(c->decay, decay.size() * 8))) {
+        delete c;
+        return rc;
+    }
+    CU(cudaMemcpy(c->decay.p, decay.data(), decay.size() * 8, cudaMemcpyHostToDevice));
     edb::nan_to_neg_inf(lt.data(), lt.size());     // device copy only: a NaN term is "never selected", like -Inf (hmm.cpp:81)
     CU(cudaMemcpy(c->lt.p, lt.data(), lt.size() * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->chains.p, c->chains_h.data(), c->n_chains * sizeof(edb::ChainDesc), cudaMemcpyHostToDevice));
@@ -511,7 +605,7 @@ void edb200_cohort_destroy(edb200_cohort* c)
     if (!c) return;
     std::lock_guard<std::mutex> lk(g_mu);
     cudaDeviceSynchronize();
-    DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->tile_base, &c->sched_begin, &c->sched_items, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->maxima,
+    DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->tile_base, &c->decay, &c->fw_grid, &c->fw_chain, &c->fw_out, &c->fw_best, &c->sched_begin, &c->sched_items, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->maxima,
                      &c->h_obs, &c->h_ref, &c->h_phi, &c->h_exp, &c->h_ll, &c->h_path, &c->h_calls, &c->h_ncalls};
     for (DevBuf* b : all) release(*b);
     delete c;
@@ -601,6 +695,70 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
     return 0;
 }
 
+// transition matrices of the grid: the CallCNVs matrix for every tp, or the cohort's own matrix when tp_grid is null
+static int forward_common(edb200_cohort* c, const double* d_ll, int64_t ll_stride, int ns, const double* tp_grid, int n_grid,
+                          double* d_loglik, int32_t* d_best, cudaStream_t st)
+{
+    const int S = c->S;
+    if (!tp_grid) n_grid = 1;
+    if (n_grid < 1 || n_grid > 4096) return fail(EDB200_ERR_ARG, "n_grid=%d not in [1, 4096]", n_grid);
+    std::vector<double> grid((size_t)n_grid * S * S);
+    for (int gi = 0; gi < n_grid; gi++) {
+        if (tp_grid) edb::callcnvs_transitions(S, tp_grid[gi], grid.data() + (size_t)gi * S * S);
+        else memcpy(grid.data(), c->T, S * S * 8);
+    }
+    if (int rc = ensure(c->fw_grid, grid.size() * 8)) return rc;
+    if (int rc = ensure(c->fw_chain, (size_t)ns * c->n_chains * n_grid * 8)) return rc;
+    CU(cudaMemcpyAsync(c->fw_grid.p, grid.data(), grid.size() * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));          // `grid` goes out of scope
+    edb::ForwardArgs a{};
+    a.chains = (const edb::ChainDesc*)c->chains.p;
+    a.n_chains = c->n_chains;
+    a.n_samples = ns;
+    a.n_states = S;
+    a.n_grid = n_grid;
+    a.ll = d_ll;
+    a.ll_sample_stride = (int64_t)S * ll_stride;
+    a.ll_state_stride = ll_stride;
+    for (int j = 0; j < S; j++) a.perm[j] = c->perm[j];
+    a.decay = (const double*)c->decay.p;
+    a.T_grid = (const double*)c->fw_grid.p;
+    a.tail_other = -100.0;                                     // R/class_definition.R:364
+    a.chain_loglik = (double*)c->fw_chain.p;
+    a.loglik = d_loglik;
+    a.best = d_best;
+    g_launches += edb::launch_forward(a, st);
+    return check_kernel("forward");
+}
+
+int edb200_cohort_forward_device(edb200_cohort* c, const edb200_batch* b, const double* tp_grid, int32_t n_grid,
+                                 double* loglik, int32_t* best, void* cuda_stream)
+{
+    if (int rc = need_ctx()) return rc;
+    if (!c || !b || !b->ll || !loglik || b->n_samples < 1) return fail(EDB200_ERR_ARG, "bad argument");
+    if (b->ll_stride < c->n_bins) return fail(EDB200_ERR_ARG, "stride smaller than n_bins");
+    return forward_common(c, b->ll, b->ll_stride, b->n_samples, tp_grid, n_grid, loglik, best, (cudaStream_t)cuda_stream);
+}
+
+int edb200_cohort_forward_last(edb200_cohort* c, const double* tp_grid, int32_t n_grid, double* loglik, int32_t* best)
+{
+    if (int rc = need_ctx()) return rc;
+    if (!c || !loglik) return fail(EDB200_ERR_ARG, "null argument");
+    if (c->last_host_samples < 1) return fail(EDB200_ERR_ARG, "no likelihoods resident: call edb200_cohort_run_host first");
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaStream_t st = g.stream;
+    const int ns = c->last_host_samples, ng = tp_grid ? n_grid : 1;
+    const int64_t nbp = (c->n_bins + 15) & ~(int64_t)15;
+    if (ng < 1 || ng > 4096) return fail(EDB200_ERR_ARG, "n_grid=%d not in [1, 4096]", ng);
+    if (int rc = ensure(c->fw_out, (size_t)ns * ng * 8)) return rc;
+    if (int rc = ensure(c->fw_best, (size_t)ns * 4)) return rc;
+    if (int rc = forward_common(c, (const double*)c->h_ll.p, nbp, ns, tp_grid, ng, (double*)c->fw_out.p, (int32_t*)c->fw_best.p, st)) return rc;
+    CU(cudaMemcpyAsync(loglik, c->fw_out.p, (size_t)ns * ng * 8, cudaMemcpyDeviceToHost, st));
+    if (best) CU(cudaMemcpyAsync(best, c->fw_best.p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission_mode)
 {
     if (int rc = need_ctx()) return rc;
@@ -619,7 +777,6 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         (rc = ensure(c->h_path, (size_t)ns * nb)) || (rc = ensure(c->h_calls, (size_t)ns * cap * 16)) ||
         (rc = ensure(c->h_ncalls, ns * 4)))
         return rc;
-    CU(cudaMemcpy2DAsync(c->h_obs.p, nb * 4, b->observed, b->obs_stride * 4, nb * 4, ns, cudaMemcpyHostToDevice, st));
     if (shared_ref) CU(cudaMemcpyAsync(c->h_ref.p, b->reference, nb * 4, cudaMemcpyHostToDevice, st));
     else CU(cudaMemcpy2DAsync(c->h_ref.p, nb * 4, b->reference, b->ref_stride * 4, nb * 4, ns, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->h_phi.p, b->phi, ns * 8, cudaMemcpyHostToDevice, st));
@@ -640,14 +797,40 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     d.ncalls = (int32_t*)c->h_ncalls.p;
     d.call_cap = cap;
     const bool want_vit = b->path || b->calls || b->ncalls;
-    if ((rc = edb200_cohort_run_device(c, &d, want_vit ? 3 : 1, emission_mode, st))) return rc;
+    c->last_host_samples = ns;
 
-    if (b->ll) CU(cudaMemcpy2DAsync(b->ll, b->ll_stride * 8, c->h_ll.p, nbp * 8, nb * 8, (size_t)ns * S, cudaMemcpyDeviceToHost, st));
+    // The likelihood matrix is 8*S bytes per bin and sample on the way back, against 4 on the way in: the call is
+    // bound by the device-to-host copy.  Samples therefore go through in chunks: the counts of chunk i+1 upload and
+    // its emission kernel runs on `st` while the likelihoods of chunk i drain on the second stream.
+    const int n_chunks = (b->ll && ns >= 2 * kHostChunks) ? kHostChunks : 1;
+    const int per = (ns + n_chunks - 1) / n_chunks;
+    for (int k = 0, s0 = 0; s0 < ns; k++, s0 += per) {
+        const int cnt = ns - s0 < per ? ns - s0 : per;
+        CU(cudaMemcpy2DAsync((int32_t*)c->h_obs.p + (size_t)s0 * nb, nb * 4, b->observed + (size_t)s0 * b->obs_stride, b->obs_stride * 4,
+                             nb * 4, cnt, cudaMemcpyHostToDevice, st));
+        edb200_batch e = d;
+        e.n_samples = cnt;
+        e.observed = d.observed + (size_t)s0 * nb;
+        if (!shared_ref) e.reference = d.reference + (size_t)s0 * nb;
+        e.phi = d.phi + s0;
+        e.expected = d.expected + s0;
+        e.ll = d.ll + (size_t)s0 * S * nbp;
+        if ((rc = edb200_cohort_run_device(c, &e, 1, emission_mode, st))) return rc;
+        if (b->ll) {
+            CU(cudaEventRecord(g.chunk_done[k], st));
+            CU(cudaStreamWaitEvent(g.stream2, g.chunk_done[k], 0));
+            CU(cudaMemcpy2DAsync(b->ll + (size_t)s0 * S * b->ll_stride, b->ll_stride * 8, e.ll, nbp * 8, nb * 8, (size_t)cnt * S,
+                                 cudaMemcpyDeviceToHost, g.stream2));
+        }
+    }
+    if (want_vit && (rc = edb200_cohort_run_device(c, &d, 2, emission_mode, st))) return rc;
+
     if (b->path) CU(cudaMemcpy2DAsync(b->path, b->path_stride, c->h_path.p, nb, nb, ns, cudaMemcpyDeviceToHost, st));
     if (b->calls && b->call_cap > 0) CU(cudaMemcpyAsync(b->calls, c->h_calls.p, (size_t)ns * cap * 16, cudaMemcpyDeviceToHost, st));
     if (b->ncalls) CU(cudaMemcpyAsync(b->ncalls, c->h_ncalls.p, ns * 4, cudaMemcpyDeviceToHost, st));
     int warn = 0;
     if ((rc = pull_flags(st, &warn))) return rc;
+    CU(cudaStreamSynchronize(g.stream2));
     if (b->ncalls && b->call_cap > 0)
         for (int s = 0; s < ns; s++) if (b->ncalls[s] > b->call_cap) warn |= EDB200_WARN_CALLCAP;
     return warn;

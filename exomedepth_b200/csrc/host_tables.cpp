@@ -89,6 +89,12 @@ void build_log_transition_rows(int S, const double* T, const int32_t* pos, int32
     for (auto& x : th) x.join();
 }
 
+void build_decay_rows(const int32_t* pos, int32_t nobs, double L, double* decay)
+{
+    if (nobs > 0) decay[0] = 0.0;
+    for (int32_t i = 1; i < nobs; i++) decay[i] = std::exp(-(double(pos[i]) - double(pos[i - 1])) / L);
+}
+
 void nan_to_neg_inf(double* v, size_t n)
 {
     for (size_t i = 0; i < n; i++)

@@ -9,6 +9,8 @@ namespace edb {
 void callcnvs_transitions(int S, double tp, double* T);
 // lt[i*pitch + j*(pitch/S) + k] = log(t_{k->j} at observation i), i = 1..nobs-1 (src/hmm.cpp:62-79); row 0 and padding zeroed
 void build_log_transition_rows(int S, const double* T, const int32_t* pos, int32_t nobs, double L, double* lt, int pitch);
+// decay[i] = exp(-(pos[i] - pos[i-1]) / L), i = 1..nobs-1 (src/hmm.cpp:62-64, host libm); decay[0] = 0
+void build_decay_rows(const int32_t* pos, int32_t nobs, double L, double* decay);
 // CallCNVs framing of one chromosome's positions (R/class_definition.R:368); pos has nb+2 entries. 0 = ok
 int frame_positions(int64_t nb, const int32_t* start, const int32_t* end, double L, int32_t* pos);
 // in-place NaN -> -Inf for the device copy of the table: in the recurrence a NaN candidate and a -Inf candidate

@@ -8,6 +8,16 @@
 
 namespace edb {
 
+// ---- optional per-kernel timing (edb200_profile): one CUDA event on the launching stream before every kernel ----
+struct KernelTimer {
+    virtual void mark(const char* name, cudaStream_t st) = 0;   // name == nullptr closes the open interval
+};
+extern KernelTimer* g_timer;                                    // null unless profiling is on (capi.cu)
+inline void prof_mark(const char* name, cudaStream_t st)
+{
+    if (g_timer) g_timer->mark(name, st);
+}
+
 // ---- emission -----------------------------------------------------------------------------------
 struct CountsView {
     const int32_t* observed;      // [n_samples][obs_stride]
@@ -102,5 +112,25 @@ inline int viterbi_chain_tiles(const ChainDesc& cd)
     if (cd.nobs <= 1) return 0;
     return (int)(((cd.em_off + cd.nobs - 1) >> 4) - ((cd.em_off + 1) >> 4) + 1);
 }
+
+// ---- forward pass / transition-probability grid (extension, forward.cu) -------------------------------
+struct ForwardArgs {
+    const ChainDesc* chains;      // [n_chains]
+    int n_chains;
+    int n_samples;
+    int n_states;
+    int n_grid;
+    const double* ll;             // emission matrix, see LLView strides
+    int64_t ll_sample_stride;
+    int64_t ll_state_stride;
+    int perm[kMaxStates];         // HMM state j reads emission column perm[j]
+    const double* decay;          // [rows] exp(-dist / L) per observation (host libm, hmm.cpp:62-64)
+    const double* T_grid;         // [n_grid][S*S] transition matrices, column-major T[k + S*j] = P(k -> j)
+    double tail_other;            // emission of the non-normal states at the dummy last observation
+    double* chain_loglik;         // scratch [n_samples][n_chains][n_grid]
+    double* loglik;               // out [n_samples][n_grid]
+    int32_t* best;                // out [n_samples] first maximiser over the grid, or null
+};
+int launch_forward(const ForwardArgs& a, cudaStream_t st);   // returns the number of launches
 
 }  // namespace edb

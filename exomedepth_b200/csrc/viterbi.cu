@@ -26,7 +26,7 @@
 //            with its consumers and the step takes 228 instead of 126 cycles.
 //   tilemap  composes the 16 back-pointer steps of every tile into a map end state -> state before
 //            the tile (fully parallel);
-//   trace    one thread per chain walks one map per tile instead of one back-pointer per observation
+//   trace    one warp per chain walks one map per tile instead of one back-pointer per observation
 //            (hmm.cpp:95-100);
 //   expand   one warp per chain fills in the per-observation states, the path bytes and the
 //            reference's call table, 32 tiles at a time;
@@ -384,31 +384,35 @@ viterbi_tilemap_kernel(ViterbiArgs a, int64_t n_records)
 }
 
 // =========================================================================================== trace
-// One thread per chain: e = state at the tile's last observation; the chain ends in state 0 (hmm.cpp:96).
-// The map words are replaced by e as they are consumed.
+// One warp per chain: e = state at the tile's last observation; the chain ends in state 0 (hmm.cpp:96).
+// The lanes fetch 32 map words at a time (the next 32 are already in flight), the walk itself passes
+// through them with one shuffle per tile, and every word is replaced by its e.
 __global__ void __launch_bounds__(128)
 viterbi_trace_kernel(ViterbiArgs a, int G)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.n_samples * a.n_chains) return;
-    const int smp = idx % a.n_samples, chain = idx / a.n_samples;       // neighbouring threads: same chromosome, same length
+    constexpr unsigned kFull = 0xffffffffu;
+    const int wid = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (wid >= a.n_samples * a.n_chains) return;
+    const int smp = wid % a.n_samples, chain = wid / a.n_samples;       // neighbouring warps: same chromosome, same length
     const int grp = smp / G, gg = smp - grp * G;
     const ChainDesc cd = a.chains[chain];
     const int n_tiles = chain_tiles(cd);
     unsigned* __restrict__ tmap = reinterpret_cast<unsigned*>(a.bp) + record_base(a, chain, grp, n_tiles) * kRecU32 + kMapOff + gg;
     unsigned e = 0;
-    int t = n_tiles - 1;
-    while (t >= 0) {
-        unsigned w[8];
-#pragma unroll
-        for (int r = 0; r < 8; r++) w[r] = t - r >= 0 ? tmap[(int64_t)(t - r) * kRecU32] : 0u;
-#pragma unroll
-        for (int r = 0; r < 8; r++)
-            if (t - r >= 0) {
-                tmap[(int64_t)(t - r) * kRecU32] = e;
-                e = (w[r] >> (4 * e)) & 0xFu;
-            }
-        t -= 8;
+    int top = n_tiles - 1;                                  // lane l holds tile top - l
+    unsigned nxt = top - lane >= 0 ? tmap[(int64_t)(top - lane) * kRecU32] : 0u;
+    while (top >= 0) {
+        const unsigned w = nxt;
+        if (top - 32 - lane >= 0) nxt = tmap[(int64_t)(top - 32 - lane) * kRecU32];
+        unsigned mine = 0;
+        const int n = top + 1 < 32 ? top + 1 : 32;
+        for (int l = 0; l < n; l++) {                       // warp-uniform
+            const unsigned wl = __shfl_sync(kFull, w, l);
+            if (lane == l) mine = e;
+            e = (wl >> (4 * e)) & 0xFu;
+        }
+        if (lane < n) tmap[(int64_t)(top - lane) * kRecU32] = mine;
+        top -= 32;
     }
 }
 
@@ -546,11 +550,15 @@ static void launch_all(const ViterbiArgs& a, int64_t n_records, cudaStream_t st)
         cudaFuncSetAttribute(viterbi_sweep_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
+    prof_mark("viterbi_sweep", st);
     viterbi_sweep_kernel<S><<<a.n_slots / kWarpsPerCta, kWarpsPerCta * 32, smem, st>>>(a);
+    prof_mark("viterbi_tilemap", st);
     const int64_t map_threads = n_records * G;
     if (map_threads > 0) viterbi_tilemap_kernel<S><<<(unsigned)((map_threads + 255) / 256), 256, 0, st>>>(a, n_records);
     const int chains = a.n_samples * a.n_chains;
-    viterbi_trace_kernel<<<(chains + 127) / 128, 128, 0, st>>>(a, G);
+    prof_mark("viterbi_trace", st);
+    viterbi_trace_kernel<<<(chains + 3) / 4, 128, 0, st>>>(a, G);
+    prof_mark("viterbi_expand", st);
     viterbi_expand_kernel<S><<<(chains + 3) / 4, 128, 0, st>>>(a);
 }
 
@@ -566,7 +574,9 @@ int launch_viterbi(const ViterbiArgs& a, int64_t n_records, cudaStream_t st)
         case 7: launch_all<7>(a, n_records, st); break;
         default: return 0;
     }
+    prof_mark("viterbi_compact", st);
     viterbi_compact_kernel<<<(a.n_samples + 3) / 4, 128, 0, st>>>(a);
+    prof_mark(nullptr, st);
     return 5;
 }
 

@@ -47,6 +47,10 @@ EDB200_API const char *edb200_last_error(void);
 EDB200_API int         edb200_device_info(char *buf, int buflen, int *n_sms, int *cc_major, int *cc_minor);
 /* count of kernels launched by this library since the last reset (bench.py's gpu_launches) */
 EDB200_API int64_t     edb200_launch_count(int reset);
+/* per-kernel device times: while enabled, every kernel launch of this library is bracketed by CUDA events on its
+ * stream; edb200_profile_read synchronises and writes "name:launches:total_ms;..." (bench.py's roofline uses it) */
+EDB200_API int         edb200_profile(int enable);
+EDB200_API int         edb200_profile_read(char *buf, int buflen);
 /* page-locked host buffers for the host-pointer entry points (optional, speeds up the copies) */
 EDB200_API void       *edb200_host_alloc(size_t bytes);
 EDB200_API void        edb200_host_free(void *p);
@@ -136,6 +140,18 @@ EDB200_API int edb200_cohort_run_device(edb200_cohort *c, const edb200_batch *b,
 
 /* Same, HOST pointers: copies in, runs, copies the non-NULL outputs back, synchronises. */
 EDB200_API int edb200_cohort_run_host(edb200_cohort *c, const edb200_batch *b, int emission_mode);
+
+/* ---- forward pass and transition-probability grid (EXTENSION: the reference has neither) ----
+ * For every sample and every transition probability tp_grid[g] (CallCNVs matrix of R/class_definition.R:343-347
+ * built for that tp; tp_grid == NULL: the cohort's own matrix, n_grid ignored): the sum over chromosomes of the
+ * forward log-likelihood with the same framing as the Viterbi (dummy first/last observation, forced end in the
+ * normal state).  loglik: double[n_samples][n_grid]; best: int32[n_samples] index of the first maximiser (the
+ * per-sample MLE over the grid), may be NULL.  Definition: oracle/oracle.c:edo_forward_loglik; parity unpinned. */
+/* device pointers (b->ll filled by edb200_cohort_run_device; loglik, best on the device); tp_grid is a HOST pointer */
+EDB200_API int edb200_cohort_forward_device(edb200_cohort *c, const edb200_batch *b, const double *tp_grid, int32_t n_grid,
+                                            double *loglik, int32_t *best, void *cuda_stream);
+/* host pointers; runs over the likelihoods the most recent edb200_cohort_run_host left resident in HBM */
+EDB200_API int edb200_cohort_forward_last(edb200_cohort *c, const double *tp_grid, int32_t n_grid, double *loglik, int32_t *best);
 
 /* sticky status word of device-side warnings since the last call with reset != 0 (EDB200_WARN_*) */
 EDB200_API int edb200_status(int reset);

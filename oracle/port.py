@@ -167,3 +167,22 @@ def callcnvs_transitions(n_states, tp):
     out = np.empty(n_states * n_states)
     lib().edo_callcnvs_transitions(n_states, float(tp), out)
     return out.reshape((n_states, n_states), order="F")
+
+
+def tp_grid_loglik(ll_rows, offsets, start, end, tp_grid, expected_length=50000.0):
+    """Extension (no reference counterpart): forward log-likelihood of one sample summed over chromosomes for every
+    transition probability of the grid, with the CallCNVs framing.  ll_rows: n_bins x S in likelihood-column order.
+    Returns (loglik[n_grid], index of the first maximiser)."""
+    from . import framing
+    S = ll_rows.shape[1]
+    out = np.zeros(len(tp_grid))
+    for gi, tp in enumerate(tp_grid):
+        T = callcnvs_transitions(S, tp)
+        tot = 0.0
+        for c in range(len(offsets) - 1):
+            b0, b1 = int(offsets[c]), int(offsets[c + 1])
+            loc, pos = framing.frame_chromosome(ll_rows[b0:b1], np.asarray(start[b0:b1], float), np.asarray(end[b0:b1], float),
+                                                expected_length)
+            tot += forward_loglik(T, loc, pos, expected_length)
+        out[gi] = tot
+    return out, int(np.argmax(out))

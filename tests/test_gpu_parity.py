@@ -149,3 +149,165 @@ def test_pathological_phi_nan_pattern(edb, port):
     got = edb.get_loglike_matrix(phi, e, tot, obs, 1.0)
     assert np.isnan(want).sum() > 100
     assert_ll_close(got, want, rtol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------ extensions (parity unpinned)
+@pytest.mark.parametrize("S", [3, 5])
+def test_forward_grid_and_tp_mle_vs_oracle(edb, port, S):
+    """Forward log-likelihood over a transition-probability grid and its maximiser.  The reference
+    has no counterpart: the oracle port is the definition; tolerance 1e-10 relative."""
+    from exomedepth_b200 import synth
+    d = synth.cohort(4, n_bins=9000)
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=S)
+    res = co.run_host(d["observed"], d["reference"], d["phi"], d["expected"], call_cap=256)
+    grid = np.logspace(-7, -1, 7)
+    loglik, best = co.forward_last(grid)
+    assert loglik.shape == (4, grid.size)
+    for s in range(4):
+        want, arg = port.tp_grid_loglik(res["ll"][s].T, d["offsets"], d["start"], d["end"], grid)
+        np.testing.assert_allclose(loglik[s], want, rtol=1e-10, atol=0)
+        assert best[s] == arg
+    # the cohort's own matrix (tp = 1e-4) is the grid point 1e-4
+    own, _ = co.forward_last(None)
+    np.testing.assert_allclose(own[:, 0], loglik[:, 3], rtol=1e-12)
+    # forward likelihood bounds the Viterbi path likelihood from above: checked in test_oracle for the port
+
+
+def test_forward_handles_negative_distances_like_the_oracle(edb, port, exomecount, kat):
+    """ExomeCount bin starts are not monotone (SURVEY §8c NaN edge): negative transition terms contribute nothing."""
+    ec = exomecount
+    n = 6000
+    test = ec["Exome4"][:n].astype(np.int32)
+    reference = (ec["Exome1"] + ec["Exome2"] + ec["Exome3"])[:n].astype(np.int32)
+    assert np.any(np.diff(ec["start"][:n]) < 0)
+    co = edb.Cohort([0, n], ec["start"][:n], ec["end"][:n], n_states=3)
+    res = co.run_host(test[None, :], reference, [kat["kat3_phi"]], [kat["kat3_expected"]], call_cap=256)
+    grid = [1e-6, 1e-4, 1e-2]
+    loglik, best = co.forward_last(grid)
+    want, arg = port.tp_grid_loglik(res["ll"][0].T, [0, n], ec["start"][:n], ec["end"][:n], grid)
+    np.testing.assert_allclose(loglik[0], want, rtol=1e-10)
+    assert best[0] == arg
+
+
+# ------------------------------------------------------------------------------------------------ the .Call glue, driven like R would
+def test_call_glue_matches_reference_vectors(edb, refvec, kat):
+    """exomedepth_b200/csrc/r_glue.c compiled against the stand-in R API (oracle/stub): same SEXP in, same SEXP out."""
+    import ctypes as C
+    import os
+    from conftest import ROOT
+    from oracle import sexp
+    p = os.path.join(ROOT, "oracle", "_ref", "librglue_stub.so")
+    if not os.path.exists(p):
+        pytest.skip("oracle/_ref/librglue_stub.so not built")
+    api = sexp.CallApi(C.CDLL(p))
+    api.quiet(True)
+    args = [refvec[k] for k in ("em_phi", "em_expected", "em_total", "em_observed")]
+    assert_ll_close(api.get_loglike_matrix(*args, 1.0), refvec["em_ll_mix1"])
+    api.rprintf_count(reset=True)
+    assert_ll_close(api.get_loglike_matrix(*args, 0.4), refvec["em_ll_mix04"])
+    assert api.rprintf_count() >= 1                       # the mixture warning of CNV_estimate.cpp:61
+    for T, ll, pos, L, path, calls in hmm_cases(refvec):
+        got = api.c_hmm(T, ll, pos, L)
+        assert np.array_equal(got[0], path) and np.array_equal(got[1], calls)
+    k = kat["kat1"]
+    path, calls = api.c_hmm(np.array(k["T"]), np.array(k["loglik"], float), k["positions"], k["L"])
+    assert path.tolist() == k["path"] and calls.tolist() == k["calls"]
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def test_ragged_and_tiny_inputs(edb, port):
+    """One bin, one chromosome of one bin next to long ones, sample counts that do not fill a warp."""
+    rng = np.random.default_rng(3)
+    for S in (3, 5, 7):
+        for sizes in ([1], [1, 40, 1, 17], [33, 16, 15, 1]):
+            off = np.concatenate([[0], np.cumsum(sizes)])
+            nb = int(off[-1])
+            start = np.concatenate([np.sort(rng.integers(1, 10_000_000, n)) for n in sizes]).astype(np.int32)
+            end = (start + rng.integers(50, 300, nb)).astype(np.int32)
+            ref = rng.poisson(600, nb).astype(np.int32)
+            ns = 7
+            e = rng.uniform(0.1, 0.3, ns)
+            phi = rng.uniform(1e-3, 1e-2, ns)
+            obs = rng.binomial(ref[None, :] * 2, e[:, None] / (1 + e[:, None])).astype(np.int32)
+            obs[0, : nb // 2] //= 3                       # a deletion-like stretch
+            co = edb.Cohort(off, start, end, n_states=S)
+            res = co.run_host(obs, ref, phi, e, call_cap=64)
+            T = port.callcnvs_transitions(S, 1e-4)
+            odds = port.state_odds(S)
+            for s in range(ns):
+                want = port.emission(phi[s], e[s], obs[s] + ref, obs[s], odds)
+                assert_ll_close(res["ll"][s].T, want)
+                k = 0
+                for c in range(len(sizes)):
+                    b0, b1 = int(off[c]), int(off[c + 1])
+                    loc, pos = framing.frame_chromosome(res["ll"][s][:, b0:b1].T, start[b0:b1].astype(float), end[b0:b1].astype(float), 50000.0)
+                    path, calls = port.c_hmm(T, loc, pos, 50000.0)
+                    assert np.array_equal(res["path"][s, b0:b1], path[1:-1])
+                    for (sp, ep, typ, nex) in calls:
+                        assert res["calls"][s, k].tolist() == [sp - 1 + b0, ep - 1 + b0, typ, nex]
+                        k += 1
+                assert res["ncalls"][s] == k
+
+
+def test_hmm_special_values(edb, port):
+    """-Inf / NaN emissions, all-(-Inf) rows ("from = -1"), zero rows in T: path and calls as the oracle port."""
+    rng = np.random.default_rng(11)
+    for trial in range(6):
+        nobs = int(rng.integers(2, 90))
+        ll = rng.normal(-5, 3, (nobs, 3))
+        ll[rng.random((nobs, 3)) < 0.08] = -np.inf
+        if trial % 2:
+            ll[rng.random((nobs, 3)) < 0.03] = np.nan
+        if trial == 4:
+            ll[nobs // 2] = -np.inf
+        T = np.array([[0.98, 0.01, 0.01], [0.5, 0.5, 0.0], [0.5, 0.0, 0.5]]) if trial < 4 else np.eye(3)
+        pos = np.cumsum(rng.integers(-200, 3000, nobs)).astype(np.int32)
+        want = port.c_hmm(T, ll, pos, 5000.0)
+        got = edb.C_hmm(3, nobs, T, ll, pos, 5000.0)
+        assert np.array_equal(got[0], want[0]), trial
+        assert np.array_equal(got[1], want[1]), trial
+
+
+def test_call_capacity_overflow_is_reported(edb):
+    from exomedepth_b200 import _lib, synth
+    d = synth.cohort(3, n_bins=9000)
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=3)
+    full = co.run_host(d["observed"], d["reference"], d["phi"], d["expected"], call_cap=512, want_ll=False)
+    small = co.run_host(d["observed"], d["reference"], d["phi"], d["expected"], call_cap=4, want_ll=False)
+    assert small["status"] & _lib.WARN_CALLCAP
+    assert np.array_equal(small["ncalls"], full["ncalls"])            # the count stays honest
+    assert full["ncalls"].min() > 4
+
+
+def test_full_size_properties(edb):
+    """BASELINE.json configs[1] shape per GPU (scaled to 32 samples to keep the test short): size-independent
+    properties — idempotence, sample-order invariance, path/call consistency, zero rows."""
+    from exomedepth_b200 import synth
+    d = synth.cohort(32, n_bins=200_000)
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=5)
+    a = co.run_host(d["observed"], d["reference"], d["phi"], d["expected"], call_cap=1024)
+    b = co.run_host(d["observed"], d["reference"], d["phi"], d["expected"], call_cap=1024)
+    for k in ("ll", "path", "ncalls"):
+        assert np.array_equal(a[k], b[k])                                # deterministic
+    perm = np.random.default_rng(0).permutation(32)
+    c = co.run_host(d["observed"][perm], d["reference"], d["phi"][perm], d["expected"][perm], call_cap=1024)
+    assert np.array_equal(c["ll"], a["ll"][perm]) and np.array_equal(c["path"], a["path"][perm])
+    assert np.array_equal(c["ncalls"], a["ncalls"][perm])
+    zero = (d["observed"] == 0) & (d["reference"] == 0)[None, :]
+    assert np.all(a["ll"][np.broadcast_to(zero[:, None, :], a["ll"].shape)] == 0.0)
+    assert np.all(a["ll"] <= 0.0)                                        # a log-probability ratio of beta functions
+    # the call table is the run-length encoding of the path (no direct CNV->CNV change in this data)
+    for s in range(0, 32, 5):
+        p = a["path"][s].astype(np.int16)
+        calls = a["calls"][s, : a["ncalls"][s]]
+        assert a["ncalls"][s] <= 1024
+        inside = np.zeros(p.size, bool)
+        for sp, ep, typ, nex in calls:
+            seg = p[sp - 1: ep]
+            assert np.all(seg == typ) and nex == ep - sp + 1
+            inside[sp - 1: ep] = True
+        off = d["offsets"]
+        direct = sum(int(np.sum((p[off[c]:off[c + 1]][1:] != p[off[c]:off[c + 1]][:-1]) & (p[off[c]:off[c + 1]][1:] != 0) & (p[off[c]:off[c + 1]][:-1] != 0)))
+                     for c in range(len(off) - 1))
+        if direct == 0:
+            assert np.array_equal(inside, p != 0)
