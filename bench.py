@@ -171,33 +171,18 @@ def gpu_arm(a, rank, world):
 
     S, ns = N_STATES, a.samples
     # ---- shared exon-bin metadata + reference aggregate: built on rank 0, NCCL-broadcast to the others ------
+    from exomedepth_b200 import shard
+    arrays = None
     if rank == 0:
         off, start, end = synth.geometry(a.bins)
-        _, ref = synth.shared(start.size)
-        meta = torch.tensor([start.size, off.size], dtype=torch.int64, device=dev)
-    else:
-        meta = torch.zeros(2, dtype=torch.int64, device=dev)
-    if dist:
-        dist.broadcast(meta, 0)
-    nb, noff = int(meta[0]), int(meta[1])
-    geo = torch.empty(3 * nb + noff, dtype=torch.int64, device=dev)
-    if rank == 0:
-        geo.copy_(torch.from_numpy(np.concatenate([start, end, ref, off]).astype(np.int64)))
-    if dist:
-        dist.broadcast(geo, 0)
-    gh = geo.cpu().numpy()
-    start, end, ref, off = gh[:nb].astype(np.int32), gh[nb:2 * nb].astype(np.int32), gh[2 * nb:3 * nb].astype(np.int32), gh[3 * nb:]
+        arrays = dict(offsets=off, start=start, end=end, reference=synth.shared(start.size)[1])
+    shared = shard.broadcast_arrays(arrays, ["offsets", "start", "end", "reference"], dist, device=dev)
+    off, start, end, ref = shared["offsets"], shared["start"], shared["end"], shared["reference"]
+    nb = int(start.size)
     t0 = time.time()
-    co = edb.Cohort(off, start, end, n_states=S, transition_probability=TP, expected_cnv_length=CNV_LEN, build_table=(rank == 0))
+    # rank 0 builds the host-libm log-transition table; its bytes are broadcast so every rank holds the same bits
+    co = shard.make_cohort(shared, dist, device=dev, n_states=S, transition_probability=TP, expected_cnv_length=CNV_LEN)
     table_s = time.time() - t0
-    tbl = torch.empty(co.table_bytes() // 8, dtype=torch.float64, device=dev)
-    if rank == 0:
-        co.table_to(tbl)
-    if dist:
-        dist.broadcast(tbl, 0)          # the host-libm log-transition table: same bits on every rank
-    if rank != 0:
-        co.table_from(tbl)
-    torch.cuda.synchronize()
 
     # ---- this rank's samples (weak scaling: `ns` per GPU) -----------------------------------------------------
     obs_h = np.empty((ns, nb), np.int32)

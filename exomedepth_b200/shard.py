@@ -1,0 +1,104 @@
+"""Multi-GPU plumbing: samples shard across ranks, the shared exon-bin metadata is broadcast once.
+
+The hot path has no data-path collective: every sample is independent for the emission, every
+(sample, chromosome) chain is independent for the Viterbi.  One process per GPU; rank 0 builds the shared bin
+geometry, the reference aggregate and — on the host, with the host libm, so that every rank holds the same bits —
+the log-transition table, and broadcasts them (NCCL on GPUs, gloo in the CPU tests).  Results stay sharded; only
+the small call tables are gathered.  torch.distributed is plumbing here, nothing more.
+"""
+import numpy as np
+
+
+def shard_range(n_samples, rank, world):
+    """Contiguous block of ceil(n/world) samples for `rank` (the last ranks may get fewer, or none)."""
+    per = -(-n_samples // world)
+    lo = min(rank * per, n_samples)
+    return lo, min(lo + per, n_samples)
+
+
+def broadcast_arrays(arrays, names, dist=None, src=0, device=None):
+    """Broadcast a dict of numpy arrays from rank `src`.  `arrays` may be None on the other ranks; `names` is the
+    ordered key list every rank knows.  One size/dtype header, then one payload per array."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return {k: np.ascontiguousarray(arrays[k]) for k in names}
+    import torch
+    rank = dist.get_rank()
+    dev = device if device is not None else torch.device("cpu")
+    codes = {"int32": 0, "int64": 1, "float64": 2, "int8": 3, "uint8": 4}
+    inv = {v: k for k, v in codes.items()}
+    hdr = torch.zeros((len(names), 4), dtype=torch.int64)
+    if rank == src:
+        for i, k in enumerate(names):
+            a = np.ascontiguousarray(arrays[k])
+            assert a.ndim <= 2, k
+            shape = list(a.shape) + [1] * (2 - a.ndim)
+            hdr[i] = torch.tensor([codes[a.dtype.name], a.ndim, shape[0], shape[1]])
+    hdr = hdr.to(dev)
+    dist.broadcast(hdr, src)
+    hdr = hdr.cpu().numpy()
+    out = {}
+    for i, k in enumerate(names):
+        dt = np.dtype(inv[int(hdr[i, 0])])
+        ndim = int(hdr[i, 1])
+        shape = tuple(int(x) for x in hdr[i, 2:2 + ndim]) if ndim else ()
+        n = int(np.prod(shape)) if ndim else 1
+        if rank == src:
+            buf = torch.from_numpy(np.ascontiguousarray(arrays[k]).reshape(-1).view(np.uint8).copy()).to(dev)
+        else:
+            buf = torch.empty(n * dt.itemsize, dtype=torch.uint8, device=dev)
+        dist.broadcast(buf, src)
+        out[k] = buf.cpu().numpy().view(dt).reshape(shape).copy()
+    return out
+
+
+def gather_calls(calls, ncalls, first_sample, dist=None, dst=0, device=None):
+    """Gather the per-sample call tables of every rank on `dst`.
+
+    calls: int32[n_local, cap, 4], ncalls: int32[n_local]; first_sample: global index of this rank's first sample.
+    Returns on `dst` a list of (global sample index, int32[n, 4]) sorted by sample, elsewhere None."""
+    local = [(first_sample + s, np.asarray(calls[s, :min(int(ncalls[s]), calls.shape[1])], np.int32)) for s in range(len(ncalls))]
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = device if device is not None else torch.device("cpu")
+    flat = np.concatenate([np.concatenate([[g, c.shape[0]], c.reshape(-1)]) for g, c in local]).astype(np.int64) if local else np.zeros(0, np.int64)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([flat.size], dtype=torch.int64, device=dev))
+    most = max(int(s.item()) for s in sizes)
+    pad = torch.zeros(max(most, 1), dtype=torch.int64, device=dev)
+    pad[:flat.size] = torch.from_numpy(flat).to(dev)
+    bufs = [torch.zeros(max(most, 1), dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    if rank != dst:
+        return None
+    out = []
+    for r in range(world):
+        v = bufs[r].cpu().numpy()[:int(sizes[r].item())]
+        i = 0
+        while i < v.size:
+            g, n = int(v[i]), int(v[i + 1])
+            out.append((g, v[i + 2:i + 2 + 4 * n].reshape(n, 4).astype(np.int32)))
+            i += 2 + 4 * n
+    return sorted(out, key=lambda t: t[0])
+
+
+def make_cohort(shared, dist=None, device=None, **cohort_kwargs):
+    """Build this rank's Cohort from the broadcast shared metadata.  Rank 0 builds the host-libm log-transition
+    table; the other ranks receive its bytes (one broadcast), so every rank runs the Viterbi on identical terms."""
+    import torch
+
+    from .cohort import Cohort
+    multi = dist is not None and dist.is_initialized() and dist.get_world_size() > 1
+    rank = dist.get_rank() if multi else 0
+    co = Cohort(shared["offsets"], shared["start"], shared["end"], build_table=(rank == 0), **cohort_kwargs)
+    if multi:
+        tbl = torch.empty(co.table_bytes() // 8, dtype=torch.float64, device=device)
+        if rank == 0:
+            co.table_to(tbl)
+        torch.cuda.synchronize()
+        dist.broadcast(tbl, 0)
+        if rank != 0:
+            co.table_from(tbl)
+        torch.cuda.synchronize()
+    return co
