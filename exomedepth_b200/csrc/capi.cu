@@ -12,6 +12,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
+
 #include "../../include/exomedepth_b200.h"
 #include "host_tables.h"
 #include "kernels.cuh"
@@ -147,6 +149,33 @@ int check_kernel(const char* what)
 struct CallScratch {
     DevBuf phi, expected, total, observed, odds, ll, consts, lt, chains, bp, path, ccalls, cncalls, calls, ncalls, sched_begin, sched_items;
 } cs;
+
+// CUtensorMap of an emission matrix for the Viterbi sweep's 2-D TMA loads: rows = (sample, state) pairs of `cols`
+// doubles (row pitch `pitch` doubles), box = 16 bins x (32/S)*S rows, 128-byte swizzle, zero fill out of bounds.
+// cuTensorMapEncodeTiled is fetched through the runtime (no link-time dependency on libcuda).
+int make_ll_map(const double* ll, int64_t rows, int64_t cols, int64_t pitch, int S, CUtensorMap* out)
+{
+    typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Encode encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+            return fail(EDB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = (Encode)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * 8};
+    const cuuint32_t box[2] = {16, (cuuint32_t)((32 / S) * S)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ll), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(EDB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): ll %p rows %lld cols %lld pitch %lld", (int)r, (const void*)ll,
+                                       (long long)rows, (long long)cols, (long long)pitch);
+    return 0;
+}
 
 // build and upload the sweep schedule (host_tables.cpp: viterbi_schedule)
 int upload_schedule(const std::vector<int32_t>& nobs, int groups, int n_ctas, DevBuf& d_begin, DevBuf& d_items, cudaStream_t st)
@@ -475,6 +504,9 @@ int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const d
     a.ll = (const double*)cs.ll.p;
     a.ll_sample_stride = 0;
     a.ll_state_stride = nobs_p;
+    alignas(64) CUtensorMap ll_map;
+    if (int rc = make_ll_map(a.ll, S, nobs_p, nobs_p, S, &ll_map)) return rc;
+    a.ll_map = &ll_map;
     for (int j = 0; j < S; j++) a.perm[j] = j;
     if (int rc = upload_schedule(std::vector<int32_t>{nobs}, 1, 1, cs.sched_begin, cs.sched_items, st)) return rc;
     a.groups = 1;
@@ -665,6 +697,9 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
         a.ll = b->ll;
         a.ll_sample_stride = (int64_t)S * b->ll_stride;
         a.ll_state_stride = b->ll_stride;
+        alignas(64) CUtensorMap ll_map;
+        if (int rc = make_ll_map(b->ll, (int64_t)ns * S, b->ll_stride, b->ll_stride, S, &ll_map)) return rc;
+        a.ll_map = &ll_map;
         for (int j = 0; j < S; j++) a.perm[j] = c->perm[j];
         if (c->sched_groups != (int)groups) {
             std::vector<int32_t> nobs(c->n_chains);

@@ -81,9 +81,10 @@ struct ViterbiArgs {
     int n_slots;                  // sweep warps in the grid (a multiple of kViterbiWarpsPerCta)
     const int32_t* sched_begin;   // [n_slots + 1] first work item of each sweep warp (viterbi_schedule)
     const int32_t* sched_items;   // [2 * n_items] (chain, group) pairs
-    const double* ll;             // emission matrix, see LLView strides
+    const double* ll;             // emission matrix, see LLView strides; sample stride must be n_states * state stride
     int64_t ll_sample_stride;
     int64_t ll_state_stride;
+    const void* ll_map;           // host pointer to the CUtensorMap of ll (2-D: rows = sample x state, box 16 bins x 32/S*S rows, 128B swizzle)
     int perm[kMaxStates];         // HMM state j reads emission column perm[j] (CallCNVs: c(2,1,3))
     const double* lt;             // [rows + tile][lt_pitch] log-transition table (host libm), row = S(j) x pitch/S (k, padded)
     uint32_t* bp;                 // scratch records, viterbi_record_bytes() each: [chain tiles][group][tile]

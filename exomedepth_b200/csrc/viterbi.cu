@@ -31,12 +31,17 @@
 //   expand   one warp per chain fills in the per-observation states, the path bytes and the
 //            reference's call table, 32 tiles at a time;
 //   compact  concatenates the per-chromosome call tables per sample.
+#include <cuda.h>
+
 #include "kernels.cuh"
 
 namespace edb {
 
 constexpr int kTile = 16;          // observations per tile (one 128-byte line of an emission row)
-constexpr int kStages = 4;         // TMA ring depth for the transition rows
+// TMA ring depth for the transition rows (227 KB of shared memory per CTA: S = 7 rows are 448 bytes per observation)
+__host__ __device__ constexpr int lt_stages(int S) { return S >= 7 ? 2 : 4; }
+constexpr int kEmStages = 2;       // TMA ring depth for the emission tiles
+constexpr int kEmStageBytes = 4096;   // 32 rows x 128 bytes, 1024-byte aligned for the 128-byte swizzle
 constexpr int kWarpsPerCta = kViterbiWarpsPerCta;
 
 // transition row of destination state j: S doubles padded to an even count, so that rows are 16-byte aligned
@@ -80,6 +85,13 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src_g
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                  "l"(src_gmem), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// 2-D tiled TMA load: box (16 bins x G*S rows) of the emission matrix, 128-byte swizzled in shared memory
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
                  : "memory");
 }
 __device__ __forceinline__ double lds_f64(uint32_t addr)
@@ -193,45 +205,51 @@ __device__ __forceinline__ int64_t record_base(const ViterbiArgs& a, int chain, 
 // =========================================================================================== sweep
 template <int S>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 1)
-viterbi_sweep_kernel(ViterbiArgs a)
+viterbi_sweep_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
 {
     constexpr int G = 32 / S;
     constexpr int LTP = lt_pitch(S);
     constexpr int LTJ = lt_jstride(S);
+    constexpr int kStages = lt_stages(S);
     constexpr unsigned kTileBytes = kTile * LTP * 8;
     constexpr unsigned kFull = 0xffffffffu;
-    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr unsigned kEmBox = G * S * kTile * 8;          // bytes one emission tile delivers
+    extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t ring = smem_u32(smem) + (uint32_t)warp * kStages * kTileBytes;                                   // [stage][obs][LTP] doubles
-    const uint32_t bars = smem_u32(smem) + (uint32_t)kWarpsPerCta * kStages * kTileBytes + (uint32_t)warp * kStages * 8;   // [stage] mbarriers
+    // [emission tiles: warp x stage x 4 KB][transition rows: warp x stage x obs x LTP doubles][mbarriers]
+    const uint32_t em_ring = smem_u32(smem) + (uint32_t)warp * kEmStages * kEmStageBytes;
+    const uint32_t ring = smem_u32(smem) + (uint32_t)kWarpsPerCta * kEmStages * kEmStageBytes + (uint32_t)warp * kStages * kTileBytes;
+    const uint32_t bars = smem_u32(smem) + (uint32_t)kWarpsPerCta * (kEmStages * kEmStageBytes + kStages * kTileBytes) +
+                          (uint32_t)warp * (kStages + kEmStages) * 8;
+    const uint32_t em_bars = bars + kStages * 8;
 
     int g = lane / S;
     const int j = lane - g * S;
     if (g >= G) g = G - 1;                                  // spare lanes shadow lanes of the last chain
     const int src0 = g * S;
     const double tail = j == 0 ? 0.0 : a.tail_other;
+    // this lane's row of the emission tile: the box holds the G*S rows of the warp's chains in likelihood-column
+    // order; chunk c (16 bytes) of row r sits at chunk c ^ (r & 7) (128-byte swizzle): conflict-free 128-bit reads
+    const int em_r = g * S + a.perm[j];
+    const uint32_t em_row_off = (uint32_t)em_r * 128u, em_x = (uint32_t)(em_r & 7);
 
     if (lane == 0) {
-        for (int s = 0; s < kStages; s++) mbar_init(bars + 8u * s, 1);
+        for (int s = 0; s < kStages + kEmStages; s++) mbar_init(bars + 8u * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    unsigned ring_seq = 0;                                  // tiles pushed through this warp's ring so far (stage / parity bookkeeping)
+    unsigned ring_seq = 0;                                  // tiles pushed through this warp's rings so far (stage / parity bookkeeping)
 
     // each warp is an independent pipeline over its own list of work items: no CTA barrier below
     const int slot = blockIdx.x * kWarpsPerCta + warp;
     for (int it = a.sched_begin[slot]; it < a.sched_begin[slot + 1]; it++) {
         const int chain = a.sched_items[2 * it], grp = a.sched_items[2 * it + 1];
-        int sample = grp * G + g;
-        if (sample >= a.n_samples) sample = a.n_samples - 1;    // chains past the batch shadow the last sample
-
         const ChainDesc cd = a.chains[chain];
         const int nobs = cd.nobs;
         // tiles follow the 128-byte lines of the emission rows: tile t covers observations i with
         // (em_off + i) / 16 == t_first + t
         const int64_t t_first = (cd.em_off + 1) >> 4;
         const int n_tiles = chain_tiles(cd);
-        const double* __restrict__ em_row = a.ll + sample * a.ll_sample_stride + a.perm[j] * a.ll_state_stride;
         const double* __restrict__ lt_base = a.lt + cd.lt_row0 * LTP;
         uint2* bp = reinterpret_cast<uint2*>(a.bp) + record_base(a, chain, grp, n_tiles) * kRecU2;
 
@@ -244,24 +262,38 @@ viterbi_sweep_kernel(ViterbiArgs a)
             mbar_expect_tx(bars + 8u * st, bytes);
             tma_load_1d(ring + (uint32_t)(st * kTile + (r0 - i0)) * LTP * 8, lt_base + (int64_t)r0 * LTP, bytes, bars + 8u * st);
         };
-        if (lane == 0)
+        // emission tile t: one 2-D TMA box (16 bins x the G*S rows of this warp's chains; rows past the batch and
+        // columns past the matrix are zero-filled by the TMA unit)
+        auto issue_em = [&](int t) {
+            const int st = (ring_seq + t) % kEmStages;
+            mbar_expect_tx(em_bars + 8u * st, kEmBox);
+            tma_load_2d(em_ring + (uint32_t)st * kEmStageBytes, &ll_map, (int)((t_first + t) << 4), grp * G * S, em_bars + 8u * st);
+        };
+        if (lane == 0) {
+            for (int t = 0; t < kEmStages && t < n_tiles; t++) issue_em(t);
             for (int t = 0; t < kStages && t < n_tiles; t++) issue_lt(t);
+        }
 
-        // ------------------------------------------------------------ emission prefetch (registers)
+        // ------------------------------------------------------------ emission prefetch (shared memory -> registers)
         double em_nxt[kTile];
 #pragma unroll
         for (int q = 0; q < kTile; q++) em_nxt[q] = 0.0;
         auto load_em = [&](int t) {
-            // tiles holding only the dummy last observation have no emission row behind them
-            if (tile_i0(t) <= cd.n_em) {
-                const double2* p = reinterpret_cast<const double2*>(em_row + ((t_first + t) << 4));
+            const unsigned seq = ring_seq + t;
+            const int st = seq % kEmStages;
+            mbar_wait(em_bars + 8u * st, (seq / kEmStages) & 1);
+            const uint32_t base = em_ring + (uint32_t)st * kEmStageBytes + em_row_off;
 #pragma unroll
-                for (int q = 0; q < kTile / 2; q++) {
-                    const double2 v = __ldcs(p + q);      // streamed once: evict-first
-                    em_nxt[2 * q] = v.x;
-                    em_nxt[2 * q + 1] = v.y;
-                }
+            for (int c = 0; c < kTile / 2; c++) {
+                const double2 v = lds_f64x2(base + (((uint32_t)c ^ em_x) << 4));
+                em_nxt[2 * c] = v.x;
+                em_nxt[2 * c + 1] = v.y;
             }
+        };
+        // the stage tile t was read from is free once its values are in registers: refill it two tiles ahead
+        auto refill_em = [&](int t) {
+            __syncwarp();
+            if (lane == 0 && t + kEmStages < n_tiles) issue_em(t + kEmStages);
         };
         // NaN or +-Inf somewhere in the prefetched tile (integer test on the exponent field: off the FP64 pipe)
         auto nonfinite_nxt = [&]() -> bool {
@@ -272,6 +304,7 @@ viterbi_sweep_kernel(ViterbiArgs a)
         };
         if (n_tiles > 0) load_em(0);
         bool special_nxt = n_tiles > 0 && nonfinite_nxt();
+        if (n_tiles > 0) refill_em(0);
         bool lt_ready = false;
 
         double V = j == 0 ? 0.0 : -HUGE_VAL;                // hmm.cpp:46-52
@@ -329,7 +362,8 @@ viterbi_sweep_kernel(ViterbiArgs a)
             if (lane == 0 && t + kStages < n_tiles) issue_lt(t + kStages);
             lt_ready = false;
             if (t + 1 < n_tiles) {
-                special_nxt = nonfinite_nxt();
+                special_nxt = nonfinite_nxt();              // consumes the registers: the shared-memory reads are complete
+                refill_em(t + 1);
                 lt_ready = try_wait_once(bars + 8u * ((seq + 1) % kStages), ((seq + 1) / kStages) & 1);
             }
         }
@@ -535,7 +569,10 @@ __global__ void viterbi_compact_kernel(ViterbiArgs a)
     if (lane == 0) a.ncalls[sample] = n;
 }
 
-size_t viterbi_smem_bytes(int S) { return (size_t)kWarpsPerCta * kStages * (kTile * lt_pitch(S) * 8 + 8); }
+size_t viterbi_smem_bytes(int S)
+{
+    return (size_t)kWarpsPerCta * (kEmStages * kEmStageBytes + lt_stages(S) * (kTile * lt_pitch(S) * 8) + (lt_stages(S) + kEmStages) * 8);
+}
 int viterbi_lt_pitch(int S) { return lt_pitch(S); }
 int viterbi_tile() { return kTile; }
 size_t viterbi_record_bytes() { return (size_t)kRecU2 * 8; }
@@ -551,7 +588,7 @@ static void launch_all(const ViterbiArgs& a, int64_t n_records, cudaStream_t st)
         configured = true;
     }
     prof_mark("viterbi_sweep", st);
-    viterbi_sweep_kernel<S><<<a.n_slots / kWarpsPerCta, kWarpsPerCta * 32, smem, st>>>(a);
+    viterbi_sweep_kernel<S><<<a.n_slots / kWarpsPerCta, kWarpsPerCta * 32, smem, st>>>(a, *reinterpret_cast<const CUtensorMap*>(a.ll_map));
     prof_mark("viterbi_tilemap", st);
     const int64_t map_threads = n_records * G;
     if (map_threads > 0) viterbi_tilemap_kernel<S><<<(unsigned)((map_threads + 255) / 256), 256, 0, st>>>(a, n_records);
