@@ -39,8 +39,8 @@ namespace edb {
 
 constexpr int kTile = 16;          // observations per tile (one 128-byte line of an emission row)
 // TMA ring depth for the transition rows (227 KB of shared memory per CTA: S = 7 rows are 448 bytes per observation)
-__host__ __device__ constexpr int lt_stages(int S) { return S >= 7 ? 2 : 4; }
-constexpr int kEmStages = 2;       // TMA ring depth for the emission tiles
+__host__ __device__ constexpr int lt_stages(int S) { return S >= 7 ? 2 : S == 6 ? 3 : 4; }
+constexpr int kEmStages = 3;       // TMA ring depth for the emission tiles
 constexpr int kEmStageBytes = 4096;   // 32 rows x 128 bytes, 1024-byte aligned for the 128-byte swizzle
 constexpr int kWarpsPerCta = kViterbiWarpsPerCta;
 
@@ -127,7 +127,7 @@ struct Cand {
 };
 
 // exchange V between the chain's S lanes, form the candidates and reduce them to the new V
-template <int S, bool SPECIAL>
+template <int S>
 __device__ __forceinline__ void sweep_step(double em, uint32_t lt_qj, int src0, double& V, Cand<S>& cd)
 {
     double lt[S + 1];                                       // this lane's transition row: independent of V, issued first
@@ -145,7 +145,7 @@ __device__ __forceinline__ void sweep_step(double em, uint32_t lt_qj, int src0, 
         lo[k] = shfl_idx(vlo, src0 + k);
         hi[k] = shfl_idx(vhi, src0 + k);
     }
-    const double em_s = (SPECIAL && em != em) ? -HUGE_VAL : em;
+    const double em_s = em != em ? -HUGE_VAL : em;         // depends on the emission only: off the chain through V
     double m[S];
 #pragma unroll
     for (int k = 0; k < S; k++) {
@@ -172,14 +172,14 @@ __device__ __forceinline__ void sweep_step(double em, uint32_t lt_qj, int src0, 
 }
 
 // back-pointer of the step whose candidates are in `cd` and whose maximum is V
-template <int S, bool SPECIAL>
+template <int S>
 __device__ __forceinline__ unsigned sweep_arg(const Cand<S>& cd, double V, double em)
 {
     unsigned arg = S - 1;
 #pragma unroll
     for (int k = S - 2; k >= 0; k--) arg = cd.c[k] == V ? (unsigned)k : arg;
     if (!(V > -HUGE_VAL)) arg = 7u;                         // 7 encodes "from = -1" (hmm.cpp:60)
-    if (SPECIAL && em == -HUGE_VAL) arg = 0u;               // hmm.cpp:87
+    if (em == -HUGE_VAL) arg = 0u;                          // hmm.cpp:87
     return arg;
 }
 
@@ -273,72 +273,40 @@ viterbi_sweep_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
             for (int t = 0; t < kEmStages && t < n_tiles; t++) issue_em(t);
             for (int t = 0; t < kStages && t < n_tiles; t++) issue_lt(t);
         }
-
-        // ------------------------------------------------------------ emission prefetch (shared memory -> registers)
-        double em_nxt[kTile];
-#pragma unroll
-        for (int q = 0; q < kTile; q++) em_nxt[q] = 0.0;
-        auto load_em = [&](int t) {
-            const unsigned seq = ring_seq + t;
-            const int st = seq % kEmStages;
-            mbar_wait(em_bars + 8u * st, (seq / kEmStages) & 1);
-            const uint32_t base = em_ring + (uint32_t)st * kEmStageBytes + em_row_off;
-#pragma unroll
-            for (int c = 0; c < kTile / 2; c++) {
-                const double2 v = lds_f64x2(base + (((uint32_t)c ^ em_x) << 4));
-                em_nxt[2 * c] = v.x;
-                em_nxt[2 * c + 1] = v.y;
-            }
-        };
-        // the stage tile t was read from is free once its values are in registers: refill it two tiles ahead
-        auto refill_em = [&](int t) {
-            __syncwarp();
-            if (lane == 0 && t + kEmStages < n_tiles) issue_em(t + kEmStages);
-        };
-        // NaN or +-Inf somewhere in the prefetched tile (integer test on the exponent field: off the FP64 pipe)
-        auto nonfinite_nxt = [&]() -> bool {
-            unsigned m = 0;
-#pragma unroll
-            for (int q = 0; q < kTile; q++) m = max(m, (unsigned)__double2hiint(em_nxt[q]) & 0x7fffffffu);
-            return m >= 0x7ff00000u;
-        };
-        if (n_tiles > 0) load_em(0);
-        bool special_nxt = n_tiles > 0 && nonfinite_nxt();
-        if (n_tiles > 0) refill_em(0);
-        bool lt_ready = false;
+        bool lt_ready = false, em_ready = false;
+        uint2* bp_t = bp + lane;
 
         double V = j == 0 ? 0.0 : -HUGE_VAL;                // hmm.cpp:46-52
 
-        for (int t = 0; t < n_tiles; t++) {
-            double em_cur[kTile];
-#pragma unroll
-            for (int q = 0; q < kTile; q++) em_cur[q] = em_nxt[q];
-            const bool special = special_nxt;
-            if (t + 1 < n_tiles) load_em(t + 1);
+        for (int t = 0; t < n_tiles; t++, bp_t += kRecU2) {
             const unsigned seq = ring_seq + t;
-            const int st = seq % kStages;
+            const int st = seq % kStages, est = seq % kEmStages;
             if (!lt_ready) mbar_wait(bars + 8u * st, (seq / kStages) & 1);
+            if (!em_ready) mbar_wait(em_bars + 8u * est, (seq / kEmStages) & 1);
             const uint32_t ltt = ring + (uint32_t)(st * kTile * LTP + j * LTJ) * 8;
+            // element q of this lane's emission row: the 128-byte swizzle is an XOR on address bits 4-6
+            const uint32_t emt = em_ring + (uint32_t)est * kEmStageBytes + em_row_off + (em_x << 4);
             const int i0 = tile_i0(t);
             unsigned lo = 0, hi = 0;                        // 16 back-pointers of this lane, 4 bits each
-            const bool whole = i0 >= 1 && i0 + kTile - 1 <= cd.n_em;   // tile entirely inside the real observations
-            if (whole && !__any_sync(kFull, special)) {
+            if (i0 >= 1 && i0 + kTile - 1 <= cd.n_em) {     // tile entirely inside the real observations
                 Cand<S> cnd;
-                double Vq = V;
+                double Vq = V, em_prev = 0.0;
 #pragma unroll
                 for (int q = 0; q < kTile; q++) {
                     Cand<S> nxt;
                     double Vn = Vq;
-                    sweep_step<S, false>(em_cur[q], ltt + q * LTP * 8, src0, Vn, nxt);
+                    const double em = lds_f64(emt ^ (uint32_t)(q << 3));
+                    sweep_step<S>(em, ltt + q * LTP * 8, src0, Vn, nxt);
                     if (q > 0) {                            // the previous step's back-pointer, in the shadow of this step's exchange
-                        const unsigned arg = sweep_arg<S, false>(cnd, Vq, 0.0);
+                        const unsigned arg = sweep_arg<S>(cnd, Vq, em_prev);
                         if (q - 1 < 8) lo |= arg << (4 * (q - 1));
                         else hi |= arg << (4 * (q - 9));
                     }
                     cnd = nxt;
                     Vq = Vn;
+                    em_prev = em;
                 }
-                hi |= sweep_arg<S, false>(cnd, Vq, 0.0) << 28;
+                hi |= sweep_arg<S>(cnd, Vq, em_prev) << 28;
                 V = Vq;
             } else {
 #pragma unroll 1
@@ -346,25 +314,25 @@ viterbi_sweep_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
                     const int i = i0 + q;
                     unsigned arg = (unsigned)j;             // observations outside the chain: identity step
                     if (i >= 1 && i < nobs) {               // warp-uniform
-                        double em = tail;
-#pragma unroll
-                        for (int r = 0; r < kTile; r++) em = (r == q && i <= cd.n_em) ? em_cur[r] : em;
+                        const double em = i <= cd.n_em ? lds_f64(emt ^ (uint32_t)(q << 3)) : tail;
                         Cand<S> cnd;
-                        sweep_step<S, true>(em, ltt + q * LTP * 8, src0, V, cnd);
-                        arg = sweep_arg<S, true>(cnd, V, em);
+                        sweep_step<S>(em, ltt + q * LTP * 8, src0, V, cnd);
+                        arg = sweep_arg<S>(cnd, V, em);
                     }
                     if (q < 8) lo |= arg << (4 * q);
                     else hi |= arg << (4 * (q - 8));
                 }
             }
-            bp[(int64_t)t * kRecU2 + lane] = make_uint2(lo, hi);
-            __syncwarp();
-            if (lane == 0 && t + kStages < n_tiles) issue_lt(t + kStages);
-            lt_ready = false;
+            *bp_t = make_uint2(lo, hi);
+            __syncwarp();                                   // every lane is done with both stages: refill them
+            if (lane == 0) {
+                if (t + kStages < n_tiles) issue_lt(t + kStages);
+                if (t + kEmStages < n_tiles) issue_em(t + kEmStages);
+            }
+            lt_ready = em_ready = false;
             if (t + 1 < n_tiles) {
-                special_nxt = nonfinite_nxt();              // consumes the registers: the shared-memory reads are complete
-                refill_em(t + 1);
                 lt_ready = try_wait_once(bars + 8u * ((seq + 1) % kStages), ((seq + 1) / kStages) & 1);
+                em_ready = try_wait_once(em_bars + 8u * ((seq + 1) % kEmStages), ((seq + 1) / kEmStages) & 1);
             }
         }
         ring_seq += (unsigned)n_tiles;
