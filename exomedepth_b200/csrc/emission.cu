@@ -240,33 +240,57 @@ emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n
         const int is_total = c.other_is_total;
         const int K = dims.K, R = dims.R, N = dims.N;
 
-        auto cell = [&](int obs, int oth, int64_t b) -> double {
+        // one cell: three gathers; out-of-lattice cells are flagged, not branched on, so that the twelve gathers
+        // of a thread's four cells are in flight together (loads are clamped and unconditional)
+        auto cell = [&](int obs, int oth, bool& in) -> double {
             const int tot = is_total ? oth : obs + oth;
             const int r = tot - obs;
-            // unsigned compares fold the >= 0 checks in; loads are clamped and unconditional so that the
-            // twelve gathers of a thread's four cells can be in flight together
-            const bool in = (unsigned)obs < (unsigned)K && (unsigned)r < (unsigned)R && (unsigned)tot < (unsigned)N;
-            const double v = (G1[min((unsigned)obs, (unsigned)K - 1)] + G2[min((unsigned)r, (unsigned)R - 1)]) -
-                             G3[min((unsigned)tot, (unsigned)N - 1)];
-            if (!in) {
-                const int q = atomicAdd(cold_n, 1);
-                if (q < kColdCap) cold[q] = (int)b;
-            }
-            return v;
+            // unsigned compares fold the >= 0 checks in
+            in = (unsigned)obs < (unsigned)K && (unsigned)r < (unsigned)R && (unsigned)tot < (unsigned)N;
+            return (G1[min((unsigned)obs, (unsigned)K - 1)] + G2[min((unsigned)r, (unsigned)R - 1)]) -
+                   G3[min((unsigned)tot, (unsigned)N - 1)];
+        };
+        auto park = [&](int64_t b) {
+            const int q = atomicAdd(cold_n, 1);
+            if (q < kColdCap) cold[q] = (int)b;
         };
 
-        for (int64_t b = (int64_t)threadIdx.x * 4; b < n4; b += (int64_t)blockDim.x * 4) {
-            const int4 ko = __ldg(reinterpret_cast<const int4*>(obs_row + b));
-            const int4 oo = __ldg(reinterpret_cast<const int4*>(oth_row + b));
+        // the counts of the next iteration are requested before the gathers of this one
+        const int64_t stride = (int64_t)blockDim.x * 4;
+        int64_t b = (int64_t)threadIdx.x * 4;
+        int4 ko = make_int4(0, 0, 0, 0), oo = ko;
+        if (b < n4) {
+            ko = __ldg(reinterpret_cast<const int4*>(obs_row + b));
+            oo = __ldg(reinterpret_cast<const int4*>(oth_row + b));
+        }
+        for (; b < n4; b += stride) {
+            int4 kn = make_int4(0, 0, 0, 0), on = kn;
+            if (b + stride < n4) {
+                kn = __ldg(reinterpret_cast<const int4*>(obs_row + b + stride));
+                on = __ldg(reinterpret_cast<const int4*>(oth_row + b + stride));
+            }
+            bool i0, i1, i2, i3;
             double2 v0, v1;
-            v0.x = cell(ko.x, oo.x, b);
-            v0.y = cell(ko.y, oo.y, b + 1);
-            v1.x = cell(ko.z, oo.z, b + 2);
-            v1.y = cell(ko.w, oo.w, b + 3);
+            v0.x = cell(ko.x, oo.x, i0);
+            v0.y = cell(ko.y, oo.y, i1);
+            v1.x = cell(ko.z, oo.z, i2);
+            v1.y = cell(ko.w, oo.w, i3);
             __stcs(reinterpret_cast<double2*>(o + b), v0);        // streaming stores: ll is write-once
             __stcs(reinterpret_cast<double2*>(o + b + 2), v1);
+            if (!(i0 && i1 && i2 && i3)) {                        // rare
+                if (!i0) park(b);
+                if (!i1) park(b + 1);
+                if (!i2) park(b + 2);
+                if (!i3) park(b + 3);
+            }
+            ko = kn;
+            oo = on;
         }
-        for (int64_t b = n4 + threadIdx.x; b < n_bins; b += blockDim.x) o[b] = cell(obs_row[b], oth_row[b], b);
+        for (int64_t bt = n4 + threadIdx.x; bt < n_bins; bt += blockDim.x) {
+            bool in;
+            o[bt] = cell(obs_row[bt], oth_row[bt], in);
+            if (!in) park(bt);
+        }
         __syncthreads();
         const int n_cold = *cold_n;
         if (n_cold > kColdCap) rescan_cold(scp, c, sample, n_bins, dims, o, flags);     // lattice far too small for this sample
