@@ -38,7 +38,8 @@ class Batch(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("observed", C.c_void_p), ("obs_stride", C.c_int64),
                 ("reference", C.c_void_p), ("ref_stride", C.c_int64), ("phi", C.c_void_p),
                 ("expected", C.c_void_p), ("ll", C.c_void_p), ("ll_stride", C.c_int64), ("path", C.c_void_p),
-                ("path_stride", C.c_int64), ("calls", C.c_void_p), ("ncalls", C.c_void_p), ("call_cap", C.c_int32)]
+                ("path_stride", C.c_int64), ("calls", C.c_void_p), ("ncalls", C.c_void_p), ("call_cap", C.c_int32),
+                ("call_stats", C.c_void_p), ("cor", C.c_void_p)]
 
 
 _lib = None

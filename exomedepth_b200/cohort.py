@@ -61,9 +61,12 @@ class Cohort:
 
     # ---- host buffers ---------------------------------------------------------------------------
     def run_host(self, observed, reference, phi, expected, want_ll=True, want_path=True, call_cap=512,
-                 mode=_lib.EMISSION_AUTO, out=None):
+                 mode=_lib.EMISSION_AUTO, out=None, want_stats=False):
         """observed int32[n_samples, n_bins]; reference int32[n_bins] (shared) or [n_samples, n_bins];
-        phi, expected float64[n_samples].  Returns dict(ll [n,S,bins], path int8 [n,bins], calls, ncalls, status)."""
+        phi, expected float64[n_samples].  Returns dict(ll [n,S,bins], path int8 [n,bins], calls, ncalls, status);
+        with want_stats also call_stats float64[n, call_cap, 3] (per call: sum of ll[,type] - ll[,normal],
+        sum of total*expected, sum of test; R/class_definition.R:393-400) and cor float64[n] (:338), both computed
+        on the device — the likelihood matrix then only crosses PCIe if want_ll is set."""
         observed = np.ascontiguousarray(np.asarray(observed, np.int32))
         reference = np.ascontiguousarray(np.asarray(reference, np.int32))
         ns = observed.shape[0]
@@ -84,11 +87,52 @@ class Cohort:
         ncalls = out.get("ncalls")
         if ncalls is None:
             ncalls = np.zeros(ns, np.int32)
+        stats = cor = None
+        if want_stats:
+            stats = out.get("call_stats")
+            if stats is None:
+                stats = np.zeros((ns, call_cap, 3))
+            cor = out.get("cor")
+            if cor is None:
+                cor = np.zeros(ns)
         b = _lib.Batch(ns, _ptr(observed), nb, _ptr(reference), 0 if reference.ndim == 1 else nb, _ptr(phi),
-                       _ptr(expected), _ptr(ll), nb, _ptr(path), nb, _ptr(calls), _ptr(ncalls), call_cap)
+                       _ptr(expected), _ptr(ll), nb, _ptr(path), nb, _ptr(calls), _ptr(ncalls), call_cap,
+                       _ptr(stats), _ptr(cor))
         rc = _lib.check(self.lib.edb200_cohort_run_host(self.handle, C.byref(b), mode), "edb200_cohort_run_host")
         self._last_ns = ns
-        return dict(ll=ll, path=path, calls=calls, ncalls=ncalls, status=rc)
+        return dict(ll=ll, path=path, calls=calls, ncalls=ncalls, status=rc, call_stats=stats, cor=cor)
+
+    def call_cnvs(self, observed, reference, phi, expected, chromosome_names=None, call_cap=512,
+                  mode=_lib.EMISSION_AUTO, want_ll=False, want_path=False):
+        """`new('ExomeDepth')`'s likelihood step + `CallCNVs` for every sample of the cohort
+        (R/class_definition.R:184-189, 311-419): returns dict(CNV_calls = one list of rows per sample with the columns
+        of x@CNV.calls, cor = x@cor.test.reference per sample, ll / path when asked for).  The per-call sums are
+        taken on the device (callcnvs.cu); only signif(), as.integer() and the id strings are done here."""
+        from .api import _signif
+        import math
+        res = self.run_host(observed, reference, phi, expected, want_ll=want_ll, want_path=want_path,
+                            call_cap=call_cap, mode=mode, want_stats=True)
+        names = chromosome_names if chromosome_names is not None else [str(c + 1) for c in range(self.n_chains)]
+        log10e = math.log10(math.e)
+        out = []
+        for s in range(res["ncalls"].size):
+            n = int(res["ncalls"][s])
+            if n > call_cap:
+                raise _lib.EDB200Error(f"sample {s}: {n} calls exceed call_cap={call_cap}")
+            rows = []
+            for k in range(n):
+                sp, ep, typ, nex = (int(v) for v in res["calls"][s, k])
+                bf, rexp, robs = (float(v) for v in res["call_stats"][s, k])
+                chrom = str(names[int(np.searchsorted(self.chain_offsets, sp - 1, side="right")) - 1])
+                st, en = float(self.start[sp - 1]), float(self.end[ep - 1])
+                rexp_i = int(rexp) if math.isfinite(rexp) else 0                       # as.integer()
+                rows.append(dict(start_p=sp, end_p=ep, type=typ, nexons=nex, start=st, end=en, chromosome=chrom,
+                                 id=f"chr{chrom}:{int(st)}-{int(en)}".replace("chrchr", "chr"),
+                                 BF=_signif(log10e * bf, 3), reads_expected=rexp_i, reads_observed=robs,
+                                 reads_ratio=_signif(robs / rexp_i, 3) if rexp_i else float("inf")))
+            out.append(rows)
+        return dict(CNV_calls=out, cor=res["cor"], ll=res["ll"], path=res["path"], status=res["status"],
+                    calls=res["calls"], ncalls=res["ncalls"], call_stats=res["call_stats"])
 
     def forward_last(self, tp_grid=None):
         """Forward log-likelihood per sample and grid point over the likelihoods of the most recent run_host call
@@ -108,7 +152,7 @@ class Cohort:
 
     # ---- device tensors (torch) -----------------------------------------------------------------
     def run_device(self, observed, reference, phi, expected, ll, path=None, calls=None, ncalls=None,
-                   what=3, mode=_lib.EMISSION_AUTO, stream=None):
+                   what=3, mode=_lib.EMISSION_AUTO, stream=None, call_stats=None, cor=None):
         """All arguments are CUDA tensors on this cohort's device; enqueues on `stream` (default: torch's
         current stream) without synchronising."""
         import torch
@@ -118,7 +162,8 @@ class Cohort:
                        0 if reference.dim() == 1 else reference.stride(0), phi.data_ptr(), expected.data_ptr(),
                        ll.data_ptr(), ll.stride(1), path.data_ptr() if path is not None else None,
                        path.stride(0) if path is not None else 0, calls.data_ptr() if calls is not None else None,
-                       ncalls.data_ptr() if ncalls is not None else None, calls.shape[1] if calls is not None else 0)
+                       ncalls.data_ptr() if ncalls is not None else None, calls.shape[1] if calls is not None else 0,
+                       call_stats.data_ptr() if call_stats is not None else None, cor.data_ptr() if cor is not None else None)
         return _lib.check(self.lib.edb200_cohort_run_device(self.handle, C.byref(b), what, mode, st),
                           "edb200_cohort_run_device")
 

@@ -214,7 +214,7 @@ struct edb200_cohort {
     DevBuf consts, bp, ccalls, cncalls, maxima, fw_grid, fw_chain, fw_out, fw_best;
     int last_host_samples = 0;           // samples whose likelihoods the last host-pointer run left in h_ll
     // host-mode staging
-    DevBuf h_obs, h_ref, h_phi, h_exp, h_ll, h_path, h_calls, h_ncalls;
+    DevBuf h_obs, h_ref, h_phi, h_exp, h_ll, h_path, h_calls, h_ncalls, h_stats, h_cor;
 };
 
 extern "C" {
@@ -638,7 +638,7 @@ void edb200_cohort_destroy(edb200_cohort* c)
     std::lock_guard<std::mutex> lk(g_mu);
     cudaDeviceSynchronize();
     DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->tile_base, &c->decay, &c->fw_grid, &c->fw_chain, &c->fw_out, &c->fw_best, &c->sched_begin, &c->sched_items, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->maxima,
-                     &c->h_obs, &c->h_ref, &c->h_phi, &c->h_exp, &c->h_ll, &c->h_path, &c->h_calls, &c->h_ncalls};
+                     &c->h_obs, &c->h_ref, &c->h_phi, &c->h_exp, &c->h_ll, &c->h_path, &c->h_calls, &c->h_ncalls, &c->h_stats, &c->h_cor};
     for (DevBuf* b : all) release(*b);
     delete c;
 }
@@ -727,6 +727,26 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
         g_launches += edb::launch_viterbi(a, groups * c->total_tiles, st);
         if (int rc = check_kernel("viterbi")) return rc;
     }
+    if ((what & 4) && (b->call_stats || b->cor)) {
+        if (!b->calls || !b->ncalls || b->call_cap < 1) return fail(EDB200_ERR_ARG, "CallCNVs post-processing needs the calls / ncalls of a Viterbi pass");
+        edb::CallSummaryArgs a{};
+        a.n_samples = ns;
+        a.n_states = S;
+        a.n_bins = c->n_bins;
+        a.counts = edb::CountsView{b->observed, b->obs_stride, b->reference, b->ref_stride, 0};
+        a.expected = b->expected;
+        a.ll = b->ll;
+        a.ll_sample_stride = (int64_t)S * b->ll_stride;
+        a.ll_state_stride = b->ll_stride;
+        for (int j = 0; j < S; j++) a.perm[j] = c->perm[j];
+        a.calls = b->calls;
+        a.ncalls = b->ncalls;
+        a.call_cap = b->call_cap;
+        a.stats = b->call_stats;
+        a.cor = b->cor;
+        g_launches += edb::launch_call_summary(a, st);
+        if (int rc = check_kernel("call_summary")) return rc;
+    }
     return 0;
 }
 
@@ -810,7 +830,8 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     if ((rc = ensure(c->h_obs, (size_t)ns * nb * 4)) || (rc = ensure(c->h_ref, (size_t)(shared_ref ? 1 : ns) * nb * 4)) ||
         (rc = ensure(c->h_phi, ns * 8)) || (rc = ensure(c->h_exp, ns * 8)) || (rc = ensure(c->h_ll, (size_t)ns * S * nbp * 8)) ||
         (rc = ensure(c->h_path, (size_t)ns * nb)) || (rc = ensure(c->h_calls, (size_t)ns * cap * 16)) ||
-        (rc = ensure(c->h_ncalls, ns * 4)))
+        (rc = ensure(c->h_ncalls, ns * 4)) || (rc = ensure(c->h_stats, b->call_stats ? (size_t)ns * cap * 24 : 8)) ||
+        (rc = ensure(c->h_cor, ns * 8)))
         return rc;
     if (shared_ref) CU(cudaMemcpyAsync(c->h_ref.p, b->reference, nb * 4, cudaMemcpyHostToDevice, st));
     else CU(cudaMemcpy2DAsync(c->h_ref.p, nb * 4, b->reference, b->ref_stride * 4, nb * 4, ns, cudaMemcpyHostToDevice, st));
@@ -831,7 +852,9 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     d.calls = (int32_t*)c->h_calls.p;
     d.ncalls = (int32_t*)c->h_ncalls.p;
     d.call_cap = cap;
-    const bool want_vit = b->path || b->calls || b->ncalls;
+    d.call_stats = b->call_stats ? (double*)c->h_stats.p : nullptr;
+    d.cor = b->cor ? (double*)c->h_cor.p : nullptr;
+    const bool want_vit = b->path || b->calls || b->ncalls || b->call_stats;
     c->last_host_samples = ns;
 
     // The likelihood matrix is 8*S bytes per bin and sample on the way back, against 4 on the way in: the call is
@@ -859,10 +882,13 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         }
     }
     if (want_vit && (rc = edb200_cohort_run_device(c, &d, 2, emission_mode, st))) return rc;
+    if ((d.call_stats || d.cor) && (rc = edb200_cohort_run_device(c, &d, 4, emission_mode, st))) return rc;
 
     if (b->path) CU(cudaMemcpy2DAsync(b->path, b->path_stride, c->h_path.p, nb, nb, ns, cudaMemcpyDeviceToHost, st));
     if (b->calls && b->call_cap > 0) CU(cudaMemcpyAsync(b->calls, c->h_calls.p, (size_t)ns * cap * 16, cudaMemcpyDeviceToHost, st));
     if (b->ncalls) CU(cudaMemcpyAsync(b->ncalls, c->h_ncalls.p, ns * 4, cudaMemcpyDeviceToHost, st));
+    if (b->call_stats && b->call_cap > 0) CU(cudaMemcpyAsync(b->call_stats, c->h_stats.p, (size_t)ns * cap * 24, cudaMemcpyDeviceToHost, st));
+    if (b->cor) CU(cudaMemcpyAsync(b->cor, c->h_cor.p, ns * 8, cudaMemcpyDeviceToHost, st));
     int warn = 0;
     if ((rc = pull_flags(st, &warn))) return rc;
     CU(cudaStreamSynchronize(g.stream2));

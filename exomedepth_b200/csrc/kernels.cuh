@@ -114,6 +114,26 @@ inline int viterbi_chain_tiles(const ChainDesc& cd)
     return (int)(((cd.em_off + cd.nobs - 1) >> 4) - ((cd.em_off + 1) >> 4) + 1);
 }
 
+// ---- CallCNVs post-processing (callcnvs.cu) -----------------------------------------------------------
+// Per-call sums of R/class_definition.R:393-400 and the per-sample cor(test, reference) of :338.
+struct CallSummaryArgs {
+    int n_samples;
+    int n_states;
+    int64_t n_bins;
+    CountsView counts;            // test counts + reference (or total) counts
+    const double* expected;       // [n_samples]
+    const double* ll;             // emission matrix, see LLView strides
+    int64_t ll_sample_stride;
+    int64_t ll_state_stride;
+    int perm[kMaxStates];         // HMM state j is likelihood column perm[j]; perm[0] is the normal column
+    const int32_t* calls;         // [n_samples][call_cap][4] as written by the Viterbi (1-based global bin indices)
+    const int32_t* ncalls;        // [n_samples]
+    int call_cap;
+    double* stats;                // out [n_samples][call_cap][3]: sum(ll_type - ll_normal), sum(total*expected), sum(test); or null
+    double* cor;                  // out [n_samples] Pearson correlation of test and reference counts; or null
+};
+int launch_call_summary(const CallSummaryArgs& a, cudaStream_t st);   // returns the number of launches
+
 // ---- forward pass / transition-probability grid (extension, forward.cu) -------------------------------
 struct ForwardArgs {
     const ChainDesc* chains;      // [n_chains]

@@ -126,6 +126,12 @@ typedef struct edb200_batch {
     int32_t       *calls;           /* out int32[n_samples][call_cap][4]  (start.p, end.p, type, nexons)   */
     int32_t       *ncalls;          /* out int32[n_samples]                                                */
     int32_t        call_cap;
+    /* CallCNVs post-processing (R/class_definition.R:393-400, :338), computed on the device so that the likelihood
+     * matrix does not have to be copied to the host to be summed over the calls; both may be NULL */
+    double        *call_stats;      /* out double[n_samples][call_cap][3] per call: sum over its bins of
+                                       ll[,type] - ll[,normal] (BF before the log10(e) factor and signif),
+                                       total*expected (reads.expected before as.integer), test (reads.observed) */
+    double        *cor;             /* out double[n_samples]  cor(test, reference) over all bins              */
 } edb200_batch;
 
 /* mode: 0 = auto, 1 = force in-register evaluation, 2 = force shared-memory lattice */
@@ -135,7 +141,8 @@ typedef struct edb200_batch {
 
 /* All pointers in `b` are DEVICE pointers on the selected GPU; work is enqueued on `cuda_stream`
  * (a cudaStream_t, 0 = default stream) and NOT synchronised.  ll must be non-NULL (the Viterbi reads it).
- * what: bit 0 emission, bit 1 Viterbi. */
+ * what: bit 0 emission, bit 1 Viterbi, bit 2 CallCNVs post-processing (call_stats / cor; needs the calls of a
+ * Viterbi pass over the same batch, in this call or an earlier one). */
 EDB200_API int edb200_cohort_run_device(edb200_cohort *c, const edb200_batch *b, int what, int emission_mode, void *cuda_stream);
 
 /* Same, HOST pointers: copies in, runs, copies the non-NULL outputs back, synchronises. */

@@ -18,6 +18,11 @@ def signif(x, digits=3):
     return round(x, digits - 1 - e)
 
 
+def _lsum(v):
+    v = np.asarray(v, float)
+    return float(math.fsum(v)) if np.all(np.isfinite(v)) else float(np.sum(v))
+
+
 def chromosome_levels(chromosome):
     """R/class_definition.R:323-326 — '1'..'22' first, then the others in order of appearance."""
     used = list(dict.fromkeys(str(c) for c in chromosome))
@@ -100,16 +105,17 @@ def call_cnvs(likelihood, test, reference, expected, chromosome, start, end, hmm
             sp0, ep0 = int(sp) - 1, int(ep) - 1                     # :371-372 (1-based into `good`)
             sl = slice(sp0 - 1, ep0) if sp0 >= 1 else slice(0, 0)
             col_type = cols[int(typ)]
-            bf = float(np.sum(loc_ll[sl, col_type] - loc_ll[sl, cols[0]]))
-            rexp = float(np.sum(total[good][sl] * expected[good][sl]))
-            robs = float(np.sum(test[good][sl]))
+            # R's sum() accumulates in long double (:395-400); math.fsum (exactly rounded) is the nearest stand-in
+            bf = _lsum(loc_ll[sl, col_type] - loc_ll[sl, cols[0]])
+            rexp = _lsum(total[good][sl] * expected[good][sl])
+            robs = _lsum(test[good][sl])
             rexp_i = int(rexp) if math.isfinite(rexp) else 0
             rows.append(dict(
                 start_p=sp0 + shift, end_p=ep0 + shift, type=int(typ), nexons=int(nex),
                 start=float(start[good][sp0 - 1]) if sp0 >= 1 else float("nan"),
                 end=float(end[good][ep0 - 1]) if ep0 >= 1 else float("nan"),
                 chromosome=levels[c],
-                BF=signif(math.log10(math.e) * bf, 3),
+                BF=signif(math.log10(math.e) * bf, 3), BF_raw=bf, reads_expected_raw=rexp,
                 reads_expected=rexp_i, reads_observed=robs,
                 reads_ratio=signif(robs / rexp_i, 3) if rexp_i else float("inf"),
             ))

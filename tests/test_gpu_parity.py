@@ -124,6 +124,39 @@ def test_cohort_vs_oracle(edb, port, S, mode):
     assert cols[0] == (1 if S == 3 else 2)
 
 
+@pytest.mark.parametrize("S", [3, 5])
+def test_cohort_callcnvs_columns_vs_oracle(edb, port, S):
+    """CallCNVs' per-call columns (BF, reads.expected, reads.observed, reads.ratio; R/class_definition.R:393-403) and
+    cor(test, reference) (:338) computed on the device, against the framing oracle run over the same likelihoods.
+    Sums: compensated FP64 on the device vs math.fsum in the oracle (R: long double) — 1e-14 relative before
+    rounding; integer columns, signif() columns and the call table exact."""
+    from exomedepth_b200 import synth
+    ns = 6
+    d = synth.cohort(ns, n_bins=12000)
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=S)
+    got = co.call_cnvs(d["observed"], d["reference"], d["phi"], d["expected"], call_cap=256, want_ll=True)
+    T = port.callcnvs_transitions(S, 1e-4)
+    chrom = np.concatenate([[str(c + 1)] * int(d["offsets"][c + 1] - d["offsets"][c]) for c in range(len(d["offsets"]) - 1)])
+    n_rows = 0
+    for s in range(ns):
+        test, ref = d["observed"][s].astype(float), d["reference"].astype(float)
+        want = framing.call_cnvs(got["ll"][s].T, test, ref, np.full(test.size, d["expected"][s]), chrom,
+                                 d["start"].astype(float), d["end"].astype(float),
+                                 lambda T_, loc, pos, L: port.c_hmm(T, loc, pos, L))
+        assert abs(got["cor"][s] - want["cor"]) < 1e-12
+        rows = got["CNV_calls"][s]
+        assert len(rows) == len(want["calls"]) and len(rows) > 10
+        for k, (g, w) in enumerate(zip(rows, want["calls"])):
+            for key in ("start_p", "end_p", "type", "nexons", "start", "end", "chromosome", "reads_expected", "reads_observed"):
+                assert g[key] == w[key], (s, k, key, g[key], w[key])
+            raw = got["call_stats"][s, k]
+            assert abs(raw[0] - w["BF_raw"]) <= 1e-14 * abs(w["BF_raw"]) + 1e-300
+            assert abs(raw[1] - w["reads_expected_raw"]) <= 1e-14 * abs(w["reads_expected_raw"])
+            assert g["BF"] == w["BF"] and g["reads_ratio"] == w["reads_ratio"], (s, k, g, w)
+            n_rows += 1
+    assert n_rows > 100
+
+
 def test_table_and_direct_paths_agree(edb):
     from exomedepth_b200 import _lib, synth
     d = synth.cohort(5, n_bins=20000)

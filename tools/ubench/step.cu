@@ -345,7 +345,7 @@ int main()
     for (int i = 0; i < 16 * 26; i++) hlt[i] = -0.5 - (i % 11) * 0.9;
     cudaMemcpy(em, hem, sizeof hem, cudaMemcpyHostToDevice);
     cudaMemcpy(lt, hlt, sizeof hlt, cudaMemcpyHostToDevice);
-    for (int w : {1, 8}) {
+    for (int w : {1, 2, 4, 8}) {
         run<0>("shfl64 exchange", w, out, cyc, em, lt);
         run<3>("shfl32 x10 (volatile asm)", w, out, cyc, em, lt);
         run<1>("smem uint4 exchange (V + anc)", w, out, cyc, em, lt);
