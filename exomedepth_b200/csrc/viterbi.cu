@@ -38,15 +38,16 @@
 namespace edb {
 
 constexpr int kTile = 16;          // observations per tile (one 128-byte line of an emission row)
-// TMA ring depth for the transition rows (227 KB of shared memory per CTA: S = 7 rows are 448 bytes per observation)
-__host__ __device__ constexpr int lt_stages(int S) { return S >= 7 ? 2 : S == 6 ? 3 : 4; }
-constexpr int kEmStages = 3;       // TMA ring depth for the emission tiles
-constexpr int kEmStageBytes = 4096;   // 32 rows x 128 bytes, 1024-byte aligned for the 128-byte swizzle
-constexpr int kWarpsPerCta = kViterbiWarpsPerCta;
+constexpr int kWarpsPerCta = kViterbiWarpsPerCta;       // consumer (sweep) warps; one more warp per CTA issues the TMA loads
+constexpr int kEmBytes = 4096;     // emission tile: up to 32 rows x 128 bytes, 1024-byte aligned for the 128-byte swizzle
 
 // transition row of destination state j: S doubles padded to an even count, so that rows are 16-byte aligned
 __host__ __device__ constexpr int lt_jstride(int S) { return S + (S & 1); }
 __host__ __device__ constexpr int lt_pitch(int S) { return S * lt_jstride(S); }          // doubles per observation
+// one ring stage of a sweep warp: [emission tile 4 KB][transition rows of the tile's 16 observations], 1 KB granular
+__host__ __device__ constexpr int stage_bytes(int S) { return (kEmBytes + kTile * lt_pitch(S) * 8 + 1023) / 1024 * 1024; }
+// ring depth (227 KB of shared memory per CTA over 8 sweep warps)
+__host__ __device__ constexpr int ring_stages(int S) { return S >= 7 ? 2 : S >= 5 ? 3 : 4; }
 
 // ---- PTX helpers (mbarrier + 1-D bulk TMA) ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,6 +81,10 @@ __device__ __forceinline__ bool try_wait_once(uint32_t bar, unsigned parity)
         : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src_gmem, unsigned bytes, uint32_t bar)
 {
@@ -126,18 +131,30 @@ struct Cand {
     double c[S];
 };
 
-// exchange V between the chain's S lanes, form the candidates and reduce them to the new V
+// what one step reads from shared memory: this lane's transition row and its emission.  Loaded one step AHEAD
+// of its use (the warp issues in order: a load placed next to its consumer stalls the whole dependent chain).
 template <int S>
-__device__ __forceinline__ void sweep_step(double em, uint32_t lt_qj, int src0, double& V, Cand<S>& cd)
+struct StepIn {
+    double lt[S + 1];
+    double em;
+};
+template <int S>
+__device__ __forceinline__ void load_step(StepIn<S>& in, uint32_t lt_qj, uint32_t em_addr)
 {
-    double lt[S + 1];                                       // this lane's transition row: independent of V, issued first
 #pragma unroll
     for (int k = 0; k + 1 < S; k += 2) {
         const double2 x = lds_f64x2(lt_qj + 8u * k);
-        lt[k] = x.x;
-        lt[k + 1] = x.y;
+        in.lt[k] = x.x;
+        in.lt[k + 1] = x.y;
     }
-    if (S & 1) lt[S - 1] = lds_f64(lt_qj + 8u * (S - 1));
+    if (S & 1) in.lt[S - 1] = lds_f64(lt_qj + 8u * (S - 1));
+    in.em = lds_f64(em_addr);
+}
+
+// exchange V between the chain's S lanes, form the candidates and reduce them to the new V
+template <int S>
+__device__ __forceinline__ void sweep_step(const StepIn<S>& in, int src0, double& V, Cand<S>& cd)
+{
     int lo[S], hi[S];
     const int vlo = __double2loint(V), vhi = __double2hiint(V);
 #pragma unroll
@@ -145,11 +162,11 @@ __device__ __forceinline__ void sweep_step(double em, uint32_t lt_qj, int src0, 
         lo[k] = shfl_idx(vlo, src0 + k);
         hi[k] = shfl_idx(vhi, src0 + k);
     }
-    const double em_s = em != em ? -HUGE_VAL : em;         // depends on the emission only: off the chain through V
+    const double em_s = in.em != in.em ? -HUGE_VAL : in.em;         // depends on the emission only: off the chain through V
     double m[S];
 #pragma unroll
     for (int k = 0; k < S; k++) {
-        cd.c[k] = __dadd_rn(__dadd_rn(em_s, __hiloint2double(hi[k], lo[k])), lt[k]);
+        cd.c[k] = __dadd_rn(__dadd_rn(em_s, __hiloint2double(hi[k], lo[k])), in.lt[k]);
         m[k] = cd.c[k];
     }
     // pairs first; the last three survivors are settled by independent compares
@@ -203,44 +220,81 @@ __device__ __forceinline__ int64_t record_base(const ViterbiArgs& a, int chain, 
 }
 
 // =========================================================================================== sweep
+// Warp roles: warps 0..7 sweep (consumers), warp 8 feeds them (producer): lane w of the producer walks the work
+// list of sweep warp w one tile ahead of it and issues, per tile, one 2-D TMA load of the emission tile and one
+// bulk copy of the tile's transition rows into the warp's ring stage, both completing on the stage's `full`
+// mbarrier; the sweep warp releases the stage through its `empty` mbarrier.  The sweep warps therefore carry no
+// address arithmetic, no expect_tx and no TMA issue between two tiles of their dependent chain.
 template <int S>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 1)
+__global__ void __launch_bounds__((kWarpsPerCta + 1) * 32, 1)
 viterbi_sweep_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
 {
     constexpr int G = 32 / S;
     constexpr int LTP = lt_pitch(S);
     constexpr int LTJ = lt_jstride(S);
-    constexpr int kStages = lt_stages(S);
-    constexpr unsigned kTileBytes = kTile * LTP * 8;
-    constexpr unsigned kFull = 0xffffffffu;
+    constexpr int kStages = ring_stages(S);
+    constexpr unsigned kStageBytes = stage_bytes(S);
     constexpr unsigned kEmBox = G * S * kTile * 8;          // bytes one emission tile delivers
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // [emission tiles: warp x stage x 4 KB][transition rows: warp x stage x obs x LTP doubles][mbarriers]
-    const uint32_t em_ring = smem_u32(smem) + (uint32_t)warp * kEmStages * kEmStageBytes;
-    const uint32_t ring = smem_u32(smem) + (uint32_t)kWarpsPerCta * kEmStages * kEmStageBytes + (uint32_t)warp * kStages * kTileBytes;
-    const uint32_t bars = smem_u32(smem) + (uint32_t)kWarpsPerCta * (kEmStages * kEmStageBytes + kStages * kTileBytes) +
-                          (uint32_t)warp * (kStages + kEmStages) * 8;
-    const uint32_t em_bars = bars + kStages * 8;
+    // [stages: warp x stage x kStageBytes][mbarriers: warp x (full[kStages], empty[kStages])]
+    const uint32_t bar0 = smem_u32(smem) + (uint32_t)kWarpsPerCta * kStages * kStageBytes;
 
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWarpsPerCta * 2 * kStages; s++) mbar_init(bar0 + 8u * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();                                        // the only CTA-wide barrier: every warp is its own pipeline below
+
+    if (warp == kWarpsPerCta) {
+        // ------------------------------------------------------------------------------------ producer
+        if (lane >= kWarpsPerCta) return;
+        const int slot = blockIdx.x * kWarpsPerCta + lane;
+        const uint32_t ring = smem_u32(smem) + (uint32_t)lane * kStages * kStageBytes;
+        const uint32_t full = bar0 + (uint32_t)lane * 2 * kStages * 8, empty = full + kStages * 8;
+        int st = 0;
+        unsigned wrap = 0;                                  // completed passes over the ring
+        for (int it = a.sched_begin[slot]; it < a.sched_begin[slot + 1]; it++) {
+            const int chain = a.sched_items[2 * it], grp = a.sched_items[2 * it + 1];
+            const ChainDesc cd = a.chains[chain];
+            const int64_t t_first = (cd.em_off + 1) >> 4;
+            const int n_tiles = chain_tiles(cd);
+            const double* __restrict__ lt_base = a.lt + cd.lt_row0 * LTP;
+            int i0 = (int)((t_first << 4) - cd.em_off);     // first observation of the tile (may be < 1)
+            int c0 = (int)(t_first << 4);
+            const int c1 = grp * G * S;
+            for (int t = 0; t < n_tiles; t++, i0 += kTile, c0 += kTile) {
+                if (wrap) mbar_wait(empty + 8u * st, (wrap - 1) & 1);
+                const int r0 = i0 < 0 ? 0 : i0;             // rows before the chain's first row are never used
+                const unsigned lt_bytes = (unsigned)(i0 + kTile - r0) * LTP * 8;
+                const uint32_t dst = ring + (uint32_t)st * kStageBytes;
+                mbar_expect_tx(full + 8u * st, lt_bytes + kEmBox);
+                // emission tile: one 2-D box (16 bins x the G*S rows of the warp's chains; rows past the batch and
+                // columns past the matrix are zero-filled by the TMA unit)
+                tma_load_2d(dst, &ll_map, c0, c1, full + 8u * st);
+                tma_load_1d(dst + kEmBytes + (uint32_t)(r0 - i0) * LTP * 8, lt_base + (int64_t)r0 * LTP, lt_bytes, full + 8u * st);
+                if (++st == kStages) { st = 0; wrap++; }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------------------------- consumer
+    const uint32_t ring = smem_u32(smem) + (uint32_t)warp * kStages * kStageBytes;
+    const uint32_t full = bar0 + (uint32_t)warp * 2 * kStages * 8, empty = full + kStages * 8;
     int g = lane / S;
     const int j = lane - g * S;
     if (g >= G) g = G - 1;                                  // spare lanes shadow lanes of the last chain
     const int src0 = g * S;
     const double tail = j == 0 ? 0.0 : a.tail_other;
     // this lane's row of the emission tile: the box holds the G*S rows of the warp's chains in likelihood-column
-    // order; chunk c (16 bytes) of row r sits at chunk c ^ (r & 7) (128-byte swizzle): conflict-free 128-bit reads
+    // order; chunk c (16 bytes) of row r sits at chunk c ^ (r & 7) (128-byte swizzle): conflict-free reads
     const int em_r = g * S + a.perm[j];
-    const uint32_t em_row_off = (uint32_t)em_r * 128u, em_x = (uint32_t)(em_r & 7);
+    const uint32_t em_lane = (uint32_t)em_r * 128u + ((uint32_t)(em_r & 7) << 4);
+    const uint32_t lt_lane = kEmBytes + (uint32_t)(j * LTJ) * 8;
 
-    if (lane == 0) {
-        for (int s = 0; s < kStages + kEmStages; s++) mbar_init(bars + 8u * s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    unsigned ring_seq = 0;                                  // tiles pushed through this warp's rings so far (stage / parity bookkeeping)
-
-    // each warp is an independent pipeline over its own list of work items: no CTA barrier below
+    int st = 0;
+    unsigned phase = 0;
     const int slot = blockIdx.x * kWarpsPerCta + warp;
     for (int it = a.sched_begin[slot]; it < a.sched_begin[slot + 1]; it++) {
         const int chain = a.sched_items[2 * it], grp = a.sched_items[2 * it + 1];
@@ -250,53 +304,35 @@ viterbi_sweep_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
         // (em_off + i) / 16 == t_first + t
         const int64_t t_first = (cd.em_off + 1) >> 4;
         const int n_tiles = chain_tiles(cd);
-        const double* __restrict__ lt_base = a.lt + cd.lt_row0 * LTP;
-        uint2* bp = reinterpret_cast<uint2*>(a.bp) + record_base(a, chain, grp, n_tiles) * kRecU2;
-
-        auto tile_i0 = [&](int t) -> int { return (int)(((t_first + t) << 4) - cd.em_off); };   // first obs of tile (may be < 1)
-        auto issue_lt = [&](int t) {
-            const int st = (ring_seq + t) % kStages;
-            const int i0 = tile_i0(t);
-            const int r0 = i0 < 0 ? 0 : i0;             // rows before the chain's first row are never used
-            const unsigned bytes = (unsigned)(i0 + kTile - r0) * LTP * 8;
-            mbar_expect_tx(bars + 8u * st, bytes);
-            tma_load_1d(ring + (uint32_t)(st * kTile + (r0 - i0)) * LTP * 8, lt_base + (int64_t)r0 * LTP, bytes, bars + 8u * st);
-        };
-        // emission tile t: one 2-D TMA box (16 bins x the G*S rows of this warp's chains; rows past the batch and
-        // columns past the matrix are zero-filled by the TMA unit)
-        auto issue_em = [&](int t) {
-            const int st = (ring_seq + t) % kEmStages;
-            mbar_expect_tx(em_bars + 8u * st, kEmBox);
-            tma_load_2d(em_ring + (uint32_t)st * kEmStageBytes, &ll_map, (int)((t_first + t) << 4), grp * G * S, em_bars + 8u * st);
-        };
-        if (lane == 0) {
-            for (int t = 0; t < kEmStages && t < n_tiles; t++) issue_em(t);
-            for (int t = 0; t < kStages && t < n_tiles; t++) issue_lt(t);
-        }
-        bool lt_ready = false, em_ready = false;
-        uint2* bp_t = bp + lane;
+        uint2* bp_t = reinterpret_cast<uint2*>(a.bp) + record_base(a, chain, grp, n_tiles) * kRecU2 + lane;
+        int i0 = (int)((t_first << 4) - cd.em_off);         // first observation of the tile (may be < 1)
+        bool ready = false;
 
         double V = j == 0 ? 0.0 : -HUGE_VAL;                // hmm.cpp:46-52
 
-        for (int t = 0; t < n_tiles; t++, bp_t += kRecU2) {
-            const unsigned seq = ring_seq + t;
-            const int st = seq % kStages, est = seq % kEmStages;
-            if (!lt_ready) mbar_wait(bars + 8u * st, (seq / kStages) & 1);
-            if (!em_ready) mbar_wait(em_bars + 8u * est, (seq / kEmStages) & 1);
-            const uint32_t ltt = ring + (uint32_t)(st * kTile * LTP + j * LTJ) * 8;
-            // element q of this lane's emission row: the 128-byte swizzle is an XOR on address bits 4-6
-            const uint32_t emt = em_ring + (uint32_t)est * kEmStageBytes + em_row_off + (em_x << 4);
-            const int i0 = tile_i0(t);
+        for (int t = 0; t < n_tiles; t++, bp_t += kRecU2, i0 += kTile) {
+            if (!ready) mbar_wait(full + 8u * st, phase);
+            const uint32_t stage = ring + (uint32_t)st * kStageBytes;
+            const uint32_t ltt = stage + lt_lane;
+            const uint32_t emt = stage + em_lane;           // element q: the 128-byte swizzle is an XOR on address bits 4-6
+            int st_n = st + 1;
+            unsigned phase_n = phase;
+            if (st_n == kStages) { st_n = 0; phase_n ^= 1u; }
+            ready = false;
             unsigned lo = 0, hi = 0;                        // 16 back-pointers of this lane, 4 bits each
             if (i0 >= 1 && i0 + kTile - 1 <= cd.n_em) {     // tile entirely inside the real observations
                 Cand<S> cnd;
                 double Vq = V, em_prev = 0.0;
+                StepIn<S> cur;
+                load_step<S>(cur, ltt, emt);
 #pragma unroll
                 for (int q = 0; q < kTile; q++) {
+                    StepIn<S> nxi;
+                    if (q + 1 < kTile) load_step<S>(nxi, ltt + (q + 1) * LTP * 8, emt ^ (uint32_t)((q + 1) << 3));
+                    if (q == kTile / 2 && t + 1 < n_tiles) ready = try_wait_once(full + 8u * st_n, phase_n);   // poll the next tile early
                     Cand<S> nxt;
                     double Vn = Vq;
-                    const double em = lds_f64(emt ^ (uint32_t)(q << 3));
-                    sweep_step<S>(em, ltt + q * LTP * 8, src0, Vn, nxt);
+                    sweep_step<S>(cur, src0, Vn, nxt);
                     if (q > 0) {                            // the previous step's back-pointer, in the shadow of this step's exchange
                         const unsigned arg = sweep_arg<S>(cnd, Vq, em_prev);
                         if (q - 1 < 8) lo |= arg << (4 * (q - 1));
@@ -304,7 +340,8 @@ viterbi_sweep_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
                     }
                     cnd = nxt;
                     Vq = Vn;
-                    em_prev = em;
+                    em_prev = cur.em;
+                    if (q + 1 < kTile) cur = nxi;
                 }
                 hi |= sweep_arg<S>(cnd, Vq, em_prev) << 28;
                 V = Vq;
@@ -314,29 +351,23 @@ viterbi_sweep_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
                     const int i = i0 + q;
                     unsigned arg = (unsigned)j;             // observations outside the chain: identity step
                     if (i >= 1 && i < nobs) {               // warp-uniform
-                        const double em = i <= cd.n_em ? lds_f64(emt ^ (uint32_t)(q << 3)) : tail;
+                        StepIn<S> in;
+                        load_step<S>(in, ltt + q * LTP * 8, emt ^ (uint32_t)(q << 3));
+                        if (i > cd.n_em) in.em = tail;
                         Cand<S> cnd;
-                        sweep_step<S>(em, ltt + q * LTP * 8, src0, V, cnd);
-                        arg = sweep_arg<S>(cnd, V, em);
+                        sweep_step<S>(in, src0, V, cnd);
+                        arg = sweep_arg<S>(cnd, V, in.em);
                     }
                     if (q < 8) lo |= arg << (4 * q);
                     else hi |= arg << (4 * (q - 8));
                 }
             }
             *bp_t = make_uint2(lo, hi);
-            __syncwarp();                                   // every lane is done with both stages: refill them
-            if (lane == 0) {
-                if (t + kStages < n_tiles) issue_lt(t + kStages);
-                if (t + kEmStages < n_tiles) issue_em(t + kEmStages);
-            }
-            lt_ready = em_ready = false;
-            if (t + 1 < n_tiles) {
-                lt_ready = try_wait_once(bars + 8u * ((seq + 1) % kStages), ((seq + 1) / kStages) & 1);
-                em_ready = try_wait_once(em_bars + 8u * ((seq + 1) % kEmStages), ((seq + 1) / kEmStages) & 1);
-            }
+            __syncwarp();                                   // every lane is done with the stage: hand it back
+            if (lane == 0) mbar_arrive(empty + 8u * st);
+            st = st_n;
+            phase = phase_n;
         }
-        ring_seq += (unsigned)n_tiles;
-        __syncwarp();
     }
 }
 
@@ -539,7 +570,7 @@ __global__ void viterbi_compact_kernel(ViterbiArgs a)
 
 size_t viterbi_smem_bytes(int S)
 {
-    return (size_t)kWarpsPerCta * (kEmStages * kEmStageBytes + lt_stages(S) * (kTile * lt_pitch(S) * 8) + (lt_stages(S) + kEmStages) * 8);
+    return (size_t)kWarpsPerCta * ring_stages(S) * (stage_bytes(S) + 16);
 }
 int viterbi_lt_pitch(int S) { return lt_pitch(S); }
 int viterbi_tile() { return kTile; }
@@ -556,7 +587,7 @@ static void launch_all(const ViterbiArgs& a, int64_t n_records, cudaStream_t st)
         configured = true;
     }
     prof_mark("viterbi_sweep", st);
-    viterbi_sweep_kernel<S><<<a.n_slots / kWarpsPerCta, kWarpsPerCta * 32, smem, st>>>(a, *reinterpret_cast<const CUtensorMap*>(a.ll_map));
+    viterbi_sweep_kernel<S><<<a.n_slots / kWarpsPerCta, (kWarpsPerCta + 1) * 32, smem, st>>>(a, *reinterpret_cast<const CUtensorMap*>(a.ll_map));
     prof_mark("viterbi_tilemap", st);
     const int64_t map_threads = n_records * G;
     if (map_threads > 0) viterbi_tilemap_kernel<S><<<(unsigned)((map_threads + 255) / 256), 256, 0, st>>>(a, n_records);
