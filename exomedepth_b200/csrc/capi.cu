@@ -178,10 +178,10 @@ int make_ll_map(const double* ll, int64_t rows, int64_t cols, int64_t pitch, int
 }
 
 // build and upload the sweep schedule (host_tables.cpp: viterbi_schedule)
-int upload_schedule(const std::vector<int32_t>& nobs, int groups, int n_ctas, DevBuf& d_begin, DevBuf& d_items, cudaStream_t st)
+int upload_schedule(const std::vector<int32_t>& nobs, int groups, int n_ctas, int warps_per_cta, DevBuf& d_begin, DevBuf& d_items, cudaStream_t st)
 {
     std::vector<int32_t> begin, items;
-    edb::viterbi_schedule(nobs.data(), (int)nobs.size(), groups, n_ctas, edb::kViterbiWarpsPerCta, begin, items);
+    edb::viterbi_schedule(nobs.data(), (int)nobs.size(), groups, n_ctas, warps_per_cta, begin, items);
     if (int rc = ensure(d_begin, begin.size() * 4)) return rc;
     if (int rc = ensure(d_items, items.size() * 4 + 8)) return rc;
     CU(cudaMemcpyAsync(d_begin.p, begin.data(), begin.size() * 4, cudaMemcpyHostToDevice, st));
@@ -210,6 +210,7 @@ struct edb200_cohort {
     DevBuf chains, lt, odds_d, tile_base, decay;
     DevBuf sched_begin, sched_items;     // sweep schedule for `sched_groups` groups of samples
     int sched_groups = 0;
+    int sched_warps = 4;                 // sweep warps per CTA the schedule was built for
     // per-batch scratch
     DevBuf consts, bp, ccalls, cncalls, maxima, fw_grid, fw_chain, fw_out, fw_best;
     int last_host_samples = 0;           // samples whose likelihoods the last host-pointer run left in h_ll
@@ -508,9 +509,10 @@ int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const d
     if (int rc = make_ll_map(a.ll, S, nobs_p, nobs_p, S, &ll_map)) return rc;
     a.ll_map = &ll_map;
     for (int j = 0; j < S; j++) a.perm[j] = j;
-    if (int rc = upload_schedule(std::vector<int32_t>{nobs}, 1, 1, cs.sched_begin, cs.sched_items, st)) return rc;
+    if (int rc = upload_schedule(std::vector<int32_t>{nobs}, 1, 1, 4, cs.sched_begin, cs.sched_items, st)) return rc;
     a.groups = 1;
-    a.n_slots = edb::kViterbiWarpsPerCta;
+    a.warps_per_cta = 4;
+    a.n_slots = 4;
     a.sched_begin = (const int32_t*)cs.sched_begin.p;
     a.sched_items = (const int32_t*)cs.sched_items.p;
     a.lt = (const double*)cs.lt.p;
@@ -704,11 +706,14 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
         if (c->sched_groups != (int)groups) {
             std::vector<int32_t> nobs(c->n_chains);
             for (int ch = 0; ch < c->n_chains; ch++) nobs[ch] = c->chains_h[ch].nobs;
-            if (int rc = upload_schedule(nobs, (int)groups, g.n_sms, c->sched_begin, c->sched_items, st)) return rc;
+            const char* force = getenv("EDB200_SWEEP_WARPS");          // experiments: 4 or 8
+            c->sched_warps = force ? (atoi(force) == 8 ? 8 : 4) : edb::viterbi_pick_warps(nobs.data(), c->n_chains, (int)groups, g.n_sms);
+            if (int rc = upload_schedule(nobs, (int)groups, g.n_sms, c->sched_warps, c->sched_begin, c->sched_items, st)) return rc;
             c->sched_groups = (int)groups;
         }
         a.groups = (int)groups;
-        a.n_slots = g.n_sms * edb::kViterbiWarpsPerCta;
+        a.warps_per_cta = c->sched_warps;
+        a.n_slots = g.n_sms * c->sched_warps;
         a.sched_begin = (const int32_t*)c->sched_begin.p;
         a.sched_items = (const int32_t*)c->sched_items.p;
         a.lt = (const double*)c->lt.p;

@@ -70,7 +70,6 @@ struct ChainDesc {
     int32_t pad;
 };
 
-constexpr int kViterbiWarpsPerCta = 8;   // two sweep warps per SM sub-partition
 
 struct ViterbiArgs {
     const ChainDesc* chains;      // [n_chains]
@@ -78,7 +77,8 @@ struct ViterbiArgs {
     int n_samples;
     int n_states;
     int groups;                   // ceil(n_samples / (32 / n_states)): warps per chromosome
-    int n_slots;                  // sweep warps in the grid (a multiple of kViterbiWarpsPerCta)
+    int warps_per_cta;            // sweep warps per CTA: 4 or 8 (viterbi_pick_warps)
+    int n_slots;                  // sweep warps in the grid (a multiple of warps_per_cta)
     const int32_t* sched_begin;   // [n_slots + 1] first work item of each sweep warp (viterbi_schedule)
     const int32_t* sched_items;   // [2 * n_items] (chain, group) pairs
     const double* ll;             // emission matrix, see LLView strides; sample stride must be n_states * state stride
@@ -103,7 +103,8 @@ struct ViterbiArgs {
 
 // enqueues sweep, tilemap, trace, expand and compact; n_records = groups * (tiles of all chains); returns the number of launches
 int launch_viterbi(const ViterbiArgs& a, int64_t n_records, cudaStream_t st);
-size_t viterbi_smem_bytes(int n_states);
+size_t viterbi_smem_bytes(int n_states, int warps_per_cta);
+int viterbi_pick_warps(const int32_t* chain_nobs, int n_chains, int groups, int n_sms);
 int viterbi_lt_pitch(int n_states);      // doubles per table row: S destination rows of S doubles padded to an even count
 int viterbi_tile();                      // observations per tile; the table carries this many spare rows
 size_t viterbi_record_bytes();           // scratch bytes per (warp, tile): packed back-pointers + tile maps

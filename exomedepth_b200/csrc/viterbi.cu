@@ -31,6 +31,8 @@
 //   expand   one warp per chain fills in the per-observation states, the path bytes and the
 //            reference's call table, 32 tiles at a time;
 //   compact  concatenates the per-chromosome call tables per sample.
+#include <algorithm>
+
 #include <cuda.h>
 
 #include "kernels.cuh"
@@ -38,7 +40,10 @@
 namespace edb {
 
 constexpr int kTile = 16;          // observations per tile (one 128-byte line of an emission row)
-constexpr int kWarpsPerCta = kViterbiWarpsPerCta;       // consumer (sweep) warps; one more warp per CTA issues the TMA loads
+// Sweep warps per CTA (one more warp issues the TMA loads): 4 = one per SM sub-partition, 8 = two.  A sweep warp alone
+// on its sub-partition AND in a CTA of 4 steps in ~135 cycles; with 8 per CTA the warps contend for the SM's
+// shared-memory / shuffle pipe and each step takes ~180 (tools/ubench/step.cu) — 8 only pays when the batch has more
+// work than 4 warps per SM can turn over within the longest chromosome's chain (viterbi_pick_warps).
 constexpr int kEmBytes = 4096;     // emission tile: up to 32 rows x 128 bytes, 1024-byte aligned for the 128-byte swizzle
 
 // transition row of destination state j: S doubles padded to an even count, so that rows are 16-byte aligned
@@ -46,8 +51,12 @@ __host__ __device__ constexpr int lt_jstride(int S) { return S + (S & 1); }
 __host__ __device__ constexpr int lt_pitch(int S) { return S * lt_jstride(S); }          // doubles per observation
 // one ring stage of a sweep warp: [emission tile 4 KB][transition rows of the tile's 16 observations], 1 KB granular
 __host__ __device__ constexpr int stage_bytes(int S) { return (kEmBytes + kTile * lt_pitch(S) * 8 + 1023) / 1024 * 1024; }
-// ring depth (227 KB of shared memory per CTA over 8 sweep warps)
-__host__ __device__ constexpr int ring_stages(int S) { return S >= 7 ? 2 : S >= 5 ? 3 : 4; }
+// ring depth: what fits in ~220 KB of shared memory per CTA, at most 6 stages
+__host__ __device__ constexpr int ring_stages(int S, int W)
+{
+    const int fit = (220 * 1024) / (W * stage_bytes(S));
+    return fit > 6 ? 6 : fit;
+}
 
 // ---- PTX helpers (mbarrier + 1-D bulk TMA) ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,6 +120,19 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
+// the same loads for data other lanes of the warp have just written (ordered against the st.shared / warp barrier)
+__device__ __forceinline__ double lds_f64_fresh(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 lds_f64x2_fresh(uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ int shfl_idx(int v, int src)
 {
     int r;
@@ -151,22 +173,35 @@ __device__ __forceinline__ void load_step(StepIn<S>& in, uint32_t lt_qj, uint32_
     in.em = lds_f64(em_addr);
 }
 
-// exchange V between the chain's S lanes, form the candidates and reduce them to the new V
+// exchange V between the chain's S lanes, form the candidates and reduce them to the new V.
+// The exchange goes through shared memory (one STS.64, a warp barrier, then 128-bit loads of the chain's S values)
+// rather than through 2*S shuffles: the latency is the same (tools/ubench/step.cu: 126 cycles per step either way)
+// but the warp barrier pins the order — ptxas is free to sink individual shuffles next to their consumers, which
+// exposes one shuffle latency per source state on the dependent chain (measured: 178 instead of 130 cycles).
+// `xch` = this chain's slot for this step (double-buffered by step parity), `xch_own` = this lane's entry in it.
 template <int S>
-__device__ __forceinline__ void sweep_step(const StepIn<S>& in, int src0, double& V, Cand<S>& cd)
+__device__ __forceinline__ void sweep_step(const StepIn<S>& in, uint32_t xch, uint32_t xch_own, double& V, Cand<S>& cd)
 {
-    int lo[S], hi[S];
-    const int vlo = __double2loint(V), vhi = __double2hiint(V);
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(xch_own), "d"(V) : "memory");
+    __syncwarp();
+    double v[S + 1];
 #pragma unroll
-    for (int k = 0; k < S; k++) {
-        lo[k] = shfl_idx(vlo, src0 + k);
-        hi[k] = shfl_idx(vhi, src0 + k);
+    for (int k = 0; k + 1 < S; k += 2) {
+        const double2 x = lds_f64x2_fresh(xch + 8u * k);
+        v[k] = x.x;
+        v[k + 1] = x.y;
     }
-    const double em_s = in.em != in.em ? -HUGE_VAL : in.em;         // depends on the emission only: off the chain through V
+    if (S & 1) v[S - 1] = lds_f64_fresh(xch + 8u * (S - 1));
+    double em_s = in.em != in.em ? -HUGE_VAL : in.em;               // depends on the emission only: off the chain through V
+    // Order pin: ptxas likes to place the first addition right behind the first of the loads above, which stalls the
+    // warp there with the other loads not yet issued (one extra shared-memory latency per step).  Tying em_s to the
+    // LAST load — through a predicate that is never true: V is never a NaN, let alone this one — makes every
+    // addition wait until all loads are in flight.
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, 0x7ff1d00d;\n\t@p mov.f64 %0, 0d0000000000000000;\n\t}" : "+d"(em_s) : "r"(__double2hiint(v[S - 1])));
     double m[S];
 #pragma unroll
     for (int k = 0; k < S; k++) {
-        cd.c[k] = __dadd_rn(__dadd_rn(em_s, __hiloint2double(hi[k], lo[k])), in.lt[k]);
+        cd.c[k] = __dadd_rn(__dadd_rn(em_s, v[k]), in.lt[k]);
         m[k] = cd.c[k];
     }
     // pairs first; the last three survivors are settled by independent compares
@@ -225,20 +260,21 @@ __device__ __forceinline__ int64_t record_base(const ViterbiArgs& a, int chain, 
 // bulk copy of the tile's transition rows into the warp's ring stage, both completing on the stage's `full`
 // mbarrier; the sweep warp releases the stage through its `empty` mbarrier.  The sweep warps therefore carry no
 // address arithmetic, no expect_tx and no TMA issue between two tiles of their dependent chain.
-template <int S>
+template <int S, int kWarpsPerCta>
 __global__ void __launch_bounds__((kWarpsPerCta + 1) * 32, 1)
 viterbi_sweep_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
 {
     constexpr int G = 32 / S;
     constexpr int LTP = lt_pitch(S);
     constexpr int LTJ = lt_jstride(S);
-    constexpr int kStages = ring_stages(S);
+    constexpr int kStages = ring_stages(S, kWarpsPerCta);
     constexpr unsigned kStageBytes = stage_bytes(S);
     constexpr unsigned kEmBox = G * S * kTile * 8;          // bytes one emission tile delivers
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // [stages: warp x stage x kStageBytes][mbarriers: warp x (full[kStages], empty[kStages])]
+    // [stages: warp x stage x kStageBytes][mbarriers: warp x (full[kStages], empty[kStages])][V exchange: warp x 2 x G x LTJ doubles]
     const uint32_t bar0 = smem_u32(smem) + (uint32_t)kWarpsPerCta * kStages * kStageBytes;
+    const uint32_t xch0 = bar0 + (uint32_t)kWarpsPerCta * 2 * kStages * 8;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kWarpsPerCta * 2 * kStages; s++) mbar_init(bar0 + 8u * s, 1);
@@ -285,7 +321,11 @@ viterbi_sweep_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
     int g = lane / S;
     const int j = lane - g * S;
     if (g >= G) g = G - 1;                                  // spare lanes shadow lanes of the last chain
-    const int src0 = g * S;
+    // V exchange slots of this lane's chain (two, alternating by step) and the lane's own entry in them; the spare
+    // lanes write to a slot of their own that nobody reads
+    constexpr uint32_t kXchBuf = (G + 1) * LTJ * 8;
+    const uint32_t xch = xch0 + (uint32_t)warp * 2 * kXchBuf + (uint32_t)g * LTJ * 8;
+    const uint32_t xch_own = (lane < G * S ? xch : xch0 + (uint32_t)warp * 2 * kXchBuf + (uint32_t)G * LTJ * 8) + 8u * j;
     const double tail = j == 0 ? 0.0 : a.tail_other;
     // this lane's row of the emission tile: the box holds the G*S rows of the warp's chains in likelihood-column
     // order; chunk c (16 bytes) of row r sits at chunk c ^ (r & 7) (128-byte swizzle): conflict-free reads
@@ -332,7 +372,7 @@ viterbi_sweep_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
                     if (q == kTile / 2 && t + 1 < n_tiles) ready = try_wait_once(full + 8u * st_n, phase_n);   // poll the next tile early
                     Cand<S> nxt;
                     double Vn = Vq;
-                    sweep_step<S>(cur, src0, Vn, nxt);
+                    sweep_step<S>(cur, xch + (q & 1) * kXchBuf, xch_own + (q & 1) * kXchBuf, Vn, nxt);
                     if (q > 0) {                            // the previous step's back-pointer, in the shadow of this step's exchange
                         const unsigned arg = sweep_arg<S>(cnd, Vq, em_prev);
                         if (q - 1 < 8) lo |= arg << (4 * (q - 1));
@@ -355,7 +395,7 @@ viterbi_sweep_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
                         load_step<S>(in, ltt + q * LTP * 8, emt ^ (uint32_t)(q << 3));
                         if (i > cd.n_em) in.em = tail;
                         Cand<S> cnd;
-                        sweep_step<S>(in, src0, V, cnd);
+                        sweep_step<S>(in, xch + (q & 1) * kXchBuf, xch_own + (q & 1) * kXchBuf, V, cnd);
                         arg = sweep_arg<S>(cnd, V, in.em);
                     }
                     if (q < 8) lo |= arg << (4 * q);
@@ -568,26 +608,45 @@ __global__ void viterbi_compact_kernel(ViterbiArgs a)
     if (lane == 0) a.ncalls[sample] = n;
 }
 
-size_t viterbi_smem_bytes(int S)
+size_t viterbi_smem_bytes(int S, int W)
 {
-    return (size_t)kWarpsPerCta * ring_stages(S) * (stage_bytes(S) + 16);
+    return (size_t)W * (ring_stages(S, W) * (stage_bytes(S) + 16) + 2 * (32 / S + 1) * lt_jstride(S) * 8);
+}
+// 4 or 8 sweep warps per CTA: whichever finishes the batch sooner under the measured per-step costs (see kTile comment)
+int viterbi_pick_warps(const int32_t* chain_nobs, int n_chains, int groups, int n_sms)
+{
+    int64_t total = 0, longest = 0;
+    for (int c = 0; c < n_chains; c++) {
+        total += (int64_t)chain_nobs[c] * groups;
+        if (chain_nobs[c] > longest) longest = chain_nobs[c];
+    }
+    const double t4 = 140.0 * (double)std::max<int64_t>(longest, total / (4 * (int64_t)n_sms) + 1);
+    const double t8 = 185.0 * (double)std::max<int64_t>(longest, total / (8 * (int64_t)n_sms) + 1);
+    return t4 <= t8 ? 4 : 8;
 }
 int viterbi_lt_pitch(int S) { return lt_pitch(S); }
 int viterbi_tile() { return kTile; }
 size_t viterbi_record_bytes() { return (size_t)kRecU2 * 8; }
 
+template <int S, int W>
+static void launch_sweep(const ViterbiArgs& a, cudaStream_t st)
+{
+    const size_t smem = viterbi_smem_bytes(S, W);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(viterbi_sweep_kernel<S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    viterbi_sweep_kernel<S, W><<<a.n_slots / W, (W + 1) * 32, smem, st>>>(a, *reinterpret_cast<const CUtensorMap*>(a.ll_map));
+}
+
 template <int S>
 static void launch_all(const ViterbiArgs& a, int64_t n_records, cudaStream_t st)
 {
     constexpr int G = 32 / S;
-    const size_t smem = viterbi_smem_bytes(S);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(viterbi_sweep_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
     prof_mark("viterbi_sweep", st);
-    viterbi_sweep_kernel<S><<<a.n_slots / kWarpsPerCta, (kWarpsPerCta + 1) * 32, smem, st>>>(a, *reinterpret_cast<const CUtensorMap*>(a.ll_map));
+    if (a.warps_per_cta == 4) launch_sweep<S, 4>(a, st);
+    else launch_sweep<S, 8>(a, st);
     prof_mark("viterbi_tilemap", st);
     const int64_t map_threads = n_records * G;
     if (map_threads > 0) viterbi_tilemap_kernel<S><<<(unsigned)((map_threads + 255) / 256), 256, 0, st>>>(a, n_records);

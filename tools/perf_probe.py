@@ -18,6 +18,7 @@ ap.add_argument("--samples", type=int, default=256)
 ap.add_argument("--bins", type=int, default=200_000)
 ap.add_argument("--states", type=int, default=5)
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--direct", action="store_true", help="also time the in-register emission kernel")
 ap.add_argument("--gen", type=int, default=16, help="distinct synthetic samples generated on the host (tiled)")
 a = ap.parse_args()
 
@@ -68,9 +69,16 @@ def timeit(fn, name, bytes_per_cell):
 B = 4 + 8 * S
 timeit(lambda: co.run_device(obs_t, ref_t, phi_t, exp_t, ll, path, calls, ncalls, what=1, mode=_lib.EMISSION_TABLE), "emission_table", B)
 ll_tab = ll.clone()
-timeit(lambda: co.run_device(obs_t, ref_t, phi_t, exp_t, ll, path, calls, ncalls, what=1, mode=_lib.EMISSION_DIRECT), "emission_direct", B)
-diff = (ll - ll_tab).abs()
-print("table vs direct: max abs", float(diff.max()), "max rel", float((diff / ll.abs().clamp_min(1e-3)).max()))
+if a.direct:
+    timeit(lambda: co.run_device(obs_t, ref_t, phi_t, exp_t, ll, path, calls, ncalls, what=1, mode=_lib.EMISSION_DIRECT), "emission_direct", B)
+    diff = (ll - ll_tab).abs()
+    print("table vs direct: max abs", float(diff.max()), "max rel", float((diff / ll.abs().clamp_min(1e-3)).max()))
+    co.run_device(obs_t, ref_t, phi_t, exp_t, ll, path, calls, ncalls, what=1, mode=_lib.EMISSION_TABLE)
 timeit(lambda: co.run_device(obs_t, ref_t, phi_t, exp_t, ll, path, calls, ncalls, what=2), "viterbi", 8 * S + 1)
+_lib.profile(True)
+for _ in range(3):
+    co.run_device(obs_t, ref_t, phi_t, exp_t, ll, path, calls, ncalls, what=2)
+print("per kernel ms:", {k: round(v[1] / v[0], 4) for k, v in _lib.profile_read().items()})
+_lib.profile(False)
 timeit(lambda: co.run_device(obs_t, ref_t, phi_t, exp_t, ll, path, calls, ncalls, what=3), "emission+viterbi", B + 1)
 print("ncalls", ncalls[:8].tolist(), "status", _lib.load().edb200_status(0))
