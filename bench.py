@@ -236,47 +236,48 @@ def gpu_arm(a, rank, world):
     total_calls = int(ncalls.sum())
     status = _lib.load().edb200_status(0)
 
-    # ---- end to end through the C ABI with HOST buffers (pinned): H2D of the counts, D2H of ll + path + calls --------
+    # ---- end to end through the C ABI with HOST buffers (pinned): H2D of the counts inside the timed region, results back
+    # in host memory.  Primary = what CallCNVs returns to the user (R/class_definition.R:311-419): the CNV call table with
+    # its BF / reads.* columns and cor(test, reference) — those sums are taken on the device (callcnvs.cu), so the FP64
+    # likelihood matrix stays in HBM as the cohort's resident `likelihood` slot.  Variants: + the per-bin Viterbi path
+    # (C_hmm's first return value), + the likelihood matrix itself (get_loglike_matrix's return value, 8*S bytes per
+    # bin*sample over PCIe: that copy alone is ~37 ms).
     e2e = None
     if not a.no_e2e:
         hb = _lib.PinnedPool()
         obs_p = hb.empty((ns, nb), np.int32)
         obs_p[:] = obs_h
-        out = dict(ll=hb.empty((ns, S, nb), np.float64), path=hb.empty((ns, nb), np.int8),
-                   calls=hb.empty((ns, cap, 4), np.int32), ncalls=hb.empty((ns,), np.int32))
-        co.run_host(obs_p, ref, phi_h, exp_h, call_cap=cap, out=out)            # warm-up (allocations)
-        barrier()
-        n_e2e = max(2, min(a.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            co.run_host(obs_p, ref, phi_h, exp_h, call_cap=cap, out=out)
-        barrier()
-        dt = (time.perf_counter() - t0) / n_e2e
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if dist:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        base = dict(calls=hb.empty((ns, cap, 4), np.int32), ncalls=hb.empty((ns,), np.int32),
+                    call_stats=hb.empty((ns, cap, 3), np.float64), cor=hb.empty((ns,), np.float64))
+        n_e2e = max(2, min(a.steps, 10))
         h2d = obs_p.nbytes + ref.nbytes + phi_h.nbytes + exp_h.nbytes
-        d2h = sum(v.nbytes for v in out.values())
-        e2e = dict(value=world * ns * nb / float(t[0]), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                   ms_per_step=1e3 * float(t[0]),
-                   api="edb200_cohort_run_host (C ABI, pinned host buffers; returns ll matrix, Viterbi path and call table); "
-                       "bound by the device-to-host copy of the FP64 ll matrix (8*S bytes per bin*sample over PCIe)")
-        assert int(out["ncalls"].sum()) == total_calls
-        # the same call when the caller leaves the likelihood matrix on the device (CallCNVs only needs path + calls)
-        out2 = dict(path=out["path"], calls=out["calls"], ncalls=out["ncalls"])
-        co.run_host(obs_p, ref, phi_h, exp_h, call_cap=cap, out=out2, want_ll=False)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            co.run_host(obs_p, ref, phi_h, exp_h, call_cap=cap, out=out2, want_ll=False)
-        barrier()
-        dt2 = (time.perf_counter() - t0) / n_e2e
-        t2 = torch.tensor([dt2], dtype=torch.float64, device=dev)
-        if dist:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e["without_ll_copy"] = dict(value=world * ns * nb / float(t2[0]), unit=UNIT, ms_per_step=1e3 * float(t2[0]),
-                                      d2h_bytes_per_step=int(sum(v.nbytes for v in out2.values())),
-                                      note="same call, likelihood matrix left in HBM; path + call table returned")
+
+        def timed(out, **kw):
+            co.run_host(obs_p, ref, phi_h, exp_h, call_cap=cap, out=out, want_stats=True, **kw)     # warm-up (allocations)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                co.run_host(obs_p, ref, phi_h, exp_h, call_cap=cap, out=out, want_stats=True, **kw)
+            barrier()
+            t = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+            if dist:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            assert int(out["ncalls"].sum()) == total_calls
+            return dict(value=world * ns * nb / float(t[0]), unit=UNIT, ms_per_step=1e3 * float(t[0]),
+                        d2h_bytes_per_step=int(sum(v.nbytes for v in out.values())))
+
+        e2e = timed(base, want_ll=False, want_path=False)
+        e2e.update(h2d_bytes_per_step=int(h2d), steps=n_e2e,
+                   api="edb200_cohort_run_host (C ABI, pinned host buffers): counts in; CNV call table, per-call BF / reads.expected / "
+                       "reads.observed sums and cor(test, reference) out — the output of CallCNVs; likelihood matrix resident in HBM; "
+                       "chromosome groups pipelined over PCIe (upload | emission | Viterbi)")
+        with_path = dict(base, path=hb.empty((ns, nb), np.int8))
+        e2e["with_path"] = dict(timed(with_path, want_ll=False, want_path=True), note="+ per-bin Viterbi path (int8) copied back")
+        if not a.no_ll:
+            with_ll = dict(with_path, ll=hb.empty((ns, S, nb), np.float64))
+            e2e["with_ll_copy"] = dict(timed(with_ll, want_ll=True, want_path=True),
+                                       note="+ FP64 likelihood matrix copied back (8*S bytes per bin*sample: bound by the PCIe device-to-host copy)")
+        hb.close()
 
     if rank != 0:
         if dist:
@@ -336,6 +337,7 @@ def main():
     ap.add_argument("--bins", type=int, default=N_BINS)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ll", action="store_true", help="skip the e2e variant that copies the likelihood matrix back")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     a.warmup = max(a.warmup, 3) if a.impl == "graft" else a.warmup

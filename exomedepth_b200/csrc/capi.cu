@@ -35,6 +35,11 @@ struct Context {
     cudaStream_t stream = nullptr;       // used by the host-pointer entry points
     cudaStream_t stream2 = nullptr;      // drains results to the host while `stream` computes the next chunk
     cudaEvent_t chunk_done[16] = {};
+    // chromosome-group pipeline: copy-in, emission and one Viterbi stream per group, forked from / joined to the caller's stream
+    static constexpr int kMaxParts = 6;
+    cudaStream_t s_copy = nullptr, s_em = nullptr, s_vit[kMaxParts] = {};
+    cudaEvent_t ev_fork = nullptr, ev_copy[kMaxParts] = {}, ev_em[kMaxParts] = {}, ev_vit[kMaxParts] = {}, ev_setup = nullptr;
+    int* d_queue = nullptr;              // work-item counter of the emission lattice kernel
     unsigned* d_flags = nullptr;         // sticky device warning word
     unsigned sticky = 0;
     std::vector<DevBuf*> bufs;
@@ -50,8 +55,8 @@ struct EventTimer : edb::KernelTimer {
     struct Interval { std::string name; cudaEvent_t e0, e1; };
     std::vector<Interval> done;
     std::vector<cudaEvent_t> pool;
-    std::string open_name;
-    cudaEvent_t open_ev = nullptr;
+    struct Open { cudaStream_t st; std::string name; cudaEvent_t ev; };
+    std::vector<Open> open;           // one open interval per stream (the group pipeline launches on several)
     cudaEvent_t get()
     {
         if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
@@ -63,9 +68,15 @@ struct EventTimer : edb::KernelTimer {
     {
         cudaEvent_t e = get();
         cudaEventRecord(e, st);
-        if (open_ev) done.push_back({open_name, open_ev, e});
-        if (name) { open_name = name; open_ev = e; }
-        else open_ev = nullptr;
+        size_t k = 0;
+        while (k < open.size() && open[k].st != st) k++;
+        if (k < open.size()) {
+            done.push_back({open[k].name, open[k].ev, e});
+            if (name) { open[k].name = name; open[k].ev = e; }
+            else open.erase(open.begin() + k);
+        } else if (name) {
+            open.push_back({st, name, e});
+        }
         // an event that only closes an interval is owned by that interval; one that opens the next is shared
     }
     std::string read()
@@ -74,9 +85,15 @@ struct EventTimer : edb::KernelTimer {
         std::vector<std::string> names;
         std::vector<double> total;
         std::vector<int> count;
+        const bool timeline = getenv("EDB200_TIMELINE") != nullptr;      // development aid: start / duration of every launch
         for (auto& iv : done) {
             float ms = 0;
             cudaEventElapsedTime(&ms, iv.e0, iv.e1);
+            if (timeline) {
+                float t0 = 0;
+                cudaEventElapsedTime(&t0, done.front().e0, iv.e0);
+                fprintf(stderr, "[timeline] %-18s start %8.3f ms  dur %7.3f ms\n", iv.name.c_str(), t0, ms);
+            }
             size_t k = 0;
             while (k < names.size() && names[k] != iv.name) k++;
             if (k == names.size()) { names.push_back(iv.name); total.push_back(0); count.push_back(0); }
@@ -208,11 +225,20 @@ struct edb200_cohort {
     int64_t total_tiles = 0;
     int lt_pitch = 0;
     DevBuf chains, lt, odds_d, tile_base, decay;
-    DevBuf sched_begin, sched_items;     // sweep schedule for `sched_groups` groups of samples
-    int sched_groups = 0;
-    int sched_warps = 4;                 // sweep warps per CTA the schedule was built for
+    // Chromosome groups ("parts"): the chains are split by length so that the emission of the long chromosomes can
+    // finish — and their sweeps, the critical path, can start — while the rest is still being computed (or uploaded).
+    struct Part {
+        std::vector<int32_t> chains;     // ascending chain ids
+        edb::BinRanges ranges;           // 16-bin aligned, merged bin ranges covering the chains
+        int max_tiles = 0;
+        DevBuf chain_list, sched_begin, sched_items;   // device chain list; sweep schedule for `sched_groups` sample groups
+        int sched_groups = 0;
+        int sched_warps = 4;             // sweep warps per CTA the schedule was built for
+        int sched_ctas = 1;              // sweep CTAs that have work
+    };
+    std::vector<Part> plans[Context::kMaxParts + 1];   // plans[n]: the split into n parts (built on first use)
     // per-batch scratch
-    DevBuf consts, bp, ccalls, cncalls, maxima, fw_grid, fw_chain, fw_out, fw_best;
+    DevBuf consts, bp, ccalls, cncalls, maxima, fw_grid, fw_chain, fw_out, fw_best, lattices;
     int last_host_samples = 0;           // samples whose likelihoods the last host-pointer run left in h_ll
     // host-mode staging
     DevBuf h_obs, h_ref, h_phi, h_exp, h_ll, h_path, h_calls, h_ncalls, h_stats, h_cor;
@@ -255,6 +281,19 @@ int edb200_init(int device)
         CU(cudaMalloc(&g.d_flags, sizeof(unsigned)));
         CU(cudaMemset(g.d_flags, 0, sizeof(unsigned)));
     }
+    if (!g.s_em) {
+        CU(cudaStreamCreateWithFlags(&g.s_copy, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&g.s_em, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&g.ev_setup, cudaEventDisableTiming));
+        for (int p = 0; p < Context::kMaxParts; p++) {
+            CU(cudaStreamCreateWithFlags(&g.s_vit[p], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&g.ev_copy[p], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&g.ev_em[p], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&g.ev_vit[p], cudaEventDisableTiming));
+        }
+        CU(cudaMalloc(&g.d_queue, sizeof(int)));
+    }
     g.ready = true;
     return 0;
 }
@@ -276,6 +315,20 @@ void edb200_shutdown(void)
         for (cudaEvent_t& e : g.chunk_done) cudaEventDestroy(e);
     }
     g.stream2 = nullptr;
+    if (g.s_em) {
+        cudaStreamDestroy(g.s_copy);
+        cudaStreamDestroy(g.s_em);
+        cudaEventDestroy(g.ev_fork);
+        cudaEventDestroy(g.ev_setup);
+        for (int p = 0; p < Context::kMaxParts; p++) {
+            cudaStreamDestroy(g.s_vit[p]);
+            cudaEventDestroy(g.ev_copy[p]);
+            cudaEventDestroy(g.ev_em[p]);
+            cudaEventDestroy(g.ev_vit[p]);
+        }
+        cudaFree(g.d_queue);
+    }
+    g.s_em = nullptr;
     g.ready = false;
 }
 
@@ -319,7 +372,7 @@ int edb200_profile(int enable)
     if (int rc = need_ctx()) return rc;
     cudaDeviceSynchronize();
     g_event_timer.done.clear();
-    g_event_timer.open_ev = nullptr;
+    g_event_timer.open.clear();
     edb::g_timer = enable ? &g_event_timer : nullptr;
     return 0;
 }
@@ -384,7 +437,11 @@ int run_emission_scalar(edb::CountsView cv, const double* d_phi, const double* d
         if (edb::emission_table_smem_bytes(d) > g.smem_optin)
             return fail(EDB200_ERR_CUDA, "device offers %zu B of shared memory per CTA; the lattice kernel needs %zu",
                         g.smem_optin, edb::emission_table_smem_bytes(d));
-        edb::launch_emission_table(cv, d_consts, n_samples, S, n_bins, d, out, g.d_flags, g.n_sms, st);
+        edb::BinRanges all{};
+        all.n = 1;
+        all.b0[0] = 0;
+        all.b1[0] = n_bins;
+        edb::launch_emission_table(cv, d_consts, n_samples, S, all, d, out, g.d_flags, g.d_queue, g.n_sms, nullptr, 0, st);
     } else {
         edb::launch_emission_direct(cv, d_consts, n_samples, S, n_bins, out, g.d_flags, st);
     }
@@ -528,7 +585,11 @@ int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const d
     a.ncalls = (int32_t*)cs.ncalls.p;
     a.call_cap = cap;
     a.flags = g.d_flags;
-    g_launches += edb::launch_viterbi(a, n_tiles, st);
+    a.chain_list = nullptr;
+    a.n_list = 1;
+    a.max_list_tiles = n_tiles;
+    g_launches += edb::launch_viterbi(a, st);
+    g_launches += edb::launch_viterbi_compact(a, st);
     if (int rc = check_kernel("viterbi")) return rc;
 
     std::vector<int8_t> p8(nobs);
@@ -639,7 +700,13 @@ void edb200_cohort_destroy(edb200_cohort* c)
     if (!c) return;
     std::lock_guard<std::mutex> lk(g_mu);
     cudaDeviceSynchronize();
-    DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->tile_base, &c->decay, &c->fw_grid, &c->fw_chain, &c->fw_out, &c->fw_best, &c->sched_begin, &c->sched_items, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->maxima,
+    for (auto& plan : c->plans)
+        for (auto& part : plan) {
+            release(part.chain_list);
+            release(part.sched_begin);
+            release(part.sched_items);
+        }
+    DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->tile_base, &c->decay, &c->fw_grid, &c->fw_chain, &c->fw_out, &c->fw_best, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->maxima, &c->lattices,
                      &c->h_obs, &c->h_ref, &c->h_phi, &c->h_exp, &c->h_ll, &c->h_path, &c->h_calls, &c->h_ncalls, &c->h_stats, &c->h_cor};
     for (DevBuf* b : all) release(*b);
     delete c;
@@ -662,6 +729,214 @@ int edb200_cohort_table_copy(edb200_cohort* c, void* device_buf, int direction, 
     return 0;
 }
 
+// ---- chromosome-group plans --------------------------------------------------------------------------
+// Split the chains into n_parts groups by descending length (cumulative bin fractions below) and describe each
+// group by its chain list and by the 16-bin aligned ranges of the likelihood matrix its chains read.
+static int build_plan(edb200_cohort* c, int n_parts)
+{
+    static const double kCuts[Context::kMaxParts + 1][Context::kMaxParts] = {
+        {}, {1.0}, {0.45, 1.0}, {0.35, 0.7, 1.0}, {0.3, 0.6, 0.85, 1.0}, {0.25, 0.5, 0.75, 0.9, 1.0}, {0.25, 0.5, 0.7, 0.85, 0.95, 1.0}};
+    std::vector<edb200_cohort::Part>& plan = c->plans[n_parts];
+    if (!plan.empty()) return 0;
+    std::vector<int> order(c->n_chains);
+    for (int i = 0; i < c->n_chains; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return c->chains_h[x].nobs > c->chains_h[y].nobs; });
+    plan.resize(n_parts);
+    int64_t cum = 0;
+    int part = 0;
+    for (int oc = 0; oc < c->n_chains; oc++) {
+        const int ch = order[oc];
+        while (part + 1 < n_parts && !plan[part].chains.empty() && (double)cum >= kCuts[n_parts][part] * (double)c->n_bins) part++;
+        plan[part].chains.push_back(ch);
+        cum += c->chains_h[ch].n_em;
+    }
+    while (!plan.empty() && plan.back().chains.empty()) plan.pop_back();
+    for (auto& pt : plan) {
+        std::sort(pt.chains.begin(), pt.chains.end());
+        std::vector<std::pair<int64_t, int64_t>> rs;
+        for (int ch : pt.chains) {
+            const edb::ChainDesc& cd = c->chains_h[ch];
+            const int64_t b0 = (cd.em_off + 1) & ~(int64_t)15;
+            const int64_t b1 = std::min<int64_t>(c->n_bins, (cd.em_off + 1 + cd.n_em + 15) & ~(int64_t)15);
+            if (!rs.empty() && b0 <= rs.back().second) rs.back().second = std::max(rs.back().second, b1);
+            else rs.push_back({b0, b1});
+            pt.max_tiles = std::max(pt.max_tiles, edb::viterbi_chain_tiles(cd));
+        }
+        while ((int)rs.size() > edb::kMaxBinRanges) {          // close the smallest gap (those bins are then computed twice)
+            size_t best = 1;
+            for (size_t i = 2; i < rs.size(); i++)
+                if (rs[i].first - rs[i - 1].second < rs[best].first - rs[best - 1].second) best = i;
+            rs[best - 1].second = rs[best].second;
+            rs.erase(rs.begin() + best);
+        }
+        pt.ranges.n = (int)rs.size();
+        for (size_t i = 0; i < rs.size(); i++) { pt.ranges.b0[i] = rs[i].first; pt.ranges.b1[i] = rs[i].second; }
+        if (int rc = ensure(pt.chain_list, pt.chains.size() * 4)) return rc;
+        CU(cudaMemcpy(pt.chain_list.p, pt.chains.data(), pt.chains.size() * 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+static bool use_table(const edb200_cohort* c, int mode)
+{
+    if (mode == EDB200_EMISSION_TABLE) return true;
+    return mode == EDB200_EMISSION_AUTO && c->n_bins >= 4 * (int64_t)(kTableK + 2 * kTableRN);
+}
+
+// how many chromosome groups a batch is pipelined over (1 = emission, then Viterbi, on the caller's stream)
+static int pick_parts(const edb200_cohort* c, int mode, int wanted)
+{
+    if (const char* e = getenv("EDB200_PARTS")) wanted = atoi(e);
+    if (!use_table(c, mode) || c->n_chains < 2 * wanted) return 1;      // small panels: launch-bound, nothing to overlap
+    return wanted < 1 ? 1 : wanted > Context::kMaxParts ? Context::kMaxParts : wanted;
+}
+
+// lattice_mode: 0 = one launch covers the batch; 1 = first part of a pipelined batch (keeps the lattices in HBM);
+// 2 = later part (reloads them)
+static int emission_part(edb200_cohort* c, const edb200_batch* b, const edb::BinRanges& rg, bool whole, int mode, int lattice_mode,
+                         cudaStream_t st)
+{
+    const int S = c->S, ns = b->n_samples;
+    edb::CountsView cv{b->observed, b->obs_stride, b->reference, b->ref_stride, 0};
+    edb::LLView out{b->ll, (int64_t)S * b->ll_stride, b->ll_stride};
+    edb::StateConst* consts = (edb::StateConst*)c->consts.p;
+    if (use_table(c, mode)) {
+        edb::TableDims d{kTableK, kTableRN, kTableRN};
+        if (edb::emission_table_smem_bytes(d) > g.smem_optin)
+            return fail(EDB200_ERR_CUDA, "device offers %zu B of shared memory per CTA; the lattice kernel needs %zu",
+                        g.smem_optin, edb::emission_table_smem_bytes(d));
+        if (lattice_mode)
+            if (int rc = ensure(c->lattices, (size_t)ns * S * (kTableK + 2 * kTableRN) * 8)) return rc;
+        edb::prof_mark("emission", st);
+        edb::launch_emission_table(cv, consts, ns, S, rg, d, out, g.d_flags, g.d_queue, g.n_sms, (double*)c->lattices.p, lattice_mode, st);
+    } else {
+        if (!whole) return fail(EDB200_ERR_ARG, "internal: the in-register emission kernel covers whole rows only");
+        edb::prof_mark("emission_direct", st);
+        edb::launch_emission_direct(cv, consts, ns, S, c->n_bins, out, g.d_flags, st);
+    }
+    edb::prof_mark(nullptr, st);
+    g_launches++;
+    return check_kernel("emission");
+}
+
+static int state_setup(edb200_cohort* c, const edb200_batch* b, cudaStream_t st)
+{
+    if (int rc = ensure(c->consts, (size_t)b->n_samples * c->S * sizeof(edb::StateConst))) return rc;
+    edb::prof_mark("state_setup", st);
+    edb::launch_state_setup(b->n_samples, c->S, b->phi, b->expected, (const double*)c->odds_d.p, (edb::StateConst*)c->consts.p, st);
+    edb::prof_mark(nullptr, st);
+    g_launches++;
+    return check_kernel("state_setup");
+}
+
+// scratch + arguments shared by every part of a Viterbi pass over batch b
+static int viterbi_prepare(edb200_cohort* c, const edb200_batch* b, edb::ViterbiArgs& a, CUtensorMap* ll_map)
+{
+    const int S = c->S, ns = b->n_samples;
+    if (!b->path || !b->calls || !b->ncalls || b->call_cap < 1 || b->path_stride < c->n_bins)
+        return fail(EDB200_ERR_ARG, "Viterbi outputs missing in batch");
+    if ((b->ll_stride & 15) || (reinterpret_cast<uintptr_t>(b->ll) & 127))
+        return fail(EDB200_ERR_ARG, "Viterbi needs ll_stride to be a multiple of 16 and ll 128-byte aligned (whole 128-byte lines per row tile)");
+    const int ccap = b->call_cap;
+    const int G = 32 / S;
+    const int64_t groups = (ns + G - 1) / G;
+    if (int rc = ensure(c->bp, (size_t)groups * (c->total_tiles + 1) * edb::viterbi_record_bytes())) return rc;
+    if (int rc = ensure(c->ccalls, (size_t)ns * c->n_chains * ccap * 16)) return rc;
+    if (int rc = ensure(c->cncalls, (size_t)ns * c->n_chains * 4)) return rc;
+    a = edb::ViterbiArgs{};
+    a.chains = (const edb::ChainDesc*)c->chains.p;
+    a.n_chains = c->n_chains;
+    a.n_samples = ns;
+    a.n_states = S;
+    a.ll = b->ll;
+    a.ll_sample_stride = (int64_t)S * b->ll_stride;
+    a.ll_state_stride = b->ll_stride;
+    if (int rc = make_ll_map(b->ll, (int64_t)ns * S, b->ll_stride, b->ll_stride, S, ll_map)) return rc;
+    a.ll_map = ll_map;
+    for (int j = 0; j < S; j++) a.perm[j] = c->perm[j];
+    a.groups = (int)groups;
+    a.lt = (const double*)c->lt.p;
+    a.bp = (uint32_t*)c->bp.p;
+    a.bp_tile_base = (const int32_t*)c->tile_base.p;
+    a.tail_other = -100.0;                                 // R/class_definition.R:364
+    a.path = b->path;
+    a.path_stride = b->path_stride;
+    a.chain_calls = (int32_t*)c->ccalls.p;
+    a.chain_ncalls = (int32_t*)c->cncalls.p;
+    a.chain_call_cap = ccap;
+    a.calls = b->calls;
+    a.ncalls = b->ncalls;
+    a.call_cap = b->call_cap;
+    a.flags = g.d_flags;
+    return 0;
+}
+
+// sweep, tilemap, trace, expand of one part on `st`; the schedule is rebuilt when the number of sample groups changes
+// `packed` > 0: the sweep shares the GPU with the emission kernel of the next part (a sweep CTA owns its SM's shared
+// memory, so does an emission CTA): its CTAs are filled instead of spread over all SMs — 1: one warp per SM
+// sub-partition, which keeps the long chains of the first part at full speed; 2: two per sub-partition (shorter chains,
+// half the SMs).
+static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiArgs a, int packed, cudaStream_t st)
+{
+    if (pt.sched_groups != a.groups) {
+        std::vector<int32_t> nobs(pt.chains.size());
+        for (size_t i = 0; i < pt.chains.size(); i++) nobs[i] = c->chains_h[pt.chains[i]].nobs;
+        const char* force = getenv("EDB200_SWEEP_WARPS");          // experiments: 4 or 8
+        pt.sched_warps = force ? (atoi(force) == 8 ? 8 : 4) : packed == 1 ? 4 : packed == 2 ? 8 : edb::viterbi_pick_warps(nobs.data(), (int)nobs.size(), a.groups, g.n_sms);
+        const int64_t n_items = (int64_t)nobs.size() * a.groups;
+        const int sched_ctas = packed ? (int)std::min<int64_t>(g.n_sms, (n_items + pt.sched_warps - 1) / pt.sched_warps) : g.n_sms;
+        std::vector<int32_t> begin, items;
+        edb::viterbi_schedule(nobs.data(), (int)nobs.size(), a.groups, sched_ctas, pt.sched_warps, begin, items);
+        for (size_t i = 0; i < items.size(); i += 2) items[i] = pt.chains[items[i]];      // index in the part -> chain id
+        // trailing sweep CTAs without work are not launched
+        int n_ctas = sched_ctas;
+        while (n_ctas > 1 && begin[(size_t)(n_ctas - 1) * pt.sched_warps] == begin[(size_t)n_ctas * pt.sched_warps]) n_ctas--;
+        pt.sched_ctas = n_ctas;
+        if (int rc = ensure(pt.sched_begin, begin.size() * 4)) return rc;
+        if (int rc = ensure(pt.sched_items, items.size() * 4 + 8)) return rc;
+        CU(cudaMemcpyAsync(pt.sched_begin.p, begin.data(), begin.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(pt.sched_items.p, items.data(), items.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));          // the vectors go out of scope
+        pt.sched_groups = a.groups;
+    }
+    a.chain_list = (const int32_t*)pt.chain_list.p;
+    a.n_list = (int)pt.chains.size();
+    a.max_list_tiles = pt.max_tiles;
+    a.warps_per_cta = pt.sched_warps;
+    a.n_slots = pt.sched_ctas * pt.sched_warps;
+    a.sched_begin = (const int32_t*)pt.sched_begin.p;
+    a.sched_items = (const int32_t*)pt.sched_items.p;
+    g_launches += edb::launch_viterbi(a, st);
+    return check_kernel("viterbi");
+}
+
+static int call_summary(edb200_cohort* c, const edb200_batch* b, bool stats, bool cor, cudaStream_t st)
+{
+    stats = stats && b->call_stats;
+    cor = cor && b->cor;
+    if (!stats && !cor) return 0;
+    if (stats && (!b->calls || !b->ncalls || b->call_cap < 1))
+        return fail(EDB200_ERR_ARG, "CallCNVs post-processing needs the calls / ncalls of a Viterbi pass");
+    const int S = c->S;
+    edb::CallSummaryArgs a{};
+    a.n_samples = b->n_samples;
+    a.n_states = S;
+    a.n_bins = c->n_bins;
+    a.counts = edb::CountsView{b->observed, b->obs_stride, b->reference, b->ref_stride, 0};
+    a.expected = b->expected;
+    a.ll = b->ll;
+    a.ll_sample_stride = (int64_t)S * b->ll_stride;
+    a.ll_state_stride = b->ll_stride;
+    for (int j = 0; j < S; j++) a.perm[j] = c->perm[j];
+    a.calls = b->calls;
+    a.ncalls = b->ncalls;
+    a.call_cap = b->call_cap;
+    a.stats = stats ? b->call_stats : nullptr;
+    a.cor = cor ? b->cor : nullptr;
+    g_launches += edb::launch_call_summary(a, st);
+    return check_kernel("call_summary");
+}
+
 int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, int emission_mode, void* cuda_stream)
 {
     if (int rc = need_ctx()) return rc;
@@ -670,88 +945,49 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
     if (!b->ll || !b->observed || !b->reference || !b->phi || !b->expected) return fail(EDB200_ERR_ARG, "null device pointer in batch");
     if (b->obs_stride < c->n_bins || b->ll_stride < c->n_bins) return fail(EDB200_ERR_ARG, "stride smaller than n_bins");
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    const int S = c->S, ns = b->n_samples;
+    edb::ViterbiArgs va{};
+    alignas(64) CUtensorMap ll_map;
+    if ((what & 2)) if (int rc = viterbi_prepare(c, b, va, &ll_map)) return rc;
 
-    if (what & 1) {
-        if (int rc = ensure(c->consts, (size_t)ns * S * sizeof(edb::StateConst))) return rc;
-        edb::CountsView cv{b->observed, b->obs_stride, b->reference, b->ref_stride, 0};
-        edb::LLView out{b->ll, (int64_t)S * b->ll_stride, b->ll_stride};
-        if (int rc = run_emission_scalar(cv, b->phi, b->expected, (const double*)c->odds_d.p, (edb::StateConst*)c->consts.p,
-                                         ns, S, c->n_bins, out, emission_mode, st))
-            return rc;
+    // Device-resident batches run emission, then Viterbi (1 part) unless EDB200_PARTS asks otherwise: both kernels own
+    // their SM's shared memory, so overlapping them takes SMs away from the sweep's critical chains — measured slower
+    // (3.0 -> 3.5 ms at 256 x 200k x 5).  The host-pointer call pipelines over PCIe instead (edb200_cohort_run_host).
+    const int n_parts = (what & 3) == 3 ? pick_parts(c, emission_mode, 1) : 1;
+    if (int rc = build_plan(c, n_parts)) return rc;
+    std::vector<edb200_cohort::Part>& plan = c->plans[n_parts];
+    if (plan.size() <= 1) {
+        // ---- one pass: emission, then Viterbi, on the caller's stream
+        if (what & 1) {
+            if (int rc = state_setup(c, b, st)) return rc;
+            edb::BinRanges all{};
+            all.n = 1;
+            all.b0[0] = 0;
+            all.b1[0] = c->n_bins;
+            if (int rc = emission_part(c, b, all, true, emission_mode, 0, st)) return rc;
+        }
+        if (what & 2)
+            if (int rc = viterbi_part(c, plan[0], va, 0, st)) return rc;
+    } else {
+        // ---- chromosome-group pipeline: the emission of group p+1 runs while group p is being swept.  Forked from
+        // and joined back into the caller's stream, so the call keeps its "enqueue on cuda_stream" contract.
+        CU(cudaEventRecord(g.ev_fork, st));
+        CU(cudaStreamWaitEvent(g.s_em, g.ev_fork, 0));
+        if (int rc = state_setup(c, b, g.s_em)) return rc;
+        for (size_t p = 0; p < plan.size(); p++) {
+            if (int rc = emission_part(c, b, plan[p].ranges, false, emission_mode, p == 0 ? 1 : 2, g.s_em)) return rc;
+            CU(cudaEventRecord(g.ev_em[p], g.s_em));
+            CU(cudaStreamWaitEvent(g.s_vit[p], g.ev_em[p], 0));
+            if (int rc = viterbi_part(c, plan[p], va, p == 0 ? 1 : 2, g.s_vit[p])) return rc;
+            CU(cudaEventRecord(g.ev_vit[p], g.s_vit[p]));
+        }
+        for (size_t p = 0; p < plan.size(); p++) CU(cudaStreamWaitEvent(st, g.ev_vit[p], 0));
     }
     if (what & 2) {
-        if (!b->path || !b->calls || !b->ncalls || b->call_cap < 1 || b->path_stride < c->n_bins)
-            return fail(EDB200_ERR_ARG, "Viterbi outputs missing in batch");
-        if ((b->ll_stride & 15) || (reinterpret_cast<uintptr_t>(b->ll) & 127))
-            return fail(EDB200_ERR_ARG, "Viterbi needs ll_stride to be a multiple of 16 and ll 128-byte aligned (whole 128-byte lines per row tile)");
-        const int ccap = b->call_cap;
-        const int G = 32 / S;
-        const int64_t groups = (ns + G - 1) / G;
-        if (int rc = ensure(c->bp, (size_t)groups * (c->total_tiles + 1) * edb::viterbi_record_bytes())) return rc;
-        if (int rc = ensure(c->ccalls, (size_t)ns * c->n_chains * ccap * 16)) return rc;
-        if (int rc = ensure(c->cncalls, (size_t)ns * c->n_chains * 4)) return rc;
-        edb::ViterbiArgs a{};
-        a.chains = (const edb::ChainDesc*)c->chains.p;
-        a.n_chains = c->n_chains;
-        a.n_samples = ns;
-        a.n_states = S;
-        a.ll = b->ll;
-        a.ll_sample_stride = (int64_t)S * b->ll_stride;
-        a.ll_state_stride = b->ll_stride;
-        alignas(64) CUtensorMap ll_map;
-        if (int rc = make_ll_map(b->ll, (int64_t)ns * S, b->ll_stride, b->ll_stride, S, &ll_map)) return rc;
-        a.ll_map = &ll_map;
-        for (int j = 0; j < S; j++) a.perm[j] = c->perm[j];
-        if (c->sched_groups != (int)groups) {
-            std::vector<int32_t> nobs(c->n_chains);
-            for (int ch = 0; ch < c->n_chains; ch++) nobs[ch] = c->chains_h[ch].nobs;
-            const char* force = getenv("EDB200_SWEEP_WARPS");          // experiments: 4 or 8
-            c->sched_warps = force ? (atoi(force) == 8 ? 8 : 4) : edb::viterbi_pick_warps(nobs.data(), c->n_chains, (int)groups, g.n_sms);
-            if (int rc = upload_schedule(nobs, (int)groups, g.n_sms, c->sched_warps, c->sched_begin, c->sched_items, st)) return rc;
-            c->sched_groups = (int)groups;
-        }
-        a.groups = (int)groups;
-        a.warps_per_cta = c->sched_warps;
-        a.n_slots = g.n_sms * c->sched_warps;
-        a.sched_begin = (const int32_t*)c->sched_begin.p;
-        a.sched_items = (const int32_t*)c->sched_items.p;
-        a.lt = (const double*)c->lt.p;
-        a.bp = (uint32_t*)c->bp.p;
-        a.bp_tile_base = (const int32_t*)c->tile_base.p;
-        a.tail_other = -100.0;                                 // R/class_definition.R:364
-        a.path = b->path;
-        a.path_stride = b->path_stride;
-        a.chain_calls = (int32_t*)c->ccalls.p;
-        a.chain_ncalls = (int32_t*)c->cncalls.p;
-        a.chain_call_cap = ccap;
-        a.calls = b->calls;
-        a.ncalls = b->ncalls;
-        a.call_cap = b->call_cap;
-        a.flags = g.d_flags;
-        g_launches += edb::launch_viterbi(a, groups * c->total_tiles, st);
-        if (int rc = check_kernel("viterbi")) return rc;
+        g_launches += edb::launch_viterbi_compact(va, st);
+        if (int rc = check_kernel("viterbi_compact")) return rc;
     }
-    if ((what & 4) && (b->call_stats || b->cor)) {
-        if (!b->calls || !b->ncalls || b->call_cap < 1) return fail(EDB200_ERR_ARG, "CallCNVs post-processing needs the calls / ncalls of a Viterbi pass");
-        edb::CallSummaryArgs a{};
-        a.n_samples = ns;
-        a.n_states = S;
-        a.n_bins = c->n_bins;
-        a.counts = edb::CountsView{b->observed, b->obs_stride, b->reference, b->ref_stride, 0};
-        a.expected = b->expected;
-        a.ll = b->ll;
-        a.ll_sample_stride = (int64_t)S * b->ll_stride;
-        a.ll_state_stride = b->ll_stride;
-        for (int j = 0; j < S; j++) a.perm[j] = c->perm[j];
-        a.calls = b->calls;
-        a.ncalls = b->ncalls;
-        a.call_cap = b->call_cap;
-        a.stats = b->call_stats;
-        a.cor = b->cor;
-        g_launches += edb::launch_call_summary(a, st);
-        if (int rc = check_kernel("call_summary")) return rc;
-    }
+    if (what & 4)
+        if (int rc = call_summary(c, b, true, true, st)) return rc;
     return 0;
 }
 
@@ -838,10 +1074,6 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         (rc = ensure(c->h_ncalls, ns * 4)) || (rc = ensure(c->h_stats, b->call_stats ? (size_t)ns * cap * 24 : 8)) ||
         (rc = ensure(c->h_cor, ns * 8)))
         return rc;
-    if (shared_ref) CU(cudaMemcpyAsync(c->h_ref.p, b->reference, nb * 4, cudaMemcpyHostToDevice, st));
-    else CU(cudaMemcpy2DAsync(c->h_ref.p, nb * 4, b->reference, b->ref_stride * 4, nb * 4, ns, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->h_phi.p, b->phi, ns * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->h_exp.p, b->expected, ns * 8, cudaMemcpyHostToDevice, st));
 
     edb200_batch d = *b;
     d.observed = (const int32_t*)c->h_obs.p;
@@ -862,34 +1094,96 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     const bool want_vit = b->path || b->calls || b->ncalls || b->call_stats;
     c->last_host_samples = ns;
 
-    // The likelihood matrix is 8*S bytes per bin and sample on the way back, against 4 on the way in: the call is
-    // bound by the device-to-host copy.  Samples therefore go through in chunks: the counts of chunk i+1 upload and
-    // its emission kernel runs on `st` while the likelihoods of chunk i drain on the second stream.
-    const int n_chunks = (b->ll && ns >= 2 * kHostChunks) ? kHostChunks : 1;
-    const int per = (ns + n_chunks - 1) / n_chunks;
-    for (int k = 0, s0 = 0; s0 < ns; k++, s0 += per) {
-        const int cnt = ns - s0 < per ? ns - s0 : per;
-        CU(cudaMemcpy2DAsync((int32_t*)c->h_obs.p + (size_t)s0 * nb, nb * 4, b->observed + (size_t)s0 * b->obs_stride, b->obs_stride * 4,
-                             nb * 4, cnt, cudaMemcpyHostToDevice, st));
-        edb200_batch e = d;
-        e.n_samples = cnt;
-        e.observed = d.observed + (size_t)s0 * nb;
-        if (!shared_ref) e.reference = d.reference + (size_t)s0 * nb;
-        e.phi = d.phi + s0;
-        e.expected = d.expected + s0;
-        e.ll = d.ll + (size_t)s0 * S * nbp;
-        if ((rc = edb200_cohort_run_device(c, &e, 1, emission_mode, st))) return rc;
-        if (b->ll) {
-            CU(cudaEventRecord(g.chunk_done[k], st));
-            CU(cudaStreamWaitEvent(g.stream2, g.chunk_done[k], 0));
-            CU(cudaMemcpy2DAsync(b->ll + (size_t)s0 * S * b->ll_stride, b->ll_stride * 8, e.ll, nbp * 8, nb * 8, (size_t)cnt * S,
-                                 cudaMemcpyDeviceToHost, g.stream2));
-        }
-    }
-    if (want_vit && (rc = edb200_cohort_run_device(c, &d, 2, emission_mode, st))) return rc;
-    if ((d.call_stats || d.cor) && (rc = edb200_cohort_run_device(c, &d, 4, emission_mode, st))) return rc;
+    const int n_parts = want_vit ? pick_parts(c, emission_mode, Context::kMaxParts) : 1;
+    if ((rc = build_plan(c, n_parts))) return rc;
+    std::vector<edb200_cohort::Part>& plan = c->plans[n_parts];
 
-    if (b->path) CU(cudaMemcpy2DAsync(b->path, b->path_stride, c->h_path.p, nb, nb, ns, cudaMemcpyDeviceToHost, st));
+    if (plan.size() > 1) {
+        // ---- chromosome-group pipeline over PCIe: the counts of the long chromosomes go up first; their emission and
+        // sweep (the critical path) run while the other groups are still uploading; results drain per group.
+        edb::ViterbiArgs va{};
+        alignas(64) CUtensorMap ll_map;
+        if ((rc = viterbi_prepare(c, &d, va, &ll_map))) return rc;
+        cudaStream_t sc = g.s_copy;
+        if (shared_ref) CU(cudaMemcpyAsync(c->h_ref.p, b->reference, nb * 4, cudaMemcpyHostToDevice, sc));
+        CU(cudaMemcpyAsync(c->h_phi.p, b->phi, ns * 8, cudaMemcpyHostToDevice, sc));
+        CU(cudaMemcpyAsync(c->h_exp.p, b->expected, ns * 8, cudaMemcpyHostToDevice, sc));
+        CU(cudaEventRecord(g.ev_setup, sc));
+        CU(cudaStreamWaitEvent(g.s_em, g.ev_setup, 0));
+        if ((rc = state_setup(c, &d, g.s_em))) return rc;
+        for (size_t p = 0; p < plan.size(); p++) {
+            const edb::BinRanges& rg = plan[p].ranges;
+            edb::prof_mark("h2d_counts", sc);
+            for (int q = 0; q < rg.n; q++) {
+                const int64_t r0 = rg.b0[q], w = rg.b1[q] - r0;
+                CU(cudaMemcpy2DAsync((int32_t*)c->h_obs.p + r0, nb * 4, b->observed + r0, b->obs_stride * 4, w * 4, ns, cudaMemcpyHostToDevice, sc));
+                if (!shared_ref)
+                    CU(cudaMemcpy2DAsync((int32_t*)c->h_ref.p + r0, nb * 4, b->reference + r0, b->ref_stride * 4, w * 4, ns, cudaMemcpyHostToDevice, sc));
+            }
+            edb::prof_mark(nullptr, sc);
+            CU(cudaEventRecord(g.ev_copy[p], sc));
+            CU(cudaStreamWaitEvent(g.s_em, g.ev_copy[p], 0));
+            if ((rc = emission_part(c, &d, rg, false, emission_mode, p == 0 ? 1 : 2, g.s_em))) return rc;
+            CU(cudaEventRecord(g.ev_em[p], g.s_em));
+            if (b->ll) {
+                CU(cudaStreamWaitEvent(g.stream2, g.ev_em[p], 0));
+                for (int q = 0; q < rg.n; q++) {
+                    const int64_t r0 = rg.b0[q], w = rg.b1[q] - r0;
+                    CU(cudaMemcpy2DAsync(b->ll + r0, b->ll_stride * 8, d.ll + r0, nbp * 8, w * 8, (size_t)ns * S, cudaMemcpyDeviceToHost, g.stream2));
+                }
+            }
+            CU(cudaStreamWaitEvent(g.s_vit[p], g.ev_em[p], 0));
+            static const int pack_rest = getenv("EDB200_PACK") ? atoi(getenv("EDB200_PACK")) : 2;     // experiments
+            if ((rc = viterbi_part(c, plan[p], va, p == 0 ? 1 : pack_rest, g.s_vit[p]))) return rc;
+            if (b->path)
+                for (int q = 0; q < rg.n; q++) {
+                    const int64_t r0 = rg.b0[q], w = rg.b1[q] - r0;
+                    CU(cudaMemcpy2DAsync(b->path + r0, b->path_stride, (int8_t*)c->h_path.p + r0, nb, w, ns, cudaMemcpyDeviceToHost, g.s_vit[p]));
+                }
+            CU(cudaEventRecord(g.ev_vit[p], g.s_vit[p]));
+        }
+        // cor(test, reference) needs the counts only: behind the last upload, beside the kernels of the last parts
+        if ((rc = call_summary(c, &d, false, true, sc))) return rc;
+        CU(cudaEventRecord(g.ev_setup, sc));
+        CU(cudaStreamWaitEvent(st, g.ev_setup, 0));
+        for (size_t p = 0; p < plan.size(); p++) CU(cudaStreamWaitEvent(st, g.ev_vit[p], 0));
+        g_launches += edb::launch_viterbi_compact(va, st);
+        if ((rc = check_kernel("viterbi_compact"))) return rc;
+        if ((rc = call_summary(c, &d, true, false, st))) return rc;
+    } else {
+        if (shared_ref) CU(cudaMemcpyAsync(c->h_ref.p, b->reference, nb * 4, cudaMemcpyHostToDevice, st));
+        else CU(cudaMemcpy2DAsync(c->h_ref.p, nb * 4, b->reference, b->ref_stride * 4, nb * 4, ns, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->h_phi.p, b->phi, ns * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->h_exp.p, b->expected, ns * 8, cudaMemcpyHostToDevice, st));
+        // The likelihood matrix is 8*S bytes per bin and sample on the way back, against 4 on the way in: the call is
+        // bound by the device-to-host copy.  Samples therefore go through in chunks: the counts of chunk i+1 upload and
+        // its emission kernel runs on `st` while the likelihoods of chunk i drain on the second stream.
+        const int n_chunks = (b->ll && ns >= 2 * kHostChunks) ? kHostChunks : 1;
+        const int per = (ns + n_chunks - 1) / n_chunks;
+        for (int k = 0, s0 = 0; s0 < ns; k++, s0 += per) {
+            const int cnt = ns - s0 < per ? ns - s0 : per;
+            CU(cudaMemcpy2DAsync((int32_t*)c->h_obs.p + (size_t)s0 * nb, nb * 4, b->observed + (size_t)s0 * b->obs_stride, b->obs_stride * 4,
+                                 nb * 4, cnt, cudaMemcpyHostToDevice, st));
+            edb200_batch e = d;
+            e.n_samples = cnt;
+            e.observed = d.observed + (size_t)s0 * nb;
+            if (!shared_ref) e.reference = d.reference + (size_t)s0 * nb;
+            e.phi = d.phi + s0;
+            e.expected = d.expected + s0;
+            e.ll = d.ll + (size_t)s0 * S * nbp;
+            if ((rc = edb200_cohort_run_device(c, &e, 1, emission_mode, st))) return rc;
+            if (b->ll) {
+                CU(cudaEventRecord(g.chunk_done[k], st));
+                CU(cudaStreamWaitEvent(g.stream2, g.chunk_done[k], 0));
+                CU(cudaMemcpy2DAsync(b->ll + (size_t)s0 * S * b->ll_stride, b->ll_stride * 8, e.ll, nbp * 8, nb * 8, (size_t)cnt * S,
+                                     cudaMemcpyDeviceToHost, g.stream2));
+            }
+        }
+        if (want_vit && (rc = edb200_cohort_run_device(c, &d, 2, emission_mode, st))) return rc;
+        if ((d.call_stats || d.cor) && (rc = edb200_cohort_run_device(c, &d, 4, emission_mode, st))) return rc;
+        if (b->path) CU(cudaMemcpy2DAsync(b->path, b->path_stride, c->h_path.p, nb, nb, ns, cudaMemcpyDeviceToHost, st));
+    }
+
     if (b->calls && b->call_cap > 0) CU(cudaMemcpyAsync(b->calls, c->h_calls.p, (size_t)ns * cap * 16, cudaMemcpyDeviceToHost, st));
     if (b->ncalls) CU(cudaMemcpyAsync(b->ncalls, c->h_ncalls.p, ns * 4, cudaMemcpyDeviceToHost, st));
     if (b->call_stats && b->call_cap > 0) CU(cudaMemcpyAsync(b->call_stats, c->h_stats.p, (size_t)ns * cap * 24, cudaMemcpyDeviceToHost, st));

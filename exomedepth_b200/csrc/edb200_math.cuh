@@ -35,16 +35,18 @@ constexpr unsigned kFlagNaN = 1u;       // a GSL-style domain error produced NaN
 // log(1+u) for u > -1 with RELATIVE accuracy for small |u| (u = (x-a)/a is known to ~2 ulp).
 __device__ __forceinline__ double log1p_rel(double u)
 {
-    double w = 1.0 + u;
-    double c = u - (w - 1.0);                 // rounding error of 1+u (exact for |u| < 2^52)
-    return log(w) + c / w;
+    // explicit roundings: every instance of this code (lattice build, in-register kernel, cold path) must produce
+    // the same bits, so nothing here is left to the compiler's mul+add contraction
+    const double w = __dadd_rn(1.0, u);
+    const double c = __dsub_rn(u, __dsub_rn(w, 1.0));   // rounding error of 1+u (exact for |u| < 2^52)
+    return __dadd_rn(log(w), __ddiv_rn(c, w));
 }
 
 // Stirling tail S(x) = lgamma(x) - [(x-1/2)ln x - x + ln(2pi)/2], x >= kStirlingMin
 __device__ __forceinline__ double stirling_tail(double x)
 {
-    const double r = 1.0 / x;
-    const double y = r * r;
+    const double r = __ddiv_rn(1.0, x);
+    const double y = __dmul_rn(r, r);
     double s = -3617.0 / 122400.0;
     s = fma(s, y, 1.0 / 156.0);
     s = fma(s, y, -691.0 / 360360.0);
@@ -53,16 +55,16 @@ __device__ __forceinline__ double stirling_tail(double x)
     s = fma(s, y, 1.0 / 1260.0);
     s = fma(s, y, -1.0 / 360.0);
     s = fma(s, y, 1.0 / 12.0);
-    return s * r;
+    return __dmul_rn(s, r);
 }
 
 // lgamma(x) for any finite x > 0: shift up to the Stirling range.
 __device__ __forceinline__ double lgamma_pos(double x)
 {
     double p = 1.0;
-    while (x < kStirlingMin) { p *= x; x += 1.0; }
-    double v = fma(x - 0.5, log(x), -x) + 0.91893853320467274178 + stirling_tail(x);
-    return p == 1.0 ? v : v - log(p);
+    while (x < kStirlingMin) { p = __dmul_rn(p, x); x = __dadd_rn(x, 1.0); }
+    const double v = __dadd_rn(__dadd_rn(fma(__dsub_rn(x, 0.5), log(x), -x), 0.91893853320467274178), stirling_tail(x));
+    return p == 1.0 ? v : __dsub_rn(v, log(p));
 }
 
 // Hoisted constants of one shape parameter a > 0.
@@ -79,9 +81,9 @@ __device__ __forceinline__ GConst make_gconst(double a)
 {
     GConst c;
     c.a = a;
-    c.ra = 1.0 / a;
+    c.ra = __ddiv_rn(1.0, a);
     c.small = !(a >= kStirlingMin);
-    c.lnam1 = log(a) - 1.0;
+    c.lnam1 = __dsub_rn(log(a), 1.0);
     c.tail = c.small ? 0.0 : stirling_tail(a);
     c.lg = c.small ? lgamma_pos(a) : 0.0;
     return c;
@@ -90,14 +92,14 @@ __device__ __forceinline__ GConst make_gconst(double a)
 // lgamma(x) - lgamma(a) for x > 0 (x is a plus a non-negative integer up to rounding).
 __device__ __forceinline__ double gdiff(const GConst& c, double x)
 {
-    const double d = x - c.a;
+    const double d = __dsub_rn(x, c.a);
     if (d == 0.0) return 0.0;
     if (!c.small && x >= kStirlingMin) {
-        const double L = log1p_rel(d * c.ra);
-        return fma(x - 0.5, L, fma(d, c.lnam1, stirling_tail(x) - c.tail));
+        const double L = log1p_rel(__dmul_rn(d, c.ra));
+        return fma(__dsub_rn(x, 0.5), L, fma(d, c.lnam1, __dsub_rn(stirling_tail(x), c.tail)));
     }
     const double lga = c.small ? c.lg : lgamma_pos(c.a);
-    return lgamma_pos(x) - lga;
+    return __dsub_rn(lgamma_pos(x), lga);
 }
 
 // Per (sample, state) constants.
@@ -439,7 +441,7 @@ __device__ __forceinline__ double cell_loglik(const StateConst& sc, int total, i
     data_args(sc.a1, sc.a2, total, observed, x, y, z);
     if (sc.ok && observed >= 0 && total >= observed) {
         // (G1 + G2) - G3 ; identical grouping in the table path so both agree bit for bit when x,y,z agree
-        return (gdiff(sc.g1, x) + gdiff(sc.g2, y)) - gdiff(sc.g12, z);
+        return __dsub_rn(__dadd_rn(gdiff(sc.g1, x), gdiff(sc.g2, y)), gdiff(sc.g12, z));
     }
     return lnbeta_gsl(x, y, flags) - lnbeta_gsl(sc.a1, sc.a2, flags);
 }

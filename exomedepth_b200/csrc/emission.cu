@@ -172,35 +172,41 @@ __device__ __noinline__ void drain_cold(const StateConst* sc, const CountsView& 
 }
 
 // more out-of-lattice cells than the parking list holds: walk the sample again and evaluate exactly those
-__device__ __noinline__ void rescan_cold(const StateConst* sc, const CountsView& c, int sample, int64_t n_bins,
+__device__ __noinline__ void rescan_cold(const StateConst* sc, const CountsView& c, int sample, const BinRanges& rg,
                                          TableDims dims, double* o, unsigned* flags)
 {
     unsigned f = 0;
-    for (int64_t b = threadIdx.x; b < n_bins; b += blockDim.x) {
-        int tot, obs;
-        load_counts(c, sample, b, tot, obs);
-        const int r = tot - obs;
-        if (!((unsigned)obs < (unsigned)dims.K && (unsigned)r < (unsigned)dims.R && (unsigned)tot < (unsigned)dims.N))
-            o[b] = cell_loglik(*sc, tot, obs, f);
-    }
+    for (int q = 0; q < rg.n; q++)
+        for (int64_t b = rg.b0[q] + threadIdx.x; b < rg.b1[q]; b += blockDim.x) {
+            int tot, obs;
+            load_counts(c, sample, b, tot, obs);
+            const int r = tot - obs;
+            if (!((unsigned)obs < (unsigned)dims.K && (unsigned)r < (unsigned)dims.R && (unsigned)tot < (unsigned)dims.N))
+                o[b] = cell_loglik(*sc, tot, obs, f);
+        }
     if (f) atomicOr(flags, f);
 }
 
-__device__ __noinline__ void whole_item_cold(const StateConst* sc, const CountsView& c, int sample, int64_t n_bins,
+__device__ __noinline__ void whole_item_cold(const StateConst* sc, const CountsView& c, int sample, const BinRanges& rg,
                                              double* o, unsigned* flags)
 {
     unsigned f = 0;
-    for (int64_t b = threadIdx.x; b < n_bins; b += blockDim.x) {
-        int tot, obs;
-        load_counts(c, sample, b, tot, obs);
-        o[b] = cell_loglik(*sc, tot, obs, f);
-    }
+    for (int q = 0; q < rg.n; q++)
+        for (int64_t b = rg.b0[q] + threadIdx.x; b < rg.b1[q]; b += blockDim.x) {
+            int tot, obs;
+            load_counts(c, sample, b, tot, obs);
+            o[b] = cell_loglik(*sc, tot, obs, f);
+        }
     if (f) atomicOr(flags, f);
 }
 
+// Work items (sample, state) are dealt through an atomic counter, not by block index: when the SMs are shared with
+// other kernels (the Viterbi sweep of another chromosome group) the CTAs that are resident take all the work.
+// `rg`: the bin ranges this launch covers (whole matrix, or the 16-bin aligned ranges of one chromosome group).
 __global__ void __launch_bounds__(kTableThreads, 1)
 emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n_states, int n_items,
-                      int64_t n_bins, TableDims dims, LLView out, unsigned* __restrict__ flags)
+                      const __grid_constant__ BinRanges rg, TableDims dims, LLView out, unsigned* __restrict__ flags,
+                      int* __restrict__ queue, double* __restrict__ lattices, int lattice_mode)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StateConst* scp = reinterpret_cast<StateConst*>(smem_raw);
@@ -208,21 +214,34 @@ emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n
     double* G2 = G1 + dims.K;
     double* G3 = G2 + dims.R;
     int* cold_n = reinterpret_cast<int*>(G3 + dims.N);
+    int* next_item = cold_n + 1;
     int* cold = cold_n + 4;
 
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (;;) {
+        __syncthreads();     // previous item's gathers are done before the lattices (and next_item) are overwritten
+        if (threadIdx.x == 0) {
+            *next_item = atomicAdd(queue, 1);
+            *cold_n = 0;
+        }
+        __syncthreads();
+        const int item = *next_item;
+        if (item >= n_items) break;
         const int sample = item / n_states, s = item - sample * n_states;
-        __syncthreads();     // previous item's gathers are done before the lattices are overwritten
         for (int i = threadIdx.x; i < (int)(sizeof(StateConst) / 8); i += blockDim.x)
             reinterpret_cast<double*>(scp)[i] = reinterpret_cast<const double*>(consts + item)[i];
-        if (threadIdx.x == 0) *cold_n = 0;
         __syncthreads();
         double* __restrict__ o = out.ptr + sample * out.sample_stride + s * out.state_stride;
         if (!scp->ok) {      // pathological shape parameters: reference NaN/sign semantics, cell by cell
-            whole_item_cold(scp, c, sample, n_bins, o, flags);
+            whole_item_cold(scp, c, sample, rg, o, flags);
             continue;
         }
-        {
+        // lattice_mode 0: build; 1: build and keep a copy in HBM (first chromosome group of a pipelined batch);
+        // 2: reload the copy (later groups: ~213 KB per item from L2 / HBM instead of ~27k lgamma differences)
+        const int n_lat = dims.K + dims.R + dims.N;
+        double* __restrict__ keep = lattices + (int64_t)item * n_lat;
+        if (lattice_mode == 2) {
+            for (int i = threadIdx.x; i < n_lat; i += blockDim.x) G1[i] = __ldcs(keep + i);
+        } else {
             const GConst g1 = scp->g1, g2 = scp->g2, g12 = scp->g12;
             const double a1 = scp->a1, a2 = scp->a2;
             for (int i = threadIdx.x; i < dims.K; i += blockDim.x) G1[i] = gdiff(g1, __dadd_rn(a1, (double)i));
@@ -231,12 +250,11 @@ emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n
                 G3[i] = gdiff(g12, __dadd_rn(a1, __dadd_rn(a2, (double)i)));
         }
         __syncthreads();
+        if (lattice_mode == 1)
+            for (int i = threadIdx.x; i < n_lat; i += blockDim.x) keep[i] = G1[i];
 
         const int32_t* __restrict__ obs_row = c.observed + sample * c.obs_stride;
         const int32_t* __restrict__ oth_row = c.other + sample * c.other_stride;
-        const bool vec = ((reinterpret_cast<uintptr_t>(obs_row) | reinterpret_cast<uintptr_t>(oth_row)) & 15) == 0 &&
-                         (reinterpret_cast<uintptr_t>(o) & 15) == 0;
-        const int64_t n4 = vec ? (n_bins & ~(int64_t)3) : 0;
         const int is_total = c.other_is_total;
         const int K = dims.K, R = dims.R, N = dims.N;
 
@@ -255,55 +273,62 @@ emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n
             if (q < kColdCap) cold[q] = (int)b;
         };
 
-        // the counts of the next iteration are requested before the gathers of this one
-        const int64_t stride = (int64_t)blockDim.x * 4;
-        int64_t b = (int64_t)threadIdx.x * 4;
-        int4 ko = make_int4(0, 0, 0, 0), oo = ko;
-        if (b < n4) {
-            ko = __ldg(reinterpret_cast<const int4*>(obs_row + b));
-            oo = __ldg(reinterpret_cast<const int4*>(oth_row + b));
-        }
-        for (; b < n4; b += stride) {
-            int4 kn = make_int4(0, 0, 0, 0), on = kn;
-            if (b + stride < n4) {
-                kn = __ldg(reinterpret_cast<const int4*>(obs_row + b + stride));
-                on = __ldg(reinterpret_cast<const int4*>(oth_row + b + stride));
+        for (int q = 0; q < rg.n; q++) {
+            const int64_t r0 = rg.b0[q], r1 = rg.b1[q];
+            const bool vec = ((reinterpret_cast<uintptr_t>(obs_row + r0) | reinterpret_cast<uintptr_t>(oth_row + r0)) & 15) == 0 &&
+                             (reinterpret_cast<uintptr_t>(o + r0) & 15) == 0;
+            const int64_t n4 = vec ? r0 + ((r1 - r0) & ~(int64_t)3) : r0;
+            // the counts of the next iteration are requested before the gathers of this one
+            const int64_t stride = (int64_t)blockDim.x * 4;
+            int64_t b = r0 + (int64_t)threadIdx.x * 4;
+            int4 ko = make_int4(0, 0, 0, 0), oo = ko;
+            if (b < n4) {
+                ko = __ldg(reinterpret_cast<const int4*>(obs_row + b));
+                oo = __ldg(reinterpret_cast<const int4*>(oth_row + b));
             }
-            bool i0, i1, i2, i3;
-            double2 v0, v1;
-            v0.x = cell(ko.x, oo.x, i0);
-            v0.y = cell(ko.y, oo.y, i1);
-            v1.x = cell(ko.z, oo.z, i2);
-            v1.y = cell(ko.w, oo.w, i3);
-            __stcs(reinterpret_cast<double2*>(o + b), v0);        // streaming stores: ll is write-once
-            __stcs(reinterpret_cast<double2*>(o + b + 2), v1);
-            if (!(i0 && i1 && i2 && i3)) {                        // rare
-                if (!i0) park(b);
-                if (!i1) park(b + 1);
-                if (!i2) park(b + 2);
-                if (!i3) park(b + 3);
+            for (; b < n4; b += stride) {
+                int4 kn = make_int4(0, 0, 0, 0), on = kn;
+                if (b + stride < n4) {
+                    kn = __ldg(reinterpret_cast<const int4*>(obs_row + b + stride));
+                    on = __ldg(reinterpret_cast<const int4*>(oth_row + b + stride));
+                }
+                bool i0, i1, i2, i3;
+                double2 v0, v1;
+                v0.x = cell(ko.x, oo.x, i0);
+                v0.y = cell(ko.y, oo.y, i1);
+                v1.x = cell(ko.z, oo.z, i2);
+                v1.y = cell(ko.w, oo.w, i3);
+                __stcs(reinterpret_cast<double2*>(o + b), v0);        // streaming stores: ll is write-once
+                __stcs(reinterpret_cast<double2*>(o + b + 2), v1);
+                if (!(i0 && i1 && i2 && i3)) {                        // rare
+                    if (!i0) park(b);
+                    if (!i1) park(b + 1);
+                    if (!i2) park(b + 2);
+                    if (!i3) park(b + 3);
+                }
+                ko = kn;
+                oo = on;
             }
-            ko = kn;
-            oo = on;
-        }
-        for (int64_t bt = n4 + threadIdx.x; bt < n_bins; bt += blockDim.x) {
-            bool in;
-            o[bt] = cell(obs_row[bt], oth_row[bt], in);
-            if (!in) park(bt);
+            for (int64_t bt = n4 + threadIdx.x; bt < r1; bt += blockDim.x) {
+                bool in;
+                o[bt] = cell(obs_row[bt], oth_row[bt], in);
+                if (!in) park(bt);
+            }
         }
         __syncthreads();
         const int n_cold = *cold_n;
-        if (n_cold > kColdCap) rescan_cold(scp, c, sample, n_bins, dims, o, flags);     // lattice far too small for this sample
+        if (n_cold > kColdCap) rescan_cold(scp, c, sample, rg, dims, o, flags);     // lattice far too small for this sample
         else if (n_cold > 0) drain_cold(scp, c, sample, cold, n_cold, o, flags);
     }
 }
 
 void launch_emission_table(CountsView c, const StateConst* consts, int n_samples, int n_states,
-                           int64_t n_bins, TableDims dims, LLView out, unsigned* flags, int n_sms,
-                           cudaStream_t st)
+                           const BinRanges& rg, TableDims dims, LLView out, unsigned* flags, int* queue, int n_sms,
+                           double* lattices, int lattice_mode, cudaStream_t st)
 {
     const int n_items = n_samples * n_states;
-    if (n_items == 0 || n_bins == 0) return;
+    if (n_items == 0 || rg.n == 0) return;
+    cudaMemsetAsync(queue, 0, sizeof(int), st);
     const size_t smem = emission_table_smem_bytes(dims);
     static size_t configured = 0;
     if (smem > configured) {
@@ -311,7 +336,7 @@ void launch_emission_table(CountsView c, const StateConst* consts, int n_samples
         configured = smem;
     }
     const int grid = n_items < n_sms ? n_items : n_sms;
-    emission_table_kernel<<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, n_bins, dims, out, flags);
+    emission_table_kernel<<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices, lattices ? lattice_mode : 0);
 }
 
 }  // namespace edb

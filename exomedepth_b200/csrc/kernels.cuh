@@ -48,10 +48,18 @@ void launch_emission_direct(CountsView c, const StateConst* consts, int n_sample
 
 // batched, per (sample,state) lgamma-difference tables in shared memory + gather
 struct TableDims { int K, R, N; };    // entries for observed, other (=total-observed), total
+constexpr int kMaxBinRanges = 32;
+struct BinRanges {                    // bins [b0[q], b1[q]) for q < n: the whole matrix, or one chromosome group
+    int n;
+    int64_t b0[kMaxBinRanges], b1[kMaxBinRanges];
+};
 size_t emission_table_smem_bytes(TableDims d);
+// `queue`: one int of device scratch per concurrent launch (the kernel's work-item counter; zeroed on `st` here).
+// `lattices`: optional HBM copy of the per-item lattices, n_items * (K + R + N) doubles (K + R + N even);
+// lattice_mode 0 = build only, 1 = build and save, 2 = reload (the same items' later bin ranges).
 void launch_emission_table(CountsView c, const StateConst* consts, int n_samples, int n_states,
-                           int64_t n_bins, TableDims dims, LLView out, unsigned* flags, int n_sms,
-                           cudaStream_t st);
+                           const BinRanges& ranges, TableDims dims, LLView out, unsigned* flags, int* queue, int n_sms,
+                           double* lattices, int lattice_mode, cudaStream_t st);
 
 // per-launch maxima of observed / other / total over the batch -> int32[3]
 void launch_count_maxima(CountsView c, int n_samples, int64_t n_bins, int32_t* maxima3, cudaStream_t st);
@@ -74,6 +82,9 @@ struct ChainDesc {
 struct ViterbiArgs {
     const ChainDesc* chains;      // [n_chains]
     int n_chains;
+    const int32_t* chain_list;    // the chains this launch covers (device, [n_list]); null = chains 0 .. n_list-1
+    int n_list;
+    int max_list_tiles;           // most tiles of any chain in the list (tilemap grid)
     int n_samples;
     int n_states;
     int groups;                   // ceil(n_samples / (32 / n_states)): warps per chromosome
@@ -101,8 +112,10 @@ struct ViterbiArgs {
     unsigned* flags;
 };
 
-// enqueues sweep, tilemap, trace, expand and compact; n_records = groups * (tiles of all chains); returns the number of launches
-int launch_viterbi(const ViterbiArgs& a, int64_t n_records, cudaStream_t st);
+// enqueues sweep, tilemap, trace and expand for the chains of a.chain_list (the schedule must cover exactly those);
+// launch_viterbi_compact then concatenates the per-chromosome call tables of ALL chains.  Both return the number of launches.
+int launch_viterbi(const ViterbiArgs& a, cudaStream_t st);
+int launch_viterbi_compact(const ViterbiArgs& a, cudaStream_t st);
 size_t viterbi_smem_bytes(int n_states, int warps_per_cta);
 int viterbi_pick_warps(const int32_t* chain_nobs, int n_chains, int groups, int n_sms);
 int viterbi_lt_pitch(int n_states);      // doubles per table row: S destination rows of S doubles padded to an even count

@@ -418,15 +418,18 @@ viterbi_sweep_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
 // walk serves all of them.
 template <int S>
 __global__ void __launch_bounds__(256)
-viterbi_tilemap_kernel(ViterbiArgs a, int64_t n_records)
+viterbi_tilemap_kernel(ViterbiArgs a)
 {
     constexpr int G = 32 / S;
     constexpr unsigned kTracked = (S >= 7 ? 0x0FFFFFFFu : ((1u << (4 * S)) - 1u)) | 0xF0000000u;
     constexpr unsigned kOnes = kTracked & 0x11111111u;
+    // blockIdx.y walks the launch's chain list, blockIdx.x the chain's records (groups x tiles, G chains each)
+    const int chain = a.chain_list ? a.chain_list[blockIdx.y] : (int)blockIdx.y;
+    const int64_t n_rec = (int64_t)chain_tiles(a.chains[chain]) * a.groups;
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= n_records * G) return;
-    const int64_t r = idx / G;
-    const int gg = (int)(idx - r * G);
+    if (idx >= n_rec * G) return;
+    const int64_t r = (int64_t)a.bp_tile_base[chain] * a.groups + idx / G;
+    const int gg = (int)(idx % G);
     const uint2* __restrict__ rec = reinterpret_cast<const uint2*>(a.bp) + r * kRecU2;
     uint2 w[S];
 #pragma unroll
@@ -465,8 +468,9 @@ viterbi_trace_kernel(ViterbiArgs a, int G)
 {
     constexpr unsigned kFull = 0xffffffffu;
     const int wid = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (wid >= a.n_samples * a.n_chains) return;
-    const int smp = wid % a.n_samples, chain = wid / a.n_samples;       // neighbouring warps: same chromosome, same length
+    if (wid >= a.n_samples * a.n_list) return;
+    const int smp = wid % a.n_samples;                      // neighbouring warps: same chromosome, same length
+    const int chain = a.chain_list ? a.chain_list[wid / a.n_samples] : wid / a.n_samples;
     const int grp = smp / G, gg = smp - grp * G;
     const ChainDesc cd = a.chains[chain];
     const int n_tiles = chain_tiles(cd);
@@ -499,8 +503,9 @@ viterbi_expand_kernel(ViterbiArgs a)
     constexpr int G = 32 / S;
     constexpr unsigned kFull = 0xffffffffu;
     const int wid = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (wid >= a.n_samples * a.n_chains) return;
-    const int smp = wid % a.n_samples, chain = wid / a.n_samples;
+    if (wid >= a.n_samples * a.n_list) return;
+    const int smp = wid % a.n_samples;
+    const int chain = a.chain_list ? a.chain_list[wid / a.n_samples] : wid / a.n_samples;
     const int grp = smp / G, gg = smp - grp * G;
     const ChainDesc cd = a.chains[chain];
     const int nobs = cd.nobs;
@@ -641,38 +646,45 @@ static void launch_sweep(const ViterbiArgs& a, cudaStream_t st)
 }
 
 template <int S>
-static void launch_all(const ViterbiArgs& a, int64_t n_records, cudaStream_t st)
+static void launch_all(const ViterbiArgs& a, cudaStream_t st)
 {
     constexpr int G = 32 / S;
     prof_mark("viterbi_sweep", st);
     if (a.warps_per_cta == 4) launch_sweep<S, 4>(a, st);
     else launch_sweep<S, 8>(a, st);
     prof_mark("viterbi_tilemap", st);
-    const int64_t map_threads = n_records * G;
-    if (map_threads > 0) viterbi_tilemap_kernel<S><<<(unsigned)((map_threads + 255) / 256), 256, 0, st>>>(a, n_records);
-    const int chains = a.n_samples * a.n_chains;
+    const int64_t map_threads = (int64_t)a.max_list_tiles * a.groups * G;
+    if (map_threads > 0) viterbi_tilemap_kernel<S><<<dim3((unsigned)((map_threads + 255) / 256), (unsigned)a.n_list), 256, 0, st>>>(a);
+    const int chains = a.n_samples * a.n_list;
     prof_mark("viterbi_trace", st);
     viterbi_trace_kernel<<<(chains + 3) / 4, 128, 0, st>>>(a, G);
     prof_mark("viterbi_expand", st);
     viterbi_expand_kernel<S><<<(chains + 3) / 4, 128, 0, st>>>(a);
 }
 
-int launch_viterbi(const ViterbiArgs& a, int64_t n_records, cudaStream_t st)
+int launch_viterbi(const ViterbiArgs& a, cudaStream_t st)
 {
-    if (a.n_chains == 0 || a.n_samples == 0) return 0;
+    if (a.n_list == 0 || a.n_samples == 0) return 0;
     switch (a.n_states) {
-        case 2: launch_all<2>(a, n_records, st); break;
-        case 3: launch_all<3>(a, n_records, st); break;
-        case 4: launch_all<4>(a, n_records, st); break;
-        case 5: launch_all<5>(a, n_records, st); break;
-        case 6: launch_all<6>(a, n_records, st); break;
-        case 7: launch_all<7>(a, n_records, st); break;
+        case 2: launch_all<2>(a, st); break;
+        case 3: launch_all<3>(a, st); break;
+        case 4: launch_all<4>(a, st); break;
+        case 5: launch_all<5>(a, st); break;
+        case 6: launch_all<6>(a, st); break;
+        case 7: launch_all<7>(a, st); break;
         default: return 0;
     }
+    prof_mark(nullptr, st);
+    return 4;
+}
+
+int launch_viterbi_compact(const ViterbiArgs& a, cudaStream_t st)
+{
+    if (a.n_chains == 0 || a.n_samples == 0) return 0;
     prof_mark("viterbi_compact", st);
     viterbi_compact_kernel<<<(a.n_samples + 3) / 4, 128, 0, st>>>(a);
     prof_mark(nullptr, st);
-    return 5;
+    return 1;
 }
 
 }  // namespace edb
