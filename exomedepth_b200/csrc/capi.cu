@@ -235,8 +235,10 @@ struct edb200_cohort {
         int sched_groups = 0;
         int sched_warps = 4;             // sweep warps per CTA the schedule was built for
         int sched_ctas = 1;              // sweep CTAs that have work
+        int sched_avail = 0;             // SMs the schedule was allowed to use
     };
-    std::vector<Part> plans[Context::kMaxParts + 1];   // plans[n]: the split into n parts (built on first use)
+    std::vector<Part> plans[Context::kMaxParts + 1];   // plans[n]: the split into n parts (built on first use);
+                                                       // plans[0]: {the longest chains, the rest} for the device-resident Viterbi
     // per-batch scratch
     DevBuf consts, bp, ccalls, cncalls, maxima, fw_grid, fw_chain, fw_out, fw_best, lattices;
     int last_host_samples = 0;           // samples whose likelihoods the last host-pointer run left in h_ll
@@ -741,14 +743,21 @@ static int build_plan(edb200_cohort* c, int n_parts)
     std::vector<int> order(c->n_chains);
     for (int i = 0; i < c->n_chains; i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return c->chains_h[x].nobs > c->chains_h[y].nobs; });
-    plan.resize(n_parts);
-    int64_t cum = 0;
-    int part = 0;
-    for (int oc = 0; oc < c->n_chains; oc++) {
-        const int ch = order[oc];
-        while (part + 1 < n_parts && !plan[part].chains.empty() && (double)cum >= kCuts[n_parts][part] * (double)c->n_bins) part++;
-        plan[part].chains.push_back(ch);
-        cum += c->chains_h[ch].n_em;
+    if (n_parts == 0) {
+        // the chains within 25 % of the longest one (their sweep is the critical path) | all others
+        plan.resize(2);
+        const double lim = 0.75 * c->chains_h[order[0]].nobs;
+        for (int oc = 0; oc < c->n_chains; oc++) plan[c->chains_h[order[oc]].nobs > lim ? 0 : 1].chains.push_back(order[oc]);
+    } else {
+        plan.resize(n_parts);
+        int64_t cum = 0;
+        int part = 0;
+        for (int oc = 0; oc < c->n_chains; oc++) {
+            const int ch = order[oc];
+            while (part + 1 < n_parts && !plan[part].chains.empty() && (double)cum >= kCuts[n_parts][part] * (double)c->n_bins) part++;
+            plan[part].chains.push_back(ch);
+            cum += c->chains_h[ch].n_em;
+        }
     }
     while (!plan.empty() && plan.back().chains.empty()) plan.pop_back();
     for (auto& pt : plan) {
@@ -876,15 +885,16 @@ static int viterbi_prepare(edb200_cohort* c, const edb200_batch* b, edb::Viterbi
 // memory, so does an emission CTA): its CTAs are filled instead of spread over all SMs — 1: one warp per SM
 // sub-partition, which keeps the long chains of the first part at full speed; 2: two per sub-partition (shorter chains,
 // half the SMs).
-static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiArgs a, int packed, cudaStream_t st)
+static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiArgs a, int packed, cudaStream_t st, int avail_sms = 0)
 {
-    if (pt.sched_groups != a.groups) {
+    if (avail_sms <= 0 || avail_sms > g.n_sms) avail_sms = g.n_sms;
+    if (pt.sched_groups != a.groups || pt.sched_avail != avail_sms) {
         std::vector<int32_t> nobs(pt.chains.size());
         for (size_t i = 0; i < pt.chains.size(); i++) nobs[i] = c->chains_h[pt.chains[i]].nobs;
         const char* force = getenv("EDB200_SWEEP_WARPS");          // experiments: 4 or 8
         pt.sched_warps = force ? (atoi(force) == 8 ? 8 : 4) : packed == 1 ? 4 : packed == 2 ? 8 : edb::viterbi_pick_warps(nobs.data(), (int)nobs.size(), a.groups, g.n_sms);
         const int64_t n_items = (int64_t)nobs.size() * a.groups;
-        const int sched_ctas = packed ? (int)std::min<int64_t>(g.n_sms, (n_items + pt.sched_warps - 1) / pt.sched_warps) : g.n_sms;
+        const int sched_ctas = packed ? (int)std::min<int64_t>(avail_sms, (n_items + pt.sched_warps - 1) / pt.sched_warps) : avail_sms;
         std::vector<int32_t> begin, items;
         edb::viterbi_schedule(nobs.data(), (int)nobs.size(), a.groups, sched_ctas, pt.sched_warps, begin, items);
         for (size_t i = 0; i < items.size(); i += 2) items[i] = pt.chains[items[i]];      // index in the part -> chain id
@@ -898,6 +908,7 @@ static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiA
         CU(cudaMemcpyAsync(pt.sched_items.p, items.data(), items.size() * 4, cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));          // the vectors go out of scope
         pt.sched_groups = a.groups;
+        pt.sched_avail = avail_sms;
     }
     a.chain_list = (const int32_t*)pt.chain_list.p;
     a.n_list = (int)pt.chains.size();
@@ -965,8 +976,26 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
             all.b1[0] = c->n_bins;
             if (int rc = emission_part(c, b, all, true, emission_mode, 0, st)) return rc;
         }
-        if (what & 2)
-            if (int rc = viterbi_part(c, plan[0], va, 0, st)) return rc;
+        if (what & 2) {
+            static const bool split = !(getenv("EDB200_VSPLIT") && atoi(getenv("EDB200_VSPLIT")) == 0);
+            if (split && c->n_chains >= 4 && va.groups >= 8) {
+                // The longest chromosomes' sweep is the critical path; everything behind a sweep (tilemap, trace, expand)
+                // scales with the chains it covers.  Two concurrent passes — {longest chains} on a few SMs of their own,
+                // {all others} on the rest — leave only the longest chains' own post-processing behind the critical sweep.
+                if (int rc = build_plan(c, 0)) return rc;
+                std::vector<edb200_cohort::Part>& vp = c->plans[0];
+                const int64_t items0 = (int64_t)vp[0].chains.size() * va.groups;
+                const int ctas0 = (int)std::min<int64_t>(g.n_sms / 2, (items0 + 3) / 4);
+                CU(cudaEventRecord(g.ev_fork, st));
+                for (int p = 0; p < 2; p++) {
+                    if (vp[p].chains.empty()) continue;
+                    CU(cudaStreamWaitEvent(g.s_vit[p], g.ev_fork, 0));
+                    if (int rc = viterbi_part(c, vp[p], va, p == 0 ? 1 : 0, g.s_vit[p], p == 0 ? ctas0 : g.n_sms - ctas0)) return rc;
+                    CU(cudaEventRecord(g.ev_vit[p], g.s_vit[p]));
+                    CU(cudaStreamWaitEvent(st, g.ev_vit[p], 0));
+                }
+            } else if (int rc = viterbi_part(c, plan[0], va, 0, st)) return rc;
+        }
     } else {
         // ---- chromosome-group pipeline: the emission of group p+1 runs while group p is being swept.  Forked from
         // and joined back into the caller's stream, so the call keeps its "enqueue on cuda_stream" contract.
