@@ -750,11 +750,21 @@ static int build_plan(edb200_cohort* c, int n_parts)
         for (int oc = 0; oc < c->n_chains; oc++) plan[c->chains_h[order[oc]].nobs > lim ? 0 : 1].chains.push_back(order[oc]);
     } else {
         plan.resize(n_parts);
+        double cuts[Context::kMaxParts];
+        for (int p = 0; p < n_parts; p++) cuts[p] = kCuts[n_parts][p];
+        if (const char* e = getenv("EDB200_CUTS")) {                 // experiments: "0.1,0.3,1.0"
+            int p = 0;
+            for (const char* q = e; *q && p < n_parts; p++) {
+                cuts[p] = atof(q);
+                while (*q && *q != ',') q++;
+                if (*q) q++;
+            }
+        }
         int64_t cum = 0;
         int part = 0;
         for (int oc = 0; oc < c->n_chains; oc++) {
             const int ch = order[oc];
-            while (part + 1 < n_parts && !plan[part].chains.empty() && (double)cum >= kCuts[n_parts][part] * (double)c->n_bins) part++;
+            while (part + 1 < n_parts && !plan[part].chains.empty() && (double)cum >= cuts[part] * (double)c->n_bins) part++;
             plan[part].chains.push_back(ch);
             cum += c->chains_h[ch].n_em;
         }
@@ -977,7 +987,7 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
             if (int rc = emission_part(c, b, all, true, emission_mode, 0, st)) return rc;
         }
         if (what & 2) {
-            static const bool split = !(getenv("EDB200_VSPLIT") && atoi(getenv("EDB200_VSPLIT")) == 0);
+            const bool split = !(getenv("EDB200_VSPLIT") && atoi(getenv("EDB200_VSPLIT")) == 0);     // 0: one pass (tests, experiments)
             if (split && c->n_chains >= 4 && va.groups >= 8) {
                 // The longest chromosomes' sweep is the critical path; everything behind a sweep (tilemap, trace, expand)
                 // scales with the chains it covers.  Two concurrent passes — {longest chains} on a few SMs of their own,
@@ -1162,8 +1172,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
                 }
             }
             CU(cudaStreamWaitEvent(g.s_vit[p], g.ev_em[p], 0));
-            static const int pack_rest = getenv("EDB200_PACK") ? atoi(getenv("EDB200_PACK")) : 2;     // experiments
-            if ((rc = viterbi_part(c, plan[p], va, p == 0 ? 1 : pack_rest, g.s_vit[p]))) return rc;
+            if ((rc = viterbi_part(c, plan[p], va, p == 0 ? 1 : 2, g.s_vit[p]))) return rc;
             if (b->path)
                 for (int q = 0; q < rg.n; q++) {
                     const int64_t r0 = rg.b0[q], w = rg.b1[q] - r0;

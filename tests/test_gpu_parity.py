@@ -301,6 +301,80 @@ def test_hmm_special_values(edb, port):
         assert np.array_equal(got[1], want[1]), trial
 
 
+def test_chromosome_group_pipeline_matches_single_pass(edb, monkeypatch):
+    """The host-pointer call uploads, computes and sweeps the chromosomes in groups (longest first) on several streams;
+    the device-resident call sweeps the longest chromosomes apart from the others.  Every grouping must give the
+    single-pass results bit for bit: likelihoods, paths, call tables, per-call sums, correlations."""
+    import torch
+    from exomedepth_b200 import _lib, synth
+    ns = 50
+    d = synth.cohort(ns, n_bins=20000)
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=5)
+    args = (d["observed"], d["reference"], d["phi"], d["expected"])
+    monkeypatch.setenv("EDB200_PARTS", "1")
+    one = co.run_host(*args, call_cap=256, mode=_lib.EMISSION_TABLE, want_stats=True)
+    assert one["ncalls"].sum() > 100
+    for parts in ("2", "3", "6"):
+        monkeypatch.setenv("EDB200_PARTS", parts)
+        got = co.run_host(*args, call_cap=256, mode=_lib.EMISSION_TABLE, want_stats=True)
+        for k in ("ll", "path", "ncalls", "cor"):
+            assert np.array_equal(got[k], one[k]), (parts, k)
+        for s in range(ns):
+            n = one["ncalls"][s]
+            assert np.array_equal(got["calls"][s, :n], one["calls"][s, :n]) and np.array_equal(got["call_stats"][s, :n], one["call_stats"][s, :n])
+    monkeypatch.delenv("EDB200_PARTS")
+    # per-sample reference counts (ref_stride != 0) go through the same grouped uploads
+    ref2 = np.tile(d["reference"], (ns, 1))
+    got = co.run_host(d["observed"], ref2, d["phi"], d["expected"], call_cap=256, mode=_lib.EMISSION_TABLE, want_stats=True)
+    assert np.array_equal(got["ll"], one["ll"]) and np.array_equal(got["path"], one["path"])
+    # device-resident call: split sweep vs one pass
+    dev = torch.device("cuda:0")
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in zip(("obs", "ref", "phi", "exp"), args)}
+    nbp = (co.n_bins + 15) // 16 * 16
+    outs = []
+    for split in ("0", "1"):
+        monkeypatch.setenv("EDB200_VSPLIT", split)
+        ll = torch.empty((ns, 5, nbp), dtype=torch.float64, device=dev)
+        path = torch.full((ns, nbp), 99, dtype=torch.int8, device=dev)
+        calls = torch.zeros((ns, 256, 4), dtype=torch.int32, device=dev)
+        ncalls = torch.zeros(ns, dtype=torch.int32, device=dev)
+        co.run_device(t["obs"], t["ref"], t["phi"], t["exp"], ll, path, calls, ncalls, what=3, mode=_lib.EMISSION_TABLE)
+        torch.cuda.synchronize()
+        outs.append((ll.cpu().numpy()[:, :, :co.n_bins], path.cpu().numpy()[:, :co.n_bins], calls.cpu().numpy(), ncalls.cpu().numpy()))
+    for x, y in zip(outs[0], outs[1]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(outs[1][0], one["ll"]) and np.array_equal(outs[1][1], one["path"]) and np.array_equal(outs[1][3], one["ncalls"])
+
+
+def test_small_panel_shape(edb, port):
+    """BASELINE.json configs[3]: 512 samples x 5,000 bins x 7 states (launch-bound regime, in-register emission kernel).
+    The first samples against the oracle, the whole cohort for determinism and sample independence."""
+    from exomedepth_b200 import synth
+    ns = 512
+    d = synth.cohort(16, n_bins=5000)
+    reps = ns // 16
+    obs = np.tile(d["observed"], (reps, 1))
+    phi, ex = np.tile(d["phi"], reps), np.tile(d["expected"], reps)
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=7)
+    a = co.run_host(obs, d["reference"], phi, ex, call_cap=128)
+    for k in ("ll", "path", "ncalls"):
+        assert np.array_equal(a[k][:16], a[k][16:32]) and np.array_equal(a[k][:16], a[k][-16:])       # a sample's result does not depend on its slot
+    odds, T = port.state_odds(7), port.callcnvs_transitions(7, 1e-4)
+    for s in range(3):
+        want = port.emission(phi[s], ex[s], obs[s] + d["reference"], obs[s], odds)
+        assert_ll_close(a["ll"][s].T, want)
+        k = 0
+        for c in range(len(d["offsets"]) - 1):
+            b0, b1 = d["offsets"][c], d["offsets"][c + 1]
+            loc, pos = framing.frame_chromosome(a["ll"][s][:, b0:b1].T, d["start"][b0:b1].astype(float), d["end"][b0:b1].astype(float), 50000.0)
+            path, calls = port.c_hmm(T, loc, pos, 50000.0)
+            assert np.array_equal(a["path"][s, b0:b1], path[1:-1])
+            for (sp, ep, typ, nex) in calls:
+                assert a["calls"][s, k].tolist() == [sp - 1 + b0, ep - 1 + b0, typ, nex]
+                k += 1
+        assert a["ncalls"][s] == k
+
+
 def test_call_capacity_overflow_is_reported(edb):
     from exomedepth_b200 import _lib, synth
     d = synth.cohort(3, n_bins=9000)
