@@ -21,6 +21,7 @@ EXPORTS = (
     "edb200_cohort_run_device",
     "edb200_cohort_run_host", "edb200_status", "edb200_profile", "edb200_profile_read",
     "edb200_cohort_forward_device", "edb200_cohort_forward_last",
+    "edb200_refset_correlations", "edb200_refset_kpad", "edb200_refset_standardize_device", "edb200_refset_gram_device",
 )
 
 
@@ -90,6 +91,14 @@ def load():
     L.edb200_cohort_forward_device.argtypes = [vp, C.POINTER(Batch), vp, i32, vp, vp, vp]
     L.edb200_cohort_forward_last.restype = C.c_int
     L.edb200_cohort_forward_last.argtypes = [vp, vp, i32, vp, vp]
+    L.edb200_refset_correlations.restype = C.c_int
+    L.edb200_refset_correlations.argtypes = [vp, i64, i32, vp, vp, i64, i32, i32, vp]
+    L.edb200_refset_kpad.restype = i64
+    L.edb200_refset_kpad.argtypes = [i64]
+    L.edb200_refset_standardize_device.restype = C.c_int
+    L.edb200_refset_standardize_device.argtypes = [vp, i64, i32, vp, vp, i64, vp, vp]
+    L.edb200_refset_gram_device.restype = C.c_int
+    L.edb200_refset_gram_device.argtypes = [vp, i32, vp, i32, i64, vp, vp]
     L.edb200_status.restype = C.c_int
     L.edb200_status.argtypes = [C.c_int]
     L.edb200_profile.restype = C.c_int
@@ -132,14 +141,14 @@ def profile(enable):
 
 
 def profile_read():
-    """{kernel: (launches, total_ms)} since profiling was enabled or last read."""
+    """{kernel: (launches, total_ms, longest_ms)} since profiling was enabled or last read."""
     buf = C.create_string_buffer(4096)
     check(load().edb200_profile_read(buf, 4096), "edb200_profile_read")
     out = {}
     for item in buf.value.decode().split(";"):
         if item:
-            name, n, ms = item.split(":")
-            out[name] = (int(n), float(ms))
+            name, n, ms, mx = item.split(":")
+            out[name] = (int(n), float(ms), float(mx))
     return out
 
 

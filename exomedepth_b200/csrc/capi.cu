@@ -83,7 +83,7 @@ struct EventTimer : edb::KernelTimer {
     {
         cudaDeviceSynchronize();
         std::vector<std::string> names;
-        std::vector<double> total;
+        std::vector<double> total, longest;
         std::vector<int> count;
         const bool timeline = getenv("EDB200_TIMELINE") != nullptr;      // development aid: start / duration of every launch
         for (auto& iv : done) {
@@ -96,15 +96,16 @@ struct EventTimer : edb::KernelTimer {
             }
             size_t k = 0;
             while (k < names.size() && names[k] != iv.name) k++;
-            if (k == names.size()) { names.push_back(iv.name); total.push_back(0); count.push_back(0); }
+            if (k == names.size()) { names.push_back(iv.name); total.push_back(0); longest.push_back(0); count.push_back(0); }
             total[k] += ms;
+            if (ms > longest[k]) longest[k] = ms;
             count[k]++;
         }
         done.clear();               // events are left to the driver: a profile run is short
         std::string out;
         char line[160];
         for (size_t k = 0; k < names.size(); k++) {
-            snprintf(line, sizeof line, "%s%s:%d:%.6f", k ? ";" : "", names[k].c_str(), count[k], total[k]);
+            snprintf(line, sizeof line, "%s%s:%d:%.6f:%.6f", k ? ";" : "", names[k].c_str(), count[k], total[k], longest[k]);
             out += line;
         }
         return out;
@@ -161,6 +162,8 @@ int check_kernel(const char* what)
     if (e != cudaSuccess) return fail(EDB200_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
     return 0;
 }
+
+void release_refset_scratch();
 
 // scratch used by the single-call (reference-shaped) entry points
 struct CallScratch {
@@ -308,6 +311,7 @@ void edb200_shutdown(void)
     DevBuf* all[] = {&cs.phi, &cs.expected, &cs.total, &cs.observed, &cs.odds, &cs.ll, &cs.consts, &cs.lt,
                      &cs.chains, &cs.bp, &cs.path, &cs.ccalls, &cs.cncalls, &cs.calls, &cs.ncalls, &cs.sched_begin, &cs.sched_items};
     for (DevBuf* b : all) release(*b);
+    release_refset_scratch();
     if (g.d_flags) cudaFree(g.d_flags);
     g.d_flags = nullptr;
     if (g.stream) cudaStreamDestroy(g.stream);
@@ -1232,6 +1236,85 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     if (b->ncalls && b->call_cap > 0)
         for (int s = 0; s < ns; s++) if (b->ncalls[s] > b->call_cap) warn |= EDB200_WARN_CALLCAP;
     return warn;
+}
+
+// ------------------------------------------------------------------------------------------------ reference-set sweep
+namespace {
+struct RefsetScratch {
+    DevBuf counts, bl, sel, z, partial, c;
+} rs;
+}  // namespace
+
+}  // extern "C"
+namespace {
+void release_refset_scratch()
+{
+    DevBuf* all[] = {&rs.counts, &rs.bl, &rs.sel, &rs.z, &rs.partial, &rs.c};
+    for (DevBuf* b : all) release(*b);
+}
+}  // namespace
+extern "C" {
+
+int64_t edb200_refset_kpad(int64_t n_selected) { return (n_selected + 15) & ~(int64_t)15; }
+
+int edb200_refset_standardize_device(const int32_t* counts, int64_t stride, int32_t n_samples, const double* bin_length,
+                                     const int32_t* selected, int64_t n_selected, double* z, void* cuda_stream)
+{
+    if (int rc = need_ctx()) return rc;
+    if (!counts || !selected || !z || n_samples < 0 || n_selected < 2) return fail(EDB200_ERR_ARG, "bad argument (at least 2 selected bins)");
+    edb::launch_refset_standardize(counts, stride, n_samples, bin_length, selected, n_selected, edb200_refset_kpad(n_selected), z,
+                                   (cudaStream_t)cuda_stream);
+    g_launches++;
+    return check_kernel("refset_standardize");
+}
+
+int edb200_refset_gram_device(const double* za, int32_t m, const double* zb, int32_t n, int64_t n_selected, double* cor_out,
+                              void* cuda_stream)
+{
+    if (int rc = need_ctx()) return rc;
+    if (!za || !zb || !cor_out || m < 0 || n < 0) return fail(EDB200_ERR_ARG, "bad argument");
+    if (m == 0 || n == 0) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);           // the K-slice scratch is shared
+    const int64_t k_pad = edb200_refset_kpad(n_selected);
+    const int slices = edb::refset_gram_slices(m, n, k_pad, g.n_sms);
+    if (int rc = ensure(rs.partial, (size_t)slices * m * n * 8)) return rc;
+    edb::launch_refset_gram(za, m, zb, n, k_pad, slices, (double*)rs.partial.p, cor_out, (cudaStream_t)cuda_stream);
+    g_launches += 2;
+    return check_kernel("refset_gram");
+}
+
+int edb200_refset_correlations(const int32_t* counts, int64_t stride, int32_t n_samples, const double* bin_length,
+                               const int32_t* selected, int64_t n_selected, int32_t row0, int32_t n_rows, double* cor_out)
+{
+    if (int rc = need_ctx()) return rc;
+    if (!counts || !selected || !cor_out || n_samples < 1 || n_selected < 2 || row0 < 0 || n_rows < 0 || row0 + n_rows > n_samples)
+        return fail(EDB200_ERR_ARG, "bad argument");
+    int64_t n_bins = 0;
+    for (int64_t i = 0; i < n_selected; i++) {
+        if (selected[i] < 0 || selected[i] >= stride) return fail(EDB200_ERR_ARG, "selected[%lld] = %d is outside the rows", (long long)i, selected[i]);
+        if (selected[i] + 1 > n_bins) n_bins = selected[i] + 1;
+    }
+    cudaStream_t st = g.stream;
+    const int64_t k_pad = edb200_refset_kpad(n_selected);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        int rc = 0;
+        if ((rc = ensure(rs.counts, (size_t)n_samples * n_bins * 4)) || (rc = ensure(rs.sel, n_selected * 4)) ||
+            (rc = ensure(rs.bl, n_bins * 8)) || (rc = ensure(rs.z, (size_t)n_samples * k_pad * 8)) || (rc = ensure(rs.c, (size_t)n_rows * n_samples * 8 + 8)))
+            return rc;
+        CU(cudaMemcpy2DAsync(rs.counts.p, n_bins * 4, counts, stride * 4, n_bins * 4, n_samples, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(rs.sel.p, selected, n_selected * 4, cudaMemcpyHostToDevice, st));
+        if (bin_length) CU(cudaMemcpyAsync(rs.bl.p, bin_length, n_bins * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (int rc = edb200_refset_standardize_device((const int32_t*)rs.counts.p, n_bins, n_samples, bin_length ? (const double*)rs.bl.p : nullptr,
+                                                  (const int32_t*)rs.sel.p, n_selected, (double*)rs.z.p, st))
+        return rc;
+    if (int rc = edb200_refset_gram_device((const double*)rs.z.p + (size_t)row0 * k_pad, n_rows, (const double*)rs.z.p, n_samples, n_selected,
+                                           (double*)rs.c.p, st))
+        return rc;
+    CU(cudaMemcpyAsync(cor_out, rs.c.p, (size_t)n_rows * n_samples * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
 }
 
 }  // extern "C"

@@ -148,6 +148,15 @@ struct CallSummaryArgs {
 };
 int launch_call_summary(const CallSummaryArgs& a, cudaStream_t st);   // returns the number of launches
 
+// ---- select.reference.set correlation sweep (refset.cu) -----------------------------------------------
+// z: [n_samples][k_pad] standardised rows over the selected bins (k_pad = n_sel rounded up to 16, zero padded)
+void launch_refset_standardize(const int32_t* counts, int64_t stride, int n_samples, const double* bin_length,
+                               const int32_t* selected, int64_t n_sel, int64_t k_pad, double* z, cudaStream_t st);
+int refset_gram_slices(int m, int n, int64_t k_pad, int n_sms);       // K-slices the Gram kernel is split into
+// c[m][n] = za . zb^T clamped to [-1, 1]; partial: scratch of n_slices * m * n doubles
+void launch_refset_gram(const double* za, int m, const double* zb, int n, int64_t k_pad, int n_slices, double* partial,
+                        double* c, cudaStream_t st);
+
 // ---- forward pass / transition-probability grid (extension, forward.cu) -------------------------------
 struct ForwardArgs {
     const ChainDesc* chains;      // [n_chains]

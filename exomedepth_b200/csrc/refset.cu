@@ -1,0 +1,183 @@
+// refset.cu — the correlation sweep of select.reference.set (sm_100a, FP64).
+//
+// Replaces  my.correlations <- apply(reference.counts, 2, function(x) cor(x/(bin.length*sum(x)/10^6),
+//                                                     test.counts/(bin.length*sum(test.counts)/10^6)))
+// (R/optimize_reference_set.R:100) for every sample of a cohort at once: with leave-one-out cohorts the selected bins
+// do not depend on which sample is the test, so the sweep is one Pearson matrix of the normalised count rows
+// (SURVEY.md §8f-1).  Two kernels:
+//   refset_standardize_kernel  one CTA per sample: gather the selected bins, y = x / (bin.length * sum(x) / 1e6)
+//                              evaluated as R does, two-pass mean / centred norm with compensated sums,
+//                              z = (y - mean) / norm  ->  Z[sample][bin], K padded with zeros.  HBM-bound (reads
+//                              the int32 counts once per pass, writes 8 bytes per selected bin).
+//   refset_gram_kernel         C = Za . Zb^T (rows of Za against rows of Zb over the selected bins), FP64 FMA on a
+//                              64 x 64 x 16 shared-memory tiling, 4 x 4 outputs per thread, split over K so that a
+//                              256-sample cohort still fills the 148 SMs; the K-slices are summed in slice order by
+//                              refset_reduce_kernel (deterministic, no atomics).  This is the one dense contraction of
+//                              the package; it stays on the FP64 pipe because the result is compared at 1e-10.
+#include "kernels.cuh"
+
+namespace edb {
+
+namespace {
+
+struct Acc {                       // compensated running sum (two-sum), value = s + c
+    double s, c;
+};
+__device__ __forceinline__ void acc_add(Acc& a, double x)
+{
+    const double t = __dadd_rn(a.s, x);
+    const double bp = __dadd_rn(t, -a.s);
+    a.c = __dadd_rn(a.c, __dadd_rn(__dadd_rn(a.s, -__dadd_rn(t, -bp)), __dadd_rn(x, -bp)));
+    a.s = t;
+}
+// CTA-wide total of a compensated sum, combined in lane / warp order (deterministic); every thread gets the result
+__device__ double cta_total(Acc a, double* red /* [2 * 32] */)
+{
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const double s2 = __shfl_xor_sync(0xffffffffu, a.s, d), c2 = __shfl_xor_sync(0xffffffffu, a.c, d);
+        Acc lo = a, hi{s2, c2};
+        if (threadIdx.x & d) { lo = hi; hi = a; }
+        acc_add(lo, hi.s);
+        lo.c = __dadd_rn(lo.c, hi.c);
+        a = lo;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) { red[2 * warp] = a.s; red[2 * warp + 1] = a.c; }
+    __syncthreads();
+    Acc t{0, 0};
+    for (int w = 0; w < n_warps; w++) {
+        acc_add(t, red[2 * w]);
+        t.c = __dadd_rn(t.c, red[2 * w + 1]);
+    }
+    return __dadd_rn(t.s, t.c);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(512)
+refset_standardize_kernel(const int32_t* __restrict__ counts, int64_t stride, const double* __restrict__ bin_length,
+                          const int32_t* __restrict__ selected, int64_t n_sel, int64_t k_pad, double* __restrict__ z)
+{
+    __shared__ double red[64];
+    const int32_t* __restrict__ row = counts + blockIdx.x * stride;
+    double* __restrict__ out = z + blockIdx.x * k_pad;
+    Acc a{0, 0};
+    for (int64_t i = threadIdx.x; i < n_sel; i += blockDim.x) acc_add(a, (double)row[selected[i]]);
+    const double total = cta_total(a, red);                 // sum(x) over the selected bins: an integer, exact
+    auto y_at = [&](int64_t i) -> double {
+        const int32_t b = selected[i];
+        const double bl = bin_length ? bin_length[b] : 1.0;
+        return __ddiv_rn((double)row[b], __ddiv_rn(__dmul_rn(bl, total), 1e6));     // x / ((bin.length * sum(x)) / 10^6)
+    };
+    a = Acc{0, 0};
+    for (int64_t i = threadIdx.x; i < n_sel; i += blockDim.x) acc_add(a, y_at(i));
+    const double mean = __ddiv_rn(cta_total(a, red), (double)n_sel);
+    a = Acc{0, 0};
+    for (int64_t i = threadIdx.x; i < n_sel; i += blockDim.x) {
+        const double d = __dadd_rn(y_at(i), -mean);
+        acc_add(a, __dmul_rn(d, d));
+    }
+    const double norm = sqrt(cta_total(a, red));            // 0 for a constant row: z becomes NaN, cor() gives NA there too
+    for (int64_t i = threadIdx.x; i < k_pad; i += blockDim.x)
+        out[i] = i < n_sel ? __ddiv_rn(__dadd_rn(y_at(i), -mean), norm) : 0.0;
+}
+
+// C_slice[slice][i][j] = sum over the slice's k of Za[i][k] * Zb[j][k]
+constexpr int kGT = 64, kGK = 16;
+__global__ void __launch_bounds__(256)
+refset_gram_kernel(const double* __restrict__ za, int m, const double* __restrict__ zb, int n, int64_t k_pad, int64_t k_slice,
+                   double* __restrict__ partial)
+{
+    __shared__ double sa[kGK][kGT + 2], sb[kGK][kGT + 2];   // k-major, padded: the inner product reads rows of 64
+    const int ti = blockIdx.y * kGT, tj = blockIdx.x * kGT;
+    const int64_t k0 = (int64_t)blockIdx.z * k_slice, k1 = k0 + k_slice < k_pad ? k0 + k_slice : k_pad;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;            // 16 x 16 threads, 4 x 4 outputs each
+    // loads: thread t brings 4 consecutive k of one row of each operand tile (64 rows x 16 k = 256 threads x 4)
+    const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;
+    double acc[4][4] = {};
+    for (int64_t k = k0; k < k1; k += kGK) {
+        double2 a0 = make_double2(0, 0), a1 = a0, b0 = a0, b1 = a0;
+        if (ti + lr < m) {
+            const double2* p = reinterpret_cast<const double2*>(za + (int64_t)(ti + lr) * k_pad + k + lk);
+            a0 = p[0];
+            a1 = p[1];
+        }
+        if (tj + lr < n) {
+            const double2* p = reinterpret_cast<const double2*>(zb + (int64_t)(tj + lr) * k_pad + k + lk);
+            b0 = p[0];
+            b1 = p[1];
+        }
+        __syncthreads();                                    // the previous chunk's products are done
+        sa[lk + 0][lr] = a0.x; sa[lk + 1][lr] = a0.y; sa[lk + 2][lr] = a1.x; sa[lk + 3][lr] = a1.y;
+        sb[lk + 0][lr] = b0.x; sb[lk + 1][lr] = b0.y; sb[lk + 2][lr] = b1.x; sb[lk + 3][lr] = b1.y;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kGK; kk++) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                av[r] = sa[kk][ty * 4 + r];
+                bv[r] = sb[kk][tx * 4 + r];
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+        }
+    }
+    double* __restrict__ out = partial + (int64_t)blockIdx.z * m * n;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int i = ti + ty * 4 + r, j = tj + tx * 4 + c;
+            if (i < m && j < n) out[(int64_t)i * n + j] = acc[r][c];
+        }
+}
+
+__global__ void __launch_bounds__(256)
+refset_reduce_kernel(const double* __restrict__ partial, int n_slices, int64_t mn, double* __restrict__ c)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= mn) return;
+    double s = 0.0;
+    for (int q = 0; q < n_slices; q++) s = __dadd_rn(s, partial[(int64_t)q * mn + i]);
+    c[i] = s > 1.0 ? 1.0 : s < -1.0 ? -1.0 : s;            // R's cor() clamps to [-1, 1]; NaN passes through
+}
+
+void launch_refset_standardize(const int32_t* counts, int64_t stride, int n_samples, const double* bin_length,
+                               const int32_t* selected, int64_t n_sel, int64_t k_pad, double* z, cudaStream_t st)
+{
+    if (n_samples == 0) return;
+    prof_mark("refset_standardize", st);
+    refset_standardize_kernel<<<n_samples, 512, 0, st>>>(counts, stride, bin_length, selected, n_sel, k_pad, z);
+    prof_mark(nullptr, st);
+}
+
+int refset_gram_slices(int m, int n, int64_t k_pad, int n_sms)
+{
+    const int64_t tiles = (int64_t)((m + kGT - 1) / kGT) * ((n + kGT - 1) / kGT);
+    int64_t want = (4 * (int64_t)n_sms + tiles - 1) / tiles;           // ~4 CTAs per SM over the grid
+    const int64_t max_slices = (k_pad + 4 * kGK - 1) / (4 * kGK);      // at least 64 k per slice
+    if (want > max_slices) want = max_slices;
+    if (want > 256) want = 256;
+    return want < 1 ? 1 : (int)want;
+}
+
+void launch_refset_gram(const double* za, int m, const double* zb, int n, int64_t k_pad, int n_slices, double* partial,
+                        double* c, cudaStream_t st)
+{
+    if (m == 0 || n == 0) return;
+    int64_t k_slice = (k_pad + n_slices - 1) / n_slices;
+    k_slice = (k_slice + kGK - 1) / kGK * kGK;
+    prof_mark("refset_gram", st);
+    refset_gram_kernel<<<dim3((n + kGT - 1) / kGT, (m + kGT - 1) / kGT, n_slices), 256, 0, st>>>(za, m, zb, n, k_pad, k_slice, partial);
+    prof_mark("refset_reduce", st);
+    const int64_t mn = (int64_t)m * n;
+    refset_reduce_kernel<<<(unsigned)((mn + 255) / 256), 256, 0, st>>>(partial, n_slices, mn, c);
+    prof_mark(nullptr, st);
+}
+
+}  // namespace edb

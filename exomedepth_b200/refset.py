@@ -1,0 +1,102 @@
+"""Host-side mirror of the deterministic front half of `select.reference.set` (R/optimize_reference_set.R:51-102):
+bin selection on the host (a few quantiles), the correlation sweep on the GPU through the C ABI.
+
+The greedy aggregate loop that follows in R (:113-141) re-fits the beta-binomial model per prefix with
+`aod::betabin` (third-party, unpinned) and is not part of this package."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def select_bins(total_counts, bin_length=None, n_bins_reduced=0):
+    """R/optimize_reference_set.R:81-88: the bins used to rank the candidate references (0-based indices).
+    total_counts = test + all candidates; quantile() is R's default (type 7)."""
+    total = np.asarray(total_counts, np.float64)
+    bl = np.ones(total.size) if bin_length is None else np.asarray(bin_length, np.float64)
+    if np.any(bl == 0):
+        n0 = int(np.sum(bl == 0))
+        raise ValueError(f"bin.length contains {n0} zero{'s' if n0 > 1 else ''}. This causes NAs in correlation computing. "
+                         "All bin lengths must be positive")                                    # :69-72
+    big = total > 30
+    hi = np.quantile(total[big], 0.9) if np.any(big) else np.nan
+    keep = big & (bl >= np.quantile(bl, 0.05)) & (bl <= np.quantile(bl, 0.95)) & (total < hi)
+    sel = np.flatnonzero(keep)
+    if 0 < n_bins_reduced < sel.size:                       # :88  selected[seq(1, length, length / n.bins.reduced)]
+        step = sel.size / n_bins_reduced
+        n = int(np.floor((sel.size - 1) / step + 1e-10)) + 1
+        sel = sel[np.floor(1 + step * np.arange(n)).astype(np.int64) - 1]
+    return sel.astype(np.int32)
+
+
+def correlations(counts, selected, bin_length=None, row0=0, n_rows=None):
+    """Pearson correlations of the normalised count rows over the selected bins (R/optimize_reference_set.R:100),
+    rows row0 .. row0 + n_rows - 1 against every sample.  counts: int32[n_samples, n_bins]."""
+    counts = np.ascontiguousarray(np.asarray(counts, np.int32))
+    ns = counts.shape[0]
+    n_rows = ns - row0 if n_rows is None else n_rows
+    sel = np.ascontiguousarray(np.asarray(selected, np.int32))
+    bl = None if bin_length is None else np.ascontiguousarray(np.asarray(bin_length, np.float64))
+    out = np.empty((n_rows, ns))
+    rc = _lib.load().edb200_refset_correlations(counts.ctypes.data, counts.shape[1], ns, None if bl is None else bl.ctypes.data,
+                                                sel.ctypes.data, sel.size, row0, n_rows, out.ctypes.data)
+    _lib.check(rc, "edb200_refset_correlations")
+    return out
+
+
+def cohort_reference_ranking(counts, bin_length=None, n_bins_reduced=0):
+    """Leave-one-out sweep: every sample in turn is the test, all others the candidates.  Returns dict(selected,
+    correlations [n, n], order [n, n-1] = for each test sample the other samples by decreasing correlation (:101))."""
+    counts = np.asarray(counts)
+    sel = select_bins(counts.sum(0, dtype=np.int64), bin_length, n_bins_reduced)
+    cor = correlations(counts, sel, bin_length)
+    n = cor.shape[0]
+    order = np.empty((n, n - 1), np.int32)
+    for t in range(n):
+        others = np.array([i for i in range(n) if i != t])
+        order[t] = others[np.argsort(-cor[t, others], kind="stable")]
+    return dict(selected=sel, correlations=cor, order=order)
+
+
+def select_reference_set(test_counts, reference_counts, bin_length=None, n_bins_reduced=0, names=None):
+    """`select.reference.set(test.counts, reference.counts, bin.length, n.bins.reduced)` up to and including the
+    ordering of the candidates (R/optimize_reference_set.R:51-102).  reference_counts: bins x candidates, as in R.
+    Returns dict(ref_samples, correlations, selected) in the order of `summary.stats`."""
+    test = np.asarray(test_counts)
+    refs = np.asarray(reference_counts)
+    if refs.ndim != 2:
+        raise ValueError("The reference sequence count data must be provided as a matrix")     # :63
+    if refs.shape[0] != test.size:
+        raise ValueError("The number of rows of the reference matrix must match the length of the test count data")
+    names = list(names) if names is not None else [f"X{i + 1}" for i in range(refs.shape[1])]  # :77
+    if int(np.sum(test > 2)) < 5:                                                               # :55-60
+        return dict(ref_samples=names[:1], correlations=None, selected=None)
+    sel = select_bins(refs.sum(1, dtype=np.int64) + test, bin_length, n_bins_reduced)
+    stacked = np.vstack([test[None, :], refs.T]).astype(np.int32)
+    cor = correlations(stacked, sel, bin_length, row0=0, n_rows=1)[0, 1:]
+    order = np.argsort(-cor, kind="stable")
+    return dict(ref_samples=[names[i] for i in order], correlations=cor[order], selected=sel)
+
+
+# ---- device tensors (torch): the two stages, for the sharded sweep --------------------------------------------
+def kpad(n_selected):
+    return int(_lib.load().edb200_refset_kpad(int(n_selected)))
+
+
+def standardize_device(counts, selected, bin_length, z, stream=None):
+    """counts: CUDA int32 [n, stride]; selected: CUDA int32 [k]; bin_length: CUDA float64 [n_bins] or None;
+    z: CUDA float64 [n, kpad(k)] (written)."""
+    import torch
+    st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+    return _lib.check(_lib.load().edb200_refset_standardize_device(
+        counts.data_ptr(), counts.stride(0), counts.shape[0], bin_length.data_ptr() if bin_length is not None else None,
+        selected.data_ptr(), selected.numel(), z.data_ptr(), st), "edb200_refset_standardize_device")
+
+
+def gram_device(za, zb, n_selected, out, stream=None):
+    """out[m, n] = correlations of the rows of za against the rows of zb."""
+    import torch
+    st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+    return _lib.check(_lib.load().edb200_refset_gram_device(za.data_ptr(), za.shape[0], zb.data_ptr(), zb.shape[0], int(n_selected),
+                                                            out.data_ptr(), st), "edb200_refset_gram_device")

@@ -5,6 +5,10 @@ The hot path has no data-path collective: every sample is indep
 geometry, the reference aggregate and — on the host, with the host libm, so that every rank holds the same bits —
 the log-transition table, and broadcasts them (NCCL on GPUs, gloo in the CPU tests).  Results stay sharded; only
 the small call tables are gathered.  torch.distributed is plumbing here, nothing more.
+
+The reference-set correlation sweep (select.reference.set) is the one place with a real
+exchange: the bin filter needs the cohort-wide total per bin (one all-reduce of a per-rank partial sum) and every
+rank needs every sample's standardised row (one all-gather) to form its block of the correlation matrix.
 """
 import numpy as np
 
@@ -102,3 +106,51 @@ def make_cohort(shared, dist=None, device=None, **cohort_kwargs):
             co.table_from(tbl)
         torch.cuda.synchronize()
     return co
+
+
+def refset_sweep(counts_local, n_total, bin_length=None, n_bins_reduced=0, dist=None, device=None, backend=None):
+    """Sharded leave-one-out correlation sweep.  counts_local: int32[n_local, n_bins] — this rank's samples
+    (contiguous blocks as shard_range deals them); n_total: samples over all ranks.
+    Returns (selected bins, float64[n_local, n_total] correlations of this rank's samples against every sample).
+
+    Collectives: all-reduce (sum) of the per-bin totals, all-gather of the standardised rows.  `backend` supplies the
+    two compute stages — default: the CUDA kernels (exomedepth_b200.refset); the CPU tests pass numpy stand-ins."""
+    from . import refset
+    multi = dist is not None and dist.is_initialized() and dist.get_world_size() > 1
+    world = dist.get_world_size() if multi else 1
+    rank = dist.get_rank() if multi else 0
+    counts_local = np.ascontiguousarray(np.asarray(counts_local, np.int32))
+    n_local, n_bins = counts_local.shape
+    import torch
+    dev = device if device is not None else torch.device("cpu")
+    total = torch.from_numpy(counts_local.sum(0, dtype=np.int64)).to(dev)
+    if multi:
+        dist.all_reduce(total)
+    sel = refset.select_bins(total.cpu().numpy(), bin_length, n_bins_reduced)
+    per = -(-n_total // world)                              # every rank contributes a block of `per` rows (zero padded)
+    if backend is None:
+        kp = refset.kpad(sel.size)
+        c_t = torch.from_numpy(counts_local).to(dev)
+        sel_t = torch.from_numpy(sel).to(dev)
+        bl_t = None if bin_length is None else torch.from_numpy(np.ascontiguousarray(np.asarray(bin_length, np.float64))).to(dev)
+        z_local = torch.zeros((per, kp), dtype=torch.float64, device=dev)
+        if n_local:
+            refset.standardize_device(c_t, sel_t, bl_t, z_local[:n_local])
+    else:
+        z = backend.standardize(counts_local, sel, bin_length)
+        z_local = torch.zeros((per, z.shape[1] if n_local else backend.kpad(sel.size)), dtype=torch.float64, device=dev)
+        if n_local:
+            z_local[:n_local] = torch.from_numpy(z).to(dev)
+    if multi:
+        z_all = torch.empty((world * per, z_local.shape[1]), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(z_all, z_local)
+        z_all = z_all[:n_total]                             # only the last ranks' blocks are padded
+    else:
+        z_all = z_local[:n_total]
+    if backend is None:
+        out = torch.empty((n_local, n_total), dtype=torch.float64, device=dev)
+        if n_local:
+            refset.gram_device(z_local[:n_local], z_all.contiguous(), sel.size, out)
+            torch.cuda.synchronize()
+        return sel, out.cpu().numpy()
+    return sel, backend.gram(z_local[:n_local].cpu().numpy(), z_all.cpu().numpy())

@@ -48,7 +48,7 @@ EDB200_API int         edb200_device_info(char *buf, int buflen, int *n_sms, int
 /* count of kernels launched by this library since the last reset (bench.py's gpu_launches) */
 EDB200_API int64_t     edb200_launch_count(int reset);
 /* per-kernel device times: while enabled, every kernel launch of this library is bracketed by CUDA events on its
- * stream; edb200_profile_read synchronises and writes "name:launches:total_ms;..." (bench.py's roofline uses it) */
+ * stream; edb200_profile_read synchronises and writes "name:launches:total_ms:longest_ms;..." (bench.py's roofline uses it) */
 EDB200_API int         edb200_profile(int enable);
 EDB200_API int         edb200_profile_read(char *buf, int buflen);
 /* page-locked host buffers for the host-pointer entry points (optional, speeds up the copies) */
@@ -159,6 +159,28 @@ EDB200_API int edb200_cohort_forward_device(edb200_cohort *c, const edb200_batch
                                             double *loglik, int32_t *best, void *cuda_stream);
 /* host pointers; runs over the likelihoods the most recent edb200_cohort_run_host left resident in HBM */
 EDB200_API int edb200_cohort_forward_last(edb200_cohort *c, const double *tp_grid, int32_t n_grid, double *loglik, int32_t *best);
+
+/* ---- select.reference.set: the correlation sweep ---------------------------------------
+ * Replaces R/optimize_reference_set.R:100 — cor(x/(bin.length*sum(x)/10^6), test/(bin.length*sum(test)/10^6)) of
+ * every candidate against the test sample — for all samples of a cohort at once: with leave-one-out cohorts the bins
+ * selected at :81-88 are the same for every test sample, so the sweep is one Pearson matrix over those bins.
+ * counts: int32[n_samples][stride]; bin_length: double[n_bins] or NULL (all 1, :66); selected: the 0-based indices of
+ * the selected bins (the filter itself is a few quantiles, done by the caller: exomedepth_b200/refset.py).
+ * cor_out: double[n_rows][n_samples], row r = correlations of sample row0 + r against every sample (diagonal 1).
+ * The beta-binomial refits of the greedy loop that follows in R (:113-141, aod::betabin) are out of scope. */
+EDB200_API int edb200_refset_correlations(const int32_t *counts, int64_t stride, int32_t n_samples,
+                                          const double *bin_length, const int32_t *selected, int64_t n_selected,
+                                          int32_t row0, int32_t n_rows, double *cor_out);
+/* The two stages on DEVICE pointers, enqueued on cuda_stream without synchronising (multi-GPU: every rank standardises
+ * its own samples, the rows are all-gathered, every rank then forms its block of the matrix).
+ * z: double[n_samples][k_pad], k_pad = edb200_refset_kpad(n_selected). */
+EDB200_API int64_t edb200_refset_kpad(int64_t n_selected);
+EDB200_API int edb200_refset_standardize_device(const int32_t *counts, int64_t stride, int32_t n_samples,
+                                                const double *bin_length, const int32_t *selected, int64_t n_selected,
+                                                double *z, void *cuda_stream);
+/* cor_out[m][n] = rows of za against rows of zb */
+EDB200_API int edb200_refset_gram_device(const double *za, int32_t m, const double *zb, int32_t n, int64_t n_selected,
+                                         double *cor_out, void *cuda_stream);
 
 /* sticky status word of device-side warnings since the last call with reset != 0 (EDB200_WARN_*) */
 EDB200_API int edb200_status(int reset);
