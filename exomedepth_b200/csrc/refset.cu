@@ -10,7 +10,7 @@
 //                              z = (y - mean) / norm  ->  Z[sample][bin], K padded with zeros.  HBM-bound (reads
 //                              the int32 counts once per pass, writes 8 bytes per selected bin).
 //   refset_gram_kernel         C = Za . Zb^T (rows of Za against rows of Zb over the selected bins), FP64 FMA on a
-//                              64 x 64 x 16 shared-memory tiling, 4 x 4 outputs per thread, split over K so that a
+//                              128 x 128 x 16 shared-memory tiling, 8 x 8 outputs per thread, split over K so that a
 //                              256-sample cohort still fills the 148 SMs; the K-slices are summed in slice order by
 //                              refset_reduce_kernel (deterministic, no atomics).  This is the one dense contraction of
 //                              the package; it stays on the FP64 pipe because the result is compared at 1e-10.
@@ -56,83 +56,95 @@ __device__ double cta_total(Acc a, double* red /* [2 * 32] */)
 
 }  // namespace
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 refset_standardize_kernel(const int32_t* __restrict__ counts, int64_t stride, const double* __restrict__ bin_length,
                           const int32_t* __restrict__ selected, int64_t n_sel, int64_t k_pad, double* __restrict__ z)
 {
     __shared__ double red[64];
     const int32_t* __restrict__ row = counts + blockIdx.x * stride;
-    double* __restrict__ out = z + blockIdx.x * k_pad;
+    double* __restrict__ out = z + blockIdx.x * k_pad;      // also the scratch for y between the passes (L2 resident)
     Acc a{0, 0};
     for (int64_t i = threadIdx.x; i < n_sel; i += blockDim.x) acc_add(a, (double)row[selected[i]]);
     const double total = cta_total(a, red);                 // sum(x) over the selected bins: an integer, exact
-    auto y_at = [&](int64_t i) -> double {
-        const int32_t b = selected[i];
-        const double bl = bin_length ? bin_length[b] : 1.0;
-        return __ddiv_rn((double)row[b], __ddiv_rn(__dmul_rn(bl, total), 1e6));     // x / ((bin.length * sum(x)) / 10^6)
-    };
-    a = Acc{0, 0};
-    for (int64_t i = threadIdx.x; i < n_sel; i += blockDim.x) acc_add(a, y_at(i));
-    const double mean = __ddiv_rn(cta_total(a, red), (double)n_sel);
     a = Acc{0, 0};
     for (int64_t i = threadIdx.x; i < n_sel; i += blockDim.x) {
-        const double d = __dadd_rn(y_at(i), -mean);
+        const int32_t b = selected[i];
+        const double bl = bin_length ? bin_length[b] : 1.0;
+        const double y = __ddiv_rn((double)row[b], __ddiv_rn(__dmul_rn(bl, total), 1e6));   // x / ((bin.length * sum(x)) / 10^6)
+        out[i] = y;
+        acc_add(a, y);
+    }
+    const double mean = __ddiv_rn(cta_total(a, red), (double)n_sel);
+    a = Acc{0, 0};
+    for (int64_t i = threadIdx.x; i < n_sel; i += blockDim.x) {      // each thread re-reads what it wrote itself
+        const double d = __dadd_rn(out[i], -mean);
+        out[i] = d;
         acc_add(a, __dmul_rn(d, d));
     }
     const double norm = sqrt(cta_total(a, red));            // 0 for a constant row: z becomes NaN, cor() gives NA there too
-    for (int64_t i = threadIdx.x; i < k_pad; i += blockDim.x)
-        out[i] = i < n_sel ? __ddiv_rn(__dadd_rn(y_at(i), -mean), norm) : 0.0;
+    for (int64_t i = threadIdx.x; i < k_pad; i += blockDim.x) out[i] = i < n_sel ? __ddiv_rn(out[i], norm) : 0.0;
 }
 
-// C_slice[slice][i][j] = sum over the slice's k of Za[i][k] * Zb[j][k]
-constexpr int kGT = 64, kGK = 16;
+// C_slice[slice][i][j] = sum over the slice's k of Za[i][k] * Zb[j][k].  128 x 128 x 16 tiles, 256 threads, 8 x 8 outputs
+// per thread (two 4-wide groups 64 apart in each direction): 4 FMAs per shared-memory double, the ratio the FP64 pipe
+// needs to stay ahead of the shared-memory bandwidth.
+constexpr int kGT = 128, kGK = 16;
 __global__ void __launch_bounds__(256)
 refset_gram_kernel(const double* __restrict__ za, int m, const double* __restrict__ zb, int n, int64_t k_pad, int64_t k_slice,
                    double* __restrict__ partial)
 {
-    __shared__ double sa[kGK][kGT + 2], sb[kGK][kGT + 2];   // k-major, padded: the inner product reads rows of 64
+    __shared__ __align__(16) double sa[kGK][kGT], sb[kGK][kGT];       // k-major
     const int ti = blockIdx.y * kGT, tj = blockIdx.x * kGT;
     const int64_t k0 = (int64_t)blockIdx.z * k_slice, k1 = k0 + k_slice < k_pad ? k0 + k_slice : k_pad;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;            // 16 x 16 threads, 4 x 4 outputs each
-    // loads: thread t brings 4 consecutive k of one row of each operand tile (64 rows x 16 k = 256 threads x 4)
-    const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;
-    double acc[4][4] = {};
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;            // 16 x 16 threads
+    // loads: thread t brings 8 consecutive k of one row of each operand tile (128 rows x 16 k = 256 threads x 8)
+    const int lr = threadIdx.x >> 1, lk = (threadIdx.x & 1) * 8;
+    double acc[8][8] = {};
     for (int64_t k = k0; k < k1; k += kGK) {
-        double2 a0 = make_double2(0, 0), a1 = a0, b0 = a0, b1 = a0;
+        double2 av[4], bv[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) av[q] = bv[q] = make_double2(0, 0);
         if (ti + lr < m) {
             const double2* p = reinterpret_cast<const double2*>(za + (int64_t)(ti + lr) * k_pad + k + lk);
-            a0 = p[0];
-            a1 = p[1];
+#pragma unroll
+            for (int q = 0; q < 4; q++) av[q] = p[q];
         }
         if (tj + lr < n) {
             const double2* p = reinterpret_cast<const double2*>(zb + (int64_t)(tj + lr) * k_pad + k + lk);
-            b0 = p[0];
-            b1 = p[1];
+#pragma unroll
+            for (int q = 0; q < 4; q++) bv[q] = p[q];
         }
         __syncthreads();                                    // the previous chunk's products are done
-        sa[lk + 0][lr] = a0.x; sa[lk + 1][lr] = a0.y; sa[lk + 2][lr] = a1.x; sa[lk + 3][lr] = a1.y;
-        sb[lk + 0][lr] = b0.x; sb[lk + 1][lr] = b0.y; sb[lk + 2][lr] = b1.x; sb[lk + 3][lr] = b1.y;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            sa[lk + 2 * q][lr] = av[q].x; sa[lk + 2 * q + 1][lr] = av[q].y;
+            sb[lk + 2 * q][lr] = bv[q].x; sb[lk + 2 * q + 1][lr] = bv[q].y;
+        }
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < kGK; kk++) {
-            double av[4], bv[4];
+            double ar[8], br[8];
 #pragma unroll
-            for (int r = 0; r < 4; r++) {
-                av[r] = sa[kk][ty * 4 + r];
-                bv[r] = sb[kk][tx * 4 + r];
+            for (int h = 0; h < 2; h++) {
+                const double2 a01 = *reinterpret_cast<const double2*>(&sa[kk][h * 64 + ty * 4]);
+                const double2 a23 = *reinterpret_cast<const double2*>(&sa[kk][h * 64 + ty * 4 + 2]);
+                const double2 b01 = *reinterpret_cast<const double2*>(&sb[kk][h * 64 + tx * 4]);
+                const double2 b23 = *reinterpret_cast<const double2*>(&sb[kk][h * 64 + tx * 4 + 2]);
+                ar[4 * h] = a01.x; ar[4 * h + 1] = a01.y; ar[4 * h + 2] = a23.x; ar[4 * h + 3] = a23.y;
+                br[4 * h] = b01.x; br[4 * h + 1] = b01.y; br[4 * h + 2] = b23.x; br[4 * h + 3] = b23.y;
             }
 #pragma unroll
-            for (int r = 0; r < 4; r++)
+            for (int r = 0; r < 8; r++)
 #pragma unroll
-                for (int c = 0; c < 4; c++) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+                for (int c = 0; c < 8; c++) acc[r][c] = fma(ar[r], br[c], acc[r][c]);
         }
     }
     double* __restrict__ out = partial + (int64_t)blockIdx.z * m * n;
 #pragma unroll
-    for (int r = 0; r < 4; r++)
+    for (int r = 0; r < 8; r++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const int i = ti + ty * 4 + r, j = tj + tx * 4 + c;
+        for (int c = 0; c < 8; c++) {
+            const int i = ti + (r >> 2) * 64 + ty * 4 + (r & 3), j = tj + (c >> 2) * 64 + tx * 4 + (c & 3);
             if (i < m && j < n) out[(int64_t)i * n + j] = acc[r][c];
         }
 }
@@ -152,7 +164,7 @@ void launch_refset_standardize(const int32_t* counts, int64_t stride, int n_samp
 {
     if (n_samples == 0) return;
     prof_mark("refset_standardize", st);
-    refset_standardize_kernel<<<n_samples, 512, 0, st>>>(counts, stride, bin_length, selected, n_sel, k_pad, z);
+    refset_standardize_kernel<<<n_samples, 1024, 0, st>>>(counts, stride, bin_length, selected, n_sel, k_pad, z);
     prof_mark(nullptr, st);
 }
 
