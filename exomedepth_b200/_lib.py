@@ -22,6 +22,7 @@ EXPORTS = (
     "edb200_cohort_run_host", "edb200_status", "edb200_profile", "edb200_profile_read",
     "edb200_cohort_forward_device", "edb200_cohort_forward_last",
     "edb200_refset_correlations", "edb200_refset_kpad", "edb200_refset_standardize_device", "edb200_refset_gram_device",
+    "edb200_betabin_fit", "edb200_betabin_fit_device",
 )
 
 
@@ -99,6 +100,10 @@ def load():
     L.edb200_refset_standardize_device.argtypes = [vp, i64, i32, vp, vp, i64, vp, vp]
     L.edb200_refset_gram_device.restype = C.c_int
     L.edb200_refset_gram_device.argtypes = [vp, i32, vp, i32, i64, vp, vp]
+    L.edb200_betabin_fit.restype = C.c_int
+    L.edb200_betabin_fit.argtypes = [vp, i64, vp, i64, i32, i64, vp, vp, vp, vp]
+    L.edb200_betabin_fit_device.restype = C.c_int
+    L.edb200_betabin_fit_device.argtypes = [vp, i64, vp, i64, i32, i64, vp, vp, vp, vp, vp]
     L.edb200_status.restype = C.c_int
     L.edb200_status.argtypes = [C.c_int]
     L.edb200_profile.restype = C.c_int

@@ -164,6 +164,7 @@ int check_kernel(const char* what)
 }
 
 void release_refset_scratch();
+void release_fit_scratch();
 
 // scratch used by the single-call (reference-shaped) entry points
 struct CallScratch {
@@ -1251,6 +1252,7 @@ void release_refset_scratch()
 {
     DevBuf* all[] = {&rs.counts, &rs.bl, &rs.sel, &rs.z, &rs.partial, &rs.c};
     for (DevBuf* b : all) release(*b);
+    release_fit_scratch();
 }
 }  // namespace
 extern "C" {
@@ -1315,6 +1317,76 @@ int edb200_refset_correlations(const int32_t* counts, int64_t stride, int32_t n_
     CU(cudaMemcpyAsync(cor_out, rs.c.p, (size_t)n_rows * n_samples * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ beta-binomial fit
+}  // extern "C"
+namespace {
+struct FitScratch {
+    DevBuf obs, ref, mu, phi, ll, info, overflow;
+} fs;
+constexpr int kFitOverflow = 4096;                 // bins per sample that may exceed the caps
+std::mutex g_fit_mu;
+constexpr int kFitK = 6144, kFitRN = 22528;       // exceedance-array caps: (6144 + 2 * 22528) * 4 B = 200 KB of shared memory
+void release_fit_scratch()
+{
+    DevBuf* all[] = {&fs.obs, &fs.ref, &fs.mu, &fs.phi, &fs.ll, &fs.info, &fs.overflow};
+    for (DevBuf* b : all) release(*b);
+}
+}  // namespace
+extern "C" {
+
+int edb200_betabin_fit_device(const int32_t* observed, int64_t obs_stride, const int32_t* reference, int64_t ref_stride,
+                              int32_t n_samples, int64_t n_bins, double* mu, double* phi, double* loglik, int32_t* info,
+                              void* cuda_stream)
+{
+    if (int rc = need_ctx()) return rc;
+    if (!observed || !reference || !mu || !phi || !loglik || !info || n_samples < 0 || n_bins < 1) return fail(EDB200_ERR_ARG, "bad argument");
+    edb::TableDims d{kFitK, kFitRN, kFitRN};
+    if (edb::betabin_fit_smem_bytes(d) > g.smem_optin)
+        return fail(EDB200_ERR_CUDA, "device offers %zu B of shared memory per CTA; the fit kernel needs %zu", g.smem_optin, edb::betabin_fit_smem_bytes(d));
+    edb::CountsView cv{observed, obs_stride, reference, ref_stride, 0};
+    {
+        std::lock_guard<std::mutex> lk(g_fit_mu);       // grows the overflow scratch (kept until shutdown)
+        if (int rc = ensure(fs.overflow, (size_t)n_samples * kFitOverflow * 8)) return rc;
+    }
+    edb::launch_betabin_fit(cv, n_samples, n_bins, d, 200, fs.overflow.p, kFitOverflow, mu, phi, loglik, info, (cudaStream_t)cuda_stream);
+    g_launches++;
+    return check_kernel("betabin_fit");
+}
+
+int edb200_betabin_fit(const int32_t* observed, int64_t obs_stride, const int32_t* reference, int64_t ref_stride, int32_t n_samples,
+                       int64_t n_bins, double* mu, double* phi, double* loglik, int32_t* info)
+{
+    if (int rc = need_ctx()) return rc;
+    if (!observed || !reference || !mu || !phi || n_samples < 1 || n_bins < 1 || obs_stride < n_bins || (ref_stride && ref_stride < n_bins))
+        return fail(EDB200_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaStream_t st = g.stream;
+    const bool shared_ref = ref_stride == 0;
+    int rc = 0;
+    if ((rc = ensure(fs.obs, (size_t)n_samples * n_bins * 4)) || (rc = ensure(fs.ref, (size_t)(shared_ref ? 1 : n_samples) * n_bins * 4)) ||
+        (rc = ensure(fs.mu, n_samples * 8)) || (rc = ensure(fs.phi, n_samples * 8)) || (rc = ensure(fs.ll, n_samples * 8)) ||
+        (rc = ensure(fs.info, n_samples * 4)))
+        return rc;
+    CU(cudaMemcpy2DAsync(fs.obs.p, n_bins * 4, observed, obs_stride * 4, n_bins * 4, n_samples, cudaMemcpyHostToDevice, st));
+    if (shared_ref) CU(cudaMemcpyAsync(fs.ref.p, reference, n_bins * 4, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemcpy2DAsync(fs.ref.p, n_bins * 4, reference, ref_stride * 4, n_bins * 4, n_samples, cudaMemcpyHostToDevice, st));
+    if ((rc = edb200_betabin_fit_device((const int32_t*)fs.obs.p, n_bins, (const int32_t*)fs.ref.p, shared_ref ? 0 : n_bins, n_samples, n_bins,
+                                        (double*)fs.mu.p, (double*)fs.phi.p, (double*)fs.ll.p, (int32_t*)fs.info.p, st)))
+        return rc;
+    std::vector<int32_t> inf(n_samples);
+    CU(cudaMemcpyAsync(mu, fs.mu.p, n_samples * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(phi, fs.phi.p, n_samples * 8, cudaMemcpyDeviceToHost, st));
+    if (loglik) CU(cudaMemcpyAsync(loglik, fs.ll.p, n_samples * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(inf.data(), fs.info.p, n_samples * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int warn = 0;
+    for (int s = 0; s < n_samples; s++) {
+        if (info) info[s] = inf[s];
+        if (inf[s] < 0) warn = EDB200_WARN_NAN;
+    }
+    return warn;
 }
 
 }  // extern "C"

@@ -157,6 +157,15 @@ int refset_gram_slices(int m, int n, int64_t k_pad, int n_sms);       // K-slice
 void launch_refset_gram(const double* za, int m, const double* zb, int n, int64_t k_pad, int n_slices, double* partial,
                         double* c, cudaStream_t st);
 
+// ---- beta-binomial maximum-likelihood fit (betabin.cu) ---------------------------------------------------
+// One CTA per sample; dims = caps of the exceedance arrays (observed, reference, total counts).
+// info[s] >= 0: Newton iterations used; -1 degenerate sample; -2 negative counts or more than ovf_cap bins beyond the
+// caps; -3 iteration cap; -4 binomial limit.
+size_t betabin_fit_smem_bytes(TableDims d);
+// overflow: device scratch of n_samples * ovf_cap int2 for the bins whose counts exceed the caps
+void launch_betabin_fit(CountsView c, int n_samples, int64_t n_bins, TableDims dims, int max_iter, void* overflow, int ovf_cap,
+                        double* mu, double* phi, double* loglik, int32_t* info, cudaStream_t st);
+
 // ---- forward pass / transition-probability grid (extension, forward.cu) -------------------------------
 struct ForwardArgs {
     const ChainDesc* chains;      // [n_chains]

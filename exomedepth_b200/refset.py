@@ -1,8 +1,8 @@
-"""Host-side mirror of the deterministic front half of `select.reference.set` (R/optimize_reference_set.R:51-102):
-bin selection on the host (a few quantiles), the correlation sweep on the GPU through the C ABI.
+"""Host-side mirror of `select.reference.set` (R/optimize_reference_set.R:51-148): bin selection on the host (a few
+quantiles), the correlation sweep and the per-prefix beta-binomial fits on the GPU through the C ABI.
 
-The greedy aggregate loop that follows in R (:113-141) re-fits the beta-binomial model per prefix with
-`aod::betabin` (third-party, unpinned) and is not part of this package."""
+The reference fits with `aod::betabin` and scores with `VGAM::dbetabinom.ab` (third-party, unpinned): here the fit is
+the likelihood maximiser of exomedepth_b200/csrc/betabin.cu and the score is restated from lgamma (betabin.py)."""
 import ctypes as C
 
 import numpy as np
@@ -59,10 +59,10 @@ def cohort_reference_ranking(counts, bin_length=None, n_bins_reduced=0):
     return dict(selected=sel, correlations=cor, order=order)
 
 
-def select_reference_set(test_counts, reference_counts, bin_length=None, n_bins_reduced=0, names=None):
-    """`select.reference.set(test.counts, reference.counts, bin.length, n.bins.reduced)` up to and including the
-    ordering of the candidates (R/optimize_reference_set.R:51-102).  reference_counts: bins x candidates, as in R.
-    Returns dict(ref_samples, correlations, selected) in the order of `summary.stats`."""
+def rank_candidates(test_counts, reference_counts, bin_length=None, n_bins_reduced=0, names=None):
+    """`select.reference.set` up to and including the ordering of the candidates (R/optimize_reference_set.R:51-102).
+    reference_counts: bins x candidates, as in R.  Returns dict(ref_samples, correlations, selected, order) in the
+    order of `summary.stats`."""
     test = np.asarray(test_counts)
     refs = np.asarray(reference_counts)
     if refs.ndim != 2:
@@ -76,7 +76,54 @@ def select_reference_set(test_counts, reference_counts, bin_length=None, n_bins_
     stacked = np.vstack([test[None, :], refs.T]).astype(np.int32)
     cor = correlations(stacked, sel, bin_length, row0=0, n_rows=1)[0, 1:]
     order = np.argsort(-cor, kind="stable")
-    return dict(ref_samples=[names[i] for i in order], correlations=cor[order], selected=sel)
+    return dict(ref_samples=[names[i] for i in order], correlations=cor[order], selected=sel, order=order)
+
+
+def select_reference_set(test_counts, reference_counts, bin_length=None, n_bins_reduced=0, names=None, chunk=32):
+    """`select.reference.set(test.counts, reference.counts, bin.length, n.bins.reduced)` for the default formula and
+    phi.bins = 1 (R/optimize_reference_set.R:51-148): candidates ordered by correlation, then the aggregate grown one
+    candidate at a time — beta-binomial fit of the test against every prefix sum (GPU, `chunk` prefixes per call),
+    expected Bayes factor of a heterozygous deletion (R/tools.R:128-166) — and the prefix with the largest expected
+    BF chosen.  Returns dict(reference_choice, summary_stats) with summary_stats holding the columns of the R data
+    frame (ref_samples, correlations, expected_BF, phi, RatioSd, mean_p, median_depth, selected) as arrays."""
+    from . import betabin
+    test = np.asarray(test_counts)
+    refs = np.asarray(reference_counts)
+    front = rank_candidates(test, refs, bin_length, n_bins_reduced, names)
+    if front["correlations"] is None:
+        return dict(reference_choice=front["ref_samples"], summary_stats=None)
+    sel, order = front["selected"], front["order"]
+    n = order.size
+    t_sel = test[sel].astype(np.int32)
+    r_sel = refs[sel][:, order].astype(np.int64)            # selected bins x candidates, best first
+    cols = {k: np.full(n, np.nan) for k in ("expected_BF", "phi", "RatioSd", "mean_p", "median_depth")}
+    running = np.zeros(sel.size, np.int64)
+    done = False
+    for i0 in range(0, n, chunk):
+        i1 = min(i0 + chunk, n)
+        prefix = running[None, :] + np.cumsum(r_sel[:, i0:i1].T, axis=0)      # :115  reference <- reference + reference.counts[, i]
+        running = prefix[-1]
+        fit = betabin.fit(np.tile(t_sel, (i1 - i0, 1)), prefix.astype(np.int32))
+        for j in range(i1 - i0):
+            i = i0 + j
+            if fit["info"][j] == -1 or fit["info"][j] == -2:
+                raise _lib.EDB200Error(f"beta-binomial fit of prefix {i + 1} failed: {betabin.INFO[int(fit['info'][j])]}")
+            phi, p = float(fit["phi"][j]), float(fit["expected"][j])
+            cols["phi"][i], cols["mean_p"][i] = phi, p                          # :125-126 (one phi, one p per fit)
+            cols["median_depth"][i] = float(np.median(prefix[j]))               # :127
+            cols["RatioSd"][i] = float(np.mean(np.sqrt(1 + (t_sel + prefix[j] - 1) * phi)))     # :128
+            if i + 1 > 2 and p < 0.05:                                          # :130
+                done = True
+                break
+            alt_odds = p / (1 - p) * 0.5                                        # :133-134
+            cols["expected_BF"][i] = betabin.get_power_betabinom(round(cols["median_depth"][i]), phi, p, alt_odds / (1 + alt_odds))
+        if done:
+            break
+    best = int(np.nanargmax(cols["expected_BF"]))                              # :143 which.max
+    chosen = np.zeros(n, bool)
+    chosen[best] = True
+    stats = dict(ref_samples=front["ref_samples"], correlations=front["correlations"], selected=chosen, **cols)
+    return dict(reference_choice=front["ref_samples"][:best + 1], summary_stats=stats)
 
 
 # ---- device tensors (torch): the two stages, for the sharded sweep --------------------------------------------

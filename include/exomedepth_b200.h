@@ -182,6 +182,25 @@ EDB200_API int edb200_refset_standardize_device(const int32_t *counts, int64_t s
 EDB200_API int edb200_refset_gram_device(const double *za, int32_t m, const double *zb, int32_t n, int64_t n_selected,
                                          double *cor_out, void *cuda_stream);
 
+/* ---- beta-binomial fit of new('ExomeDepth') ---------------------------------------------
+ * Stands in for aod::betabin(cbind(test, reference) ~ 1, random = ~ 1, link = 'logit') + aod::fitted
+ * (R/class_definition.R:118-119, 168) for the default formula: per sample the maximum-likelihood expected proportion
+ * mu (= x@expected, constant over the bins) and over-dispersion phi (= x@phi) of
+ * test ~ BetaBinomial(test + reference, a = mu(1-phi)/phi, b = (1-mu)(1-phi)/phi).  aod is third-party and absent from the
+ * reference tree: parity unpinned, the result is the maximiser of the likelihood (gradient < 1e-12 of the curvature).
+ * observed: int32[n_samples][obs_stride]; reference: int32[n_bins] (ref_stride 0) or [n_samples][ref_stride].
+ * loglik: the maximised log-likelihood without the binomial coefficients; info[s] >= 0: Newton iterations,
+ * -1: degenerate sample (no reads / all reads in the test), -2: negative counts, or more than 4096 bins beyond the
+ * kernel's histogram caps (6143 test reads, 22527 reference or total reads in one bin; up to 4096 such bins per sample
+ * are handled exactly), -3: iteration cap reached, -4: no over-dispersion (phi -> 0).
+ * Returns EDB200_WARN_NAN when any sample has info < 0 (its mu, phi are NaN except for -3 / -4). */
+EDB200_API int edb200_betabin_fit(const int32_t *observed, int64_t obs_stride, const int32_t *reference, int64_t ref_stride,
+                                  int32_t n_samples, int64_t n_bins, double *mu, double *phi, double *loglik, int32_t *info);
+/* same on DEVICE pointers, enqueued on cuda_stream, not synchronised (always returns 0 unless the launch fails) */
+EDB200_API int edb200_betabin_fit_device(const int32_t *observed, int64_t obs_stride, const int32_t *reference, int64_t ref_stride,
+                                         int32_t n_samples, int64_t n_bins, double *mu, double *phi, double *loglik,
+                                         int32_t *info, void *cuda_stream);
+
 /* sticky status word of device-side warnings since the last call with reset != 0 (EDB200_WARN_*) */
 EDB200_API int edb200_status(int reset);
 

@@ -5,8 +5,9 @@ Follows R/optimize_reference_set.R:
             below the 90 % quantile of the bins above 30), optional grid sub-sampling (:88)
   :100      my.correlations: cor(x / (bin.length * sum(x) / 1e6), test / (bin.length * sum(test) / 1e6)) per reference
   :101-102  references ordered by decreasing correlation
-The greedy aggregate loop that follows (:113-141) re-fits the beta-binomial model per prefix with aod::betabin
-(third-party, unpinned) and is not restated here.
+The greedy aggregate loop that follows (:113-141) re-fits the beta-binomial model per prefix with aod::betabin and
+scores it with VGAM::dbetabinom.ab (third-party, unpinned): select_reference_set() below restates it on the scipy
+stand-ins of oracle/betabin.py.
 
 With leave-one-out cohorts (every sample in turn is the test, all others the candidates) total.counts and the bin
 filter do not depend on which sample is the test, so the whole sweep is one N x N Pearson matrix.
@@ -63,3 +64,33 @@ def ranking(cor_row, self_index):
     """:101 order(my.correlations, decreasing = TRUE) over the other samples (stable, like R's order)."""
     idx = np.array([i for i in range(cor_row.size) if i != self_index])
     return idx[np.argsort(-cor_row[idx], kind="stable")]
+
+
+def select_reference_set(test, references, bin_length=None, n_bins_reduced=0, names=None):
+    """The whole function for the default formula / phi.bins = 1 (R/optimize_reference_set.R:51-148), with the scipy
+    stand-ins of oracle/betabin.py for aod::betabin and VGAM::dbetabinom.ab (parity unpinned)."""
+    from oracle import betabin as obb
+    test = np.asarray(test, float)
+    references = np.asarray(references, float)
+    names = list(names) if names is not None else [f"X{i + 1}" for i in range(references.shape[1])]
+    sel = select_bins(references.sum(1) + test, bin_length, n_bins_reduced)
+    bl = np.ones(test.size) if bin_length is None else np.asarray(bin_length, float)
+    cor = correlations(test[sel], references[sel], bl[sel])
+    order = np.argsort(-cor, kind="stable")
+    t, r = test[sel], references[sel][:, order]
+    n = order.size
+    cols = {k: np.full(n, np.nan) for k in ("expected_BF", "phi", "RatioSd", "mean_p", "median_depth")}
+    reference = np.zeros(sel.size)
+    for i in range(n):
+        reference = reference + r[:, i]
+        mu, phi, _ = obb.fit(t, reference)
+        cols["phi"][i], cols["mean_p"][i] = phi, mu
+        cols["median_depth"][i] = np.median(reference)
+        cols["RatioSd"][i] = np.mean(np.sqrt(1 + (t + reference - 1) * phi))
+        if i + 1 > 2 and mu < 0.05:
+            break
+        alt_odds = mu / (1 - mu) * 0.5
+        cols["expected_BF"][i] = obb.get_power_betabinom(round(cols["median_depth"][i]), phi, mu, alt_odds / (1 + alt_odds))
+    best = int(np.nanargmax(cols["expected_BF"]))
+    return dict(reference_choice=[names[j] for j in order[:best + 1]], ref_samples=[names[j] for j in order],
+                correlations=cor[order], **cols)

@@ -148,15 +148,40 @@ def test_cuda_select_reference_set_front_half(exomecount):
     ec = exomecount
     test = ec["Exome1"][:4000]
     refs = np.stack([ec["Exome2"][:4000], ec["Exome3"][:4000], ec["Exome4"][:4000]], 1)
-    got = refset.select_reference_set(test, refs, names=["Ex1", "Ex2", "Ex3"])
+    got = refset.rank_candidates(test, refs, names=["Ex1", "Ex2", "Ex3"])
     sel = oref.select_bins(refs.sum(1) + test)
     cor = oref.correlations(test[sel], refs[sel])
     order = np.argsort(-cor, kind="stable")
     assert got["ref_samples"] == [["Ex1", "Ex2", "Ex3"][i] for i in order]
     np.testing.assert_allclose(got["correlations"], cor[order], rtol=1e-10)
     with pytest.raises(ValueError):
-        refset.select_reference_set(test, refs[:-1])
-    assert refset.select_reference_set(np.zeros(50, np.int32), refs[:50])["correlations"] is None      # :55-60
+        refset.rank_candidates(test, refs[:-1])
+    assert refset.rank_candidates(np.zeros(50, np.int32), refs[:50])["correlations"] is None      # :55-60
+
+
+@pytest.mark.gpu
+def test_cuda_select_reference_set_whole_function():
+    """Correlation ranking, per-prefix beta-binomial fits, expected BF and the chosen prefix against the oracle
+    restatement (scipy stand-ins for aod / VGAM: parity unpinned; tolerances are those of two optimisers)."""
+    from exomedepth_b200 import refset, synth
+    d = synth.cohort(9, n_bins=12000)
+    test, refs = d["observed"][0], d["observed"][1:].T
+    bl = (d["end"] - d["start"] + 1).astype(float)
+    names = [f"S{i}" for i in range(1, 9)]
+    got = refset.select_reference_set(test, refs, bl, names=names, chunk=3)
+    want = oref.select_reference_set(test, refs, bl, names=names)
+    st = got["summary_stats"]
+    assert st["ref_samples"] == want["ref_samples"] and got["reference_choice"] == want["reference_choice"]
+    assert 1 <= len(got["reference_choice"]) <= 8 and int(st["selected"].sum()) == 1
+    np.testing.assert_allclose(st["correlations"], want["correlations"], rtol=1e-10)
+    filled = ~np.isnan(want["phi"])
+    assert np.array_equal(filled, ~np.isnan(st["phi"]))
+    np.testing.assert_allclose(st["phi"][filled], want["phi"][filled], rtol=1e-5)
+    np.testing.assert_allclose(st["mean_p"][filled], want["mean_p"][filled], rtol=1e-6)
+    assert np.array_equal(st["median_depth"][filled], want["median_depth"][filled])
+    np.testing.assert_allclose(st["RatioSd"][filled], want["RatioSd"][filled], rtol=1e-6)
+    bf = ~np.isnan(want["expected_BF"])
+    np.testing.assert_allclose(st["expected_BF"][bf], want["expected_BF"][bf], rtol=1e-4)
 
 
 @pytest.mark.gpu
