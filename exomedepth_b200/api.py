@@ -103,24 +103,36 @@ def _signif(x, digits=3):
 class ExomeDepth:
     """The S4 class of R/class_definition.R:36-46, restricted to the slots the hot path touches.
 
-    The beta-binomial fit (`aod::betabin`, R/class_definition.R:118-168) is third-party and out of scope:
-    `phi` and `expected` are inputs here, exactly as they are inputs to get_loglike_matrix."""
+    `phi` and `expected` may be given (e.g. from an R-side `aod::betabin` fit); when they are None the beta-binomial
+    model of the default formula `cbind(test, reference) ~ 1` is fitted on the GPU (betabin.py; the stand-in for
+    aod::betabin, R/class_definition.R:118-119, 168 — parity unpinned, the result is the likelihood maximiser)."""
 
-    def __init__(self, test, reference, phi, expected, prop_tumor=1.0, verbose=False):
+    def __init__(self, test, reference, phi=None, expected=None, prop_tumor=1.0, verbose=False):
         test = np.asarray(test, float)
         reference = np.asarray(reference, float)
         if test.size != reference.size:
             raise ValueError("Length of test and numeric must match")
         self.test, self.reference = test, reference
-        self.phi = np.broadcast_to(np.asarray(phi, float), test.shape).copy()
-        self.expected = np.broadcast_to(np.asarray(expected, float), test.shape).copy()
         self.likelihood = None
         self.annotations = None
         self.CNV_calls = []
         self.cor_test_reference = float("nan")
         if np.sum(test > 5) < 5:                      # R/class_definition.R:95-98
             self.phi = np.zeros(0)
+            self.expected = np.zeros(0)
             return
+        if phi is None or expected is None:
+            from . import betabin
+            if verbose:
+                print(f"Now fitting the beta-binomial model on a data frame with {test.size} rows : this step can take a few minutes.",
+                      file=sys.stderr)
+            fit = betabin.fit(_i32(test), _i32(reference))
+            if fit["info"][0] in (-1, -2):
+                raise _lib.EDB200Error(f"beta-binomial fit failed: {betabin.INFO[int(fit['info'][0])]}")
+            phi = fit["phi"][0] if phi is None else phi
+            expected = fit["expected"][0] if expected is None else expected
+        self.phi = np.broadcast_to(np.asarray(phi, float), test.shape).copy()
+        self.expected = np.broadcast_to(np.asarray(expected, float), test.shape).copy()
         if verbose:
             print("Now computing the likelihood for the different copy number states", file=sys.stderr)
         self.likelihood = get_loglike_matrix(self.phi, self.expected, _i32(reference + test), _i32(test), prop_tumor)

@@ -102,6 +102,16 @@ class Cohort:
         self._last_ns = ns
         return dict(ll=ll, path=path, calls=calls, ncalls=ncalls, status=rc, call_stats=stats, cor=cor)
 
+    def fit(self, observed, reference):
+        """Beta-binomial fit of every sample against its reference (default formula of new('ExomeDepth'),
+        R/class_definition.R:118-119, 168; betabin.py).  Returns (phi, expected) per sample for run_host / call_cnvs."""
+        from . import betabin
+        r = betabin.fit(observed, reference)
+        bad = np.flatnonzero((r["info"] == -1) | (r["info"] == -2))
+        if bad.size:
+            raise _lib.EDB200Error(f"beta-binomial fit failed for sample {int(bad[0])}: {betabin.INFO[int(r['info'][bad[0]])]}")
+        return r["phi"], r["expected"]
+
     def call_cnvs(self, observed, reference, phi, expected, chromosome_names=None, call_cap=512,
                   mode=_lib.EMISSION_AUTO, want_ll=False, want_path=False):
         """`new('ExomeDepth')`'s likelihood step + `CallCNVs` for every sample of the cohort

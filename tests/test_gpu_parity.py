@@ -346,6 +346,20 @@ def test_chromosome_group_pipeline_matches_single_pass(edb, monkeypatch):
     assert np.array_equal(outs[1][0], one["ll"]) and np.array_equal(outs[1][1], one["path"]) and np.array_equal(outs[1][3], one["ncalls"])
 
 
+def test_exomedepth_object_fits_when_phi_is_not_given(edb, exomecount, kat):
+    """new('ExomeDepth', test, reference) without an external fit: the GPU beta-binomial fit supplies phi / expected
+    (~0.00451 / ~0.2176 for Exome4 against Exome1+2+3), and the calls are those of KAT-4 up to the
+    difference between the fitted and the rounded KAT parameters."""
+    ec = exomecount
+    test = ec["Exome4"].astype(float)
+    reference = (ec["Exome1"] + ec["Exome2"] + ec["Exome3"]).astype(float)
+    x = edb.ExomeDepth(test, reference)
+    assert abs(x.phi[0] - kat["kat3_phi"]) < 1e-6 and abs(x.expected[0] - kat["kat3_expected"]) < 1e-5
+    n = test.size
+    x = edb.CallCNVs(x, ["chr1"] * n, ec["start"], ec["end"], [f"b{i}" for i in range(n)])
+    assert len(x.CNV_calls) == 25 and sum(c["type"] == "deletion" for c in x.CNV_calls) == 19        # KAT-4
+
+
 def test_small_panel_shape(edb, port):
     """BASELINE.json configs[3]: 512 samples x 5,000 bins x 7 states (launch-bound regime, in-register emission kernel).
     The first samples against the oracle, the whole cohort for determinism and sample independence."""

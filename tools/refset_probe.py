@@ -59,3 +59,19 @@ if a.cpu:
     t0 = time.perf_counter()
     _, want = oref.cohort_correlations(counts[:a.cpu], bl)
     print(f"  numpy oracle on {a.cpu} samples: {time.perf_counter() - t0:.3f} s")
+# the beta-binomial fit of every sample against the shared reference aggregate
+ref_t = torch.from_numpy(d["reference"]).to(dev)
+mu = torch.empty(a.samples, dtype=torch.float64, device=dev)
+phi = torch.empty_like(mu)
+ll = torch.empty_like(mu)
+info = torch.empty(a.samples, dtype=torch.int32, device=dev)
+L = _lib.load()
+st = torch.cuda.current_stream().cuda_stream
+_lib.profile(True)
+for _ in range(a.reps):
+    _lib.check(L.edb200_betabin_fit_device(c_t.data_ptr(), c_t.stride(0), ref_t.data_ptr(), 0, a.samples, c_t.shape[1],
+                                           mu.data_ptr(), phi.data_ptr(), ll.data_ptr(), info.data_ptr(), st), "fit")
+prof = _lib.profile_read()
+_lib.profile(False)
+print(f"  betabin_fit          {prof['betabin_fit'][1] / prof['betabin_fit'][0]:9.4f} ms for {a.samples} samples; "
+      f"iterations min/median/max {int(info.min())}/{int(info.median())}/{int(info.max())}")
