@@ -168,21 +168,24 @@ void launch_refset_standardize(const int32_t* counts, int64_t stride, int n_samp
     prof_mark(nullptr, st);
 }
 
+// K-slices of the Gram kernel.  The slice length depends on K only — not on the block of rows a GPU forms — so that an
+// entry of the matrix is the same sum in the same order however the samples are sharded: at most 64 slices of at
+// least 1024 bins.
 int refset_gram_slices(int m, int n, int64_t k_pad, int n_sms)
 {
-    const int64_t tiles = (int64_t)((m + kGT - 1) / kGT) * ((n + kGT - 1) / kGT);
-    int64_t want = (4 * (int64_t)n_sms + tiles - 1) / tiles;           // ~4 CTAs per SM over the grid
-    const int64_t max_slices = (k_pad + 4 * kGK - 1) / (4 * kGK);      // at least 64 k per slice
-    if (want > max_slices) want = max_slices;
-    if (want > 256) want = 256;
-    return want < 1 ? 1 : (int)want;
+    (void)m; (void)n; (void)n_sms;
+    int64_t k_slice = (k_pad + 63) / 64;
+    if (k_slice < 1024) k_slice = 1024;
+    k_slice = (k_slice + kGK - 1) / kGK * kGK;
+    return (int)((k_pad + k_slice - 1) / k_slice);
 }
 
 void launch_refset_gram(const double* za, int m, const double* zb, int n, int64_t k_pad, int n_slices, double* partial,
                         double* c, cudaStream_t st)
 {
     if (m == 0 || n == 0) return;
-    int64_t k_slice = (k_pad + n_slices - 1) / n_slices;
+    int64_t k_slice = (k_pad + 63) / 64;                    // as in refset_gram_slices
+    if (k_slice < 1024) k_slice = 1024;
     k_slice = (k_slice + kGK - 1) / kGK * kGK;
     prof_mark("refset_gram", st);
     refset_gram_kernel<<<dim3((n + kGT - 1) / kGT, (m + kGT - 1) / kGT, n_slices), 256, 0, st>>>(za, m, zb, n, k_pad, k_slice, partial);

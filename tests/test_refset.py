@@ -137,7 +137,7 @@ def test_cuda_sweep_vs_oracle(reduced):
         gaps = np.abs(np.diff(want[t, ref_order]))
         if np.all(gaps > 1e-9):
             assert np.array_equal(got["order"][t], ref_order)
-    # rows of a block against all: the block form the sharded sweep uses
+    # rows of a block against all — the block form the sharded sweep uses — are the same bits as in the full matrix
     blk = refset.correlations(counts, sel, bl, row0=13, n_rows=9)
     assert np.array_equal(blk, got["correlations"][13:22])
 
