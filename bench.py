@@ -282,6 +282,40 @@ def gpu_arm(a, rank, world):
                                        note="+ FP64 likelihood matrix copied back (8*S bytes per bin*sample: bound by the PCIe device-to-host copy)")
         hb.close()
 
+    # ---- the rows around the hot path, device-resident on this rank's cohort: reported, not part of `value`
+    aux = None
+    if rank == 0 and not a.no_aux:
+        from exomedepth_b200 import refset
+        bl = (end - start + 1).astype(np.float64)
+        sel = refset.select_bins(obs_h.sum(0, dtype=np.int64), bl)
+        sel_t, bl_t = torch.from_numpy(sel).to(dev), torch.from_numpy(bl).to(dev)
+        kp = refset.kpad(sel.size)
+        z = torch.empty((ns, kp), dtype=torch.float64, device=dev)
+        cmat = torch.empty((ns, ns), dtype=torch.float64, device=dev)
+        mu_t, phi2_t, ll_t = (torch.empty(ns, dtype=torch.float64, device=dev) for _ in range(3))
+        info_t = torch.empty(ns, dtype=torch.int32, device=dev)
+        L = _lib.load()
+        st0 = torch.cuda.current_stream().cuda_stream
+
+        def aux_step():
+            _lib.check(L.edb200_betabin_fit_device(obs_t.data_ptr(), obs_t.stride(0), ref_t.data_ptr(), 0, ns, nb, mu_t.data_ptr(),
+                                                   phi2_t.data_ptr(), ll_t.data_ptr(), info_t.data_ptr(), st0), "betabin_fit")
+            refset.standardize_device(obs_t, sel_t, bl_t, z)
+            refset.gram_device(z, z, sel.size, cmat)
+
+        aux_step()
+        torch.cuda.synchronize()
+        _lib.profile(True)
+        for _ in range(3):
+            aux_step()
+        pa = {k: v[1] / v[0] for k, v in _lib.profile_read().items()}
+        _lib.profile(False)
+        aux = dict(betabin_fit_ms=pa["betabin_fit"], betabin_fit_iterations_max=int(info_t.max()),
+                   refset_standardize_ms=pa["refset_standardize"], refset_gram_ms=pa["refset_gram"] + pa["refset_reduce"],
+                   refset_gram_tflops_fp64=2.0 * ns * ns * kp / pa["refset_gram"] / 1e9, refset_selected_bins=int(sel.size),
+                   note="beta-binomial fit (aod::betabin stand-in) and select.reference.set correlation sweep of the same cohort; "
+                        "device-resident, CUDA events, not part of `value`")
+
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -316,7 +350,7 @@ def gpu_arm(a, rank, world):
                            if world > 1 else "single rank", table_build_s=table_s, total_calls=total_calls, status=status),
                clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roof(dom),
                roofline_other=roof("emission" if dom != "emission" else "viterbi_sweep"),
-               kernel_ms_per_step={k: round(v, 5) for k, v in sorted(kt.items(), key=lambda kv: -kv[1])})
+               kernel_ms_per_step={k: round(v, 5) for k, v in sorted(kt.items(), key=lambda kv: -kv[1])}, aux=aux)
     if world == 1 and not a.no_cpu:
         from oracle import ref as oref
         cores = os.cpu_count() or 1
@@ -342,6 +376,7 @@ def main():
     ap.add_argument("--bins", type=int, default=N_BINS)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the timings of the fit / reference-set kernels")
     ap.add_argument("--no-ll", action="store_true", help="skip the e2e variant that copies the likelihood matrix back")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
