@@ -1177,7 +1177,10 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
                 }
             }
             CU(cudaStreamWaitEvent(g.s_vit[p], g.ev_em[p], 0));
-            if ((rc = viterbi_part(c, plan[p], va, p == 0 ? 1 : 2, g.s_vit[p]))) return rc;
+            // packing per part: "1" = one sweep warp per SM sub-partition (fast), "2" = two (half the SMs)
+            const char* pp = getenv("EDB200_PACKPLAN");      // experiments, e.g. "222111"
+            const int pack = (pp && strlen(pp) > p) ? pp[p] - '0' : (p == 0 ? 1 : 2);
+            if ((rc = viterbi_part(c, plan[p], va, pack, g.s_vit[p]))) return rc;
             if (b->path)
                 for (int q = 0; q < rg.n; q++) {
                     const int64_t r0 = rg.b0[q], w = rg.b1[q] - r0;

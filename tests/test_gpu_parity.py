@@ -248,6 +248,36 @@ def test_call_glue_matches_reference_vectors(edb, refvec, kat):
 
 
 # ------------------------------------------------------------------------------------------------ edge cases
+def test_call_glue_of_the_widened_rows(edb, exomecount, kat):
+    """r_glue_ext.c driven with fake SEXPs like R's .Call: the beta-binomial fit and the reference-set correlations."""
+    import ctypes as C
+    import os
+    from conftest import ROOT
+    from oracle import refset as oref, sexp
+    p = os.path.join(ROOT, "oracle", "_ref", "librglue_stub.so")
+    if not os.path.exists(p):
+        pytest.skip("oracle/_ref/librglue_stub.so not built (make -C oracle glue)")
+    g = sexp.bind_call_api(C.CDLL(p))
+    g.edb_betabin_fit.restype = sexp.SEXP
+    g.edb_betabin_fit.argtypes = [sexp.SEXP] * 2
+    g.edb_refset_correlations.restype = sexp.SEXP
+    g.edb_refset_correlations.argtypes = [sexp.SEXP] * 4
+    ec = exomecount
+    test, ref = ec["Exome4"], ec["Exome1"] + ec["Exome2"] + ec["Exome3"]
+    h = [sexp.integer(test), sexp.integer(ref)]
+    out = g.edb_betabin_fit(*[x.ptr for x in h])
+    phi, expected, ll, info = sexp.read_real(out)
+    g.edb200_stub_free(out)
+    assert abs(phi - kat["kat3_phi"]) < 1e-6 and abs(expected - kat["kat3_expected"]) < 1e-5 and info >= 0
+    refs = np.stack([ec["Exome1"], ec["Exome2"], ec["Exome3"]], 1)            # bins x candidates, like the R matrix
+    sel = oref.select_bins(refs.sum(1) + test)
+    h = [sexp.integer(test), sexp.integer(np.asfortranarray(refs).ravel(order="F")), sexp.real(np.zeros(0)), sexp.integer(sel + 1)]
+    out = g.edb_refset_correlations(*[x.ptr for x in h])
+    got = sexp.read_real(out)
+    g.edb200_stub_free(out)
+    np.testing.assert_allclose(got, oref.correlations(test[sel], refs[sel]), rtol=1e-10)
+
+
 def test_ragged_and_tiny_inputs(edb, port):
     """One bin, one chromosome of one bin next to long ones, sample counts that do not fill a warp."""
     rng = np.random.default_rng(3)
