@@ -244,7 +244,7 @@ struct edb200_cohort {
     std::vector<Part> plans[Context::kMaxParts + 1];   // plans[n]: the split into n parts (built on first use);
                                                        // plans[0]: {the longest chains, the rest} for the device-resident Viterbi
     // per-batch scratch
-    DevBuf consts, bp, ccalls, cncalls, maxima, fw_grid, fw_chain, fw_out, fw_best, lattices;
+    DevBuf consts, bp, ccalls, cncalls, fw_grid, fw_chain, fw_out, fw_best, lattices;
     int last_host_samples = 0;           // samples whose likelihoods the last host-pointer run left in h_ll
     // host-mode staging
     DevBuf h_obs, h_ref, h_phi, h_exp, h_ll, h_path, h_calls, h_ncalls, h_stats, h_cor;
@@ -713,7 +713,7 @@ void edb200_cohort_destroy(edb200_cohort* c)
             release(part.sched_begin);
             release(part.sched_items);
         }
-    DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->tile_base, &c->decay, &c->fw_grid, &c->fw_chain, &c->fw_out, &c->fw_best, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->maxima, &c->lattices,
+    DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->tile_base, &c->decay, &c->fw_grid, &c->fw_chain, &c->fw_out, &c->fw_best, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->lattices,
                      &c->h_obs, &c->h_ref, &c->h_phi, &c->h_exp, &c->h_ll, &c->h_path, &c->h_calls, &c->h_ncalls, &c->h_stats, &c->h_cor};
     for (DevBuf* b : all) release(*b);
     delete c;

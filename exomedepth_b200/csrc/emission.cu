@@ -106,40 +106,6 @@ void launch_emission_direct(CountsView c, const StateConst* consts, int n_sample
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-count_maxima_kernel(CountsView c, int n_samples, int64_t n_bins, int32_t* __restrict__ maxima3)
-{
-    int mo = 0, mr = 0, mt = 0;
-    const int64_t total = (int64_t)n_samples * n_bins;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int sample = (int)(i / n_bins);
-        const int64_t b = i - sample * n_bins;
-        int tot, obs;
-        load_counts(c, sample, b, tot, obs);
-        mo = max(mo, obs);
-        mr = max(mr, tot - obs);
-        mt = max(mt, tot);
-    }
-    for (int d = 16; d; d >>= 1) {
-        mo = max(mo, __shfl_xor_sync(0xffffffffu, mo, d));
-        mr = max(mr, __shfl_xor_sync(0xffffffffu, mr, d));
-        mt = max(mt, __shfl_xor_sync(0xffffffffu, mt, d));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMax(maxima3 + 0, mo);
-        atomicMax(maxima3 + 1, mr);
-        atomicMax(maxima3 + 2, mt);
-    }
-}
-
-void launch_count_maxima(CountsView c, int n_samples, int64_t n_bins, int32_t* maxima3, cudaStream_t st)
-{
-    cudaMemsetAsync(maxima3, 0, 3 * sizeof(int32_t), st);
-    if (n_bins == 0 || n_samples == 0) return;
-    count_maxima_kernel<<<148 * 4, 256, 0, st>>>(c, n_samples, n_bins, maxima3);
-}
-
-// ---------------------------------------------------------------------------------------------
 // Table path.  One work item = (sample, state).  Lattices (see DESIGN.md "emission_table"):
 //   G1[k] = lgamma(fl(a1+k))            - lgamma(a1)          k = observed
 //   G2[r] = lgamma(fl(a2+r))            - lgamma(a2)          r = total - observed

@@ -61,9 +61,6 @@ void launch_emission_table(CountsView c, const StateConst* consts, int n_samples
                            const BinRanges& ranges, TableDims dims, LLView out, unsigned* flags, int* queue, int n_sms,
                            double* lattices, int lattice_mode, cudaStream_t st);
 
-// per-launch maxima of observed / other / total over the batch -> int32[3]
-void launch_count_maxima(CountsView c, int n_samples, int64_t n_bins, int32_t* maxima3, cudaStream_t st);
-
 // ---- Viterbi ------------------------------------------------------------------------------------
 // One chain template per chromosome; shared by every sample of the batch.
 struct ChainDesc {

@@ -133,12 +133,6 @@ __device__ __forceinline__ double2 lds_f64x2_fresh(uint32_t addr)
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ int shfl_idx(int v, int src)
-{
-    int r;
-    asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(r) : "r"(v), "r"(src));
-    return r;
-}
 
 // ---- the recurrence -----------------------------------------------------------------------------------
 // cand_k = (em + V[k]) + lt[k]  (hmm.cpp:79), winner = FIRST maximum (strict '>' of hmm.cpp:81).
@@ -150,7 +144,7 @@ __device__ __forceinline__ int shfl_idx(int v, int src)
 // is replaced by -Inf (all candidates lose, from stays -1, V stays -Inf, as in the reference).
 template <int S>
 struct Cand {
-    double c[S];
+    int arg;                        // source state of the step's maximum (first maximum, like the reference's scan)
 };
 
 // what one step reads from shared memory: this lane's transition row and its emission.  Loaded one step AHEAD
@@ -199,37 +193,47 @@ __device__ __forceinline__ void sweep_step(const StepIn<S>& in, uint32_t xch, ui
     // addition wait until all loads are in flight.
     asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, 0x7ff1d00d;\n\t@p mov.f64 %0, 0d0000000000000000;\n\t}" : "+d"(em_s) : "r"(__double2hiint(v[S - 1])));
     double m[S];
+    int id[S];
 #pragma unroll
     for (int k = 0; k < S; k++) {
-        cd.c[k] = __dadd_rn(__dadd_rn(em_s, v[k]), in.lt[k]);
-        m[k] = cd.c[k];
+        m[k] = __dadd_rn(__dadd_rn(em_s, v[k]), in.lt[k]);
+        id[k] = k;
     }
-    // pairs first; the last three survivors are settled by independent compares
+    // pairs first; the last three survivors are settled by independent compares.  A node keeps its left entry unless
+    // the right one is strictly greater, so the surviving index is the reference's first maximum; the index selects
+    // ride on the predicates the value selects need anyway and feed nothing on the dependent chain.
     int n = S;
 #pragma unroll
     for (; n > 3; n = (n + 1) / 2) {
 #pragma unroll
-        for (int p = 0; p + 1 < n; p += 2) m[p / 2] = m[p + 1] > m[p] ? m[p + 1] : m[p];
-        if (n & 1) m[n / 2] = m[n - 1];
+        for (int p = 0; p + 1 < n; p += 2) {
+            const bool right = m[p + 1] > m[p];
+            m[p / 2] = right ? m[p + 1] : m[p];
+            id[p / 2] = right ? id[p + 1] : id[p];
+        }
+        if (n & 1) { m[n / 2] = m[n - 1]; id[n / 2] = id[n - 1]; }
     }
     if (n == 3) {
         const bool p = m[1] > m[0], q2 = m[2] > m[0], r2 = m[2] > m[1];
         const double t = p ? m[1] : m[0];
+        const int ti = p ? id[1] : id[0];
         V = (q2 && r2) ? m[2] : t;
+        cd.arg = (q2 && r2) ? id[2] : ti;
     } else if (n == 2) {
-        V = m[1] > m[0] ? m[1] : m[0];
+        const bool p = m[1] > m[0];
+        V = p ? m[1] : m[0];
+        cd.arg = p ? id[1] : id[0];
     } else {
         V = m[0];
+        cd.arg = id[0];
     }
 }
 
-// back-pointer of the step whose candidates are in `cd` and whose maximum is V
+// back-pointer of the step whose winning source is in `cd` and whose maximum is V
 template <int S>
 __device__ __forceinline__ unsigned sweep_arg(const Cand<S>& cd, double V, double em)
 {
-    unsigned arg = S - 1;
-#pragma unroll
-    for (int k = S - 2; k >= 0; k--) arg = cd.c[k] == V ? (unsigned)k : arg;
+    unsigned arg = (unsigned)cd.arg;
     if (!(V > -HUGE_VAL)) arg = 7u;                         // 7 encodes "from = -1" (hmm.cpp:60)
     if (em == -HUGE_VAL) arg = 0u;                          // hmm.cpp:87
     return arg;
