@@ -1021,7 +1021,10 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
             if (int rc = emission_part(c, b, plan[p].ranges, false, emission_mode, p == 0 ? 1 : 2, g.s_em)) return rc;
             CU(cudaEventRecord(g.ev_em[p], g.s_em));
             CU(cudaStreamWaitEvent(g.s_vit[p], g.ev_em[p], 0));
-            if (int rc = viterbi_part(c, plan[p], va, p == 0 ? 1 : 2, g.s_vit[p])) return rc;
+            // first part: one warp per sub-partition on SMs of its own; later parts spread over the others
+            const int64_t items0 = (int64_t)plan[0].chains.size() * va.groups;
+            const int ctas0 = (int)std::min<int64_t>(g.n_sms / 2, (items0 + 3) / 4);
+            if (int rc = viterbi_part(c, plan[p], va, p == 0 ? 1 : 0, g.s_vit[p], p == 0 ? ctas0 : g.n_sms - ctas0)) return rc;
             CU(cudaEventRecord(g.ev_vit[p], g.s_vit[p]));
         }
         for (size_t p = 0; p < plan.size(); p++) CU(cudaStreamWaitEvent(st, g.ev_vit[p], 0));
