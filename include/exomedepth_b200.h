@@ -9,6 +9,10 @@
  * Every entry point runs on the selected B200 (sm_100a).  There is NO CPU fallback: without a usable
  * device the calls return EDB200_ERR_CUDA and edb200_last_error() says why.
  *
+ * Threading: the host-pointer entry points serialise on an internal mutex.  The device-pointer entry points only
+ * enqueue work; they share the context's helper streams and scratch buffers, so calls into one context must not be
+ * issued concurrently from several host threads (one process per GPU is the intended deployment).
+ *
  * Return value of every int function: 0 on success, otherwise a bit mask of the EDB200_* codes.
  * EDB200_WARN_NAN alone is not a failure: like the reference (src/error.c:35-52, error.h:9) a GSL-style
  * domain error yields NaN in the affected cells, a message, and the computation continues.

@@ -40,8 +40,9 @@ obs_t = torch.from_numpy(obs).to(dev)
 ref_t = torch.from_numpy(d["reference"]).to(dev)
 phi_t = torch.from_numpy(phi).to(dev)
 exp_t = torch.from_numpy(exp).to(dev)
-ll = torch.empty((ns, S, nb), dtype=torch.float64, device=dev)
-path = torch.empty((ns, nb), dtype=torch.int8, device=dev)
+nbp = (nb + 15) // 16 * 16                                  # the Viterbi reads whole 128-byte lines of the rows
+ll = torch.empty((ns, S, nbp), dtype=torch.float64, device=dev)
+path = torch.empty((ns, nbp), dtype=torch.int8, device=dev)
 calls = torch.zeros((ns, 512, 4), dtype=torch.int32, device=dev)
 ncalls = torch.zeros(ns, dtype=torch.int32, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
