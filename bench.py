@@ -167,6 +167,9 @@ def gpu_arm(a, rank, world):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION: keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     S, ns = N_STATES, a.samples

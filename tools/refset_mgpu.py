@@ -25,6 +25,8 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 edb.init(local)
 if world > 1:
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"                  # the version banner goes to stdout
     dist.init_process_group("nccl", device_id=dev)
 d = synth.cohort(16, n_bins=a.bins)
 rng = np.random.default_rng(0)                              # every rank generates the same cohort, then keeps its block
