@@ -150,7 +150,7 @@ def reference_arm(a, rank):
                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=kind, sample=sample,
                                  per_core=float(np.mean(per_core))),
                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -167,9 +167,6 @@ def gpu_arm(a, rank, world):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION: keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     S, ns = N_STATES, a.samples
@@ -364,12 +361,29 @@ def gpu_arm(a, rank, world):
         out["cpu_baseline"] = dict(value=v, unit=UNIT, cores=cores, kind=kind, per_core=pc, wall_s=wall,
                                    sample=f"{nsamp} of the same synthetic samples x {nb} bins, {states} states "
                                           f"(the reference implements 3 states only), one sample per worker process")
-    print(json.dumps(out), flush=True)
+    emit(out)
     if dist:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Libraries write banners to file descriptor 1 (NCCL prints its version there at NCCL_DEBUG=VERSION, which this
+    image sets): everything but the final JSON line is sent to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(out):
+    print(json.dumps(out), file=_REAL_STDOUT or sys.stdout, flush=True)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
