@@ -13,17 +13,18 @@
 //   sweep    one lane per (chain, destination state); a warp carries G = 32/S chains of the SAME
 //            chromosome from G consecutive samples.  The sweep is a chain of dependent FP64 operations
 //            (~20,000 steps for chromosome 1), so this kernel is about the latency of ONE step
-//            (tools/ubench/step.cu measures the variants on a B200): the S lanes of a chain exchange
-//            V[i-1][k] with SHFL.IDX issued back to back; the maximum is a tournament on VALUES only and
-//            the winning source state (the back-pointer) is derived afterwards as "first candidate equal
-//            to the maximum", in the shadow of the next step's exchange; the shared log-transition rows
-//            stream through a per-warp shared-memory ring with TMA (cp.async.bulk + mbarrier
-//            complete_tx), 16 observations per tile; every lane prefetches its own emission row one
-//            tile ahead with 128-bit loads; back-pointers leave as 64 bits per lane and tile.
+//            (tools/ubench/step.cu measures the variants on a B200).  Warp roles: 4 or 8 sweep warps and one
+//            producer warp per CTA; the producer issues, per 16-observation tile and sweep warp, one 2-D TMA
+//            load of the emission tile (128-byte swizzle) and one bulk copy of the tile's log-transition rows
+//            into the warp's ring stage (full / empty mbarriers).  Inside a tile the S lanes of a chain exchange
+//            V[i-1][k] through shared memory (STS.64, warp barrier, 128-bit loads), the additions are pinned
+//            behind the last exchange load, transition rows and emissions are read one step ahead, the maximum
+//            is a left-keeping tournament whose predicates also select the winning source state (the
+//            back-pointer), and back-pointers leave as 64 bits per lane and tile.
 //            Work items (chromosome x group of samples) are placed on the SM sub-partitions by the
 //            host (longest-processing-time first), so the longest chains run alone on theirs.
 //            This file is compiled with ptxas -O1: at the default level ptxas interleaves the exchange
-//            with its consumers and the step takes 228 instead of 126 cycles.
+//            with its consumers (2.32 instead of 2.06 ms per sweep when measured).
 //   tilemap  composes the 16 back-pointer steps of every tile into a map end state -> state before
 //            the tile (fully parallel);
 //   trace    one warp per chain walks one map per tile instead of one back-pointer per observation
