@@ -23,6 +23,7 @@ EXPORTS = (
     "edb200_cohort_forward_device", "edb200_cohort_forward_last",
     "edb200_refset_correlations", "edb200_refset_kpad", "edb200_refset_standardize_device", "edb200_refset_gram_device",
     "edb200_betabin_fit", "edb200_betabin_fit_device",
+    "edb200_refset_block_alloc", "edb200_refset_peers_open", "edb200_refset_peers_close", "edb200_refset_gram_peers_device",
 )
 
 
@@ -100,6 +101,14 @@ def load():
     L.edb200_refset_standardize_device.argtypes = [vp, i64, i32, vp, vp, i64, vp, vp]
     L.edb200_refset_gram_device.restype = C.c_int
     L.edb200_refset_gram_device.argtypes = [vp, i32, vp, i32, i64, vp, vp]
+    L.edb200_refset_block_alloc.restype = C.c_int
+    L.edb200_refset_block_alloc.argtypes = [i32, i64, C.POINTER(vp), vp]
+    L.edb200_refset_peers_open.restype = C.c_int
+    L.edb200_refset_peers_open.argtypes = [vp, i32, i32]
+    L.edb200_refset_peers_close.restype = C.c_int
+    L.edb200_refset_peers_close.argtypes = []
+    L.edb200_refset_gram_peers_device.restype = C.c_int
+    L.edb200_refset_gram_peers_device.argtypes = [i32, i32, i32, i64, vp, vp]
     L.edb200_betabin_fit.restype = C.c_int
     L.edb200_betabin_fit.argtypes = [vp, i64, vp, i64, i32, i64, vp, vp, vp, vp]
     L.edb200_betabin_fit_device.restype = C.c_int

@@ -1248,7 +1248,9 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
 // ------------------------------------------------------------------------------------------------ reference-set sweep
 namespace {
 struct RefsetScratch {
-    DevBuf counts, bl, sel, z, partial, c;
+    DevBuf counts, bl, sel, z, partial, c, block;      // block: this rank's standardised rows, shared with the peers over IPC
+    void* peer[edb::kMaxPeers] = {};
+    int n_peers = 0, my_rank = 0;
 } rs;
 }  // namespace
 
@@ -1256,7 +1258,7 @@ struct RefsetScratch {
 namespace {
 void release_refset_scratch()
 {
-    DevBuf* all[] = {&rs.counts, &rs.bl, &rs.sel, &rs.z, &rs.partial, &rs.c};
+    DevBuf* all[] = {&rs.counts, &rs.bl, &rs.sel, &rs.z, &rs.partial, &rs.c, &rs.block};
     for (DevBuf* b : all) release(*b);
     release_fit_scratch();
 }
@@ -1276,19 +1278,91 @@ int edb200_refset_standardize_device(const int32_t* counts, int64_t stride, int3
     return check_kernel("refset_standardize");
 }
 
+static int refset_gram_common(const double* za, int32_t m, const edb::PeerRows& zb, int32_t n, int64_t n_selected, double* cor_out,
+                              cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lk(g_mu);           // the K-slice scratch is shared
+    const int64_t k_pad = edb200_refset_kpad(n_selected);
+    const int slices = edb::refset_gram_slices(m, n, k_pad, g.n_sms);
+    if (int rc = ensure(rs.partial, (size_t)slices * m * n * 8)) return rc;
+    edb::launch_refset_gram(za, m, zb, n, k_pad, slices, (double*)rs.partial.p, cor_out, st);
+    g_launches += 2;
+    return check_kernel("refset_gram");
+}
+
 int edb200_refset_gram_device(const double* za, int32_t m, const double* zb, int32_t n, int64_t n_selected, double* cor_out,
                               void* cuda_stream)
 {
     if (int rc = need_ctx()) return rc;
     if (!za || !zb || !cor_out || m < 0 || n < 0) return fail(EDB200_ERR_ARG, "bad argument");
     if (m == 0 || n == 0) return 0;
-    std::lock_guard<std::mutex> lk(g_mu);           // the K-slice scratch is shared
-    const int64_t k_pad = edb200_refset_kpad(n_selected);
-    const int slices = edb::refset_gram_slices(m, n, k_pad, g.n_sms);
-    if (int rc = ensure(rs.partial, (size_t)slices * m * n * 8)) return rc;
-    edb::launch_refset_gram(za, m, zb, n, k_pad, slices, (double*)rs.partial.p, cor_out, (cudaStream_t)cuda_stream);
-    g_launches += 2;
-    return check_kernel("refset_gram");
+    edb::PeerRows rows{};
+    rows.base[0] = zb;
+    rows.rows_per_rank = n > 0 ? n : 1;
+    return refset_gram_common(za, m, rows, n, n_selected, cor_out, (cudaStream_t)cuda_stream);
+}
+
+// ---- the sharded sweep without an all-gather: peers' standardised blocks are mapped with CUDA IPC -----------------
+int edb200_refset_block_alloc(int32_t rows_per_rank, int64_t n_selected, void** z_dev, void* ipc_handle_out)
+{
+    if (int rc = need_ctx()) return rc;
+    if (rows_per_rank < 1 || n_selected < 2 || !z_dev || !ipc_handle_out) return fail(EDB200_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(g_mu);
+    const size_t bytes = (size_t)rows_per_rank * edb200_refset_kpad(n_selected) * 8;
+    // a fresh cudaMalloc allocation: IPC handles cover whole allocations, so the block must not share one with anything
+    if (rs.block.p) CU(cudaFree(rs.block.p));
+    rs.block.p = nullptr;
+    rs.block.cap = 0;
+    CU(cudaMalloc(&rs.block.p, bytes));
+    rs.block.cap = bytes;
+    CU(cudaMemset(rs.block.p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, rs.block.p));
+    static_assert(sizeof(h) == EDB200_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    memcpy(ipc_handle_out, &h, sizeof h);
+    *z_dev = rs.block.p;
+    return 0;
+}
+
+int edb200_refset_peers_open(const void* handles, int32_t world, int32_t my_rank)
+{
+    if (int rc = need_ctx()) return rc;
+    if (!handles || world < 1 || world > edb::kMaxPeers || my_rank < 0 || my_rank >= world) return fail(EDB200_ERR_ARG, "bad argument (at most %d ranks)", edb::kMaxPeers);
+    if (!rs.block.p) return fail(EDB200_ERR_ARG, "edb200_refset_block_alloc has not been called");
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int r = 0; r < world; r++) {
+        if (r == my_rank) { rs.peer[r] = rs.block.p; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)r * sizeof h, sizeof h);
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        rs.peer[r] = p;
+    }
+    rs.n_peers = world;
+    rs.my_rank = my_rank;
+    return 0;
+}
+
+int edb200_refset_peers_close(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < rs.n_peers; r++)
+        if (r != rs.my_rank && rs.peer[r]) cudaIpcCloseMemHandle(rs.peer[r]);
+    rs.n_peers = 0;
+    return 0;
+}
+
+int edb200_refset_gram_peers_device(int32_t m, int32_t rows_per_rank, int32_t n_total, int64_t n_selected, double* cor_out, void* cuda_stream)
+{
+    if (int rc = need_ctx()) return rc;
+    if (rs.n_peers < 1) return fail(EDB200_ERR_ARG, "edb200_refset_peers_open has not been called");
+    if (!cor_out || m < 0 || m > rows_per_rank || n_total < 1 || (int64_t)rs.n_peers * rows_per_rank < n_total) return fail(EDB200_ERR_ARG, "bad argument");
+    if (m == 0) return 0;
+    edb::PeerRows rows{};
+    for (int r = 0; r < rs.n_peers; r++) rows.base[r] = (const double*)rs.peer[r];
+    rows.rows_per_rank = rows_per_rank;
+    return refset_gram_common((const double*)rs.block.p, m, rows, n_total, n_selected, cor_out, (cudaStream_t)cuda_stream);
 }
 
 int edb200_refset_correlations(const int32_t* counts, int64_t stride, int32_t n_samples, const double* bin_length,

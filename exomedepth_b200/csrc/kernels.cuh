@@ -150,8 +150,13 @@ int launch_call_summary(const CallSummaryArgs& a, cudaStream_t st);   // returns
 void launch_refset_standardize(const int32_t* counts, int64_t stride, int n_samples, const double* bin_length,
                                const int32_t* selected, int64_t n_sel, int64_t k_pad, double* z, cudaStream_t st);
 int refset_gram_slices(int m, int n, int64_t k_pad, int n_sms);       // K-slices the Gram kernel is split into
+constexpr int kMaxPeers = 16;
+struct PeerRows {                     // rows of the B operand: row j lives at base[j / rows_per_rank] + (j % rows_per_rank) * k_pad
+    const double* base[kMaxPeers];
+    int rows_per_rank;
+};
 // c[m][n] = za . zb^T clamped to [-1, 1]; partial: scratch of n_slices * m * n doubles
-void launch_refset_gram(const double* za, int m, const double* zb, int n, int64_t k_pad, int n_slices, double* partial,
+void launch_refset_gram(const double* za, int m, const PeerRows& zb, int n, int64_t k_pad, int n_slices, double* partial,
                         double* c, cudaStream_t st);
 
 // ---- beta-binomial maximum-likelihood fit (betabin.cu) ---------------------------------------------------

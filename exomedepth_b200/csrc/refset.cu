@@ -88,9 +88,13 @@ refset_standardize_kernel(const int32_t* __restrict__ counts, int64_t stride, co
 // C_slice[slice][i][j] = sum over the slice's k of Za[i][k] * Zb[j][k].  128 x 128 x 16 tiles, 256 threads, 8 x 8 outputs
 // per thread (two 4-wide groups 64 apart in each direction): 4 FMAs per shared-memory double, the ratio the FP64 pipe
 // needs to stay ahead of the shared-memory bandwidth.
+// The B operand may live on several GPUs: row j of the cohort is row j % rows_per_rank of rank j / rows_per_rank, and
+// `zb.base[rank]` is that rank's standardised block mapped into this process (CUDA IPC; loads go over NVLink / NVSwitch
+// peer memory).  The all-gather of the sharded sweep is thereby fused into the contraction: tiles are fetched from
+// their owners while other tiles are being multiplied, and no rank ever holds a copy of the whole matrix Z.
 constexpr int kGT = 128, kGK = 16;
 __global__ void __launch_bounds__(256)
-refset_gram_kernel(const double* __restrict__ za, int m, const double* __restrict__ zb, int n, int64_t k_pad, int64_t k_slice,
+refset_gram_kernel(const double* __restrict__ za, int m, const __grid_constant__ PeerRows zb, int n, int64_t k_pad, int64_t k_slice,
                    double* __restrict__ partial)
 {
     __shared__ __align__(16) double sa[kGK][kGT], sb[kGK][kGT];       // k-major
@@ -110,7 +114,8 @@ refset_gram_kernel(const double* __restrict__ za, int m, const double* __restric
             for (int q = 0; q < 4; q++) av[q] = p[q];
         }
         if (tj + lr < n) {
-            const double2* p = reinterpret_cast<const double2*>(zb + (int64_t)(tj + lr) * k_pad + k + lk);
+            const int row = tj + lr, owner = row / zb.rows_per_rank;
+            const double2* p = reinterpret_cast<const double2*>(zb.base[owner] + (int64_t)(row - owner * zb.rows_per_rank) * k_pad + k + lk);
 #pragma unroll
             for (int q = 0; q < 4; q++) bv[q] = p[q];
         }
@@ -180,7 +185,7 @@ int refset_gram_slices(int m, int n, int64_t k_pad, int n_sms)
     return (int)((k_pad + k_slice - 1) / k_slice);
 }
 
-void launch_refset_gram(const double* za, int m, const double* zb, int n, int64_t k_pad, int n_slices, double* partial,
+void launch_refset_gram(const double* za, int m, const PeerRows& zb, int n, int64_t k_pad, int n_slices, double* partial,
                         double* c, cudaStream_t st)
 {
     if (m == 0 || n == 0) return;

@@ -133,12 +133,40 @@ def kpad(n_selected):
 
 def standardize_device(counts, selected, bin_length, z, stream=None):
     """counts: CUDA int32 [n, stride]; selected: CUDA int32 [k]; bin_length: CUDA float64 [n_bins] or None;
-    z: CUDA float64 [n, kpad(k)] (written)."""
+    z: CUDA float64 [n, kpad(k)] (written), or the raw device address of such a block (block_alloc)."""
     import torch
     st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
     return _lib.check(_lib.load().edb200_refset_standardize_device(
         counts.data_ptr(), counts.stride(0), counts.shape[0], bin_length.data_ptr() if bin_length is not None else None,
-        selected.data_ptr(), selected.numel(), z.data_ptr(), st), "edb200_refset_standardize_device")
+        selected.data_ptr(), selected.numel(), z if isinstance(z, int) else z.data_ptr(), st), "edb200_refset_standardize_device")
+
+
+def block_alloc(rows_per_rank, n_selected):
+    """This rank's block of standardised rows for the all-gather-free sharded sweep: (device address, 64-byte CUDA IPC
+    handle to pass to the other ranks)."""
+    p = C.c_void_p()
+    h = C.create_string_buffer(64)
+    _lib.check(_lib.load().edb200_refset_block_alloc(int(rows_per_rank), int(n_selected), C.byref(p), h), "edb200_refset_block_alloc")
+    return int(p.value), h.raw
+
+
+def peers_open(handles, my_rank):
+    """handles: the 64-byte IPC handles of every rank's block, in rank order."""
+    blob = b"".join(handles)
+    _lib.check(_lib.load().edb200_refset_peers_open(blob, len(handles), int(my_rank)), "edb200_refset_peers_open")
+
+
+def peers_close():
+    _lib.check(_lib.load().edb200_refset_peers_close(), "edb200_refset_peers_close")
+
+
+def gram_peers_device(m, rows_per_rank, n_total, n_selected, out, stream=None):
+    """out[m, n_total] = this rank's first m block rows against every sample, the other ranks' rows read from their
+    memory over NVLink (CUDA IPC) inside the Gram kernel."""
+    import torch
+    st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+    return _lib.check(_lib.load().edb200_refset_gram_peers_device(int(m), int(rows_per_rank), int(n_total), int(n_selected),
+                                                                  out.data_ptr(), st), "edb200_refset_gram_peers_device")
 
 
 def gram_device(za, zb, n_selected, out, stream=None):

@@ -185,6 +185,22 @@ EDB200_API int edb200_refset_standardize_device(const int32_t *counts, int64_t s
 /* cor_out[m][n] = rows of za against rows of zb */
 EDB200_API int edb200_refset_gram_device(const double *za, int32_t m, const double *zb, int32_t n, int64_t n_selected,
                                          double *cor_out, void *cuda_stream);
+/* The sharded sweep WITHOUT an all-gather (one process per GPU of one NVLink / NVSwitch box): every rank keeps its
+ * standardised rows in a block owned by this library; the other ranks map it with CUDA IPC and the Gram kernel reads
+ * the B tiles straight from their owners' memory while it multiplies others — the all-gather is fused into the
+ * contraction and no rank holds the whole matrix.  Protocol (exomedepth_b200/shard.py:refset_sweep, fused=True):
+ *   1. edb200_refset_block_alloc            allocate the block (rows_per_rank rows, zero filled), get its IPC handle
+ *   2. exchange the handles (any channel), edb200_refset_peers_open(all handles, world, my_rank)
+ *   3. edb200_refset_standardize_device into the block; synchronise the device; barrier across the ranks
+ *   4. edb200_refset_gram_peers_device      this rank's m rows against all n_total rows (row j lives on rank
+ *                                           j / rows_per_rank); identical bits to the all-gather form
+ *   5. barrier; edb200_refset_peers_close */
+#define EDB200_IPC_HANDLE_BYTES 64
+EDB200_API int edb200_refset_block_alloc(int32_t rows_per_rank, int64_t n_selected, void **z_dev, void *ipc_handle_out);
+EDB200_API int edb200_refset_peers_open(const void *handles /* world x 64 bytes, rank order */, int32_t world, int32_t my_rank);
+EDB200_API int edb200_refset_peers_close(void);
+EDB200_API int edb200_refset_gram_peers_device(int32_t m, int32_t rows_per_rank, int32_t n_total, int64_t n_selected,
+                                               double *cor_out, void *cuda_stream);
 
 /* ---- beta-binomial fit of new('ExomeDepth') ---------------------------------------------
  * Stands in for aod::betabin(cbind(test, reference) ~ 1, random = ~ 1, link = 'logit') + aod::fitted

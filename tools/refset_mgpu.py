@@ -19,6 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--samples", type=int, default=512)
 ap.add_argument("--bins", type=int, default=200_000)
 ap.add_argument("--check", type=int, default=1)
+ap.add_argument("--fused", type=int, default=0, help="1: no all-gather, the Gram kernel reads the peers' blocks over NVLink (CUDA IPC)")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -36,13 +37,13 @@ for s in range(a.samples):
 bl = (d["end"] - d["start"] + 1).astype(float)
 lo, hi = shard.shard_range(a.samples, rank, world)
 grp = dist if world > 1 else None
-shard.refset_sweep(counts[lo:hi], a.samples, bl, 0, grp, device=dev)          # warm-up
+shard.refset_sweep(counts[lo:hi], a.samples, bl, 0, grp, device=dev, fused=bool(a.fused))          # warm-up
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 e0.record()
-sel, cor = shard.refset_sweep(counts[lo:hi], a.samples, bl, 0, grp, device=dev)
+sel, cor = shard.refset_sweep(counts[lo:hi], a.samples, bl, 0, grp, device=dev, fused=bool(a.fused))
 e1.record()
 torch.cuda.synchronize()
 t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -61,6 +62,54 @@ if rank == 0:
         ok = bool(np.array_equal(full, want))
         print("max |difference| to the single-GPU matrix:", float(np.max(np.abs(full - want))))
     print(json.dumps(dict(workload=f"reference-set sweep, {a.samples} samples x {counts.shape[1]} bins, {sel.size} selected bins",
-                          n_gpus=world, ms_sweep_incl_upload_and_collectives=float(t[0]), identical_to_single_gpu=ok)))
+                          n_gpus=world, fused=bool(a.fused), ms_sweep_incl_upload_and_collectives=float(t[0]), identical_to_single_gpu=ok)))
+# ---- device time of the exchange + contraction stage alone (inputs resident, rows already standardised) ----------
 if world > 1:
+    sel_t = torch.from_numpy(sel).to(dev)
+    bl_t = torch.from_numpy(bl).to(dev)
+    c_t = torch.from_numpy(counts[lo:hi]).to(dev)
+    per = -(-a.samples // world)
+    kp = refset.kpad(sel.size)
+    n_local = hi - lo
+    out = torch.empty((n_local, a.samples), dtype=torch.float64, device=dev)
+
+    def stage_time(fn, reps=5):
+        best = 1e30
+        for _ in range(reps):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = min(best, float(t[0]))
+        return best
+
+    z_local = torch.zeros((per, kp), dtype=torch.float64, device=dev)
+    refset.standardize_device(c_t, sel_t, bl_t, z_local[:n_local])
+    z_all = torch.empty((world * per, kp), dtype=torch.float64, device=dev)
+
+    def gather_then_gram():
+        dist.all_gather_into_tensor(z_all, z_local)
+        refset.gram_device(z_local[:n_local], z_all[:a.samples], sel.size, out)
+
+    t_nccl = stage_time(gather_then_gram)
+    ref_out = out.clone()
+    z_ptr, handle = refset.block_alloc(per, sel.size)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle)
+    refset.peers_open(handles, rank)
+    refset.standardize_device(c_t, sel_t, bl_t, z_ptr)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_fused = stage_time(lambda: refset.gram_peers_device(n_local, per, a.samples, sel.size, out))
+    same = bool(torch.equal(out, ref_out))
+    dist.barrier()
+    refset.peers_close()
+    if rank == 0:
+        print(json.dumps(dict(stage="exchange + Gram, device time, max over ranks", n_gpus=world, samples=a.samples,
+                              ms_nccl_all_gather_then_gram=t_nccl, ms_fused_peer_memory_gram=t_fused, identical=same,
+                              all_gather_bytes_per_rank=int((world - 1) * per * kp * 8))))
     dist.destroy_process_group()
