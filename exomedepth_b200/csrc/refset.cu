@@ -5,7 +5,8 @@
 // (R/optimize_reference_set.R:100) for every sample of a cohort at once: with leave-one-out cohorts the selected bins
 // do not depend on which sample is the test, so the sweep is one Pearson matrix of the normalised count rows
 // (SURVEY.md §8f-1).  Two kernels:
-//   refset_standardize_kernel  one CTA per sample: gather the selected bins, y = x / (bin.length * sum(x) / 1e6)
+//   refset_standardize_kernel  one thread-block cluster of 8 CTAs per sample (sums exchanged through distributed shared
+//                              memory): gather the selected bins, y = x / (bin.length * sum(x) / 1e6)
 //                              evaluated as R does, two-pass mean / centred norm with compensated sums,
 //                              z = (y - mean) / norm  ->  Z[sample][bin], K padded with zeros.  HBM-bound (reads
 //                              the int32 counts once per pass, writes 8 bytes per selected bin).
@@ -14,6 +15,8 @@
 //                              256-sample cohort still fills the 148 SMs; the K-slices are summed in slice order by
 //                              refset_reduce_kernel (deterministic, no atomics).  This is the one dense contraction of
 //                              the package; it stays on the FP64 pipe because the result is compared at 1e-10.
+#include <cooperative_groups.h>
+
 #include "kernels.cuh"
 
 namespace edb {
@@ -30,9 +33,19 @@ __device__ __forceinline__ void acc_add(Acc& a, double x)
     a.c = __dadd_rn(a.c, __dadd_rn(__dadd_rn(a.s, -__dadd_rn(t, -bp)), __dadd_rn(x, -bp)));
     a.s = t;
 }
-// CTA-wide total of a compensated sum, combined in lane / warp order (deterministic); every thread gets the result
-__device__ double cta_total(Acc a, double* red /* [2 * 32] */)
+}  // namespace
+
+// One thread-block CLUSTER of kStdCluster CTAs per sample: every CTA takes one contiguous slice of the selected bins; the
+// three sample-wide sums (total, mean, centred norm) are exchanged through distributed shared memory — each CTA
+// publishes its compensated partial sum in its own shared memory, the cluster synchronises, and every CTA adds the
+// partials of all ranks in rank order, so all of them hold the same bits.
+constexpr int kStdCluster = 8, kStdThreads = 512;
+
+__device__ double cluster_total(Acc a, double* red /* [64] */, double* slot /* [2], this CTA's published partial */)
 {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    // CTA-wide partial, compensated, in lane / warp order
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
         const double s2 = __shfl_xor_sync(0xffffffffu, a.s, d), c2 = __shfl_xor_sync(0xffffffffu, a.c, d);
@@ -43,51 +56,61 @@ __device__ double cta_total(Acc a, double* red /* [2 * 32] */)
         a = lo;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-    __syncthreads();
     if (lane == 0) { red[2 * warp] = a.s; red[2 * warp + 1] = a.c; }
     __syncthreads();
-    Acc t{0, 0};
-    for (int w = 0; w < n_warps; w++) {
-        acc_add(t, red[2 * w]);
-        t.c = __dadd_rn(t.c, red[2 * w + 1]);
+    if (threadIdx.x == 0) {
+        Acc t{0, 0};
+        for (int w = 0; w < n_warps; w++) {
+            acc_add(t, red[2 * w]);
+            t.c = __dadd_rn(t.c, red[2 * w + 1]);
+        }
+        slot[0] = t.s;
+        slot[1] = t.c;
     }
+    cluster.sync();                                         // every CTA's partial is published
+    Acc t{0, 0};
+    for (unsigned r = 0; r < cluster.num_blocks(); r++) {
+        const double* remote = cluster.map_shared_rank(slot, r);
+        acc_add(t, remote[0]);
+        t.c = __dadd_rn(t.c, remote[1]);
+    }
+    cluster.sync();                                         // nobody overwrites its slot while others still read it
     return __dadd_rn(t.s, t.c);
 }
 
-}  // namespace
-
-__global__ void __launch_bounds__(1024)
+__global__ void __cluster_dims__(kStdCluster, 1, 1) __launch_bounds__(kStdThreads)
 refset_standardize_kernel(const int32_t* __restrict__ counts, int64_t stride, const double* __restrict__ bin_length,
                           const int32_t* __restrict__ selected, int64_t n_sel, int64_t k_pad, double* __restrict__ z)
 {
     __shared__ double red[64];
-    const int32_t* __restrict__ row = counts + blockIdx.x * stride;
-    double* __restrict__ out = z + blockIdx.x * k_pad;      // also the scratch for y between the passes (L2 resident)
+    __shared__ double slot[2];
+    const int sample = blockIdx.x / kStdCluster, part = blockIdx.x % kStdCluster;
+    const int32_t* __restrict__ row = counts + sample * stride;
+    double* __restrict__ out = z + sample * k_pad;          // also the scratch for y between the passes (L2 resident)
+    const int64_t per = (k_pad / 16 + kStdCluster - 1) / kStdCluster * 16;      // slice of this CTA, whole 16-bin groups
+    const int64_t i0 = part * per, i1 = i0 + per < k_pad ? i0 + per : k_pad, s1 = i1 < n_sel ? i1 : n_sel;
     Acc a{0, 0};
-    for (int64_t i = threadIdx.x; i < n_sel; i += blockDim.x) acc_add(a, (double)row[selected[i]]);
-    const double total = cta_total(a, red);                 // sum(x) over the selected bins: an integer, exact
+    for (int64_t i = i0 + threadIdx.x; i < s1; i += blockDim.x) acc_add(a, (double)row[selected[i]]);
+    const double total = cluster_total(a, red, slot);       // sum(x) over the selected bins: an integer, exact
     a = Acc{0, 0};
-    for (int64_t i = threadIdx.x; i < n_sel; i += blockDim.x) {
+    for (int64_t i = i0 + threadIdx.x; i < s1; i += blockDim.x) {
         const int32_t b = selected[i];
         const double bl = bin_length ? bin_length[b] : 1.0;
         const double y = __ddiv_rn((double)row[b], __ddiv_rn(__dmul_rn(bl, total), 1e6));   // x / ((bin.length * sum(x)) / 10^6)
         out[i] = y;
         acc_add(a, y);
     }
-    const double mean = __ddiv_rn(cta_total(a, red), (double)n_sel);
+    const double mean = __ddiv_rn(cluster_total(a, red, slot), (double)n_sel);
     a = Acc{0, 0};
-    for (int64_t i = threadIdx.x; i < n_sel; i += blockDim.x) {      // each thread re-reads what it wrote itself
+    for (int64_t i = i0 + threadIdx.x; i < s1; i += blockDim.x) {      // each thread re-reads what it wrote itself
         const double d = __dadd_rn(out[i], -mean);
         out[i] = d;
         acc_add(a, __dmul_rn(d, d));
     }
-    const double norm = sqrt(cta_total(a, red));            // 0 for a constant row: z becomes NaN, cor() gives NA there too
-    for (int64_t i = threadIdx.x; i < k_pad; i += blockDim.x) out[i] = i < n_sel ? __ddiv_rn(out[i], norm) : 0.0;
+    const double norm = sqrt(cluster_total(a, red, slot));  // 0 for a constant row: z becomes NaN, cor() gives NA there too
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) out[i] = i < n_sel ? __ddiv_rn(out[i], norm) : 0.0;
 }
 
-// C_slice[slice][i][j] = sum over the slice's k of Za[i][k] * Zb[j][k].  128 x 128 x 16 tiles, 256 threads, 8 x 8 outputs
-// per thread (two 4-wide groups 64 apart in each direction): 4 FMAs per shared-memory double, the ratio the FP64 pipe
-// needs to stay ahead of the shared-memory bandwidth.
 // The B operand may live on several GPUs: row j of the cohort is row j % rows_per_rank of rank j / rows_per_rank, and
 // `zb.base[rank]` is that rank's standardised block mapped into this process (CUDA IPC; loads go over NVLink / NVSwitch
 // peer memory).  The all-gather of the sharded sweep is thereby fused into the contraction: tiles are fetched from
@@ -169,7 +192,7 @@ void launch_refset_standardize(const int32_t* counts, int64_t stride, int n_samp
 {
     if (n_samples == 0) return;
     prof_mark("refset_standardize", st);
-    refset_standardize_kernel<<<n_samples, 1024, 0, st>>>(counts, stride, bin_length, selected, n_sel, k_pad, z);
+    refset_standardize_kernel<<<n_samples * kStdCluster, kStdThreads, 0, st>>>(counts, stride, bin_length, selected, n_sel, k_pad, z);
     prof_mark(nullptr, st);
 }
 
