@@ -107,12 +107,17 @@ class ExomeDepth:
     model of the default formula `cbind(test, reference) ~ 1` is fitted on the GPU (betabin.py; the stand-in for
     aod::betabin, R/class_definition.R:118-119, 168 — parity unpinned, the result is the likelihood maximiser)."""
 
-    def __init__(self, test, reference, phi=None, expected=None, prop_tumor=1.0, verbose=False):
+    def __init__(self, test, reference, phi=None, expected=None, prop_tumor=1.0, verbose=False, positions=None):
         test = np.asarray(test, float)
         reference = np.asarray(reference, float)
         if test.size != reference.size:
             raise ValueError("Length of test and numeric must match")
         self.test, self.reference = test, reference
+        # `positions` (the GRanges slot, R/class_definition.R:44): dict(chromosome, start, end), one entry per bin
+        if positions is not None and len(positions["start"]) != test.size:
+            raise ValueError("The provided genomic positions (GRanges object) and test count vector are not matching in length: "
+                             f"{len(positions['start'])}, {test.size}")                       # R/class_definition.R:163-165
+        self.positions = positions
         self.likelihood = None
         self.annotations = None
         self.CNV_calls = []
@@ -136,6 +141,21 @@ class ExomeDepth:
         if verbose:
             print("Now computing the likelihood for the different copy number states", file=sys.stderr)
         self.likelihood = get_loglike_matrix(self.phi, self.expected, _i32(reference + test), _i32(test), prop_tumor)
+
+
+def TestCNV(x, chromosome, start, end, type):
+    """R/class_definition.R:243-256 — the log likelihood ratio in favour of a CNV of the given type over the bins that
+    lie inside [start, end] on `chromosome` (the likelihood matrix is the one the GPU computed at construction)."""
+    if type not in ("deletion", "duplication"):
+        raise ValueError("type must be either duplication or deletion")
+    if not isinstance(chromosome, str):
+        raise ValueError("The input chromosome must be a character or a factor")
+    if getattr(x, "positions", None) is None:
+        raise ValueError("This function cannot be used if the position of the exons/DNA segments was not included in the ExomeDepth object")
+    pos = x.positions
+    inside = (np.asarray([str(c) for c in pos["chromosome"]]) == chromosome) & (np.asarray(pos["start"]) >= start) & (np.asarray(pos["end"]) <= end)
+    col = 0 if type == "deletion" else 2
+    return float(math.fsum(x.likelihood[inside, col] - x.likelihood[inside, 1]))
 
 
 def CallCNVs(x, chromosome, start, end, name, transition_probability=1e-4, expected_CNV_length=50000):

@@ -390,6 +390,30 @@ def test_exomedepth_object_fits_when_phi_is_not_given(edb, exomecount, kat):
     assert len(x.CNV_calls) == 25 and sum(c["type"] == "deletion" for c in x.CNV_calls) == 19        # KAT-4
 
 
+def test_testcnv_matches_the_called_bayes_factor(edb, exomecount, kat):
+    """TestCNV (R/class_definition.R:243-256) over the extent of a called CNV is that call's Bayes factor before the
+    log10(e) factor and signif(): the doc example's positive control region is a called deletion."""
+    import math
+    ec = exomecount
+    n = 4000
+    test = ec["Exome4"][:n].astype(float)
+    reference = (ec["Exome1"] + ec["Exome2"] + ec["Exome3"])[:n].astype(float)
+    pos = dict(chromosome=["chr1"] * n, start=ec["start"][:n], end=ec["end"][:n])
+    x = edb.ExomeDepth(test, reference, kat["kat3_phi"], kat["kat3_expected"], positions=pos)
+    x = edb.CallCNVs(x, pos["chromosome"], pos["start"], pos["end"], [f"b{i}" for i in range(n)])
+    assert len(x.CNV_calls) >= 5
+    for c in x.CNV_calls[:5]:
+        lr = edb.TestCNV(x, "chr1", c["start"], c["end"], c["type"])
+        inside = (pos["start"] >= c["start"]) & (pos["end"] <= c["end"])
+        if int(inside.sum()) == c["nexons"]:                 # overlapping bins can add or drop a bin at the edges
+            assert float(f"{math.log10(math.e) * lr:.3g}") == pytest.approx(c["BF"], rel=1e-9)
+            assert lr > 0
+    with pytest.raises(ValueError):
+        edb.TestCNV(x, "chr1", 1, 2, "gain")
+    with pytest.raises(ValueError):
+        edb.TestCNV(edb.ExomeDepth(test, reference, 0.01, 0.2), "chr1", 1, 2, "deletion")
+
+
 def test_small_panel_shape(edb, port):
     """BASELINE.json configs[3]: 512 samples x 5,000 bins x 7 states (launch-bound regime, in-register emission kernel).
     The first samples against the oracle, the whole cohort for determinism and sample independence."""
