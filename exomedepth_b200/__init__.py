@@ -7,6 +7,7 @@ Host-side mirror of the reference's interface for ONE hot path (emission log-lik
     ExomeDepth(test, reference, phi, expected, ...)                R/class_definition.R:82-191 (likelihood step)
     CallCNVs(x, chromosome, start, end, name, ...)                 R/class_definition.R:311-419
     TestCNV(x, chromosome, start, end, type)                       R/class_definition.R:243-256
+    somatic_CNV_call(normal, tumor, prop_tumor, ...)               R/class_definition.R:442-461
     Cohort                                                         many samples × one bin set, device resident
 and, widening along SURVEY.md §8f:
     betabin.fit(test, reference)                                   stand-in for aod::betabin (R/class_definition.R:118-119)
@@ -16,6 +17,6 @@ All numerics run in hand-written sm_100a CUDA kernels through the C ABI in inclu
 There is no CPU fallback.
 """
 from ._lib import EDB200Error, device_info, init, launch_count  # noqa: F401
-from .api import C_hmm, CallCNVs, ExomeDepth, TestCNV, emission, get_loglike_matrix, viterbi_hmm  # noqa: F401
+from .api import C_hmm, CallCNVs, ExomeDepth, TestCNV, emission, get_loglike_matrix, somatic_CNV_call, viterbi_hmm  # noqa: F401
 from .cohort import Cohort  # noqa: F401
 from . import betabin, refset  # noqa: F401

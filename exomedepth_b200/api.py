@@ -158,6 +158,14 @@ def TestCNV(x, chromosome, start, end, type):
     return float(math.fsum(x.likelihood[inside, col] - x.likelihood[inside, 1]))
 
 
+def somatic_CNV_call(normal, tumor, prop_tumor=1.0, chromosome=None, start=None, end=None, names=None):
+    """R/class_definition.R:442-461 — tumour against its matched normal: the tumour is the test sample, the normal the
+    reference, `prop.tumor` the mixture coefficient of the emission model; beta-binomial fit and CallCNVs as usual."""
+    print("Warning: this function is largely untested and experimental", file=sys.stderr)       # :444
+    x = ExomeDepth(tumor, normal, prop_tumor=prop_tumor)
+    return CallCNVs(x, chromosome, start, end, names, transition_probability=1e-4)
+
+
 def CallCNVs(x, chromosome, start, end, name, transition_probability=1e-4, expected_CNV_length=50000):
     """R/class_definition.R:311-419 on top of the GPU Viterbi. Fills and returns x (x.CNV_calls: list of dict)."""
     if x.phi.size == 0:

@@ -414,6 +414,20 @@ def test_testcnv_matches_the_called_bayes_factor(edb, exomecount, kat):
         edb.TestCNV(edb.ExomeDepth(test, reference, 0.01, 0.2), "chr1", 1, 2, "deletion")
 
 
+def test_somatic_call_is_fit_plus_callcnvs_with_the_mixture(edb, exomecount, port, capsys):
+    """somatic.CNV.call (R/class_definition.R:442-461): prop.tumor reaches get_loglike_matrix as the mixture."""
+    ec = exomecount
+    n = 3000
+    tumor, normal = ec["Exome4"][:n], (ec["Exome1"] + ec["Exome2"] + ec["Exome3"])[:n]
+    x = edb.somatic_CNV_call(normal, tumor, 0.6, ["chr1"] * n, ec["start"][:n], ec["end"][:n], [f"b{i}" for i in range(n)])
+    assert "experimental" in capsys.readouterr().err
+    want = port.get_loglike_matrix(x.phi, x.expected, (tumor + normal).astype(np.int32), tumor.astype(np.int32), 0.6)
+    assert_ll_close(x.likelihood, want)
+    y = edb.CallCNVs(edb.ExomeDepth(tumor, normal, x.phi[0], x.expected[0], prop_tumor=0.6), ["chr1"] * n, ec["start"][:n], ec["end"][:n],
+                     [f"b{i}" for i in range(n)])
+    assert x.CNV_calls == y.CNV_calls
+
+
 def test_small_panel_shape(edb, port):
     """BASELINE.json configs[3]: 512 samples x 5,000 bins x 7 states (launch-bound regime, in-register emission kernel).
     The first samples against the oracle, the whole cohort for determinism and sample independence."""
