@@ -19,7 +19,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--samples", type=int, default=512)
 ap.add_argument("--bins", type=int, default=200_000)
 ap.add_argument("--check", type=int, default=1)
-ap.add_argument("--fused", type=int, default=0, help="1: no all-gather, the Gram kernel reads the peers' blocks over NVLink (CUDA IPC)")
+ap.add_argument("--fused", type=int, default=-1, help="1: no all-gather, the Gram kernel reads the peers' blocks over NVLink (CUDA IPC); "
+                                                     "0: NCCL all-gather, then Gram; -1: the library's choice (fused up to 256 rows per rank)")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -37,13 +38,13 @@ for s in range(a.samples):
 bl = (d["end"] - d["start"] + 1).astype(float)
 lo, hi = shard.shard_range(a.samples, rank, world)
 grp = dist if world > 1 else None
-shard.refset_sweep(counts[lo:hi], a.samples, bl, 0, grp, device=dev, fused=bool(a.fused))          # warm-up
+shard.refset_sweep(counts[lo:hi], a.samples, bl, 0, grp, device=dev, fused=None if a.fused < 0 else bool(a.fused))          # warm-up
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 e0.record()
-sel, cor = shard.refset_sweep(counts[lo:hi], a.samples, bl, 0, grp, device=dev, fused=bool(a.fused))
+sel, cor = shard.refset_sweep(counts[lo:hi], a.samples, bl, 0, grp, device=dev, fused=None if a.fused < 0 else bool(a.fused))
 e1.record()
 torch.cuda.synchronize()
 t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -62,7 +63,7 @@ if rank == 0:
         ok = bool(np.array_equal(full, want))
         print("max |difference| to the single-GPU matrix:", float(np.max(np.abs(full - want))))
     print(json.dumps(dict(workload=f"reference-set sweep, {a.samples} samples x {counts.shape[1]} bins, {sel.size} selected bins",
-                          n_gpus=world, fused=bool(a.fused), ms_sweep_incl_upload_and_collectives=float(t[0]), identical_to_single_gpu=ok)))
+                          n_gpus=world, fused={-1: "auto", 0: False, 1: True}[a.fused], ms_sweep_incl_upload_and_collectives=float(t[0]), identical_to_single_gpu=ok)))
 # ---- device time of the exchange + contraction stage alone (inputs resident, rows already standardised) ----------
 if world > 1:
     sel_t = torch.from_numpy(sel).to(dev)
