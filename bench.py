@@ -154,6 +154,60 @@ def reference_arm(a, rank):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def small_panel(dev, ns=512, states=7, steps=50):
+    """512 samples x 5,000 bins (chr1-chr5, 1,000 each) x 7 states, device-resident: emission + Viterbi + CallCNVs sums per
+    step, as stream launches and as one graph replay."""
+    import torch
+
+    import exomedepth_b200 as edb
+    from exomedepth_b200 import _lib, synth
+    d = synth.cohort(64, per_chrom=(5, 1000))
+    reps = ns // 64
+    nb = int(d["start"].size)
+    nbp = (nb + 15) // 16 * 16
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=states, transition_probability=TP, expected_cnv_length=CNV_LEN)
+    obs = torch.from_numpy(np.tile(d["observed"], (reps, 1))).to(dev)
+    ref = torch.from_numpy(d["reference"]).to(dev)
+    phi, exp = torch.from_numpy(np.tile(d["phi"], reps)).to(dev), torch.from_numpy(np.tile(d["expected"], reps)).to(dev)
+    ll = torch.empty((ns, states, nbp), dtype=torch.float64, device=dev)
+    path = torch.empty((ns, nbp), dtype=torch.int8, device=dev)
+    calls = torch.zeros((ns, 256, 4), dtype=torch.int32, device=dev)
+    ncalls = torch.zeros(ns, dtype=torch.int32, device=dev)
+    stats = torch.zeros((ns, 256, 3), dtype=torch.float64, device=dev)
+    cor = torch.zeros(ns, dtype=torch.float64, device=dev)
+    args, kw = (obs, ref, phi, exp, ll, path, calls, ncalls), dict(what=7, call_stats=stats, cor=cor)
+
+    def timed(fn):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        host_ms = 1e3 * (time.perf_counter() - t0) / steps          # time the host spends enqueueing one step
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, host_ms
+
+    stream_ms, stream_host = timed(lambda: co.run_device(*args, **kw))
+    want = (path.clone(), ncalls.clone(), ll.clone())
+    _lib.launch_count(reset=True)
+    gr = co.capture_device(*args, **kw)
+    per_step = _lib.launch_count(reset=True)
+    graph_ms, graph_host = timed(gr.launch)
+    same = bool(torch.equal(path, want[0]) and torch.equal(ncalls, want[1]) and torch.equal(ll.nan_to_num(), want[2].nan_to_num()))
+    gr.close()
+    co.close()
+    cells = ns * nb
+    return dict(workload=f"synthetic {ns} samples x {nb} bins x {states} CN states (BASELINE.json configs[3]), device-resident, "
+                         "emission + Viterbi + CallCNVs sums", kernels_per_step=int(per_step),
+                stream_launch_ms=stream_ms, stream_launch_host_ms=stream_host, graph_replay_ms=graph_ms, graph_replay_host_ms=graph_host,
+                stream_launch_value=cells / (stream_ms / 1e3), graph_replay_value=cells / (graph_ms / 1e3), unit=UNIT,
+                replay_identical=same, note="CUDA events over 50 back-to-back steps; working set 150 MB > L2")
+
+
 def gpu_arm(a, rank, world):
     import torch
 
@@ -315,6 +369,13 @@ def gpu_arm(a, rank, world):
                    refset_gram_tflops_fp64=2.0 * ns * ns * kp / pa["refset_gram"] / 1e9, refset_selected_bins=int(sel.size),
                    note="beta-binomial fit (aod::betabin stand-in) and select.reference.set correlation sweep of the same cohort; "
                         "device-resident, CUDA events, not part of `value`")
+
+        # BASELINE.json configs[3], the launch-bound regime: plain stream launches against the replay of a captured CUDA
+        # graph (edb200_cohort_capture_device).  Reported only; a failure here must not take the bench line with it.
+        try:
+            aux["small_panel"] = small_panel(dev)
+        except Exception as e:                                          # noqa: BLE001
+            aux["small_panel"] = dict(error=f"{type(e).__name__}: {e}")
 
     if rank != 0:
         if dist:

@@ -18,7 +18,7 @@ EXPORTS = (
     "edb200_init", "edb200_shutdown", "edb200_last_error", "edb200_device_info", "edb200_launch_count",
     "edb200_host_alloc", "edb200_host_free", "edb200_get_loglike_matrix", "edb200_emission", "edb200_hmm",
     "edb200_cohort_create", "edb200_cohort_destroy", "edb200_cohort_table", "edb200_cohort_table_copy",
-    "edb200_cohort_run_device",
+    "edb200_cohort_run_device", "edb200_cohort_capture_device", "edb200_graph_launch", "edb200_graph_destroy",
     "edb200_cohort_run_host", "edb200_status", "edb200_profile", "edb200_profile_read",
     "edb200_cohort_forward_device", "edb200_cohort_forward_last",
     "edb200_refset_correlations", "edb200_refset_kpad", "edb200_refset_standardize_device", "edb200_refset_gram_device",
@@ -87,6 +87,12 @@ def load():
     L.edb200_cohort_table_copy.argtypes = [vp, vp, C.c_int, vp]
     L.edb200_cohort_run_device.restype = C.c_int
     L.edb200_cohort_run_device.argtypes = [vp, C.POINTER(Batch), C.c_int, C.c_int, vp]
+    L.edb200_cohort_capture_device.restype = C.c_int
+    L.edb200_cohort_capture_device.argtypes = [vp, C.POINTER(Batch), C.c_int, C.c_int, C.POINTER(vp)]
+    L.edb200_graph_launch.restype = C.c_int
+    L.edb200_graph_launch.argtypes = [vp, vp]
+    L.edb200_graph_destroy.restype = None
+    L.edb200_graph_destroy.argtypes = [vp]
     L.edb200_cohort_run_host.restype = C.c_int
     L.edb200_cohort_run_host.argtypes = [vp, C.POINTER(Batch), C.c_int]
     L.edb200_cohort_forward_device.restype = C.c_int

@@ -13,6 +13,30 @@ def _ptr(a):
     return a.ctypes.data if a is not None else None
 
 
+class DeviceGraph:
+    """A captured device-resident batch (Cohort.capture_device).  Holds the tensors it was captured over."""
+
+    def __init__(self, lib, handle, tensors, status):
+        self.lib, self.handle, self._tensors, self.status = lib, handle, tensors, status
+
+    def launch(self, stream=None):
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        return _lib.check(self.lib.edb200_graph_launch(self.handle, st), "edb200_graph_launch")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.edb200_graph_destroy(self.handle)
+            self.handle = None
+            self._tensors = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Cohort:
     def __init__(self, chain_offsets, start, end, n_states=3, mixture=1.0, odds=None, transitions=None,
                  transition_probability=1e-4, expected_cnv_length=50000.0, build_table=True, device=-1):
@@ -161,21 +185,35 @@ class Cohort:
         return loglik, best
 
     # ---- device tensors (torch) -----------------------------------------------------------------
+    def _device_batch(self, observed, reference, phi, expected, ll, path, calls, ncalls, call_stats, cor):
+        return _lib.Batch(observed.shape[0], observed.data_ptr(), observed.stride(0), reference.data_ptr(),
+                          0 if reference.dim() == 1 else reference.stride(0), phi.data_ptr(), expected.data_ptr(),
+                          ll.data_ptr(), ll.stride(1), path.data_ptr() if path is not None else None,
+                          path.stride(0) if path is not None else 0, calls.data_ptr() if calls is not None else None,
+                          ncalls.data_ptr() if ncalls is not None else None, calls.shape[1] if calls is not None else 0,
+                          call_stats.data_ptr() if call_stats is not None else None, cor.data_ptr() if cor is not None else None)
+
     def run_device(self, observed, reference, phi, expected, ll, path=None, calls=None, ncalls=None,
                    what=3, mode=_lib.EMISSION_AUTO, stream=None, call_stats=None, cor=None):
         """All arguments are CUDA tensors on this cohort's device; enqueues on `stream` (default: torch's
         current stream) without synchronising."""
         import torch
-        ns = observed.shape[0]
         st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
-        b = _lib.Batch(ns, observed.data_ptr(), observed.stride(0), reference.data_ptr(),
-                       0 if reference.dim() == 1 else reference.stride(0), phi.data_ptr(), expected.data_ptr(),
-                       ll.data_ptr(), ll.stride(1), path.data_ptr() if path is not None else None,
-                       path.stride(0) if path is not None else 0, calls.data_ptr() if calls is not None else None,
-                       ncalls.data_ptr() if ncalls is not None else None, calls.shape[1] if calls is not None else 0,
-                       call_stats.data_ptr() if call_stats is not None else None, cor.data_ptr() if cor is not None else None)
+        b = self._device_batch(observed, reference, phi, expected, ll, path, calls, ncalls, call_stats, cor)
         return _lib.check(self.lib.edb200_cohort_run_device(self.handle, C.byref(b), what, mode, st),
                           "edb200_cohort_run_device")
+
+    def capture_device(self, observed, reference, phi, expected, ll, path=None, calls=None, ncalls=None,
+                       what=3, mode=_lib.EMISSION_AUTO, call_stats=None, cor=None):
+        """Same arguments as run_device: runs the batch once, records it into a CUDA graph and returns a
+        DeviceGraph whose launch() replays it over the same tensors (their contents may change in between) —
+        for small panels, where the step is bound by its launches (edb200_cohort_capture_device)."""
+        b = self._device_batch(observed, reference, phi, expected, ll, path, calls, ncalls, call_stats, cor)
+        h = C.c_void_p()
+        rc = _lib.check(self.lib.edb200_cohort_capture_device(self.handle, C.byref(b), what, mode, C.byref(h)),
+                        "edb200_cohort_capture_device")
+        keep = (observed, reference, phi, expected, ll, path, calls, ncalls, call_stats, cor)
+        return DeviceGraph(self.lib, h, keep, rc)
 
     def forward_device(self, ll, loglik, best=None, tp_grid=None, stream=None):
         """ll: CUDA float64 [n_samples, S, stride] as filled by run_device; loglik: CUDA float64 [n_samples, n_grid];

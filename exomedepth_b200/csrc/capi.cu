@@ -131,9 +131,13 @@ int fail(int code, const char* fmt, ...)
             return fail(EDB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// bumped whenever a workspace moves: captured graphs (edb200_cohort_capture_device) hold workspace addresses
+std::atomic<long long> g_realloc_gen{0};
+
 int ensure(DevBuf& b, size_t bytes)
 {
     if (bytes <= b.cap) return 0;
+    g_realloc_gen++;
     if (b.p) CU(cudaFree(b.p));
     b.p = nullptr;
     b.cap = 0;
@@ -216,6 +220,13 @@ int upload_schedule(const std::vector<int32_t>& nobs, int groups, int n_ctas, in
 edb::KernelTimer* edb::g_timer = nullptr;
 
 // =====================================================================================================
+struct edb200_graph {
+    cudaGraphExec_t exec = nullptr;      // null once the cohort it was captured from is destroyed
+    edb200_cohort* cohort = nullptr;
+    long long realloc_gen = 0;           // g_realloc_gen at capture
+    int kernels = 0;                     // kernel nodes (edb200_launch_count advances by this per replay)
+};
+
 struct edb200_cohort {
     int64_t n_bins = 0;
     int32_t n_chains = 0;
@@ -245,6 +256,7 @@ struct edb200_cohort {
                                                        // plans[0]: {the longest chains, the rest} for the device-resident Viterbi
     // per-batch scratch
     DevBuf consts, bp, ccalls, cncalls, fw_grid, fw_chain, fw_out, fw_best, lattices;
+    std::vector<edb200_graph*> graphs;   // captured replays of this cohort (invalidated when the cohort goes)
     int last_host_samples = 0;           // samples whose likelihoods the last host-pointer run left in h_ll
     // host-mode staging
     DevBuf h_obs, h_ref, h_phi, h_exp, h_ll, h_path, h_calls, h_ncalls, h_stats, h_cor;
@@ -313,6 +325,7 @@ void edb200_shutdown(void)
                      &cs.chains, &cs.bp, &cs.path, &cs.ccalls, &cs.cncalls, &cs.calls, &cs.ncalls, &cs.sched_begin, &cs.sched_items};
     for (DevBuf* b : all) release(*b);
     release_refset_scratch();
+    release_fit_scratch();
     if (g.d_flags) cudaFree(g.d_flags);
     g.d_flags = nullptr;
     if (g.stream) cudaStreamDestroy(g.stream);
@@ -707,6 +720,11 @@ void edb200_cohort_destroy(edb200_cohort* c)
     if (!c) return;
     std::lock_guard<std::mutex> lk(g_mu);
     cudaDeviceSynchronize();
+    for (edb200_graph* gr : c->graphs) {
+        if (gr->exec) cudaGraphExecDestroy(gr->exec);
+        gr->exec = nullptr;
+        gr->cohort = nullptr;
+    }
     for (auto& plan : c->plans)
         for (auto& part : plan) {
             release(part.chain_list);
@@ -993,11 +1011,13 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
         }
         if (what & 2) {
             const bool split = !(getenv("EDB200_VSPLIT") && atoi(getenv("EDB200_VSPLIT")) == 0);     // 0: one pass (tests, experiments)
-            if (split && c->n_chains >= 4 && va.groups >= 8) {
+            if (split && c->n_chains >= 4 && va.groups >= 8)
+                if (int rc = build_plan(c, 0)) return rc;
+            // (chains of near-equal length — small panels — all fall into the first group: nothing to split)
+            if (split && c->n_chains >= 4 && va.groups >= 8 && c->plans[0].size() == 2) {
                 // The longest chromosomes' sweep is the critical path; everything behind a sweep (tilemap, trace, expand)
                 // scales with the chains it covers.  Two concurrent passes — {longest chains} on a few SMs of their own,
                 // {all others} on the rest — leave only the longest chains' own post-processing behind the critical sweep.
-                if (int rc = build_plan(c, 0)) return rc;
                 std::vector<edb200_cohort::Part>& vp = c->plans[0];
                 const int64_t items0 = (int64_t)vp[0].chains.size() * va.groups;
                 const int ctas0 = (int)std::min<int64_t>(g.n_sms / 2, (items0 + 3) / 4);
@@ -1036,6 +1056,83 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
     if (what & 4)
         if (int rc = call_summary(c, b, true, true, st)) return rc;
     return 0;
+}
+
+// ---- CUDA-graph replay of a device-resident batch (small panels: the step is bound by its ~10 launches) ----
+int edb200_cohort_capture_device(edb200_cohort* c, const edb200_batch* b, int what, int emission_mode, edb200_graph** out)
+{
+    if (int rc = need_ctx()) return rc;
+    if (!c || !b || !out) return fail(EDB200_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (b->n_samples <= 0) return fail(EDB200_ERR_ARG, "empty batch");
+    if (edb::g_timer) return fail(EDB200_ERR_ARG, "edb200_profile is on: its event marks cannot be part of a captured graph");
+    cudaStream_t st = g.stream;
+    // 1. one plain run: workspaces are sized, sweep schedules uploaded, argument errors surface un-captured
+    int warn = edb200_cohort_run_device(c, b, what, emission_mode, st);
+    if (warn & (EDB200_ERR_NSTATES | EDB200_ERR_CUDA | EDB200_ERR_ARG)) return warn;
+    CU(cudaStreamSynchronize(st));
+    // 2. the same enqueue again, recorded.  Thread-local mode: an allocation or a synchronisation inside the recorded
+    // call (there is none after step 1) fails the capture instead of being silently left out of the graph.
+    const long long gen = g_realloc_gen.load();
+    const long long launches0 = g_launches.load();
+    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = edb200_cohort_run_device(c, b, what, emission_mode, st);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e_end = cudaStreamEndCapture(st, &graph);
+    const int kernels = (int)(g_launches.load() - launches0);
+    g_launches.store(launches0);                                    // nothing ran
+    if (rc & (EDB200_ERR_NSTATES | EDB200_ERR_CUDA | EDB200_ERR_ARG)) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return rc;
+    }
+    if (e_end != cudaSuccess || !graph) {
+        cudaGetLastError();
+        return fail(EDB200_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(e_end));
+    }
+    if (gen != g_realloc_gen.load()) {
+        cudaGraphDestroy(graph);
+        return fail(EDB200_ERR_CUDA, "internal: a workspace moved during capture");
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t e_inst = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e_inst != cudaSuccess) return fail(EDB200_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e_inst));
+    edb200_graph* gr = new edb200_graph;
+    gr->exec = exec;
+    gr->cohort = c;
+    gr->realloc_gen = gen;
+    gr->kernels = kernels;
+    c->graphs.push_back(gr);
+    *out = gr;
+    return warn;
+}
+
+int edb200_graph_launch(edb200_graph* gr, void* cuda_stream)
+{
+    if (int rc = need_ctx()) return rc;
+    if (!gr) return fail(EDB200_ERR_ARG, "null graph");
+    if (!gr->exec) return fail(EDB200_ERR_ARG, "the cohort this graph was captured from has been destroyed");
+    if (gr->realloc_gen != g_realloc_gen.load())
+        return fail(EDB200_ERR_ARG, "a library workspace was re-allocated after this graph was captured (a larger batch ran since); capture it again");
+    CU(cudaGraphLaunch(gr->exec, (cudaStream_t)cuda_stream));
+    g_launches += gr->kernels;
+    return 0;
+}
+
+void edb200_graph_destroy(edb200_graph* gr)
+{
+    if (!gr) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (gr->exec) {
+        cudaDeviceSynchronize();
+        cudaGraphExecDestroy(gr->exec);
+    }
+    if (gr->cohort) {
+        auto& v = gr->cohort->graphs;
+        v.erase(std::remove(v.begin(), v.end(), gr), v.end());
+    }
+    delete gr;
 }
 
 // transition matrices of the grid: the CallCNVs matrix for every tp, or the cohort's own matrix when tp_grid is null

@@ -152,6 +152,22 @@ EDB200_API int edb200_cohort_run_device(edb200_cohort *c, const edb200_batch *b,
 /* Same, HOST pointers: copies in, runs, copies the non-NULL outputs back, synchronises. */
 EDB200_API int edb200_cohort_run_host(edb200_cohort *c, const edb200_batch *b, int emission_mode);
 
+/* ---- CUDA-graph replay of a device-resident batch ------------------------------------------------------
+ * Small panels (BASELINE config 4: 512 samples x 5,000 bins x 7 states) are bound by the ~10 kernel launches and the
+ * stream fork / join of edb200_cohort_run_device, not by the kernels.  edb200_cohort_capture_device runs the batch
+ * once on an internal stream (so that every workspace is sized), records the same enqueue into a CUDA graph and
+ * returns it; edb200_graph_launch replays it on cuda_stream without synchronising.  The graph holds the ADDRESSES in
+ * `b` and of the library's workspaces: the batch's device buffers must stay allocated, their contents may change
+ * between replays (that is the point).  A replay fails with EDB200_ERR_ARG after the cohort was destroyed or after
+ * any library workspace was re-allocated (a larger batch ran since): capture again.  Not available while
+ * edb200_profile is on.  Replaces the per-sample R loop around the two .Call routines (R/class_definition.R:184-189,
+ * R/tools.R:97) for callers that process many same-shaped batches. */
+typedef struct edb200_graph edb200_graph;
+EDB200_API int  edb200_cohort_capture_device(edb200_cohort *c, const edb200_batch *b, int what, int emission_mode,
+                                             edb200_graph **out);
+EDB200_API int  edb200_graph_launch(edb200_graph *g, void *cuda_stream);
+EDB200_API void edb200_graph_destroy(edb200_graph *g);
+
 /* ---- forward pass and transition-probability grid (EXTENSION: the reference has neither) ----
  * For every sample and every transition probability tp_grid[g] (CallCNVs matrix of R/class_definition.R:343-347
  * built for that tp; tp_grid == NULL: the cohort's own matrix, n_grid ignored): the sum over chromosomes of the

@@ -500,3 +500,121 @@ def test_full_size_properties(edb):
                      for c in range(len(off) - 1))
         if direct == 0:
             assert np.array_equal(inside, p != 0)
+
+
+def _device_batch(d, S, call_cap=256):
+    import torch
+    dev = torch.device("cuda:0")
+    ns, nb = d["observed"].shape
+    nbp = (nb + 15) & ~15
+    t = dict(obs=torch.from_numpy(d["observed"]).to(dev), ref=torch.from_numpy(d["reference"]).to(dev),
+             phi=torch.from_numpy(d["phi"]).to(dev), exp=torch.from_numpy(d["expected"]).to(dev),
+             ll=torch.zeros((ns, S, nbp), dtype=torch.float64, device=dev),
+             path=torch.full((ns, nbp), 99, dtype=torch.int8, device=dev),
+             calls=torch.zeros((ns, call_cap, 4), dtype=torch.int32, device=dev),
+             ncalls=torch.zeros(ns, dtype=torch.int32, device=dev),
+             stats=torch.zeros((ns, call_cap, 3), dtype=torch.float64, device=dev),
+             cor=torch.zeros(ns, dtype=torch.float64, device=dev))
+    return t
+
+
+def _snapshot(t, nb):
+    import torch
+    torch.cuda.synchronize()
+    n = t["ncalls"].cpu().numpy()
+    calls = t["calls"].cpu().numpy()
+    stats = t["stats"].cpu().numpy()
+    return dict(ll=t["ll"][:, :, :nb].cpu().numpy(), path=t["path"][:, :nb].cpu().numpy(), ncalls=n,
+                calls=[calls[s, :n[s]].copy() for s in range(n.size)], stats=[stats[s, :n[s]].copy() for s in range(n.size)],
+                cor=t["cor"].cpu().numpy())
+
+
+def _same(a, b):
+    return (np.array_equal(a["ll"], b["ll"], equal_nan=True) and np.array_equal(a["path"], b["path"]) and
+            np.array_equal(a["ncalls"], b["ncalls"]) and np.array_equal(a["cor"], b["cor"]) and
+            all(np.array_equal(x, y) for x, y in zip(a["calls"], b["calls"])) and
+            all(np.array_equal(x, y) for x, y in zip(a["stats"], b["stats"])))
+
+
+def test_equal_length_chains_device_call(edb, port):
+    """Small-panel geometry of SURVEY.md §8d (C4: the first 1,000 bins of chr1–chr5): every chain has the same length, so
+    the device call's {longest chains | others} split has nothing in its second group — one pass, checked against the
+    oracle for one sample group and for sample independence over the rest."""
+    from exomedepth_b200 import synth
+    import torch
+    S = 7
+    d = synth.cohort(8, per_chrom=(5, 1000))
+    assert np.all(np.diff(d["offsets"]) == 1000)
+    reps = 8                                                            # 64 samples = 16 sample groups at S = 7 (>= 8: the split path is tried)
+    big = dict(d, observed=np.tile(d["observed"], (reps, 1)), phi=np.tile(d["phi"], reps), expected=np.tile(d["expected"], reps))
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=S)
+    t = _device_batch(big, S)
+    co.run_device(t["obs"], t["ref"], t["phi"], t["exp"], t["ll"], t["path"], t["calls"], t["ncalls"], what=7,
+                  call_stats=t["stats"], cor=t["cor"])
+    got = _snapshot(t, 5000)
+    for r in range(1, reps):
+        assert np.array_equal(got["path"][:8], got["path"][8 * r: 8 * r + 8]) and np.array_equal(got["ncalls"][:8], got["ncalls"][8 * r: 8 * r + 8])
+    odds, T = port.state_odds(S), port.callcnvs_transitions(S, 1e-4)
+    for s in range(3):
+        assert_ll_close(got["ll"][s].T, port.emission(d["phi"][s], d["expected"][s], d["observed"][s] + d["reference"], d["observed"][s], odds))
+        k = 0
+        for c in range(5):
+            b0, b1 = d["offsets"][c], d["offsets"][c + 1]
+            loc, pos = framing.frame_chromosome(got["ll"][s][:, b0:b1].T, d["start"][b0:b1].astype(float), d["end"][b0:b1].astype(float), 50000.0)
+            path, calls = port.c_hmm(T, loc, pos, 50000.0)
+            assert np.array_equal(got["path"][s, b0:b1], path[1:-1])
+            for (sp, ep, typ, nex) in calls:
+                assert got["calls"][s][k].tolist() == [sp - 1 + b0, ep - 1 + b0, typ, nex]
+                k += 1
+        assert got["ncalls"][s] == k
+
+
+@pytest.mark.parametrize("shape", ["small_panel", "genome"])
+def test_graph_replay_matches_stream_launches(edb, shape):
+    """edb200_cohort_capture_device / edb200_graph_launch: the replay of a captured batch is bit-identical to the plain
+    stream launches — also after the CONTENTS of the batch's buffers changed (the graph holds addresses, not data)."""
+    from exomedepth_b200 import _lib, synth
+    import torch
+    if shape == "small_panel":
+        S, nb = 7, 5000
+        d = synth.cohort(40, per_chrom=(5, 1000))                       # 10 sample groups: equal chains, one pass
+    else:
+        S, nb = 5, 9000
+        d = synth.cohort(48, n_bins=nb)                                 # 8 sample groups, 24 ragged chains: the split Viterbi (two streams)
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=S)
+    t = _device_batch(d, S)
+    args = (t["obs"], t["ref"], t["phi"], t["exp"], t["ll"], t["path"], t["calls"], t["ncalls"])
+    kw = dict(what=7, call_stats=t["stats"], cor=t["cor"])
+    co.run_device(*args, **kw)
+    want_a = _snapshot(t, nb)
+    _lib.launch_count(reset=True)
+    gr = co.capture_device(*args, **kw)
+    per_step = _lib.launch_count(reset=True)                            # the capture's own plain run
+    assert per_step >= 6
+    assert _same(_snapshot(t, nb), want_a)
+    # new contents in the same buffers: rotate the samples
+    for k in ("obs", "phi", "exp"):
+        t[k].copy_(torch.roll(t[k], 3, 0))
+    for k in ("ll", "path", "calls", "ncalls", "stats", "cor"):
+        t[k].zero_()
+    gr.launch()
+    got_b = _snapshot(t, nb)
+    assert _lib.launch_count() == per_step                              # a replay counts the kernels it launches
+    for k in ("ll", "path", "calls", "ncalls", "stats", "cor"):
+        t[k].zero_()
+    co.run_device(*args, **kw)
+    want_b = _snapshot(t, nb)
+    assert _same(got_b, want_b)
+    assert np.array_equal(np.roll(want_a["path"], 3, 0), want_b["path"])
+    # replays are repeatable, and on a side stream
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    for _ in range(3):
+        gr.launch(stream=side.cuda_stream)
+    side.synchronize()
+    assert _same(_snapshot(t, nb), want_b)
+    # a destroyed cohort invalidates its graphs loudly
+    co.close()
+    with pytest.raises(_lib.EDB200Error, match="destroyed"):
+        gr.launch()
+    gr.close()
