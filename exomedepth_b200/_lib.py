@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("EDB200_LIB") or os.path.join(_HERE, "libexomedepth_b2
 
 OK, WARN_NAN, ERR_NSTATES, ERR_CUDA, ERR_ARG, WARN_CALLCAP = 0, 1, 2, 4, 8, 16
 MAX_STATES = 7
-EMISSION_AUTO, EMISSION_DIRECT, EMISSION_TABLE = 0, 1, 2
+EMISSION_AUTO, EMISSION_DIRECT, EMISSION_TABLE, EMISSION_PANEL = 0, 1, 2, 3
 
 EXPORTS = (
     "edb200_init", "edb200_shutdown", "edb200_last_error", "edb200_device_info", "edb200_launch_count",

@@ -324,8 +324,7 @@ void edb200_shutdown(void)
     DevBuf* all[] = {&cs.phi, &cs.expected, &cs.total, &cs.observed, &cs.odds, &cs.ll, &cs.consts, &cs.lt,
                      &cs.chains, &cs.bp, &cs.path, &cs.ccalls, &cs.cncalls, &cs.calls, &cs.ncalls, &cs.sched_begin, &cs.sched_items};
     for (DevBuf* b : all) release(*b);
-    release_refset_scratch();
-    release_fit_scratch();
+    release_refset_scratch();            // also releases the fit scratch
     if (g.d_flags) cudaFree(g.d_flags);
     g.d_flags = nullptr;
     if (g.stream) cudaStreamDestroy(g.stream);
@@ -825,6 +824,18 @@ static bool use_table(const edb200_cohort* c, int mode)
     return mode == EDB200_EMISSION_AUTO && c->n_bins >= 4 * (int64_t)(kTableK + 2 * kTableRN);
 }
 
+// Panels (a few thousand bins, many samples): the full lattice does not amortise its 26,624-entry build over the bins of
+// one (sample, state), the in-register kernel pays ~450 FP64 instructions per cell — a lattice sized to the panel, built
+// by all threads over one shared index space (emission.cu, kPanel), costs ~65 per entry and a gather per cell.  Worth it
+// once there are enough (sample, state) items to fill the SMs; counts beyond it take the in-register path cell by cell.
+static bool panel_table(const edb200_cohort* c, int64_t n_items, int mode, edb::TableDims* d)
+{
+    if (mode == EDB200_EMISSION_DIRECT || mode == EDB200_EMISSION_TABLE) return false;
+    if (mode == EDB200_EMISSION_AUTO && (c->n_bins < 4096 || n_items < 2 * (int64_t)g.n_sms)) return false;
+    *d = c->n_bins < 16384 ? edb::TableDims{2048, 4096, 4096} : edb::TableDims{2048, 8192, 8192};
+    return true;
+}
+
 // how many chromosome groups a batch is pipelined over (1 = emission, then Viterbi, on the caller's stream)
 static int pick_parts(const edb200_cohort* c, int mode, int wanted)
 {
@@ -842,14 +853,15 @@ static int emission_part(edb200_cohort* c, const edb200_batch* b, const edb::Bin
     edb::CountsView cv{b->observed, b->obs_stride, b->reference, b->ref_stride, 0};
     edb::LLView out{b->ll, (int64_t)S * b->ll_stride, b->ll_stride};
     edb::StateConst* consts = (edb::StateConst*)c->consts.p;
-    if (use_table(c, mode)) {
-        edb::TableDims d{kTableK, kTableRN, kTableRN};
+    edb::TableDims d{kTableK, kTableRN, kTableRN};
+    const bool panel = !use_table(c, mode) && whole && lattice_mode == 0 && panel_table(c, (int64_t)ns * S, mode, &d);
+    if (panel || use_table(c, mode)) {
         if (edb::emission_table_smem_bytes(d) > g.smem_optin)
             return fail(EDB200_ERR_CUDA, "device offers %zu B of shared memory per CTA; the lattice kernel needs %zu",
                         g.smem_optin, edb::emission_table_smem_bytes(d));
         if (lattice_mode)
             if (int rc = ensure(c->lattices, (size_t)ns * S * (kTableK + 2 * kTableRN) * 8)) return rc;
-        edb::prof_mark("emission", st);
+        edb::prof_mark(panel ? "emission_panel" : "emission", st);
         edb::launch_emission_table(cv, consts, ns, S, rg, d, out, g.d_flags, g.d_queue, g.n_sms, (double*)c->lattices.p, lattice_mode, st);
     } else {
         if (!whole) return fail(EDB200_ERR_ARG, "internal: the in-register emission kernel covers whole rows only");
@@ -925,7 +937,7 @@ static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiA
         std::vector<int32_t> nobs(pt.chains.size());
         for (size_t i = 0; i < pt.chains.size(); i++) nobs[i] = c->chains_h[pt.chains[i]].nobs;
         const char* force = getenv("EDB200_SWEEP_WARPS");          // experiments: 4 or 8
-        pt.sched_warps = force ? (atoi(force) == 8 ? 8 : 4) : packed == 1 ? 4 : packed == 2 ? 8 : edb::viterbi_pick_warps(nobs.data(), (int)nobs.size(), a.groups, g.n_sms);
+        pt.sched_warps = force ? (atoi(force) == 8 ? 8 : 4) : packed == 1 ? 4 : packed == 2 ? 8 : edb::viterbi_pick_warps(nobs.data(), (int)nobs.size(), a.groups, avail_sms);
         const int64_t n_items = (int64_t)nobs.size() * a.groups;
         const int sched_ctas = packed ? (int)std::min<int64_t>(avail_sms, (n_items + pt.sched_warps - 1) / pt.sched_warps) : avail_sms;
         std::vector<int32_t> begin, items;

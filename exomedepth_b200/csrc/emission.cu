@@ -114,6 +114,7 @@ void launch_emission_direct(CountsView c, const StateConst* consts, int n_sample
 // roundings (CNV_estimate.cpp:49); for k > 0 they can differ from them by one rounding of a sum of
 // magnitude a1+a2+n, i.e. by <= ~4e-12 absolute on cells whose |ll| is then > 1.
 constexpr int kTableThreads = 1024;
+constexpr int kPanelEntries = 20000;   // lattices with fewer entries in total are built by the shared-index-space scheme (kPanel)
 constexpr int kColdCap = 2048;      // out-of-lattice cells parked per work item before they are drained
 
 size_t emission_table_smem_bytes(TableDims d)
@@ -169,6 +170,10 @@ __device__ __noinline__ void whole_item_cold(const StateConst* sc, const CountsV
 // Work items (sample, state) are dealt through an atomic counter, not by block index: when the SMs are shared with
 // other kernels (the Viterbi sweep of another chromosome group) the CTAs that are resident take all the work.
 // `rg`: the bin ranges this launch covers (whole matrix, or the 16-bin aligned ranges of one chromosome group).
+// kPanel: small lattices for panels of a few thousand bins (many items, few bins each): the K + R + N entries are one
+// index space shared evenly by ALL threads — one anchor + ~8 recurrence steps per thread — instead of one run per lattice
+// and thread, whose anchors (a full lgamma difference each) would dominate a 9 K-entry build.
+template <bool kPanel>
 __global__ void __launch_bounds__(kTableThreads, 1)
 emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n_states, int n_items,
                       const __grid_constant__ BinRanges rg, TableDims dims, LLView out, unsigned* __restrict__ flags,
@@ -237,9 +242,35 @@ emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n
                     G[i] = __dadd_rn(s, comp);
                 }
             };
-            build(G1, dims.K, g1, [&](int i) { return __dadd_rn(a1, (double)i); });
-            build(G2, dims.R, g2, [&](int i) { return __dadd_rn(a2, (double)i); });
-            build(G3, dims.N, g12, [&](int i) { return __dadd_rn(a1, __dadd_rn(a2, (double)i)); });
+            if constexpr (!kPanel) {
+                build(G1, dims.K, g1, [&](int i) { return __dadd_rn(a1, (double)i); });
+                build(G2, dims.R, g2, [&](int i) { return __dadd_rn(a2, (double)i); });
+                build(G3, dims.N, g12, [&](int i) { return __dadd_rn(a1, __dadd_rn(a2, (double)i)); });
+            } else {
+                const int KR = dims.K + dims.R;
+                const int per = (n_lat + (int)blockDim.x - 1) / (int)blockDim.x;
+                int i = threadIdx.x * per;
+                const int end = min(i + per, n_lat);
+                double x = 0.0, s = 0.0, comp = 0.0;
+                for (bool first = true; i < end; ++i, first = false) {
+                    // entry i of [G1 | G2 | G3]: its lattice's constants and its argument, rounded as the gather expects
+                    const GConst& g = i < dims.K ? scp->g1 : i < KR ? scp->g2 : scp->g12;
+                    const double xn = i < dims.K ? __dadd_rn(a1, (double)i)
+                                      : i < KR   ? __dadd_rn(a2, (double)(i - dims.K))
+                                                 : __dadd_rn(a1, __dadd_rn(a2, (double)(i - KR)));
+                    if (!first && i != dims.K && i != KR && __dadd_rn(xn, -x) == 1.0) {
+                        const double t = log(x);
+                        const double u = __dadd_rn(s, t), bp = __dadd_rn(u, -s);
+                        comp = __dadd_rn(comp, __dadd_rn(__dadd_rn(s, -__dadd_rn(u, -bp)), __dadd_rn(t, -bp)));
+                        s = u;
+                    } else {                                    // run start, lattice boundary, or a rounding step != 1
+                        s = gdiff(g, xn);
+                        comp = 0.0;
+                    }
+                    x = xn;
+                    G1[i] = __dadd_rn(s, comp);
+                }
+            }
         }
         __syncthreads();
         if (lattice_mode == 1)
@@ -322,13 +353,22 @@ void launch_emission_table(CountsView c, const StateConst* consts, int n_samples
     if (n_items == 0 || rg.n == 0) return;
     cudaMemsetAsync(queue, 0, sizeof(int), st);
     const size_t smem = emission_table_smem_bytes(dims);
+    const int grid = n_items < n_sms ? n_items : n_sms;
+    if (dims.K + dims.R + dims.N < kPanelEntries) {
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaFuncSetAttribute(emission_table_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
+        }
+        emission_table_kernel<true><<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices, lattices ? lattice_mode : 0);
+        return;
+    }
     static size_t configured = 0;
     if (smem > configured) {
-        cudaFuncSetAttribute(emission_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(emission_table_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    const int grid = n_items < n_sms ? n_items : n_sms;
-    emission_table_kernel<<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices, lattices ? lattice_mode : 0);
+    emission_table_kernel<false><<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices, lattices ? lattice_mode : 0);
 }
 
 }  // namespace edb

@@ -33,9 +33,11 @@
 //            reference's call table, 32 tiles at a time;
 //   compact  concatenates the per-chromosome call tables per sample.
 #include <algorithm>
+#include <vector>
 
 #include <cuda.h>
 
+#include "host_tables.h"
 #include "kernels.cuh"
 
 namespace edb {
@@ -622,17 +624,26 @@ size_t viterbi_smem_bytes(int S, int W)
 {
     return (size_t)W * (ring_stages(S, W) * (stage_bytes(S) + 16) + 2 * (32 / S + 1) * lt_jstride(S) * 8);
 }
-// 4 or 8 sweep warps per CTA: whichever finishes the batch sooner under the measured per-step costs (see kTile comment)
+// 4 or 8 sweep warps per CTA: whichever finishes the batch sooner under the measured per-step costs (see kTile comment).
+// Work items are indivisible, so the finishing time is the busiest warp's load under the real placement
+// (viterbi_schedule), not the average load: 640 equal items on 592 warps take two rounds, on 1184 warps one.
 int viterbi_pick_warps(const int32_t* chain_nobs, int n_chains, int groups, int n_sms)
 {
-    int64_t total = 0, longest = 0;
-    for (int c = 0; c < n_chains; c++) {
-        total += (int64_t)chain_nobs[c] * groups;
-        if (chain_nobs[c] > longest) longest = chain_nobs[c];
+    if (n_chains < 1 || groups < 1 || n_sms < 1) return 4;
+    double t[2];
+    for (int v = 0; v < 2; v++) {
+        const int W = v ? 8 : 4;
+        std::vector<int32_t> begin, items;
+        viterbi_schedule(chain_nobs, n_chains, groups, n_sms, W, begin, items);
+        int64_t busiest = 0;
+        for (int s = 0; s + 1 < (int)begin.size(); s++) {
+            int64_t load = 0;
+            for (int q = begin[s]; q < begin[s + 1]; q++) load += chain_nobs[items[2 * q]];
+            if (load > busiest) busiest = load;
+        }
+        t[v] = (v ? 185.0 : 140.0) * (double)busiest;
     }
-    const double t4 = 140.0 * (double)std::max<int64_t>(longest, total / (4 * (int64_t)n_sms) + 1);
-    const double t8 = 185.0 * (double)std::max<int64_t>(longest, total / (8 * (int64_t)n_sms) + 1);
-    return t4 <= t8 ? 4 : 8;
+    return t[0] <= t[1] ? 4 : 8;
 }
 int viterbi_lt_pitch(int S) { return lt_pitch(S); }
 int viterbi_tile() { return kTile; }

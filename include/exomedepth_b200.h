@@ -138,10 +138,13 @@ typedef struct edb200_batch {
     double        *cor;             /* out double[n_samples]  cor(test, reference) over all bins              */
 } edb200_batch;
 
-/* mode: 0 = auto, 1 = force in-register evaluation, 2 = force shared-memory lattice */
+/* mode: 0 = auto (full lattice from 106,496 bins; panel lattice from 4,096 bins when samples x states >= 2 x SMs;
+ * in-register otherwise), 1 = force in-register evaluation, 2 = force the full shared-memory lattice,
+ * 3 = force the panel-sized lattice (cohort API only) */
 #define EDB200_EMISSION_AUTO   0
 #define EDB200_EMISSION_DIRECT 1
 #define EDB200_EMISSION_TABLE  2
+#define EDB200_EMISSION_PANEL  3
 
 /* All pointers in `b` are DEVICE pointers on the selected GPU; work is enqueued on `cuda_stream`
  * (a cudaStream_t, 0 = default stream) and NOT synchronised.  ll must be non-NULL (the Viterbi reads it).

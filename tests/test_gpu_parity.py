@@ -94,13 +94,13 @@ def test_kat4_exomecount_end_to_end(edb, refvec, exomecount, kat):
 
 # ------------------------------------------------------------------------------------------------ oracle, seeded inputs
 @pytest.mark.parametrize("S", [3, 5, 7])
-@pytest.mark.parametrize("mode", ["direct", "table"])
+@pytest.mark.parametrize("mode", ["direct", "table", "panel"])
 def test_cohort_vs_oracle(edb, port, S, mode):
     from exomedepth_b200 import _lib, synth
     d = synth.cohort(7, n_bins=9000)
     co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=S)
     res = co.run_host(d["observed"], d["reference"], d["phi"], d["expected"], call_cap=256,
-                      mode=_lib.EMISSION_DIRECT if mode == "direct" else _lib.EMISSION_TABLE)
+                      mode=dict(direct=_lib.EMISSION_DIRECT, table=_lib.EMISSION_TABLE, panel=_lib.EMISSION_PANEL)[mode])
     odds = port.state_odds(S)
     T = port.callcnvs_transitions(S, 1e-4)
     cols = framing.hmm_column_order(S)
@@ -168,6 +168,32 @@ def test_table_and_direct_paths_agree(edb):
     assert_ll_close(b, a, rtol=2e-11, atol=0)
     both_zero = np.broadcast_to(((d["observed"] == 0) & (d["reference"] == 0))[:, None, :], a.shape)
     assert np.all(a[both_zero] == 0.0)
+
+
+@pytest.mark.parametrize("n_bins,scale", [(9000, 1), (20000, 1), (9000, 12)])
+def test_panel_lattice_vs_oracle(edb, port, n_bins, scale):
+    """The panel-sized lattices (2048 + 2 x 4096 entries below 16,384 bins, 2048 + 2 x 8192 from there) against the oracle,
+    cell by cell; scale = 12 multiplies the counts so that most cells leave the lattice (more than the parking list holds:
+    the kernel walks the sample again and evaluates exactly those cells in registers)."""
+    from exomedepth_b200 import _lib, synth
+    d = synth.cohort(4, n_bins=n_bins)
+    obs, ref = d["observed"] * scale, d["reference"] * scale
+    if scale > 1:
+        assert np.mean(ref > 4096) > 0.4
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=5)
+    got = co.run_host(obs, ref, d["phi"], d["expected"], want_path=False, mode=_lib.EMISSION_PANEL)["ll"]
+    if scale == 1:                                                      # the oracle at the bench's count range
+        odds = port.state_odds(5)
+        for s in range(4):
+            assert_ll_close(got[s].T, port.emission(d["phi"][s], d["expected"][s], obs[s] + ref, obs[s], odds))
+    direct = co.run_host(obs, ref, d["phi"], d["expected"], want_path=False, mode=_lib.EMISSION_DIRECT)["ll"]
+    assert_ll_close(got, direct, rtol=2e-11, atol=0)
+    # pathological shape parameters: the whole (sample, state) goes cell by cell through the reference's semantics
+    phi = d["phi"].copy()
+    phi[1] = 0.93
+    a = co.run_host(obs, ref, phi, d["expected"], want_path=False, mode=_lib.EMISSION_PANEL)["ll"]
+    b = co.run_host(obs, ref, phi, d["expected"], want_path=False, mode=_lib.EMISSION_DIRECT)["ll"]
+    assert_ll_close(a, b, rtol=1e-9)                                    # incl. the NaN pattern
 
 
 def test_pathological_phi_nan_pattern(edb, port):
