@@ -358,9 +358,18 @@ void launch_emission_table(CountsView c, const StateConst* consts, int n_samples
         static size_t configured = 0;
         if (smem > configured) {
             cudaFuncSetAttribute(emission_table_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(emission_table_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             configured = smem;
         }
-        emission_table_kernel<true><<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices, lattices ? lattice_mode : 0);
+        // A panel item is a chain of latency-bound phases (anchor + recurrence build, one or two gather passes, a handful
+        // of out-of-lattice cells evaluated in registers): when two CTAs fit an SM's shared memory (228 KB, 1 KB reserved
+        // per CTA) they run with 512 threads each — 64 registers per thread either way — and one CTA's build overlaps the
+        // other's gathers.
+        const bool two = 2 * (smem + 1024) <= 228 * 1024;
+        const int threads = two ? kTableThreads / 2 : kTableThreads;
+        const int ctas = two ? 2 * n_sms : n_sms;
+        emission_table_kernel<true><<<n_items < ctas ? n_items : ctas, threads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices,
+                                                                                          lattices ? lattice_mode : 0);
         return;
     }
     static size_t configured = 0;
