@@ -925,6 +925,19 @@ static int viterbi_prepare(edb200_cohort* c, const edb200_batch* b, edb::Viterbi
     return 0;
 }
 
+// Sweep warps per CTA of the pass that carries the longest chains (`packed` = 1 below): 4 = one per SM sub-partition.
+// EDB200_CRIT_WARPS = 1 or 2 (experiment, unmeasured): fewer warps share an SM's shared-memory pipe — four warps keep it
+// busy for 118 of a step's 160 cycles (DESIGN.md "what comes next" 4b) — at the price of more SMs taken from the other pass.
+static int crit_warps()
+{
+    static const int w = [] {
+        const char* e = getenv("EDB200_CRIT_WARPS");
+        const int v = e ? atoi(e) : 4;
+        return v == 1 || v == 2 ? v : 4;
+    }();
+    return w;
+}
+
 // sweep, tilemap, trace, expand of one part on `st`; the schedule is rebuilt when the number of sample groups changes
 // `packed` > 0: the sweep shares the GPU with the emission kernel of the next part (a sweep CTA owns its SM's shared
 // memory, so does an emission CTA): its CTAs are filled instead of spread over all SMs — 1: one warp per SM
@@ -937,7 +950,7 @@ static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiA
         std::vector<int32_t> nobs(pt.chains.size());
         for (size_t i = 0; i < pt.chains.size(); i++) nobs[i] = c->chains_h[pt.chains[i]].nobs;
         const char* force = getenv("EDB200_SWEEP_WARPS");          // experiments: 4 or 8
-        pt.sched_warps = force ? (atoi(force) == 8 ? 8 : 4) : packed == 1 ? 4 : packed == 2 ? 8 : edb::viterbi_pick_warps(nobs.data(), (int)nobs.size(), a.groups, avail_sms);
+        pt.sched_warps = force ? (atoi(force) == 8 ? 8 : 4) : packed == 1 ? crit_warps() : packed == 2 ? 8 : edb::viterbi_pick_warps(nobs.data(), (int)nobs.size(), a.groups, avail_sms);
         const int64_t n_items = (int64_t)nobs.size() * a.groups;
         const int sched_ctas = packed ? (int)std::min<int64_t>(avail_sms, (n_items + pt.sched_warps - 1) / pt.sched_warps) : avail_sms;
         std::vector<int32_t> begin, items;
@@ -1032,7 +1045,7 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
                 // {all others} on the rest — leave only the longest chains' own post-processing behind the critical sweep.
                 std::vector<edb200_cohort::Part>& vp = c->plans[0];
                 const int64_t items0 = (int64_t)vp[0].chains.size() * va.groups;
-                const int ctas0 = (int)std::min<int64_t>(g.n_sms / 2, (items0 + 3) / 4);
+                const int ctas0 = (int)std::min<int64_t>(g.n_sms / 2, (items0 + crit_warps() - 1) / crit_warps());
                 CU(cudaEventRecord(g.ev_fork, st));
                 for (int p = 0; p < 2; p++) {
                     if (vp[p].chains.empty()) continue;
@@ -1055,7 +1068,7 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
             CU(cudaStreamWaitEvent(g.s_vit[p], g.ev_em[p], 0));
             // first part: one warp per sub-partition on SMs of its own; later parts spread over the others
             const int64_t items0 = (int64_t)plan[0].chains.size() * va.groups;
-            const int ctas0 = (int)std::min<int64_t>(g.n_sms / 2, (items0 + 3) / 4);
+            const int ctas0 = (int)std::min<int64_t>(g.n_sms / 2, (items0 + crit_warps() - 1) / crit_warps());
             if (int rc = viterbi_part(c, plan[p], va, p == 0 ? 1 : 0, g.s_vit[p], p == 0 ? ctas0 : g.n_sms - ctas0)) return rc;
             CU(cudaEventRecord(g.ev_vit[p], g.s_vit[p]));
         }

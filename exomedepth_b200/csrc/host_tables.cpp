@@ -104,7 +104,9 @@ void nan_to_neg_inf(double* v, size_t n)
 void viterbi_schedule(const int32_t* chain_nobs, int n_chains, int groups, int n_ctas, int warps_per_cta,
                       std::vector<int32_t>& begin, std::vector<int32_t>& items)
 {
-    const int n_slots = n_ctas * warps_per_cta, n_parts = n_ctas * 4;
+    // sub-partitions that hold sweep warps: 4 per CTA (warp slots w and w + 4 share one), fewer when the CTA has < 4 warps
+    const int subs = warps_per_cta < 4 ? warps_per_cta : 4;
+    const int n_slots = n_ctas * warps_per_cta, n_parts = n_ctas * subs;
     std::vector<int> order(n_chains);
     for (int c = 0; c < n_chains; c++) order[c] = c;
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return chain_nobs[x] > chain_nobs[y]; });
@@ -119,9 +121,9 @@ void viterbi_schedule(const int32_t* chain_nobs, int n_chains, int groups, int n
         for (int g = 0; g < groups; g++) {
             Key k = heap.top();
             heap.pop();
-            const int p = k.second, cta = p / 4, sub = p % 4;
+            const int p = k.second, cta = p / subs, sub = p % subs;
             int best = -1;
-            for (int w = sub; w < warps_per_cta; w += 4) {
+            for (int w = sub; w < warps_per_cta; w += subs) {
                 const int s = cta * warps_per_cta + w;
                 if (best < 0 || slot_load[s] < slot_load[best]) best = s;
             }

@@ -670,8 +670,12 @@ static void launch_all(const ViterbiArgs& a, cudaStream_t st)
 {
     constexpr int G = 32 / S;
     prof_mark("viterbi_sweep", st);
-    if (a.warps_per_cta == 4) launch_sweep<S, 4>(a, st);
-    else launch_sweep<S, 8>(a, st);
+    switch (a.warps_per_cta) {
+        case 1: launch_sweep<S, 1>(a, st); break;          // 1, 2: experiments (EDB200_CRIT_WARPS), see DESIGN.md "what comes next"
+        case 2: launch_sweep<S, 2>(a, st); break;
+        case 4: launch_sweep<S, 4>(a, st); break;
+        default: launch_sweep<S, 8>(a, st); break;
+    }
     prof_mark("viterbi_tilemap", st);
     const int64_t map_threads = (int64_t)a.max_list_tiles * a.groups * G;
     if (map_threads > 0) viterbi_tilemap_kernel<S><<<dim3((unsigned)((map_threads + 255) / 256), (unsigned)a.n_list), 256, 0, st>>>(a);

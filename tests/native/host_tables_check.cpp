@@ -1,0 +1,111 @@
+// CPU check of the host-side shared metadata (exomedepth_b200/csrc/host_tables.cpp), compiled and run by
+// tests/test_host_tables.py: the sweep placement for every CTA shape, the CallCNVs transition matrix
+// (R/class_definition.R:343-347), the position framing (:368) and the log-transition rows against a direct
+// evaluation of src/hmm.cpp:62-79.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <set>
+#include <utility>
+#include <vector>
+
+#include "host_tables.h"
+
+static int fails = 0;
+#define CHECK(c)                                                        \
+    do {                                                                \
+        if (!(c)) { printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); fails++; } \
+    } while (0)
+
+static void check_schedule(const std::vector<int32_t>& nobs, int groups, int n_ctas, int W)
+{
+    std::vector<int32_t> begin, items;
+    edb::viterbi_schedule(nobs.data(), (int)nobs.size(), groups, n_ctas, W, begin, items);
+    const int n_slots = n_ctas * W;
+    CHECK((int)begin.size() == n_slots + 1);
+    CHECK(begin[0] == 0 && begin[n_slots] == (int)nobs.size() * groups);
+    CHECK(items.size() == (size_t)2 * nobs.size() * groups);
+    std::set<std::pair<int, int>> seen;
+    int64_t busiest = 0, total = 0, longest = 0;
+    for (int s = 0; s < n_slots; s++) {
+        CHECK(begin[s] <= begin[s + 1]);
+        int64_t load = 0;
+        for (int q = begin[s]; q < begin[s + 1]; q++) {
+            const int c = items[2 * q], g = items[2 * q + 1];
+            CHECK(c >= 0 && c < (int)nobs.size() && g >= 0 && g < groups);
+            CHECK(seen.insert({c, g}).second);             // every work item exactly once
+            load += nobs[c];
+        }
+        if (load > busiest) busiest = load;
+        total += load;
+    }
+    for (int32_t n : nobs) if (n > longest) longest = n;
+    CHECK(seen.size() == nobs.size() * (size_t)groups);
+    // greedy placement on the least loaded sub-partition, then on its less loaded warp: no warp carries more than the
+    // mean load plus two work items
+    CHECK((double)busiest <= (double)total / n_slots + 2.0 * (double)longest);
+    // the longest work items sit alone on their sub-partition whenever there are at least as many sub-partitions as items
+    if ((int64_t)nobs.size() * groups <= (int64_t)n_ctas * (W < 4 ? W : 4)) CHECK(busiest == longest);
+}
+
+int main()
+{
+    // ---- placement -------------------------------------------------------------------------------------
+    const std::vector<int32_t> genome = {19803, 14662, 11433, 11265, 11138, 10912, 10693, 9535, 8919, 8493, 8245, 7930,
+                                         7786, 7623, 7476, 6969, 6658, 6490, 6179, 4743, 4167, 3393, 2959, 1984, 595};
+    for (int W : {1, 2, 4, 8})
+        for (int n_ctas : {1, 11, 137, 148})
+            for (int groups : {1, 8, 43, 334}) check_schedule(genome, groups, n_ctas, W);
+    for (int W : {1, 2, 4, 8}) check_schedule(std::vector<int32_t>(5, 1002), 128, 148, W);      // the small panel
+    check_schedule({7}, 1, 1, 4);
+    // ---- CallCNVs transition matrix, column-major T[k + S*j] = P(k -> j) ---------------------------------
+    for (int S : {3, 5, 7}) {
+        std::vector<double> T(S * S);
+        const double tp = 1e-4;
+        edb::callcnvs_transitions(S, tp, T.data());
+        for (int k = 0; k < S; k++) {
+            double row = 0;
+            for (int j = 0; j < S; j++) row += T[k + S * j];
+            CHECK(std::fabs(row - 1.0) < 1e-15);
+        }
+        CHECK(T[0] == 1 - tp);
+        for (int j = 1; j < S; j++) {
+            CHECK(T[0 + S * j] == tp / (S - 1));
+            CHECK(T[j + S * 0] == 0.5 && T[j + S * j] == 0.5);
+        }
+    }
+    // ---- framing: as.integer(c(start[1] - 2 L, start, end[last] + 2 L)) ------------------------------------
+    {
+        const int32_t start[3] = {12012, 13000, 12990}, end[3] = {12057, 13100, 13200};
+        int32_t pos[5];
+        CHECK(edb::frame_positions(3, start, end, 50000.0, pos) == 0);
+        CHECK(pos[0] == 12012 - 100000 && pos[1] == 12012 && pos[2] == 13000 && pos[3] == 12990 && pos[4] == 13200 + 100000);
+        const int32_t far_end[1] = {2147483000};
+        CHECK(edb::frame_positions(1, start, far_end, 50000.0, pos) != 0);                      // R would give NA
+    }
+    // ---- log-transition rows against hmm.cpp:62-79 evaluated directly -------------------------------------
+    for (int S : {3, 5, 7}) {
+        std::vector<double> T(S * S);
+        edb::callcnvs_transitions(S, 1e-4, T.data());
+        const int32_t pos[6] = {-87988, 12012, 13000, 12990, 12990, 113200};                   // a negative and a zero gap
+        for (int pitch : {S * (S + (S & 1)), S * 10}) {
+            std::vector<double> lt(6 * pitch, -1.0);
+            edb::build_log_transition_rows(S, T.data(), pos, 6, 50000.0, lt.data(), pitch);
+            const int js = pitch / S;
+            for (int i = 1; i < 6; i++) {
+                const double d = std::exp(-(double(pos[i]) - double(pos[i - 1])) / 50000.0);
+                for (int j = 0; j < S; j++)
+                    for (int k = 0; k < js; k++) {
+                        const double got = lt[i * pitch + j * js + k];
+                        if (k >= S) { CHECK(got == 0.0); continue; }
+                        const double t0 = T[j * S];
+                        const double t = k == 0 ? t0 : d * T[j * S + k] + (1.0 - d) * t0;
+                        const double want = std::log(t);
+                        CHECK((got == want) || (got != got && want != want));                   // same bits, NaN where log(negative)
+                    }
+            }
+        }
+    }
+    if (!fails) printf("ok\n");
+    return fails ? 1 : 0;
+}

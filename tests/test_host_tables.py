@@ -1,0 +1,23 @@
+"""The native host-side logic (exomedepth_b200/csrc/host_tables.cpp: sweep placement, CallCNVs transition matrix,
+position framing, host-libm log-transition rows) checked on the CPU by a small C++ driver compiled here."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "exomedepth_b200", "csrc")
+
+
+def test_host_tables_native(tmp_path):
+    cxx = shutil.which("g++") or shutil.which("c++")
+    if not cxx:
+        pytest.skip("no C++ compiler")
+    exe = str(tmp_path / "host_tables_check")
+    # the flags of csrc/Makefile for this file: no FMA contraction, so log / exp arguments carry the reference's bits
+    subprocess.run([cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-pthread", "-I", CSRC,
+                    os.path.join(ROOT, "tests", "native", "host_tables_check.cpp"), os.path.join(CSRC, "host_tables.cpp"),
+                    "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
