@@ -106,6 +106,27 @@ int main()
             }
         }
     }
+    // ---- structure of the CallCNVs table (DESIGN.md "what comes next" 4b): per observation and destination state j the
+    // row holds at most three distinct values — k = 0, k = j, and one shared by every other source state
+    for (int S : {5, 7}) {
+        std::vector<double> T(S * S);
+        edb::callcnvs_transitions(S, 1e-4, T.data());
+        const int32_t pos[5] = {0, 100000, 101685, 101600, 151600};
+        const int pitch = S * (S == 7 ? 10 : S + (S & 1)), js = pitch / S;
+        std::vector<double> lt(5 * pitch, 0.0);
+        edb::build_log_transition_rows(S, T.data(), pos, 5, 50000.0, lt.data(), pitch);
+        auto same = [](double a, double b) { return a == b || (a != a && b != b); };
+        for (int i = 1; i < 5; i++)
+            for (int j = 0; j < S; j++) {
+                const double* row = &lt[i * pitch + j * js];
+                int other = -1;
+                for (int k = 1; k < S; k++) {
+                    if (k == j) continue;
+                    if (other < 0) other = k;
+                    CHECK(same(row[k], row[other]));
+                }
+            }
+    }
     if (!fails) printf("ok\n");
     return fails ? 1 : 0;
 }
