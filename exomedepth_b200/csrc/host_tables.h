@@ -4,7 +4,20 @@
 #include <cstdint>
 #include <vector>
 
+#ifdef __CUDACC__
+#define EDB_HD __host__ __device__
+#else
+#define EDB_HD
+#endif
+
 namespace edb {
+// transition row of destination state j: S doubles padded to an even count, so that rows are 16-byte aligned — and for
+// S = 7 to 10, not 8: lane (chain, j) reads row j with 128-bit loads, and rows 64 bytes apart put j = 0, 2, 4, 6 on the
+// same four banks (16 wavefronts per load instead of 4; the S = 7 sweep was shared-memory bound, 80 wavefronts per
+// warp-step, profiles/r1l_sweep_s7_summary.txt); 80 bytes apart the seven rows, and the four chains' exchange slots, fall
+// on distinct banks.  Strides of 4 (S = 3, 4) and 6 doubles (S = 5, 6) are conflict-free as they are.
+EDB_HD constexpr int lt_jstride(int S) { return S == 7 ? 10 : S + (S & 1); }
+EDB_HD constexpr int lt_pitch(int S) { return S * lt_jstride(S); }          // doubles per observation
 // CallCNVs transition matrix for `tp` (R/class_definition.R:343-347), column-major T[k + S*j] = P(k -> j)
 void callcnvs_transitions(int S, double tp, double* T);
 // lt[i*pitch + j*(pitch/S) + k] = log(t_{k->j} at observation i), i = 1..nobs-1 (src/hmm.cpp:62-79); row 0 and padding zeroed

@@ -49,13 +49,7 @@ constexpr int kTile = 16;          // observations per tile (one 128-byte line o
 // work than 4 warps per SM can turn over within the longest chromosome's chain (viterbi_pick_warps).
 constexpr int kEmBytes = 4096;     // emission tile: up to 32 rows x 128 bytes, 1024-byte aligned for the 128-byte swizzle
 
-// transition row of destination state j: S doubles padded to an even count, so that rows are 16-byte aligned — and for
-// S = 7 to 10, not 8: lane (chain, j) reads row j with 128-bit loads, and rows 64 bytes apart put j = 0, 2, 4, 6 on the
-// same four banks (16 wavefronts per load instead of 4; the S = 7 sweep was shared-memory bound, 80 wavefronts per
-// warp-step, profiles/r1l_sweep_s7_summary.txt); 80 bytes apart the seven rows, and the four chains' exchange slots, fall
-// on distinct banks.  Strides of 4 (S = 3, 4) and 6 doubles (S = 5, 6) are conflict-free as they are.
-__host__ __device__ constexpr int lt_jstride(int S) { return S == 7 ? 10 : S + (S & 1); }
-__host__ __device__ constexpr int lt_pitch(int S) { return S * lt_jstride(S); }          // doubles per observation
+// lt_jstride / lt_pitch (layout of a log-transition row): host_tables.h, shared with the host-side table builder
 // one ring stage of a sweep warp: [emission tile 4 KB][transition rows of the tile's 16 observations], 1 KB granular
 __host__ __device__ constexpr int stage_bytes(int S) { return (kEmBytes + kTile * lt_pitch(S) * 8 + 1023) / 1024 * 1024; }
 // ring depth: what fits in ~220 KB of shared memory per CTA, at most 6 stages

@@ -2,6 +2,7 @@
 // tests/test_host_tables.py: the sweep placement for every CTA shape, the CallCNVs transition matrix
 // (R/class_definition.R:343-347), the position framing (:368) and the log-transition rows against a direct
 // evaluation of src/hmm.cpp:62-79.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -48,8 +49,59 @@ static void check_schedule(const std::vector<int32_t>& nobs, int groups, int n_c
     if ((int64_t)nobs.size() * groups <= (int64_t)n_ctas * (W < 4 ? W : 4)) CHECK(busiest == longest);
 }
 
+// Shared-memory wavefronts of one warp-wide load under the bank model ncu confirmed on the S = 7 sweep
+// (profiles/r1l_sweep_s7_summary.txt: 16 per LDS.128 with rows 64 bytes apart): 32 banks of 4 bytes; a load of `width`
+// bytes per lane is served in phases of 128 / width lanes; within a phase, distinct words on one bank serialise and
+// equal addresses are a broadcast.
+static int wavefronts(const int* addr, int width)
+{
+    const int per_phase = 128 / width, words = width / 4;
+    int total = 0;
+    for (int l0 = 0; l0 < 32; l0 += per_phase) {
+        int worst = 0;
+        for (int bank = 0; bank < 32; bank++) {
+            std::set<int> distinct;
+            for (int l = l0; l < l0 + per_phase; l++)
+                for (int w = 0; w < words; w++)
+                    if ((addr[l] / 4 + w) % 32 == bank) distinct.insert(addr[l] / 4 + w);
+            if ((int)distinct.size() > worst) worst = (int)distinct.size();
+        }
+        total += worst;
+    }
+    return total;
+}
+
+// the sweep's two multi-lane read patterns (viterbi.cu: load_step, sweep_step): lane = (chain g, destination state j);
+// transition row j at j * stride doubles, the chain's exchanged V at g * stride doubles; 128-bit loads of the S values
+static void check_sweep_banks(int S, int stride, bool expect_clean)
+{
+    const int G = 32 / S;
+    int worst_lt = 0, worst_x = 0;
+    for (int q = 0; 2 * q + 1 < S; q++) {
+        int a_lt[32], a_x[32];
+        for (int lane = 0; lane < 32; lane++) {
+            int g = lane / S;
+            const int j = lane - g * S;
+            if (g >= G) g = G - 1;
+            a_lt[lane] = j * stride * 8 + 16 * q;
+            a_x[lane] = g * stride * 8 + 16 * q;
+        }
+        worst_lt = std::max(worst_lt, wavefronts(a_lt, 16));
+        worst_x = std::max(worst_x, wavefronts(a_x, 16));
+    }
+    if (expect_clean) {
+        CHECK(worst_lt == 4);                               // 4 phases, no conflict
+        CHECK(worst_x == 4);
+    } else {
+        CHECK(worst_lt == 16);                              // what ncu measured before the fix
+    }
+}
+
 int main()
 {
+    for (int S = 2; S <= 7; S++) check_sweep_banks(S, edb::lt_jstride(S), true);
+    check_sweep_banks(7, 8, false);
+    for (int S = 2; S <= 7; S++) CHECK(edb::lt_jstride(S) >= S && edb::lt_jstride(S) % 2 == 0 && edb::lt_pitch(S) == S * edb::lt_jstride(S));
     // ---- placement -------------------------------------------------------------------------------------
     const std::vector<int32_t> genome = {19803, 14662, 11433, 11265, 11138, 10912, 10693, 9535, 8919, 8493, 8245, 7930,
                                          7786, 7623, 7476, 6969, 6658, 6490, 6179, 4743, 4167, 3393, 2959, 1984, 595};
