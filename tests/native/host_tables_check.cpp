@@ -97,8 +97,44 @@ static void check_sweep_banks(int S, int stride, bool expect_clean)
     }
 }
 
+// the emission tile of a sweep warp: row r of the TMA box at r * 128 bytes, its 16-byte chunk c at c ^ (r & 7)
+// (128-byte swizzle); lane (g, j) reads observation q of row g * S + perm[j].  Returns wavefronts per observation for
+// (a) the 8-byte read per step the kernel does today, (b) a 16-byte read of two observations every other step.
+static void emission_tile_wavefronts(int S, double* per_step_now, double* per_step_paired)
+{
+    const int G = 32 / S, normal = S == 3 ? 1 : 2;
+    int perm[8], n = 1;
+    perm[0] = normal;
+    for (int s = 0; s < S; s++) if (s != normal) perm[n++] = s;
+    int now = 0, paired = 0;
+    for (int q = 0; q < 16; q++) {
+        int a8[32], a16[32];
+        for (int lane = 0; lane < 32; lane++) {
+            int g = lane / S;
+            const int j = lane - g * S;
+            if (g >= G) g = G - 1;
+            const int r = g * S + perm[j];
+            a8[lane] = (r * 128 + ((r & 7) << 4)) ^ (q << 3);
+            a16[lane] = (r * 128 + ((r & 7) << 4)) ^ ((q & ~1) << 3);
+        }
+        now += wavefronts(a8, 8);
+        if (!(q & 1)) paired += wavefronts(a16, 16);
+    }
+    *per_step_now = now / 16.0;
+    *per_step_paired = paired / 16.0;
+}
+
 int main()
 {
+    {
+        // DESIGN.md "what comes next" 4b: today's emission read costs ~5 wavefronts per step at S = 5 (2 would be ideal:
+        // rows r and r + 8 of a 16-lane phase share a bank pair); a paired 128-bit read would cost 3
+        double now = 0, paired = 0;
+        emission_tile_wavefronts(5, &now, &paired);
+        CHECK(now >= 4.0 && now <= 6.0);
+        CHECK(paired <= 3.0);
+        printf("emission tile read at S = 5: %.2f wavefronts per step now, %.2f with paired 128-bit reads\n", now, paired);
+    }
     for (int S = 2; S <= 7; S++) check_sweep_banks(S, edb::lt_jstride(S), true);
     check_sweep_banks(7, 8, false);
     for (int S = 2; S <= 7; S++) CHECK(edb::lt_jstride(S) >= S && edb::lt_jstride(S) % 2 == 0 && edb::lt_pitch(S) == S * edb::lt_jstride(S));
