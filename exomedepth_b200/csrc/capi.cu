@@ -1331,6 +1331,13 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         // its emission kernel runs on `st` while the likelihoods of chunk i drain on the second stream.
         const int n_chunks = (b->ll && ns >= 2 * kHostChunks) ? kHostChunks : 1;
         const int per = (ns + n_chunks - 1) / n_chunks;
+        // the emission kernel is chosen once for the call, from the whole batch: a (smaller) last chunk must not fall
+        // back to another kernel — a sample's likelihoods do not depend on its slot in the batch
+        int chunk_mode = emission_mode;
+        if (emission_mode == EDB200_EMISSION_AUTO && !use_table(c, emission_mode)) {
+            edb::TableDims unused{};
+            chunk_mode = panel_table(c, (int64_t)ns * S, emission_mode, &unused) ? EDB200_EMISSION_PANEL : EDB200_EMISSION_DIRECT;
+        }
         for (int k = 0, s0 = 0; s0 < ns; k++, s0 += per) {
             const int cnt = ns - s0 < per ? ns - s0 : per;
             CU(cudaMemcpy2DAsync((int32_t*)c->h_obs.p + (size_t)s0 * nb, nb * 4, b->observed + (size_t)s0 * b->obs_stride, b->obs_stride * 4,
@@ -1342,7 +1349,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
             e.phi = d.phi + s0;
             e.expected = d.expected + s0;
             e.ll = d.ll + (size_t)s0 * S * nbp;
-            if ((rc = edb200_cohort_run_device(c, &e, 1, emission_mode, st))) return rc;
+            if ((rc = edb200_cohort_run_device(c, &e, 1, chunk_mode, st))) return rc;
             if (b->ll) {
                 CU(cudaEventRecord(g.chunk_done[k], st));
                 CU(cudaStreamWaitEvent(g.stream2, g.chunk_done[k], 0));

@@ -644,3 +644,18 @@ def test_graph_replay_matches_stream_launches(edb, shape):
     with pytest.raises(_lib.EDB200Error, match="destroyed"):
         gr.launch()
     gr.close()
+
+
+def test_ragged_last_chunk_uses_the_same_emission_kernel(edb):
+    """The host call moves the samples through in 8 chunks when the likelihood matrix is wanted; the emission kernel is
+    chosen once from the whole batch (500 samples x 5 states: panel lattices), so the smaller last chunk (59 samples = 295
+    items, below the panel threshold on its own) must give the same bits as the first one."""
+    from exomedepth_b200 import synth
+    d = synth.cohort(20, n_bins=5000)
+    reps = 25
+    obs = np.tile(d["observed"], (reps, 1))
+    phi, ex = np.tile(d["phi"], reps), np.tile(d["expected"], reps)
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=5)
+    a = co.run_host(obs, d["reference"], phi, ex, call_cap=128)
+    for k in ("ll", "path", "ncalls"):
+        assert np.array_equal(a[k][:20], a[k][-20:], equal_nan=True) and np.array_equal(a[k][:20], a[k][240:260], equal_nan=True)
