@@ -927,7 +927,7 @@ static int viterbi_prepare(edb200_cohort* c, const edb200_batch* b, edb::Viterbi
 
 // Sweep warps per CTA of the pass that carries the longest chains (`packed` = 1 below): 4 = one per SM sub-partition.
 // EDB200_CRIT_WARPS = 1 or 2 (experiment, unmeasured): fewer warps share an SM's shared-memory pipe — four warps keep it
-// busy for 118 of a step's 160 cycles (DESIGN.md "what comes next" 4b) — at the price of more SMs taken from the other pass.
+// busy for 118 of a step's 160 cycles (DESIGN.md "what comes next" 1) — at the price of more SMs taken from the other pass.
 static int crit_warps()
 {
     static const int w = [] {

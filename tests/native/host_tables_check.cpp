@@ -127,7 +127,7 @@ static void emission_tile_wavefronts(int S, double* per_step_now, double* per_st
 int main()
 {
     {
-        // DESIGN.md "what comes next" 4b: today's emission read costs ~5 wavefronts per step at S = 5 (2 would be ideal:
+        // DESIGN.md "what comes next" 1b: today's emission read costs ~5 wavefronts per step at S = 5 (2 would be ideal:
         // rows r and r + 8 of a 16-lane phase share a bank pair); a paired 128-bit read would cost 3
         double now = 0, paired = 0;
         emission_tile_wavefronts(5, &now, &paired);
@@ -194,7 +194,7 @@ int main()
             }
         }
     }
-    // ---- structure of the CallCNVs table (DESIGN.md "what comes next" 4b): per observation and destination state j the
+    // ---- structure of the CallCNVs table (DESIGN.md "what comes next" 1): per observation and destination state j the
     // row holds at most three distinct values — k = 0, k = j, and one shared by every other source state
     for (int S : {5, 7}) {
         std::vector<double> T(S * S);
