@@ -13,6 +13,8 @@
 //                           three 8-byte shared-memory gathers + two FP64 adds per cell instead of
 //                           ~150 FP64 instructions.  HBM traffic is the algorithmic 4 + 8S bytes per
 //                           bin·sample (the count vector is re-read once per state, from L2).
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace edb {
@@ -173,7 +175,12 @@ __device__ __noinline__ void whole_item_cold(const StateConst* sc, const CountsV
 // kPanel: small lattices for panels of a few thousand bins (many items, few bins each): the K + R + N entries are one
 // index space shared evenly by ALL threads — one anchor + ~8 recurrence steps per thread — instead of one run per lattice
 // and thread, whose anchors (a full lgamma difference each) would dominate a 9 K-entry build.
-template <bool kPanel>
+// kWarpRows (experiment, EDB200_EMISSION_WARPROWS=1, unmeasured): a lane takes bins {2l, 2l+1} and {64+2l, 64+2l+1} of
+// its warp's 128-bin block instead of four consecutive bins, so that each 128-bit store instruction of a warp covers
+// 512 contiguous bytes.  With four consecutive bins per lane the two stores of an iteration each write HALF of every
+// 32-byte sector they touch: ncu counts 128 M store sectors per launch where 64 M carry the data
+// (profiles/r1i_ncu_full_summary.txt), on the L1 data pipe that bounds the kernel.
+template <bool kPanel, bool kWarpRows>
 __global__ void __launch_bounds__(kTableThreads, 1)
 emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n_states, int n_items,
                       const __grid_constant__ BinRanges rg, TableDims dims, LLView out, unsigned* __restrict__ flags,
@@ -300,6 +307,52 @@ emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n
             const int64_t r0 = rg.b0[q], r1 = rg.b1[q];
             const bool vec = ((reinterpret_cast<uintptr_t>(obs_row + r0) | reinterpret_cast<uintptr_t>(oth_row + r0)) & 15) == 0 &&
                              (reinterpret_cast<uintptr_t>(o + r0) & 15) == 0;
+            if constexpr (kWarpRows) {
+                const int64_t n128 = vec ? r0 + ((r1 - r0) & ~(int64_t)127) : r0;
+                const int64_t stride = (int64_t)blockDim.x * 4;
+                const int l2 = 2 * (int)(threadIdx.x & 31);
+                int64_t b = r0 + (int64_t)(threadIdx.x >> 5) * 128 + l2;          // this lane's first pair; the second is 64 bins on
+                int2 ka = make_int2(0, 0), kb = ka, oa = ka, ob = ka;
+                if (b - l2 < n128) {
+                    ka = __ldg(reinterpret_cast<const int2*>(obs_row + b));
+                    kb = __ldg(reinterpret_cast<const int2*>(obs_row + b + 64));
+                    oa = __ldg(reinterpret_cast<const int2*>(oth_row + b));
+                    ob = __ldg(reinterpret_cast<const int2*>(oth_row + b + 64));
+                }
+                for (; b - l2 < n128; b += stride) {
+                    int2 kan = make_int2(0, 0), kbn = kan, oan = kan, obn = kan;
+                    if (b - l2 + stride < n128) {
+                        kan = __ldg(reinterpret_cast<const int2*>(obs_row + b + stride));
+                        kbn = __ldg(reinterpret_cast<const int2*>(obs_row + b + stride + 64));
+                        oan = __ldg(reinterpret_cast<const int2*>(oth_row + b + stride));
+                        obn = __ldg(reinterpret_cast<const int2*>(oth_row + b + stride + 64));
+                    }
+                    bool i0, i1, i2, i3;
+                    double2 v0, v1;
+                    v0.x = cell(ka.x, oa.x, i0);
+                    v0.y = cell(ka.y, oa.y, i1);
+                    v1.x = cell(kb.x, ob.x, i2);
+                    v1.y = cell(kb.y, ob.y, i3);
+                    __stcs(reinterpret_cast<double2*>(o + b), v0);
+                    __stcs(reinterpret_cast<double2*>(o + b + 64), v1);
+                    if (!(i0 && i1 && i2 && i3)) {                        // rare
+                        if (!i0) park(b);
+                        if (!i1) park(b + 1);
+                        if (!i2) park(b + 64);
+                        if (!i3) park(b + 65);
+                    }
+                    ka = kan;
+                    kb = kbn;
+                    oa = oan;
+                    ob = obn;
+                }
+                for (int64_t bt = n128 + threadIdx.x; bt < r1; bt += blockDim.x) {
+                    bool in;
+                    o[bt] = cell(obs_row[bt], oth_row[bt], in);
+                    if (!in) park(bt);
+                }
+                continue;
+            }
             const int64_t n4 = vec ? r0 + ((r1 - r0) & ~(int64_t)3) : r0;
             // the counts of the next iteration are requested before the gathers of this one
             const int64_t stride = (int64_t)blockDim.x * 4;
@@ -357,8 +410,8 @@ void launch_emission_table(CountsView c, const StateConst* consts, int n_samples
     if (dims.K + dims.R + dims.N < kPanelEntries) {
         static size_t configured = 0;
         if (smem > configured) {
-            cudaFuncSetAttribute(emission_table_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(emission_table_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(emission_table_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(emission_table_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             configured = smem;
         }
         // A panel item is a chain of latency-bound phases (anchor + recurrence build, one or two gather passes, a handful
@@ -368,16 +421,21 @@ void launch_emission_table(CountsView c, const StateConst* consts, int n_samples
         const bool two = 2 * (smem + 1024) <= 228 * 1024;
         const int threads = two ? kTableThreads / 2 : kTableThreads;
         const int ctas = two ? 2 * n_sms : n_sms;
-        emission_table_kernel<true><<<n_items < ctas ? n_items : ctas, threads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices,
+        emission_table_kernel<true, false><<<n_items < ctas ? n_items : ctas, threads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices,
                                                                                           lattices ? lattice_mode : 0);
         return;
     }
     static size_t configured = 0;
     if (smem > configured) {
-        cudaFuncSetAttribute(emission_table_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(emission_table_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(emission_table_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    emission_table_kernel<false><<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices, lattices ? lattice_mode : 0);
+    static const bool warp_rows = getenv("EDB200_EMISSION_WARPROWS") && atoi(getenv("EDB200_EMISSION_WARPROWS")) == 1;   // experiment
+    if (warp_rows)
+        emission_table_kernel<false, true><<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices, lattices ? lattice_mode : 0);
+    else
+        emission_table_kernel<false, false><<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices, lattices ? lattice_mode : 0);
 }
 
 }  // namespace edb

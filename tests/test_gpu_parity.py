@@ -659,3 +659,41 @@ def test_ragged_last_chunk_uses_the_same_emission_kernel(edb):
     a = co.run_host(obs, d["reference"], phi, ex, call_cap=128)
     for k in ("ll", "path", "ncalls"):
         assert np.array_equal(a[k][:20], a[k][-20:]) and np.array_equal(a[k][:20], a[k][240:260])
+
+
+# ------------------------------------------------------------------------------------------------ experiment knobs
+_EXPERIMENT = '''
+import hashlib, sys
+import numpy as np
+import exomedepth_b200 as edb
+from exomedepth_b200 import _lib, synth
+edb.init()
+d = synth.cohort(6, n_bins=20000)
+co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=5)
+r = co.run_host(d["observed"], d["reference"], d["phi"], d["expected"], call_cap=512, mode=_lib.EMISSION_TABLE)
+h = hashlib.sha256()
+for k in ("ll", "path", "calls", "ncalls"):
+    h.update(np.ascontiguousarray(r[k]).tobytes())
+print(h.hexdigest())
+'''
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("EDB200_TEST_EXPERIMENTS"),
+                    reason="experiment knobs (built, not yet measured: DESIGN.md section 9); set EDB200_TEST_EXPERIMENTS=1 to run")
+@pytest.mark.parametrize("knob", ["EDB200_EMISSION_WARPROWS=1", "EDB200_CRIT_WARPS=2", "EDB200_CRIT_WARPS=1"])
+def test_experiment_knobs_do_not_change_results(edb, knob):
+    """The knobs only re-map work (bins to lanes, sweep warps to CTAs): every output must be bit-identical to the default's.
+    The knobs are read once per process, hence the subprocesses."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def run(extra):
+        env = dict(os.environ, PYTHONPATH=root, **extra)
+        out = subprocess.run([sys.executable, "-c", _EXPERIMENT], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return out.stdout.strip().splitlines()[-1]
+
+    name, value = knob.split("=")
+    assert run({name: value}) == run({})
