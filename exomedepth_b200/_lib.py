@@ -13,11 +13,13 @@ LIB_PATH = os.environ.get("EDB200_LIB") or os.path.join(_HERE, "libexomedepth_b2
 OK, WARN_NAN, ERR_NSTATES, ERR_CUDA, ERR_ARG, WARN_CALLCAP = 0, 1, 2, 4, 8, 16
 MAX_STATES = 7
 EMISSION_AUTO, EMISSION_DIRECT, EMISSION_TABLE, EMISSION_PANEL = 0, 1, 2, 3
+OPTIONS = dict(sweep=1, parts=2, vsplit=3, crit_warps=4, sweep_warps=5, packplan=6)      # EDB200_OPT_*
+SWEEP_AUTO, SWEEP_LANE_PER_STATE, SWEEP_THREAD_PER_CHAIN = 0, 1, 2
 
 EXPORTS = (
     "edb200_init", "edb200_shutdown", "edb200_last_error", "edb200_device_info", "edb200_launch_count",
     "edb200_host_alloc", "edb200_host_free", "edb200_get_loglike_matrix", "edb200_emission", "edb200_hmm",
-    "edb200_cohort_create", "edb200_cohort_destroy", "edb200_cohort_table", "edb200_cohort_table_copy",
+    "edb200_cohort_create", "edb200_cohort_destroy", "edb200_cohort_set_option", "edb200_cohort_table", "edb200_cohort_table_copy",
     "edb200_cohort_run_device", "edb200_cohort_capture_device", "edb200_graph_launch", "edb200_graph_destroy",
     "edb200_cohort_run_host", "edb200_status", "edb200_profile", "edb200_profile_read",
     "edb200_cohort_forward_device", "edb200_cohort_forward_last",
@@ -81,6 +83,8 @@ def load():
     L.edb200_cohort_create.argtypes = [C.POINTER(CohortSpec), C.POINTER(vp)]
     L.edb200_cohort_destroy.restype = None
     L.edb200_cohort_destroy.argtypes = [vp]
+    L.edb200_cohort_set_option.restype = C.c_int
+    L.edb200_cohort_set_option.argtypes = [vp, C.c_int, C.c_int]
     L.edb200_cohort_table.restype = C.c_int
     L.edb200_cohort_table.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.edb200_cohort_table_copy.restype = C.c_int
@@ -157,7 +161,7 @@ def launch_count(reset=False):
 
 def profile(enable):
     """Bracket every kernel launch with CUDA events on its stream (bench.py's per-kernel roofline)."""
-    check(load().edb200_profile(1 if enable else 0), "edb200_profile")
+    check(load().edb200_profile(int(enable)), "edb200_profile")      # 2: also print the launch timeline on read
 
 
 def profile_read():

@@ -68,6 +68,12 @@ class Cohort:
         except Exception:
             pass
 
+    def set_option(self, name, value):
+        """Execution options (include/exomedepth_b200.h, EDB200_OPT_*): 'sweep' (0 auto, 1 lane per state, 2 thread per
+        chain), 'parts', 'vsplit', 'crit_warps', 'sweep_warps', 'packplan'.  Results never depend on them."""
+        _lib.check(self.lib.edb200_cohort_set_option(self.handle, _lib.OPTIONS[name], int(value)), "edb200_cohort_set_option")
+        return self
+
     # ---- shared metadata ------------------------------------------------------------------------
     def table_bytes(self):
         p, n = C.c_void_p(), C.c_size_t()

@@ -57,6 +57,7 @@ struct EventTimer : edb::KernelTimer {
     std::vector<cudaEvent_t> pool;
     struct Open { cudaStream_t st; std::string name; cudaEvent_t ev; };
     std::vector<Open> open;           // one open interval per stream (the group pipeline launches on several)
+    bool print_timeline = false;
     cudaEvent_t get()
     {
         if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
@@ -85,7 +86,7 @@ struct EventTimer : edb::KernelTimer {
         std::vector<std::string> names;
         std::vector<double> total, longest;
         std::vector<int> count;
-        const bool timeline = getenv("EDB200_TIMELINE") != nullptr;      // development aid: start / duration of every launch
+        const bool timeline = print_timeline;                            // edb200_profile(2): start / duration of every launch
         for (auto& iv : done) {
             float ms = 0;
             cudaEventElapsedTime(&ms, iv.e0, iv.e1);
@@ -178,7 +179,7 @@ struct CallScratch {
 // CUtensorMap of an emission matrix for the Viterbi sweep's 2-D TMA loads: rows = (sample, state) pairs of `cols`
 // doubles (row pitch `pitch` doubles), box = 16 bins x (32/S)*S rows, 128-byte swizzle, zero fill out of bounds.
 // cuTensorMapEncodeTiled is fetched through the runtime (no link-time dependency on libcuda).
-int make_ll_map(const double* ll, int64_t rows, int64_t cols, int64_t pitch, int S, CUtensorMap* out)
+int make_ll_map(const double* ll, int64_t rows, int64_t cols, int64_t pitch, int box_rows, CUtensorMap* out)
 {
     typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -192,7 +193,7 @@ int make_ll_map(const double* ll, int64_t rows, int64_t cols, int64_t pitch, int
     }
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)pitch * 8};
-    const cuuint32_t box[2] = {16, (cuuint32_t)((32 / S) * S)};
+    const cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ll), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -239,7 +240,16 @@ struct edb200_cohort {
     std::vector<edb::ChainDesc> chains_h;
     int64_t total_tiles = 0;
     int lt_pitch = 0;
-    DevBuf chains, lt, odds_d, tile_base, decay;
+    DevBuf chains, lt, odds_d, tile_base, decay, srows;
+    // CallCNVs-structured view of the table for the one-thread-per-chain sweep (built lazily from the device table, so
+    // that ranks that received the table by broadcast get it too): 0 = not examined, 1 = structured, -1 = arbitrary matrix
+    int struct_state = 0;
+    double c0 = 0, c1 = 0;
+    // edb200_cohort_set_option
+    int opt_sweep = 0;                   // 0 auto, 1 one lane per (chain, state), 2 one thread per chain
+    int opt_parts = 0;                   // chromosome groups of a pipelined batch (0 auto)
+    int opt_vsplit = -1;                 // device-resident Viterbi as two concurrent passes (-1 auto)
+    int opt_crit_warps = 0, opt_sweep_warps = 0, opt_packplan = 0;
     // Chromosome groups ("parts"): the chains are split by length so that the emission of the long chromosomes can
     // finish — and their sweeps, the critical path, can start — while the rest is still being computed (or uploaded).
     struct Part {
@@ -392,6 +402,7 @@ int edb200_profile(int enable)
     cudaDeviceSynchronize();
     g_event_timer.done.clear();
     g_event_timer.open.clear();
+    g_event_timer.print_timeline = enable == 2;
     edb::g_timer = enable ? &g_event_timer : nullptr;
     return 0;
 }
@@ -582,7 +593,7 @@ int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const d
     a.ll_sample_stride = 0;
     a.ll_state_stride = nobs_p;
     alignas(64) CUtensorMap ll_map;
-    if (int rc = make_ll_map(a.ll, S, nobs_p, nobs_p, S, &ll_map)) return rc;
+    if (int rc = make_ll_map(a.ll, S, nobs_p, nobs_p, (32 / S) * S, &ll_map)) return rc;
     a.ll_map = &ll_map;
     for (int j = 0; j < S; j++) a.perm[j] = j;
     if (int rc = upload_schedule(std::vector<int32_t>{nobs}, 1, 1, 4, cs.sched_begin, cs.sched_items, st)) return rc;
@@ -730,7 +741,7 @@ void edb200_cohort_destroy(edb200_cohort* c)
             release(part.sched_begin);
             release(part.sched_items);
         }
-    DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->tile_base, &c->decay, &c->fw_grid, &c->fw_chain, &c->fw_out, &c->fw_best, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->lattices,
+    DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->tile_base, &c->decay, &c->srows, &c->fw_grid, &c->fw_chain, &c->fw_out, &c->fw_best, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->lattices,
                      &c->h_obs, &c->h_ref, &c->h_phi, &c->h_exp, &c->h_ll, &c->h_path, &c->h_calls, &c->h_ncalls, &c->h_stats, &c->h_cor};
     for (DevBuf* b : all) release(*b);
     delete c;
@@ -749,7 +760,53 @@ int edb200_cohort_table_copy(edb200_cohort* c, void* device_buf, int direction, 
     if (!c || !device_buf) return fail(EDB200_ERR_ARG, "null argument");
     const size_t bytes = ((size_t)c->total_rows + edb::viterbi_tile()) * c->lt_pitch * 8;
     if (direction == 0) CU(cudaMemcpyAsync(device_buf, c->lt.p, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
-    else CU(cudaMemcpyAsync(c->lt.p, device_buf, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
+    else {
+        CU(cudaMemcpyAsync(c->lt.p, device_buf, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
+        c->struct_state = 0;                        // the structured view follows the table
+    }
+    return 0;
+}
+
+int edb200_cohort_set_option(edb200_cohort* c, int option, int value)
+{
+    if (!c) return fail(EDB200_ERR_ARG, "null cohort");
+    std::lock_guard<std::mutex> lk(g_mu);
+    switch (option) {
+        case EDB200_OPT_SWEEP:
+            if (value < 0 || value > 2) return fail(EDB200_ERR_ARG, "EDB200_OPT_SWEEP: 0 auto, 1 lane per state, 2 thread per chain");
+            c->opt_sweep = value;
+            break;
+        case EDB200_OPT_PARTS:
+            if (value < 0 || value > Context::kMaxParts) return fail(EDB200_ERR_ARG, "EDB200_OPT_PARTS: 0 (auto) .. %d", Context::kMaxParts);
+            c->opt_parts = value;
+            break;
+        case EDB200_OPT_VSPLIT: c->opt_vsplit = value < 0 ? -1 : value != 0; break;
+        case EDB200_OPT_CRIT_WARPS: c->opt_crit_warps = value; break;
+        case EDB200_OPT_SWEEP_WARPS: c->opt_sweep_warps = value; break;
+        case EDB200_OPT_PACKPLAN: c->opt_packplan = value; break;
+        default: return fail(EDB200_ERR_ARG, "unknown option %d", option);
+    }
+    for (auto& plan : c->plans)
+        for (auto& part : plan) part.sched_groups = 0;      // schedules are rebuilt under the new options
+    return 0;
+}
+
+// The structured view of the log-transition table (host_tables.h: build_struct_rows), from the DEVICE copy so that a
+// rank that received the table by broadcast sees the same rows.  Once per cohort (and per table copy).
+static int ensure_struct(edb200_cohort* c)
+{
+    if (c->struct_state != 0) return 0;
+    const int S = c->S;
+    c->struct_state = -1;
+    if (S != 3 && S != 5 && S != 7) return 0;
+    const size_t n_rows = (size_t)c->total_rows + edb::viterbi_tile();
+    std::vector<double> lt(n_rows * c->lt_pitch);
+    CU(cudaMemcpy(lt.data(), c->lt.p, lt.size() * 8, cudaMemcpyDeviceToHost));
+    std::vector<edb::StructRow> rows(n_rows);
+    if (!edb::build_struct_rows(S, lt.data(), c->lt_pitch, (int64_t)n_rows, rows.data(), &c->c0, &c->c1)) return 0;
+    if (int rc = ensure(c->srows, n_rows * sizeof(edb::StructRow))) return rc;
+    CU(cudaMemcpy(c->srows.p, rows.data(), n_rows * sizeof(edb::StructRow), cudaMemcpyHostToDevice));
+    c->struct_state = 1;
     return 0;
 }
 
@@ -774,14 +831,6 @@ static int build_plan(edb200_cohort* c, int n_parts)
         plan.resize(n_parts);
         double cuts[Context::kMaxParts];
         for (int p = 0; p < n_parts; p++) cuts[p] = kCuts[n_parts][p];
-        if (const char* e = getenv("EDB200_CUTS")) {                 // experiments: "0.1,0.3,1.0"
-            int p = 0;
-            for (const char* q = e; *q && p < n_parts; p++) {
-                cuts[p] = atof(q);
-                while (*q && *q != ',') q++;
-                if (*q) q++;
-            }
-        }
         int64_t cum = 0;
         int part = 0;
         for (int oc = 0; oc < c->n_chains; oc++) {
@@ -839,7 +888,7 @@ static bool panel_table(const edb200_cohort* c, int64_t n_items, int mode, edb::
 // how many chromosome groups a batch is pipelined over (1 = emission, then Viterbi, on the caller's stream)
 static int pick_parts(const edb200_cohort* c, int mode, int wanted)
 {
-    if (const char* e = getenv("EDB200_PARTS")) wanted = atoi(e);
+    if (c->opt_parts > 0) wanted = c->opt_parts;
     if (!use_table(c, mode) || c->n_chains < 2 * wanted) return 1;      // small panels: launch-bound, nothing to overlap
     return wanted < 1 ? 1 : wanted > Context::kMaxParts ? Context::kMaxParts : wanted;
 }
@@ -884,8 +933,32 @@ static int state_setup(edb200_cohort* c, const edb200_batch* b, cudaStream_t st)
 }
 
 // scratch + arguments shared by every part of a Viterbi pass over batch b
+// Which sweep kernel: both are exact; they differ in what bounds them (DESIGN.md "Viterbi").  One lane per (chain, state)
+// steps in ~150 cycles but a warp carries only 32/S chains; one thread per chain steps in ~205 cycles and a warp carries 32.
+// The pass ends when the longest chain does, or when the warps have turned over all chain-steps: whichever kernel's larger
+// bound is smaller wins (256 samples x 200k bins: lane per state, 1.5 vs 2.0 ms; 2,000 samples: thread per chain, 14.5 vs 2.6 ms).
+static bool use_tpc(const edb200_cohort* c, int n_samples)
+{
+    if (c->struct_state != 1 || c->opt_sweep == 1) return false;
+    if (c->opt_sweep == 2) return true;
+    const int S = c->S, G = 32 / S;
+    int64_t longest = 0, total = 0;
+    for (const auto& cd : c->chains_h) {
+        longest = std::max<int64_t>(longest, cd.nobs);
+        total += cd.nobs;
+    }
+    const double slots = 4.0 * g.n_sms;                  // one sweep warp per SM sub-partition
+    const double lane = std::max(150.0 * longest, 165.0 * total * ((n_samples + G - 1) / G) / slots);
+    const double tpc = std::max(205.0 * longest, 205.0 * total * ((n_samples + 31) / 32) / slots);
+    return tpc < lane;
+}
+
+// ll_map: two tensor maps (lane-per-state box, thread-per-chain box)
 static int viterbi_prepare(edb200_cohort* c, const edb200_batch* b, edb::ViterbiArgs& a, CUtensorMap* ll_map)
 {
+    if (int rc = ensure_struct(c)) return rc;
+    if (c->opt_sweep == 2 && c->struct_state != 1)
+        return fail(EDB200_ERR_ARG, "EDB200_OPT_SWEEP = 2 needs 3, 5 or 7 states and the CallCNVs transition structure");
     const int S = c->S, ns = b->n_samples;
     if (!b->path || !b->calls || !b->ncalls || b->call_cap < 1 || b->path_stride < c->n_bins)
         return fail(EDB200_ERR_ARG, "Viterbi outputs missing in batch");
@@ -905,8 +978,16 @@ static int viterbi_prepare(edb200_cohort* c, const edb200_batch* b, edb::Viterbi
     a.ll = b->ll;
     a.ll_sample_stride = (int64_t)S * b->ll_stride;
     a.ll_state_stride = b->ll_stride;
-    if (int rc = make_ll_map(b->ll, (int64_t)ns * S, b->ll_stride, b->ll_stride, S, ll_map)) return rc;
+    if (int rc = make_ll_map(b->ll, (int64_t)ns * S, b->ll_stride, b->ll_stride, (32 / S) * S, ll_map)) return rc;
     a.ll_map = ll_map;
+    a.tpc = use_tpc(c, ns) ? 1 : 0;
+    if (a.tpc) {
+        if (int rc = make_ll_map(b->ll, (int64_t)ns * S, b->ll_stride, b->ll_stride, 32 * S, ll_map + 1)) return rc;
+        a.ll_map_tpc = ll_map + 1;
+        a.srows = (const edb::StructRow*)c->srows.p;
+        a.c0 = c->c0;
+        a.c1 = c->c1;
+    }
     for (int j = 0; j < S; j++) a.perm[j] = c->perm[j];
     a.groups = (int)groups;
     a.lt = (const double*)c->lt.p;
@@ -925,17 +1006,13 @@ static int viterbi_prepare(edb200_cohort* c, const edb200_batch* b, edb::Viterbi
     return 0;
 }
 
-// Sweep warps per CTA of the pass that carries the longest chains (`packed` = 1 below): 4 = one per SM sub-partition.
-// EDB200_CRIT_WARPS = 1 or 2 (experiment, unmeasured): fewer warps share an SM's shared-memory pipe — four warps keep it
-// busy for 118 of a step's 160 cycles (DESIGN.md "what comes next" 1) — at the price of more SMs taken from the other pass.
-static int crit_warps()
+// Lane-per-state sweep: warps per CTA of the pass that carries the longest chains (`packed` = 1 below).  Two warps per
+// CTA: four warps keep an SM's shared-memory pipe busy for 118 of a step's 160 cycles; measured 1.617 (4 warps) /
+// 1.514 (2) / 1.526 ms (1) for the critical sweep at 256 x 200k x 5 (profiles/r2a_knob_ab.log).
+static int crit_warps(const edb200_cohort* c)
 {
-    static const int w = [] {
-        const char* e = getenv("EDB200_CRIT_WARPS");
-        const int v = e ? atoi(e) : 4;
-        return v == 1 || v == 2 ? v : 4;
-    }();
-    return w;
+    const int v = c->opt_crit_warps;
+    return v == 1 || v == 2 || v == 4 ? v : 2;
 }
 
 // sweep, tilemap, trace, expand of one part on `st`; the schedule is rebuilt when the number of sample groups changes
@@ -946,15 +1023,28 @@ static int crit_warps()
 static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiArgs a, int packed, cudaStream_t st, int avail_sms = 0)
 {
     if (avail_sms <= 0 || avail_sms > g.n_sms) avail_sms = g.n_sms;
-    if (pt.sched_groups != a.groups || pt.sched_avail != avail_sms) {
+    // thread-per-chain sweep: work items are (chain, 32 samples); lane-per-state sweep: (chain, 32/S samples)
+    const int sched_groups = a.tpc ? (a.n_samples + 31) / 32 : a.groups;
+    const int key = sched_groups * 2 + a.tpc;
+    if (pt.sched_groups != key || pt.sched_avail != avail_sms) {
         std::vector<int32_t> nobs(pt.chains.size());
         for (size_t i = 0; i < pt.chains.size(); i++) nobs[i] = c->chains_h[pt.chains[i]].nobs;
-        const char* force = getenv("EDB200_SWEEP_WARPS");          // experiments: 4 or 8
-        pt.sched_warps = force ? (atoi(force) == 8 ? 8 : 4) : packed == 1 ? crit_warps() : packed == 2 ? 8 : edb::viterbi_pick_warps(nobs.data(), (int)nobs.size(), a.groups, avail_sms);
-        const int64_t n_items = (int64_t)nobs.size() * a.groups;
-        const int sched_ctas = packed ? (int)std::min<int64_t>(avail_sms, (n_items + pt.sched_warps - 1) / pt.sched_warps) : avail_sms;
+        const int64_t n_items = (int64_t)nobs.size() * sched_groups;
+        int sched_ctas;
+        if (a.tpc) {
+            // one sweep warp per SM sub-partition; as few warps per CTA as place the items on the available SMs, because
+            // the CTA's shared memory is split between its warps' rings (the fewer, the deeper)
+            const int max_w = edb::viterbi_tpc_max_warps(a.n_states);
+            int w = c->opt_sweep_warps > 0 ? c->opt_sweep_warps : (int)((n_items + avail_sms - 1) / avail_sms);
+            pt.sched_warps = w < 1 ? 1 : w > max_w ? max_w : w;
+            sched_ctas = (int)std::min<int64_t>(avail_sms, (n_items + pt.sched_warps - 1) / pt.sched_warps);
+        } else {
+            const int force = c->opt_sweep_warps;
+            pt.sched_warps = force ? (force == 8 ? 8 : 4) : packed == 1 ? crit_warps(c) : packed == 2 ? 8 : edb::viterbi_pick_warps(nobs.data(), (int)nobs.size(), a.groups, avail_sms);
+            sched_ctas = packed ? (int)std::min<int64_t>(avail_sms, (n_items + pt.sched_warps - 1) / pt.sched_warps) : avail_sms;
+        }
         std::vector<int32_t> begin, items;
-        edb::viterbi_schedule(nobs.data(), (int)nobs.size(), a.groups, sched_ctas, pt.sched_warps, begin, items);
+        edb::viterbi_schedule(nobs.data(), (int)nobs.size(), sched_groups, sched_ctas, pt.sched_warps, begin, items);
         for (size_t i = 0; i < items.size(); i += 2) items[i] = pt.chains[items[i]];      // index in the part -> chain id
         // trailing sweep CTAs without work are not launched
         int n_ctas = sched_ctas;
@@ -965,7 +1055,7 @@ static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiA
         CU(cudaMemcpyAsync(pt.sched_begin.p, begin.data(), begin.size() * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(pt.sched_items.p, items.data(), items.size() * 4, cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));          // the vectors go out of scope
-        pt.sched_groups = a.groups;
+        pt.sched_groups = key;
         pt.sched_avail = avail_sms;
     }
     a.chain_list = (const int32_t*)pt.chain_list.p;
@@ -1015,8 +1105,8 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
     if (b->obs_stride < c->n_bins || b->ll_stride < c->n_bins) return fail(EDB200_ERR_ARG, "stride smaller than n_bins");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     edb::ViterbiArgs va{};
-    alignas(64) CUtensorMap ll_map;
-    if ((what & 2)) if (int rc = viterbi_prepare(c, b, va, &ll_map)) return rc;
+    alignas(64) CUtensorMap ll_map[2];
+    if ((what & 2)) if (int rc = viterbi_prepare(c, b, va, ll_map)) return rc;
 
     // Device-resident batches run emission, then Viterbi (1 part) unless EDB200_PARTS asks otherwise: both kernels own
     // their SM's shared memory, so overlapping them takes SMs away from the sweep's critical chains — measured slower
@@ -1035,7 +1125,7 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
             if (int rc = emission_part(c, b, all, true, emission_mode, 0, st)) return rc;
         }
         if (what & 2) {
-            const bool split = !(getenv("EDB200_VSPLIT") && atoi(getenv("EDB200_VSPLIT")) == 0);     // 0: one pass (tests, experiments)
+            const bool split = c->opt_vsplit != 0;                    // 0: one pass (tests, experiments)
             if (split && c->n_chains >= 4 && va.groups >= 8)
                 if (int rc = build_plan(c, 0)) return rc;
             // (chains of near-equal length — small panels — all fall into the first group: nothing to split)
@@ -1045,7 +1135,7 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
                 // {all others} on the rest — leave only the longest chains' own post-processing behind the critical sweep.
                 std::vector<edb200_cohort::Part>& vp = c->plans[0];
                 const int64_t items0 = (int64_t)vp[0].chains.size() * va.groups;
-                const int ctas0 = (int)std::min<int64_t>(g.n_sms / 2, (items0 + crit_warps() - 1) / crit_warps());
+                const int ctas0 = (int)std::min<int64_t>(g.n_sms / 2, (items0 + crit_warps(c) - 1) / crit_warps(c));
                 CU(cudaEventRecord(g.ev_fork, st));
                 for (int p = 0; p < 2; p++) {
                     if (vp[p].chains.empty()) continue;
@@ -1068,7 +1158,7 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
             CU(cudaStreamWaitEvent(g.s_vit[p], g.ev_em[p], 0));
             // first part: one warp per sub-partition on SMs of its own; later parts spread over the others
             const int64_t items0 = (int64_t)plan[0].chains.size() * va.groups;
-            const int ctas0 = (int)std::min<int64_t>(g.n_sms / 2, (items0 + crit_warps() - 1) / crit_warps());
+            const int ctas0 = (int)std::min<int64_t>(g.n_sms / 2, (items0 + crit_warps(c) - 1) / crit_warps(c));
             if (int rc = viterbi_part(c, plan[p], va, p == 0 ? 1 : 0, g.s_vit[p], p == 0 ? ctas0 : g.n_sms - ctas0)) return rc;
             CU(cudaEventRecord(g.ev_vit[p], g.s_vit[p]));
         }
@@ -1271,8 +1361,8 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         // ---- chromosome-group pipeline over PCIe: the counts of the long chromosomes go up first; their emission and
         // sweep (the critical path) run while the other groups are still uploading; results drain per group.
         edb::ViterbiArgs va{};
-        alignas(64) CUtensorMap ll_map;
-        if ((rc = viterbi_prepare(c, &d, va, &ll_map))) return rc;
+        alignas(64) CUtensorMap ll_map[2];
+        if ((rc = viterbi_prepare(c, &d, va, ll_map))) return rc;
         cudaStream_t sc = g.s_copy;
         if (shared_ref) CU(cudaMemcpyAsync(c->h_ref.p, b->reference, nb * 4, cudaMemcpyHostToDevice, sc));
         CU(cudaMemcpyAsync(c->h_phi.p, b->phi, ns * 8, cudaMemcpyHostToDevice, sc));
@@ -1303,8 +1393,13 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
             }
             CU(cudaStreamWaitEvent(g.s_vit[p], g.ev_em[p], 0));
             // packing per part: "1" = one sweep warp per SM sub-partition (fast), "2" = two (half the SMs)
-            const char* pp = getenv("EDB200_PACKPLAN");      // experiments, e.g. "222111"
-            const int pack = (pp && strlen(pp) > p) ? pp[p] - '0' : (p == 0 ? 1 : 2);
+            // EDB200_OPT_PACKPLAN (experiments): decimal digits, one per part from the left, e.g. 222111
+            int pack = p == 0 ? 1 : 2;
+            if (c->opt_packplan > 0) {
+                char pp[16];
+                snprintf(pp, sizeof pp, "%d", c->opt_packplan);
+                if (strlen(pp) > p) pack = pp[p] - '0';
+            }
             if ((rc = viterbi_part(c, plan[p], va, pack, g.s_vit[p]))) return rc;
             if (b->path)
                 for (int q = 0; q < rg.n; q++) {

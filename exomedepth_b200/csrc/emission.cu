@@ -13,8 +13,6 @@
 //                           three 8-byte shared-memory gathers + two FP64 adds per cell instead of
 //                           ~150 FP64 instructions.  HBM traffic is the algorithmic 4 + 8S bytes per
 //                           bin·sample (the count vector is re-read once per state, from L2).
-#include <cstdlib>
-
 #include "kernels.cuh"
 
 namespace edb {
@@ -175,11 +173,11 @@ __device__ __noinline__ void whole_item_cold(const StateConst* sc, const CountsV
 // kPanel: small lattices for panels of a few thousand bins (many items, few bins each): the K + R + N entries are one
 // index space shared evenly by ALL threads — one anchor + ~8 recurrence steps per thread — instead of one run per lattice
 // and thread, whose anchors (a full lgamma difference each) would dominate a 9 K-entry build.
-// kWarpRows (experiment, EDB200_EMISSION_WARPROWS=1, unmeasured): a lane takes bins {2l, 2l+1} and {64+2l, 64+2l+1} of
-// its warp's 128-bin block instead of four consecutive bins, so that each 128-bit store instruction of a warp covers
-// 512 contiguous bytes.  With four consecutive bins per lane the two stores of an iteration each write HALF of every
-// 32-byte sector they touch: ncu counts 128 M store sectors per launch where 64 M carry the data
-// (profiles/r1i_ncu_full_summary.txt), on the L1 data pipe that bounds the kernel.
+// kWarpRows (the full lattice kernel): a lane takes bins {2l, 2l+1} and {64+2l, 64+2l+1} of its warp's 128-bin block
+// instead of four consecutive bins, so that each 128-bit store instruction of a warp covers 512 contiguous bytes.  With
+// four consecutive bins per lane the two stores of an iteration each write HALF of every 32-byte sector they touch:
+// ncu counted 128 M store sectors per launch where 64 M carry the data (profiles/r1i_ncu_full_summary.txt), on the L1
+// data pipe that bounds the kernel; measured 0.967 -> 0.895 ms per launch (profiles/r2a_knob_ab.log).
 template <bool kPanel, bool kWarpRows>
 __global__ void __launch_bounds__(kTableThreads, 1)
 emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n_states, int n_items,
@@ -408,11 +406,10 @@ void launch_emission_table(CountsView c, const StateConst* consts, int n_samples
     const size_t smem = emission_table_smem_bytes(dims);
     const int grid = n_items < n_sms ? n_items : n_sms;
     if (dims.K + dims.R + dims.N < kPanelEntries) {
-        static size_t configured = 0;
-        if (smem > configured) {
+        static PerDevice configured;
+        if (configured.raise(smem)) {
             cudaFuncSetAttribute(emission_table_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(emission_table_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            configured = smem;
         }
         // A panel item is a chain of latency-bound phases (anchor + recurrence build, one or two gather passes, a handful
         // of out-of-lattice cells evaluated in registers): when two CTAs fit an SM's shared memory (228 KB, 1 KB reserved
@@ -425,17 +422,10 @@ void launch_emission_table(CountsView c, const StateConst* consts, int n_samples
                                                                                           lattices ? lattice_mode : 0);
         return;
     }
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(emission_table_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(emission_table_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
-    static const bool warp_rows = getenv("EDB200_EMISSION_WARPROWS") && atoi(getenv("EDB200_EMISSION_WARPROWS")) == 1;   // experiment
-    if (warp_rows)
-        emission_table_kernel<false, true><<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices, lattices ? lattice_mode : 0);
-    else
-        emission_table_kernel<false, false><<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices, lattices ? lattice_mode : 0);
+    static PerDevice configured;
+    if (configured.raise(smem)) cudaFuncSetAttribute(emission_table_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // warp-row bin mapping (full-sector 128-bit stores): measured 0.967 -> 0.895 ms per launch at 256 x 200k x 5 (profiles/r2a_knob_ab.log)
+    emission_table_kernel<false, true><<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices, lattices ? lattice_mode : 0);
 }
 
 }  // namespace edb

@@ -8,6 +8,7 @@
 // The table legitimately contains -Inf (log 0) and NaN (log of a negative term when bin starts are
 // not monotone, SURVEY.md §8c "NaN edge"); both are kept.  Compiled without FMA contraction.
 #include "host_tables.h"
+#include "viterbi_step.h"
 
 #include <algorithm>
 #include <cmath>
@@ -99,6 +100,50 @@ void nan_to_neg_inf(double* v, size_t n)
 {
     for (size_t i = 0; i < n; i++)
         if (v[i] != v[i]) v[i] = -HUGE_VAL;
+}
+
+int build_struct_rows(int S, const double* lt, int pitch, int64_t n_rows, StructRow* rows, double* c0, double* c1)
+{
+    if (S < 3) return 0;
+    const int js = pitch / S;
+    bool have = false;
+    uint64_t k0 = 0, k1 = 0;
+    for (int64_t i = 0; i < n_rows; i++) {
+        const double* r = lt + i * pitch;
+        bool zero = true;
+        for (int q = 0; q < pitch && zero; q++) zero = bits_of(r[q]) == 0;
+        rows[i] = StructRow{0.0, 0.0, 0.0, 0.0};
+        if (zero) continue;
+        const uint64_t a0 = bits_of(r[0]), a1 = bits_of(r[js]);              // t(0 -> 0), t(0 -> 1)
+        const uint64_t b0 = bits_of(r[1]), sf = bits_of(r[js + 1]), ot = bits_of(r[js + 2]);     // t(k>0 -> 0), t(1 -> 1), t(2 -> 1)
+        if (!have) { k0 = a0; k1 = a1; have = true; }
+        if (a0 != k0 || a1 != k1) return 0;
+        for (int j = 0; j < S; j++)
+            for (int k = 0; k < S; k++) {
+                const uint64_t v = bits_of(r[j * js + k]);
+                const uint64_t want = k == 0 ? (j == 0 ? k0 : k1) : j == 0 ? b0 : k == j ? sf : ot;
+                if (v != want) return 0;
+            }
+        rows[i].b0 = r[1];
+        rows[i].sf = r[js + 1];
+        rows[i].ot = r[js + 2];                  // t(2 -> 1); S >= 3 so state 2 exists
+    }
+    if (!have) return 0;
+    memcpy(c0, &k0, 8);
+    memcpy(c1, &k1, 8);
+    // What the speculative step (viterbi_step.h) takes for granted: log-probabilities (<= 0), c0 and c1 finite, and
+    // per row  ot - c1 <= b0 - c0  — the "other copy-number state" term loses to k = 0 by at least as much as the
+    // return-to-normal term does, so one comparison covers both groups.  With the CallCNVs matrix that is
+    // log(1 - d) <= log(1 - d + d/(2(1 - tp))), true for every d; it is verified here, not assumed.
+    if (!(std::fabs(*c0) < 1e300) || !(std::fabs(*c1) < 1e300) || *c0 > 0 || *c1 > 0) return 0;
+    for (int64_t i = 0; i < n_rows; i++) {
+        const StructRow& q = rows[i];
+        if (bits_of(q.b0) == 0 && bits_of(q.sf) == 0 && bits_of(q.ot) == 0) continue;          // unused row (see above)
+        if (q.b0 > 0 || q.sf > 0 || q.ot > 0 || q.b0 != q.b0 || q.sf != q.sf || q.ot != q.ot) return 0;
+        if (q.ot == -HUGE_VAL) continue;
+        if (q.b0 == -HUGE_VAL || !(q.ot - *c1 <= q.b0 - *c0 + 9.5367431640625e-07)) return 0;      // 2^-20 of slack
+    }
+    return 1;
 }
 
 void viterbi_schedule(const int32_t* chain_nobs, int n_chains, int groups, int n_ctas, int warps_per_cta,

@@ -29,6 +29,13 @@ int frame_positions(int64_t nb, const int32_t* start, const int32_t* end, double
 // in-place NaN -> -Inf for the device copy of the table: in the recurrence a NaN candidate and a -Inf candidate
 // behave identically (neither can satisfy the strict '>' of src/hmm.cpp:81)
 void nan_to_neg_inf(double* v, size_t n);
+// CallCNVs-structured view of a built table (viterbi_step.h): per observation row the three distance-dependent terms
+// b0 = log t(k>0 -> 0), sf = log t(j -> j), ot = log t(k -> j) for k outside {0, j}, plus the two row-independent
+// terms c0 = log t(0 -> 0), c1 = log t(0 -> j>0).  Returns 1 when EVERY row of `lt` (device copy: NaN already -Inf)
+// has exactly that structure, bit for bit — the one-thread-per-chain sweep is then exact by construction — else 0
+// (arbitrary matrices keep the general sweep).  All-zero rows (row 0 of every chain, never read) are skipped.
+struct StructRow;
+int build_struct_rows(int S, const double* lt, int pitch, int64_t n_rows, StructRow* rows, double* c0, double* c1);
 // Placement of the Viterbi sweep's work items (chromosome x group of samples) on the sweep warps: items are
 // dealt longest first to the least loaded SM sub-partition (warp slots w and w + 4 of a CTA share one), then to
 // its less loaded warp.  The sweep is a latency-bound dependent chain, so the longest chromosomes end up alone

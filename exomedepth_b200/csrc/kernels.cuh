@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "edb200_math.cuh"
+#include "viterbi_step.h"
 
 namespace edb {
 
@@ -17,6 +18,22 @@ inline void prof_mark(const char* name, cudaStream_t st)
 {
     if (g_timer) g_timer->mark(name, st);
 }
+
+// Per-device one-time kernel attributes (cudaFuncSetAttribute is per device, a process may drive several): `seen` is a
+// function-local static of the launcher, one slot per device ordinal.
+struct PerDevice {
+    size_t v[64] = {};
+    // true when `want` exceeds what was configured on the current device so far (and records it)
+    bool raise(size_t want)
+    {
+        int d = 0;
+        cudaGetDevice(&d);
+        d &= 63;
+        if (want <= v[d]) return false;
+        v[d] = want;
+        return true;
+    }
+};
 
 // ---- emission -----------------------------------------------------------------------------------
 struct CountsView {
@@ -107,6 +124,12 @@ struct ViterbiArgs {
     int32_t* ncalls;              // out [n_samples]
     int call_cap;
     unsigned* flags;
+    // one-thread-per-chain sweep for CallCNVs-structured transition rows (viterbi_tpc.cu); the schedule then deals
+    // (chain, group of 32 samples) items and warps_per_cta counts that kernel's sweep warps
+    int tpc;                      // 1: use it
+    const StructRow* srows;       // [rows + tile] structured rows (host_tables.h: build_struct_rows)
+    double c0, c1;                // log t(0 -> 0), log t(0 -> j > 0)
+    const void* ll_map_tpc;       // host pointer to the CUtensorMap with box 16 bins x 32*S rows
 };
 
 // enqueues sweep, tilemap, trace and expand for the chains of a.chain_list (the schedule must cover exactly those);
@@ -114,6 +137,9 @@ struct ViterbiArgs {
 int launch_viterbi(const ViterbiArgs& a, cudaStream_t st);
 int launch_viterbi_compact(const ViterbiArgs& a, cudaStream_t st);
 size_t viterbi_smem_bytes(int n_states, int warps_per_cta);
+int launch_viterbi_tpc_sweep(const ViterbiArgs& a, cudaStream_t st);   // viterbi_tpc.cu; 3, 5 or 7 states
+size_t viterbi_tpc_smem_bytes(int n_states, int warps_per_cta);
+int viterbi_tpc_max_warps(int n_states);
 int viterbi_pick_warps(const int32_t* chain_nobs, int n_chains, int groups, int n_sms);
 int viterbi_lt_pitch(int n_states);      // doubles per table row: S destination rows of S doubles padded to an even count
 int viterbi_tile();                      // observations per tile; the table carries this many spare rows

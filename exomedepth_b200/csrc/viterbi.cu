@@ -39,10 +39,11 @@
 
 #include "host_tables.h"
 #include "kernels.cuh"
+#include "tma_ptx.cuh"
+#include "viterbi_common.cuh"
 
 namespace edb {
 
-constexpr int kTile = 16;          // observations per tile (one 128-byte line of an emission row)
 // Sweep warps per CTA (one more warp issues the TMA loads): 4 = one per SM sub-partition, 8 = two.  A sweep warp alone
 // on its sub-partition AND in a CTA of 4 steps in ~135 cycles; with 8 per CTA the warps contend for the SM's
 // shared-memory / shuffle pipe and each step takes ~180 (tools/ubench/step.cu) — 8 only pays when the batch has more
@@ -57,82 +58,6 @@ __host__ __device__ constexpr int ring_stages(int S, int W)
 {
     const int fit = (220 * 1024) / (W * stage_bytes(S));
     return fit > 6 ? 6 : fit;
-}
-
-// ---- PTX helpers (mbarrier + 1-D bulk TMA) ---------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-// (all shared-memory operands are 32-bit shared-window addresses computed once per warp)
-__device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ bool try_wait_once(uint32_t bar, unsigned parity)
-{
-    unsigned ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src_gmem, unsigned bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-                 "l"(src_gmem), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-// 2-D tiled TMA load: box (16 bins x G*S rows) of the emission matrix, 128-byte swizzled in shared memory
-__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
-                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ double lds_f64(uint32_t addr)
-{
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
-{
-    double2 v;
-    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-    return v;
-}
-// the same loads for data other lanes of the warp have just written (ordered against the st.shared / warp barrier)
-__device__ __forceinline__ double lds_f64_fresh(uint32_t addr)
-{
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ double2 lds_f64x2_fresh(uint32_t addr)
-{
-    double2 v;
-    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
-    return v;
 }
 
 // ---- the recurrence -----------------------------------------------------------------------------------
@@ -238,25 +163,6 @@ __device__ __forceinline__ unsigned sweep_arg(const Cand<S>& cd, double V, doubl
     if (!(V > -HUGE_VAL)) arg = 7u;                         // 7 encodes "from = -1" (hmm.cpp:60)
     if (em == -HUGE_VAL) arg = 0u;                          // hmm.cpp:87
     return arg;
-}
-
-// ---- per-tile scratch record ---------------------------------------------------------------------------
-// One record per (work item, tile): 32 lanes x 8 bytes of packed back-pointers (16 observations x 4 bits),
-// then 16 x 4 bytes of tile maps, one per chain of the warp.  A tile map composes the tile's 16 back-pointer
-// steps: nibble e (e = 0..6, or 7 for the reference's "from = -1") holds the state at the observation just
-// BEFORE the tile given state e at the tile's last observation.
-constexpr int kRecU2 = 40;                 // uint2 per record (32 lanes + 64 bytes of maps)
-constexpr int kRecU32 = 2 * kRecU2;
-constexpr int kMapOff = 64;                // uint32 offset of the maps inside a record
-
-__device__ __forceinline__ unsigned bp_nibble(const uint2& w, int q) { return ((q < 8 ? w.x : w.y) >> (4 * (q & 7))) & 0xFu; }
-__device__ __forceinline__ int chain_tiles(const ChainDesc& cd)
-{
-    return cd.nobs > 1 ? (int)(((cd.em_off + cd.nobs - 1) >> 4) - ((cd.em_off + 1) >> 4) + 1) : 0;
-}
-__device__ __forceinline__ int64_t record_base(const ViterbiArgs& a, int chain, int grp, int n_tiles)
-{
-    return (int64_t)a.bp_tile_base[chain] * a.groups + (int64_t)grp * n_tiles;
 }
 
 // =========================================================================================== sweep
@@ -651,11 +557,8 @@ template <int S, int W>
 static void launch_sweep(const ViterbiArgs& a, cudaStream_t st)
 {
     const size_t smem = viterbi_smem_bytes(S, W);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(viterbi_sweep_kernel<S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    static PerDevice configured;
+    if (configured.raise(smem)) cudaFuncSetAttribute(viterbi_sweep_kernel<S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     viterbi_sweep_kernel<S, W><<<a.n_slots / W, (W + 1) * 32, smem, st>>>(a, *reinterpret_cast<const CUtensorMap*>(a.ll_map));
 }
 
@@ -664,7 +567,8 @@ static void launch_all(const ViterbiArgs& a, cudaStream_t st)
 {
     constexpr int G = 32 / S;
     prof_mark("viterbi_sweep", st);
-    switch (a.warps_per_cta) {
+    if (a.tpc) launch_viterbi_tpc_sweep(a, st);
+    else switch (a.warps_per_cta) {
         case 1: launch_sweep<S, 1>(a, st); break;          // 1, 2: experiments (EDB200_CRIT_WARPS), see DESIGN.md "what comes next"
         case 2: launch_sweep<S, 2>(a, st); break;
         case 4: launch_sweep<S, 4>(a, st); break;

@@ -1,0 +1,353 @@
+// viterbi_tpc.cu — Viterbi sweep with ONE THREAD PER CHAIN, for CallCNVs-structured transition rows (sm_100a).
+//
+// Same recurrence, same bits as src/hmm.cpp:58-90 (see viterbi_step.h for why the structured step is exact).  Where
+// viterbi.cu spreads a chain's S destination states over S lanes and pays a shared-memory exchange of V on every one
+// of the ~20,000 dependent steps of chromosome 1 (~150 cycles per step however few warps share the SM), here a lane
+// keeps all S values of V in registers: no exchange, 32 chains per warp instead of 32/S, and per step ~45 FP64
+// instructions instead of 14 per lane x S lanes.  A warp = the same chromosome of 32 consecutive samples, so the
+// distance-dependent transition terms of an observation are warp-uniform (three doubles, broadcast loads).
+//
+// Warp roles as in viterbi.cu: W sweep warps and one producer warp per CTA; lane w of the producer feeds sweep warp
+// w's ring: per 16-observation tile one 2-D TMA load of the emission tile (box 16 bins x 32*S rows, 128-byte swizzle:
+// a quarter-warp's 128-bit reads of two observations hit 8 distinct 16-byte chunks) and one bulk copy of the tile's 16
+// StructRows, completing on the stage's `full` mbarrier; the sweep warp hands the stage back through `empty`.
+// Back-pointers leave in the record layout of viterbi_common.cuh, so tilemap / trace / expand are shared.
+#include <cuda.h>
+
+#include "host_tables.h"
+#include "kernels.cuh"
+#include "tma_ptx.cuh"
+#include "viterbi_common.cuh"
+#include "viterbi_step.h"
+
+namespace edb {
+
+__host__ __device__ constexpr int tpc_em_bytes(int S) { return 32 * S * 128; }                       // 32 chains x S rows x 128 B
+__host__ __device__ constexpr int tpc_stage_bytes(int S) { return (tpc_em_bytes(S) + kTile * (int)sizeof(StructRow) + 1023) / 1024 * 1024; }
+__host__ __device__ constexpr int tpc_stages(int S, int W)
+{
+    const int fit = (214 * 1024) / (W * tpc_stage_bytes(S));
+    return fit > 8 ? 8 : fit;
+}
+
+// ---- the exact pair: out of line, taken when the speculative steps of a pair of observations do not apply --------
+// (a group of copy-number states may win or tie — inside and around CNV regions, a few percent of the pairs of a
+// warp — or an emission is NaN / +-Inf / huge: pathological phi).  By-value arguments and result: the caller's V
+// stays in registers.
+template <int S>
+struct PairArgs {
+    double v[S];
+    uint32_t em[S];             // shared-memory address of this lane's two emissions (observations A, B) per HMM state
+    uint32_t rows;              // shared-memory address of the two StructRows
+    double c0, c1;
+};
+template <int S>
+struct PairRes {
+    double v[S];
+    unsigned acc[S];            // per destination: back-pointer of the first observation | second << 4
+};
+
+template <int S>
+__device__ __noinline__ PairRes<S> tpc_pair_exact(const PairArgs<S> a)
+{
+    PairRes<S> r;
+    double V[S], ea[S], eb[S];
+    unsigned worst = (unsigned)__double2hiint(a.v[0]) << 1;
+#pragma unroll
+    for (int j = 0; j < S; j++) {
+        V[j] = a.v[j];
+        const double2 e = lds_f64x2(a.em[j]);
+        ea[j] = e.x;
+        eb[j] = e.y;
+        worst = max(worst, max((unsigned)__double2hiint(e.x) << 1, (unsigned)__double2hiint(e.y) << 1));
+    }
+    const double2 r0a = lds_f64x2(a.rows), r1a = lds_f64x2(a.rows + 32);
+    const StructRow rowA{r0a.x, r0a.y, lds_f64(a.rows + 16), 0.0}, rowB{r1a.x, r1a.y, lds_f64(a.rows + 48), 0.0};
+    if (worst >= 0xFFE00000u) {                             // NaN / Inf in sight: the fully checked step
+        unsigned arg[S];
+        viterbi_step_struct<S>(V, ea, a.c0, a.c1, rowA, r.acc);
+        viterbi_step_struct<S>(V, eb, a.c0, a.c1, rowB, arg);
+#pragma unroll
+        for (int j = 0; j < S; j++) r.acc[j] |= arg[j] << 4;
+    } else {
+        double VpB[S];
+        unsigned argB[S];
+        const unsigned needA = viterbi_step_fast<S>(V, ea, a.c0, a.c1, rowA, r.acc);
+#pragma unroll
+        for (int j = 0; j < S; j++) VpB[j] = V[j];
+        const unsigned needB = viterbi_step_fast<S>(V, eb, a.c0, a.c1, rowB, argB);
+#pragma unroll
+        for (int j = 0; j < S; j++) {
+            r.acc[j] |= argB[j] << 4;
+            if (needA >> j & 1u) r.acc[j] = (r.acc[j] & 0xF0u) | viterbi_resolve_arg<S>(a.v, ea[j], j, a.c0, a.c1, rowA);
+            if (needB >> j & 1u) r.acc[j] = (r.acc[j] & 0x0Fu) | (viterbi_resolve_arg<S>(VpB, eb[j], j, a.c0, a.c1, rowB) << 4);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < S; j++) r.v[j] = V[j];
+    return r;
+}
+
+#ifndef EDB_TPC_UNROLL_HALVES
+#define EDB_TPC_UNROLL_HALVES 0
+#endif
+constexpr bool kUnrollHalves = EDB_TPC_UNROLL_HALVES != 0;
+
+template <int S, int W>
+__global__ void __launch_bounds__((W + 1) * 32, 1)
+viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
+{
+    constexpr int G = 32 / S;                               // chains per back-pointer record (viterbi_common.cuh)
+    constexpr int kStages = tpc_stages(S, W);
+    static_assert(kStages >= 2, "ring needs two stages");
+    constexpr unsigned kStageBytes = tpc_stage_bytes(S);
+    constexpr unsigned kEmBytes = tpc_em_bytes(S);
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_u32(smem) + (uint32_t)W * kStages * kStageBytes;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < W * 2 * kStages; s++) mbar_init(bar0 + 8u * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == W) {
+        // ------------------------------------------------------------------------------------ producer
+        if (lane >= W) return;
+        const int slot = blockIdx.x * W + lane;
+        const uint32_t ring = smem_u32(smem) + (uint32_t)lane * kStages * kStageBytes;
+        const uint32_t full = bar0 + (uint32_t)lane * 2 * kStages * 8, empty = full + kStages * 8;
+        int st = 0;
+        unsigned wrap = 0;
+        for (int it = a.sched_begin[slot]; it < a.sched_begin[slot + 1]; it++) {
+            const int chain = a.sched_items[2 * it], g32 = a.sched_items[2 * it + 1];
+            const ChainDesc cd = a.chains[chain];
+            const int64_t t_first = (cd.em_off + 1) >> 4;
+            const int n_tiles = chain_tiles(cd);
+            const StructRow* __restrict__ rows = a.srows + cd.lt_row0;
+            int i0 = (int)((t_first << 4) - cd.em_off);
+            int c0 = (int)(t_first << 4);
+            const int c1 = g32 * 32 * S;
+            for (int t = 0; t < n_tiles; t++, i0 += kTile, c0 += kTile) {
+                if (wrap) mbar_wait(empty + 8u * st, (wrap - 1) & 1);
+                const int r0 = i0 < 0 ? 0 : i0;
+                const unsigned row_bytes = (unsigned)(i0 + kTile - r0) * (unsigned)sizeof(StructRow);
+                const uint32_t dst = ring + (uint32_t)st * kStageBytes;
+                mbar_expect_tx(full + 8u * st, row_bytes + kEmBytes);
+                tma_load_2d(dst, &ll_map, c0, c1, full + 8u * st);
+                tma_load_1d(dst + kEmBytes + (uint32_t)(r0 - i0) * (uint32_t)sizeof(StructRow), rows + r0, row_bytes, full + 8u * st);
+                if (++st == kStages) { st = 0; wrap++; }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------------------------- consumer
+    const uint32_t ring = smem_u32(smem) + (uint32_t)warp * kStages * kStageBytes;
+    const uint32_t full = bar0 + (uint32_t)warp * 2 * kStages * 8, empty = full + kStages * 8;
+    // this lane's S rows of the emission tile (likelihood-column order inside the box); chunk c (16 bytes) of row r
+    // sits at chunk c ^ (r & 7)
+    uint32_t em_row[S], em_sw[S];
+#pragma unroll
+    for (int j = 0; j < S; j++) {
+        const int r = lane * S + a.perm[j];
+        em_row[j] = (uint32_t)r * 128u;
+        em_sw[j] = (uint32_t)(r & 7) << 4;
+    }
+    const double c0 = a.c0, c1 = a.c1, tail_other = a.tail_other;
+    const double c0m = __dadd_rn(c0, -kSpecMargin);     // the speculative step's acceptance margin
+
+    int st = 0;
+    unsigned phase = 0;
+    const int slot = blockIdx.x * W + warp;
+    for (int it = a.sched_begin[slot]; it < a.sched_begin[slot + 1]; it++) {
+        const int chain = a.sched_items[2 * it], g32 = a.sched_items[2 * it + 1];
+        const ChainDesc cd = a.chains[chain];
+        const int nobs = cd.nobs;
+        const int64_t t_first = (cd.em_off + 1) >> 4;
+        const int n_tiles = chain_tiles(cd);
+        const int smp = g32 * 32 + lane;
+        const bool live = smp < a.n_samples;                // lanes past the batch sweep zero-filled rows and write nothing
+        const int grp = smp / G, gg = smp - grp * G;
+        uint2* bp_t = reinterpret_cast<uint2*>(a.bp) + record_base(a, chain, grp, n_tiles) * kRecU2 + gg * S;
+        int i0 = (int)((t_first << 4) - cd.em_off);
+        bool ready = false;
+
+        double V[S];
+#pragma unroll
+        for (int j = 0; j < S; j++) V[j] = j == 0 ? 0.0 : -HUGE_VAL;         // hmm.cpp:46-52
+
+        for (int t = 0; t < n_tiles; t++, bp_t += kRecU2, i0 += kTile) {
+            if (!ready) mbar_wait(full + 8u * st, phase);
+            const uint32_t stage = ring + (uint32_t)st * kStageBytes;
+            const uint32_t rows = stage + kEmBytes;
+            int st_n = st + 1;
+            unsigned phase_n = phase;
+            if (st_n == kStages) { st_n = 0; phase_n ^= 1u; }
+            ready = false;
+            unsigned lo[S], hi[S];
+#pragma unroll
+            for (int j = 0; j < S; j++) lo[j] = hi[j] = 0u;
+            if (i0 >= 1 && i0 + kTile - 1 <= cd.n_em) {     // tile entirely inside the real observations
+                // two halves of 4 pairs of observations.  The speculative step leaves ONE BIT per destination and
+                // observation (k = j won, or k = 0); a half's 8 observations x (S - 1) bits are spread into the record's
+                // 4-bit back-pointers once per half (bit -> nibble, times j).  The exact pair (out of line) overrides
+                // its two nibbles per destination.
+                constexpr int kBitWords = (S - 1 + 3) / 4;  // bits of destinations 1..4 in word 0, 5..6 in word 1
+                double2 e[S];
+                uint32_t ea[S];
+#pragma unroll
+                for (int j = 0; j < S; j++) {
+                    ea[j] = stage + em_row[j] + em_sw[j];
+                    e[j] = lds_f64x2(ea[j]);
+                }
+#pragma unroll(kUnrollHalves ? 2 : 1)
+                for (int h = 0; h < 2; h++) {
+                    unsigned pb[kBitWords], ovm[S], ovv[S];
+#pragma unroll
+                    for (int w = 0; w < kBitWords; w++) pb[w] = 0u;
+#pragma unroll
+                    for (int j = 0; j < S; j++) ovm[j] = ovv[j] = 0u;
+#pragma unroll
+                    for (int pp = 0; pp < kTile / 4; pp++) {
+                        const int p = h * (kTile / 4) + pp;
+                        double2 en[S];
+                        uint32_t ean[S];
+                        const uint32_t pn = (uint32_t)((p + 1) & 7) << 4;    // (the last pair reloads pair 0: harmless)
+#pragma unroll
+                        for (int j = 0; j < S; j++) {
+                            ean[j] = stage + em_row[j] + (pn ^ em_sw[j]);
+                            en[j] = lds_f64x2(ean[j]);
+                        }
+                        const uint32_t ra = rows + (uint32_t)p * 2u * (uint32_t)sizeof(StructRow);
+                        const double2 r0a = lds_f64x2(ra), r1a = lds_f64x2(ra + 32);
+                        const double r0o = lds_f64(ra + 16), r1o = lds_f64(ra + 48);
+                        if (pp == 2 && h == 0 && t + 1 < n_tiles) ready = try_wait_once(full + 8u * st_n, phase_n);   // poll the next tile early
+                        unsigned worst = (unsigned)__double2hiint(V[0]) << 1;
+                        double emA[S], emB[S], Vn[S];
+#pragma unroll
+                        for (int j = 0; j < S; j++) {
+                            worst = max(worst, max((unsigned)__double2hiint(e[j].x) << 1, (unsigned)__double2hiint(e[j].y) << 1));
+                            emA[j] = e[j].x;
+                            emB[j] = e[j].y;
+                            Vn[j] = V[j];
+                        }
+                        const StructRow rowA{r0a.x, r0a.y, r0o, 0.0}, rowB{r1a.x, r1a.y, r1o, 0.0};
+                        bool ok = worst < kSpecBigHi2;
+                        const unsigned bitsA = viterbi_step_spec<S>(Vn, emA, c0, c1, c0m, rowA, ok);
+                        const unsigned bitsB = viterbi_step_spec<S>(Vn, emB, c0, c1, c0m, rowB, ok);
+#pragma unroll
+                        for (int w = 0; w < kBitWords; w++)
+                            pb[w] |= ((bitsA >> (4 * w)) & 0xFu) << (8 * pp) | ((bitsB >> (4 * w)) & 0xFu) << (8 * pp + 4);
+                        if (!ok) {
+                            PairArgs<S> pa;
+#pragma unroll
+                            for (int j = 0; j < S; j++) {
+                                pa.v[j] = V[j];
+                                pa.em[j] = ea[j];
+                            }
+                            pa.rows = ra;
+                            pa.c0 = c0;
+                            pa.c1 = c1;
+                            const PairRes<S> pr = tpc_pair_exact<S>(pa);
+#pragma unroll
+                            for (int j = 0; j < S; j++) {
+                                Vn[j] = pr.v[j];
+                                ovm[j] |= 0xFFu << (8 * pp);
+                                ovv[j] |= pr.acc[j] << (8 * pp);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < S; j++) {
+                            V[j] = Vn[j];
+                            e[j] = en[j];
+                            ea[j] = ean[j];
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < S; j++) {
+                        // destination j's bit of every observation -> its nibble, times j; destination 0: all zero
+                        unsigned word = j == 0 ? 0u : ((pb[(j - 1) / 4] >> ((j - 1) & 3)) & 0x11111111u) * (unsigned)j;
+                        word = (word & ~ovm[j]) | ovv[j];
+                        if (h == 0) lo[j] = word;
+                        else hi[j] = word;
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int q = 0; q < kTile; q++) {
+                    const int i = i0 + q;
+                    unsigned arg[S];
+#pragma unroll
+                    for (int j = 0; j < S; j++) arg[j] = (unsigned)j;        // observations outside the chain: identity step
+                    if (i >= 1 && i < nobs) {               // warp-uniform
+                        double em[S];
+                        const uint32_t qa = ((uint32_t)(q >> 1) << 4), qb = (uint32_t)(q & 1) << 3;
+#pragma unroll
+                        for (int j = 0; j < S; j++) {
+                            em[j] = lds_f64(stage + em_row[j] + (qa ^ em_sw[j]) + qb);
+                            if (i > cd.n_em) em[j] = j == 0 ? 0.0 : tail_other;
+                        }
+                        const uint32_t ra = rows + (uint32_t)q * (uint32_t)sizeof(StructRow);
+                        const double2 rab = lds_f64x2(ra);
+                        const StructRow row{rab.x, rab.y, lds_f64(ra + 16), 0.0};
+                        viterbi_step_struct<S>(V, em, c0, c1, row, arg);
+                    }
+#pragma unroll
+                    for (int j = 0; j < S; j++) {
+                        if (q < 8) lo[j] |= arg[j] << (4 * q);
+                        else hi[j] |= arg[j] << (4 * (q - 8));
+                    }
+                }
+            }
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < S; j++) bp_t[j] = make_uint2(lo[j], hi[j]);
+            }
+            __syncwarp();                                   // every lane is done with the stage: hand it back
+            if (lane == 0) mbar_arrive(empty + 8u * st);
+            st = st_n;
+            phase = phase_n;
+        }
+    }
+}
+
+size_t viterbi_tpc_smem_bytes(int S, int W) { return (size_t)W * tpc_stages(S, W) * (tpc_stage_bytes(S) + 16); }
+int viterbi_tpc_max_warps(int S) { return S <= 3 ? 4 : S <= 5 ? 4 : 3; }
+
+template <int S, int W>
+static void launch_tpc(const ViterbiArgs& a, cudaStream_t st)
+{
+    if constexpr (tpc_stages(S, W) >= 2) {
+        const size_t smem = viterbi_tpc_smem_bytes(S, W);
+        static PerDevice configured;
+        if (configured.raise(smem)) cudaFuncSetAttribute(viterbi_tpc_kernel<S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        viterbi_tpc_kernel<S, W><<<a.n_slots / W, (W + 1) * 32, smem, st>>>(a, *reinterpret_cast<const CUtensorMap*>(a.ll_map_tpc));
+    }
+}
+
+template <int S>
+static void launch_tpc_w(const ViterbiArgs& a, cudaStream_t st)
+{
+    switch (a.warps_per_cta) {
+        case 1: launch_tpc<S, 1>(a, st); break;
+        case 2: launch_tpc<S, 2>(a, st); break;
+        case 3: launch_tpc<S, 3>(a, st); break;
+        default: launch_tpc<S, 4>(a, st); break;
+    }
+}
+
+// the structured sweep of the chains in a.chain_list (schedule: 32-sample groups); returns the number of launches
+int launch_viterbi_tpc_sweep(const ViterbiArgs& a, cudaStream_t st)
+{
+    switch (a.n_states) {
+        case 3: launch_tpc_w<3>(a, st); break;
+        case 5: launch_tpc_w<5>(a, st); break;
+        case 7: launch_tpc_w<7>(a, st); break;
+        default: return 0;
+    }
+    return 1;
+}
+
+}  // namespace edb

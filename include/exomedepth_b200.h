@@ -53,7 +53,7 @@ EDB200_API int         edb200_device_info(char *buf, int buflen, int *n_sms, int
 EDB200_API int64_t     edb200_launch_count(int reset);
 /* per-kernel device times: while enabled, every kernel launch of this library is bracketed by CUDA events on its
  * stream; edb200_profile_read synchronises and writes "name:launches:total_ms:longest_ms;..." (bench.py's roofline uses it) */
-EDB200_API int         edb200_profile(int enable);
+EDB200_API int         edb200_profile(int enable);   /* 0 off, 1 on, 2 on + print start / duration of every launch to stderr on read */
 EDB200_API int         edb200_profile_read(char *buf, int buflen);
 /* page-locked host buffers for the host-pointer entry points (optional, speeds up the copies) */
 EDB200_API void       *edb200_host_alloc(size_t bytes);
@@ -109,6 +109,18 @@ typedef struct edb200_cohort_spec {
  * reference's own bits) and uploads them. */
 EDB200_API int  edb200_cohort_create(const edb200_cohort_spec *spec, edb200_cohort **out);
 EDB200_API void edb200_cohort_destroy(edb200_cohort *c);
+
+/* Per-cohort execution options.  Defaults (0 / -1 = auto) are what every documented number uses; the other values
+ * exist so that tests can drive both sweep kernels over the same inputs and experiments can vary the placement.
+ * Results never depend on them (tests/test_gpu_parity.py). */
+#define EDB200_OPT_SWEEP       1   /* 0 auto; 1 one lane per (chain, state): any transition matrix (viterbi.cu);
+                                      2 one thread per chain: CallCNVs-structured matrices, 3/5/7 states (viterbi_tpc.cu) */
+#define EDB200_OPT_PARTS       2   /* chromosome groups a batch is pipelined over: 0 auto, 1 = one pass, .. 6 */
+#define EDB200_OPT_VSPLIT      3   /* device-resident Viterbi as {longest chains} | {others} concurrently: -1 auto, 0, 1 */
+#define EDB200_OPT_CRIT_WARPS  4   /* lane-per-state sweep: warps per CTA of the pass with the longest chains (1, 2, 4) */
+#define EDB200_OPT_SWEEP_WARPS 5   /* sweep warps per CTA (lane-per-state: 4 or 8; thread-per-chain: 1..4), 0 auto */
+#define EDB200_OPT_PACKPLAN    6   /* host pipeline: sweep packing per part as decimal digits, e.g. 122222; 0 auto */
+EDB200_API int  edb200_cohort_set_option(edb200_cohort *c, int option, int value);
 
 /* Size in bytes and device address of the shared log-transition table (for an NCCL broadcast from rank 0). */
 EDB200_API int  edb200_cohort_table(edb200_cohort *c, void **device_ptr, size_t *bytes);

@@ -357,7 +357,7 @@ def test_hmm_special_values(edb, port):
         assert np.array_equal(got[1], want[1]), trial
 
 
-def test_chromosome_group_pipeline_matches_single_pass(edb, monkeypatch):
+def test_chromosome_group_pipeline_matches_single_pass(edb):
     """The host-pointer call uploads, computes and sweeps the chromosomes in groups (longest first) on several streams;
     the device-resident call sweeps the longest chromosomes apart from the others.  Every grouping must give the
     single-pass results bit for bit: likelihoods, paths, call tables, per-call sums, correlations."""
@@ -367,18 +367,18 @@ def test_chromosome_group_pipeline_matches_single_pass(edb, monkeypatch):
     d = synth.cohort(ns, n_bins=20000)
     co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=5)
     args = (d["observed"], d["reference"], d["phi"], d["expected"])
-    monkeypatch.setenv("EDB200_PARTS", "1")
+    co.set_option("parts", 1)
     one = co.run_host(*args, call_cap=256, mode=_lib.EMISSION_TABLE, want_stats=True)
     assert one["ncalls"].sum() > 100
-    for parts in ("2", "3", "6"):
-        monkeypatch.setenv("EDB200_PARTS", parts)
+    for parts in (2, 3, 6):
+        co.set_option("parts", parts)
         got = co.run_host(*args, call_cap=256, mode=_lib.EMISSION_TABLE, want_stats=True)
         for k in ("ll", "path", "ncalls", "cor"):
             assert np.array_equal(got[k], one[k]), (parts, k)
         for s in range(ns):
             n = one["ncalls"][s]
             assert np.array_equal(got["calls"][s, :n], one["calls"][s, :n]) and np.array_equal(got["call_stats"][s, :n], one["call_stats"][s, :n])
-    monkeypatch.delenv("EDB200_PARTS")
+    co.set_option("parts", 0)
     # per-sample reference counts (ref_stride != 0) go through the same grouped uploads
     ref2 = np.tile(d["reference"], (ns, 1))
     got = co.run_host(d["observed"], ref2, d["phi"], d["expected"], call_cap=256, mode=_lib.EMISSION_TABLE, want_stats=True)
@@ -388,8 +388,8 @@ def test_chromosome_group_pipeline_matches_single_pass(edb, monkeypatch):
     t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in zip(("obs", "ref", "phi", "exp"), args)}
     nbp = (co.n_bins + 15) // 16 * 16
     outs = []
-    for split in ("0", "1"):
-        monkeypatch.setenv("EDB200_VSPLIT", split)
+    for split in (0, 1):
+        co.set_option("vsplit", split)
         ll = torch.empty((ns, 5, nbp), dtype=torch.float64, device=dev)
         path = torch.full((ns, nbp), 99, dtype=torch.int8, device=dev)
         calls = torch.zeros((ns, 256, 4), dtype=torch.int32, device=dev)
@@ -662,38 +662,68 @@ def test_ragged_last_chunk_uses_the_same_emission_kernel(edb):
 
 
 # ------------------------------------------------------------------------------------------------ experiment knobs
-_EXPERIMENT = '''
-import hashlib, sys
-import numpy as np
-import exomedepth_b200 as edb
-from exomedepth_b200 import _lib, synth
-edb.init()
-d = synth.cohort(6, n_bins=20000)
-co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=5)
-r = co.run_host(d["observed"], d["reference"], d["phi"], d["expected"], call_cap=512, mode=_lib.EMISSION_TABLE)
-h = hashlib.sha256()
-for k in ("ll", "path", "calls", "ncalls"):
-    h.update(np.ascontiguousarray(r[k]).tobytes())
-print(h.hexdigest())
-'''
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("EDB200_TEST_EXPERIMENTS"),
-                    reason="experiment knobs (built, not yet measured: DESIGN.md section 9); set EDB200_TEST_EXPERIMENTS=1 to run")
-@pytest.mark.parametrize("knob", ["EDB200_EMISSION_WARPROWS=1", "EDB200_CRIT_WARPS=2", "EDB200_CRIT_WARPS=1"])
-def test_experiment_knobs_do_not_change_results(edb, knob):
-    """The knobs only re-map work (bins to lanes, sweep warps to CTAs): every output must be bit-identical to the default's.
-    The knobs are read once per process, hence the subprocesses."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+def _run_dev(co, d, S, ns, **opts):
+    import torch
+    from exomedepth_b200 import _lib
+    dev = torch.device("cuda:0")
+    for k, v in opts.items():
+        co.set_option(k, v)
+    t = {k: torch.from_numpy(np.ascontiguousarray(d[k])).to(dev) for k in ("observed", "reference", "phi", "expected")}
+    nbp = (co.n_bins + 15) // 16 * 16
+    ll = torch.empty((ns, S, nbp), dtype=torch.float64, device=dev)
+    path = torch.full((ns, nbp), 99, dtype=torch.int8, device=dev)
+    calls = torch.zeros((ns, 512, 4), dtype=torch.int32, device=dev)
+    ncalls = torch.zeros(ns, dtype=torch.int32, device=dev)
+    co.run_device(t["observed"], t["reference"], t["phi"], t["expected"], ll, path, calls, ncalls, what=3, mode=_lib.EMISSION_AUTO)
+    torch.cuda.synchronize()
+    return ll.cpu().numpy()[:, :, :co.n_bins], path.cpu().numpy()[:, :co.n_bins], calls.cpu().numpy(), ncalls.cpu().numpy()
 
-    def run(extra):
-        env = dict(os.environ, PYTHONPATH=root, **extra)
-        out = subprocess.run([sys.executable, "-c", _EXPERIMENT], env=env, capture_output=True, text=True, timeout=300)
-        assert out.returncode == 0, out.stderr[-2000:]
-        return out.stdout.strip().splitlines()[-1]
 
-    name, value = knob.split("=")
-    assert run({name: value}) == run({})
+@pytest.mark.parametrize("S", [3, 5, 7])
+def test_thread_per_chain_sweep_matches_lane_per_state_sweep(edb, S):
+    """The two sweep kernels (viterbi_tpc.cu for CallCNVs-structured transition rows, viterbi.cu for any matrix) must give
+    the same paths and call tables bit for bit, for every placement of the work: ragged sample counts (not a multiple of 32
+    or of 32/S), 1 to 4 sweep warps per CTA, split and single-pass Viterbi, planted CNVs that make states change directly."""
+    from exomedepth_b200 import synth
+    for ns, nb in ((70, 24000), (33, 9000), (5, 3000)):
+        d = synth.cohort(ns, n_bins=nb)
+        co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=S)
+        want = _run_dev(co, d, S, ns, sweep=1)
+        assert want[3].sum() > 0
+        for warps in (0, 1, 2, 3, 4):
+            for split in (0, 1):
+                got = _run_dev(co, d, S, ns, sweep=2, sweep_warps=warps, vsplit=split)
+                for k, (x, y) in enumerate(zip(want, got)):
+                    assert np.array_equal(x, y), (S, ns, warps, split, k)
+        co.close()
+
+
+def test_thread_per_chain_sweep_special_emissions(edb, port):
+    """Pathological phi puts NaN cells into the likelihood matrix (the reference's a1 < 0 rows), zero-count runs make all
+    states tie: the structured sweep must follow the oracle port's path through both, like the general sweep."""
+    from exomedepth_b200 import synth
+    from oracle import framing
+    ns, S = 40, 5
+    d = synth.cohort(ns, n_bins=6000)
+    d["phi"][::7] = 0.93                                   # NaN cells for the low copy-number states
+    d["observed"][:, 100:140] = 0
+    d["observed"][3, :] = 0
+    ref = d["reference"].copy()
+    ref[100:140] = 0                                       # total = 0: every state's likelihood is exactly 0
+    d["reference"] = ref
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=S)
+    a = _run_dev(co, d, S, ns, sweep=1)
+    b = _run_dev(co, d, S, ns, sweep=2)
+    assert np.isnan(a[0]).any()
+    for x, y in zip(a[1:], b[1:]):
+        assert np.array_equal(x, y)
+    T = port.callcnvs_transitions(S, 1e-4)
+    for s in (0, 3, 7, 14):
+        ll = b[0][s].T
+        for c in range(len(d["offsets"]) - 1):
+            b0, b1 = d["offsets"][c], d["offsets"][c + 1]
+            loc, pos = framing.frame_chromosome(ll[b0:b1], d["start"][b0:b1].astype(float), d["end"][b0:b1].astype(float), 50000.0)
+            path, _ = port.c_hmm(T, loc, pos, 50000.0)
+            assert np.array_equal(b[1][s, b0:b1], path[1:-1]), (s, c)

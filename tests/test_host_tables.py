@@ -21,3 +21,17 @@ def test_host_tables_native(tmp_path):
                     "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_structured_viterbi_step_native(tmp_path):
+    """viterbi_step.h (the one-thread-per-chain sweep's step for CallCNVs-structured transition rows) against the plain
+    scan of src/hmm.cpp:66-88, bit for bit, on adversarial inputs; and the structured rows against the general table."""
+    cxx = shutil.which("g++") or shutil.which("c++")
+    if not cxx:
+        pytest.skip("no C++ compiler")
+    exe = str(tmp_path / "viterbi_step_check")
+    subprocess.run([cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-pthread", "-I", CSRC,
+                    os.path.join(ROOT, "tests", "native", "viterbi_step_check.cpp"), os.path.join(CSRC, "host_tables.cpp"),
+                    "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-3000:] + r.stderr[-2000:]
