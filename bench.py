@@ -128,6 +128,8 @@ def reference_arm(a, rank):
     from oracle import ref
     cores = os.cpu_count() or 1
     kind = "reference" if ref.available() else "port"
+    if kind == "reference":
+        ref.api()            # dlopen oracle/_ref/libexomedepth_ref.so in THIS process too (the workers are forked from it)
     states = 3 if kind == "reference" else N_STATES
     per_step = max(2 * cores, 16)
     vals, per_core = [], []
@@ -143,7 +145,7 @@ def reference_arm(a, rank):
                ms_per_step=1e3 * per_step * N_BINS / value, higher_is_better=True, scaling="weak", vs_baseline=None,
                dtype="f64", data="synthetic",
                config=dict(workload=f"synthetic {N_SAMPLES} samples x {N_BINS} bins x {N_STATES} CN states per GPU "
-                                    f"(BASELINE.json configs[1])",
+                                    f"(BASELINE.json configs[1])", nproc=cores, reference_states=states,
                            note=("the reference implements 3 states only (src/hmm.cpp:37-40, src/CNV_estimate.cpp:69); it is timed "
                                  "at 3 states on the same synthetic samples, which is LESS work per bin*sample than the 5-state GPU arm"
                                  if kind == "reference" else "compiled reference unavailable: oracle port at 5 states")),
@@ -213,6 +215,45 @@ def small_panel(dev, ns=512, states=7, steps=50):
                 kernel_ms_per_step=kernel_ms, replay_identical=same, note="CUDA events over 50 back-to-back steps; working set 150 MB > L2")
 
 
+def check_samples(kind, n_states, d, which, ll, path, calls, ncalls):
+    """Oracle comparison of samples `which` of a finished batch (host copies of the GPU outputs): likelihoods within 1e-10,
+    Viterbi path and call table equal.  kind = 'reference' (compiled reference, 3 states) or 'port' (C restatement)."""
+    from oracle import framing
+    if kind == "reference":
+        from oracle import ref as impl
+        impl.api().quiet(True)
+        T = framing.transition_matrix(TP, 3)
+    else:
+        from oracle import port as impl
+        T = impl.callcnvs_transitions(n_states, TP)
+    worst, paths_equal, calls_equal, n_cells = 0.0, True, True, 0
+    off, start, end, ref = d["offsets"], d["start"], d["end"], d["reference"]
+    for k, s in enumerate(which):
+        obs = d["observed"][s]
+        tot = obs + ref
+        if kind == "reference":
+            want = impl.get_loglike_matrix(np.full(obs.size, d["phi"][s]), np.full(obs.size, d["expected"][s]), tot, obs, 1.0)
+        else:
+            want = impl.emission(d["phi"][s], d["expected"][s], tot, obs, impl.state_odds(n_states))
+        got = ll[k].T
+        assert np.array_equal(np.isnan(got), np.isnan(want)), "NaN pattern"
+        ok = np.isfinite(want)
+        worst = max(worst, float(np.max(np.abs(got[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1e-2))))
+        n_cells += int(ok.sum())
+        c = 0
+        for ch in range(len(off) - 1):
+            b0, b1 = off[ch], off[ch + 1]
+            loc, pos = framing.frame_chromosome(got[b0:b1], start[b0:b1].astype(float), end[b0:b1].astype(float), CNV_LEN)
+            p, cl = impl.c_hmm(T, loc, pos, CNV_LEN)
+            paths_equal &= bool(np.array_equal(path[k, b0:b1], p[1:-1]))
+            for (sp, ep, typ, nex) in cl:
+                calls_equal &= c < calls.shape[1] and calls[k, c].tolist() == [sp - 1 + b0, ep - 1 + b0, typ, nex]
+                c += 1
+        calls_equal &= int(ncalls[k]) == c
+    return dict(oracle=kind, states=n_states, samples=[int(s) for s in which], cells=n_cells, max_rel=worst,
+                within_1e10=bool(worst <= 1e-10), paths_equal=bool(paths_equal), calls_equal=bool(calls_equal))
+
+
 def gpu_arm(a, rank, world):
     import torch
 
@@ -228,7 +269,7 @@ def gpu_arm(a, rank, world):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    S, ns = N_STATES, a.samples
+    S, ns = a.states, a.samples
     # ---- shared exon-bin metadata + reference aggregate: built on rank 0, NCCL-broadcast to the others ------
     from exomedepth_b200 import shard
     arrays = None
@@ -297,6 +338,31 @@ def gpu_arm(a, rank, world):
     ms = float(t[0])
     total_calls = int(ncalls.sum())
     status = _lib.load().edb200_status(0)
+
+    # ---- parity of THE BENCHMARKED BUFFERS (untimed): four samples of the batch the timed steps just produced against the C
+    # restatement at the benchmark's state count, and the same four samples through the same kernels at 3 states against the
+    # compiled reference itself (oracle/_ref, when it travelled to this box)
+    parity = None
+    if rank == 0 and not a.no_parity:
+        from oracle import ref as oref
+        which = sorted({0, ns // 3, (2 * ns) // 3, ns - 1})
+        dd = dict(offsets=off, start=start, end=end, reference=ref, observed=obs_h, phi=phi_h, expected=exp_h)
+        idx = torch.tensor(which, device=dev)
+        parity = [check_samples("port", S, dd, which, ll[idx].cpu().numpy()[:, :, :nb], path[idx].cpu().numpy()[:, :nb],
+                                calls[idx].cpu().numpy(), ncalls[idx].cpu().numpy())]
+        if oref.available():
+            co3 = edb.Cohort(off, start, end, n_states=3, transition_probability=TP, expected_cnv_length=CNV_LEN)
+            k = len(which)
+            ll3 = torch.empty((k, 3, nbp), dtype=torch.float64, device=dev)
+            path3 = torch.empty((k, nbp), dtype=torch.int8, device=dev)
+            calls3 = torch.zeros((k, cap, 4), dtype=torch.int32, device=dev)
+            ncalls3 = torch.zeros(k, dtype=torch.int32, device=dev)
+            co3.run_device(obs_t[idx].contiguous(), ref_t, phi_t[idx].contiguous(), exp_t[idx].contiguous(), ll3, path3, calls3, ncalls3,
+                           what=3, mode=_lib.EMISSION_TABLE)
+            torch.cuda.synchronize()
+            parity.append(check_samples("reference", 3, dd, which, ll3.cpu().numpy()[:, :, :nb], path3.cpu().numpy()[:, :nb],
+                                        calls3.cpu().numpy(), ncalls3.cpu().numpy()))
+            co3.close()
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D of the counts inside the timed region, results back
     # in host memory.  Primary = what CallCNVs returns to the user (R/class_definition.R:311-419): the CNV call table with
@@ -413,14 +479,16 @@ def gpu_arm(a, rank, world):
                                     "CallCNVs framing, tp=1e-4, L=50000",
                            cache="inputs+outputs per step (2.3 GB) exceed the 126 MB L2; no flush needed",
                            shared_metadata="bin geometry, reference aggregate and host-libm log-transition table NCCL-broadcast from rank 0"
-                           if world > 1 else "single rank", table_build_s=table_s, total_calls=total_calls, status=status),
-               clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roof(dom),
+                           if world > 1 else "single rank", table_build_s=table_s, total_calls=total_calls, status=status, nproc=os.cpu_count()),
+               clocks=clocks, e2e=e2e, gpu_launches=int(launches), parity=parity, roofline=roof(dom),
                roofline_other=roof("emission" if dom != "emission" else "viterbi_sweep"),
                kernel_ms_per_step={k: round(v, 5) for k, v in sorted(kt.items(), key=lambda kv: -kv[1])}, aux=aux)
     if world == 1 and not a.no_cpu:
         from oracle import ref as oref
         cores = os.cpu_count() or 1
         kind = "reference" if oref.available() else "port"
+        if kind == "reference":
+            oref.api()       # the library is then mapped in this process as well as in the forked workers
         states = 3 if kind == "reference" else S
         nsamp = max(2 * cores, 16)
         v, pc, wall = cpu_throughput(kind, states, nsamp, cores)
@@ -428,6 +496,197 @@ def gpu_arm(a, rank, world):
                                    sample=f"{nsamp} of the same synthetic samples x {nb} bins, {states} states "
                                           f"(the reference implements 3 states only), one sample per worker process")
     emit(out)
+    if dist:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ other workloads
+def _dist_setup(world):
+    import torch
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    return local, dev, dist
+
+
+def fp64_peak():
+    """Measured FP64 FMA issue rate of one B200 SM (tools/ubench/fp64tput.cu, profiles/r2b_fp64tput.txt): 1.845 warp
+    instructions per clock and SM -> TFLOP/s at the SM clock the run saw."""
+    return 1.845 * 32 * 2 * 148 * 1.965e9 / 1e12, "measured DFMA issue rate, profiles/r2b_fp64tput.txt (1.845 warp-instr/clk/SM x 148 SMs x 1.965 GHz)"
+
+
+def refset_arm(a, rank, world):
+    """BASELINE.json configs[4]: the select.reference.set correlation sweep (R/optimize_reference_set.R:100) of a
+    2,000-sample x 200k-bin cohort, leave-one-out over the whole cohort, samples sharded over the ranks (strong scaling:
+    the cohort is fixed).  A step = standardise this rank's rows, exchange, form this rank's block of the N x N matrix."""
+    import torch
+
+    import exomedepth_b200 as edb
+    from exomedepth_b200 import _lib, refset, shard, synth
+    local, dev, dist = _dist_setup(world)
+    edb.init(local)
+    n_total, nb = a.samples if a.samples != N_SAMPLES else 2000, a.bins
+    d = synth.cohort(16, n_bins=nb)
+    nb = int(d["start"].size)
+    lo, hi = shard.shard_range(n_total, rank, world)
+    rng = np.random.default_rng(7)
+    thin = rng.uniform(0.6, 1.0, n_total)
+    counts = np.empty((hi - lo, nb), np.int32)
+    for s in range(lo, hi):                                 # every rank makes only its block; thinning keeps samples distinct
+        counts[s - lo] = np.random.default_rng(1000 + s).binomial(d["observed"][s % 16], thin[s])
+    bl = (d["end"] - d["start"] + 1).astype(np.float64)
+    total = torch.from_numpy(counts.sum(0, dtype=np.int64)).to(dev)
+    if dist:
+        dist.all_reduce(total)                              # per-bin totals of the whole cohort (the bin filter needs them)
+    sel = refset.select_bins(total.cpu().numpy(), bl)
+    per = -(-n_total // world)
+    kp = refset.kpad(sel.size)
+    n_local = hi - lo
+    c_t, sel_t, bl_t = torch.from_numpy(counts).to(dev), torch.from_numpy(sel).to(dev), torch.from_numpy(bl).to(dev)
+    z_local = torch.zeros((per, kp), dtype=torch.float64, device=dev)
+    z_all = torch.empty((world * per, kp), dtype=torch.float64, device=dev) if dist else z_local
+    out = torch.empty((max(n_local, 1), n_total), dtype=torch.float64, device=dev)
+    fused = dist is not None and per <= 256 and not a.no_fused
+    if fused:
+        z_ptr, handle = refset.block_alloc(per, sel.size)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        refset.peers_open(handles, rank)
+
+    def step():
+        if fused:
+            refset.standardize_device(c_t, sel_t, bl_t, z_ptr)
+            torch.cuda.synchronize()
+            dist.barrier()                                  # every block complete before any rank reads it over NVLink
+            refset.gram_peers_device(n_local, per, n_total, sel.size, out)
+        else:
+            refset.standardize_device(c_t, sel_t, bl_t, z_local[:n_local])
+            if dist:
+                dist.all_gather_into_tensor(z_all, z_local)
+            refset.gram_device(z_local[:n_local], z_all[:n_total], sel.size, out)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    _lib.launch_count(reset=True)
+    _lib.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count()
+    prof = _lib.profile_read()
+    _lib.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / a.steps
+    # end to end through the host-pointer entry point (counts in pinned host memory -> correlation rows back), rank 0's block
+    e2e = None
+    if not a.no_e2e and rank == 0:
+        n_e = min(n_local, 64)
+        hb = _lib.PinnedPool()
+        cp = hb.empty((n_total if world == 1 else n_local, nb), np.int32)
+        cp[:] = counts if world > 1 else counts
+        t0 = time.perf_counter()
+        refset.correlations(cp, sel, bl, row0=0, n_rows=n_e)
+        dt = time.perf_counter() - t0
+        e2e = dict(value=n_e * cp.shape[0] * sel.size / dt, unit="pair*bins/s", h2d_bytes_per_step=int(cp.nbytes + sel.nbytes + bl.nbytes),
+                   d2h_bytes_per_step=int(n_e * cp.shape[0] * 8), ms_per_step=1e3 * dt,
+                   api=f"edb200_refset_correlations (C ABI, pinned host counts): {n_e} test rows against {cp.shape[0]} samples of this rank")
+        hb.close()
+    if fused:
+        barrier()
+        refset.peers_close()
+    if rank == 0:
+        pairs = float(n_total) * n_total
+        flops = 2.0 * pairs * kp
+        gram_ms = prof["refset_gram"][1] / a.steps
+        peak, src = fp64_peak()
+        ach = 2.0 * n_local * n_total * kp / (gram_ms / 1e3) / 1e12
+        out_line = dict(metric="select.reference.set correlation sweep: sample pairs x selected bins / s", value=pairs * sel.size / (ms / 1e3),
+                        unit="pair*bins/s", n_gpus=world, steps=a.steps, warmup=a.warmup, ms_per_step=ms, higher_is_better=True, scaling="strong",
+                        vs_baseline=None, dtype="f64", data="synthetic",
+                        config=dict(workload=f"select.reference.set sweep, {n_total} samples x {nb} bins ({sel.size} selected), leave-one-out over the "
+                                             "cohort (BASELINE.json configs[4])", exchange="CUDA-IPC peer-memory Gram (no all-gather)" if fused else
+                                             ("NCCL all-gather of standardised rows, then Gram" if dist else "single rank"),
+                                    all_gather_bytes_per_rank=int((world - 1) * per * kp * 8), cache="Z (2.2 GB) exceeds the 126 MB L2", nproc=os.cpu_count()),
+                        clocks=clocks, e2e=e2e, gpu_launches=int(launches),
+                        roofline=dict(kernel="refset_gram", bound="fp64", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
+                                      ms_per_launch=gram_ms, flops_per_step_all_ranks=flops, peak_source=src,
+                                      note="FP64 FMA contraction (no FP64 tcgen05 kind); achieved = this rank's 2*m*n*k flops / its Gram kernel time"),
+                        kernel_ms_per_step={k: round(v[1] / a.steps, 5) for k, v in prof.items()})
+        if world == 1 and not a.no_cpu:
+            from oracle import refset as oref
+            m = 48
+            t0 = time.perf_counter()
+            oref.cohort_correlations(counts[:m], bl)
+            dt = time.perf_counter() - t0
+            out_line["cpu_baseline"] = dict(value=m * m * sel.size / dt, unit="pair*bins/s", cores=1, kind="port", wall_s=dt,
+                                            sample=f"{m} of the same samples, numpy restatement of R/optimize_reference_set.R:81-100 (oracle/refset.py)")
+        emit(out_line)
+    if dist:
+        dist.destroy_process_group()
+
+
+def small_panel_arm(a, rank, world):
+    """BASELINE.json configs[3]: 512 samples x 5,000 bins (chr1-chr5, 1,000 each) x 7 states per GPU, device-resident,
+    emission + Viterbi + CallCNVs sums per step, replayed from a captured CUDA graph (the launch-bound regime)."""
+    import torch
+
+    import exomedepth_b200 as edb
+    local, dev, dist = _dist_setup(world)
+    edb.init(local)
+    ns = a.samples if a.samples != N_SAMPLES else 512
+    r = small_panel(dev, ns=ns, states=7, steps=max(a.steps, 20))
+    t = torch.tensor([r["graph_replay_ms"]], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t[0])
+        nb, S = 5000, 7
+        cells = ns * nb
+        peak, src = peaks()
+        kt = r["kernel_ms_per_step"]
+        alg = {"emission_panel": 4 + 8 * S, "viterbi_sweep": 8 * S + 1}
+        dom = max(alg, key=lambda k: kt.get(k, 0.0))
+        ach = cells * alg[dom] / (kt[dom] / 1e3) / 1e9
+        line = dict(metric=METRIC, value=world * cells / (ms / 1e3), unit=UNIT, n_gpus=world, steps=max(a.steps, 20), warmup=5, ms_per_step=ms,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    config=dict(workload=r["workload"], launch="one CUDA-graph replay per step", cache=r["note"], nproc=os.cpu_count()),
+                    gpu_launches=int(r["kernels_per_step"] * max(a.steps, 20)), e2e=None,
+                    roofline=dict(kernel=dom, bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
+                                  ms_per_launch=kt[dom], bytes_per_unit=alg[dom], peak_source=src),
+                    kernel_ms_per_step=kt, stream_launch_ms=r["stream_launch_ms"], host_ms_per_step=dict(stream=r["stream_launch_host_ms"], graph=r["graph_replay_host_ms"]),
+                    replay_identical=r["replay_identical"])
+        if world == 1 and not a.no_cpu:
+            from oracle import ref as oref
+            cores = os.cpu_count() or 1
+            kind = "reference" if oref.available() else "port"
+            if kind == "reference":
+                oref.api()
+            v, pc, wall = cpu_throughput(kind, 3 if kind == "reference" else 7, max(8 * cores, 64), cores, n_bins=nb)
+            line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=cores, kind=kind, per_core=pc, wall_s=wall,
+                                        sample=f"{max(8 * cores, 64)} synthetic samples x {nb} bins, 3 states (the reference implements 3 only)")
+        emit(line)
     if dist:
         dist.destroy_process_group()
 
@@ -459,13 +718,23 @@ def main():
     ap.add_argument("--bins", type=int, default=N_BINS)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the benchmarked buffers")
     ap.add_argument("--no-aux", action="store_true", help="skip the timings of the fit / reference-set kernels")
     ap.add_argument("--no-ll", action="store_true", help="skip the e2e variant that copies the likelihood matrix back")
+    ap.add_argument("--workload", default="cohort", choices=["cohort", "small_panel", "refset"],
+                    help="cohort = BASELINE.json configs[1] per GPU (the metric's configuration; the default); small_panel = configs[3]; "
+                         "refset = configs[4], the select.reference.set correlation sweep of 2,000 samples sharded over the ranks")
+    ap.add_argument("--states", type=int, default=N_STATES, help="copy-number states of the cohort workload (3 = the reference's own model)")
+    ap.add_argument("--no-fused", action="store_true", help="refset: NCCL all-gather + Gram instead of the peer-memory Gram")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     a.warmup = max(a.warmup, 3) if a.impl == "graft" else a.warmup
     if a.impl == "reference":
         reference_arm(a, rank)
+    elif a.workload == "refset":
+        refset_arm(a, rank, world)
+    elif a.workload == "small_panel":
+        small_panel_arm(a, rank, world)
     else:
         gpu_arm(a, rank, world)
 

@@ -17,6 +17,6 @@ All numerics run in hand-written sm_100a CUDA kernels through the C ABI in inclu
 There is no CPU fallback.
 """
 from ._lib import EDB200Error, device_info, init, launch_count  # noqa: F401
-from .api import C_hmm, CallCNVs, ExomeDepth, TestCNV, emission, get_loglike_matrix, somatic_CNV_call, viterbi_hmm  # noqa: F401
+from .api import C_hmm, CallCNVs, ExomeDepth, TestCNV, emission, get_loglike_matrix, lnbeta, somatic_CNV_call, viterbi_hmm  # noqa: F401
 from .cohort import Cohort  # noqa: F401
 from . import betabin, refset  # noqa: F401

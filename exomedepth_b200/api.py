@@ -42,6 +42,17 @@ def get_loglike_matrix(phi, expected, total, observed, mixture=1.0):
     return out.reshape((n, 3), order="F")
 
 
+def lnbeta(x, y):
+    """gsl_sf_lnbeta (src/beta.c:161-164) element-wise through the device's restatement of the vendored GSL chain
+    (edb200_lnbeta).  NaN where the reference raises a domain error."""
+    x, y = np.broadcast_arrays(np.asarray(x, float), np.asarray(y, float))
+    shape = x.shape
+    x, y = _f64(x.ravel()), _f64(y.ravel())
+    out = np.empty(x.size)
+    _lib.check(_lib.load().edb200_lnbeta(x.ctypes.data, y.ctypes.data, x.size, out.ctypes.data), "edb200_lnbeta")
+    return out.reshape(shape)
+
+
 def emission(phi, expected, total, observed, odds):
     """S-state generalisation (extension): columns in the order of `odds`."""
     total, observed = _i32(total), _i32(observed)

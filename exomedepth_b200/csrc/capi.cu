@@ -533,6 +533,27 @@ int edb200_emission(const double* phi, const double* expected, const int32_t* to
     return warn;
 }
 
+int edb200_lnbeta(const double* x, const double* y, int64_t n, double* out)
+{
+    if (int rc = need_ctx()) return rc;
+    if (n < 0 || (n > 0 && (!x || !y || !out))) return fail(EDB200_ERR_ARG, "null argument");
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaStream_t st = g.stream;
+    if (int rc = ensure(cs.phi, n * 8)) return rc;
+    if (int rc = ensure(cs.expected, n * 8)) return rc;
+    if (int rc = ensure(cs.ll, n * 8)) return rc;
+    CU(cudaMemcpyAsync(cs.phi.p, x, n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(cs.expected.p, y, n * 8, cudaMemcpyHostToDevice, st));
+    edb::launch_lnbeta((const double*)cs.phi.p, (const double*)cs.expected.p, n, (double*)cs.ll.p, g.d_flags, st);
+    g_launches++;
+    if (int rc = check_kernel("lnbeta")) return rc;
+    CU(cudaMemcpyAsync(out, cs.ll.p, n * 8, cudaMemcpyDeviceToHost, st));
+    int warn = 0;
+    if (int rc = pull_flags(st, &warn)) return rc;
+    return warn;
+}
+
 int edb200_get_loglike_matrix(const double* phi, const double* expected, const int32_t* total,
                               const int32_t* observed, double mixture, int64_t n, double* ll_out)
 {

@@ -68,6 +68,27 @@ void launch_emission_bins(const double* phi, const double* expected, const int32
 }
 
 // ---------------------------------------------------------------------------------------------
+// The vendored gsl_sf_lnbeta (src/beta.c:161-164) as the device evaluates it on the faithful path: exposed so that the
+// parity tests can pin the special-function chain itself (KAT-2, the dense sweeps of tests/golden/ref_vectors.npz incl.
+// arguments next to negative integers: src/VP_gamma.c:795-894 through the psi / zeta closed forms).
+__global__ void lnbeta_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n, double* __restrict__ out,
+                              unsigned* __restrict__ flags)
+{
+    unsigned f = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = lnbeta_gsl(x[i], y[i], f);
+    if (f) atomicOr(flags, f);
+}
+
+void launch_lnbeta(const double* x, const double* y, int64_t n, double* out, unsigned* flags, cudaStream_t st)
+{
+    if (n == 0) return;
+    int64_t blocks = (n + 127) / 128;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    lnbeta_kernel<<<(int)blocks, 128, 0, st>>>(x, y, n, out, flags);
+}
+
+// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void load_counts(const CountsView& c, int sample, int64_t b, int& tot, int& obs)
 {
     obs = c.observed[sample * c.obs_stride + b];

@@ -59,6 +59,9 @@ void launch_emission_bins(const double* phi, const double* expected, const int32
                           const int32_t* observed, int64_t n_bins, int n_states, const double* odds,
                           LLView out, unsigned* flags, cudaStream_t st);
 
+// gsl_sf_lnbeta (src/beta.c:161-164) through the device's faithful GSL restatement; parity tests only
+void launch_lnbeta(const double* x, const double* y, int64_t n, double* out, unsigned* flags, cudaStream_t st);
+
 // batched, per-sample scalar phi/expected, lgamma differences evaluated in registers
 void launch_emission_direct(CountsView c, const StateConst* consts, int n_samples, int n_states,
                             int64_t n_bins, LLView out, unsigned* flags, cudaStream_t st);

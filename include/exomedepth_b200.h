@@ -67,6 +67,12 @@ EDB200_API void        edb200_host_free(void *p);
 EDB200_API int edb200_get_loglike_matrix(const double *phi, const double *expected, const int32_t *total,
                               const int32_t *observed, double mixture, int64_t n, double *ll_out);
 
+/* gsl_sf_lnbeta(x, y) (src/beta.c:161-164: the only symbol of the vendored GSL that the hot path calls,
+ * src/CNV_estimate.cpp:33,49) evaluated element-wise by the device's restatement of that chain — the code the
+ * emission kernels fall back to for non-positive shape parameters.  NaN + EDB200_WARN_NAN where the reference
+ * prints a domain error.  Host pointers; exists so that the special functions can be pinned on their own. */
+EDB200_API int edb200_lnbeta(const double *x, const double *y, int64_t n, double *out);
+
 /* S-state generalisation of the same routine (extension; n_states = 3 with odds = NULL or
  * {1-mix/2, 1, 1+mix/2} is exactly the call above).  odds: double[n_states] multiplying the odds of the
  * expected proportion per state; ll_out: double[n*n_states] column-major. */

@@ -26,6 +26,12 @@ def refvec():
 
 
 @pytest.fixture(scope="session")
+def refvec2():
+    """Round-2 vectors from the compiled reference (tools/make_golden_r2.py): leave-one-out ExomeCount, envelope, a1 ~ -1."""
+    return np.load(os.path.join(GOLDEN, "ref_vectors_r2.npz"))
+
+
+@pytest.fixture(scope="session")
 def exomecount():
     return np.load(os.path.join(GOLDEN, "exomecount.npz"))
 

@@ -193,7 +193,7 @@ def test_panel_lattice_vs_oracle(edb, port, n_bins, scale):
     phi[1] = 0.93
     a = co.run_host(obs, ref, phi, d["expected"], want_path=False, mode=_lib.EMISSION_PANEL)["ll"]
     b = co.run_host(obs, ref, phi, d["expected"], want_path=False, mode=_lib.EMISSION_DIRECT)["ll"]
-    assert_ll_close(a, b, rtol=1e-9)                                    # incl. the NaN pattern
+    assert_ll_close(a, b)                                               # incl. the NaN pattern; 1e-10 like everywhere
 
 
 def test_pathological_phi_nan_pattern(edb, port):
@@ -207,7 +207,7 @@ def test_pathological_phi_nan_pattern(edb, port):
     want = port.get_loglike_matrix(phi, e, tot, obs, 1.0)
     got = edb.get_loglike_matrix(phi, e, tot, obs, 1.0)
     assert np.isnan(want).sum() > 100
-    assert_ll_close(got, want, rtol=1e-9)
+    assert_ll_close(got, want)                                          # 1e-10 (the faithful path is compiled without FMA contraction)
 
 
 # ------------------------------------------------------------------------------------------------ extensions (parity unpinned)
@@ -727,3 +727,107 @@ def test_thread_per_chain_sweep_special_emissions(edb, port):
             loc, pos = framing.frame_chromosome(ll[b0:b1], d["start"][b0:b1].astype(float), d["end"][b0:b1].astype(float), 50000.0)
             path, _ = port.c_hmm(T, loc, pos, 50000.0)
             assert np.array_equal(b[1][s, b0:b1], path[1:-1]), (s, c)
+
+
+# ------------------------------------------------------------------------------------------------ round-2 vectors
+def test_device_lnbeta_vs_reference(edb, refvec, kat):
+    """The vendored GSL chain itself (rows B1, G1-G3, L1, X1, P1 of SURVEY.md §8a) on the device: gsl_sf_lnbeta over
+    4,000 arguments of the compiled reference — every branch of src/beta.c:49-114, src/VP_gamma.c:1219-1285 incl. 300
+    arguments within 0.014 of a NEGATIVE INTEGER, which walk lngamma_sgn_sing (src/VP_gamma.c:795-894) and the psi / zeta
+    closed forms behind it — and KAT-2.  Tolerance 1e-10 relative, NaN exactly where the reference raises a domain error."""
+    x, y, want = refvec["lnbeta_x"], refvec["lnbeta_y"], refvec["lnbeta_val"]
+    got = edb.lnbeta(x, y)
+    near = np.abs(x - np.round(x)) < 0.015
+    near &= x < 0
+    assert near.sum() >= 250 and np.isfinite(want[near]).sum() >= 100           # the slow path is exercised with finite values
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = np.isfinite(want)
+    rel = np.abs(got[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1e-2)
+    assert rel.max() <= 1e-10, (rel.max(), x[ok][rel.argmax()], y[ok][rel.argmax()])
+    assert (np.abs(got[near & ok] - want[near & ok]) / np.maximum(np.abs(want[near & ok]), 1e-2)).max() <= 1e-10
+    for xx, yy, v in kat["kat2"]:
+        assert abs(float(edb.lnbeta(xx, yy)) - v) <= 1e-13 * abs(v), (xx, yy)
+
+
+def test_shape_parameter_next_to_minus_one(edb, refvec2):
+    """expected -> 1 with a huge phi puts a1 within 0.015 of -1: the reference evaluates lngamma_sgn_sing for it, then
+    rejects the sign (Gamma < 0 on (-1, 0): src/beta.c:43-45) — every such cell is NaN there, and must be here."""
+    r = refvec2
+    got = edb.get_loglike_matrix(r["negint_phi"], r["negint_expected"], r["negint_total"], r["negint_observed"], 1.0)
+    assert np.isnan(r["negint_ll"]).all() and np.isnan(got).all()
+
+
+def test_exomecount_leave_one_out_through_the_cohort_path(edb, exomecount, refvec2):
+    """BASELINE config 1 through the BATCHED path: the four ExomeCount samples as one cohort, each against its own
+    reference (the other three: ref_stride != 0), one edb200_cohort_run_host call — likelihoods within 1e-10, Viterbi
+    path, call table and CallCNVs columns equal to what the compiled reference + the CallCNVs framing give per sample
+    (R/class_definition.R:354-409; fixture: tools/make_golden_r2.py)."""
+    from exomedepth_b200 import _lib
+    ec, r = exomecount, refvec2
+    names = ["Exome1", "Exome2", "Exome3", "Exome4"]
+    obs = np.stack([ec[nm] for nm in names]).astype(np.int32)
+    ref = np.stack([sum(ec[o] for o in names if o != nm) for nm in names]).astype(np.int32)
+    phi = np.array([float(r[f"loo{s}_phi"][0]) for s in range(4)])
+    exp = np.array([float(r[f"loo{s}_expected"][0]) for s in range(4)])
+    n = obs.shape[1]
+    co = edb.Cohort([0, n], ec["start"], ec["end"], n_states=3)
+    keys = [str(k) for k in r["loo_keys"]]
+    for mode in (_lib.EMISSION_AUTO, _lib.EMISSION_TABLE):
+        res = co.call_cnvs(obs, ref, phi, exp, chromosome_names=["1"], call_cap=256, mode=mode, want_ll=True, want_path=True)
+        for s in range(4):
+            assert_ll_close(res["ll"][s].T, r[f"loo{s}_ll"])
+            assert np.array_equal(res["path"][s], r[f"loo{s}_path"][1:-1]), s
+            want = r[f"loo{s}_calls"]
+            rows = res["CNV_calls"][s]
+            assert len(rows) == want.shape[0], (s, len(rows))
+            for row, w in zip(rows, want):
+                wd = dict(zip(keys, w))
+                assert [row["start_p"], row["end_p"], row["type"], row["nexons"]] == [int(wd["start_p"]), int(wd["end_p"]), int(wd["type"]), int(wd["nexons"])]
+                assert row["start"] == wd["start"] and row["end"] == wd["end"]
+                assert row["reads_expected"] == int(wd["reads_expected"]) and row["reads_observed"] == wd["reads_observed"]
+                assert row["reads_ratio"] == wd["reads_ratio"]
+                # the Bayes factor sums likelihoods that agree to 1e-10 with the reference's: 3 significant digits agree
+                # unless the 4th sits on a rounding edge; the raw sum is compared at 1e-9
+                assert abs(res["call_stats"][s, rows.index(row), 0] - wd["BF_raw"]) <= 1e-9 * abs(wd["BF_raw"])
+                assert row["BF"] == pytest.approx(wd["BF"], rel=2e-3)
+            assert res["cor"][s] == pytest.approx(float(r[f"loo{s}_cor"][0]), rel=1e-12)
+
+
+def test_accuracy_envelope_against_the_reference(edb, refvec2):
+    """Where does 1e-10 hold?  24,000 cells of the compiled reference over phi 1e-5 .. 0.99, expected 0.005 .. 0.97, totals up
+    to 1e5 (SURVEY.md §8d covers phi 5e-4 .. 1e-2, counts of a few hundred).  Asserted: the NaN pattern everywhere; 1e-10
+    relative (1e-12 absolute floor) inside the documented envelope; outside it the deviation is bounded and REPORTED
+    (gpurun_out/envelope.json feeds DESIGN.md) — there the reference's own lnbeta loses digits to cancellation in a1 + a2
+    (SURVEY.md §7 hard part 3), which an independent 50-digit evaluation attributes to the reference, not to this code
+    (tests/test_oracle.py::test_envelope_reference_error_vs_mpmath)."""
+    import json
+    import os
+    r = refvec2
+    phi, e, tot = r["env_phi"], r["env_expected"], r["env_total"]
+    want = r["env_ll"]
+    got = edb.get_loglike_matrix(phi, e, tot, r["env_observed"], 1.0)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = np.isfinite(want).all(1)
+    rel = np.zeros(phi.size)
+    rel[ok] = (np.abs(got[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1e-2)).max(1)
+    report = {}
+    edges = [1e-5, 1e-4, 3e-4, 1e-3, 1e-2, 1e-1, 0.99]
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        for tlo, thi in ((0, 2000), (2000, 20000), (20000, 100001)):
+            m = ok & (phi >= lo) & (phi < hi) & (tot >= tlo) & (tot < thi)
+            if m.any():
+                w = int(np.flatnonzero(m)[rel[m].argmax()])
+                report[f"phi[{lo:g},{hi:g}) total[{tlo},{thi})"] = dict(
+                    cells=int(m.sum()), max_rel=float(rel[m].max()),
+                    worst=dict(phi=float(phi[w]), expected=float(e[w]), total=int(tot[w]), observed=int(r["env_observed"][w]),
+                               got=[float(v) for v in got[w]], reference=[float(v) for v in want[w]]))
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(report, open("gpurun_out/envelope.json", "w"), indent=1)
+    # Measured (profiles/r2c_envelope.json): <= 3.3e-11 for 3e-4 <= phi < 0.1 at every total up to 1e5 — the envelope in which
+    # 1e-10 is asserted; it covers every fit the reference's data and SURVEY.md §8d produce (phi 5e-4 .. 1e-2).  Outside:
+    # up to 1.8e-9 for phi < 3e-4 on bins with a few reads, where the reference's own lnbeta difference is 5e-11 off the
+    # 50-digit value (test_envelope_reference_error_vs_mpmath), and 1.7e-10 for phi >= 0.1 with thousands of reads.
+    inside = ok & (phi >= 3e-4) & (phi < 0.1)
+    assert inside.sum() > 10000
+    assert rel[inside].max() <= 1e-10, max(report.items(), key=lambda kv: kv[1]["max_rel"])
+    assert rel[ok].max() <= 1e-8, max(report.items(), key=lambda kv: kv[1]["max_rel"])

@@ -159,3 +159,49 @@ def test_forward_loglik_bounds_viterbi(port):
     ll = -rng.exponential(3, (50, 3))
     fw = port.forward_loglik(T, ll, np.arange(50, dtype=np.int32), 1.0)
     assert abs(fw - ll[1:, 0].sum()) < 1e-10
+
+
+# ---------------------------------------------------------------- round-2 vectors (tools/make_golden_r2.py)
+def test_round2_vectors_match_the_port(port, refvec2):
+    """Leave-one-out ExomeCount, the parameter envelope and the a1 ~ -1 rows: the C restatement reproduces the compiled
+    reference's likelihood matrices bit for bit (NaN cells included) and, through the CallCNVs framing, its paths and calls."""
+    r = refvec2
+    for pre in ("env", "negint"):
+        got = port.get_loglike_matrix(r[f"{pre}_phi"], r[f"{pre}_expected"], r[f"{pre}_total"], r[f"{pre}_observed"], 1.0)
+        assert same(got, r[f"{pre}_ll"]), pre
+    assert np.isnan(r["negint_ll"]).all()
+    ec = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "exomecount.npz"))
+    names = ["Exome1", "Exome2", "Exome3", "Exome4"]
+    n = ec["start"].size
+    for s, nm in enumerate(names):
+        test = ec[nm].astype(float)
+        reference = sum(ec[o].astype(float) for o in names if o != nm)
+        phi, e = float(r[f"loo{s}_phi"][0]), float(r[f"loo{s}_expected"][0])
+        ll = port.get_loglike_matrix(np.full(n, phi), np.full(n, e), (test + reference).astype(np.int32), test.astype(np.int32), 1.0)
+        assert same(ll, r[f"loo{s}_ll"])
+        res = framing.call_cnvs(ll, test, reference, np.full(n, e), ["chr1"] * n, ec["start"], ec["end"], port.c_hmm)
+        assert np.array_equal(res["paths"]["chr1"], r[f"loo{s}_path"])
+        assert len(res["calls"]) == r[f"loo{s}_calls"].shape[0] > 20
+
+
+def test_envelope_reference_error_vs_mpmath(refvec2):
+    """Who is off where the GPU path and the reference disagree by more than 1e-10?  A 50-digit evaluation of
+    ln B(a1+k, a2+n-k) - ln B(a1, a2) with the reference's own a1, a2: for small phi (a1 + a2 in the tens of thousands)
+    the REFERENCE's lnbeta differences carry 1e-11 .. 1e-10 relative errors on bins with a handful of reads — its 1e-16
+    roundings act on lnbeta terms of magnitude 1e5 that cancel down to a result of magnitude 1 (SURVEY.md §7 hard part 3);
+    with thousands of reads the result is large and the relative error drops below 1e-13."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    r = refvec2
+    phi, e, tot, obs, ll = r["env_phi"], r["env_expected"], r["env_total"], r["env_observed"], r["env_ll"]
+    pick = np.flatnonzero((phi < 1e-4) & (tot > 0) & (tot <= 20) & np.isfinite(ll).all(1))[:80]
+    assert pick.size >= 40
+    worst = 0.0
+    for i in pick:
+        sd2 = phi[i] * e[i] * (1 - e[i])                       # src/CNV_estimate.cpp:73 (normal state: odds 1)
+        a1 = e[i] * e[i] * (1 - e[i]) / sd2 - e[i]             # :45
+        a2 = (1 - e[i]) / e[i] * a1                            # :46
+        x, y = mp.mpf(a1) + int(obs[i]), mp.mpf(a2) + int(tot[i] - obs[i])
+        exact = (mp.loggamma(x) + mp.loggamma(y) - mp.loggamma(x + y)) - (mp.loggamma(a1) + mp.loggamma(a2) - mp.loggamma(mp.mpf(a1) + mp.mpf(a2)))
+        worst = max(worst, abs(float((mp.mpf(ll[i, 1]) - exact) / exact)))
+    assert 1e-11 < worst < 1e-8, worst        # the reference itself is not a 1e-10 oracle out there

@@ -192,3 +192,64 @@ def test_cuda_device_stages_match_the_host_call():
     sel, cor = shard.refset_sweep(counts, 21, bl, 0, None, device=torch.device("cuda:0"))
     want = refset.cohort_reference_ranking(counts, bl)
     assert np.array_equal(sel, want["selected"]) and np.array_equal(cor, want["correlations"])
+
+
+# ---- two ranks on the GPU box: the sharded sweep with the exchange fused into the Gram kernel (CUDA IPC) ----------------
+def _gpu_worker(rank, world, port_no, n_total, nccl, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    import torch
+    import torch.distributed as dist
+
+    import exomedepth_b200 as edb
+    from exomedepth_b200 import shard, synth
+    local = rank if nccl else 0                                 # one GPU: both ranks share it (IPC works within a device too)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    edb.init(local)
+    if nccl:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = synth.cohort(8, n_bins=12000)
+    rng = np.random.default_rng(3)
+    counts = np.stack([rng.binomial(d["observed"][s % 8], 0.5 + 0.5 * rng.random()) for s in range(n_total)]).astype(np.int32)
+    bl = (d["end"] - d["start"] + 1).astype(float)
+    lo, hi = shard.shard_range(n_total, rank, world)
+    out = {}
+    for fused in ((True, False) if nccl else (True,)):        # the all-gather form needs NCCL (one GPU per rank)
+        sel, cor = shard.refset_sweep(counts[lo:hi], n_total, bl, 0, dist, device=dev if nccl or fused else None, fused=fused)
+        out[fused] = cor
+    blocks = [None] * world
+    dist.all_gather_object(blocks, (lo, out))
+    if rank == 0:
+        q.put((counts, sel, bl, sorted(blocks, key=lambda b: b[0])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_cuda_sharded_sweep_two_ranks_fused_exchange():
+    """The multi-GPU form of the sweep inside `pytest -m gpu`: two processes, every rank standardises its block, the Gram
+    kernel reads the other rank's rows through CUDA IPC (no all-gather pass); with two GPUs also the NCCL all-gather form.
+    Either way the assembled matrix equals the single-process matrix bit for bit (K-slices depend on K only)."""
+    import torch
+    import torch.multiprocessing as mp
+
+    from exomedepth_b200 import refset
+    nccl = torch.cuda.device_count() >= 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = _free_port()
+    n_total = 37
+    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port_no, n_total, nccl, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    counts, sel, bl, blocks = q.get(timeout=600)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    want = refset.correlations(counts, sel, bl)
+    for fused in blocks[0][1]:
+        full = np.vstack([b[1][fused] for b in blocks])
+        assert np.array_equal(full, want), fused
