@@ -375,17 +375,21 @@ def gpu_arm(a, rank, world):
         hb = _lib.PinnedPool()
         obs_p = hb.empty((ns, nb), np.int32)
         obs_p[:] = obs_h
+        # the ingestion layout (edb200_batch.observed16): 16-bit counts + overflow list, written once per cohort by the loader
+        obs16_p, ovf_i, ovf_v = edb.pack_counts(obs_h, out=hb.empty((ns, nb), np.uint16))
         base = dict(calls=hb.empty((ns, cap, 4), np.int32), ncalls=hb.empty((ns,), np.int32),
                     call_stats=hb.empty((ns, cap, 3), np.float64), cor=hb.empty((ns,), np.float64))
         n_e2e = max(2, min(a.steps, 10))
-        h2d = obs_p.nbytes + ref.nbytes + phi_h.nbytes + exp_h.nbytes
+        h2d = obs16_p.nbytes + ovf_i.nbytes + ovf_v.nbytes + ref.nbytes + phi_h.nbytes + exp_h.nbytes
 
-        def timed(out, **kw):
-            co.run_host(obs_p, ref, phi_h, exp_h, call_cap=cap, out=out, want_stats=True, **kw)     # warm-up (allocations)
+        def timed(out, counts=None, **kw):
+            counts = obs16_p if counts is None else counts
+            ovf = (ovf_i, ovf_v) if counts is obs16_p else None
+            co.run_host(counts, ref, phi_h, exp_h, call_cap=cap, out=out, want_stats=True, overflow=ovf, **kw)     # warm-up (allocations)
             barrier()
             t0 = time.perf_counter()
             for _ in range(n_e2e):
-                co.run_host(obs_p, ref, phi_h, exp_h, call_cap=cap, out=out, want_stats=True, **kw)
+                co.run_host(counts, ref, phi_h, exp_h, call_cap=cap, out=out, want_stats=True, overflow=ovf, **kw)
             barrier()
             t = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
             if dist:
@@ -396,9 +400,12 @@ def gpu_arm(a, rank, world):
 
         e2e = timed(base, want_ll=False, want_path=False)
         e2e.update(h2d_bytes_per_step=int(h2d), steps=n_e2e,
+                   counts_layout=f"uint16 [sample][bin] + overflow list ({int(ovf_i.size)} entries) — edb200_batch.observed16",
                    api="edb200_cohort_run_host (C ABI, pinned host buffers): counts in; CNV call table, per-call BF / reads.expected / "
                        "reads.observed sums and cor(test, reference) out — the output of CallCNVs; likelihood matrix resident in HBM; "
                        "chromosome groups pipelined over PCIe (upload | emission | Viterbi)")
+        e2e["int32_counts"] = dict(timed(base, counts=obs_p, want_ll=False, want_path=False), h2d_bytes_per_step=int(obs_p.nbytes + ref.nbytes + phi_h.nbytes + exp_h.nbytes),
+                                   note="the same call with the counts as int32 [sample][bin] (edb200_batch.observed)")
         with_path = dict(base, path=hb.empty((ns, nb), np.int8))
         e2e["with_path"] = dict(timed(with_path, want_ll=False, want_path=True), note="+ per-bin Viterbi path (int8) copied back")
         if not a.no_ll:

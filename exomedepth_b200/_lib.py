@@ -45,7 +45,9 @@ class Batch(C.Structure):
                 ("reference", C.c_void_p), ("ref_stride", C.c_int64), ("phi", C.c_void_p),
                 ("expected", C.c_void_p), ("ll", C.c_void_p), ("ll_stride", C.c_int64), ("path", C.c_void_p),
                 ("path_stride", C.c_int64), ("calls", C.c_void_p), ("ncalls", C.c_void_p), ("call_cap", C.c_int32),
-                ("call_stats", C.c_void_p), ("cor", C.c_void_p)]
+                ("call_stats", C.c_void_p), ("cor", C.c_void_p),
+                ("observed16", C.c_void_p), ("obs16_stride", C.c_int64), ("n_overflow", C.c_int64),
+                ("overflow_index", C.c_void_p), ("overflow_value", C.c_void_p)]
 
 
 _lib = None

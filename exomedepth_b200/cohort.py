@@ -13,6 +13,22 @@ def _ptr(a):
     return a.ctypes.data if a is not None else None
 
 
+def pack_counts(observed, out=None):
+    """The 16-bit ingestion layout of a count matrix (include/exomedepth_b200.h, edb200_batch.observed16): returns
+    (uint16[n_samples, n_bins] with 65535 = "see the overflow list", int64 flat indices sample * n_bins + bin, int32 values).
+    `out`: an existing uint16 array (e.g. pinned) to fill.  This is the layout a loader writes ONCE per cohort
+    (R/countBamInGranges.R:356-369 produces the counts); it halves the bytes every later call moves over PCIe."""
+    observed = np.asarray(observed)
+    if observed.min(initial=0) < 0:
+        raise ValueError("negative read count")
+    big = observed >= 65535
+    idx = np.flatnonzero(big.ravel()).astype(np.int64)
+    val = observed.ravel()[idx].astype(np.int32)
+    u16 = out if out is not None else np.empty(observed.shape, np.uint16)
+    np.minimum(observed, 65535, out=u16, casting="unsafe")
+    return u16, idx, val
+
+
 class DeviceGraph:
     """A captured device-resident batch (Cohort.capture_device).  Holds the tensors it was captured over."""
 
@@ -91,15 +107,21 @@ class Cohort:
 
     # ---- host buffers ---------------------------------------------------------------------------
     def run_host(self, observed, reference, phi, expected, want_ll=True, want_path=True, call_cap=512,
-                 mode=_lib.EMISSION_AUTO, out=None, want_stats=False):
-        """observed int32[n_samples, n_bins]; reference int32[n_bins] (shared) or [n_samples, n_bins];
+                 mode=_lib.EMISSION_AUTO, out=None, want_stats=False, overflow=None):
+        """observed int32[n_samples, n_bins] — or uint16 in the ingestion layout of pack_counts, with overflow = (flat indices,
+        values) of the counts that do not fit 16 bits; reference int32[n_bins] (shared) or [n_samples, n_bins];
         phi, expected float64[n_samples].  Returns dict(ll [n,S,bins], path int8 [n,bins], calls, ncalls, status);
         with want_stats also call_stats float64[n, call_cap, 3] (per call: sum of ll[,type] - ll[,normal],
         sum of total*expected, sum of test; R/class_definition.R:393-400) and cor float64[n] (:338), both computed
         on the device — the likelihood matrix then only crosses PCIe if want_ll is set."""
-        observed = np.ascontiguousarray(np.asarray(observed, np.int32))
+        u16 = np.asarray(observed).dtype == np.uint16
+        observed = np.ascontiguousarray(np.asarray(observed, np.uint16 if u16 else np.int32))
         reference = np.ascontiguousarray(np.asarray(reference, np.int32))
         ns = observed.shape[0]
+        ovf_i = ovf_v = None
+        if u16 and overflow is not None and len(overflow[0]):
+            ovf_i = np.ascontiguousarray(np.asarray(overflow[0], np.int64))
+            ovf_v = np.ascontiguousarray(np.asarray(overflow[1], np.int32))
         phi = np.ascontiguousarray(np.broadcast_to(np.asarray(phi, np.float64), (ns,)))
         expected = np.ascontiguousarray(np.broadcast_to(np.asarray(expected, np.float64), (ns,)))
         S, nb = self.n_states, self.n_bins
@@ -125,9 +147,10 @@ class Cohort:
             cor = out.get("cor")
             if cor is None:
                 cor = np.zeros(ns)
-        b = _lib.Batch(ns, _ptr(observed), nb, _ptr(reference), 0 if reference.ndim == 1 else nb, _ptr(phi),
+        b = _lib.Batch(ns, None if u16 else _ptr(observed), nb, _ptr(reference), 0 if reference.ndim == 1 else nb, _ptr(phi),
                        _ptr(expected), _ptr(ll), nb, _ptr(path), nb, _ptr(calls), _ptr(ncalls), call_cap,
-                       _ptr(stats), _ptr(cor))
+                       _ptr(stats), _ptr(cor), _ptr(observed) if u16 else None, nb, 0 if ovf_i is None else ovf_i.size,
+                       _ptr(ovf_i), _ptr(ovf_v))
         rc = _lib.check(self.lib.edb200_cohort_run_host(self.handle, C.byref(b), mode), "edb200_cohort_run_host")
         self._last_ns = ns
         return dict(ll=ll, path=path, calls=calls, ncalls=ncalls, status=rc, call_stats=stats, cor=cor)

@@ -180,4 +180,69 @@ int launch_call_summary(const CallSummaryArgs& a, cudaStream_t st)
     return launches;
 }
 
+// ---- count ingestion: 16-bit counts + overflow list -> the int32 rows the kernels read ---------------
+// Exome read counts per bin fit 16 bits except for a handful of bins per sample: the ingestion layout is uint16
+// [sample][bin] with 65535 standing for "see the overflow list" (sorted flat indices sample * n_bins + bin, int32 values).
+// It halves the bytes that cross PCIe per sample; the device widens the columns of one chromosome group right behind
+// their upload, on the copy stream.
+__global__ void __launch_bounds__(256)
+widen_counts_kernel(const uint16_t* __restrict__ src, int64_t src_stride, int32_t* __restrict__ dst, int64_t dst_stride, int n_samples,
+                    const __grid_constant__ BinRanges rg)
+{
+    const int sample = blockIdx.y;
+    const uint16_t* __restrict__ s = src + sample * src_stride;
+    int32_t* __restrict__ d = dst + sample * dst_stride;
+    const bool vec = ((reinterpret_cast<uintptr_t>(s) | (uintptr_t)(src_stride * 2)) & 15) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(d) | (uintptr_t)(dst_stride * 4)) & 15) == 0;
+    for (int q = 0; q < rg.n; q++) {
+        const int64_t b0 = rg.b0[q], b1 = rg.b1[q];
+        const int64_t n8 = vec && (b0 & 7) == 0 ? b0 + ((b1 - b0) & ~(int64_t)7) : b0;
+        for (int64_t b = b0 + (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 8; b < n8; b += (int64_t)gridDim.x * blockDim.x * 8) {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(s + b));
+            reinterpret_cast<int4*>(d + b)[0] = make_int4((int)(v.x & 0xFFFFu), (int)(v.x >> 16), (int)(v.y & 0xFFFFu), (int)(v.y >> 16));
+            reinterpret_cast<int4*>(d + b)[1] = make_int4((int)(v.z & 0xFFFFu), (int)(v.z >> 16), (int)(v.w & 0xFFFFu), (int)(v.w >> 16));
+        }
+        for (int64_t b = n8 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < b1; b += (int64_t)gridDim.x * blockDim.x) d[b] = s[b];
+    }
+}
+
+__global__ void patch_overflow_kernel(const int64_t* __restrict__ index, const int32_t* __restrict__ value, int64_t n_overflow, int64_t n_bins,
+                                      int32_t* __restrict__ dst, int64_t dst_stride, const __grid_constant__ BinRanges rg)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_overflow) return;
+    const int64_t sample = index[i] / n_bins, b = index[i] - sample * n_bins;
+    for (int q = 0; q < rg.n; q++)
+        if (b >= rg.b0[q] && b < rg.b1[q]) dst[sample * dst_stride + b] = value[i];
+}
+
+int launch_widen_counts(const uint16_t* src, int64_t src_stride, int32_t* dst, int64_t dst_stride, int n_samples, int64_t n_bins,
+                        const BinRanges& rg, const int64_t* ovf_index, const int32_t* ovf_value, int64_t n_overflow, cudaStream_t st)
+{
+    if (n_samples == 0 || rg.n == 0) return 0;
+    int64_t width = 0;
+    for (int q = 0; q < rg.n; q++) width += rg.b1[q] - rg.b0[q];
+    int bx = (int)((width / 8 + 255) / 256);
+    bx = bx < 1 ? 1 : bx > 64 ? 64 : bx;
+    prof_mark("widen_counts", st);
+    widen_counts_kernel<<<dim3((unsigned)bx, (unsigned)n_samples), 256, 0, st>>>(src, src_stride, dst, dst_stride, n_samples, rg);
+    int launches = 1;
+    if (n_overflow > 0) {
+        // (dst is row 0 of the batch here: the list's flat indices are absolute)
+        patch_overflow_kernel<<<(unsigned)((n_overflow + 127) / 128), 128, 0, st>>>(ovf_index, ovf_value, n_overflow, n_bins, dst, dst_stride, rg);
+        launches++;
+    }
+    prof_mark(nullptr, st);
+    return launches;
+}
+
+// the overflow entries alone, over the bins of `rg` (dst = row 0 of the batch)
+int launch_patch_overflow(int32_t* dst, int64_t dst_stride, int64_t n_bins, const BinRanges& rg, const int64_t* ovf_index,
+                          const int32_t* ovf_value, int64_t n_overflow, cudaStream_t st)
+{
+    if (n_overflow <= 0) return 0;
+    patch_overflow_kernel<<<(unsigned)((n_overflow + 127) / 128), 128, 0, st>>>(ovf_index, ovf_value, n_overflow, n_bins, dst, dst_stride, rg);
+    return 1;
+}
+
 }  // namespace edb

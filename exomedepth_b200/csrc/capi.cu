@@ -269,7 +269,7 @@ struct edb200_cohort {
     std::vector<edb200_graph*> graphs;   // captured replays of this cohort (invalidated when the cohort goes)
     int last_host_samples = 0;           // samples whose likelihoods the last host-pointer run left in h_ll
     // host-mode staging
-    DevBuf h_obs, h_ref, h_phi, h_exp, h_ll, h_path, h_calls, h_ncalls, h_stats, h_cor;
+    DevBuf h_obs, h_ref, h_phi, h_exp, h_ll, h_path, h_calls, h_ncalls, h_stats, h_cor, h_obs16, h_ovf_i, h_ovf_v;
 };
 
 extern "C" {
@@ -763,7 +763,8 @@ void edb200_cohort_destroy(edb200_cohort* c)
             release(part.sched_items);
         }
     DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->tile_base, &c->decay, &c->srows, &c->fw_grid, &c->fw_chain, &c->fw_out, &c->fw_best, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->lattices,
-                     &c->h_obs, &c->h_ref, &c->h_phi, &c->h_exp, &c->h_ll, &c->h_path, &c->h_calls, &c->h_ncalls, &c->h_stats, &c->h_cor};
+                     &c->h_obs, &c->h_ref, &c->h_phi, &c->h_exp, &c->h_ll, &c->h_path, &c->h_calls, &c->h_ncalls, &c->h_stats, &c->h_cor,
+                     &c->h_obs16, &c->h_ovf_i, &c->h_ovf_v};
     for (DevBuf* b : all) release(*b);
     delete c;
 }
@@ -837,7 +838,9 @@ static int ensure_struct(edb200_cohort* c)
 static int build_plan(edb200_cohort* c, int n_parts)
 {
     static const double kCuts[Context::kMaxParts + 1][Context::kMaxParts] = {
-        {}, {1.0}, {0.45, 1.0}, {0.35, 0.7, 1.0}, {0.3, 0.6, 0.85, 1.0}, {0.25, 0.5, 0.75, 0.9, 1.0}, {0.25, 0.5, 0.7, 0.85, 0.95, 1.0}};
+        {}, {1.0}, {0.45, 1.0}, {0.35, 0.7, 1.0}, {0.3, 0.6, 0.85, 1.0}, {0.25, 0.5, 0.75, 0.9, 1.0}, {0.09, 0.28, 0.5, 0.7, 0.88, 1.0}};
+    // (6 parts: the longest chromosome on its own — its sweep is the longest dependent chain of the batch and can start as soon
+    // as a tenth of the counts has arrived)
     std::vector<edb200_cohort::Part>& plan = c->plans[n_parts];
     if (!plan.empty()) return 0;
     std::vector<int> order(c->n_chains);
@@ -917,8 +920,9 @@ static int pick_parts(const edb200_cohort* c, int mode, int wanted)
 // lattice_mode: 0 = one launch covers the batch; 1 = first part of a pipelined batch (keeps the lattices in HBM);
 // 2 = later part (reloads them)
 static int emission_part(edb200_cohort* c, const edb200_batch* b, const edb::BinRanges& rg, bool whole, int mode, int lattice_mode,
-                         cudaStream_t st)
+                         cudaStream_t st, int n_sms = 0)
 {
+    if (n_sms <= 0 || n_sms > g.n_sms) n_sms = g.n_sms;
     const int S = c->S, ns = b->n_samples;
     edb::CountsView cv{b->observed, b->obs_stride, b->reference, b->ref_stride, 0};
     edb::LLView out{b->ll, (int64_t)S * b->ll_stride, b->ll_stride};
@@ -932,7 +936,7 @@ static int emission_part(edb200_cohort* c, const edb200_batch* b, const edb::Bin
         if (lattice_mode)
             if (int rc = ensure(c->lattices, (size_t)ns * S * (kTableK + 2 * kTableRN) * 8)) return rc;
         edb::prof_mark(panel ? "emission_panel" : "emission", st);
-        edb::launch_emission_table(cv, consts, ns, S, rg, d, out, g.d_flags, g.d_queue, g.n_sms, (double*)c->lattices.p, lattice_mode, st);
+        edb::launch_emission_table(cv, consts, ns, S, rg, d, out, g.d_flags, g.d_queue, n_sms, (double*)c->lattices.p, lattice_mode, st);
     } else {
         if (!whole) return fail(EDB200_ERR_ARG, "internal: the in-register emission kernel covers whole rows only");
         edb::prof_mark("emission_direct", st);
@@ -1002,7 +1006,7 @@ static int viterbi_prepare(edb200_cohort* c, const edb200_batch* b, edb::Viterbi
     if (int rc = make_ll_map(b->ll, (int64_t)ns * S, b->ll_stride, b->ll_stride, (32 / S) * S, ll_map)) return rc;
     a.ll_map = ll_map;
     a.tpc = use_tpc(c, ns) ? 1 : 0;
-    if (a.tpc) {
+    if (c->struct_state == 1 && c->opt_sweep != 1) {
         if (int rc = make_ll_map(b->ll, (int64_t)ns * S, b->ll_stride, b->ll_stride, 32 * S, ll_map + 1)) return rc;
         a.ll_map_tpc = ll_map + 1;
         a.srows = (const edb::StructRow*)c->srows.p;
@@ -1041,12 +1045,17 @@ static int crit_warps(const edb200_cohort* c)
 // memory, so does an emission CTA): its CTAs are filled instead of spread over all SMs — 1: one warp per SM
 // sub-partition, which keeps the long chains of the first part at full speed; 2: two per sub-partition (shorter chains,
 // half the SMs).
-static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiArgs a, int packed, cudaStream_t st, int avail_sms = 0)
+static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiArgs a, int packed, cudaStream_t st, int avail_sms = 0,
+                        int tpc_warps = 0)
 {
     if (avail_sms <= 0 || avail_sms > g.n_sms) avail_sms = g.n_sms;
+    // tpc_warps > 0: a pipelined part — the one-thread-per-chain sweep (when the table allows it) with that many warps per
+    // CTA: it needs 32/S times fewer warps, hence SMs, than the lane-per-state sweep, and the SMs are what the emission of
+    // the next chromosome group is waiting for
+    if (tpc_warps > 0 && c->struct_state == 1 && c->opt_sweep != 1 && a.srows) a.tpc = 1;
     // thread-per-chain sweep: work items are (chain, 32 samples); lane-per-state sweep: (chain, 32/S samples)
     const int sched_groups = a.tpc ? (a.n_samples + 31) / 32 : a.groups;
-    const int key = sched_groups * 2 + a.tpc;
+    const int key = (sched_groups * 2 + a.tpc) * 8 + tpc_warps;
     if (pt.sched_groups != key || pt.sched_avail != avail_sms) {
         std::vector<int32_t> nobs(pt.chains.size());
         for (size_t i = 0; i < pt.chains.size(); i++) nobs[i] = c->chains_h[pt.chains[i]].nobs;
@@ -1056,7 +1065,7 @@ static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiA
             // one sweep warp per SM sub-partition; as few warps per CTA as place the items on the available SMs, because
             // the CTA's shared memory is split between its warps' rings (the fewer, the deeper)
             const int max_w = edb::viterbi_tpc_max_warps(a.n_states);
-            int w = c->opt_sweep_warps > 0 ? c->opt_sweep_warps : (int)((n_items + avail_sms - 1) / avail_sms);
+            int w = c->opt_sweep_warps > 0 ? c->opt_sweep_warps : tpc_warps > 0 ? tpc_warps : (int)((n_items + avail_sms - 1) / avail_sms);
             pt.sched_warps = w < 1 ? 1 : w > max_w ? max_w : w;
             sched_ctas = (int)std::min<int64_t>(avail_sms, (n_items + pt.sched_warps - 1) / pt.sched_warps);
         } else {
@@ -1378,6 +1387,17 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     if ((rc = build_plan(c, n_parts))) return rc;
     std::vector<edb200_cohort::Part>& plan = c->plans[n_parts];
 
+    // 16-bit ingestion layout: the overflow list goes up once, every group's columns are widened behind their upload
+    const bool u16 = b->observed16 != nullptr;
+    if (u16) {
+        if (b->obs16_stride < nb || b->n_overflow < 0 || (b->n_overflow > 0 && (!b->overflow_index || !b->overflow_value)))
+            return fail(EDB200_ERR_ARG, "bad 16-bit count layout (stride / overflow list)");
+        if ((rc = ensure(c->h_obs16, (size_t)ns * nb * 2)) || (rc = ensure(c->h_ovf_i, (size_t)b->n_overflow * 8 + 8)) ||
+            (rc = ensure(c->h_ovf_v, (size_t)b->n_overflow * 4 + 8)))
+            return rc;
+    } else if (!b->observed)
+        return fail(EDB200_ERR_ARG, "no test counts in batch (observed or observed16)");
+
     if (plan.size() > 1) {
         // ---- chromosome-group pipeline over PCIe: the counts of the long chromosomes go up first; their emission and
         // sweep (the critical path) run while the other groups are still uploading; results drain per group.
@@ -1388,22 +1408,39 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         if (shared_ref) CU(cudaMemcpyAsync(c->h_ref.p, b->reference, nb * 4, cudaMemcpyHostToDevice, sc));
         CU(cudaMemcpyAsync(c->h_phi.p, b->phi, ns * 8, cudaMemcpyHostToDevice, sc));
         CU(cudaMemcpyAsync(c->h_exp.p, b->expected, ns * 8, cudaMemcpyHostToDevice, sc));
+        if (u16 && b->n_overflow > 0) {
+            CU(cudaMemcpyAsync(c->h_ovf_i.p, b->overflow_index, (size_t)b->n_overflow * 8, cudaMemcpyHostToDevice, sc));
+            CU(cudaMemcpyAsync(c->h_ovf_v.p, b->overflow_value, (size_t)b->n_overflow * 4, cudaMemcpyHostToDevice, sc));
+        }
         CU(cudaEventRecord(g.ev_setup, sc));
         CU(cudaStreamWaitEvent(g.s_em, g.ev_setup, 0));
         if ((rc = state_setup(c, &d, g.s_em))) return rc;
+        // SM budget.  With the one-thread-per-chain sweep the Viterbi work of the whole batch is (samples / 32 / 2 warps per CTA)
+        // x bins x ~104 ns of SM time, the uploads take samples x bins x bytes / ~53 GB/s: their ratio — the SMs the sweeps
+        // need in order to finish with the uploads — does not depend on the batch: ~44 for 16-bit counts, ~22 for 32-bit.
+        // The emission launches of the later groups leave that many SMs alone (an emission CTA and a sweep CTA both own their
+        // SM's shared memory; emission CTAs are persistent over the launch, so sweep CTAs launched behind them would wait).
+        const bool tpc_parts = c->struct_state == 1 && c->opt_sweep != 1;
+        const int reserve = !tpc_parts ? 0 : std::min(g.n_sms / 3, u16 ? 44 : 22);
         for (size_t p = 0; p < plan.size(); p++) {
             const edb::BinRanges& rg = plan[p].ranges;
             edb::prof_mark("h2d_counts", sc);
             for (int q = 0; q < rg.n; q++) {
                 const int64_t r0 = rg.b0[q], w = rg.b1[q] - r0;
-                CU(cudaMemcpy2DAsync((int32_t*)c->h_obs.p + r0, nb * 4, b->observed + r0, b->obs_stride * 4, w * 4, ns, cudaMemcpyHostToDevice, sc));
+                if (u16)
+                    CU(cudaMemcpy2DAsync((uint16_t*)c->h_obs16.p + r0, nb * 2, b->observed16 + r0, b->obs16_stride * 2, w * 2, ns, cudaMemcpyHostToDevice, sc));
+                else
+                    CU(cudaMemcpy2DAsync((int32_t*)c->h_obs.p + r0, nb * 4, b->observed + r0, b->obs_stride * 4, w * 4, ns, cudaMemcpyHostToDevice, sc));
                 if (!shared_ref)
                     CU(cudaMemcpy2DAsync((int32_t*)c->h_ref.p + r0, nb * 4, b->reference + r0, b->ref_stride * 4, w * 4, ns, cudaMemcpyHostToDevice, sc));
             }
             edb::prof_mark(nullptr, sc);
+            if (u16)
+                g_launches += edb::launch_widen_counts((const uint16_t*)c->h_obs16.p, nb, (int32_t*)c->h_obs.p, nb, ns, nb, rg,
+                                                       (const int64_t*)c->h_ovf_i.p, (const int32_t*)c->h_ovf_v.p, b->n_overflow, sc);
             CU(cudaEventRecord(g.ev_copy[p], sc));
             CU(cudaStreamWaitEvent(g.s_em, g.ev_copy[p], 0));
-            if ((rc = emission_part(c, &d, rg, false, emission_mode, p == 0 ? 1 : 2, g.s_em))) return rc;
+            if ((rc = emission_part(c, &d, rg, false, emission_mode, p == 0 ? 1 : 2, g.s_em, p == 0 ? g.n_sms : g.n_sms - reserve))) return rc;
             CU(cudaEventRecord(g.ev_em[p], g.s_em));
             if (b->ll) {
                 CU(cudaStreamWaitEvent(g.stream2, g.ev_em[p], 0));
@@ -1421,7 +1458,9 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
                 snprintf(pp, sizeof pp, "%d", c->opt_packplan);
                 if (strlen(pp) > p) pack = pp[p] - '0';
             }
-            if ((rc = viterbi_part(c, plan[p], va, pack, g.s_vit[p]))) return rc;
+            // the first group (the longest chains) keeps the lane-per-state sweep, two warps per CTA: ~150 instead of ~205 cycles
+            // per step of the chain everything else waits for; the other groups take the thread-per-chain sweep
+            if ((rc = viterbi_part(c, plan[p], va, pack, g.s_vit[p], 0, tpc_parts && p > 0 ? 2 : 0))) return rc;
             if (b->path)
                 for (int q = 0; q < rg.n; q++) {
                     const int64_t r0 = rg.b0[q], w = rg.b1[q] - r0;
@@ -1456,8 +1495,25 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         }
         for (int k = 0, s0 = 0; s0 < ns; k++, s0 += per) {
             const int cnt = ns - s0 < per ? ns - s0 : per;
-            CU(cudaMemcpy2DAsync((int32_t*)c->h_obs.p + (size_t)s0 * nb, nb * 4, b->observed + (size_t)s0 * b->obs_stride, b->obs_stride * 4,
-                                 nb * 4, cnt, cudaMemcpyHostToDevice, st));
+            if (u16) {
+                CU(cudaMemcpy2DAsync((uint16_t*)c->h_obs16.p + (size_t)s0 * nb, nb * 2, b->observed16 + (size_t)s0 * b->obs16_stride, b->obs16_stride * 2,
+                                     nb * 2, cnt, cudaMemcpyHostToDevice, st));
+                if (k == 0 && b->n_overflow > 0) {
+                    CU(cudaMemcpyAsync(c->h_ovf_i.p, b->overflow_index, (size_t)b->n_overflow * 8, cudaMemcpyHostToDevice, st));
+                    CU(cudaMemcpyAsync(c->h_ovf_v.p, b->overflow_value, (size_t)b->n_overflow * 4, cudaMemcpyHostToDevice, st));
+                }
+                edb::BinRanges all{};
+                all.n = 1;
+                all.b0[0] = 0;
+                all.b1[0] = nb;
+                g_launches += edb::launch_widen_counts((const uint16_t*)c->h_obs16.p + (size_t)s0 * nb, nb, (int32_t*)c->h_obs.p + (size_t)s0 * nb, nb, cnt, nb, all,
+                                                       nullptr, nullptr, 0, st);
+                // the overflow entries of every sample, after every chunk: rows not yet uploaded are overwritten by their own widen
+                // pass and patched again then (the entries are idempotent)
+                g_launches += edb::launch_patch_overflow((int32_t*)c->h_obs.p, nb, nb, all, (const int64_t*)c->h_ovf_i.p, (const int32_t*)c->h_ovf_v.p, b->n_overflow, st);
+            } else
+                CU(cudaMemcpy2DAsync((int32_t*)c->h_obs.p + (size_t)s0 * nb, nb * 4, b->observed + (size_t)s0 * b->obs_stride, b->obs_stride * 4,
+                                     nb * 4, cnt, cudaMemcpyHostToDevice, st));
             edb200_batch e = d;
             e.n_samples = cnt;
             e.observed = d.observed + (size_t)s0 * nb;

@@ -14,6 +14,7 @@
 //                           ~150 FP64 instructions.  HBM traffic is the algorithmic 4 + 8S bytes per
 //                           bin·sample (the count vector is re-read once per state, from L2).
 #include "kernels.cuh"
+#include "tma_ptx.cuh"
 
 namespace edb {
 
@@ -138,9 +139,10 @@ constexpr int kTableThreads = 1024;
 constexpr int kPanelEntries = 20000;   // lattices with fewer entries in total are built by the shared-index-space scheme (kPanel)
 constexpr int kColdCap = 2048;      // out-of-lattice cells parked per work item before they are drained
 
+constexpr size_t kConstSlot = (sizeof(StateConst) + 15) / 16 * 16;      // the lattices start 16-byte aligned (bulk copies)
 size_t emission_table_smem_bytes(TableDims d)
 {
-    return sizeof(double) * ((size_t)d.K + d.R + d.N) + sizeof(StateConst) + sizeof(int) * (kColdCap + 4);
+    return sizeof(double) * ((size_t)d.K + d.R + d.N) + kConstSlot + sizeof(int) * (kColdCap + 4) + 16;
 }
 
 // Out-of-lattice cells (counts beyond the lattice, inconsistent counts) and whole pathological
@@ -207,12 +209,22 @@ emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StateConst* scp = reinterpret_cast<StateConst*>(smem_raw);
-    double* G1 = reinterpret_cast<double*>(smem_raw + sizeof(StateConst));
+    double* G1 = reinterpret_cast<double*>(smem_raw + kConstSlot);
     double* G2 = G1 + dims.K;
     double* G3 = G2 + dims.R;
     int* cold_n = reinterpret_cast<int*>(G3 + dims.N);
     int* next_item = cold_n + 1;
     int* cold = cold_n + 4;
+    // lattice reloads (lattice_mode 2) arrive as ONE bulk copy per item, completing on this barrier
+    const uint32_t reload_bar = smem_u32(cold + kColdCap) + ((16u - (smem_u32(cold + kColdCap) & 15u)) & 15u);
+    unsigned reload_phase = 0;
+    if (lattice_mode == 2) {
+        if (threadIdx.x == 0) {
+            mbar_init(reload_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
 
     for (;;) {
         __syncthreads();     // previous item's gathers are done before the lattices (and next_item) are overwritten
@@ -237,7 +249,16 @@ emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n
         const int n_lat = dims.K + dims.R + dims.N;
         double* __restrict__ keep = lattices + (int64_t)item * n_lat;
         if (lattice_mode == 2) {
-            for (int i = threadIdx.x; i < n_lat; i += blockDim.x) G1[i] = __ldcs(keep + i);
+            // one bulk copy (cp.async.bulk, the TMA unit) instead of a load / store loop: that loop has one 8-byte load in
+            // flight per thread, ~8 GB/s per SM against the ~1 us latency of HBM, i.e. ~26 us per 213 KB item — and a
+            // pipelined batch reloads every item once per chromosome group (profiles/r2d_e2e_timeline.txt)
+            if (threadIdx.x == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic-proxy accesses to the lattices are done (barrier above)
+                mbar_expect_tx(reload_bar, (unsigned)n_lat * 8u);
+                tma_load_1d(smem_u32(G1), keep, (unsigned)n_lat * 8u, reload_bar);
+            }
+            mbar_wait(reload_bar, reload_phase);
+            reload_phase ^= 1u;
         } else {
             // Every thread owns a short run of consecutive entries: the first one is a full lgamma difference, the
             // following ones use lgamma(x + 1) = lgamma(x) + log(x) — one log and a compensated addition instead of

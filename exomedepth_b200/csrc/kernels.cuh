@@ -174,6 +174,13 @@ struct CallSummaryArgs {
 };
 int launch_call_summary(const CallSummaryArgs& a, cudaStream_t st);   // returns the number of launches
 
+// 16-bit counts (65535 = see the overflow list) -> int32 rows, for the bins of `rg`; returns the number of launches
+int launch_widen_counts(const uint16_t* src, int64_t src_stride, int32_t* dst, int64_t dst_stride, int n_samples, int64_t n_bins,
+                        const BinRanges& rg, const int64_t* ovf_index, const int32_t* ovf_value, int64_t n_overflow, cudaStream_t st);
+
+int launch_patch_overflow(int32_t* dst, int64_t dst_stride, int64_t n_bins, const BinRanges& rg, const int64_t* ovf_index,
+                          const int32_t* ovf_value, int64_t n_overflow, cudaStream_t st);
+
 // ---- select.reference.set correlation sweep (refset.cu) -----------------------------------------------
 // z: [n_samples][k_pad] standardised rows over the selected bins (k_pad = n_sel rounded up to 16, zero padded)
 void launch_refset_standardize(const int32_t* counts, int64_t stride, int n_samples, const double* bin_length,

@@ -154,6 +154,16 @@ typedef struct edb200_batch {
                                        ll[,type] - ll[,normal] (BF before the log10(e) factor and signif),
                                        total*expected (reads.expected before as.integer), test (reads.observed) */
     double        *cor;             /* out double[n_samples]  cor(test, reference) over all bins              */
+    /* Count-matrix ingestion layout (HOST mode only, used instead of `observed` when non-NULL): test
+     * counts as uint16 [n_samples][obs16_stride] with 65535 standing for "see the overflow list", the list being
+     * n_overflow entries sorted by flat index sample * n_bins + bin with their int32 counts.  Exome read counts per bin
+     * fit 16 bits except for a handful of bins, so this halves the bytes that cross PCIe per call; the device widens
+     * every chromosome group right behind its upload.  exomedepth_b200/cohort.py:pack_counts builds it from int32. */
+    const uint16_t *observed16;
+    int64_t        obs16_stride;
+    int64_t        n_overflow;
+    const int64_t *overflow_index;
+    const int32_t *overflow_value;
 } edb200_batch;
 
 /* mode: 0 = auto (full lattice from 106,496 bins; panel lattice from 4,096 bins when samples x states >= 2 x SMs;

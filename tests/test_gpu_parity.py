@@ -831,3 +831,25 @@ def test_accuracy_envelope_against_the_reference(edb, refvec2):
     assert inside.sum() > 10000
     assert rel[inside].max() <= 1e-10, max(report.items(), key=lambda kv: kv[1]["max_rel"])
     assert rel[ok].max() <= 1e-8, max(report.items(), key=lambda kv: kv[1]["max_rel"])
+
+
+def test_16_bit_count_layout_matches_32_bit(edb):
+    """edb200_batch.observed16: uint16 counts + overflow list (counts of 65535 and beyond, incl. exactly 65535) give the
+    same likelihoods, paths, calls and per-call sums as the int32 matrix, through the chromosome-group pipeline and through
+    the sample-chunked single pass."""
+    from exomedepth_b200 import _lib, synth
+    for ns, nb, mode in ((40, 20000, _lib.EMISSION_TABLE), (9, 3000, _lib.EMISSION_AUTO)):
+        d = synth.cohort(ns, n_bins=nb)
+        obs = d["observed"].copy()
+        rng = np.random.default_rng(2)
+        for _ in range(12):                                    # a few bins beyond 16 bits, one exactly at the sentinel
+            obs[rng.integers(ns), rng.integers(obs.shape[1])] = int(rng.integers(65536, 300000))
+        obs[ns // 2, 17] = 65535
+        co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=5)
+        want = co.run_host(obs, d["reference"], d["phi"], d["expected"], call_cap=256, mode=mode, want_stats=True)
+        u16, idx, val = edb.pack_counts(obs)
+        assert idx.size == 13 and u16.dtype == np.uint16
+        got = co.run_host(u16, d["reference"], d["phi"], d["expected"], call_cap=256, mode=mode, want_stats=True, overflow=(idx, val))
+        for k in ("ll", "path", "calls", "ncalls", "call_stats", "cor"):
+            assert np.array_equal(got[k], want[k], equal_nan=True), (ns, k)
+        co.close()
