@@ -179,7 +179,7 @@ struct CallScratch {
 // CUtensorMap of an emission matrix for the Viterbi sweep's 2-D TMA loads: rows = (sample, state) pairs of `cols`
 // doubles (row pitch `pitch` doubles), box = 16 bins x (32/S)*S rows, 128-byte swizzle, zero fill out of bounds.
 // cuTensorMapEncodeTiled is fetched through the runtime (no link-time dependency on libcuda).
-int make_ll_map(const double* ll, int64_t rows, int64_t cols, int64_t pitch, int box_rows, CUtensorMap* out)
+int make_ll_map(const double* ll, int64_t rows, int64_t cols, int64_t pitch, int box_rows, CUtensorMap* out, int box_cols = 16)
 {
     typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -193,10 +193,10 @@ int make_ll_map(const double* ll, int64_t rows, int64_t cols, int64_t pitch, int
     }
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)pitch * 8};
-    const cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ll), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(EDB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): ll %p rows %lld cols %lld pitch %lld", (int)r, (const void*)ll,
                                        (long long)rows, (long long)cols, (long long)pitch);
@@ -1007,7 +1007,7 @@ static int viterbi_prepare(edb200_cohort* c, const edb200_batch* b, edb::Viterbi
     a.ll_map = ll_map;
     a.tpc = use_tpc(c, ns) ? 1 : 0;
     if (c->struct_state == 1 && c->opt_sweep != 1) {
-        if (int rc = make_ll_map(b->ll, (int64_t)ns * S, b->ll_stride, b->ll_stride, 32 * S, ll_map + 1)) return rc;
+        if (int rc = make_ll_map(b->ll, (int64_t)ns * S, b->ll_stride, b->ll_stride, 32 * S, ll_map + 1, 8)) return rc;
         a.ll_map_tpc = ll_map + 1;
         a.srows = (const edb::StructRow*)c->srows.p;
         a.c0 = c->c0;
@@ -1415,13 +1415,14 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         CU(cudaEventRecord(g.ev_setup, sc));
         CU(cudaStreamWaitEvent(g.s_em, g.ev_setup, 0));
         if ((rc = state_setup(c, &d, g.s_em))) return rc;
-        // SM budget.  With the one-thread-per-chain sweep the Viterbi work of the whole batch is (samples / 32 / 2 warps per CTA)
+        // SM budget.  With the one-thread-per-chain sweep the Viterbi work of the whole batch is (samples / 32 / 4 warps per CTA)
         // x bins x ~104 ns of SM time, the uploads take samples x bins x bytes / ~53 GB/s: their ratio — the SMs the sweeps
-        // need in order to finish with the uploads — does not depend on the batch: ~44 for 16-bit counts, ~22 for 32-bit.
+        // need in order to finish with the uploads — does not depend on the batch: ~22 for 16-bit counts, ~11 for 32-bit; the
+        // longest chromosome's lane-per-state sweep (two warps per CTA) takes another 22 at 256 samples.
         // The emission launches of the later groups leave that many SMs alone (an emission CTA and a sweep CTA both own their
         // SM's shared memory; emission CTAs are persistent over the launch, so sweep CTAs launched behind them would wait).
         const bool tpc_parts = c->struct_state == 1 && c->opt_sweep != 1;
-        const int reserve = !tpc_parts ? 0 : std::min(g.n_sms / 3, u16 ? 44 : 22);
+        const int reserve = !tpc_parts ? 0 : std::min(g.n_sms / 3, u16 ? 44 : 33);
         for (size_t p = 0; p < plan.size(); p++) {
             const edb::BinRanges& rg = plan[p].ranges;
             edb::prof_mark("h2d_counts", sc);
@@ -1460,7 +1461,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
             }
             // the first group (the longest chains) keeps the lane-per-state sweep, two warps per CTA: ~150 instead of ~205 cycles
             // per step of the chain everything else waits for; the other groups take the thread-per-chain sweep
-            if ((rc = viterbi_part(c, plan[p], va, pack, g.s_vit[p], 0, tpc_parts && p > 0 ? 2 : 0))) return rc;
+            if ((rc = viterbi_part(c, plan[p], va, pack, g.s_vit[p], 0, tpc_parts && p > 0 ? 4 : 0))) return rc;
             if (b->path)
                 for (int q = 0; q < rg.n; q++) {
                     const int64_t r0 = rg.b0[q], w = rg.b1[q] - r0;

@@ -8,8 +8,8 @@
 // distance-dependent transition terms of an observation are warp-uniform (three doubles, broadcast loads).
 //
 // Warp roles as in viterbi.cu: W sweep warps and one producer warp per CTA; lane w of the producer feeds sweep warp
-// w's ring: per 16-observation tile one 2-D TMA load of the emission tile (box 16 bins x 32*S rows, 128-byte swizzle:
-// a quarter-warp's 128-bit reads of two observations hit 8 distinct 16-byte chunks) and one bulk copy of the tile's 16
+// w's ring: per 8-observation half-tile one 2-D TMA load of the emissions (box 8 bins x 32*S rows, 64-byte swizzle:
+// a quarter-warp's 128-bit reads of two observations hit 8 distinct 16-byte chunks) and one bulk copy of the half's 8
 // StructRows, completing on the stage's `full` mbarrier; the sweep warp hands the stage back through `empty`.
 // Back-pointers leave in the record layout of viterbi_common.cuh, so tilemap / trace / expand are shared.
 #include <cuda.h>
@@ -22,12 +22,17 @@
 
 namespace edb {
 
-__host__ __device__ constexpr int tpc_em_bytes(int S) { return 32 * S * 128; }                       // 32 chains x S rows x 128 B
-__host__ __device__ constexpr int tpc_stage_bytes(int S) { return (tpc_em_bytes(S) + kTile * (int)sizeof(StructRow) + 1023) / 1024 * 1024; }
+// A ring stage holds HALF a record: 8 observations of the warp's 32 chains (32*S rows x 64 bytes, 64-byte swizzle)
+// and their 8 StructRows — 10.5 KB at S = 5, so that four sweep warps (one per SM sub-partition) get five stages each.
+// With whole 16-observation tiles (21 KB) four warps got two stages and the sweep stalled on its loads (2.8 vs 2.05 ms
+// at 256 x 200k x 5), two warps per CTA got five but took twice the SMs.
+constexpr int kHalf = kTile / 2;
+__host__ __device__ constexpr int tpc_em_bytes(int S) { return 32 * S * kHalf * 8; }                 // 32 chains x S rows x 64 B
+__host__ __device__ constexpr int tpc_stage_bytes(int S) { return (tpc_em_bytes(S) + kHalf * (int)sizeof(StructRow) + 511) / 512 * 512; }
 __host__ __device__ constexpr int tpc_stages(int S, int W)
 {
     const int fit = (214 * 1024) / (W * tpc_stage_bytes(S));
-    return fit > 8 ? 8 : fit;
+    return fit > 10 ? 10 : fit;
 }
 
 // ---- the exact pair: out of line, taken when the speculative steps of a pair of observations do not apply --------
@@ -88,11 +93,6 @@ __device__ __noinline__ PairRes<S> tpc_pair_exact(const PairArgs<S> a)
     return r;
 }
 
-#ifndef EDB_TPC_UNROLL_HALVES
-#define EDB_TPC_UNROLL_HALVES 0
-#endif
-constexpr bool kUnrollHalves = EDB_TPC_UNROLL_HALVES != 0;
-
 template <int S, int W>
 __global__ void __launch_bounds__((W + 1) * 32, 1)
 viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
@@ -129,14 +129,16 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
             int i0 = (int)((t_first << 4) - cd.em_off);
             int c0 = (int)(t_first << 4);
             const int c1 = g32 * 32 * S;
-            for (int t = 0; t < n_tiles; t++, i0 += kTile, c0 += kTile) {
+            for (int t = 0; t < 2 * n_tiles; t++, i0 += kHalf, c0 += kHalf) {
                 if (wrap) mbar_wait(empty + 8u * st, (wrap - 1) & 1);
                 const int r0 = i0 < 0 ? 0 : i0;
-                const unsigned row_bytes = (unsigned)(i0 + kTile - r0) * (unsigned)sizeof(StructRow);
+                const int n_rows = i0 + kHalf - r0;         // rows before the chain's first row are never used
+                const unsigned row_bytes = n_rows > 0 ? (unsigned)n_rows * (unsigned)sizeof(StructRow) : 0u;
                 const uint32_t dst = ring + (uint32_t)st * kStageBytes;
                 mbar_expect_tx(full + 8u * st, row_bytes + kEmBytes);
                 tma_load_2d(dst, &ll_map, c0, c1, full + 8u * st);
-                tma_load_1d(dst + kEmBytes + (uint32_t)(r0 - i0) * (uint32_t)sizeof(StructRow), rows + r0, row_bytes, full + 8u * st);
+                if (row_bytes)
+                    tma_load_1d(dst + kEmBytes + (uint32_t)(r0 - i0) * (uint32_t)sizeof(StructRow), rows + r0, row_bytes, full + 8u * st);
                 if (++st == kStages) { st = 0; wrap++; }
             }
         }
@@ -146,14 +148,15 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
     // ---------------------------------------------------------------------------------------- consumer
     const uint32_t ring = smem_u32(smem) + (uint32_t)warp * kStages * kStageBytes;
     const uint32_t full = bar0 + (uint32_t)warp * 2 * kStages * 8, empty = full + kStages * 8;
-    // this lane's S rows of the emission tile (likelihood-column order inside the box); chunk c (16 bytes) of row r
-    // sits at chunk c ^ (r & 7)
+    // this lane's S rows of the emission half-tile (likelihood-column order inside the box); 64-byte rows, 64-byte
+    // swizzle: chunk c (16 bytes) of row r sits at chunk c ^ ((r >> 1) & 3), so the 128-bit reads of a quarter warp
+    // (8 lanes, 8 distinct r & 7 because S is odd) cover the 32 banks once
     uint32_t em_row[S], em_sw[S];
 #pragma unroll
     for (int j = 0; j < S; j++) {
         const int r = lane * S + a.perm[j];
-        em_row[j] = (uint32_t)r * 128u;
-        em_sw[j] = (uint32_t)(r & 7) << 4;
+        em_row[j] = (uint32_t)r * 64u;
+        em_sw[j] = (uint32_t)((r >> 1) & 3) << 4;
     }
     const double c0 = a.c0, c1 = a.c1, tail_other = a.tail_other;
     const double c0m = __dadd_rn(c0, -kSpecMargin);     // the speculative step's acceptance margin
@@ -179,51 +182,50 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
         for (int j = 0; j < S; j++) V[j] = j == 0 ? 0.0 : -HUGE_VAL;         // hmm.cpp:46-52
 
         for (int t = 0; t < n_tiles; t++, bp_t += kRecU2, i0 += kTile) {
-            if (!ready) mbar_wait(full + 8u * st, phase);
-            const uint32_t stage = ring + (uint32_t)st * kStageBytes;
-            const uint32_t rows = stage + kEmBytes;
-            int st_n = st + 1;
-            unsigned phase_n = phase;
-            if (st_n == kStages) { st_n = 0; phase_n ^= 1u; }
-            ready = false;
             unsigned lo[S], hi[S];
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                if (!ready) mbar_wait(full + 8u * st, phase);
+                const uint32_t stage = ring + (uint32_t)st * kStageBytes;
+                const uint32_t rows = stage + kEmBytes;
+                int st_n = st + 1;
+                unsigned phase_n = phase;
+                if (st_n == kStages) { st_n = 0; phase_n ^= 1u; }
+                ready = false;
+                const int ih = i0 + h * kHalf;              // first observation of this half
+                const bool more = h == 0 || t + 1 < n_tiles;
+                unsigned word[S];                           // 8 back-pointers (4 bits each) per destination
+                if (ih >= 1 && ih + kHalf - 1 <= cd.n_em) { // half entirely inside the real observations
+                    // The speculative step leaves ONE BIT per destination and observation (k = j won, or k = 0); the half's
+                    // 8 observations x (S - 1) bits are spread into the record's 4-bit back-pointers at its end (bit -> nibble,
+                    // times j).  The exact pair (out of line) overrides its two nibbles per destination.
+                    constexpr int kBitWords = (S - 1 + 3) / 4;  // bits of destinations 1..4 in word 0, 5..6 in word 1
+                    double2 e[S];
+                    uint32_t ea[S];
 #pragma unroll
-            for (int j = 0; j < S; j++) lo[j] = hi[j] = 0u;
-            if (i0 >= 1 && i0 + kTile - 1 <= cd.n_em) {     // tile entirely inside the real observations
-                // two halves of 4 pairs of observations.  The speculative step leaves ONE BIT per destination and
-                // observation (k = j won, or k = 0); a half's 8 observations x (S - 1) bits are spread into the record's
-                // 4-bit back-pointers once per half (bit -> nibble, times j).  The exact pair (out of line) overrides
-                // its two nibbles per destination.
-                constexpr int kBitWords = (S - 1 + 3) / 4;  // bits of destinations 1..4 in word 0, 5..6 in word 1
-                double2 e[S];
-                uint32_t ea[S];
-#pragma unroll
-                for (int j = 0; j < S; j++) {
-                    ea[j] = stage + em_row[j] + em_sw[j];
-                    e[j] = lds_f64x2(ea[j]);
-                }
-#pragma unroll(kUnrollHalves ? 2 : 1)
-                for (int h = 0; h < 2; h++) {
+                    for (int j = 0; j < S; j++) {
+                        ea[j] = stage + em_row[j] + em_sw[j];
+                        e[j] = lds_f64x2(ea[j]);
+                    }
                     unsigned pb[kBitWords], ovm[S], ovv[S];
 #pragma unroll
                     for (int w = 0; w < kBitWords; w++) pb[w] = 0u;
 #pragma unroll
                     for (int j = 0; j < S; j++) ovm[j] = ovv[j] = 0u;
 #pragma unroll
-                    for (int pp = 0; pp < kTile / 4; pp++) {
-                        const int p = h * (kTile / 4) + pp;
+                    for (int pp = 0; pp < kHalf / 2; pp++) {
                         double2 en[S];
                         uint32_t ean[S];
-                        const uint32_t pn = (uint32_t)((p + 1) & 7) << 4;    // (the last pair reloads pair 0: harmless)
+                        const uint32_t pn = (uint32_t)((pp + 1) & 3) << 4;   // (the last pair reloads pair 0: harmless)
 #pragma unroll
                         for (int j = 0; j < S; j++) {
                             ean[j] = stage + em_row[j] + (pn ^ em_sw[j]);
                             en[j] = lds_f64x2(ean[j]);
                         }
-                        const uint32_t ra = rows + (uint32_t)p * 2u * (uint32_t)sizeof(StructRow);
+                        const uint32_t ra = rows + (uint32_t)pp * 2u * (uint32_t)sizeof(StructRow);
                         const double2 r0a = lds_f64x2(ra), r1a = lds_f64x2(ra + 32);
                         const double r0o = lds_f64(ra + 16), r1o = lds_f64(ra + 48);
-                        if (pp == 2 && h == 0 && t + 1 < n_tiles) ready = try_wait_once(full + 8u * st_n, phase_n);   // poll the next tile early
+                        if (pp == 2 && more) ready = try_wait_once(full + 8u * st_n, phase_n);       // poll the next stage early
                         unsigned worst = (unsigned)__double2hiint(V[0]) << 1;
                         double emA[S], emB[S], Vn[S];
 #pragma unroll
@@ -268,53 +270,55 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
 #pragma unroll
                     for (int j = 0; j < S; j++) {
                         // destination j's bit of every observation -> its nibble, times j; destination 0: all zero
-                        unsigned word = j == 0 ? 0u : ((pb[(j - 1) / 4] >> ((j - 1) & 3)) & 0x11111111u) * (unsigned)j;
-                        word = (word & ~ovm[j]) | ovv[j];
-                        if (h == 0) lo[j] = word;
-                        else hi[j] = word;
+                        const unsigned spread = j == 0 ? 0u : ((pb[(j - 1) / 4] >> ((j - 1) & 3)) & 0x11111111u) * (unsigned)j;
+                        word[j] = (spread & ~ovm[j]) | ovv[j];
                     }
-                }
-            } else {
+                } else {
+#pragma unroll
+                    for (int j = 0; j < S; j++) word[j] = 0u;
 #pragma unroll 1
-                for (int q = 0; q < kTile; q++) {
-                    const int i = i0 + q;
-                    unsigned arg[S];
+                    for (int q = 0; q < kHalf; q++) {
+                        const int i = ih + q;
+                        unsigned arg[S];
 #pragma unroll
-                    for (int j = 0; j < S; j++) arg[j] = (unsigned)j;        // observations outside the chain: identity step
-                    if (i >= 1 && i < nobs) {               // warp-uniform
-                        double em[S];
-                        const uint32_t qa = ((uint32_t)(q >> 1) << 4), qb = (uint32_t)(q & 1) << 3;
+                        for (int j = 0; j < S; j++) arg[j] = (unsigned)j;    // observations outside the chain: identity step
+                        if (i >= 1 && i < nobs) {           // warp-uniform
+                            double em[S];
+                            const uint32_t qa = ((uint32_t)(q >> 1) << 4), qb = (uint32_t)(q & 1) << 3;
 #pragma unroll
-                        for (int j = 0; j < S; j++) {
-                            em[j] = lds_f64(stage + em_row[j] + (qa ^ em_sw[j]) + qb);
-                            if (i > cd.n_em) em[j] = j == 0 ? 0.0 : tail_other;
+                            for (int j = 0; j < S; j++) {
+                                em[j] = lds_f64(stage + em_row[j] + (qa ^ em_sw[j]) + qb);
+                                if (i > cd.n_em) em[j] = j == 0 ? 0.0 : tail_other;
+                            }
+                            const uint32_t ra = rows + (uint32_t)q * (uint32_t)sizeof(StructRow);
+                            const double2 rab = lds_f64x2(ra);
+                            const StructRow row{rab.x, rab.y, lds_f64(ra + 16), 0.0};
+                            viterbi_step_struct<S>(V, em, c0, c1, row, arg);
                         }
-                        const uint32_t ra = rows + (uint32_t)q * (uint32_t)sizeof(StructRow);
-                        const double2 rab = lds_f64x2(ra);
-                        const StructRow row{rab.x, rab.y, lds_f64(ra + 16), 0.0};
-                        viterbi_step_struct<S>(V, em, c0, c1, row, arg);
-                    }
 #pragma unroll
-                    for (int j = 0; j < S; j++) {
-                        if (q < 8) lo[j] |= arg[j] << (4 * q);
-                        else hi[j] |= arg[j] << (4 * (q - 8));
+                        for (int j = 0; j < S; j++) word[j] |= arg[j] << (4 * q);
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < S; j++) {
+                    if (h == 0) lo[j] = word[j];
+                    else hi[j] = word[j];
+                }
+                __syncwarp();                               // every lane is done with the stage: hand it back
+                if (lane == 0) mbar_arrive(empty + 8u * st);
+                st = st_n;
+                phase = phase_n;
             }
             if (live) {
 #pragma unroll
                 for (int j = 0; j < S; j++) bp_t[j] = make_uint2(lo[j], hi[j]);
             }
-            __syncwarp();                                   // every lane is done with the stage: hand it back
-            if (lane == 0) mbar_arrive(empty + 8u * st);
-            st = st_n;
-            phase = phase_n;
         }
     }
 }
 
 size_t viterbi_tpc_smem_bytes(int S, int W) { return (size_t)W * tpc_stages(S, W) * (tpc_stage_bytes(S) + 16); }
-int viterbi_tpc_max_warps(int S) { return S <= 3 ? 4 : S <= 5 ? 4 : 3; }
+int viterbi_tpc_max_warps(int S) { return 4; }
 
 template <int S, int W>
 static void launch_tpc(const ViterbiArgs& a, cudaStream_t st)
