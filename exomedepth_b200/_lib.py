@@ -46,7 +46,7 @@ class Batch(C.Structure):
                 ("expected", C.c_void_p), ("ll", C.c_void_p), ("ll_stride", C.c_int64), ("path", C.c_void_p),
                 ("path_stride", C.c_int64), ("calls", C.c_void_p), ("ncalls", C.c_void_p), ("call_cap", C.c_int32),
                 ("call_stats", C.c_void_p), ("cor", C.c_void_p),
-                ("observed16", C.c_void_p), ("obs16_stride", C.c_int64), ("n_overflow", C.c_int64),
+                ("per_bin_stride", C.c_int64), ("observed16", C.c_void_p), ("obs16_stride", C.c_int64), ("n_overflow", C.c_int64),
                 ("overflow_index", C.c_void_p), ("overflow_value", C.c_void_p)]
 
 

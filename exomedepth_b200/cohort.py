@@ -122,9 +122,11 @@ class Cohort:
         if u16 and overflow is not None and len(overflow[0]):
             ovf_i = np.ascontiguousarray(np.asarray(overflow[0], np.int64))
             ovf_v = np.ascontiguousarray(np.asarray(overflow[1], np.int32))
-        phi = np.ascontiguousarray(np.broadcast_to(np.asarray(phi, np.float64), (ns,)))
-        expected = np.ascontiguousarray(np.broadcast_to(np.asarray(expected, np.float64), (ns,)))
         S, nb = self.n_states, self.n_bins
+        per_bin = np.ndim(phi) == 2 or np.ndim(expected) == 2     # [n_samples, n_bins]: per-bin fits (phi.bins > 1, covariates)
+        shape = (ns, nb) if per_bin else (ns,)
+        phi = np.ascontiguousarray(np.broadcast_to(np.asarray(phi, np.float64), shape))
+        expected = np.ascontiguousarray(np.broadcast_to(np.asarray(expected, np.float64), shape))
         assert observed.shape == (ns, nb)
         out = out or {}
         ll = out.get("ll") if want_ll else None
@@ -149,7 +151,7 @@ class Cohort:
                 cor = np.zeros(ns)
         b = _lib.Batch(ns, None if u16 else _ptr(observed), nb, _ptr(reference), 0 if reference.ndim == 1 else nb, _ptr(phi),
                        _ptr(expected), _ptr(ll), nb, _ptr(path), nb, _ptr(calls), _ptr(ncalls), call_cap,
-                       _ptr(stats), _ptr(cor), _ptr(observed) if u16 else None, nb, 0 if ovf_i is None else ovf_i.size,
+                       _ptr(stats), _ptr(cor), nb if per_bin else 0, _ptr(observed) if u16 else None, nb, 0 if ovf_i is None else ovf_i.size,
                        _ptr(ovf_i), _ptr(ovf_v))
         rc = _lib.check(self.lib.edb200_cohort_run_host(self.handle, C.byref(b), mode), "edb200_cohort_run_host")
         self._last_ns = ns

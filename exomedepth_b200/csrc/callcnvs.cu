@@ -74,8 +74,10 @@ call_summary_kernel(CallSummaryArgs a)
         const double* __restrict__ lln = a.ll + sample * a.ll_sample_stride + (int64_t)a.perm[0] * a.ll_state_stride;
         const int32_t* __restrict__ obs = a.counts.observed + sample * a.counts.obs_stride;
         const int32_t* __restrict__ oth = a.counts.other + sample * a.counts.other_stride;
-        const double e = a.expected[sample];
+        // per-sample scalar, or one value per bin (edb200_batch.per_bin_stride: R/class_definition.R:168-180)
+        const double* __restrict__ ev = a.expected + (int64_t)sample * (a.expected_stride ? a.expected_stride : 1);
         for (int64_t b = sp - 1 + lane; b < ep; b += 32) {
+            const double e = a.expected_stride ? ev[b] : ev[0];
             comp_add(bf, __dadd_rn(llt[b], -lln[b]));
             const int o = obs[b];
             const double tot = a.counts.other_is_total ? (double)oth[b] : __dadd_rn((double)o, (double)oth[b]);

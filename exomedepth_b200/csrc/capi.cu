@@ -924,6 +924,16 @@ static int emission_part(edb200_cohort* c, const edb200_batch* b, const edb::Bin
 {
     if (n_sms <= 0 || n_sms > g.n_sms) n_sms = g.n_sms;
     const int S = c->S, ns = b->n_samples;
+    if (b->per_bin_stride) {                                 // per-bin phi / expected: constants per bin, in registers
+        if (!whole) return fail(EDB200_ERR_ARG, "internal: the per-bin emission kernel covers whole rows only");
+        edb::prof_mark("emission_bins", st);
+        edb::launch_emission_bins_batch(edb::CountsView{b->observed, b->obs_stride, b->reference, b->ref_stride, 0}, b->phi, b->expected,
+                                        b->per_bin_stride, ns, S, c->n_bins, (const double*)c->odds_d.p,
+                                        edb::LLView{b->ll, (int64_t)S * b->ll_stride, b->ll_stride}, g.d_flags, st);
+        edb::prof_mark(nullptr, st);
+        g_launches++;
+        return check_kernel("emission_bins");
+    }
     edb::CountsView cv{b->observed, b->obs_stride, b->reference, b->ref_stride, 0};
     edb::LLView out{b->ll, (int64_t)S * b->ll_stride, b->ll_stride};
     edb::StateConst* consts = (edb::StateConst*)c->consts.p;
@@ -949,6 +959,7 @@ static int emission_part(edb200_cohort* c, const edb200_batch* b, const edb::Bin
 
 static int state_setup(edb200_cohort* c, const edb200_batch* b, cudaStream_t st)
 {
+    if (b->per_bin_stride) return 0;                        // nothing to hoist: the constants change with the bin
     if (int rc = ensure(c->consts, (size_t)b->n_samples * c->S * sizeof(edb::StateConst))) return rc;
     edb::prof_mark("state_setup", st);
     edb::launch_state_setup(b->n_samples, c->S, b->phi, b->expected, (const double*)c->odds_d.p, (edb::StateConst*)c->consts.p, st);
@@ -1113,6 +1124,7 @@ static int call_summary(edb200_cohort* c, const edb200_batch* b, bool stats, boo
     a.n_bins = c->n_bins;
     a.counts = edb::CountsView{b->observed, b->obs_stride, b->reference, b->ref_stride, 0};
     a.expected = b->expected;
+    a.expected_stride = b->per_bin_stride;
     a.ll = b->ll;
     a.ll_sample_stride = (int64_t)S * b->ll_stride;
     a.ll_state_stride = b->ll_stride;
@@ -1141,7 +1153,8 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
     // Device-resident batches run emission, then Viterbi (1 part) unless EDB200_PARTS asks otherwise: both kernels own
     // their SM's shared memory, so overlapping them takes SMs away from the sweep's critical chains — measured slower
     // (3.0 -> 3.5 ms at 256 x 200k x 5).  The host-pointer call pipelines over PCIe instead (edb200_cohort_run_host).
-    const int n_parts = (what & 3) == 3 ? pick_parts(c, emission_mode, 1) : 1;
+    if (b->per_bin_stride && b->per_bin_stride < c->n_bins) return fail(EDB200_ERR_ARG, "per_bin_stride smaller than n_bins");
+    const int n_parts = (what & 3) == 3 && !b->per_bin_stride ? pick_parts(c, emission_mode, 1) : 1;
     if (int rc = build_plan(c, n_parts)) return rc;
     std::vector<edb200_cohort::Part>& plan = c->plans[n_parts];
     if (plan.size() <= 1) {
@@ -1155,7 +1168,10 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
             if (int rc = emission_part(c, b, all, true, emission_mode, 0, st)) return rc;
         }
         if (what & 2) {
-            const bool split = c->opt_vsplit != 0;                    // 0: one pass (tests, experiments)
+            // 0: one pass (tests, experiments).  The thread-per-chain sweep is split only while there are fewer work items than
+            // sweep warps on the GPU (the passes then just let the short chromosomes' post-processing start early); beyond
+            // that the work is throughput-bound and one balanced launch is better (2,000 samples: 5.6 -> see DESIGN.md)
+            const bool split = c->opt_vsplit != 0 && (c->opt_vsplit == 1 || !va.tpc || (int64_t)c->n_chains * ((b->n_samples + 31) / 32) <= 4LL * g.n_sms);
             if (split && c->n_chains >= 4 && va.groups >= 8)
                 if (int rc = build_plan(c, 0)) return rc;
             // (chains of near-equal length — small panels — all fall into the first group: nothing to split)
@@ -1358,7 +1374,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     const int64_t nbp = (nb + 15) & ~(int64_t)15;          // device rows padded to whole 128-byte lines
     int rc = 0;
     if ((rc = ensure(c->h_obs, (size_t)ns * nb * 4)) || (rc = ensure(c->h_ref, (size_t)(shared_ref ? 1 : ns) * nb * 4)) ||
-        (rc = ensure(c->h_phi, ns * 8)) || (rc = ensure(c->h_exp, ns * 8)) || (rc = ensure(c->h_ll, (size_t)ns * S * nbp * 8)) ||
+        (rc = ensure(c->h_phi, (size_t)ns * (b->per_bin_stride ? nb : 1) * 8)) || (rc = ensure(c->h_exp, (size_t)ns * (b->per_bin_stride ? nb : 1) * 8)) || (rc = ensure(c->h_ll, (size_t)ns * S * nbp * 8)) ||
         (rc = ensure(c->h_path, (size_t)ns * nb)) || (rc = ensure(c->h_calls, (size_t)ns * cap * 16)) ||
         (rc = ensure(c->h_ncalls, ns * 4)) || (rc = ensure(c->h_stats, b->call_stats ? (size_t)ns * cap * 24 : 8)) ||
         (rc = ensure(c->h_cor, ns * 8)))
@@ -1371,6 +1387,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     d.ref_stride = shared_ref ? 0 : nb;
     d.phi = (const double*)c->h_phi.p;
     d.expected = (const double*)c->h_exp.p;
+    d.per_bin_stride = b->per_bin_stride ? nb : 0;
     d.ll = (double*)c->h_ll.p;
     d.ll_stride = nbp;
     d.path = (int8_t*)c->h_path.p;
@@ -1383,7 +1400,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     const bool want_vit = b->path || b->calls || b->ncalls || b->call_stats;
     c->last_host_samples = ns;
 
-    const int n_parts = want_vit ? pick_parts(c, emission_mode, Context::kMaxParts) : 1;
+    const int n_parts = want_vit && !b->per_bin_stride ? pick_parts(c, emission_mode, Context::kMaxParts) : 1;
     if ((rc = build_plan(c, n_parts))) return rc;
     std::vector<edb200_cohort::Part>& plan = c->plans[n_parts];
 
@@ -1480,8 +1497,13 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     } else {
         if (shared_ref) CU(cudaMemcpyAsync(c->h_ref.p, b->reference, nb * 4, cudaMemcpyHostToDevice, st));
         else CU(cudaMemcpy2DAsync(c->h_ref.p, nb * 4, b->reference, b->ref_stride * 4, nb * 4, ns, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(c->h_phi.p, b->phi, ns * 8, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(c->h_exp.p, b->expected, ns * 8, cudaMemcpyHostToDevice, st));
+        if (b->per_bin_stride) {
+            CU(cudaMemcpy2DAsync(c->h_phi.p, nb * 8, b->phi, b->per_bin_stride * 8, nb * 8, ns, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpy2DAsync(c->h_exp.p, nb * 8, b->expected, b->per_bin_stride * 8, nb * 8, ns, cudaMemcpyHostToDevice, st));
+        } else {
+            CU(cudaMemcpyAsync(c->h_phi.p, b->phi, ns * 8, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(c->h_exp.p, b->expected, ns * 8, cudaMemcpyHostToDevice, st));
+        }
         // The likelihood matrix is 8*S bytes per bin and sample on the way back, against 4 on the way in: the call is
         // bound by the device-to-host copy.  Samples therefore go through in chunks: the counts of chunk i+1 upload and
         // its emission kernel runs on `st` while the likelihoods of chunk i drain on the second stream.
@@ -1519,8 +1541,8 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
             e.n_samples = cnt;
             e.observed = d.observed + (size_t)s0 * nb;
             if (!shared_ref) e.reference = d.reference + (size_t)s0 * nb;
-            e.phi = d.phi + s0;
-            e.expected = d.expected + s0;
+            e.phi = d.phi + (size_t)s0 * (b->per_bin_stride ? nb : 1);
+            e.expected = d.expected + (size_t)s0 * (b->per_bin_stride ? nb : 1);
             e.ll = d.ll + (size_t)s0 * S * nbp;
             if ((rc = edb200_cohort_run_device(c, &e, 1, chunk_mode, st))) return rc;
             if (b->ll) {

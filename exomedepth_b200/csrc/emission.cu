@@ -68,6 +68,43 @@ void launch_emission_bins(const double* phi, const double* expected, const int32
     emission_bins_kernel<<<(int)blocks, 128, 0, st>>>(phi, expected, total, observed, n_bins, n_states, odds, out, flags);
 }
 
+// per-bin phi / expected for every sample of a cohort (phi.bins > 1 and covariate formulas give per-bin fits,
+// R/class_definition.R:121-147, 168-180): the per-state constants are rebuilt for every bin — ~3x the arithmetic of the
+// scalar kernels and 16 more bytes read per bin and sample; FP64-pipe bound
+__global__ void __launch_bounds__(128)
+emission_bins_batch_kernel(CountsView c, const double* __restrict__ phi, const double* __restrict__ expected, int64_t pb_stride,
+                           int n_states, int64_t n_bins, const double* __restrict__ odds, LLView out, unsigned* __restrict__ flags)
+{
+    const int sample = blockIdx.y;
+    const double* __restrict__ ph = phi + sample * pb_stride;
+    const double* __restrict__ ex = expected + sample * pb_stride;
+    double* o = out.ptr + sample * out.sample_stride;
+    unsigned f = 0;
+    for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < n_bins; b += (int64_t)gridDim.x * blockDim.x) {
+        int tot, obs;
+        obs = c.observed[sample * c.obs_stride + b];
+        const int oth = c.other[sample * c.other_stride + b];
+        tot = c.other_is_total ? oth : obs + oth;
+        const double e = ex[b];
+        const double sd = best_sd(ph[b], e);
+        for (int s = 0; s < n_states; s++) {
+            const StateConst sc = make_state_const(state_expected(e, odds[s]), sd);
+            o[s * out.state_stride + b] = cell_loglik(sc, tot, obs, f);
+        }
+    }
+    if (f) atomicOr(flags, f);
+}
+
+void launch_emission_bins_batch(CountsView c, const double* phi, const double* expected, int64_t pb_stride, int n_samples,
+                                int n_states, int64_t n_bins, const double* odds, LLView out, unsigned* flags, cudaStream_t st)
+{
+    if (n_bins == 0 || n_samples == 0) return;
+    int64_t bx = (n_bins + 127) / 128;
+    const int64_t want = (148 * 16 + n_samples - 1) / n_samples;
+    if (bx > want) bx = want < 1 ? 1 : want;
+    emission_bins_batch_kernel<<<dim3((unsigned)bx, (unsigned)n_samples), 128, 0, st>>>(c, phi, expected, pb_stride, n_states, n_bins, odds, out, flags);
+}
+
 // ---------------------------------------------------------------------------------------------
 // The vendored gsl_sf_lnbeta (src/beta.c:161-164) as the device evaluates it on the faithful path: exposed so that the
 // parity tests can pin the special-function chain itself (KAT-2, the dense sweeps of tests/golden/ref_vectors.npz incl.

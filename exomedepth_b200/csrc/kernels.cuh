@@ -62,6 +62,10 @@ void launch_emission_bins(const double* phi, const double* expected, const int32
 // gsl_sf_lnbeta (src/beta.c:161-164) through the device's faithful GSL restatement; parity tests only
 void launch_lnbeta(const double* x, const double* y, int64_t n, double* out, unsigned* flags, cudaStream_t st);
 
+// batched form of the same: per-bin phi / expected of EVERY sample, [n_samples][pb_stride] (reference-API-faithful cohort)
+void launch_emission_bins_batch(CountsView c, const double* phi, const double* expected, int64_t pb_stride, int n_samples,
+                                int n_states, int64_t n_bins, const double* odds, LLView out, unsigned* flags, cudaStream_t st);
+
 // batched, per-sample scalar phi/expected, lgamma differences evaluated in registers
 void launch_emission_direct(CountsView c, const StateConst* consts, int n_samples, int n_states,
                             int64_t n_bins, LLView out, unsigned* flags, cudaStream_t st);
@@ -161,7 +165,8 @@ struct CallSummaryArgs {
     int n_states;
     int64_t n_bins;
     CountsView counts;            // test counts + reference (or total) counts
-    const double* expected;       // [n_samples]
+    const double* expected;       // [n_samples], or [n_samples][expected_stride] per bin
+    int64_t expected_stride;      // 0: one value per sample
     const double* ll;             // emission matrix, see LLView strides
     int64_t ll_sample_stride;
     int64_t ll_state_stride;

@@ -159,6 +159,11 @@ typedef struct edb200_batch {
      * n_overflow entries sorted by flat index sample * n_bins + bin with their int32 counts.  Exome read counts per bin
      * fit 16 bits except for a handful of bins, so this halves the bytes that cross PCIe per call; the device widens
      * every chromosome group right behind its upload.  exomedepth_b200/cohort.py:pack_counts builds it from int32. */
+    /* Per-bin fits (R/class_definition.R:121-147 `phi.bins > 1`, :168-180 covariate formulas): when per_bin_stride != 0,
+     * phi and expected are double[n_samples][per_bin_stride] — one value per bin and sample, exactly the vectors
+     * get_loglike_matrix receives — instead of one scalar per sample.  The per-state constants are then rebuilt per bin
+     * (in-register kernel; the lattice kernels need per-sample constants). */
+    int64_t        per_bin_stride;
     const uint16_t *observed16;
     int64_t        obs16_stride;
     int64_t        n_overflow;

@@ -853,3 +853,81 @@ def test_16_bit_count_layout_matches_32_bit(edb):
         for k in ("ll", "path", "calls", "ncalls", "call_stats", "cor"):
             assert np.array_equal(got[k], want[k], equal_nan=True), (ns, k)
         co.close()
+
+
+def test_cohort_call_glue_on_exomecount(edb, exomecount, refvec2):
+    """r_glue_cohort.c (`.Call("edb_cohort_callcnvs", ...)`, one call per COHORT) driven with fake SEXPs like R: the four
+    leave-one-out ExomeCount samples as the columns of one count matrix, each with its own reference column — the
+    returned per-sample matrices carry the reference's calls, Bayes factors, reads.* sums and correlations
+    (fixture from the compiled reference: tools/make_golden_r2.py; R/class_definition.R:354-409)."""
+    import ctypes as C
+    import os
+    from conftest import ROOT
+    from oracle import sexp
+    p = os.path.join(ROOT, "oracle", "_ref", "librglue_stub.so")
+    if not os.path.exists(p):
+        pytest.skip("oracle/_ref/librglue_stub.so not built (make -C oracle glue)")
+    g = sexp.bind_call_api(C.CDLL(p))
+    g.edb_cohort_callcnvs.restype = sexp.SEXP
+    g.edb_cohort_callcnvs.argtypes = [sexp.SEXP] * 9
+    ec, r = exomecount, refvec2
+    names = ["Exome1", "Exome2", "Exome3", "Exome4"]
+    n = ec["start"].size
+    counts = np.stack([ec[nm] for nm in names], 1)                                  # bins x samples, like the R matrix
+    refs = np.stack([sum(ec[o] for o in names if o != nm) for nm in names], 1)
+    phi = np.array([float(r[f"loo{s}_phi"][0]) for s in range(4)])
+    exp = np.array([float(r[f"loo{s}_expected"][0]) for s in range(4)])
+    keys = [str(k) for k in r["loo_keys"]]
+    for per_bin in (False, True):
+        ph = np.repeat(phi[None, :], n, 0) if per_bin else phi                      # per-bin: n.bins x n.samples matrices
+        ex = np.repeat(exp[None, :], n, 0) if per_bin else exp
+        h = [sexp.integer(np.asfortranarray(counts).ravel(order="F")), sexp.integer(np.asfortranarray(refs).ravel(order="F")),
+             sexp.integer(np.ones(n, np.int32)), sexp.integer(ec["start"]), sexp.integer(ec["end"]),
+             sexp.real(np.asfortranarray(ph).ravel(order="F")), sexp.real(np.asfortranarray(ex).ravel(order="F")),
+             sexp.real([1e-4]), sexp.real([50000.0])]
+        out = g.edb_cohort_callcnvs(*[x.ptr for x in h])
+        for s in range(4):
+            m = sexp.read_real(sexp.list_elt(out, s))
+            want = r[f"loo{s}_calls"]
+            assert m.shape == (want.shape[0], 8), (per_bin, s, m.shape)
+            for row, w in zip(m, want):
+                wd = dict(zip(keys, w))
+                assert [int(v) for v in row[:4]] == [int(wd["start_p"]), int(wd["end_p"]), int(wd["type"]), int(wd["nexons"])]
+                assert abs(row[4] - 0.43429448190325182765 * wd["BF_raw"]) <= 1e-9 * abs(wd["BF_raw"])
+                assert abs(row[5] - wd["reads_expected_raw"]) <= 1e-12 * abs(wd["reads_expected_raw"]) and row[6] == wd["reads_observed"]
+                assert row[7] == pytest.approx(float(r[f"loo{s}_cor"][0]), rel=1e-12)
+        g.edb200_stub_free(out)
+
+
+def test_per_bin_phi_and_expected_through_the_cohort_path(edb, port):
+    """edb200_batch.per_bin_stride: phi / expected as one value per bin and sample (phi.bins > 1, covariate formulas:
+    R/class_definition.R:121-147, 168-180) — likelihoods against the oracle port cell by cell (1e-10), Viterbi and the
+    reads.expected sums with the per-bin expected."""
+    from exomedepth_b200 import synth
+    from oracle import framing
+    ns, S = 5, 3
+    d = synth.cohort(ns, n_bins=7000)
+    nb = d["start"].size
+    rng = np.random.default_rng(9)
+    gc = rng.uniform(0.3, 0.7, nb)                                                 # a per-bin covariate, e.g. GC content
+    phi = d["phi"][:, None] * (1 + 0.5 * (rng.random((ns, nb)) < 0.5))             # two phi bins per sample
+    exp = np.clip(d["expected"][:, None] * (0.8 + 0.4 * gc[None, :]), 0.01, 0.9)
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=S)
+    res = co.run_host(d["observed"], d["reference"], phi, exp, call_cap=256, want_stats=True)
+    T = port.callcnvs_transitions(S, 1e-4)
+    for s in range(ns):
+        tot = d["observed"][s] + d["reference"]
+        want = port.get_loglike_matrix(phi[s], exp[s], tot, d["observed"][s], 1.0)
+        assert_ll_close(res["ll"][s].T, want)
+        k = 0
+        for c in range(len(d["offsets"]) - 1):
+            b0, b1 = d["offsets"][c], d["offsets"][c + 1]
+            loc, pos = framing.frame_chromosome(res["ll"][s].T[b0:b1], d["start"][b0:b1].astype(float), d["end"][b0:b1].astype(float), 50000.0)
+            path, calls = port.c_hmm(T, loc, pos, 50000.0)
+            assert np.array_equal(res["path"][s, b0:b1], path[1:-1])
+            for (sp, ep, typ, nex) in calls:
+                lo, hi = sp - 2 + b0, ep - 1 + b0
+                want_exp = float(np.sum(tot[lo:hi] * exp[s, lo:hi]))
+                assert abs(res["call_stats"][s, k, 1] - want_exp) <= 1e-12 * abs(want_exp)
+                k += 1
+        assert res["ncalls"][s] == k
