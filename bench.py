@@ -448,6 +448,87 @@ def gpu_arm(a, rank, world):
                    note="beta-binomial fit (aod::betabin stand-in) and select.reference.set correlation sweep of the same cohort; "
                         "device-resident, CUDA events, not part of `value`")
 
+        # ---- the drop-in shape R gets from r_glue.c: ONE sample per .Call — get_loglike_matrix, then C_hmm per chromosome
+        # (R/class_definition.R:184-189, R/tools.R:97), host buffers in and out, every call its own round trip
+        try:
+            from oracle import framing
+            n_ps = 4
+            t0 = time.perf_counter()
+            for s_i in range(n_ps):
+                ll_h = edb.get_loglike_matrix(np.full(nb, phi_h[s_i]), np.full(nb, exp_h[s_i]), obs_h[s_i] + ref, obs_h[s_i], 1.0)
+                T3 = framing.transition_matrix(TP, 3)
+                for ch in range(len(off) - 1):
+                    b0, b1 = off[ch], off[ch + 1]
+                    loc, pos = framing.frame_chromosome(ll_h[b0:b1], start[b0:b1].astype(float), end[b0:b1].astype(float), CNV_LEN)
+                    edb.C_hmm(3, loc.shape[0], T3, loc, pos, CNV_LEN)
+            dt = (time.perf_counter() - t0) / n_ps
+            aux["per_sample_call_shape"] = dict(ms_per_sample=1e3 * dt, value=nb / dt, unit=UNIT, states=3, calls_per_sample=1 + len(off) - 1,
+                                                note="edb200_get_loglike_matrix + one edb200_hmm per chromosome per sample (the two-routine drop-in "
+                                                     "of src/ExomeDepth_init.c:14-24), incl. the Python framing of R/class_definition.R:364-368")
+        except Exception as e:                                          # noqa: BLE001
+            aux["per_sample_call_shape"] = dict(error=f"{type(e).__name__}: {e}")
+
+        # ---- reference-API-faithful cohort: per-bin phi / expected vectors (SURVEY.md §8d "+20 B" variant), 64 samples
+        try:
+            npb = min(ns, 64)
+            phi_pb = phi_t[:npb, None].expand(npb, nbp).contiguous()
+            exp_pb = exp_t[:npb, None].expand(npb, nbp).contiguous()
+            bpb = _lib.Batch(npb, obs_t.data_ptr(), obs_t.stride(0), ref_t.data_ptr(), 0, phi_pb.data_ptr(), exp_pb.data_ptr(), ll.data_ptr(),
+                             ll.stride(1), path.data_ptr(), path.stride(0), calls.data_ptr(), ncalls.data_ptr(), cap, None, None, nbp)
+            import ctypes as C
+            run_pb = lambda: _lib.check(L.edb200_cohort_run_device(co.handle, C.byref(bpb), 3, 0, st0), "per-bin run")
+            run_pb()
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(3):
+                run_pb()
+            ev1.record()
+            torch.cuda.synchronize()
+            ms_pb = ev0.elapsed_time(ev1) / 3
+            aux["per_bin_phi_expected"] = dict(samples=npb, ms_per_step=ms_pb, value=npb * nb / (ms_pb / 1e3), unit=UNIT,
+                                               bytes_per_unit=4 + 8 * S + 1 + 8 * S + 16,
+                                               note="phi / expected as per-bin vectors per sample (edb200_batch.per_bin_stride): per-state constants "
+                                                    "rebuilt per bin in registers — FP64-pipe bound, not HBM bound")
+            step()                                                      # leave the scalar results in the output buffers
+        except Exception as e:                                          # noqa: BLE001
+            aux["per_bin_phi_expected"] = dict(error=f"{type(e).__name__}: {e}")
+
+        # ---- the north star's single-GPU configuration: 2,000 samples x 200k bins x 5 states on ONE B200 (the 256 samples tiled)
+        try:
+            if S == N_STATES and ns == N_SAMPLES and not a.no_large:
+                big = 2000
+                rep = -(-big // ns)
+                obs_b = obs_t.repeat(rep, 1)[:big].contiguous()
+                phi_b, exp_b = phi_t.repeat(rep)[:big].contiguous(), exp_t.repeat(rep)[:big].contiguous()
+                ll_b = torch.empty((big, S, nbp), dtype=torch.float64, device=dev)
+                path_b = torch.empty((big, nbp), dtype=torch.int8, device=dev)
+                calls_b = torch.zeros((big, cap, 4), dtype=torch.int32, device=dev)
+                ncalls_b = torch.zeros(big, dtype=torch.int32, device=dev)
+                run_b = lambda: co.run_device(obs_b, ref_t, phi_b, exp_b, ll_b, path_b, calls_b, ncalls_b, what=3)
+                run_b()
+                torch.cuda.synchronize()
+                _lib.profile(True)
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                for _ in range(3):
+                    run_b()
+                ev1.record()
+                torch.cuda.synchronize()
+                pk = {k: round(v[1] / 3, 4) for k, v in _lib.profile_read().items()}
+                _lib.profile(False)
+                ms_b = ev0.elapsed_time(ev1) / 3
+                peak_b, _src = peaks()
+                aux["large_cohort_one_gpu"] = dict(
+                    workload=f"{big} samples x {nb} bins x {S} states on one GPU (north star; the {ns} synthetic samples tiled), device-resident",
+                    ms_per_step=ms_b, value=big * nb / (ms_b / 1e3), unit=UNIT, kernel_ms_per_step=pk,
+                    sweep_hbm_frac=big * nb * (8 * S + 1) / (pk.get("viterbi_sweep", float("nan")) / 1e3) / 1e9 / peak_b,
+                    emission_hbm_frac=big * nb * (4 + 8 * S) / (pk.get("emission", float("nan")) / 1e3) / 1e9 / peak_b,
+                    calls_match_tiled=bool(int(ncalls_b.sum()) == int(sum(int(ncalls[i % ns]) for i in range(big)))))
+                del obs_b, ll_b, path_b, calls_b
+        except Exception as e:                                          # noqa: BLE001
+            aux["large_cohort_one_gpu"] = dict(error=f"{type(e).__name__}: {e}")
+
         # BASELINE.json configs[3], the launch-bound regime: plain stream launches against the replay of a captured CUDA
         # graph (edb200_cohort_capture_device).  Reported only; a failure here must not take the bench line with it.
         try:
@@ -728,6 +809,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the benchmarked buffers")
     ap.add_argument("--no-aux", action="store_true", help="skip the timings of the fit / reference-set kernels")
     ap.add_argument("--no-ll", action="store_true", help="skip the e2e variant that copies the likelihood matrix back")
+    ap.add_argument("--no-large", action="store_true", help="skip the 2,000-sample single-GPU aux measurement")
     ap.add_argument("--workload", default="cohort", choices=["cohort", "small_panel", "refset"],
                     help="cohort = BASELINE.json configs[1] per GPU (the metric's configuration; the default); small_panel = configs[3]; "
                          "refset = configs[4], the select.reference.set correlation sweep of 2,000 samples sharded over the ranks")

@@ -197,8 +197,9 @@ widen_counts_kernel(const uint16_t* __restrict__ src, int64_t src_stride, int32_
     const bool vec = ((reinterpret_cast<uintptr_t>(s) | (uintptr_t)(src_stride * 2)) & 15) == 0 &&
                      ((reinterpret_cast<uintptr_t>(d) | (uintptr_t)(dst_stride * 4)) & 15) == 0;
     for (int q = 0; q < rg.n; q++) {
-        const int64_t b0 = rg.b0[q], b1 = rg.b1[q];
-        const int64_t n8 = vec && (b0 & 7) == 0 ? b0 + ((b1 - b0) & ~(int64_t)7) : b0;
+        const int64_t b1 = rg.b1[q], b0 = min(b1, (rg.b0[q] + 7) & ~(int64_t)7);      // scalar head up to a multiple of 8 bins
+        for (int64_t b = rg.b0[q] + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < b0; b += (int64_t)gridDim.x * blockDim.x) d[b] = s[b];
+        const int64_t n8 = vec ? b0 + ((b1 - b0) & ~(int64_t)7) : b0;
         for (int64_t b = b0 + (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 8; b < n8; b += (int64_t)gridDim.x * blockDim.x * 8) {
             const uint4 v = __ldcs(reinterpret_cast<const uint4*>(s + b));
             reinterpret_cast<int4*>(d + b)[0] = make_int4((int)(v.x & 0xFFFFu), (int)(v.x >> 16), (int)(v.y & 0xFFFFu), (int)(v.y >> 16));

@@ -867,16 +867,22 @@ static int build_plan(edb200_cohort* c, int n_parts)
     while (!plan.empty() && plan.back().chains.empty()) plan.pop_back();
     for (auto& pt : plan) {
         std::sort(pt.chains.begin(), pt.chains.end());
+        // EXACT bin ranges of the part's chains (adjacent chains merged).  Not rounded out to whole 16-bin tiles: the bins of
+        // a neighbouring chromosome belong to another part, whose sweep may be running — the lattice kernel stores a
+        // clamped-gather value for out-of-lattice cells before its cold pass writes the right one, and a rewrite of
+        // somebody else's bins exposes that transient to a concurrent reader (seen as one extra call in one sample every
+        // few calls with pinned buffers).  The kernels take unaligned ranges: scalar head and tail, vector body.
         std::vector<std::pair<int64_t, int64_t>> rs;
         for (int ch : pt.chains) {
             const edb::ChainDesc& cd = c->chains_h[ch];
-            const int64_t b0 = (cd.em_off + 1) & ~(int64_t)15;
-            const int64_t b1 = std::min<int64_t>(c->n_bins, (cd.em_off + 1 + cd.n_em + 15) & ~(int64_t)15);
+            const int64_t b0 = cd.em_off + 1;
+            const int64_t b1 = std::min<int64_t>(c->n_bins, cd.em_off + 1 + cd.n_em);
             if (!rs.empty() && b0 <= rs.back().second) rs.back().second = std::max(rs.back().second, b1);
             else rs.push_back({b0, b1});
             pt.max_tiles = std::max(pt.max_tiles, edb::viterbi_chain_tiles(cd));
         }
-        while ((int)rs.size() > edb::kMaxBinRanges) {          // close the smallest gap (those bins are then computed twice)
+        while ((int)rs.size() > edb::kMaxBinRanges) {          // (more than 32 disjoint runs in one part: close the smallest gaps;
+                                                               //  cannot happen with up to 32 chromosomes per part)
             size_t best = 1;
             for (size_t i = 2; i < rs.size(); i++)
                 if (rs[i].first - rs[i - 1].second < rs[best].first - rs[best - 1].second) best = i;

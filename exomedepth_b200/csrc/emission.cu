@@ -381,7 +381,13 @@ emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n
         };
 
         for (int q = 0; q < rg.n; q++) {
-            const int64_t r0 = rg.b0[q], r1 = rg.b1[q];
+            // a range may start anywhere (a chromosome's first bin): scalar head up to the next multiple of 4 bins
+            const int64_t r1 = rg.b1[q], r0 = min(r1, (rg.b0[q] + 3) & ~(int64_t)3);
+            for (int64_t bt = rg.b0[q] + threadIdx.x; bt < r0; bt += blockDim.x) {
+                bool in;
+                o[bt] = cell(obs_row[bt], oth_row[bt], in);
+                if (!in) park(bt);
+            }
             const bool vec = ((reinterpret_cast<uintptr_t>(obs_row + r0) | reinterpret_cast<uintptr_t>(oth_row + r0)) & 15) == 0 &&
                              (reinterpret_cast<uintptr_t>(o + r0) & 15) == 0;
             if constexpr (kWarpRows) {

@@ -931,3 +931,36 @@ def test_per_bin_phi_and_expected_through_the_cohort_path(edb, port):
                 assert abs(res["call_stats"][s, k, 1] - want_exp) <= 1e-12 * abs(want_exp)
                 k += 1
         assert res["ncalls"][s] == k
+
+
+def test_pipelined_groups_do_not_touch_each_others_bins(edb):
+    """Regression: the chromosome groups of a host-pointer call run concurrently (upload | emission | sweeps), so a group's
+    emission launch must write the bins of ITS chromosomes only.  With ranges rounded out to 16-bin tiles it rewrote the
+    first / last bins of the neighbouring chromosomes, and for out-of-lattice counts (>= 2048 reads) the lattice kernel's
+    store of a clamped-gather value — corrected by its cold pass a moment later — was visible to the neighbour's running
+    sweep: one extra call in one sample every few calls, only with pinned buffers (truly asynchronous copies).  Here the
+    bins around every chromosome boundary carry such counts; 12 pipelined calls must all equal the single-pass result."""
+    from exomedepth_b200 import _lib, synth
+    ns = 96
+    d = synth.cohort(16, n_bins=60000)
+    obs = np.tile(d["observed"], (ns // 16, 1))
+    rng = np.random.default_rng(4)
+    for b in d["offsets"][1:-1]:
+        for s in range(ns):
+            obs[s, b - 6:b + 6] = rng.integers(2100, 9000, 12)          # beyond the observed-count lattice (2047)
+    phi, ex = np.tile(d["phi"], ns // 16), np.tile(d["expected"], ns // 16)
+    hb = _lib.PinnedPool()
+    obs_p = hb.empty(obs.shape, np.int32)
+    obs_p[:] = obs
+    out = dict(calls=hb.empty((ns, 512, 4), np.int32), ncalls=hb.empty((ns,), np.int32), path=hb.empty(obs.shape, np.int8))
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=5)
+    co.set_option("parts", 1)
+    want = co.run_host(obs_p, d["reference"], phi, ex, call_cap=512, mode=_lib.EMISSION_TABLE, want_ll=False, out=dict(out))
+    want = (want["path"].copy(), want["ncalls"].copy(), want["calls"].copy())
+    co.set_option("parts", 0)
+    for rep in range(12):
+        got = co.run_host(obs_p, d["reference"], phi, ex, call_cap=512, mode=_lib.EMISSION_TABLE, want_ll=False, out=out)
+        assert np.array_equal(got["ncalls"], want[1]), rep
+        assert np.array_equal(got["path"], want[0]), rep
+    co.close()
+    hb.close()
