@@ -638,7 +638,7 @@ def refset_arm(a, rank, world):
     z_local = torch.zeros((per, kp), dtype=torch.float64, device=dev)
     z_all = torch.empty((world * per, kp), dtype=torch.float64, device=dev) if dist else z_local
     out = torch.empty((max(n_local, 1), n_total), dtype=torch.float64, device=dev)
-    fused = dist is not None and per <= 256 and not a.no_fused
+    fused = dist is not None and per <= 256 and world <= 4 and not a.no_fused
     if fused:
         z_ptr, handle = refset.block_alloc(per, sel.size)
         handles = [None] * world

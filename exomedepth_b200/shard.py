@@ -117,8 +117,10 @@ def refset_sweep(counts_local, n_total, bin_length=None, n_bins_reduced=0, dist=
     two compute stages — default: the CUDA kernels (exomedepth_b200.refset); the CPU tests pass numpy stand-ins.
     fused=True (CUDA, one process per GPU of one NVLink box): no all-gather — every rank maps the other ranks' blocks
     with CUDA IPC and the Gram kernel reads its B tiles from their owners' memory (same bits as the all-gather form).
-    fused=None picks it when a rank forms at most 256 rows (two row tiles: every remote tile then crosses NVLink at most
-    twice; measured on 2 GPUs: 2.6 vs 2.9 ms at 256 rows per rank, 35 vs 33 ms at 1,000)."""
+    fused=None picks it when a rank forms at most 256 rows AND there are at most 4 ranks (two row tiles: every remote tile
+    then crosses NVLink at most twice; measured: 2 GPUs 2.6 vs 2.9 ms at 256 rows per rank and 35 vs 33 ms at 1,000; 4 GPUs
+    5.2 vs 5.4 ms at 250 rows; 8 GPUs 11.7 vs 11.3 ms at 250 rows — with seven peers the remote reads of the Gram kernel
+    cost more than NCCL's all-gather, profiles/r2f_bench_refset_n8*.json)."""
     from . import refset
     multi = dist is not None and dist.is_initialized() and dist.get_world_size() > 1
     world = dist.get_world_size() if multi else 1
@@ -133,7 +135,7 @@ def refset_sweep(counts_local, n_total, bin_length=None, n_bins_reduced=0, dist=
     sel = refset.select_bins(total.cpu().numpy(), bin_length, n_bins_reduced)
     per = -(-n_total // world)                              # every rank contributes a block of `per` rows (zero padded)
     if fused is None:
-        fused = per <= 256
+        fused = per <= 256 and world <= 4
     if fused and multi and backend is None:
         c_t = torch.from_numpy(counts_local).to(dev)
         sel_t = torch.from_numpy(sel).to(dev)
