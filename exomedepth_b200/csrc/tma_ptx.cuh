@@ -26,6 +26,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity)
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+// the producer's wait: it shares an SM sub-partition with a sweep warp (five warps, four sub-partitions), so it backs off
+// between polls instead of competing for that sub-partition's issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "nanosleep.u32 256;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ bool try_wait_once(uint32_t bar, unsigned parity)
 {
     unsigned ok;

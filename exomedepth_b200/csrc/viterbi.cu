@@ -211,7 +211,7 @@ viterbi_sweep_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
             int c0 = (int)(t_first << 4);
             const int c1 = grp * G * S;
             for (int t = 0; t < n_tiles; t++, i0 += kTile, c0 += kTile) {
-                if (wrap) mbar_wait(empty + 8u * st, (wrap - 1) & 1);
+                if (wrap) mbar_wait_relaxed(empty + 8u * st, (wrap - 1) & 1);
                 const int r0 = i0 < 0 ? 0 : i0;             // rows before the chain's first row are never used
                 const unsigned lt_bytes = (unsigned)(i0 + kTile - r0) * LTP * 8;
                 const uint32_t dst = ring + (uint32_t)st * kStageBytes;

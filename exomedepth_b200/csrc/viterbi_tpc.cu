@@ -130,7 +130,7 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
             int c0 = (int)(t_first << 4);
             const int c1 = g32 * 32 * S;
             for (int t = 0; t < 2 * n_tiles; t++, i0 += kHalf, c0 += kHalf) {
-                if (wrap) mbar_wait(empty + 8u * st, (wrap - 1) & 1);
+                if (wrap) mbar_wait_relaxed(empty + 8u * st, (wrap - 1) & 1);
                 const int r0 = i0 < 0 ? 0 : i0;
                 const int n_rows = i0 + kHalf - r0;         // rows before the chain's first row are never used
                 const unsigned row_bytes = n_rows > 0 ? (unsigned)n_rows * (unsigned)sizeof(StructRow) : 0u;
