@@ -13,13 +13,13 @@ LIB_PATH = os.environ.get("EDB200_LIB") or os.path.join(_HERE, "libexomedepth_b2
 OK, WARN_NAN, ERR_NSTATES, ERR_CUDA, ERR_ARG, WARN_CALLCAP = 0, 1, 2, 4, 8, 16
 MAX_STATES = 7
 EMISSION_AUTO, EMISSION_DIRECT, EMISSION_TABLE, EMISSION_PANEL = 0, 1, 2, 3
-OPTIONS = dict(sweep=1, parts=2, vsplit=3, crit_warps=4, sweep_warps=5, packplan=6)      # EDB200_OPT_*
+OPTIONS = dict(sweep=1, parts=2, vsplit=3, crit_warps=4, sweep_warps=5, packplan=6, segments=7, seg_warm=8, seg_min=9, seg_repair=10)      # EDB200_OPT_*
 SWEEP_AUTO, SWEEP_LANE_PER_STATE, SWEEP_THREAD_PER_CHAIN = 0, 1, 2
 
 EXPORTS = (
     "edb200_init", "edb200_shutdown", "edb200_last_error", "edb200_device_info", "edb200_launch_count",
     "edb200_host_alloc", "edb200_host_free", "edb200_get_loglike_matrix", "edb200_emission", "edb200_lnbeta", "edb200_hmm",
-    "edb200_cohort_create", "edb200_cohort_destroy", "edb200_cohort_set_option", "edb200_cohort_table", "edb200_cohort_table_copy",
+    "edb200_cohort_create", "edb200_cohort_destroy", "edb200_cohort_set_option", "edb200_cohort_segment_stats", "edb200_cohort_table", "edb200_cohort_table_copy",
     "edb200_cohort_run_device", "edb200_cohort_capture_device", "edb200_graph_launch", "edb200_graph_destroy",
     "edb200_cohort_run_host", "edb200_status", "edb200_profile", "edb200_profile_read",
     "edb200_cohort_forward_device", "edb200_cohort_forward_last",
@@ -89,6 +89,8 @@ def load():
     L.edb200_cohort_destroy.argtypes = [vp]
     L.edb200_cohort_set_option.restype = C.c_int
     L.edb200_cohort_set_option.argtypes = [vp, C.c_int, C.c_int]
+    L.edb200_cohort_segment_stats.restype = C.c_int
+    L.edb200_cohort_segment_stats.argtypes = [vp, C.POINTER(C.c_int32)]
     L.edb200_cohort_table.restype = C.c_int
     L.edb200_cohort_table.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.edb200_cohort_table_copy.restype = C.c_int

@@ -86,9 +86,18 @@ class Cohort:
 
     def set_option(self, name, value):
         """Execution options (include/exomedepth_b200.h, EDB200_OPT_*): 'sweep' (0 auto, 1 lane per state, 2 thread per
-        chain), 'parts', 'vsplit', 'crit_warps', 'sweep_warps', 'packplan'.  Results never depend on them."""
+        chain), 'parts', 'vsplit', 'crit_warps', 'sweep_warps', 'packplan', 'segments' (-1 auto, 0, 1), 'seg_warm', 'seg_min',
+        'seg_repair'.  Results never depend on them."""
         _lib.check(self.lib.edb200_cohort_set_option(self.handle, _lib.OPTIONS[name], int(value)), "edb200_cohort_set_option")
         return self
+
+    def segment_stats(self):
+        """dict(pieces, listed, chains_repaired, pairs_repaired) of the last Viterbi pass if it was a segmented sweep
+        (pieces = 0 otherwise); see include/exomedepth_b200.h: edb200_cohort_segment_stats."""
+        out = (C.c_int32 * 10)()
+        _lib.check(self.lib.edb200_cohort_segment_stats(self.handle, out), "edb200_cohort_segment_stats")
+        why = dict(zip(("non_finite", "list_full", "seam_values", "seam_error", "on_path", "forced"), list(out)[4:10]))
+        return dict(pieces=out[0], listed=out[1], chains_repaired=out[2], pairs_repaired=out[3], why=why)
 
     # ---- shared metadata ------------------------------------------------------------------------
     def table_bytes(self):

@@ -17,6 +17,7 @@
 #include "../../include/exomedepth_b200.h"
 #include "host_tables.h"
 #include "kernels.cuh"
+#include "viterbi_seam.h"
 
 namespace {
 
@@ -251,6 +252,14 @@ struct edb200_cohort {
     int opt_parts = 0;                   // chromosome groups of a pipelined batch (0 auto)
     int opt_vsplit = -1;                 // device-resident Viterbi as two concurrent passes (-1 auto)
     int opt_crit_warps = 0, opt_sweep_warps = 0, opt_packplan = 0;
+    int opt_segments = -1, opt_seg_warm = 0, opt_seg_min = 0, opt_seg_repair = 0;
+    // segmented sweep (viterbi_seam.h): pieces for `seg_key` (samples, warm-up, shortest piece), scratch, the plain
+    // schedule of the repair pass; seg_ok: the transition terms are small enough for the error bound (ensure_struct)
+    int seg_ok = 0;
+    long long seg_key = -1;
+    int seg_pieces = 0, seg_ctas = 0;
+    int seg_last_samples = 0;            // samples of the last Viterbi pass if it was segmented, else 0 (edb200_cohort_segment_stats)
+    DevBuf seg_desc, seg_first, seg_begin, seg_items, seam_in, seam_out, seam_mag, seg_close, seg_flags;
     // Chromosome groups ("parts"): the chains are split by length so that the emission of the long chromosomes can
     // finish — and their sweeps, the critical path, can start — while the rest is still being computed (or uploaded).
     struct Part {
@@ -765,7 +774,8 @@ void edb200_cohort_destroy(edb200_cohort* c)
         }
     DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->tile_base, &c->decay, &c->srows, &c->fw_grid, &c->fw_chain, &c->fw_out, &c->fw_best, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->lattices,
                      &c->h_obs, &c->h_ref, &c->h_phi, &c->h_exp, &c->h_ll, &c->h_path, &c->h_calls, &c->h_ncalls, &c->h_stats, &c->h_cor,
-                     &c->h_obs16, &c->h_ovf_i, &c->h_ovf_v};
+                     &c->h_obs16, &c->h_ovf_i, &c->h_ovf_v,
+                     &c->seg_desc, &c->seg_first, &c->seg_begin, &c->seg_items, &c->seam_in, &c->seam_out, &c->seam_mag, &c->seg_close, &c->seg_flags};
     for (DevBuf* b : all) release(*b);
     delete c;
 }
@@ -807,10 +817,41 @@ int edb200_cohort_set_option(edb200_cohort* c, int option, int value)
         case EDB200_OPT_CRIT_WARPS: c->opt_crit_warps = value; break;
         case EDB200_OPT_SWEEP_WARPS: c->opt_sweep_warps = value; break;
         case EDB200_OPT_PACKPLAN: c->opt_packplan = value; break;
+        case EDB200_OPT_SEGMENTS: c->opt_segments = value < 0 ? -1 : value != 0; break;
+        case EDB200_OPT_SEG_WARM:
+            if (value < 0 || value > 64) return fail(EDB200_ERR_ARG, "EDB200_OPT_SEG_WARM: 0 (default) .. 64 tiles");
+            c->opt_seg_warm = value;
+            break;
+        case EDB200_OPT_SEG_MIN:
+            if (value < 0) return fail(EDB200_ERR_ARG, "EDB200_OPT_SEG_MIN: tiles >= 0");
+            c->opt_seg_min = value;
+            break;
+        case EDB200_OPT_SEG_REPAIR: c->opt_seg_repair = value != 0; break;
         default: return fail(EDB200_ERR_ARG, "unknown option %d", option);
     }
     for (auto& plan : c->plans)
         for (auto& part : plan) part.sched_groups = 0;      // schedules are rebuilt under the new options
+    c->seg_key = -1;
+    return 0;
+}
+
+int edb200_cohort_segment_stats(edb200_cohort* c, int32_t out[10])
+{
+    if (!c || !out) return fail(EDB200_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int i = 0; i < 10; i++) out[i] = 0;
+    if (!c->seg_last_samples || !c->seg_flags.p) return 0;
+    CU(cudaDeviceSynchronize());
+    const int ns = c->seg_last_samples, n_g32 = edb::seg_n_g32(ns);
+    std::vector<int32_t> f(edb::seg_flag_ints(c->n_chains, ns));
+    CU(cudaMemcpy(f.data(), c->seg_flags.p, f.size() * 4, cudaMemcpyDeviceToHost));
+    out[0] = c->seg_pieces;
+    out[1] = f[0];
+    for (int i = 0; i < c->n_chains; i++) out[2] += f[1 + i] != 0;
+    for (size_t i = 1 + (size_t)c->n_chains * (1 + n_g32); i < f.size(); i++) {
+        out[3] += f[i] != 0;
+        for (int b = 0; b < 6; b++) out[4 + b] += (f[i] >> b) & 1;
+    }
     return 0;
 }
 
@@ -827,6 +868,11 @@ static int ensure_struct(edb200_cohort* c)
     CU(cudaMemcpy(lt.data(), c->lt.p, lt.size() * 8, cudaMemcpyDeviceToHost));
     std::vector<edb::StructRow> rows(n_rows);
     if (!edb::build_struct_rows(S, lt.data(), c->lt_pitch, (int64_t)n_rows, rows.data(), &c->c0, &c->c1)) return 0;
+    // the error bound of the segmented sweep (viterbi_seam.h) takes |log t| <= 1024 for every finite term
+    c->seg_ok = std::isfinite(c->c0) && std::isfinite(c->c1) && std::fabs(c->c0) <= 1024.0 && std::fabs(c->c1) <= 1024.0;
+    for (const edb::StructRow& r : rows)
+        for (double v : {r.b0, r.sf, r.ot})
+            if (v != v || v == HUGE_VAL || (v > -HUGE_VAL && std::fabs(v) > 1024.0)) c->seg_ok = 0;
     if (int rc = ensure(c->srows, n_rows * sizeof(edb::StructRow))) return rc;
     CU(cudaMemcpy(c->srows.p, rows.data(), n_rows * sizeof(edb::StructRow), cudaMemcpyHostToDevice));
     c->struct_state = 1;
@@ -1117,6 +1163,94 @@ static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiA
     return check_kernel("viterbi");
 }
 
+// ---- segmented sweep (viterbi_seam.h) ------------------------------------------------------------------------
+// Whether to cut the chains: when an even share of all tiles per sweep warp (plus its warm-up) is well below what bounds
+// the plain sweeps — the longest chain, or the whole lines packed onto the warps.
+static bool use_segments(const edb200_cohort* c, int n_samples)
+{
+    if (c->struct_state != 1 || !c->seg_ok || c->opt_sweep == 1 || c->opt_segments == 0) return false;
+    if (c->opt_segments == 1) return true;
+    const int S = c->S, G = 32 / S;
+    int64_t longest = 0, total = 0;
+    for (const auto& cd : c->chains_h) {
+        longest = std::max<int64_t>(longest, cd.nobs);
+        total += cd.nobs;
+    }
+    const double slots = 4.0 * g.n_sms;
+    const double lane = std::max(150.0 * longest, 165.0 * total * ((n_samples + G - 1) / G) / slots);
+    const double tpc = std::max(205.0 * longest, 205.0 * total * ((n_samples + 31) / 32) / slots);
+    const double min_piece = 16.0 * (c->opt_seg_min > 0 ? c->opt_seg_min : 32), warm = 16.0 * (c->opt_seg_warm > 0 ? c->opt_seg_warm : 4);
+    const double share = std::max((double)total * ((n_samples + 31) / 32) / slots, std::min((double)longest, min_piece));
+    return 215.0 * (share + warm) < 0.8 * std::min(lane, tpc);
+}
+
+// seg sweep, tilemap, trace, expand, check, and the (normally empty) repair pass over all chains, on `st`
+static int viterbi_segmented(edb200_cohort* c, edb::ViterbiArgs a, cudaStream_t st)
+{
+    const int S = c->S, ns = a.n_samples, n_g32 = edb::seg_n_g32(ns);
+    const int warm = c->opt_seg_warm > 0 ? c->opt_seg_warm : 4;
+    const int min_piece = c->opt_seg_min > 0 ? c->opt_seg_min : 32;
+    constexpr int kW = 4, kCloseCap = 1 << 16;
+    if (int rc = build_plan(c, 1)) return rc;
+    edb200_cohort::Part& all = c->plans[1][0];
+    const long long key = ((long long)ns << 24) | ((long long)warm << 16) | (long long)std::min(min_piece, 65535);
+    if (c->seg_key != key) {
+        std::vector<int32_t> tiles(c->n_chains), begin, items, desc, first;
+        for (int i = 0; i < c->n_chains; i++) tiles[i] = edb::viterbi_chain_tiles(c->chains_h[i]);
+        edb::viterbi_cut_pieces(tiles.data(), c->n_chains, n_g32, g.n_sms, kW, warm, min_piece, begin, items, desc, first);
+        int n_ctas = g.n_sms;
+        while (n_ctas > 1 && begin[(size_t)(n_ctas - 1) * kW] == begin[(size_t)n_ctas * kW]) n_ctas--;
+        c->seg_ctas = n_ctas;
+        c->seg_pieces = (int)(desc.size() / 4);
+        if (int rc = ensure(c->seg_desc, desc.size() * 4)) return rc;
+        if (int rc = ensure(c->seg_first, first.size() * 4)) return rc;
+        if (int rc = ensure(c->seg_begin, begin.size() * 4)) return rc;
+        if (int rc = ensure(c->seg_items, items.size() * 4 + 8)) return rc;
+        if (int rc = ensure(c->seam_in, (size_t)c->seg_pieces * S * 32 * 8)) return rc;
+        if (int rc = ensure(c->seam_out, (size_t)c->seg_pieces * S * 32 * 8)) return rc;
+        if (int rc = ensure(c->seam_mag, (size_t)c->seg_pieces * edb::kSeamWords * 32 * 4)) return rc;
+        if (int rc = ensure(c->seg_close, (size_t)kCloseCap * 16)) return rc;
+        if (int rc = ensure(c->seg_flags, edb::seg_flag_ints(c->n_chains, ns) * 4)) return rc;
+        CU(cudaMemcpyAsync(c->seg_desc.p, desc.data(), desc.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->seg_first.p, first.data(), first.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->seg_begin.p, begin.data(), begin.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->seg_items.p, items.data(), items.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));          // the vectors go out of scope
+        c->seg_key = key;
+    }
+    c->seg_last_samples = ns;
+    a.tpc = 1;
+    a.seg = 1;
+    a.seg_warm = warm;
+    a.seg_desc = (const int4*)c->seg_desc.p;
+    a.seg_first = (const int32_t*)c->seg_first.p;
+    a.seam_in = (double*)c->seam_in.p;
+    a.seam_out = (double*)c->seam_out.p;
+    a.seam_mag = (unsigned*)c->seam_mag.p;
+    a.seg_close = (int4*)c->seg_close.p;
+    a.seg_close_cap = kCloseCap;
+    a.seg_flags = (int32_t*)c->seg_flags.p;
+    a.seg_force_repair = c->opt_seg_repair;
+    a.chain_list = (const int32_t*)all.chain_list.p;
+    a.n_list = (int)all.chains.size();
+    a.max_list_tiles = all.max_tiles;
+    a.warps_per_cta = kW;
+    a.n_slots = c->seg_ctas * kW;
+    a.sched_begin = (const int32_t*)c->seg_begin.p;
+    a.sched_items = (const int32_t*)c->seg_items.p;
+    CU(cudaMemsetAsync(c->seg_flags.p, 0, edb::seg_flag_ints(c->n_chains, ns) * 4, st));
+    g_launches += edb::launch_viterbi(a, st);
+    edb::prof_mark("viterbi_seg_check", st);
+    g_launches += edb::launch_viterbi_seg_check(a, st);
+    edb::prof_mark(nullptr, st);
+    if (int rc = check_kernel("viterbi (segmented)")) return rc;
+    // repair pass: the plain exact sweep and its post-processing over the refused chains (normally none: four launches
+    // that find nothing to do)
+    a.seg = 0;
+    a.only_bad = 1;
+    return viterbi_part(c, all, a, 0, st, 0, kW);
+}
+
 static int call_summary(edb200_cohort* c, const edb200_batch* b, bool stats, bool cor, cudaStream_t st)
 {
     stats = stats && b->call_stats;
@@ -1178,6 +1312,10 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
             // 0: one pass (tests, experiments).  The thread-per-chain sweep is split only while there are fewer work items than
             // sweep warps on the GPU (the passes then just let the short chromosomes' post-processing start early); beyond
             // that the work is throughput-bound and one balanced launch is better (2,000 samples: 5.6 -> see DESIGN.md)
+            if (use_segments(c, b->n_samples)) {
+                if (int rc = viterbi_segmented(c, va, st)) return rc;
+            } else {
+            c->seg_last_samples = 0;
             const bool split = c->opt_vsplit != 0 && (c->opt_vsplit == 1 || !va.tpc || (int64_t)c->n_chains * ((b->n_samples + 31) / 32) <= 4LL * g.n_sms);
             if (split && c->n_chains >= 4 && va.groups >= 8)
                 if (int rc = build_plan(c, 0)) return rc;
@@ -1198,6 +1336,7 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
                     CU(cudaStreamWaitEvent(st, g.ev_vit[p], 0));
                 }
             } else if (int rc = viterbi_part(c, plan[0], va, 0, st)) return rc;
+            }
         }
     } else {
         // ---- chromosome-group pipeline: the emission of group p+1 runs while group p is being swept.  Forked from

@@ -188,6 +188,65 @@ void viterbi_schedule(const int32_t* chain_nobs, int n_chains, int groups, int n
     begin[n_slots] = (int32_t)(items.size() / 2);
 }
 
+// Segmented sweep (viterbi_seam.h): the (chain, 32-sample group) lines of tiles are laid end to end and cut into equal
+// shares, one per sweep warp; a line that straddles a share boundary is cut there into pieces, which the kernel sweeps
+// concurrently.  A piece that does not start its line costs `warm` warm-up tiles on top of its own.  No piece is
+// shorter than min_piece tiles (a cut that would leave a shorter head or tail moves to the line's end), so small
+// batches use fewer warps.  Logical share q goes to warp q / n_ctas of CTA q % n_ctas: the shares spread over the SMs
+// before they stack up on one.
+void viterbi_cut_pieces(const int32_t* chain_tiles, int n_chains, int n_g32, int n_ctas, int warps_per_cta, int warm, int min_piece,
+                        std::vector<int32_t>& begin, std::vector<int32_t>& items, std::vector<int32_t>& desc, std::vector<int32_t>& first)
+{
+    const int n_slots = n_ctas * warps_per_cta;
+    if (min_piece < warm + 2) min_piece = warm + 2;
+    int64_t total = 0;
+    for (int c = 0; c < n_chains; c++) total += (int64_t)chain_tiles[c] * n_g32;
+    int64_t target = (total + (int64_t)n_slots * warm + n_slots - 1) / n_slots;
+    if (target < min_piece) target = min_piece;
+    std::vector<std::vector<int32_t>> per_slot(n_slots);
+    desc.clear();
+    first.assign((size_t)n_chains * n_g32 + 1, 0);
+    int q = 0;
+    int64_t room = target;
+    for (int c = 0; c < n_chains; c++)
+        for (int g = 0; g < n_g32; g++) {
+            first[(size_t)c * n_g32 + g] = (int32_t)(desc.size() / 4);
+            const int nt = chain_tiles[c];
+            int pos = 0;
+            while (pos < nt) {
+                const int cost0 = pos > 0 ? warm : 0;
+                int64_t take = room - cost0;
+                if (q == n_slots - 1) take = nt - pos;                       // the last share takes what is left
+                if (take < min_piece) take = min_piece;
+                if (take > nt - pos) take = nt - pos;
+                if (nt - (pos + take) < min_piece) take = nt - pos;          // no short tail
+                const int piece = (int)(desc.size() / 4);
+                desc.push_back(c);
+                desc.push_back(g);
+                desc.push_back(pos);
+                desc.push_back(pos + (int)take);
+                const int slot = (q % n_ctas) * warps_per_cta + q / n_ctas;
+                per_slot[slot].push_back(piece);
+                per_slot[slot].push_back(0);
+                room -= take + cost0;
+                pos += (int)take;
+                if (room <= 0 && q < n_slots - 1) {
+                    q++;
+                    room += target;
+                    if (room < min_piece) room = min_piece;
+                }
+            }
+        }
+    first[(size_t)n_chains * n_g32] = (int32_t)(desc.size() / 4);
+    begin.assign(n_slots + 1, 0);
+    items.clear();
+    for (int s = 0; s < n_slots; s++) {
+        begin[s] = (int32_t)(items.size() / 2);
+        items.insert(items.end(), per_slot[s].begin(), per_slot[s].end());
+    }
+    begin[n_slots] = (int32_t)(items.size() / 2);
+}
+
 int frame_positions(int64_t nb, const int32_t* start, const int32_t* end, double L, int32_t* pos)
 {
     // R/class_definition.R:368: as.integer(c(start[1] - 2*L, start, end[last] + 2*L))

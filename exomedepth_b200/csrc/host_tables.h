@@ -42,4 +42,9 @@ int build_struct_rows(int S, const double* lt, int pitch, int64_t n_rows, Struct
 // on their sub-partition.  begin has n_slots + 1 entries, items 2 per work item (chain, group).
 void viterbi_schedule(const int32_t* chain_nobs, int n_chains, int groups, int n_ctas, int warps_per_cta,
                       std::vector<int32_t>& begin, std::vector<int32_t>& items);
+// Pieces of the segmented sweep (viterbi_seam.h): desc = 4 ints per piece (chain, 32-sample group, first tile, end tile),
+// a line's pieces consecutive; first[chain * n_g32 + g] = the line's first piece (n_chains * n_g32 + 1 entries);
+// begin / items = the pieces of every sweep warp, 2 ints per item (piece, 0).
+void viterbi_cut_pieces(const int32_t* chain_tiles, int n_chains, int n_g32, int n_ctas, int warps_per_cta, int warm, int min_piece,
+                        std::vector<int32_t>& begin, std::vector<int32_t>& items, std::vector<int32_t>& desc, std::vector<int32_t>& first);
 }  // namespace edb

@@ -137,7 +137,26 @@ struct ViterbiArgs {
     const StructRow* srows;       // [rows + tile] structured rows (host_tables.h: build_struct_rows)
     double c0, c1;                // log t(0 -> 0), log t(0 -> j > 0)
     const void* ll_map_tpc;       // host pointer to the CUtensorMap with box 16 bins x 32*S rows
+    // segmented sweep (viterbi_seam.h): every (chain, 32 samples) line of tiles is cut into pieces that are swept
+    // concurrently; sched_items then holds piece ids
+    int seg;                      // 1: the schedule deals pieces
+    int seg_warm;                 // warm-up tiles in front of a piece that does not start its chain
+    const int4* seg_desc;         // [n_pieces] (chain, 32-sample group, first recorded tile, end tile)
+    const int32_t* seg_first;     // [n_chains * n_g32 + 1] first piece of every line; a line's pieces are consecutive
+    double* seam_in;              // [n_pieces][S][32] V of a piece after its warm-up
+    double* seam_out;             // [n_pieces][S][32] V of a piece after its last observation
+    unsigned* seam_mag;           // [n_pieces][kSeamWords][32] magnitudes and error multipliers of a piece (viterbi_seam.h: PieceErr)
+    int4* seg_close;              // [seg_close_cap] decisions with a lead below kSegTau: (chain, sample, observation, destination)
+    int seg_close_cap;
+    // repair flags, zeroed per run: [0] number of listed decisions, then chain_any[n_chains], line_bad[n_chains * n_g32],
+    // chain_bad[n_chains * n_samples]
+    int32_t* seg_flags;
+    int only_bad;                 // 1: the repair pass — only the lines / chains whose flags are raised
+    int seg_force_repair;         // test hook: the check kernel sends every chain to the repair pass
 };
+// views into ViterbiArgs::seg_flags
+__host__ __device__ inline int seg_n_g32(int n_samples) { return (n_samples + 31) / 32; }
+__host__ __device__ inline size_t seg_flag_ints(int n_chains, int n_samples) { return 1 + (size_t)n_chains * (1 + seg_n_g32(n_samples) + n_samples); }
 
 // enqueues sweep, tilemap, trace and expand for the chains of a.chain_list (the schedule must cover exactly those);
 // launch_viterbi_compact then concatenates the per-chromosome call tables of ALL chains.  Both return the number of launches.
@@ -145,6 +164,7 @@ int launch_viterbi(const ViterbiArgs& a, cudaStream_t st);
 int launch_viterbi_compact(const ViterbiArgs& a, cudaStream_t st);
 size_t viterbi_smem_bytes(int n_states, int warps_per_cta);
 int launch_viterbi_tpc_sweep(const ViterbiArgs& a, cudaStream_t st);   // viterbi_tpc.cu; 3, 5 or 7 states
+int launch_viterbi_seg_check(const ViterbiArgs& a, cudaStream_t st);   // viterbi_tpc.cu: certifies a segmented sweep (after expand)
 size_t viterbi_tpc_smem_bytes(int n_states, int warps_per_cta);
 int viterbi_tpc_max_warps(int n_states);
 int viterbi_pick_warps(const int32_t* chain_nobs, int n_chains, int groups, int n_sms);

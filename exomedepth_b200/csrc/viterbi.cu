@@ -336,6 +336,7 @@ viterbi_tilemap_kernel(ViterbiArgs a)
     constexpr unsigned kOnes = kTracked & 0x11111111u;
     // blockIdx.y walks the launch's chain list, blockIdx.x the chain's records (groups x tiles, G chains each)
     const int chain = a.chain_list ? a.chain_list[blockIdx.y] : (int)blockIdx.y;
+    if (a.only_bad && a.seg_flags[1 + chain] == 0) return;      // repair pass of the segmented sweep: refused chains only
     const int64_t n_rec = (int64_t)chain_tiles(a.chains[chain]) * a.groups;
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (idx >= n_rec * G) return;
@@ -382,6 +383,7 @@ viterbi_trace_kernel(ViterbiArgs a, int G)
     if (wid >= a.n_samples * a.n_list) return;
     const int smp = wid % a.n_samples;                      // neighbouring warps: same chromosome, same length
     const int chain = a.chain_list ? a.chain_list[wid / a.n_samples] : wid / a.n_samples;
+    if (a.only_bad && a.seg_flags[1 + chain] == 0) return;
     const int grp = smp / G, gg = smp - grp * G;
     const ChainDesc cd = a.chains[chain];
     const int n_tiles = chain_tiles(cd);
@@ -417,6 +419,7 @@ viterbi_expand_kernel(ViterbiArgs a)
     if (wid >= a.n_samples * a.n_list) return;
     const int smp = wid % a.n_samples;
     const int chain = a.chain_list ? a.chain_list[wid / a.n_samples] : wid / a.n_samples;
+    if (a.only_bad && a.seg_flags[1 + chain] == 0) return;
     const int grp = smp / G, gg = smp - grp * G;
     const ChainDesc cd = a.chains[chain];
     const int nobs = cd.nobs;
@@ -562,11 +565,15 @@ static void launch_sweep(const ViterbiArgs& a, cudaStream_t st)
     viterbi_sweep_kernel<S, W><<<a.n_slots / W, (W + 1) * 32, smem, st>>>(a, *reinterpret_cast<const CUtensorMap*>(a.ll_map));
 }
 
+static const char* const kPassNames[4] = {"viterbi_sweep", "viterbi_tilemap", "viterbi_trace", "viterbi_expand"};
+static const char* const kRepairNames[4] = {"repair_sweep", "repair_tilemap", "repair_trace", "repair_expand"};
 template <int S>
 static void launch_all(const ViterbiArgs& a, cudaStream_t st)
 {
     constexpr int G = 32 / S;
-    prof_mark("viterbi_sweep", st);
+    // (the repair pass of a segmented sweep is timed under names of its own: normally four launches that find nothing to do)
+    const char* const* nm = a.only_bad ? kRepairNames : kPassNames;
+    prof_mark(nm[0], st);
     if (a.tpc) launch_viterbi_tpc_sweep(a, st);
     else switch (a.warps_per_cta) {
         case 1: launch_sweep<S, 1>(a, st); break;          // 1, 2: experiments (EDB200_CRIT_WARPS), see DESIGN.md "what comes next"
@@ -574,13 +581,13 @@ static void launch_all(const ViterbiArgs& a, cudaStream_t st)
         case 4: launch_sweep<S, 4>(a, st); break;
         default: launch_sweep<S, 8>(a, st); break;
     }
-    prof_mark("viterbi_tilemap", st);
+    prof_mark(nm[1], st);
     const int64_t map_threads = (int64_t)a.max_list_tiles * a.groups * G;
     if (map_threads > 0) viterbi_tilemap_kernel<S><<<dim3((unsigned)((map_threads + 255) / 256), (unsigned)a.n_list), 256, 0, st>>>(a);
     const int chains = a.n_samples * a.n_list;
-    prof_mark("viterbi_trace", st);
+    prof_mark(nm[2], st);
     viterbi_trace_kernel<<<(chains + 3) / 4, 128, 0, st>>>(a, G);
-    prof_mark("viterbi_expand", st);
+    prof_mark(nm[3], st);
     viterbi_expand_kernel<S><<<(chains + 3) / 4, 128, 0, st>>>(a);
 }
 

@@ -293,6 +293,114 @@ EDB_STEP_HD unsigned viterbi_step_spec(double* V, const double* em, double c0, d
     return bits;
 }
 
+// ---- segments: steps that also certify their decisions (viterbi_seam.h) -------------------------------------------
+// A chain cut into segments is swept from an approximate start vector: the values X of such a sweep follow the
+// reference's values R up to a constant and a small error, |X[k] + C - R[k]| <= eps for every state k (viterbi_seam.h
+// derives eps).  Every candidate then obeys |xc_k + C - rc_k| <= eps' (eps plus the roundings of the step), so a decision
+// whose winner leads every other candidate by more than 2 eps' in X arithmetic has the same winner in the reference's.
+// The steps below report the decisions whose lead is below kSegTau; the caller guarantees 2 eps' < kSegTau.
+constexpr double kSegTau = 6.103515625e-05;             // 2^-14
+constexpr unsigned kSegTauHi = (1023u - 14u) << 20;     // its high word
+
+EDB_STEP_HD unsigned f64_hi(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return (unsigned)__double2hiint(x);
+#else
+    unsigned long long u;
+    __builtin_memcpy(&u, &x, 8);
+    return (unsigned)(u >> 32);
+#endif
+}
+
+// viterbi_step_spec with the lead of every decision it takes: min_hi collects the smallest high word of |self - cand0|
+// over the destinations (the decision between k = j and k = 0; the group candidates are kept away by the 2^-12 of the
+// acceptance test itself).  The caller rejects the pair when min_hi < kSegTauHi, i.e. some |self - cand0| < 2^-14.
+template <int S>
+EDB_STEP_HD unsigned viterbi_step_spec_m(double* V, const double* em, double c0, double c1, double c0m, const StructRow& row, bool& ok,
+                                         unsigned& min_hi)
+{
+    static_assert(S == 3 || S == 5 || S == 7, "structured step: 3, 5 or 7 states");
+    const double y = EDB_ADD(V[0], c0m);
+    bool fine = ok;
+#pragma unroll
+    for (int k = 1; k < S; k++) fine = fine && (EDB_ADD(V[k], row.b0) < y);
+    ok = fine;
+    double nv[S];
+    unsigned bits = 0u, mh = min_hi;
+    nv[0] = EDB_ADD(EDB_ADD(em[0], V[0]), c0);
+#pragma unroll
+    for (int j = 1; j < S; j++) {
+        const double cand0 = EDB_ADD(EDB_ADD(em[j], V[0]), c1);
+        const double self = EDB_ADD(EDB_ADD(em[j], V[j]), row.sf);
+        const bool p1 = self > cand0;
+        nv[j] = p1 ? self : cand0;
+        bits |= p1 ? (1u << (j - 1)) : 0u;
+        const unsigned h = f64_hi(EDB_ADD(self, -cand0)) & 0x7FFFFFFFu;      // -Inf (self = -Inf) and NaN read as "large"
+        mh = h < mh ? h : mh;
+    }
+    min_hi = mh;
+#pragma unroll
+    for (int j = 0; j < S; j++) V[j] = nv[j];
+    return bits;
+}
+
+// The plain scan of src/hmm.cpp:66-88 over the structured row, keeping the runner-up: arg[j] is the reference's first
+// maximum (in the arithmetic of the V given), and bit j of the result is set when destination j's winner leads the best
+// other candidate by less than kSegTau (ties included).  Preconditions (caller): every V and emission finite, c0 and c1
+// finite — so a finite candidate from k = 0 exists, no "from = -1", no forced 0.
+template <int S>
+EDB_STEP_HD unsigned viterbi_step_margin(double* V, const double* em, double c0, double c1, const StructRow& row, unsigned* arg)
+{
+    const double ninf = -HUGE_VAL;
+    double nv[S];
+    unsigned close = 0u;
+#pragma unroll
+    for (int j = 0; j < S; j++) {
+        double best = ninf, second = ninf;
+        unsigned a = 7u;
+#pragma unroll
+        for (int k = 0; k < S; k++) {
+            const double lt = k == 0 ? (j == 0 ? c0 : c1) : j == 0 ? row.b0 : k == j ? row.sf : row.ot;
+            const double c = EDB_ADD(EDB_ADD(em[j], V[k]), lt);
+            const bool win = c > best;
+            const double loser = win ? best : c;            // a candidate equal to the leader becomes the runner-up: lead 0
+            second = loser > second ? loser : second;
+            best = win ? c : best;
+            a = win ? (unsigned)k : a;
+        }
+        if (!(EDB_ADD(best, -second) >= kSegTau)) close |= 1u << j;
+        nv[j] = best;
+        arg[j] = a;
+    }
+#pragma unroll
+    for (int j = 0; j < S; j++) V[j] = nv[j];
+    return close;
+}
+
+// How far a segment's RELATIVE vector can be from the reference's (viterbi_seam.h): D = the spread max_k err[k] - min_k
+// err[k] of the deviations err[k] = (R[k] - R[0]) - (X[k] - X[0]), as two multipliers, D <= a * e0 + b * 2 rho  (e0: the
+// bound at the seam, rho: the rounding of one candidate in both arithmetics).  A step gives
+// err'[j] - err'[j'] = err[w(j)] - err[w(j')] + (rho_j - rho_j')  with w(j) the winner of destination j:
+//   kind 0  every destination has the same winner (certified): the old deviations cancel,   (a, b) -> (0, 1)
+//   kind 1  anything else — also a listed decision, whose winner may differ in the reference's arithmetic (max is
+//           1-Lipschitz: every R'[j] - X'[j] stays inside the old interval widened by rho):   (a, b) -> (a, b + 1)
+// (saturating: a chain whose multipliers run away is refused by the check kernel).
+EDB_STEP_HD void seg_err_step(unsigned& a, unsigned& b, int kind)
+{
+    a = kind == 0 ? 0u : a;
+    b = kind == 0 ? 1u : (b < (1u << 24) ? b + 1u : b);
+}
+// kind of a step from its winners (arg[j], 7 = none) and the mask of listed decisions
+template <int S>
+EDB_STEP_HD int seg_err_kind(const unsigned* arg, unsigned close)
+{
+    bool same = close == 0u;
+#pragma unroll
+    for (int j = 1; j < S; j++) same = same && arg[j] == arg[0];
+    return same ? 0 : 1;
+}
+
 // exponent field of x at least 1023 + 30 (|x| >= 2^30, Inf or NaN), from the high word alone
 constexpr unsigned kSpecBigHi2 = (1023u + 30u) << 21;          // compared with hi << 1
 EDB_STEP_HD bool big_or_nonfinite_hi(unsigned hi) { return (hi << 1) >= kSpecBigHi2; }

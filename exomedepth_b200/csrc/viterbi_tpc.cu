@@ -12,12 +12,14 @@
 // a quarter-warp's 128-bit reads of two observations hit 8 distinct 16-byte chunks) and one bulk copy of the half's 8
 // StructRows, completing on the stage's `full` mbarrier; the sweep warp hands the stage back through `empty`.
 // Back-pointers leave in the record layout of viterbi_common.cuh, so tilemap / trace / expand are shared.
+#include <algorithm>
 #include <cuda.h>
 
 #include "host_tables.h"
 #include "kernels.cuh"
 #include "tma_ptx.cuh"
 #include "viterbi_common.cuh"
+#include "viterbi_seam.h"
 #include "viterbi_step.h"
 
 namespace edb {
@@ -93,7 +95,106 @@ __device__ __noinline__ PairRes<S> tpc_pair_exact(const PairArgs<S> a)
     return r;
 }
 
-template <int S, int W>
+// ---- segmented sweep: flags and the certifying step -----------------------------------------------------------------
+struct SegOut {                 // where a piece reports (views into ViterbiArgs::seg_flags / seg_close)
+    int32_t* flags;
+    int4* close;
+    int close_cap;
+    int n_chains, n_samples;
+};
+__device__ __forceinline__ void seg_mark_bad(int32_t* flags, int n_chains, int n_samples, int chain, int smp, int why)
+{
+    const int n_g32 = seg_n_g32(n_samples);
+    flags[1 + chain] = 1;
+    flags[1 + n_chains + chain * n_g32 + (smp >> 5)] = 1;
+    atomicOr(&flags[1 + n_chains * (1 + n_g32) + chain * n_samples + smp], why);
+}
+
+// One observation of a piece that did not start its chain, whenever the speculative step does not apply: the plain
+// scan with the runner-up (viterbi_step.h: viterbi_step_margin); decisions with a lead below kSegTau are listed for the
+// check kernel.  A NaN / Inf in sight — or more listed decisions than the list holds — sends the chain to the repair pass.
+template <int S>
+struct MStepArgs {
+    double v[S], em[S];
+    double b0, sf, ot, c0, c1;
+    SegOut o;
+    int chain, smp, obs;
+    int rec;                    // 0: warm-up (decisions are not recorded, hence not listed)
+};
+template <int S>
+struct MStepRes {
+    double v[S];
+    unsigned arg[S];
+    int kind;                   // how the step moves the error multipliers (viterbi_step.h: seg_err_step)
+};
+template <int S>
+__device__ __noinline__ MStepRes<S> tpc_step_margin(const MStepArgs<S> a)
+{
+    MStepRes<S> r;
+    double V[S], em[S];
+    unsigned worst = 0;
+#pragma unroll
+    for (int j = 0; j < S; j++) {
+        V[j] = a.v[j];
+        em[j] = a.em[j];
+        worst = max(worst, max((unsigned)__double2hiint(V[j]) << 1, (unsigned)__double2hiint(em[j]) << 1));
+    }
+    const StructRow row{a.b0, a.sf, a.ot, 0.0};
+    if (worst >= 0xFFE00000u) {
+        viterbi_step_struct<S>(V, em, a.c0, a.c1, row, r.arg);
+        r.kind = 1;
+        if (a.rec) seg_mark_bad(a.o.flags, a.o.n_chains, a.o.n_samples, a.chain, a.smp, kBadNonFinite);
+    } else {
+        const unsigned close = viterbi_step_margin<S>(V, em, a.c0, a.c1, row, r.arg);
+        r.kind = seg_err_kind<S>(r.arg, close);
+        if (close && a.rec) {
+#pragma unroll 1
+            for (int j = 0; j < S; j++)
+                if (close >> j & 1u) {
+                    const int q = atomicAdd(a.o.flags, 1);
+                    if (q < a.o.close_cap) a.o.close[q] = make_int4(a.chain, a.smp, a.obs, j);
+                    else seg_mark_bad(a.o.flags, a.o.n_chains, a.o.n_samples, a.chain, a.smp, kBadListFull);
+                }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < S; j++) r.v[j] = V[j];
+    return r;
+}
+
+// a work item of the sweep: a whole (chain, 32 samples) line of tiles, or one piece of it (segmented sweep)
+struct TpcItem {
+    int chain, g32;
+    int t_begin, t_seam, t_end;     // tiles of the chain: swept from t_begin, recorded from t_seam, up to t_end
+    int piece;
+    bool skip;
+};
+template <bool kSeg>
+__device__ __forceinline__ TpcItem tpc_item(const ViterbiArgs& a, int it)
+{
+    TpcItem wi;
+    if (kSeg) {
+        wi.piece = a.sched_items[2 * it];
+        const int4 d = a.seg_desc[wi.piece];
+        wi.chain = d.x;
+        wi.g32 = d.y;
+        wi.t_seam = d.z;
+        wi.t_end = d.w;
+        wi.t_begin = d.z > 0 ? d.z - a.seg_warm : 0;
+        wi.skip = false;
+    } else {
+        wi.piece = 0;
+        wi.chain = a.sched_items[2 * it];
+        wi.g32 = a.sched_items[2 * it + 1];
+        wi.t_begin = wi.t_seam = 0;
+        wi.t_end = chain_tiles(a.chains[wi.chain]);
+        // the repair pass sweeps only the lines the check kernel refused
+        wi.skip = a.only_bad && a.seg_flags[1 + a.n_chains + wi.chain * seg_n_g32(a.n_samples) + wi.g32] == 0;
+    }
+    return wi;
+}
+
+template <int S, int W, bool kSeg>
 __global__ void __launch_bounds__((W + 1) * 32, 1)
 viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
 {
@@ -121,15 +222,16 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
         int st = 0;
         unsigned wrap = 0;
         for (int it = a.sched_begin[slot]; it < a.sched_begin[slot + 1]; it++) {
-            const int chain = a.sched_items[2 * it], g32 = a.sched_items[2 * it + 1];
+            const TpcItem wi = tpc_item<kSeg>(a, it);
+            if (wi.skip) continue;
+            const int chain = wi.chain, g32 = wi.g32;
             const ChainDesc cd = a.chains[chain];
-            const int64_t t_first = (cd.em_off + 1) >> 4;
-            const int n_tiles = chain_tiles(cd);
+            const int64_t t_first = ((cd.em_off + 1) >> 4) + wi.t_begin;
             const StructRow* __restrict__ rows = a.srows + cd.lt_row0;
             int i0 = (int)((t_first << 4) - cd.em_off);
             int c0 = (int)(t_first << 4);
             const int c1 = g32 * 32 * S;
-            for (int t = 0; t < 2 * n_tiles; t++, i0 += kHalf, c0 += kHalf) {
+            for (int t = 2 * wi.t_begin; t < 2 * wi.t_end; t++, i0 += kHalf, c0 += kHalf) {
                 if (wrap) mbar_wait_relaxed(empty + 8u * st, (wrap - 1) & 1);
                 const int r0 = i0 < 0 ? 0 : i0;
                 const int n_rows = i0 + kHalf - r0;         // rows before the chain's first row are never used
@@ -165,7 +267,9 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
     unsigned phase = 0;
     const int slot = blockIdx.x * W + warp;
     for (int it = a.sched_begin[slot]; it < a.sched_begin[slot + 1]; it++) {
-        const int chain = a.sched_items[2 * it], g32 = a.sched_items[2 * it + 1];
+        const TpcItem wi = tpc_item<kSeg>(a, it);
+        if (wi.skip) continue;
+        const int chain = wi.chain, g32 = wi.g32;
         const ChainDesc cd = a.chains[chain];
         const int nobs = cd.nobs;
         const int64_t t_first = (cd.em_off + 1) >> 4;
@@ -173,16 +277,29 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
         const int smp = g32 * 32 + lane;
         const bool live = smp < a.n_samples;                // lanes past the batch sweep zero-filled rows and write nothing
         const int grp = smp / G, gg = smp - grp * G;
-        uint2* bp_t = reinterpret_cast<uint2*>(a.bp) + record_base(a, chain, grp, n_tiles) * kRecU2 + gg * S;
-        int i0 = (int)((t_first << 4) - cd.em_off);
+        uint2* bp_t = reinterpret_cast<uint2*>(a.bp) + (record_base(a, chain, grp, n_tiles) + wi.t_begin) * kRecU2 + gg * S;
+        int i0 = (int)(((t_first + wi.t_begin) << 4) - cd.em_off);
         bool ready = false;
+        // a piece that does not start its chain (segmented sweep): V is approximate, every decision is certified
+        const bool mseg = kSeg && wi.t_seam > 0;
+        unsigned mag_v = 0, mag_e = 0;                      // largest (high word << 1) of V / of the emissions since the seam
+        unsigned err_a = 0, err_b = 0, max_a = 0, max_b = 0;   // error multipliers of the relative vector (viterbi_step.h: seg_err_step)
+        const SegOut so{a.seg_flags, a.seg_close, a.seg_close_cap, a.n_chains, a.n_samples};
 
         double V[S];
 #pragma unroll
-        for (int j = 0; j < S; j++) V[j] = j == 0 ? 0.0 : -HUGE_VAL;         // hmm.cpp:46-52
+        for (int j = 0; j < S; j++) V[j] = j == 0 ? 0.0 : -HUGE_VAL;         // hmm.cpp:46-52 (and the start of a warm-up)
 
-        for (int t = 0; t < n_tiles; t++, bp_t += kRecU2, i0 += kTile) {
+        for (int t = wi.t_begin; t < wi.t_end; t++, bp_t += kRecU2, i0 += kTile) {
             unsigned lo[S], hi[S];
+            const bool rec = !kSeg || t >= wi.t_seam;        // warm-up tiles are swept, not recorded
+            if (kSeg && mseg && t == wi.t_seam) {
+#pragma unroll
+                for (int j = 0; j < S; j++) a.seam_in[((int64_t)wi.piece * S + j) * 32 + lane] = V[j];
+                mag_v = mag_e = 0;
+                err_a = max_a = 1u;                         // the seam's own deviation e0, carried until the first step that cancels it
+                err_b = max_b = 0u;
+            }
 #pragma unroll 1
             for (int h = 0; h < 2; h++) {
                 if (!ready) mbar_wait(full + 8u * st, phase);
@@ -193,7 +310,7 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
                 if (st_n == kStages) { st_n = 0; phase_n ^= 1u; }
                 ready = false;
                 const int ih = i0 + h * kHalf;              // first observation of this half
-                const bool more = h == 0 || t + 1 < n_tiles;
+                const bool more = h == 0 || t + 1 < wi.t_end;
                 unsigned word[S];                           // 8 back-pointers (4 bits each) per destination
                 if (ih >= 1 && ih + kHalf - 1 <= cd.n_em) { // half entirely inside the real observations
                     // The speculative step leaves ONE BIT per destination and observation (k = j won, or k = 0); the half's
@@ -228,21 +345,81 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
                         if (pp == 2 && more) ready = try_wait_once(full + 8u * st_n, phase_n);       // poll the next stage early
                         unsigned worst = (unsigned)__double2hiint(V[0]) << 1;
                         double emA[S], emB[S], Vn[S];
+                        if (kSeg) {
+                            unsigned we = 0;
+#pragma unroll
+                            for (int j = 0; j < S; j++) {
+                                we = max(we, max((unsigned)__double2hiint(e[j].x) << 1, (unsigned)__double2hiint(e[j].y) << 1));
+                                mag_v = max(mag_v, (unsigned)__double2hiint(V[j]) << 1);
+                            }
+                            mag_e = max(mag_e, we);
+                            worst = max(worst, we);
+                        }
 #pragma unroll
                         for (int j = 0; j < S; j++) {
-                            worst = max(worst, max((unsigned)__double2hiint(e[j].x) << 1, (unsigned)__double2hiint(e[j].y) << 1));
+                            if (!kSeg) worst = max(worst, max((unsigned)__double2hiint(e[j].x) << 1, (unsigned)__double2hiint(e[j].y) << 1));
                             emA[j] = e[j].x;
                             emB[j] = e[j].y;
                             Vn[j] = V[j];
                         }
                         const StructRow rowA{r0a.x, r0a.y, r0o, 0.0}, rowB{r1a.x, r1a.y, r1o, 0.0};
                         bool ok = worst < kSpecBigHi2;
-                        const unsigned bitsA = viterbi_step_spec<S>(Vn, emA, c0, c1, c0m, rowA, ok);
-                        const unsigned bitsB = viterbi_step_spec<S>(Vn, emB, c0, c1, c0m, rowB, ok);
+                        unsigned bitsA, bitsB;
+                        if (kSeg) {
+                            // the lead of every decision rides along; a pair with a lead below 2^-14 goes the slow way (for a
+                            // piece that starts its chain the slow way is simply the exact pair)
+                            unsigned min_hi = 0x7FFFFFFFu;
+                            bitsA = viterbi_step_spec_m<S>(Vn, emA, c0, c1, c0m, rowA, ok, min_hi);
+                            bitsB = viterbi_step_spec_m<S>(Vn, emB, c0, c1, c0m, rowB, ok, min_hi);
+                            ok = ok && min_hi >= kSegTauHi;
+                            if (mseg && ok) {
+                                // destination 0 keeps k = 0 here; no bit set = every destination was won by k = 0: the deviations cancel
+                                err_a = bitsA ? err_a : 0u;
+                                err_b = bitsA ? err_b + 1u : 1u;
+                                max_b = max(max_b, err_b);
+                                err_a = bitsB ? err_a : 0u;
+                                err_b = bitsB ? err_b + 1u : 1u;
+                                max_b = max(max_b, err_b);
+                            }
+                        } else {
+                            bitsA = viterbi_step_spec<S>(Vn, emA, c0, c1, c0m, rowA, ok);
+                            bitsB = viterbi_step_spec<S>(Vn, emB, c0, c1, c0m, rowB, ok);
+                        }
 #pragma unroll
                         for (int w = 0; w < kBitWords; w++)
                             pb[w] |= ((bitsA >> (4 * w)) & 0xFu) << (8 * pp) | ((bitsB >> (4 * w)) & 0xFu) << (8 * pp + 4);
-                        if (!ok) {
+                        if (kSeg && mseg) {
+                            if (!ok && live) {
+                                MStepArgs<S> ma;
+#pragma unroll
+                                for (int j = 0; j < S; j++) {
+                                    ma.v[j] = V[j];
+                                    ma.em[j] = emA[j];
+                                }
+                                ma.b0 = rowA.b0, ma.sf = rowA.sf, ma.ot = rowA.ot, ma.c0 = c0, ma.c1 = c1;
+                                ma.o = so;
+                                ma.chain = chain, ma.smp = smp, ma.obs = ih + 2 * pp, ma.rec = rec ? 1 : 0;
+                                const MStepRes<S> ra = tpc_step_margin<S>(ma);
+#pragma unroll
+                                for (int j = 0; j < S; j++) {
+                                    ma.v[j] = ra.v[j];
+                                    ma.em[j] = emB[j];
+                                }
+                                ma.b0 = rowB.b0, ma.sf = rowB.sf, ma.ot = rowB.ot;
+                                ma.obs = ih + 2 * pp + 1;
+                                const MStepRes<S> rb = tpc_step_margin<S>(ma);
+                                seg_err_step(err_a, err_b, ra.kind);
+                                max_b = max(max_b, err_b);
+                                seg_err_step(err_a, err_b, rb.kind);
+                                max_b = max(max_b, err_b);
+#pragma unroll
+                                for (int j = 0; j < S; j++) {
+                                    Vn[j] = rb.v[j];
+                                    ovm[j] |= 0xFFu << (8 * pp);
+                                    ovv[j] |= (ra.arg[j] | rb.arg[j] << 4) << (8 * pp);
+                                }
+                            }
+                        } else if (!ok) {
                             PairArgs<S> pa;
 #pragma unroll
                             for (int j = 0; j < S; j++) {
@@ -293,7 +470,29 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
                             const uint32_t ra = rows + (uint32_t)q * (uint32_t)sizeof(StructRow);
                             const double2 rab = lds_f64x2(ra);
                             const StructRow row{rab.x, rab.y, lds_f64(ra + 16), 0.0};
-                            viterbi_step_struct<S>(V, em, c0, c1, row, arg);
+                            if (kSeg && mseg) {
+                                if (live) {
+                                    MStepArgs<S> ma;
+#pragma unroll
+                                    for (int j = 0; j < S; j++) {
+                                        ma.v[j] = V[j];
+                                        ma.em[j] = em[j];
+                                        mag_v = max(mag_v, (unsigned)__double2hiint(V[j]) << 1);
+                                        mag_e = max(mag_e, (unsigned)__double2hiint(em[j]) << 1);
+                                    }
+                                    ma.b0 = row.b0, ma.sf = row.sf, ma.ot = row.ot, ma.c0 = c0, ma.c1 = c1;
+                                    ma.o = so;
+                                    ma.chain = chain, ma.smp = smp, ma.obs = i, ma.rec = rec ? 1 : 0;
+                                    const MStepRes<S> rm = tpc_step_margin<S>(ma);
+                                    seg_err_step(err_a, err_b, rm.kind);
+                                    max_b = max(max_b, err_b);
+#pragma unroll
+                                    for (int j = 0; j < S; j++) {
+                                        V[j] = rm.v[j];
+                                        arg[j] = rm.arg[j];
+                                    }
+                                }
+                            } else viterbi_step_struct<S>(V, em, c0, c1, row, arg);
                         }
 #pragma unroll
                         for (int j = 0; j < S; j++) word[j] |= arg[j] << (4 * q);
@@ -309,36 +508,104 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
                 st = st_n;
                 phase = phase_n;
             }
-            if (live) {
+            if (live && rec) {
 #pragma unroll
                 for (int j = 0; j < S; j++) bp_t[j] = make_uint2(lo[j], hi[j]);
             }
         }
+        if (kSeg) {
+            // what the check kernel needs to certify the NEXT piece of this line (and this one): V after the last
+            // observation, and how large the values of this piece were
+#pragma unroll
+            for (int j = 0; j < S; j++) {
+                a.seam_out[((int64_t)wi.piece * S + j) * 32 + lane] = V[j];
+                mag_v = max(mag_v, (unsigned)__double2hiint(V[j]) << 1);
+            }
+            unsigned* pe = a.seam_mag + (int64_t)wi.piece * (kSeamWords * 32) + lane;
+            pe[0] = mag_v, pe[32] = mag_e, pe[64] = max_a, pe[96] = max_b, pe[128] = err_a, pe[160] = err_b;
+        }
     }
+}
+
+// ---- check kernel of the segmented sweep (after expand: it reads the path) --------------------------------------------
+// Part 1, one thread per (chain, sample): walks the seams of the line in order (viterbi_seam.h: seam_advance) and refuses
+// the chain when a seam does not close or the certified error outgrows kSegEpsMax.  Part 2, one thread per listed decision
+// (lead below kSegTau): the decision (observation i, destination j) is read by the traceback only if the path is in
+// state j at observation i; then the chain is refused too.  Refused chains are swept again by the repair pass.
+template <int S>
+__global__ void __launch_bounds__(256)
+viterbi_seg_check_kernel(ViterbiArgs a)
+{
+    const int n_g32 = seg_n_g32(a.n_samples);
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, n_thr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = tid; q < (int64_t)a.n_chains * a.n_samples; q += n_thr) {
+        const int chain = (int)(q / a.n_samples), smp = (int)(q - (int64_t)chain * a.n_samples);
+        const int line = chain * n_g32 + (smp >> 5), lane = smp & 31;
+        SeamState st{0.0, 0.0, a.seg_force_repair ? kBadForced : 0};
+        for (int pc = a.seg_first[line] + 1; pc < a.seg_first[line + 1] && !st.bad; pc++) {
+            double x_in[S], x_prev[S];
+#pragma unroll
+            for (int j = 0; j < S; j++) {
+                x_in[j] = a.seam_in[((int64_t)pc * S + j) * 32 + lane];
+                x_prev[j] = a.seam_out[((int64_t)(pc - 1) * S + j) * 32 + lane];
+            }
+            const int4 d = a.seg_desc[pc];
+            const unsigned* w = a.seam_mag + (int64_t)pc * (kSeamWords * 32) + lane;
+            const PieceErr pe{w[0], w[32], w[64], w[96], w[128], w[160]};
+            seam_advance<S>(st, x_in, x_prev, pe, (d.w - d.z) * kTile);
+        }
+        if (st.bad) seg_mark_bad(a.seg_flags, a.n_chains, a.n_samples, chain, smp, st.bad);
+    }
+    const int n_close = min(a.seg_flags[0], a.seg_close_cap);
+    for (int64_t q = tid; q < n_close; q += n_thr) {
+        const int4 e = a.seg_close[q];
+        const ChainDesc cd = a.chains[e.x];
+        bool on = true;                                     // an observation whose state is not on record: assume the worst
+        if (e.z == cd.nobs - 1) on = e.w == 0;              // the chain ends in state 0 (hmm.cpp:96)
+        else if (e.z >= cd.out_first && e.z <= cd.out_last) on = (int)a.path[e.y * a.path_stride + cd.out_off + e.z] == e.w;
+        if (on) seg_mark_bad(a.seg_flags, a.n_chains, a.n_samples, e.x, e.y, kBadOnPath);
+    }
+}
+
+int launch_viterbi_seg_check(const ViterbiArgs& a, cudaStream_t st)
+{
+    const int64_t n = (int64_t)a.n_chains * a.n_samples;
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 1184);
+    switch (a.n_states) {
+        case 3: viterbi_seg_check_kernel<3><<<blocks, 256, 0, st>>>(a); break;
+        case 5: viterbi_seg_check_kernel<5><<<blocks, 256, 0, st>>>(a); break;
+        case 7: viterbi_seg_check_kernel<7><<<blocks, 256, 0, st>>>(a); break;
+        default: return 0;
+    }
+    return 1;
 }
 
 size_t viterbi_tpc_smem_bytes(int S, int W) { return (size_t)W * tpc_stages(S, W) * (tpc_stage_bytes(S) + 16); }
 int viterbi_tpc_max_warps(int S) { return 4; }
 
-template <int S, int W>
+template <int S, int W, bool kSeg>
 static void launch_tpc(const ViterbiArgs& a, cudaStream_t st)
 {
     if constexpr (tpc_stages(S, W) >= 2) {
         const size_t smem = viterbi_tpc_smem_bytes(S, W);
         static PerDevice configured;
-        if (configured.raise(smem)) cudaFuncSetAttribute(viterbi_tpc_kernel<S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        viterbi_tpc_kernel<S, W><<<a.n_slots / W, (W + 1) * 32, smem, st>>>(a, *reinterpret_cast<const CUtensorMap*>(a.ll_map_tpc));
+        if (configured.raise(smem)) cudaFuncSetAttribute(viterbi_tpc_kernel<S, W, kSeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        viterbi_tpc_kernel<S, W, kSeg><<<a.n_slots / W, (W + 1) * 32, smem, st>>>(a, *reinterpret_cast<const CUtensorMap*>(a.ll_map_tpc));
     }
 }
 
 template <int S>
 static void launch_tpc_w(const ViterbiArgs& a, cudaStream_t st)
 {
+    if (a.seg) {                                            // pieces are dealt for four sweep warps per CTA
+        launch_tpc<S, 4, true>(a, st);
+        return;
+    }
     switch (a.warps_per_cta) {
-        case 1: launch_tpc<S, 1>(a, st); break;
-        case 2: launch_tpc<S, 2>(a, st); break;
-        case 3: launch_tpc<S, 3>(a, st); break;
-        default: launch_tpc<S, 4>(a, st); break;
+        case 1: launch_tpc<S, 1, false>(a, st); break;
+        case 2: launch_tpc<S, 2, false>(a, st); break;
+        case 3: launch_tpc<S, 3, false>(a, st); break;
+        default: launch_tpc<S, 4, false>(a, st); break;
     }
 }
 

@@ -126,7 +126,17 @@ EDB200_API void edb200_cohort_destroy(edb200_cohort *c);
 #define EDB200_OPT_CRIT_WARPS  4   /* lane-per-state sweep: warps per CTA of the pass with the longest chains (1, 2, 4) */
 #define EDB200_OPT_SWEEP_WARPS 5   /* sweep warps per CTA (lane-per-state: 4 or 8; thread-per-chain: 1..4), 0 auto */
 #define EDB200_OPT_PACKPLAN    6   /* host pipeline: sweep packing per part as decimal digits, e.g. 122222; 0 auto */
+#define EDB200_OPT_SEGMENTS    7   /* segmented Viterbi sweep (chains cut into concurrently swept, certified pieces): -1 auto, 0 off, 1 on */
+#define EDB200_OPT_SEG_WARM    8   /* warm-up tiles (16 observations each) in front of a piece: 1 .. 64, 0 = default (4) */
+#define EDB200_OPT_SEG_MIN     9   /* shortest piece in tiles, 0 = default (32); small values are for tests */
+#define EDB200_OPT_SEG_REPAIR 10   /* test hook: 1 sends every chain through the repair pass of the segmented sweep */
 EDB200_API int  edb200_cohort_set_option(edb200_cohort *c, int option, int value);
+/* What the last segmented sweep of this cohort did (synchronises the device): out[0] pieces the chains were cut into (0: the
+ * last Viterbi pass was not segmented), out[1] decisions listed with a lead below 2^-14, out[2] chains sent to the repair
+ * pass, out[3] (chain, sample) pairs among them, out[4..9] those pairs by reason: a NaN / Inf in a piece, the list of
+ * decisions full, a seam with non-finite or huge values, a seam whose certified error outgrew its bound, a listed decision on
+ * the final path, the test hook.  For tests and for bench.py's evidence; results never depend on it. */
+EDB200_API int  edb200_cohort_segment_stats(edb200_cohort *c, int32_t out[10]);
 
 /* Size in bytes and device address of the shared log-transition table (for an NCCL broadcast from rank 0). */
 EDB200_API int  edb200_cohort_table(edb200_cohort *c, void **device_ptr, size_t *bytes);

@@ -700,6 +700,58 @@ def test_thread_per_chain_sweep_matches_lane_per_state_sweep(edb, S):
         co.close()
 
 
+@pytest.mark.parametrize("S", [3, 5, 7])
+def test_segmented_sweep_matches_plain_sweep(edb, S):
+    """Chains cut into concurrently swept, certified pieces (viterbi_seam.h) must give the bits of the sequential sweep: for
+    pieces of every size (a few tiles — a seam every ~100 observations — up to the default), warm-ups from one tile up,
+    ragged sample counts, and with every chain forced through the repair pass (the exact re-sweep of refused chains)."""
+    from exomedepth_b200 import synth
+    for ns, nb in ((70, 24000), (33, 9000), (5, 3000)):
+        d = synth.cohort(ns, n_bins=nb)
+        co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=S)
+        want = _run_dev(co, d, S, ns, sweep=1, segments=0)
+        assert want[3].sum() > 0 and co.segment_stats()["pieces"] == 0
+        for seg_min, warm, repair in ((3, 1, 0), (6, 2, 0), (12, 4, 0), (0, 0, 0), (6, 2, 1)):
+            got = _run_dev(co, d, S, ns, sweep=0, segments=1, seg_min=seg_min, seg_warm=warm, seg_repair=repair)
+            st = co.segment_stats()
+            for k, (x, y) in enumerate(zip(want, got)):
+                assert np.array_equal(x, y), (S, ns, seg_min, warm, repair, k, st)
+            lines = (len(d["offsets"]) - 1) * ((ns + 31) // 32)
+            assert st["pieces"] >= lines and (st["pieces"] > lines or seg_min == 0 or nb < 5000), st
+            if repair:
+                assert st["chains_repaired"] == len(d["offsets"]) - 1 and st["pairs_repaired"] == ns * (len(d["offsets"]) - 1), st
+            elif warm >= 2:
+                # a 32-observation warm-up closes nearly every seam of this cohort
+                assert st["pairs_repaired"] <= 0.01 * ns * (len(d["offsets"]) - 1) + 2, st
+        co.set_option("seg_repair", 0)
+        co.close()
+
+
+def test_segmented_sweep_special_emissions(edb):
+    """NaN / -Inf cells (pathological phi) and long runs of bins without any read (every state's likelihood exactly 0: no
+    information, exact ties) across the seams: the pieces that meet them cannot be certified and go to the repair pass;
+    the result is the sequential sweep's either way."""
+    from exomedepth_b200 import synth
+    ns, S = 40, 5
+    d = synth.cohort(ns, n_bins=6000)
+    d["phi"][::7] = 0.93                                   # NaN cells for the low copy-number states
+    d["observed"][:, 100:400] = 0
+    d["observed"][3, :] = 0
+    ref = d["reference"].copy()
+    ref[100:400] = 0                                       # total = 0: every state's likelihood is exactly 0
+    d["reference"] = ref
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=S)
+    a = _run_dev(co, d, S, ns, sweep=1, segments=0)
+    assert np.isnan(a[0]).any()
+    for seg_min, warm in ((3, 1), (8, 4)):
+        b = _run_dev(co, d, S, ns, sweep=0, segments=1, seg_min=seg_min, seg_warm=warm)
+        st = co.segment_stats()
+        for x, y in zip(a[1:], b[1:]):
+            assert np.array_equal(x, y), st
+        assert st["pairs_repaired"] > 0, st               # the NaN samples
+    co.close()
+
+
 def test_thread_per_chain_sweep_special_emissions(edb, port):
     """Pathological phi puts NaN cells into the likelihood matrix (the reference's a1 < 0 rows), zero-count runs make all
     states tie: the structured sweep must follow the oracle port's path through both, like the general sweep."""

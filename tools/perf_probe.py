@@ -20,6 +20,9 @@ ap.add_argument("--states", type=int, default=5)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--direct", action="store_true", help="also time the in-register emission kernel")
 ap.add_argument("--gen", type=int, default=16, help="distinct synthetic samples generated on the host (tiled)")
+ap.add_argument("--seg", type=int, default=-1, help="segmented sweep: -1 auto, 0 off, 1 on")
+ap.add_argument("--seg-min", type=int, default=0)
+ap.add_argument("--seg-warm", type=int, default=0)
 a = ap.parse_args()
 
 edb.init(0)
@@ -34,6 +37,7 @@ exp = np.tile(d["expected"], reps)[:a.samples]
 t0 = time.time()
 co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=a.states)
 print("cohort create (host table build)", time.time() - t0, "table MB", co.table_bytes() / 1e6)
+co.set_option("segments", a.seg).set_option("seg_min", a.seg_min).set_option("seg_warm", a.seg_warm)
 dev = torch.device("cuda:0")
 S, nb, ns = a.states, co.n_bins, a.samples
 obs_t = torch.from_numpy(obs).to(dev)
@@ -82,4 +86,5 @@ for _ in range(3):
 print("per kernel ms:", {k: round(v[1] / v[0], 4) for k, v in _lib.profile_read().items()})
 _lib.profile(False)
 timeit(lambda: co.run_device(obs_t, ref_t, phi_t, exp_t, ll, path, calls, ncalls, what=3), "emission+viterbi", B + 1)
+print("segments", co.segment_stats())
 print("ncalls", ncalls[:8].tolist(), "status", _lib.load().edb200_status(0))
