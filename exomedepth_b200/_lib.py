@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("EDB200_LIB") or os.path.join(_HERE, "libexomedepth_b2
 OK, WARN_NAN, ERR_NSTATES, ERR_CUDA, ERR_ARG, WARN_CALLCAP = 0, 1, 2, 4, 8, 16
 MAX_STATES = 7
 EMISSION_AUTO, EMISSION_DIRECT, EMISSION_TABLE, EMISSION_PANEL = 0, 1, 2, 3
-OPTIONS = dict(sweep=1, parts=2, vsplit=3, crit_warps=4, sweep_warps=5, packplan=6, segments=7, seg_warm=8, seg_min=9, seg_repair=10)      # EDB200_OPT_*
+OPTIONS = dict(sweep=1, parts=2, vsplit=3, crit_warps=4, sweep_warps=5, packplan=6, segments=7, seg_warm=8, seg_min=9, seg_repair=10, reserve=11, chunks=12)      # EDB200_OPT_*
 SWEEP_AUTO, SWEEP_LANE_PER_STATE, SWEEP_THREAD_PER_CHAIN = 0, 1, 2
 
 EXPORTS = (

@@ -9,6 +9,7 @@
 // over a few hundred short segments.  R's sum() accumulates in long double; here every sum is a compensated
 // (two-sum) FP64 accumulation, which carries more than the 64 mantissa bits of x87 long double, combined in a fixed
 // order: the results are deterministic and agree with an exactly rounded sum except in the last bit of rare cases.
+#include <cstdint>
 #include "kernels.cuh"
 
 namespace edb {
@@ -210,11 +211,12 @@ widen_counts_kernel(const uint16_t* __restrict__ src, int64_t src_stride, int32_
 }
 
 __global__ void patch_overflow_kernel(const int64_t* __restrict__ index, const int32_t* __restrict__ value, int64_t n_overflow, int64_t n_bins,
-                                      int32_t* __restrict__ dst, int64_t dst_stride, const __grid_constant__ BinRanges rg)
+                                      int32_t* __restrict__ dst, int64_t dst_stride, const __grid_constant__ BinRanges rg, int64_t s_lo, int64_t s_hi)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_overflow) return;
     const int64_t sample = index[i] / n_bins, b = index[i] - sample * n_bins;
+    if (sample < s_lo || sample >= s_hi) return;
     for (int q = 0; q < rg.n; q++)
         if (b >= rg.b0[q] && b < rg.b1[q]) dst[sample * dst_stride + b] = value[i];
 }
@@ -232,19 +234,19 @@ int launch_widen_counts(const uint16_t* src, int64_t src_stride, int32_t* dst, i
     int launches = 1;
     if (n_overflow > 0) {
         // (dst is row 0 of the batch here: the list's flat indices are absolute)
-        patch_overflow_kernel<<<(unsigned)((n_overflow + 127) / 128), 128, 0, st>>>(ovf_index, ovf_value, n_overflow, n_bins, dst, dst_stride, rg);
+        patch_overflow_kernel<<<(unsigned)((n_overflow + 127) / 128), 128, 0, st>>>(ovf_index, ovf_value, n_overflow, n_bins, dst, dst_stride, rg, 0, INT64_MAX);
         launches++;
     }
     prof_mark(nullptr, st);
     return launches;
 }
 
-// the overflow entries alone, over the bins of `rg` (dst = row 0 of the batch)
+// the overflow entries alone, over the bins of `rg` and the samples s_lo .. s_hi-1 (dst = row 0 of the batch)
 int launch_patch_overflow(int32_t* dst, int64_t dst_stride, int64_t n_bins, const BinRanges& rg, const int64_t* ovf_index,
-                          const int32_t* ovf_value, int64_t n_overflow, cudaStream_t st)
+                          const int32_t* ovf_value, int64_t n_overflow, cudaStream_t st, int64_t s_lo, int64_t s_hi)
 {
     if (n_overflow <= 0) return 0;
-    patch_overflow_kernel<<<(unsigned)((n_overflow + 127) / 128), 128, 0, st>>>(ovf_index, ovf_value, n_overflow, n_bins, dst, dst_stride, rg);
+    patch_overflow_kernel<<<(unsigned)((n_overflow + 127) / 128), 128, 0, st>>>(ovf_index, ovf_value, n_overflow, n_bins, dst, dst_stride, rg, s_lo, s_hi);
     return 1;
 }
 

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -198,7 +199,8 @@ int make_ll_map(const double* ll, int64_t rows, int64_t cols, int64_t pitch, int
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ll), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                              // (L2 promotion to 128 bytes for the 64-byte rows of the half-tile boxes: measured, no change)
+                              // (L2 promotion to 128 / 256 bytes for the 64-byte rows of the half-tile boxes: measured for the latency-bound and for
+                              //  the segmented sweep, no change; an L2 prefetch of the box two stages ahead: 0.67 -> 1.18 ms)
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(EDB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): ll %p rows %lld cols %lld pitch %lld", (int)r, (const void*)ll,
                                        (long long)rows, (long long)cols, (long long)pitch);
@@ -252,14 +254,17 @@ struct edb200_cohort {
     int opt_parts = 0;                   // chromosome groups of a pipelined batch (0 auto)
     int opt_vsplit = -1;                 // device-resident Viterbi as two concurrent passes (-1 auto)
     int opt_crit_warps = 0, opt_sweep_warps = 0, opt_packplan = 0;
-    int opt_segments = -1, opt_seg_warm = 0, opt_seg_min = 0, opt_seg_repair = 0;
-    // segmented sweep (viterbi_seam.h): pieces for `seg_key` (samples, warm-up, shortest piece), scratch, the plain
-    // schedule of the repair pass; seg_ok: the transition terms are small enough for the error bound (ensure_struct)
+    int opt_segments = -1, opt_seg_warm = 0, opt_seg_min = 0, opt_seg_repair = 0, opt_reserve = 0, opt_chunks = 0;
+    // segmented sweep (viterbi_seam.h); seg_ok: the transition terms are small enough for the error bound (ensure_struct)
     int seg_ok = 0;
-    long long seg_key = -1;
-    int seg_pieces = 0, seg_ctas = 0;
-    int seg_last_samples = 0;            // samples of the last Viterbi pass if it was segmented, else 0 (edb200_cohort_segment_stats)
-    DevBuf seg_desc, seg_first, seg_begin, seg_items, seam_in, seam_out, seam_mag, seg_close, seg_flags;
+    int seg_slot = 0;                    // which sample chunk of a host call is being processed (its pieces and flags are its own)
+    bool in_host_call = false;
+    // the pieces of one chromosome group for `key` (samples, warps, warm-up, shortest piece), its scratch and flags
+    struct SegPlan {
+        long long key = -1;
+        int pieces = 0, ctas = 0;
+        DevBuf desc, first, begin, items, seam_in, seam_out, seam_mag, close, flags;
+    };
     // Chromosome groups ("parts"): the chains are split by length so that the emission of the long chromosomes can
     // finish — and their sweeps, the critical path, can start — while the rest is still being computed (or uploaded).
     struct Part {
@@ -271,9 +276,14 @@ struct edb200_cohort {
         int sched_warps = 4;             // sweep warps per CTA the schedule was built for
         int sched_ctas = 1;              // sweep CTAs that have work
         int sched_avail = 0;             // SMs the schedule was allowed to use
+        SegPlan seg;
     };
     std::vector<Part> plans[Context::kMaxParts + 1];   // plans[n]: the split into n parts (built on first use);
                                                        // plans[0]: {the longest chains, the rest} for the device-resident Viterbi
+    // segmented sweeps: all chains as one group, per (samples, chunk slot) — pieces, scratch and flags depend on the sample
+    // count, and the sample chunks of one host call keep their flags apart (edb200_cohort_segment_stats adds them up)
+    std::map<std::pair<int, int>, Part> seg_parts;
+    std::vector<std::pair<Part*, int>> seg_used;       // (group, samples) of the segmented passes since the last top-level call
     // per-batch scratch
     DevBuf consts, bp, ccalls, cncalls, fw_grid, fw_chain, fw_out, fw_best, lattices;
     std::vector<edb200_graph*> graphs;   // captured replays of this cohort (invalidated when the cohort goes)
@@ -771,11 +781,19 @@ void edb200_cohort_destroy(edb200_cohort* c)
             release(part.chain_list);
             release(part.sched_begin);
             release(part.sched_items);
+            for (DevBuf* b : {&part.seg.desc, &part.seg.first, &part.seg.begin, &part.seg.items, &part.seg.seam_in, &part.seg.seam_out,
+                              &part.seg.seam_mag, &part.seg.close, &part.seg.flags})
+                release(*b);
         }
+    for (auto& kv : c->seg_parts) {
+        edb200_cohort::Part& part = kv.second;
+        for (DevBuf* b : {&part.chain_list, &part.sched_begin, &part.sched_items, &part.seg.desc, &part.seg.first, &part.seg.begin, &part.seg.items,
+                          &part.seg.seam_in, &part.seg.seam_out, &part.seg.seam_mag, &part.seg.close, &part.seg.flags})
+            release(*b);
+    }
     DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->tile_base, &c->decay, &c->srows, &c->fw_grid, &c->fw_chain, &c->fw_out, &c->fw_best, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->lattices,
                      &c->h_obs, &c->h_ref, &c->h_phi, &c->h_exp, &c->h_ll, &c->h_path, &c->h_calls, &c->h_ncalls, &c->h_stats, &c->h_cor,
-                     &c->h_obs16, &c->h_ovf_i, &c->h_ovf_v,
-                     &c->seg_desc, &c->seg_first, &c->seg_begin, &c->seg_items, &c->seam_in, &c->seam_out, &c->seam_mag, &c->seg_close, &c->seg_flags};
+                     &c->h_obs16, &c->h_ovf_i, &c->h_ovf_v};
     for (DevBuf* b : all) release(*b);
     delete c;
 }
@@ -827,11 +845,19 @@ int edb200_cohort_set_option(edb200_cohort* c, int option, int value)
             c->opt_seg_min = value;
             break;
         case EDB200_OPT_SEG_REPAIR: c->opt_seg_repair = value != 0; break;
+        case EDB200_OPT_RESERVE: c->opt_reserve = value < 0 ? 0 : value; break;
+        case EDB200_OPT_CHUNKS: c->opt_chunks = value < 0 ? 0 : value; break;
         default: return fail(EDB200_ERR_ARG, "unknown option %d", option);
     }
     for (auto& plan : c->plans)
-        for (auto& part : plan) part.sched_groups = 0;      // schedules are rebuilt under the new options
-    c->seg_key = -1;
+        for (auto& part : plan) {
+            part.sched_groups = 0;                          // schedules are rebuilt under the new options
+            part.seg.key = -1;
+        }
+    for (auto& kv : c->seg_parts) {
+        kv.second.sched_groups = 0;
+        kv.second.seg.key = -1;
+    }
     return 0;
 }
 
@@ -840,17 +866,21 @@ int edb200_cohort_segment_stats(edb200_cohort* c, int32_t out[10])
     if (!c || !out) return fail(EDB200_ERR_ARG, "null argument");
     std::lock_guard<std::mutex> lk(g_mu);
     for (int i = 0; i < 10; i++) out[i] = 0;
-    if (!c->seg_last_samples || !c->seg_flags.p) return 0;
+    if (c->seg_used.empty()) return 0;
     CU(cudaDeviceSynchronize());
-    const int ns = c->seg_last_samples, n_g32 = edb::seg_n_g32(ns);
-    std::vector<int32_t> f(edb::seg_flag_ints(c->n_chains, ns));
-    CU(cudaMemcpy(f.data(), c->seg_flags.p, f.size() * 4, cudaMemcpyDeviceToHost));
-    out[0] = c->seg_pieces;
-    out[1] = f[0];
-    for (int i = 0; i < c->n_chains; i++) out[2] += f[1 + i] != 0;
-    for (size_t i = 1 + (size_t)c->n_chains * (1 + n_g32); i < f.size(); i++) {
-        out[3] += f[i] != 0;
-        for (int b = 0; b < 6; b++) out[4 + b] += (f[i] >> b) & 1;
+    for (auto& used : c->seg_used) {                           // one set of flags per segmented pass
+        edb200_cohort::Part& part = *used.first;
+        const int ns = used.second;
+        if (!part.seg.flags.p || part.seg.key < 0) continue;
+        std::vector<int32_t> f(edb::seg_flag_ints(c->n_chains, ns));
+        CU(cudaMemcpy(f.data(), part.seg.flags.p, f.size() * 4, cudaMemcpyDeviceToHost));
+        out[0] += part.seg.pieces;
+        out[1] += f[0];
+        for (int i = 0; i < c->n_chains; i++) out[2] += f[edb::seg_off_chain(i)] != 0;
+        for (size_t i = edb::seg_off_pair(c->n_chains, ns, 0, 0); i < edb::seg_off_pair(c->n_chains, ns, c->n_chains, 0); i++) {
+            out[3] += f[i] != 0;
+            for (int b = 0; b < 6; b++) out[4 + b] += (f[i] >> b) & 1;
+        }
     }
     return 0;
 }
@@ -1155,6 +1185,7 @@ static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiA
     a.chain_list = (const int32_t*)pt.chain_list.p;
     a.n_list = (int)pt.chains.size();
     a.max_list_tiles = pt.max_tiles;
+    if (!a.only_bad) a.flat_records = (int)pt.chains.size() == c->n_chains ? (int64_t)c->total_tiles * a.groups : 0;
     a.warps_per_cta = pt.sched_warps;
     a.n_slots = pt.sched_ctas * pt.sched_warps;
     a.sched_begin = (const int32_t*)pt.sched_begin.p;
@@ -1164,6 +1195,9 @@ static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiA
 }
 
 // ---- segmented sweep (viterbi_seam.h) ------------------------------------------------------------------------
+// Defaults: a warm-up of 2 tiles (32 observations; 8 already close every seam of the synthetic cohorts, and a seam that does
+// not close only costs its chain the repair pass), pieces of at least 12 tiles.
+constexpr int kSegWarm = 2, kSegMinPiece = 12;
 // Whether to cut the chains: when an even share of all tiles per sweep warp (plus its warm-up) is well below what bounds
 // the plain sweeps — the longest chain, or the whole lines packed onto the warps.
 static bool use_segments(const edb200_cohort* c, int n_samples)
@@ -1179,76 +1213,101 @@ static bool use_segments(const edb200_cohort* c, int n_samples)
     const double slots = 4.0 * g.n_sms;
     const double lane = std::max(150.0 * longest, 165.0 * total * ((n_samples + G - 1) / G) / slots);
     const double tpc = std::max(205.0 * longest, 205.0 * total * ((n_samples + 31) / 32) / slots);
-    const double min_piece = 16.0 * (c->opt_seg_min > 0 ? c->opt_seg_min : 32), warm = 16.0 * (c->opt_seg_warm > 0 ? c->opt_seg_warm : 4);
-    const double share = std::max((double)total * ((n_samples + 31) / 32) / slots, std::min((double)longest, min_piece));
-    return 215.0 * (share + warm) < 0.8 * std::min(lane, tpc);
+    const double min_piece = 16.0 * (c->opt_seg_min > 0 ? c->opt_seg_min : kSegMinPiece), warm = 16.0 * (c->opt_seg_warm > 0 ? c->opt_seg_warm : kSegWarm);
+    // (two sweep warps per SM sub-partition: ~330 cycles per step and warp, twice the warps)
+    const double seg_slots = (double)edb::viterbi_seg_warps(S) * g.n_sms;
+    const double share = std::max((double)total * ((n_samples + 31) / 32) / seg_slots, std::min((double)longest, min_piece));
+    return 330.0 * (share + warm) < 0.8 * std::min(lane, tpc);
 }
 
-// seg sweep, tilemap, trace, expand, check, and the (normally empty) repair pass over all chains, on `st`
-static int viterbi_segmented(edb200_cohort* c, edb::ViterbiArgs a, cudaStream_t st)
+// all chains as one group, for `ns` samples and chunk slot `slot`
+static int seg_part(edb200_cohort* c, int ns, int slot, edb200_cohort::Part** out)
+{
+    edb200_cohort::Part& pt = c->seg_parts[{ns, slot}];
+    if (pt.chains.empty()) {
+        pt.chains.resize(c->n_chains);
+        for (int i = 0; i < c->n_chains; i++) {
+            pt.chains[i] = i;
+            pt.max_tiles = std::max(pt.max_tiles, edb::viterbi_chain_tiles(c->chains_h[i]));
+        }
+        if (int rc = ensure(pt.chain_list, pt.chains.size() * 4)) return rc;
+        CU(cudaMemcpy(pt.chain_list.p, pt.chains.data(), pt.chains.size() * 4, cudaMemcpyHostToDevice));
+    }
+    *out = &pt;
+    return 0;
+}
+
+// seg sweep, tilemap, trace, expand, check, and the (normally empty) repair pass over the chains of one chromosome group
+// on `st`.  The pieces are cut for every SM: they are independent, so CTAs that find the SMs taken
+// (by the emission of the next group) simply run when one frees up.
+static int viterbi_segmented(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiArgs a, cudaStream_t st)
 {
     const int S = c->S, ns = a.n_samples, n_g32 = edb::seg_n_g32(ns);
-    const int warm = c->opt_seg_warm > 0 ? c->opt_seg_warm : 4;
-    const int min_piece = c->opt_seg_min > 0 ? c->opt_seg_min : 32;
-    constexpr int kW = 4, kCloseCap = 1 << 16;
-    if (int rc = build_plan(c, 1)) return rc;
-    edb200_cohort::Part& all = c->plans[1][0];
-    const long long key = ((long long)ns << 24) | ((long long)warm << 16) | (long long)std::min(min_piece, 65535);
-    if (c->seg_key != key) {
-        std::vector<int32_t> tiles(c->n_chains), begin, items, desc, first;
-        for (int i = 0; i < c->n_chains; i++) tiles[i] = edb::viterbi_chain_tiles(c->chains_h[i]);
-        edb::viterbi_cut_pieces(tiles.data(), c->n_chains, n_g32, g.n_sms, kW, warm, min_piece, begin, items, desc, first);
+    const int warm = c->opt_seg_warm > 0 ? c->opt_seg_warm : kSegWarm;
+    const int min_piece = c->opt_seg_min > 0 ? c->opt_seg_min : kSegMinPiece;
+    constexpr int kCloseCap = 1 << 16;
+    const int sw = c->opt_sweep_warps;
+    const int kW = sw == 4 || ((sw == 6 || sw == 8) && sw <= edb::viterbi_seg_warps(S)) ? sw : edb::viterbi_seg_warps(S);
+    edb200_cohort::SegPlan& sp = pt.seg;
+    const long long key = ((long long)ns << 28) | ((long long)kW << 24) | ((long long)warm << 16) | (long long)std::min(min_piece, 65535);
+    const int n_list = (int)pt.chains.size();
+    if (sp.key != key) {
+        std::vector<int32_t> tiles(n_list), begin, items, desc, first;
+        for (int i = 0; i < n_list; i++) tiles[i] = edb::viterbi_chain_tiles(c->chains_h[pt.chains[i]]);
+        edb::viterbi_cut_pieces(tiles.data(), n_list, n_g32, g.n_sms, kW, warm, min_piece, begin, items, desc, first);
+        for (size_t i = 0; i < desc.size(); i += 4) desc[i] = pt.chains[desc[i]];          // index in the group -> chain id
         int n_ctas = g.n_sms;
         while (n_ctas > 1 && begin[(size_t)(n_ctas - 1) * kW] == begin[(size_t)n_ctas * kW]) n_ctas--;
-        c->seg_ctas = n_ctas;
-        c->seg_pieces = (int)(desc.size() / 4);
-        if (int rc = ensure(c->seg_desc, desc.size() * 4)) return rc;
-        if (int rc = ensure(c->seg_first, first.size() * 4)) return rc;
-        if (int rc = ensure(c->seg_begin, begin.size() * 4)) return rc;
-        if (int rc = ensure(c->seg_items, items.size() * 4 + 8)) return rc;
-        if (int rc = ensure(c->seam_in, (size_t)c->seg_pieces * S * 32 * 8)) return rc;
-        if (int rc = ensure(c->seam_out, (size_t)c->seg_pieces * S * 32 * 8)) return rc;
-        if (int rc = ensure(c->seam_mag, (size_t)c->seg_pieces * edb::kSeamWords * 32 * 4)) return rc;
-        if (int rc = ensure(c->seg_close, (size_t)kCloseCap * 16)) return rc;
-        if (int rc = ensure(c->seg_flags, edb::seg_flag_ints(c->n_chains, ns) * 4)) return rc;
-        CU(cudaMemcpyAsync(c->seg_desc.p, desc.data(), desc.size() * 4, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(c->seg_first.p, first.data(), first.size() * 4, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(c->seg_begin.p, begin.data(), begin.size() * 4, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(c->seg_items.p, items.data(), items.size() * 4, cudaMemcpyHostToDevice, st));
+        sp.ctas = n_ctas;
+        sp.pieces = (int)(desc.size() / 4);
+        if (int rc = ensure(sp.desc, desc.size() * 4 + 16)) return rc;
+        if (int rc = ensure(sp.first, first.size() * 4)) return rc;
+        if (int rc = ensure(sp.begin, begin.size() * 4)) return rc;
+        if (int rc = ensure(sp.items, items.size() * 4 + 8)) return rc;
+        if (int rc = ensure(sp.seam_in, (size_t)sp.pieces * S * 32 * 8 + 8)) return rc;
+        if (int rc = ensure(sp.seam_out, (size_t)sp.pieces * S * 32 * 8 + 8)) return rc;
+        if (int rc = ensure(sp.seam_mag, (size_t)sp.pieces * edb::kSeamWords * 32 * 4 + 8)) return rc;
+        if (int rc = ensure(sp.close, (size_t)kCloseCap * 16)) return rc;
+        if (int rc = ensure(sp.flags, edb::seg_flag_ints(c->n_chains, ns) * 4)) return rc;
+        CU(cudaMemcpyAsync(sp.desc.p, desc.data(), desc.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(sp.first.p, first.data(), first.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(sp.begin.p, begin.data(), begin.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(sp.items.p, items.data(), items.size() * 4, cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));          // the vectors go out of scope
-        c->seg_key = key;
+        sp.key = key;
     }
-    c->seg_last_samples = ns;
+    c->seg_used.push_back({&pt, ns});
     a.tpc = 1;
     a.seg = 1;
     a.seg_warm = warm;
-    a.seg_desc = (const int4*)c->seg_desc.p;
-    a.seg_first = (const int32_t*)c->seg_first.p;
-    a.seam_in = (double*)c->seam_in.p;
-    a.seam_out = (double*)c->seam_out.p;
-    a.seam_mag = (unsigned*)c->seam_mag.p;
-    a.seg_close = (int4*)c->seg_close.p;
+    a.seg_desc = (const int4*)sp.desc.p;
+    a.seg_first = (const int32_t*)sp.first.p;
+    a.seam_in = (double*)sp.seam_in.p;
+    a.seam_out = (double*)sp.seam_out.p;
+    a.seam_mag = (unsigned*)sp.seam_mag.p;
+    a.seg_close = (int4*)sp.close.p;
     a.seg_close_cap = kCloseCap;
-    a.seg_flags = (int32_t*)c->seg_flags.p;
+    a.seg_flags = (int32_t*)sp.flags.p;
     a.seg_force_repair = c->opt_seg_repair;
-    a.chain_list = (const int32_t*)all.chain_list.p;
-    a.n_list = (int)all.chains.size();
-    a.max_list_tiles = all.max_tiles;
+    a.chain_list = (const int32_t*)pt.chain_list.p;
+    a.n_list = n_list;
+    a.max_list_tiles = pt.max_tiles;
+    a.flat_records = n_list == c->n_chains ? (int64_t)c->total_tiles * a.groups : 0;
     a.warps_per_cta = kW;
-    a.n_slots = c->seg_ctas * kW;
-    a.sched_begin = (const int32_t*)c->seg_begin.p;
-    a.sched_items = (const int32_t*)c->seg_items.p;
-    CU(cudaMemsetAsync(c->seg_flags.p, 0, edb::seg_flag_ints(c->n_chains, ns) * 4, st));
+    a.n_slots = sp.ctas * kW;
+    a.sched_begin = (const int32_t*)sp.begin.p;
+    a.sched_items = (const int32_t*)sp.items.p;
+    CU(cudaMemsetAsync(sp.flags.p, 0, edb::seg_flag_ints(c->n_chains, ns) * 4, st));
     g_launches += edb::launch_viterbi(a, st);
     edb::prof_mark("viterbi_seg_check", st);
-    g_launches += edb::launch_viterbi_seg_check(a, st);
+    g_launches += edb::launch_viterbi_seg_check(a, sp.pieces, st);
     edb::prof_mark(nullptr, st);
     if (int rc = check_kernel("viterbi (segmented)")) return rc;
     // repair pass: the plain exact sweep and its post-processing over the refused chains (normally none: four launches
     // that find nothing to do)
     a.seg = 0;
     a.only_bad = 1;
-    return viterbi_part(c, all, a, 0, st, 0, kW);
+    return viterbi_part(c, pt, a, 0, st, 0, 4);
 }
 
 static int call_summary(edb200_cohort* c, const edb200_batch* b, bool stats, bool cor, cudaStream_t st)
@@ -1290,6 +1349,7 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
     edb::ViterbiArgs va{};
     alignas(64) CUtensorMap ll_map[2];
     if ((what & 2)) if (int rc = viterbi_prepare(c, b, va, ll_map)) return rc;
+    if ((what & 2) && !c->in_host_call) c->seg_used.clear();
 
     // Device-resident batches run emission, then Viterbi (1 part) unless EDB200_PARTS asks otherwise: both kernels own
     // their SM's shared memory, so overlapping them takes SMs away from the sweep's critical chains — measured slower
@@ -1313,9 +1373,10 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
             // sweep warps on the GPU (the passes then just let the short chromosomes' post-processing start early); beyond
             // that the work is throughput-bound and one balanced launch is better (2,000 samples: 5.6 -> see DESIGN.md)
             if (use_segments(c, b->n_samples)) {
-                if (int rc = viterbi_segmented(c, va, st)) return rc;
+                edb200_cohort::Part* sp = nullptr;
+                if (int rc = seg_part(c, b->n_samples, c->seg_slot, &sp)) return rc;
+                if (int rc = viterbi_segmented(c, *sp, va, st)) return rc;
             } else {
-            c->seg_last_samples = 0;
             const bool split = c->opt_vsplit != 0 && (c->opt_vsplit == 1 || !va.tpc || (int64_t)c->n_chains * ((b->n_samples + 31) / 32) <= 4LL * g.n_sms);
             if (split && c->n_chains >= 4 && va.groups >= 8)
                 if (int rc = build_plan(c, 0)) return rc;
@@ -1512,6 +1573,11 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     if (!c || !b) return fail(EDB200_ERR_ARG, "null argument");
     if (b->n_samples <= 0) return 0;
     std::lock_guard<std::mutex> lk(g_mu);
+    struct HostCall {
+        edb200_cohort* c;
+        explicit HostCall(edb200_cohort* c_) : c(c_) { c->in_host_call = true; c->seg_used.clear(); }
+        ~HostCall() { c->in_host_call = false; c->seg_slot = 0; }
+    } host_call(c);
     cudaStream_t st = g.stream;
     const int S = c->S, ns = b->n_samples;
     const int64_t nb = c->n_bins;
@@ -1561,7 +1627,107 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     } else if (!b->observed)
         return fail(EDB200_ERR_ARG, "no test counts in batch (observed or observed16)");
 
-    if (plan.size() > 1) {
+    // ---- sample-chunk pipeline (segmented sweeps).  With the chains cut into pieces no chromosome is a critical path any
+    // more, so the batch goes through in chunks of SAMPLES: chunk k+1 uploads (contiguous rows) while chunk k runs emission,
+    // then its segmented sweep, on ONE compute stream — both kernels fill every SM; side by side they only trade SMs.
+    // T ~ U / k + G + k * o  (U upload, G device time of the batch, o ~ 0.25 ms of launches, tails and partly filled rounds per
+    // chunk): k ~ sqrt(U / o).
+    int seg_k = 0, seg_per = 0;
+    if (want_vit && !b->per_bin_stride && use_table(c, emission_mode) && c->opt_parts == 0) {
+        if ((rc = ensure_struct(c))) return rc;
+        const double upload_ms = (double)ns * nb * (u16 ? 2.0 : 4.0) / 53e6, per_chunk_ms = 0.25;
+        int k = c->opt_chunks > 0 ? c->opt_chunks : (int)std::lround(std::sqrt(upload_ms / per_chunk_ms));       // (3 at 256 x 200k, 16-bit)
+        k = std::max(1, std::min({k, Context::kMaxParts, ns / 24}));
+        // chunk size: a whole number of rounds of the emission kernel's (sample, state) items over the SMs (64 samples x 5
+        // states on 148 SMs are 2.16 rounds and cost 3)
+        // balanced chunks; when a chunk is a little more than a whole number of rounds of the emission kernel's (sample, state)
+        // items over the SMs (64 samples x 5 states on 148 SMs: 2.16 rounds, which cost 3), one more chunk of whole rounds
+        int per = (ns + k - 1) / k;
+        const double rounds = (double)per * S / g.n_sms;
+        if (rounds > 1.0 && rounds - std::floor(rounds) < 0.25 && k < Context::kMaxParts) {
+            const int per2 = (int)std::floor(rounds) * g.n_sms / S;
+            if ((ns + per2 - 1) / per2 <= k + 1 && ns - per2 * k >= per2 / 2) per = per2;
+        }
+        if (use_segments(c, per)) {
+            seg_per = per;
+            seg_k = (ns + per - 1) / per;
+        }
+    }
+    if (seg_k > 0) {
+        cudaStream_t sc = g.s_copy, sx = g.s_em, sv = g.s_vit[0];
+        if (shared_ref) CU(cudaMemcpyAsync(c->h_ref.p, b->reference, nb * 4, cudaMemcpyHostToDevice, sc));
+        CU(cudaMemcpyAsync(c->h_phi.p, b->phi, ns * 8, cudaMemcpyHostToDevice, sc));
+        CU(cudaMemcpyAsync(c->h_exp.p, b->expected, ns * 8, cudaMemcpyHostToDevice, sc));
+        if (u16 && b->n_overflow > 0) {
+            CU(cudaMemcpyAsync(c->h_ovf_i.p, b->overflow_index, (size_t)b->n_overflow * 8, cudaMemcpyHostToDevice, sc));
+            CU(cudaMemcpyAsync(c->h_ovf_v.p, b->overflow_value, (size_t)b->n_overflow * 4, cudaMemcpyHostToDevice, sc));
+        }
+        edb::BinRanges all{};
+        all.n = 1;
+        all.b0[0] = 0;
+        all.b1[0] = nb;
+        for (int k = 0, s0 = 0; s0 < ns; k++, s0 += seg_per) {
+            const int cnt = std::min(seg_per, ns - s0);
+            edb::prof_mark("h2d_counts", sc);
+            if (u16)
+                CU(cudaMemcpy2DAsync((uint16_t*)c->h_obs16.p + (size_t)s0 * nb, nb * 2, b->observed16 + (size_t)s0 * b->obs16_stride, b->obs16_stride * 2,
+                                     nb * 2, cnt, cudaMemcpyHostToDevice, sc));
+            else
+                CU(cudaMemcpy2DAsync((int32_t*)c->h_obs.p + (size_t)s0 * nb, nb * 4, b->observed + (size_t)s0 * b->obs_stride, b->obs_stride * 4,
+                                     nb * 4, cnt, cudaMemcpyHostToDevice, sc));
+            if (!shared_ref)
+                CU(cudaMemcpy2DAsync((int32_t*)c->h_ref.p + (size_t)s0 * nb, nb * 4, b->reference + (size_t)s0 * b->ref_stride, b->ref_stride * 4,
+                                     nb * 4, cnt, cudaMemcpyHostToDevice, sc));
+            edb::prof_mark(nullptr, sc);
+            if (u16) {
+                g_launches += edb::launch_widen_counts((const uint16_t*)c->h_obs16.p + (size_t)s0 * nb, nb, (int32_t*)c->h_obs.p + (size_t)s0 * nb, nb, cnt, nb,
+                                                       all, nullptr, nullptr, 0, sc);
+                g_launches += edb::launch_patch_overflow((int32_t*)c->h_obs.p, nb, nb, all, (const int64_t*)c->h_ovf_i.p, (const int32_t*)c->h_ovf_v.p,
+                                                         b->n_overflow, sc, s0, s0 + cnt);
+            }
+            CU(cudaEventRecord(g.ev_copy[k], sc));
+            CU(cudaStreamWaitEvent(sx, g.ev_copy[k], 0));
+            edb200_batch e = d;
+            e.n_samples = cnt;
+            e.observed = d.observed + (size_t)s0 * nb;
+            if (!shared_ref) e.reference = d.reference + (size_t)s0 * nb;
+            e.phi = d.phi + s0;
+            e.expected = d.expected + s0;
+            e.ll = d.ll + (size_t)s0 * S * nbp;
+            e.path = d.path + (size_t)s0 * nb;
+            e.calls = d.calls + (size_t)s0 * cap * 4;
+            e.ncalls = d.ncalls + s0;
+            if (d.call_stats) e.call_stats = d.call_stats + (size_t)s0 * cap * 3;
+            if (d.cor) e.cor = d.cor + s0;
+            c->seg_slot = k;
+            // cor(test, reference) needs the counts only: on a stream of its own behind the chunk's upload (one CTA per sample:
+            // 0.18 ms for 64 samples if it ran in line, and on the copy stream it would hold up the next upload)
+            if (d.cor) {
+                CU(cudaStreamWaitEvent(g.s_vit[1], g.ev_copy[k], 0));
+                if ((rc = call_summary(c, &e, false, true, g.s_vit[1]))) return rc;
+            }
+            e.cor = nullptr;
+            // two compute streams: the emission of chunk k+1 behind the emission of chunk k, the Viterbi of chunk k behind its
+            // emission and behind the Viterbi of chunk k-1 (they share the back-pointer scratch) — the SMs a sweep's last CTAs
+            // and the small kernels behind it leave idle go to the next emission
+            if ((rc = edb200_cohort_run_device(c, &e, 1, emission_mode, sx))) return rc;
+            CU(cudaEventRecord(g.ev_em[k], sx));
+            CU(cudaStreamWaitEvent(sv, g.ev_em[k], 0));
+            if ((rc = edb200_cohort_run_device(c, &e, 2 | (d.call_stats ? 4 : 0), emission_mode, sv))) return rc;
+            CU(cudaEventRecord(g.ev_vit[k], sv));
+            if (b->ll || b->path) {
+                CU(cudaStreamWaitEvent(g.stream2, g.ev_vit[k], 0));
+                if (b->ll)
+                    CU(cudaMemcpy2DAsync(b->ll + (size_t)s0 * S * b->ll_stride, b->ll_stride * 8, e.ll, nbp * 8, nb * 8, (size_t)cnt * S,
+                                         cudaMemcpyDeviceToHost, g.stream2));
+                if (b->path)
+                    CU(cudaMemcpy2DAsync(b->path + (size_t)s0 * b->path_stride, b->path_stride, e.path, nb, nb, cnt, cudaMemcpyDeviceToHost, g.stream2));
+            }
+        }
+        CU(cudaEventRecord(g.ev_setup, g.s_vit[1]));
+        CU(cudaStreamWaitEvent(st, g.ev_setup, 0));
+        CU(cudaStreamWaitEvent(st, g.ev_vit[seg_k - 1], 0));
+    } else if (plan.size() > 1) {
         // ---- chromosome-group pipeline over PCIe: the counts of the long chromosomes go up first; their emission and
         // sweep (the critical path) run while the other groups are still uploading; results drain per group.
         edb::ViterbiArgs va{};
@@ -1585,7 +1751,10 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         // The emission launches of the later groups leave that many SMs alone (an emission CTA and a sweep CTA both own their
         // SM's shared memory; emission CTAs are persistent over the launch, so sweep CTAs launched behind them would wait).
         const bool tpc_parts = c->struct_state == 1 && c->opt_sweep != 1;
-        const int reserve = !tpc_parts ? 0 : std::min(g.n_sms / 3, u16 ? 44 : 33);
+        // segmented sweeps (viterbi_seam.h) for every group when cutting pays for the batch as a whole: no chain is a critical
+        // path any more, a group's sweep is ~0.67 ms x its share of the bins x 148 / the SMs it finds free
+        const bool seg_parts = use_segments(c, ns);
+        const int reserve = c->opt_reserve > 0 ? std::min(c->opt_reserve, g.n_sms / 2) : !tpc_parts ? 0 : std::min(g.n_sms / 3, u16 ? 44 : 33);
         for (size_t p = 0; p < plan.size(); p++) {
             const edb::BinRanges& rg = plan[p].ranges;
             edb::prof_mark("h2d_counts", sc);
@@ -1624,7 +1793,9 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
             }
             // the first group (the longest chains) keeps the lane-per-state sweep, two warps per CTA: ~150 instead of ~205 cycles
             // per step of the chain everything else waits for; the other groups take the thread-per-chain sweep
-            if ((rc = viterbi_part(c, plan[p], va, pack, g.s_vit[p], 0, tpc_parts && p > 0 ? 4 : 0))) return rc;
+            if (seg_parts) {
+                if ((rc = viterbi_segmented(c, plan[p], va, g.s_vit[p]))) return rc;
+            } else if ((rc = viterbi_part(c, plan[p], va, pack, g.s_vit[p], 0, tpc_parts && p > 0 ? 4 : 0))) return rc;
             if (b->path)
                 for (int q = 0; q < rg.n; q++) {
                     const int64_t r0 = rg.b0[q], w = rg.b1[q] - r0;

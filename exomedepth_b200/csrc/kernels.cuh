@@ -106,6 +106,7 @@ struct ViterbiArgs {
     const int32_t* chain_list;    // the chains this launch covers (device, [n_list]); null = chains 0 .. n_list-1
     int n_list;
     int max_list_tiles;           // most tiles of any chain in the list (tilemap grid)
+    int64_t flat_records;         // > 0: the launch covers ALL chains — the tilemap kernel walks the records 0 .. flat_records-1 as they lie
     int n_samples;
     int n_states;
     int groups;                   // ceil(n_samples / (32 / n_states)): warps per chromosome
@@ -142,21 +143,33 @@ struct ViterbiArgs {
     int seg;                      // 1: the schedule deals pieces
     int seg_warm;                 // warm-up tiles in front of a piece that does not start its chain
     const int4* seg_desc;         // [n_pieces] (chain, 32-sample group, first recorded tile, end tile)
-    const int32_t* seg_first;     // [n_chains * n_g32 + 1] first piece of every line; a line's pieces are consecutive
+    const int32_t* seg_first;     // [n_list * n_g32 + 1] first piece of every line (chain_list order); a line's pieces are consecutive
+                                  // (for the statistics; the kernels go by seg_desc)
     double* seam_in;              // [n_pieces][S][32] V of a piece after its warm-up
     double* seam_out;             // [n_pieces][S][32] V of a piece after its last observation
     unsigned* seam_mag;           // [n_pieces][kSeamWords][32] magnitudes and error multipliers of a piece (viterbi_seam.h: PieceErr)
     int4* seg_close;              // [seg_close_cap] decisions with a lead below kSegTau: (chain, sample, observation, destination)
     int seg_close_cap;
-    // repair flags, zeroed per run: [0] number of listed decisions, then chain_any[n_chains], line_bad[n_chains * n_g32],
-    // chain_bad[n_chains * n_samples]
+    // repair flags, zeroed per run (layout: seg_off_* below)
     int32_t* seg_flags;
     int only_bad;                 // 1: the repair pass — only the lines / chains whose flags are raised
     int seg_force_repair;         // test hook: the check kernel sends every chain to the repair pass
 };
-// views into ViterbiArgs::seg_flags
+// views into ViterbiArgs::seg_flags: [0] listed decisions, [1] any chain refused, then one word per chain, per line
+// (chain, 32-sample group) and per (chain, sample) ...
 __host__ __device__ inline int seg_n_g32(int n_samples) { return (n_samples + 31) / 32; }
-__host__ __device__ inline size_t seg_flag_ints(int n_chains, int n_samples) { return 1 + (size_t)n_chains * (1 + seg_n_g32(n_samples) + n_samples); }
+__host__ __device__ inline size_t seg_off_chain(int chain) { return 2 + (size_t)chain; }
+__host__ __device__ inline size_t seg_off_line(int n_chains, int n_samples, int chain, int g32) { return 2 + (size_t)n_chains + (size_t)chain * seg_n_g32(n_samples) + g32; }
+__host__ __device__ inline size_t seg_off_pair(int n_chains, int n_samples, int chain, int smp)
+{
+    return 2 + (size_t)n_chains * (1 + seg_n_g32(n_samples)) + (size_t)chain * n_samples + smp;
+}
+// ... and, as doubles, the bound of |C| per line and lane (viterbi_seam.h: piece_cabs_share), 8-byte aligned
+__host__ __device__ inline size_t seg_off_cabs(int n_chains, int n_samples) { return (seg_off_pair(n_chains, n_samples, n_chains, 0) + 1) & ~(size_t)1; }
+__host__ __device__ inline size_t seg_flag_ints(int n_chains, int n_samples)
+{
+    return seg_off_cabs(n_chains, n_samples) + 2 * (size_t)n_chains * seg_n_g32(n_samples) * 32;
+}
 
 // enqueues sweep, tilemap, trace and expand for the chains of a.chain_list (the schedule must cover exactly those);
 // launch_viterbi_compact then concatenates the per-chromosome call tables of ALL chains.  Both return the number of launches.
@@ -164,9 +177,10 @@ int launch_viterbi(const ViterbiArgs& a, cudaStream_t st);
 int launch_viterbi_compact(const ViterbiArgs& a, cudaStream_t st);
 size_t viterbi_smem_bytes(int n_states, int warps_per_cta);
 int launch_viterbi_tpc_sweep(const ViterbiArgs& a, cudaStream_t st);   // viterbi_tpc.cu; 3, 5 or 7 states
-int launch_viterbi_seg_check(const ViterbiArgs& a, cudaStream_t st);   // viterbi_tpc.cu: certifies a segmented sweep (after expand)
+int launch_viterbi_seg_check(const ViterbiArgs& a, int n_pieces, cudaStream_t st);   // viterbi_tpc.cu: certifies a segmented sweep (after expand)
 size_t viterbi_tpc_smem_bytes(int n_states, int warps_per_cta);
 int viterbi_tpc_max_warps(int n_states);
+int viterbi_seg_warps(int n_states);      // sweep warps per CTA of the segmented sweep (4, 6 or 8)
 int viterbi_pick_warps(const int32_t* chain_nobs, int n_chains, int groups, int n_sms);
 int viterbi_lt_pitch(int n_states);      // doubles per table row: S destination rows of S doubles padded to an even count
 int viterbi_tile();                      // observations per tile; the table carries this many spare rows
@@ -204,7 +218,7 @@ int launch_widen_counts(const uint16_t* src, int64_t src_stride, int32_t* dst, i
                         const BinRanges& rg, const int64_t* ovf_index, const int32_t* ovf_value, int64_t n_overflow, cudaStream_t st);
 
 int launch_patch_overflow(int32_t* dst, int64_t dst_stride, int64_t n_bins, const BinRanges& rg, const int64_t* ovf_index,
-                          const int32_t* ovf_value, int64_t n_overflow, cudaStream_t st);
+                          const int32_t* ovf_value, int64_t n_overflow, cudaStream_t st, int64_t s_lo = 0, int64_t s_hi = INT64_MAX);
 
 // ---- select.reference.set correlation sweep (refset.cu) -----------------------------------------------
 // z: [n_samples][k_pad] standardised rows over the selected bins (k_pad = n_sel rounded up to 16, zero padded)

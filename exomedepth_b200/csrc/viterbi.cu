@@ -335,13 +335,24 @@ viterbi_tilemap_kernel(ViterbiArgs a)
     constexpr unsigned kTracked = (S >= 7 ? 0x0FFFFFFFu : ((1u << (4 * S)) - 1u)) | 0xF0000000u;
     constexpr unsigned kOnes = kTracked & 0x11111111u;
     // blockIdx.y walks the launch's chain list, blockIdx.x the chain's records (groups x tiles, G chains each)
-    const int chain = a.chain_list ? a.chain_list[blockIdx.y] : (int)blockIdx.y;
-    if (a.only_bad && a.seg_flags[1 + chain] == 0) return;      // repair pass of the segmented sweep: refused chains only
-    const int64_t n_rec = (int64_t)chain_tiles(a.chains[chain]) * a.groups;
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= n_rec * G) return;
-    const int64_t r = (int64_t)a.bp_tile_base[chain] * a.groups + idx / G;
-    const int gg = (int)(idx % G);
+    int64_t r;
+    int gg;
+    if (a.flat_records > 0) {
+        // every chain is covered: the records lie contiguously, [chain][group][tile] (no block is launched for nothing)
+        const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        if (idx >= a.flat_records * G) return;
+        r = idx / G;
+        gg = (int)(idx % G);
+    } else {
+        if (a.only_bad && a.seg_flags[1] == 0) return;          // repair pass of the segmented sweep, nothing refused
+        const int chain = a.chain_list ? a.chain_list[blockIdx.y] : (int)blockIdx.y;
+        if (a.only_bad && a.seg_flags[seg_off_chain(chain)] == 0) return;      // ... refused chains only
+        const int64_t n_rec = (int64_t)chain_tiles(a.chains[chain]) * a.groups;
+        const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        if (idx >= n_rec * G) return;
+        r = (int64_t)a.bp_tile_base[chain] * a.groups + idx / G;
+        gg = (int)(idx % G);
+    }
     const uint2* __restrict__ rec = reinterpret_cast<const uint2*>(a.bp) + r * kRecU2;
     uint2 w[S];
 #pragma unroll
@@ -382,8 +393,9 @@ viterbi_trace_kernel(ViterbiArgs a, int G)
     const int wid = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (wid >= a.n_samples * a.n_list) return;
     const int smp = wid % a.n_samples;                      // neighbouring warps: same chromosome, same length
+    if (a.only_bad && a.seg_flags[1] == 0) return;
     const int chain = a.chain_list ? a.chain_list[wid / a.n_samples] : wid / a.n_samples;
-    if (a.only_bad && a.seg_flags[1 + chain] == 0) return;
+    if (a.only_bad && a.seg_flags[seg_off_chain(chain)] == 0) return;
     const int grp = smp / G, gg = smp - grp * G;
     const ChainDesc cd = a.chains[chain];
     const int n_tiles = chain_tiles(cd);
@@ -418,8 +430,9 @@ viterbi_expand_kernel(ViterbiArgs a)
     const int wid = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (wid >= a.n_samples * a.n_list) return;
     const int smp = wid % a.n_samples;
+    if (a.only_bad && a.seg_flags[1] == 0) return;
     const int chain = a.chain_list ? a.chain_list[wid / a.n_samples] : wid / a.n_samples;
-    if (a.only_bad && a.seg_flags[1 + chain] == 0) return;
+    if (a.only_bad && a.seg_flags[seg_off_chain(chain)] == 0) return;
     const int grp = smp / G, gg = smp - grp * G;
     const ChainDesc cd = a.chains[chain];
     const int nobs = cd.nobs;
@@ -582,8 +595,14 @@ static void launch_all(const ViterbiArgs& a, cudaStream_t st)
         default: launch_sweep<S, 8>(a, st); break;
     }
     prof_mark(nm[1], st);
-    const int64_t map_threads = (int64_t)a.max_list_tiles * a.groups * G;
-    if (map_threads > 0) viterbi_tilemap_kernel<S><<<dim3((unsigned)((map_threads + 255) / 256), (unsigned)a.n_list), 256, 0, st>>>(a);
+    if (a.flat_records > 0 && !a.only_bad)
+        viterbi_tilemap_kernel<S><<<(unsigned)((a.flat_records * G + 255) / 256), 256, 0, st>>>(a);
+    else {
+        ViterbiArgs b = a;
+        b.flat_records = 0;
+        const int64_t map_threads = (int64_t)a.max_list_tiles * a.groups * G;
+        if (map_threads > 0) viterbi_tilemap_kernel<S><<<dim3((unsigned)((map_threads + 255) / 256), (unsigned)a.n_list), 256, 0, st>>>(b);
+    }
     const int chains = a.n_samples * a.n_list;
     prof_mark(nm[2], st);
     viterbi_trace_kernel<<<(chains + 3) / 4, 128, 0, st>>>(a, G);

@@ -30,7 +30,8 @@
 //
 // The seam itself: segment s - 1, certified up to its end with spread D', hands over X'_end[k]; segment s arrives from
 // its warm-up with X_in[k].  With m = max_k |(X_in[k] - X_in[0]) - (X'_end[k] - X'_end[0])| segment s starts with
-// D_0 <= D' + 2 m.  m is at rounding level when the warm-up has coalesced (every state's value derives from the newest
+// D_0 <= D' + 2 m, D' = (end_b + 1) 2 rho of the previous segment (a segment none of whose steps cancelled the deviation
+// it started with is refused).  m is at rounding level when the warm-up has coalesced (every state's value derives from the newest
 // few observations), and the seam fails (repair) when it has not.
 #pragma once
 #include <cmath>
@@ -44,12 +45,6 @@ constexpr double kSegMagMax = 536870912.0;          // 2^29: magnitudes the acce
 
 // why a chain goes to the repair pass (bits of its flag words; edb200_cohort_segment_stats counts them)
 constexpr int kBadNonFinite = 1, kBadListFull = 2, kBadSeamValues = 4, kBadSeamError = 8, kBadOnPath = 16, kBadForced = 32;
-
-struct SeamState {
-    double eps;        // bound of the spread D of the relative deviations at the end of the segments verified so far
-    double cabs;       // bound of |C| = |R[0] - X[0]|
-    int bad;
-};
 
 // what a piece reports per lane besides its seam vectors (ViterbiArgs::seam_mag, kSeamWords words per lane)
 constexpr int kSeamWords = 6;       // mag_v, mag_e, max_a, max_b, end_a, end_b
@@ -67,10 +62,32 @@ EDB_STEP_HD double mag_bound(unsigned hi2)
     return ldexp(1.0, e - 1022);
 }
 
-// One seam.  x_in: the segment's V after its warm-up; x_prev: the previous segment's V after its last observation;
-// pe: what the segment reported; n_steps: its observations.
+// Every seam is judged on its own (the check kernel runs one thread per seam and sample), which takes a bound of
+// |C| = |R[0] - X[0]| that does not depend on the seams before it.  C changes at a seam by X'_end[0] - X_in[0] (plus the
+// seam's deviation, below kSegTau / 4) and drifts inside a piece by at most D + rho < kSegTau per step; with bv_p the
+// magnitude bound of piece p's values, |X'_end[0]| + |X_in[0]| <= bv_{p-1} + bv_p, so along the whole line
+//     |C| <= sum over its pieces of  2 bv_p + (n_p + 1) kSegTau
+// — each sweep warp adds its piece's share to the line's sum when the piece ends (piece_cabs_share).
+EDB_STEP_HD double piece_cabs_share(unsigned mag_v, int n_steps)
+{
+    return 2.0 * mag_bound(mag_v) * (1.0 + 1e-9) + ((double)n_steps + 1.0) * kSegTau;
+}
+
+// rho of a piece: the rounding of one candidate in both arithmetics, 2^-52 (M_X + M_R).  Values between two recorded
+// observations exceed the recorded bound by at most one emission and one transition term (|log t| <= 1024 for every finite
+// term: capi.cu, ensure_struct); M_R = M_X + |C|.
+EDB_STEP_HD double piece_rho(const PieceErr& pe, double cabs)
+{
+    const double kUlp = 2.220446049250313e-16;                              // 2^-52
+    const double m_x = mag_bound(pe.mag_v) + 2.0 * mag_bound(pe.mag_e) + 2048.0;
+    return kUlp * (2.0 * m_x + cabs + 1.0) * 1.0001;
+}
+
+// One seam.  x_in: the piece's V after its warm-up; x_prev: the previous piece's V after its last observation; pe / prev:
+// what the two pieces reported (prev = null: the previous piece starts the chain, its values are the reference's own);
+// cabs: the line's bound of |C|.  Returns 0 when every decision the piece did not list is certified, else the reason.
 template <int S>
-EDB_STEP_HD void seam_advance(SeamState& s, const double* x_in, const double* x_prev, const PieceErr& pe, int n_steps)
+EDB_STEP_HD int seam_check(const double* x_in, const double* x_prev, const PieceErr& pe, const PieceErr* prev, double cabs)
 {
     double m = 0.0, big = 0.0;
     bool finite = true;
@@ -83,23 +100,19 @@ EDB_STEP_HD void seam_advance(SeamState& s, const double* x_in, const double* x_
         big = fabs(x_prev[k]) > big ? fabs(x_prev[k]) : big;
     }
     const double bv = mag_bound(pe.mag_v), be = mag_bound(pe.mag_e);
-    if (!finite || !(bv < kSegMagMax) || !(be < kSegMagMax)) {
-        s.bad = kBadSeamValues;
-        return;
+    if (!finite || !(bv < kSegMagMax) || !(be < kSegMagMax) || !(cabs < kSegMagMax)) return kBadSeamValues;
+    // spread of the previous piece's deviations at its end: (end_b + 1) 2 rho once a step has cancelled what it started with
+    double eps_prev = 0.0;
+    if (prev) {
+        if (prev->end_a != 0u || !(mag_bound(prev->mag_v) < kSegMagMax) || !(mag_bound(prev->mag_e) < kSegMagMax)) return kBadSeamError;
+        eps_prev = ((double)prev->end_b + 1.0) * 2.0 * piece_rho(*prev, cabs);
     }
-    const double kUlp = 2.220446049250313e-16;                              // 2^-52
-    const double e0 = (s.eps + 2.0 * m + 16.0 * kUlp * big) * 1.0001;      // (the three subtractions behind m, rounded)
-    // |C| at the seam, and its drift inside the segment: |C_{i+1} - C_i| <= D_i + rho, below kSegTau per step
-    const double cabs = s.cabs + fabs(x_prev[0] - x_in[0]) * (1.0 + 4.0 * kUlp) + e0 + (double)n_steps * kSegTau;
-    // values between two recorded observations exceed the recorded bound by at most one emission and one transition term
-    // (|log t| <= 1024 for every finite term: capi.cu, ensure_struct)
-    const double m_x = bv + 2.0 * be + 2048.0;
-    const double m_r = m_x + cabs + 1.0;
-    const double rho = kUlp * (m_x + m_r) * 1.0001;
+    const double kUlp = 2.220446049250313e-16;
+    const double e0 = (eps_prev + 2.0 * m + 16.0 * kUlp * big) * 1.0001;   // (the three subtractions behind m, rounded)
+    const double rho = piece_rho(pe, cabs);
     const double worst = (double)pe.max_a * e0 + ((double)pe.max_b + 2.0) * 2.0 * rho;
-    s.eps = (double)pe.end_a * e0 + ((double)pe.end_b + 1.0) * 2.0 * rho;
-    s.cabs = cabs;
-    if (!(worst <= kSegEpsMax) || !(bv + cabs < kSegMagMax)) s.bad = kBadSeamError;
+    if (!(worst <= kSegEpsMax) || !(bv + cabs < kSegMagMax)) return kBadSeamError;
+    return 0;
 }
 
 }  // namespace edb

@@ -47,11 +47,16 @@ struct PairArgs {
     uint32_t em[S];             // shared-memory address of this lane's two emissions (observations A, B) per HMM state
     uint32_t rows;              // shared-memory address of the two StructRows
     double c0, c1;
+    // segmented sweep only (tpc_pair_margin): where to report, and which decisions these are
+    const ViterbiArgs* va;
+    int chain, smp, obs;        // obs: the first observation of the pair
+    int rec;                    // 0: warm-up (decisions are not recorded, hence not listed)
 };
 template <int S>
 struct PairRes {
     double v[S];
     unsigned acc[S];            // per destination: back-pointer of the first observation | second << 4
+    unsigned kinds;             // tpc_pair_margin: how the two steps move the error multipliers (seg_err_step), bit 0 / bit 1
 };
 
 template <int S>
@@ -96,67 +101,97 @@ __device__ __noinline__ PairRes<S> tpc_pair_exact(const PairArgs<S> a)
 }
 
 // ---- segmented sweep: flags and the certifying step -----------------------------------------------------------------
-struct SegOut {                 // where a piece reports (views into ViterbiArgs::seg_flags / seg_close)
-    int32_t* flags;
-    int4* close;
-    int close_cap;
-    int n_chains, n_samples;
-};
 __device__ __forceinline__ void seg_mark_bad(int32_t* flags, int n_chains, int n_samples, int chain, int smp, int why)
 {
-    const int n_g32 = seg_n_g32(n_samples);
-    flags[1 + chain] = 1;
-    flags[1 + n_chains + chain * n_g32 + (smp >> 5)] = 1;
-    atomicOr(&flags[1 + n_chains * (1 + n_g32) + chain * n_samples + smp], why);
+    flags[1] = 1;
+    flags[seg_off_chain(chain)] = 1;
+    flags[seg_off_line(n_chains, n_samples, chain, smp >> 5)] = 1;
+    atomicOr(&flags[seg_off_pair(n_chains, n_samples, chain, smp)], why);
 }
 
 // One observation of a piece that did not start its chain, whenever the speculative step does not apply: the plain
 // scan with the runner-up (viterbi_step.h: viterbi_step_margin); decisions with a lead below kSegTau are listed for the
 // check kernel.  A NaN / Inf in sight — or more listed decisions than the list holds — sends the chain to the repair pass.
+// Returns the step's kind for the error multipliers.
+template <int S>
+__device__ __forceinline__ int seg_step_margin(double* V, const double* em, const StructRow& row, double c0, double c1, unsigned* arg,
+                                               const ViterbiArgs* va, int chain, int smp, int obs, int rec)
+{
+    unsigned worst = 0;
+#pragma unroll
+    for (int j = 0; j < S; j++) worst = max(worst, max((unsigned)__double2hiint(V[j]) << 1, (unsigned)__double2hiint(em[j]) << 1));
+    if (worst >= 0xFFE00000u) {
+        viterbi_step_struct<S>(V, em, c0, c1, row, arg);
+        if (rec) seg_mark_bad(va->seg_flags, va->n_chains, va->n_samples, chain, smp, kBadNonFinite);
+        return 1;
+    }
+    const unsigned close = viterbi_step_margin<S>(V, em, c0, c1, row, arg);
+    if (close && rec) {
+#pragma unroll 1
+        for (int j = 0; j < S; j++)
+            if (close >> j & 1u) {
+                const int q = atomicAdd(va->seg_flags, 1);
+                if (q < va->seg_close_cap) va->seg_close[q] = make_int4(chain, smp, obs, j);
+                else seg_mark_bad(va->seg_flags, va->n_chains, va->n_samples, chain, smp, kBadListFull);
+            }
+    }
+    return seg_err_kind<S>(arg, close);
+}
+
+// the pair of observations the speculative steps did not settle, for a piece that did not start its chain (out of line)
+template <int S>
+__device__ __noinline__ PairRes<S> tpc_pair_margin(const PairArgs<S> a)
+{
+    PairRes<S> r;
+    double V[S], ea[S], eb[S];
+#pragma unroll
+    for (int j = 0; j < S; j++) {
+        V[j] = a.v[j];
+        const double2 e = lds_f64x2(a.em[j]);
+        ea[j] = e.x;
+        eb[j] = e.y;
+    }
+    const double2 r0a = lds_f64x2(a.rows), r1a = lds_f64x2(a.rows + 32);
+    const StructRow rowA{r0a.x, r0a.y, lds_f64(a.rows + 16), 0.0}, rowB{r1a.x, r1a.y, lds_f64(a.rows + 48), 0.0};
+    unsigned argB[S];
+    const int ka = seg_step_margin<S>(V, ea, rowA, a.c0, a.c1, r.acc, a.va, a.chain, a.smp, a.obs, a.rec);
+    const int kb = seg_step_margin<S>(V, eb, rowB, a.c0, a.c1, argB, a.va, a.chain, a.smp, a.obs + 1, a.rec);
+#pragma unroll
+    for (int j = 0; j < S; j++) {
+        r.acc[j] |= argB[j] << 4;
+        r.v[j] = V[j];
+    }
+    r.kinds = (unsigned)ka | (unsigned)kb << 1;
+    return r;
+}
+
+// one observation of such a piece outside the speculative loop (the ragged ends of a chain; out of line)
 template <int S>
 struct MStepArgs {
     double v[S], em[S];
     double b0, sf, ot, c0, c1;
-    SegOut o;
+    const ViterbiArgs* va;
     int chain, smp, obs;
-    int rec;                    // 0: warm-up (decisions are not recorded, hence not listed)
+    int rec;
 };
 template <int S>
 struct MStepRes {
     double v[S];
     unsigned arg[S];
-    int kind;                   // how the step moves the error multipliers (viterbi_step.h: seg_err_step)
+    int kind;
 };
 template <int S>
 __device__ __noinline__ MStepRes<S> tpc_step_margin(const MStepArgs<S> a)
 {
     MStepRes<S> r;
     double V[S], em[S];
-    unsigned worst = 0;
 #pragma unroll
     for (int j = 0; j < S; j++) {
         V[j] = a.v[j];
         em[j] = a.em[j];
-        worst = max(worst, max((unsigned)__double2hiint(V[j]) << 1, (unsigned)__double2hiint(em[j]) << 1));
     }
     const StructRow row{a.b0, a.sf, a.ot, 0.0};
-    if (worst >= 0xFFE00000u) {
-        viterbi_step_struct<S>(V, em, a.c0, a.c1, row, r.arg);
-        r.kind = 1;
-        if (a.rec) seg_mark_bad(a.o.flags, a.o.n_chains, a.o.n_samples, a.chain, a.smp, kBadNonFinite);
-    } else {
-        const unsigned close = viterbi_step_margin<S>(V, em, a.c0, a.c1, row, r.arg);
-        r.kind = seg_err_kind<S>(r.arg, close);
-        if (close && a.rec) {
-#pragma unroll 1
-            for (int j = 0; j < S; j++)
-                if (close >> j & 1u) {
-                    const int q = atomicAdd(a.o.flags, 1);
-                    if (q < a.o.close_cap) a.o.close[q] = make_int4(a.chain, a.smp, a.obs, j);
-                    else seg_mark_bad(a.o.flags, a.o.n_chains, a.o.n_samples, a.chain, a.smp, kBadListFull);
-                }
-        }
-    }
+    r.kind = seg_step_margin<S>(V, em, row, a.c0, a.c1, r.arg, a.va, a.chain, a.smp, a.obs, a.rec);
 #pragma unroll
     for (int j = 0; j < S; j++) r.v[j] = V[j];
     return r;
@@ -189,23 +224,29 @@ __device__ __forceinline__ TpcItem tpc_item(const ViterbiArgs& a, int it)
         wi.t_begin = wi.t_seam = 0;
         wi.t_end = chain_tiles(a.chains[wi.chain]);
         // the repair pass sweeps only the lines the check kernel refused
-        wi.skip = a.only_bad && a.seg_flags[1 + a.n_chains + wi.chain * seg_n_g32(a.n_samples) + wi.g32] == 0;
+        wi.skip = a.only_bad && a.seg_flags[seg_off_line(a.n_chains, a.n_samples, wi.chain, wi.g32)] == 0;
     }
     return wi;
 }
 
+// kSeg (segmented sweep): no producer warp — every sweep warp issues its own loads kStages half-tiles ahead (the refill
+// of a stage follows the warp barrier behind its last read), so that W = 8 puts two sweep warps on every SM
+// sub-partition with 255 registers each: a ninth warp would leave one sub-partition's register file to three warps.
+// Pieces need throughput, not latency: one sweep warp per sub-partition issues on 30 % of the cycles.
 template <int S, int W, bool kSeg>
-__global__ void __launch_bounds__((W + 1) * 32, 1)
-viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
+__global__ void __launch_bounds__((W + (kSeg ? 0 : 1)) * 32, 1)
+viterbi_tpc_kernel(const __grid_constant__ ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
 {
     constexpr int G = 32 / S;                               // chains per back-pointer record (viterbi_common.cuh)
     constexpr int kStages = tpc_stages(S, W);
     static_assert(kStages >= 2, "ring needs two stages");
     constexpr unsigned kStageBytes = tpc_stage_bytes(S);
     constexpr unsigned kEmBytes = tpc_em_bytes(S);
+    constexpr int kPairUnroll = kSeg ? 1 : kHalf / 2;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(smem) + (uint32_t)W * kStages * kStageBytes;
+    if (!kSeg && a.only_bad && a.seg_flags[1] == 0) return;    // repair pass of a segmented sweep, nothing refused
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < W * 2 * kStages; s++) mbar_init(bar0 + 8u * s, 1);
@@ -213,7 +254,7 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
     }
     __syncthreads();
 
-    if (warp == W) {
+    if (!kSeg && warp == W) {
         // ------------------------------------------------------------------------------------ producer
         if (lane >= W) return;
         const int slot = blockIdx.x * W + lane;
@@ -266,6 +307,40 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
     int st = 0;
     unsigned phase = 0;
     const int slot = blockIdx.x * W + warp;
+    // the warp's own feed (kSeg): the half-tile kStages ahead of the one being swept, walking the same work list
+    int f_it = a.sched_begin[slot], f_t = 0, f_tend = 0, f_i0 = 0, f_c0 = 0, f_c1 = 0, f_st = 0;
+    const int f_end = a.sched_begin[slot + 1];
+    const StructRow* __restrict__ f_rows = nullptr;
+    auto feed = [&]() {
+        while (f_t == f_tend) {
+            if (f_it == f_end) return;
+            const TpcItem fi = tpc_item<kSeg>(a, f_it++);
+            const ChainDesc fd = a.chains[fi.chain];
+            const int64_t t_first = ((fd.em_off + 1) >> 4) + fi.t_begin;
+            f_rows = a.srows + fd.lt_row0;
+            f_i0 = (int)((t_first << 4) - fd.em_off);
+            f_c0 = (int)(t_first << 4);
+            f_c1 = fi.g32 * 32 * S;
+            f_t = 2 * fi.t_begin;
+            f_tend = 2 * fi.t_end;
+        }
+        if (lane == 0) {
+            const int r0 = f_i0 < 0 ? 0 : f_i0;
+            const int n_rows = f_i0 + kHalf - r0;
+            const unsigned row_bytes = n_rows > 0 ? (unsigned)n_rows * (unsigned)sizeof(StructRow) : 0u;
+            const uint32_t dst = ring + (uint32_t)f_st * kStageBytes;
+            mbar_expect_tx(full + 8u * f_st, row_bytes + kEmBytes);
+            tma_load_2d(dst, &ll_map, f_c0, f_c1, full + 8u * f_st);
+            if (row_bytes)
+                tma_load_1d(dst + kEmBytes + (uint32_t)(r0 - f_i0) * (uint32_t)sizeof(StructRow), f_rows + r0, row_bytes, full + 8u * f_st);
+        }
+        f_t++, f_i0 += kHalf, f_c0 += kHalf;
+        f_st = f_st + 1 == kStages ? 0 : f_st + 1;
+    };
+    if (kSeg) {
+#pragma unroll 1
+        for (int q = 0; q < kStages; q++) feed();
+    }
     for (int it = a.sched_begin[slot]; it < a.sched_begin[slot + 1]; it++) {
         const TpcItem wi = tpc_item<kSeg>(a, it);
         if (wi.skip) continue;
@@ -284,7 +359,6 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
         const bool mseg = kSeg && wi.t_seam > 0;
         unsigned mag_v = 0, mag_e = 0;                      // largest (high word << 1) of V / of the emissions since the seam
         unsigned err_a = 0, err_b = 0, max_a = 0, max_b = 0;   // error multipliers of the relative vector (viterbi_step.h: seg_err_step)
-        const SegOut so{a.seg_flags, a.seg_close, a.seg_close_cap, a.n_chains, a.n_samples};
 
         double V[S];
 #pragma unroll
@@ -329,7 +403,10 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
                     for (int w = 0; w < kBitWords; w++) pb[w] = 0u;
 #pragma unroll
                     for (int j = 0; j < S; j++) ovm[j] = ovv[j] = 0u;
-#pragma unroll
+                    // kSeg: one pair per trip — ~230 instructions, inside the 6 KB of a sub-partition's L0 instruction cache; the
+                    // four-pair body streamed from L1.5 on every trip and the warps issued at the rate of that fetch (a
+                    // no_instruction stall at every 128-byte line, 0.25 instructions per cycle and sub-partition)
+#pragma unroll kPairUnroll
                     for (int pp = 0; pp < kHalf / 2; pp++) {
                         double2 en[S];
                         uint32_t ean[S];
@@ -342,7 +419,7 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
                         const uint32_t ra = rows + (uint32_t)pp * 2u * (uint32_t)sizeof(StructRow);
                         const double2 r0a = lds_f64x2(ra), r1a = lds_f64x2(ra + 32);
                         const double r0o = lds_f64(ra + 16), r1o = lds_f64(ra + 48);
-                        if (pp == 2 && more) ready = try_wait_once(full + 8u * st_n, phase_n);       // poll the next stage early
+                        if (pp == 2 && more) ready = try_wait_once(full + 8u * st_n, phase_n);   // poll the next stage early
                         unsigned worst = (unsigned)__double2hiint(V[0]) << 1;
                         double emA[S], emB[S], Vn[S];
                         if (kSeg) {
@@ -388,38 +465,8 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
 #pragma unroll
                         for (int w = 0; w < kBitWords; w++)
                             pb[w] |= ((bitsA >> (4 * w)) & 0xFu) << (8 * pp) | ((bitsB >> (4 * w)) & 0xFu) << (8 * pp + 4);
-                        if (kSeg && mseg) {
-                            if (!ok && live) {
-                                MStepArgs<S> ma;
-#pragma unroll
-                                for (int j = 0; j < S; j++) {
-                                    ma.v[j] = V[j];
-                                    ma.em[j] = emA[j];
-                                }
-                                ma.b0 = rowA.b0, ma.sf = rowA.sf, ma.ot = rowA.ot, ma.c0 = c0, ma.c1 = c1;
-                                ma.o = so;
-                                ma.chain = chain, ma.smp = smp, ma.obs = ih + 2 * pp, ma.rec = rec ? 1 : 0;
-                                const MStepRes<S> ra = tpc_step_margin<S>(ma);
-#pragma unroll
-                                for (int j = 0; j < S; j++) {
-                                    ma.v[j] = ra.v[j];
-                                    ma.em[j] = emB[j];
-                                }
-                                ma.b0 = rowB.b0, ma.sf = rowB.sf, ma.ot = rowB.ot;
-                                ma.obs = ih + 2 * pp + 1;
-                                const MStepRes<S> rb = tpc_step_margin<S>(ma);
-                                seg_err_step(err_a, err_b, ra.kind);
-                                max_b = max(max_b, err_b);
-                                seg_err_step(err_a, err_b, rb.kind);
-                                max_b = max(max_b, err_b);
-#pragma unroll
-                                for (int j = 0; j < S; j++) {
-                                    Vn[j] = rb.v[j];
-                                    ovm[j] |= 0xFFu << (8 * pp);
-                                    ovv[j] |= (ra.arg[j] | rb.arg[j] << 4) << (8 * pp);
-                                }
-                            }
-                        } else if (!ok) {
+                        if (!ok && (!(kSeg && mseg) || live)) {
+                            // (dead lanes of a certified piece sweep zero-filled rows — ties everywhere — and stay out of the slow path)
                             PairArgs<S> pa;
 #pragma unroll
                             for (int j = 0; j < S; j++) {
@@ -429,7 +476,16 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
                             pa.rows = ra;
                             pa.c0 = c0;
                             pa.c1 = c1;
-                            const PairRes<S> pr = tpc_pair_exact<S>(pa);
+                            pa.va = &a;
+                            pa.chain = chain, pa.smp = smp, pa.obs = ih + 2 * pp, pa.rec = rec ? 1 : 0;
+                            PairRes<S> pr;
+                            if (kSeg && mseg) {
+                                pr = tpc_pair_margin<S>(pa);
+                                seg_err_step(err_a, err_b, (int)(pr.kinds & 1u));
+                                max_b = max(max_b, err_b);
+                                seg_err_step(err_a, err_b, (int)(pr.kinds >> 1));
+                                max_b = max(max_b, err_b);
+                            } else pr = tpc_pair_exact<S>(pa);
 #pragma unroll
                             for (int j = 0; j < S; j++) {
                                 Vn[j] = pr.v[j];
@@ -481,7 +537,7 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
                                         mag_e = max(mag_e, (unsigned)__double2hiint(em[j]) << 1);
                                     }
                                     ma.b0 = row.b0, ma.sf = row.sf, ma.ot = row.ot, ma.c0 = c0, ma.c1 = c1;
-                                    ma.o = so;
+                                    ma.va = &a;
                                     ma.chain = chain, ma.smp = smp, ma.obs = i, ma.rec = rec ? 1 : 0;
                                     const MStepRes<S> rm = tpc_step_margin<S>(ma);
                                     seg_err_step(err_a, err_b, rm.kind);
@@ -504,7 +560,8 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
                     else hi[j] = word[j];
                 }
                 __syncwarp();                               // every lane is done with the stage: hand it back
-                if (lane == 0) mbar_arrive(empty + 8u * st);
+                if (kSeg) feed();                           // (... to this warp's own feed: the stage takes the half-tile kStages ahead)
+                else if (lane == 0) mbar_arrive(empty + 8u * st);
                 st = st_n;
                 phase = phase_n;
             }
@@ -523,38 +580,48 @@ viterbi_tpc_kernel(ViterbiArgs a, const __grid_constant__ CUtensorMap ll_map)
             }
             unsigned* pe = a.seam_mag + (int64_t)wi.piece * (kSeamWords * 32) + lane;
             pe[0] = mag_v, pe[32] = mag_e, pe[64] = max_a, pe[96] = max_b, pe[128] = err_a, pe[160] = err_b;
+            // this piece's share of the line's bound of |C| (viterbi_seam.h)
+            double* cabs = reinterpret_cast<double*>(a.seg_flags + seg_off_cabs(a.n_chains, a.n_samples));
+            // (the piece that starts its chain is exact and enters the sum through its last V[0] alone: its V[k > 0] start at -Inf)
+            atomicAdd(cabs + ((int64_t)chain * seg_n_g32(a.n_samples) + g32) * 32 + lane,
+                      piece_cabs_share(mseg ? mag_v : (unsigned)__double2hiint(V[0]) << 1, (wi.t_end - wi.t_seam) * kTile));
         }
     }
 }
 
 // ---- check kernel of the segmented sweep (after expand: it reads the path) --------------------------------------------
-// Part 1, one thread per (chain, sample): walks the seams of the line in order (viterbi_seam.h: seam_advance) and refuses
-// the chain when a seam does not close or the certified error outgrows kSegEpsMax.  Part 2, one thread per listed decision
-// (lead below kSegTau): the decision (observation i, destination j) is read by the traceback only if the path is in
-// state j at observation i; then the chain is refused too.  Refused chains are swept again by the repair pass.
+// Part 1, one thread per (piece, sample): the seam in front of the piece (viterbi_seam.h: seam_check) — the chain is
+// refused when the seam does not close or the certified deviation outgrows kSegEpsMax.  Part 2, one thread per listed
+// decision (lead below kSegTau): the decision (observation i, destination j) is read by the traceback only if the path is
+// in state j at observation i; then the chain is refused too.  Refused chains are swept again by the repair pass.
 template <int S>
-__global__ void __launch_bounds__(256)
-viterbi_seg_check_kernel(ViterbiArgs a)
+__global__ void __launch_bounds__(128)
+viterbi_seg_check_kernel(ViterbiArgs a, int n_pieces)
 {
     const int n_g32 = seg_n_g32(a.n_samples);
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, n_thr = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t q = tid; q < (int64_t)a.n_chains * a.n_samples; q += n_thr) {
-        const int chain = (int)(q / a.n_samples), smp = (int)(q - (int64_t)chain * a.n_samples);
-        const int line = chain * n_g32 + (smp >> 5), lane = smp & 31;
-        SeamState st{0.0, 0.0, a.seg_force_repair ? kBadForced : 0};
-        for (int pc = a.seg_first[line] + 1; pc < a.seg_first[line + 1] && !st.bad; pc++) {
+    const double* cabs = reinterpret_cast<const double*>(a.seg_flags + seg_off_cabs(a.n_chains, a.n_samples));
+    for (int64_t q = tid; q < (int64_t)n_pieces * 32; q += n_thr) {
+        const int pc = (int)(q >> 5), lane = (int)(q & 31);
+        const int4 d = a.seg_desc[pc];
+        const int smp = d.y * 32 + lane;
+        if (smp >= a.n_samples) continue;
+        int bad = a.seg_force_repair ? kBadForced : 0;
+        if (d.z > 0) {                                      // a piece behind a seam; piece pc - 1 is the one before it on its line
             double x_in[S], x_prev[S];
 #pragma unroll
             for (int j = 0; j < S; j++) {
                 x_in[j] = a.seam_in[((int64_t)pc * S + j) * 32 + lane];
                 x_prev[j] = a.seam_out[((int64_t)(pc - 1) * S + j) * 32 + lane];
             }
-            const int4 d = a.seg_desc[pc];
             const unsigned* w = a.seam_mag + (int64_t)pc * (kSeamWords * 32) + lane;
             const PieceErr pe{w[0], w[32], w[64], w[96], w[128], w[160]};
-            seam_advance<S>(st, x_in, x_prev, pe, (d.w - d.z) * kTile);
+            const unsigned* v = w - kSeamWords * 32;
+            const PieceErr prev{v[0], v[32], v[64], v[96], v[128], v[160]};
+            const bool prev_exact = a.seg_desc[pc - 1].z == 0;
+            bad |= seam_check<S>(x_in, x_prev, pe, prev_exact ? nullptr : &prev, cabs[((int64_t)d.x * n_g32 + d.y) * 32 + lane]);
         }
-        if (st.bad) seg_mark_bad(a.seg_flags, a.n_chains, a.n_samples, chain, smp, st.bad);
+        if (bad) seg_mark_bad(a.seg_flags, a.n_chains, a.n_samples, d.x, smp, bad);
     }
     const int n_close = min(a.seg_flags[0], a.seg_close_cap);
     for (int64_t q = tid; q < n_close; q += n_thr) {
@@ -567,14 +634,14 @@ viterbi_seg_check_kernel(ViterbiArgs a)
     }
 }
 
-int launch_viterbi_seg_check(const ViterbiArgs& a, cudaStream_t st)
+int launch_viterbi_seg_check(const ViterbiArgs& a, int n_pieces, cudaStream_t st)
 {
-    const int64_t n = (int64_t)a.n_chains * a.n_samples;
-    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 1184);
+    const int64_t n = (int64_t)n_pieces * 32;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 127) / 128, 2368));
     switch (a.n_states) {
-        case 3: viterbi_seg_check_kernel<3><<<blocks, 256, 0, st>>>(a); break;
-        case 5: viterbi_seg_check_kernel<5><<<blocks, 256, 0, st>>>(a); break;
-        case 7: viterbi_seg_check_kernel<7><<<blocks, 256, 0, st>>>(a); break;
+        case 3: viterbi_seg_check_kernel<3><<<blocks, 128, 0, st>>>(a, n_pieces); break;
+        case 5: viterbi_seg_check_kernel<5><<<blocks, 128, 0, st>>>(a, n_pieces); break;
+        case 7: viterbi_seg_check_kernel<7><<<blocks, 128, 0, st>>>(a, n_pieces); break;
         default: return 0;
     }
     return 1;
@@ -582,6 +649,8 @@ int launch_viterbi_seg_check(const ViterbiArgs& a, cudaStream_t st)
 
 size_t viterbi_tpc_smem_bytes(int S, int W) { return (size_t)W * tpc_stages(S, W) * (tpc_stage_bytes(S) + 16); }
 int viterbi_tpc_max_warps(int S) { return 4; }
+// sweep warps per CTA of the segmented sweep: two per SM sub-partition where two ring stages per warp fit the shared memory
+int viterbi_seg_warps(int S) { return tpc_stages(S, 8) >= 2 ? 8 : tpc_stages(S, 6) >= 2 ? 6 : 4; }
 
 template <int S, int W, bool kSeg>
 static void launch_tpc(const ViterbiArgs& a, cudaStream_t st)
@@ -590,15 +659,17 @@ static void launch_tpc(const ViterbiArgs& a, cudaStream_t st)
         const size_t smem = viterbi_tpc_smem_bytes(S, W);
         static PerDevice configured;
         if (configured.raise(smem)) cudaFuncSetAttribute(viterbi_tpc_kernel<S, W, kSeg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        viterbi_tpc_kernel<S, W, kSeg><<<a.n_slots / W, (W + 1) * 32, smem, st>>>(a, *reinterpret_cast<const CUtensorMap*>(a.ll_map_tpc));
+        viterbi_tpc_kernel<S, W, kSeg><<<a.n_slots / W, (W + (kSeg ? 0 : 1)) * 32, smem, st>>>(a, *reinterpret_cast<const CUtensorMap*>(a.ll_map_tpc));
     }
 }
 
 template <int S>
 static void launch_tpc_w(const ViterbiArgs& a, cudaStream_t st)
 {
-    if (a.seg) {                                            // pieces are dealt for four sweep warps per CTA
-        launch_tpc<S, 4, true>(a, st);
+    if (a.seg) {                                            // pieces are dealt for 4, 6 or 8 self-feeding sweep warps per CTA
+        if (a.warps_per_cta == 8) launch_tpc<S, 8, true>(a, st);
+        else if (a.warps_per_cta == 6) launch_tpc<S, 6, true>(a, st);
+        else launch_tpc<S, 4, true>(a, st);
         return;
     }
     switch (a.warps_per_cta) {

@@ -127,9 +127,11 @@ EDB200_API void edb200_cohort_destroy(edb200_cohort *c);
 #define EDB200_OPT_SWEEP_WARPS 5   /* sweep warps per CTA (lane-per-state: 4 or 8; thread-per-chain: 1..4), 0 auto */
 #define EDB200_OPT_PACKPLAN    6   /* host pipeline: sweep packing per part as decimal digits, e.g. 122222; 0 auto */
 #define EDB200_OPT_SEGMENTS    7   /* segmented Viterbi sweep (chains cut into concurrently swept, certified pieces): -1 auto, 0 off, 1 on */
-#define EDB200_OPT_SEG_WARM    8   /* warm-up tiles (16 observations each) in front of a piece: 1 .. 64, 0 = default (4) */
-#define EDB200_OPT_SEG_MIN     9   /* shortest piece in tiles, 0 = default (32); small values are for tests */
+#define EDB200_OPT_SEG_WARM    8   /* warm-up tiles (16 observations each) in front of a piece: 1 .. 64, 0 = default (2) */
+#define EDB200_OPT_SEG_MIN     9   /* shortest piece in tiles, 0 = default (12); small values are for tests */
 #define EDB200_OPT_SEG_REPAIR 10   /* test hook: 1 sends every chain through the repair pass of the segmented sweep */
+#define EDB200_OPT_CHUNKS     12   /* host call with segmented sweeps: sample chunks the batch is pipelined over, 0 auto */
+#define EDB200_OPT_RESERVE    11   /* host pipeline: SMs the emission launches of the later groups leave to the sweeps, 0 auto */
 EDB200_API int  edb200_cohort_set_option(edb200_cohort *c, int option, int value);
 /* What the last segmented sweep of this cohort did (synchronises the device): out[0] pieces the chains were cut into (0: the
  * last Viterbi pass was not segmented), out[1] decisions listed with a lead below 2^-14, out[2] chains sent to the repair

@@ -907,6 +907,49 @@ def test_16_bit_count_layout_matches_32_bit(edb):
         co.close()
 
 
+def test_sample_chunk_pipeline_matches_single_pass(edb):
+    """The host call with segmented sweeps moves the batch through in chunks of samples (upload k+1 | emission and sweep of
+    chunk k): every output — likelihoods, paths, call tables, per-call sums, correlations — must equal the unsegmented
+    single pass bit for bit; ragged chunk sizes (a last chunk that is not a multiple of 32), 1 to 4 chunks, int32 and
+    16-bit counts with overflow entries in every chunk, a per-sample reference, pieces of a few tiles."""
+    from exomedepth_b200 import _lib, synth
+    ns, nb, S = 150, 20000, 5
+    d = synth.cohort(30, n_bins=nb)
+    obs = np.tile(d["observed"], (5, 1))
+    rng = np.random.default_rng(11)
+    for s in range(0, ns, 7):
+        obs[s, rng.integers(nb)] = int(rng.integers(65535, 200000))
+    phi, ex = np.tile(d["phi"], 5), np.tile(d["expected"], 5)
+    ref = np.tile(d["reference"], (ns, 1)) + rng.integers(0, 3, (ns, 1)).astype(np.int32)        # per-sample references
+    co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=S)
+    co.set_option("segments", 0)
+    want = co.run_host(obs, ref, phi, ex, call_cap=256, mode=_lib.EMISSION_TABLE, want_stats=True)
+    assert co.segment_stats()["pieces"] == 0 and want["ncalls"].sum() > 0
+    u16, idx, val = edb.pack_counts(obs)
+    co.set_option("segments", 1).set_option("seg_min", 6).set_option("seg_warm", 2)
+    for chunks in (1, 2, 3, 4):
+        co.set_option("chunks", chunks)
+        for counts, ovf in ((obs, None), (u16, (idx, val))):
+            got = co.run_host(counts, ref, phi, ex, call_cap=256, mode=_lib.EMISSION_TABLE, want_stats=True, overflow=ovf)
+            st = co.segment_stats()
+            for k in ("ll", "path", "calls", "ncalls", "call_stats", "cor"):
+                assert np.array_equal(got[k], want[k], equal_nan=True), (chunks, k, st)
+            assert st["pieces"] > 25 * 5 and st["pairs_repaired"] <= 0.01 * ns * 25 + 2, st
+    # the same through the shared-reference form and without the likelihood matrix / path
+    want = None
+    for seg in (0, 1):
+        co.set_option("segments", seg).set_option("chunks", 3)
+        got = co.run_host(u16, d["reference"], phi, ex, call_cap=256, mode=_lib.EMISSION_TABLE, want_ll=False, want_path=False, want_stats=True,
+                          overflow=(idx, val))
+        keep = {k: got[k].copy() for k in ("calls", "ncalls", "call_stats", "cor")}
+        if want is None:
+            want = keep
+        else:
+            for k in keep:
+                assert np.array_equal(keep[k], want[k], equal_nan=True), k
+    co.close()
+
+
 def test_cohort_call_glue_on_exomecount(edb, exomecount, refvec2):
     """r_glue_cohort.c (`.Call("edb_cohort_callcnvs", ...)`, one call per COHORT) driven with fake SEXPs like R: the four
     leave-one-out ExomeCount samples as the columns of one count matrix, each with its own reference column — the

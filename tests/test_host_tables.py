@@ -35,3 +35,18 @@ def test_structured_viterbi_step_native(tmp_path):
                     "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_segmented_sweep_native(tmp_path):
+    """The segmented Viterbi sweep's logic on the CPU (tests/native/segments_check.cpp): the piece cutter of host_tables.cpp,
+    the lead-reporting steps of viterbi_step.h against the plain scan of src/hmm.cpp:66-88, and the certification scheme of
+    viterbi_seam.h end to end — every certified decision of chains swept as pieces equals the sequential sweep's."""
+    cxx = shutil.which("g++") or shutil.which("c++")
+    if not cxx:
+        pytest.skip("no C++ compiler")
+    exe = str(tmp_path / "segments_check")
+    subprocess.run([cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-pthread", "-I", CSRC,
+                    os.path.join(ROOT, "tests", "native", "segments_check.cpp"), os.path.join(CSRC, "host_tables.cpp"),
+                    "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-3000:] + r.stderr[-2000:]

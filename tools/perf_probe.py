@@ -23,6 +23,7 @@ ap.add_argument("--gen", type=int, default=16, help="distinct synthetic samples 
 ap.add_argument("--seg", type=int, default=-1, help="segmented sweep: -1 auto, 0 off, 1 on")
 ap.add_argument("--seg-min", type=int, default=0)
 ap.add_argument("--seg-warm", type=int, default=0)
+ap.add_argument("--warps", type=int, default=0)
 a = ap.parse_args()
 
 edb.init(0)
@@ -37,7 +38,7 @@ exp = np.tile(d["expected"], reps)[:a.samples]
 t0 = time.time()
 co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=a.states)
 print("cohort create (host table build)", time.time() - t0, "table MB", co.table_bytes() / 1e6)
-co.set_option("segments", a.seg).set_option("seg_min", a.seg_min).set_option("seg_warm", a.seg_warm)
+co.set_option("segments", a.seg).set_option("seg_min", a.seg_min).set_option("seg_warm", a.seg_warm).set_option("sweep_warps", a.warps)
 dev = torch.device("cuda:0")
 S, nb, ns = a.states, co.n_bins, a.samples
 obs_t = torch.from_numpy(obs).to(dev)
