@@ -327,8 +327,9 @@ def gpu_arm(a, rank, world):
     launches = _lib.launch_count()
     prof = _lib.profile_read()          # {kernel: (launches, total ms, longest ms)} over exactly the timed region
     _lib.profile(False)
-    # device time per step and kernel.  The sweep runs as two CONCURRENT launches per step (longest chromosomes | all
-    # others, forked from the same point): the step pays for the longer one, so that is the duration the roofline uses.
+    # device time per step and kernel.  An unsegmented sweep runs as two CONCURRENT launches per step (longest chromosomes |
+    # all others, forked from the same point): the step pays for the longer one, so that is the duration the roofline uses;
+    # the segmented sweep (the default at this shape) is one launch.
     kt = {k: (v[2] if k == "viterbi_sweep" and v[0] > a.steps else v[1] / a.steps) for k, v in prof.items()}
     launches_per_step = {k: v[0] / a.steps for k, v in prof.items()}
     clocks = sampler.stop() if rank == 0 else None
@@ -338,6 +339,9 @@ def gpu_arm(a, rank, world):
     ms = float(t[0])
     total_calls = int(ncalls.sum())
     status = _lib.load().edb200_status(0)
+    # what the segmented sweep of the last timed step did: pieces, decisions listed with a lead below 2^-14, chains that
+    # went to the exact repair pass (include/exomedepth_b200.h: edb200_cohort_segment_stats)
+    segments = co.segment_stats()
 
     # ---- parity of THE BENCHMARKED BUFFERS (untimed): four samples of the batch the timed steps just produced against the C
     # restatement at the benchmark's state count, and the same four samples through the same kernels at 3 states against the
@@ -403,7 +407,8 @@ def gpu_arm(a, rank, world):
                    counts_layout=f"uint16 [sample][bin] + overflow list ({int(ovf_i.size)} entries) — edb200_batch.observed16",
                    api="edb200_cohort_run_host (C ABI, pinned host buffers): counts in; CNV call table, per-call BF / reads.expected / "
                        "reads.observed sums and cor(test, reference) out — the output of CallCNVs; likelihood matrix resident in HBM; "
-                       "chromosome groups pipelined over PCIe (upload | emission | Viterbi)")
+                       "sample chunks pipelined over PCIe (upload k+1 | emission k+1 | segmented Viterbi k)",
+                   segmented_sweep=co.segment_stats())
         e2e["int32_counts"] = dict(timed(base, counts=obs_p, want_ll=False, want_path=False), h2d_bytes_per_step=int(obs_p.nbytes + ref.nbytes + phi_h.nbytes + exp_h.nbytes),
                                    note="the same call with the counts as int32 [sample][bin] (edb200_batch.observed)")
         with_path = dict(base, path=hb.empty((ns, nb), np.int8))
@@ -568,7 +573,7 @@ def gpu_arm(a, rank, world):
                            cache="inputs+outputs per step (2.3 GB) exceed the 126 MB L2; no flush needed",
                            shared_metadata="bin geometry, reference aggregate and host-libm log-transition table NCCL-broadcast from rank 0"
                            if world > 1 else "single rank", table_build_s=table_s, total_calls=total_calls, status=status, nproc=os.cpu_count()),
-               clocks=clocks, e2e=e2e, gpu_launches=int(launches), parity=parity, roofline=roof(dom),
+               clocks=clocks, e2e=e2e, gpu_launches=int(launches), parity=parity, segmented_sweep=segments, roofline=roof(dom),
                roofline_other=roof("emission" if dom != "emission" else "viterbi_sweep"),
                kernel_ms_per_step={k: round(v, 5) for k, v in sorted(kt.items(), key=lambda kv: -kv[1])}, aux=aux)
     if world == 1 and not a.no_cpu:

@@ -1205,6 +1205,9 @@ static bool use_segments(const edb200_cohort* c, int n_samples)
     if (c->struct_state != 1 || !c->seg_ok || c->opt_sweep == 1 || c->opt_segments == 0) return false;
     if (c->opt_segments == 1) return true;
     const int S = c->S, G = 32 / S;
+    // measured: 3 and 5 states (256 x 200k x 5: sweep 1.51 -> 0.60 ms; 2,000 samples: 4.4 -> 4.3).  The 7-state instantiation
+    // spills (255 registers) and runs six warps per CTA: 0.53 ms where the plain sweeps take 0.17 on the 512 x 5,000 panel.
+    if (S == 7) return false;
     int64_t longest = 0, total = 0;
     for (const auto& cd : c->chains_h) {
         longest = std::max<int64_t>(longest, cd.nobs);
@@ -1217,7 +1220,9 @@ static bool use_segments(const edb200_cohort* c, int n_samples)
     // (two sweep warps per SM sub-partition: ~330 cycles per step and warp, twice the warps)
     const double seg_slots = (double)edb::viterbi_seg_warps(S) * g.n_sms;
     const double share = std::max((double)total * ((n_samples + 31) / 32) / seg_slots, std::min((double)longest, min_piece));
-    return 330.0 * (share + warm) < 0.8 * std::min(lane, tpc);
+    // ... and only where a chain is long enough to bound the batch (panels of a few thousand bins are launch- and
+    // tail-bound: the check and repair launches of the segmented pass cost more than the cut saves)
+    return longest >= 4096 && 330.0 * (share + warm) < 0.8 * std::min(lane, tpc);
 }
 
 // all chains as one group, for `ns` samples and chunk slot `slot`

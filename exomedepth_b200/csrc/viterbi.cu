@@ -334,25 +334,21 @@ viterbi_tilemap_kernel(ViterbiArgs a)
     constexpr int G = 32 / S;
     constexpr unsigned kTracked = (S >= 7 ? 0x0FFFFFFFu : ((1u << (4 * S)) - 1u)) | 0xF0000000u;
     constexpr unsigned kOnes = kTracked & 0x11111111u;
-    // blockIdx.y walks the launch's chain list, blockIdx.x the chain's records (groups x tiles, G chains each)
-    int64_t r;
-    int gg;
-    if (a.flat_records > 0) {
-        // every chain is covered: the records lie contiguously, [chain][group][tile] (no block is launched for nothing)
-        const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-        if (idx >= a.flat_records * G) return;
-        r = idx / G;
-        gg = (int)(idx % G);
-    } else {
+    // the records of this thread: all chains as they lie (flat), or the launch's chain blockIdx.y (grid-stride: the repair
+    // pass of a segmented sweep launches a few blocks per chain, which normally find nothing to do)
+    int64_t first, count, step = (int64_t)gridDim.x * blockDim.x, base = 0;
+    if (a.flat_records > 0) count = a.flat_records * G;
+    else {
         if (a.only_bad && a.seg_flags[1] == 0) return;          // repair pass of the segmented sweep, nothing refused
         const int chain = a.chain_list ? a.chain_list[blockIdx.y] : (int)blockIdx.y;
         if (a.only_bad && a.seg_flags[seg_off_chain(chain)] == 0) return;      // ... refused chains only
-        const int64_t n_rec = (int64_t)chain_tiles(a.chains[chain]) * a.groups;
-        const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-        if (idx >= n_rec * G) return;
-        r = (int64_t)a.bp_tile_base[chain] * a.groups + idx / G;
-        gg = (int)(idx % G);
+        count = (int64_t)chain_tiles(a.chains[chain]) * a.groups * G;
+        base = (int64_t)a.bp_tile_base[chain] * a.groups;
     }
+    first = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int64_t idx = first; idx < count; idx += step) {
+    const int64_t r = base + idx / G;
+    const int gg = (int)(idx % G);
     const uint2* __restrict__ rec = reinterpret_cast<const uint2*>(a.bp) + r * kRecU2;
     uint2 w[S];
 #pragma unroll
@@ -380,6 +376,7 @@ viterbi_tilemap_kernel(ViterbiArgs a)
         cur = st1 * kOnes;
     }
     reinterpret_cast<unsigned*>(a.bp)[r * kRecU32 + kMapOff + gg] = cur;
+    }
 }
 
 // =========================================================================================== trace
@@ -601,7 +598,8 @@ static void launch_all(const ViterbiArgs& a, cudaStream_t st)
         ViterbiArgs b = a;
         b.flat_records = 0;
         const int64_t map_threads = (int64_t)a.max_list_tiles * a.groups * G;
-        if (map_threads > 0) viterbi_tilemap_kernel<S><<<dim3((unsigned)((map_threads + 255) / 256), (unsigned)a.n_list), 256, 0, st>>>(b);
+        const unsigned bx = (unsigned)((map_threads + 255) / 256);
+        if (map_threads > 0) viterbi_tilemap_kernel<S><<<dim3(a.only_bad ? std::min(bx, 16u) : bx, (unsigned)a.n_list), 256, 0, st>>>(b);
     }
     const int chains = a.n_samples * a.n_list;
     prof_mark(nm[2], st);

@@ -1,4 +1,12 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q > gpurun_out/all_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/all_pytest.log
-for o in "chunks=0" "chunks=2" "chunks=3" "chunks=4" "chunks=6" "segments=0"; do timeout 200 python tools/e2e_probe.py --opts $o --reps 8 2>&1 | grep "^calls+stats " ; done
-timeout 200 python tools/e2e_probe.py --reps 3 --timeline > gpurun_out/e2e_timeline.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/all_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/all_pytest.log
+timeout 100 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 400 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err
+python - <<PY
+import json
+j = json.loads(open("gpurun_out/bench.json").read().strip().splitlines()[-1])
+print(j["value"], j["ms_per_step"], "e2e", j["e2e"]["ms_per_step"], j["e2e"]["value"], "roof", j["roofline"]["kernel"], j["roofline"]["frac"], j["roofline_other"]["kernel"], j["roofline_other"]["frac"])
+print(j["kernel_ms_per_step"]); print(j["segmented_sweep"]); print(j["parity"]); print(j["clocks"])
+print({k: (v.get("ms_per_step"), v.get("value")) for k, v in j["e2e"].items() if isinstance(v, dict) and "ms_per_step" in v})
+print(json.dumps(j["aux"].get("large_cohort_one_gpu"))[:600]); print(json.dumps(j["aux"].get("small_panel"))[:900])
+PY
