@@ -24,7 +24,7 @@ EXPORTS = (
     "edb200_cohort_run_host", "edb200_status", "edb200_profile", "edb200_profile_read",
     "edb200_cohort_forward_device", "edb200_cohort_forward_last",
     "edb200_refset_correlations", "edb200_refset_kpad", "edb200_refset_standardize_device", "edb200_refset_gram_device",
-    "edb200_betabin_fit", "edb200_betabin_fit_device",
+    "edb200_betabin_fit", "edb200_betabin_fit_device", "edb200_power_betabinom", "edb200_gsl_error_log",
     "edb200_refset_block_alloc", "edb200_refset_peers_open", "edb200_refset_peers_close", "edb200_refset_gram_peers_device",
 )
 
@@ -127,6 +127,10 @@ def load():
     L.edb200_refset_gram_peers_device.argtypes = [i32, i32, i32, i64, vp, vp]
     L.edb200_betabin_fit.restype = C.c_int
     L.edb200_betabin_fit.argtypes = [vp, i64, vp, i64, i32, i64, vp, vp, vp, vp]
+    L.edb200_gsl_error_log.restype = C.c_int64
+    L.edb200_gsl_error_log.argtypes = [C.c_char_p, C.c_size_t, C.c_int64, C.POINTER(C.c_int64)]
+    L.edb200_power_betabinom.restype = C.c_int
+    L.edb200_power_betabinom.argtypes = [vp, vp, vp, vp, i32, vp]
     L.edb200_betabin_fit_device.restype = C.c_int
     L.edb200_betabin_fit_device.argtypes = [vp, i64, vp, i64, i32, i64, vp, vp, vp, vp, vp]
     L.edb200_status.restype = C.c_int

@@ -29,6 +29,17 @@ def fit(observed, reference):
     return dict(expected=mu, phi=phi, loglik=ll, info=info)
 
 
+def get_power_betabinom_batch(size, my_phi, my_p, my_alt_p):
+    """get.power.betabinom for arrays of problems on the GPU (edb200_power_betabinom, one CTA per problem); the scalar
+    function below is the host restatement the tests compare it with."""
+    size = np.ascontiguousarray(np.asarray(size, np.int32))
+    phi, p, ap = (np.ascontiguousarray(np.broadcast_to(np.asarray(v, np.float64), size.shape)) for v in (my_phi, my_p, my_alt_p))
+    out = np.empty(size.shape, np.float64)
+    _lib.check(_lib.load().edb200_power_betabinom(size.ctypes.data, phi.ctypes.data, p.ctypes.data, ap.ctypes.data, size.size, out.ctypes.data),
+               "edb200_power_betabinom")
+    return out
+
+
 def _ldbetabinom(x, size, a, b):
     """log dbetabinom.ab(x, size, a, b) — VGAM's density, from lgamma."""
     lg = math.lgamma

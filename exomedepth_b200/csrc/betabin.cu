@@ -267,6 +267,57 @@ betabin_fit_kernel(CountsView c, int n_samples, int64_t n_bins, TableDims dims, 
     }
 }
 
+// ---- expected Bayes factor of get.power.betabinom (R/tools.R:128-166; theory = FALSE, limit = FALSE) -----------------
+// One CTA per problem (size, phi, p, alt.p):  sum over x = 0 .. size of  dbetabinom.ab(x | alt) * log10(e) * (log dbetabinom.ab(x | alt)
+// - log dbetabinom.ab(x | null)).  The binomial coefficients cancel in the difference; every thread takes x = t, t + 256, ...
+// into a compensated sum, the 256 partial sums are added in thread order (deterministic).
+constexpr int kPowerThreads = 256;
+__global__ void __launch_bounds__(kPowerThreads)
+power_betabinom_kernel(const int32_t* __restrict__ size_in, const double* __restrict__ phi_in, const double* __restrict__ p_in,
+                       const double* __restrict__ alt_in, double* __restrict__ out)
+{
+    __shared__ double part[kPowerThreads], comp[kPowerThreads];
+    const int q = blockIdx.x;
+    const int size = size_in[q];
+    const double phi = phi_in[q], p = p_in[q], ap = alt_in[q];
+    const double a0 = p * (1 - phi) / phi, b0 = (1 - p) * (1 - phi) / phi;          // R/tools.R:132-135
+    const double a1 = ap * (1 - phi) / phi, b1 = (1 - ap) * (1 - phi) / phi;
+    const double n = (double)size;
+    const double k0 = lgamma(a0 + b0 + n) + (lgamma(a0) + lgamma(b0) - lgamma(a0 + b0));
+    const double k1 = lgamma(a1 + b1 + n) + (lgamma(a1) + lgamma(b1) - lgamma(a1 + b1));
+    const double lfn = lgamma(n + 1.0);
+    double s = 0.0, c = 0.0;
+    for (int x = threadIdx.x; x <= size; x += kPowerThreads) {
+        const double xd = (double)x;
+        const double choose = lfn - lgamma(xd + 1.0) - lgamma(n - xd + 1.0);
+        const double l1 = lgamma(a1 + xd) + lgamma(b1 + n - xd) - k1, l0 = lgamma(a0 + xd) + lgamma(b0 + n - xd) - k0;
+        const double t = exp(choose + l1) * (0.43429448190325182765 * (l1 - l0));
+        const double u = s + t, bp = u - s;
+        c += (s - (u - bp)) + (t - bp);
+        s = u;
+    }
+    part[threadIdx.x] = s;
+    comp[threadIdx.x] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double S = 0.0, C = 0.0;
+        for (int t = 0; t < kPowerThreads; t++) {
+            const double v = part[t], u = S + v, bp = u - S;
+            C += (S - (u - bp)) + (v - bp) + comp[t];
+            S = u;
+        }
+        out[q] = size < 0 || !(phi > 0.0 && phi < 1.0) ? __longlong_as_double(0x7ff8000000000000LL) : S + C;
+    }
+}
+
+void launch_power_betabinom(const int32_t* size, const double* phi, const double* p, const double* alt_p, int n, double* out, cudaStream_t st)
+{
+    if (n <= 0) return;
+    prof_mark("power_betabinom", st);
+    power_betabinom_kernel<<<n, kPowerThreads, 0, st>>>(size, phi, p, alt_p, out);
+    prof_mark(nullptr, st);
+}
+
 size_t betabin_fit_smem_bytes(TableDims d)
 {
     return sizeof(int) * ((size_t)d.K + d.R + d.N + kFitThreads) + sizeof(double) * 32 * 6 + 64;
@@ -277,11 +328,8 @@ void launch_betabin_fit(CountsView c, int n_samples, int64_t n_bins, TableDims d
 {
     if (n_samples == 0) return;
     const size_t smem = betabin_fit_smem_bytes(dims);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(betabin_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static PerDevice configured;
+    if (configured.raise(smem)) cudaFuncSetAttribute(betabin_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     prof_mark("betabin_fit", st);
     betabin_fit_kernel<<<n_samples, kFitThreads, smem, st>>>(c, n_samples, n_bins, dims, max_iter, (int2*)overflow, ovf_cap, mu, phi, loglik, info);
     prof_mark(nullptr, st);

@@ -43,6 +43,8 @@ struct Context {
     cudaEvent_t ev_fork = nullptr, ev_copy[kMaxParts] = {}, ev_em[kMaxParts] = {}, ev_vit[kMaxParts] = {}, ev_setup = nullptr;
     int* d_queue = nullptr;              // work-item counter of the emission lattice kernel
     unsigned* d_flags = nullptr;         // sticky device warning word
+    unsigned* d_gsl_count = nullptr;     // per-cell GSL error log of the `.Call`-shaped emission (kernels.cuh: GslEventLog)
+    uint4* d_gsl_events = nullptr;
     unsigned sticky = 0;
     std::vector<DevBuf*> bufs;
 };
@@ -357,6 +359,10 @@ void edb200_shutdown(void)
     release_refset_scratch();            // also releases the fit scratch
     if (g.d_flags) cudaFree(g.d_flags);
     g.d_flags = nullptr;
+    if (g.d_gsl_count) cudaFree(g.d_gsl_count);
+    if (g.d_gsl_events) cudaFree(g.d_gsl_events);
+    g.d_gsl_count = nullptr;
+    g.d_gsl_events = nullptr;
     if (g.stream) cudaStreamDestroy(g.stream);
     g.stream = nullptr;
     if (g.stream2) {
@@ -458,6 +464,48 @@ namespace {
 constexpr int kHostChunks = 8;                     // sample chunks of the host-pointer cohort call (<= 16 events)
 constexpr int kTableK = 2048, kTableRN = 12288;   // lattice caps: (2048 + 2*12288) * 8 B = 208 KB of shared memory
 
+// ---- per-cell GSL error log (src/error.c:35-52) -------------------------------------------------------------
+constexpr unsigned kGslLogCap = 1u << 16;
+struct GslSite { const char* file; int line; const char* reason; };
+// bit order = edb200_math.cuh kSite* (the order the reference reaches them inside one gsl_sf_lnbeta call)
+const GslSite kGslSites[10] = {{"beta.c", 56, "domain error"},      {"beta.c", 59, "domain error"},      {"VP_gamma.c", 1338, "domain error"},
+                               {"VP_log.c", 202, "domain error"},   {"VP_gamma.c", 1239, "domain error"}, {"VP_gamma.c", 1253, "domain error"},
+                               {"VP_gamma.c", 1261, "error"},       {"VP_gamma.c", 803, "error"},         {"VP_gamma.c", 1283, "error"},
+                               {"beta.c", 44, "domain error"}};
+std::vector<uint4> g_gsl_log;            // events of the last `.Call`-shaped emission, in the reference's order (bin, state)
+long long g_gsl_raised = 0;              // events raised (the log keeps the first kGslLogCap)
+
+edb::GslEventLog gsl_log_begin(cudaStream_t st)
+{
+    g_gsl_log.clear();
+    g_gsl_raised = 0;
+    if (!g.d_gsl_count) {
+        if (cudaMalloc(&g.d_gsl_count, 16) != cudaSuccess || cudaMalloc(&g.d_gsl_events, (size_t)kGslLogCap * sizeof(uint4)) != cudaSuccess)
+            return edb::GslEventLog{nullptr, nullptr, 0};
+    }
+    cudaMemsetAsync(g.d_gsl_count, 0, 4, st);
+    return edb::GslEventLog{g.d_gsl_count, g.d_gsl_events, kGslLogCap};
+}
+int gsl_log_end(cudaStream_t st)
+{
+    if (!g.d_gsl_count) return 0;
+    unsigned n = 0;
+    CU(cudaMemcpyAsync(&n, g.d_gsl_count, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    g_gsl_raised = n;
+    g_gsl_log.resize(std::min(n, kGslLogCap));
+    if (!g_gsl_log.empty()) {
+        CU(cudaMemcpyAsync(g_gsl_log.data(), g.d_gsl_events, g_gsl_log.size() * sizeof(uint4), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        // the reference walks the bins in order and, per bin, the states (src/CNV_estimate.cpp:71-80)
+        std::sort(g_gsl_log.begin(), g_gsl_log.end(), [](const uint4& a, const uint4& b) {
+            const unsigned long long ka = ((unsigned long long)(a.y >> 8) << 32 | a.x), kb = ((unsigned long long)(b.y >> 8) << 32 | b.x);
+            return ka != kb ? ka < kb : (a.y & 0xFFu) < (b.y & 0xFFu);
+        });
+    }
+    return 0;
+}
+
 int pull_flags(cudaStream_t st, int* warn)
 {
     unsigned f = 0;
@@ -543,13 +591,34 @@ int edb200_emission(const double* phi, const double* expected, const int32_t* to
         CU(cudaMemcpyAsync(cs.phi.p, phi, n * 8, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(cs.expected.p, expected, n * 8, cudaMemcpyHostToDevice, st));
         edb::launch_emission_bins((double*)cs.phi.p, (double*)cs.expected.p, (int32_t*)cs.total.p, (int32_t*)cs.observed.p,
-                                  n, S, (double*)cs.odds.p, out, g.d_flags, st);
+                                  n, S, (double*)cs.odds.p, out, g.d_flags, gsl_log_begin(st), st);
         g_launches++;
         if (int rc = check_kernel("emission_bins")) return rc;
+        if (int rc = gsl_log_end(st)) return rc;
     }
     CU(cudaMemcpyAsync(ll_out, cs.ll.p, (size_t)n * S * 8, cudaMemcpyDeviceToHost, st));
     int warn = 0;
     if (int rc = pull_flags(st, &warn)) return rc;
+    if (constant) {
+        g_gsl_log.clear();
+        g_gsl_raised = 0;
+        if (warn & EDB200_WARN_NAN) {
+            // the hoisted kernels report only THAT a call failed; the reference names every failing call (src/error.c:45-48):
+            // the per-bin kernel — same arithmetic, same bits — runs once more over the broadcast pair to list them
+            std::vector<double> ph((size_t)n, phi[0]), ex((size_t)n, expected[0]);
+            if (int rc = ensure(cs.phi, n * 8)) return rc;
+            if (int rc = ensure(cs.expected, n * 8)) return rc;
+            CU(cudaMemcpyAsync(cs.phi.p, ph.data(), n * 8, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(cs.expected.p, ex.data(), n * 8, cudaMemcpyHostToDevice, st));
+            edb::launch_emission_bins((double*)cs.phi.p, (double*)cs.expected.p, (int32_t*)cs.total.p, (int32_t*)cs.observed.p,
+                                      n, S, (double*)cs.odds.p, out, g.d_flags, gsl_log_begin(st), st);
+            g_launches++;
+            if (int rc = check_kernel("emission_bins")) return rc;
+            if (int rc = gsl_log_end(st)) return rc;
+            int again = 0;
+            if (int rc = pull_flags(st, &again)) return rc;
+        }
+    }
     return warn;
 }
 
@@ -572,6 +641,40 @@ int edb200_lnbeta(const double* x, const double* y, int64_t n, double* out)
     int warn = 0;
     if (int rc = pull_flags(st, &warn)) return rc;
     return warn;
+}
+
+int64_t edb200_gsl_error_log(char* buf, size_t buflen, int64_t first_event, int64_t* next_event)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    size_t used = 0;
+    int64_t ev = first_event < 0 ? 0 : first_event;
+    if (buf && buflen) buf[0] = 0;
+    auto put = [&](const char* file, int line, const char* reason) {
+        // src/error.c:45-48
+        const int w = snprintf(buf + used, buflen - used, "ERROR %s %i %s\nDefault GSL error handler invoked.\n", file, line, reason);
+        if (w < 0 || (size_t)w >= buflen - used) return false;
+        used += (size_t)w;
+        return true;
+    };
+    for (; buf && ev < (int64_t)g_gsl_log.size(); ev++) {
+        const size_t mark = used;
+        bool fits = true;
+        for (int call = 0; call < 2 && fits; call++) {
+            const unsigned sites = call == 0 ? g_gsl_log[ev].z : g_gsl_log[ev].w;
+            if (!sites) continue;
+            for (int b = 0; b < 10 && fits; b++)
+                if (sites >> b & 1u) fits = put(kGslSites[b].file, kGslSites[b].line, kGslSites[b].reason);
+            // the value wrapper reports the failed call once more (src/beta.c:163, eval.h:3-9)
+            if (fits) fits = put("beta.c", 163, "gsl_sf_lnbeta_e(x, y, &result)");
+        }
+        if (!fits) {
+            used = mark;
+            buf[used] = 0;
+            break;
+        }
+    }
+    if (next_event) *next_event = ev;
+    return g_gsl_raised;
 }
 
 int edb200_get_loglike_matrix(const double* phi, const double* expected, const int32_t* total,
@@ -2049,14 +2152,14 @@ int edb200_refset_correlations(const int32_t* counts, int64_t stride, int32_t n_
 }  // extern "C"
 namespace {
 struct FitScratch {
-    DevBuf obs, ref, mu, phi, ll, info, overflow;
+    DevBuf obs, ref, mu, phi, ll, info, overflow, power;
 } fs;
 constexpr int kFitOverflow = 4096;                 // bins per sample that may exceed the caps
 std::mutex g_fit_mu;
 constexpr int kFitK = 6144, kFitRN = 22528;       // exceedance-array caps: (6144 + 2 * 22528) * 4 B = 200 KB of shared memory
 void release_fit_scratch()
 {
-    DevBuf* all[] = {&fs.obs, &fs.ref, &fs.mu, &fs.phi, &fs.ll, &fs.info, &fs.overflow};
+    DevBuf* all[] = {&fs.obs, &fs.ref, &fs.mu, &fs.phi, &fs.ll, &fs.info, &fs.overflow, &fs.power};
     for (DevBuf* b : all) release(*b);
 }
 }  // namespace
@@ -2079,6 +2182,30 @@ int edb200_betabin_fit_device(const int32_t* observed, int64_t obs_stride, const
     edb::launch_betabin_fit(cv, n_samples, n_bins, d, 200, fs.overflow.p, kFitOverflow, mu, phi, loglik, info, (cudaStream_t)cuda_stream);
     g_launches++;
     return check_kernel("betabin_fit");
+}
+
+int edb200_power_betabinom(const int32_t* size, const double* phi, const double* p, const double* alt_p, int32_t n, double* expected_bf)
+{
+    if (int rc = need_ctx()) return rc;
+    if (n < 0 || (n > 0 && (!size || !phi || !p || !alt_p || !expected_bf))) return fail(EDB200_ERR_ARG, "bad argument");
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaStream_t st = g.stream;
+    // one staging block: [size | phi | p | alt_p | out]
+    const size_t pad = ((size_t)n * 4 + 7) & ~(size_t)7;
+    if (int rc = ensure(fs.power, pad + (size_t)n * 8 * 4)) return rc;
+    char* base = (char*)fs.power.p;
+    double* d_phi = (double*)(base + pad);
+    CU(cudaMemcpyAsync(base, size, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_phi, phi, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_phi + n, p, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_phi + 2 * (size_t)n, alt_p, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    edb::launch_power_betabinom((const int32_t*)base, d_phi, d_phi + n, d_phi + 2 * (size_t)n, n, d_phi + 3 * (size_t)n, st);
+    g_launches++;
+    if (int rc = check_kernel("power_betabinom")) return rc;
+    CU(cudaMemcpyAsync(expected_bf, d_phi + 3 * (size_t)n, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
 }
 
 int edb200_betabin_fit(const int32_t* observed, int64_t obs_stride, const int32_t* reference, int64_t ref_stride, int32_t n_samples,

@@ -27,6 +27,21 @@ constexpr double kStirlingMin = 10.0;   // 8-term Stirling tail is exact to < 2e
 
 // status bits (mirrors include/exomedepth_b200.h)
 constexpr unsigned kFlagNaN = 1u;       // a GSL-style domain error produced NaN cells (reference prints + continues)
+// ... and WHICH error site of the vendored GSL chain raised it (src/error.c:35-52 prints file, line and reason of every
+// failing call and carries on): one bit per site, in the order the reference reaches them inside one gsl_sf_lnbeta call.
+// capi.cu: kGslSites holds the file / line / reason of every bit; edb200_gsl_error_log prints them like the reference.
+constexpr unsigned kSiteShift = 8;
+constexpr unsigned kSiteBetaZero = 1u << 8;         // beta.c:56      x == 0 || y == 0
+constexpr unsigned kSiteBetaNegInt = 1u << 9;       // beta.c:59      negative integer argument
+constexpr unsigned kSiteGammastar = 1u << 10;       // VP_gamma.c:1338  gammastar(x <= 0)
+constexpr unsigned kSiteLog1p = 1u << 11;           // VP_log.c:202   log_1plusx(x <= -1)
+constexpr unsigned kSiteLngammaZero = 1u << 12;     // VP_gamma.c:1239  lngamma_sgn(0)
+constexpr unsigned kSiteLngammaSin = 1u << 13;      // VP_gamma.c:1253  sin(pi x) == 0
+constexpr unsigned kSiteLngammaRound1 = 1u << 14;   // VP_gamma.c:1261  "error" (x < INT_MIN + 2)
+constexpr unsigned kSiteNearNegInt = 1u << 15;      // VP_gamma.c:803   "error" (eps == 0)
+constexpr unsigned kSiteLngammaRound2 = 1u << 16;   // VP_gamma.c:1283  "error" (|x| too large)
+constexpr unsigned kSiteBetaSign = 1u << 17;        // beta.c:44      the beta function is negative
+constexpr unsigned kSiteMask = 0x3FFu << 8;
 
 // ------------------------------------------------------------------------------------------------
 // product path
@@ -215,7 +230,7 @@ static __device__ __noinline__ double clenshaw(const double* c, int order, doubl
 // VP_log.c:196-232
 static __device__ __noinline__ double log_1plusx(double x, unsigned& flags)
 {
-    if (x <= -1.0) { flags |= kFlagNaN; return nan(""); }
+    if (x <= -1.0) { flags |= kFlagNaN | kSiteLog1p; return nan(""); }
     if (fabs(x) < 2.4607833005759251e-03) {
         double t = -1.0 / 6.0 + x * (1.0 / 7.0 + x * (-1.0 / 8.0 + x * (1.0 / 9.0 + x * (-1.0 / 10.0))));
         return x * (1.0 + x * (-0.5 + x * (1.0 / 3.0 + x * (-0.25 + x * (0.2 + x * t)))));
@@ -301,7 +316,7 @@ static __device__ __noinline__ double polygamma_int(int n, long long m)
 // VP_gamma.c:795-894 (x = -N + eps)
 static __device__ __noinline__ double lngamma_near_negint(int N, double eps, double& sgn, unsigned& flags)
 {
-    if (eps == 0.0) { sgn = 0.0; flags |= kFlagNaN; return 0.0; }
+    if (eps == 0.0) { sgn = 0.0; flags |= kFlagNaN | kSiteNearNegInt; return 0.0; }
     if (N == 1) {
         const double g5 = 0.00275661310191541584 +
                           eps * (-0.00124162645565305019 +
@@ -352,15 +367,15 @@ static __device__ __noinline__ double lngamma_sgn(double x, double& sgn, unsigne
                          0.0001067287169183665, -0.0000693271800931282, 0.0000407220927867950);
     }
     if (x >= 0.5) { sgn = 1.0; return lanczos_lngamma(x); }
-    if (x == 0.0) { sgn = 0.0; flags |= kFlagNaN; return nan(""); }
+    if (x == 0.0) { sgn = 0.0; flags |= kFlagNaN | kSiteLngammaZero; return nan(""); }
     if (fabs(x) < 0.02) return lngamma_near_0(x, sgn);
     if (x > -0.5 / (kEps * kPi)) {
         const double z = 1.0 - x;
         const double s = sin(kPi * (use_1mx ? z : x));
         const double as = fabs(s);
-        if (s == 0.0) { sgn = 0.0; flags |= kFlagNaN; return nan(""); }
+        if (s == 0.0) { sgn = 0.0; flags |= kFlagNaN | kSiteLngammaSin; return nan(""); }
         if (as < kPi * 0.015) {
-            if (x < -2147483646.0) { sgn = 0.0; flags |= kFlagNaN; return 0.0; }
+            if (x < -2147483646.0) { sgn = 0.0; flags |= kFlagNaN | kSiteLngammaRound1; return 0.0; }
             const int N = -(int)(x - 0.5);
             return lngamma_near_negint(N, x + N, sgn, flags);
         }
@@ -368,14 +383,14 @@ static __device__ __noinline__ double lngamma_sgn(double x, double& sgn, unsigne
         return kLnPi - (log(as) + lanczos_lngamma(z));
     }
     sgn = 0.0;
-    flags |= kFlagNaN;
+    flags |= kFlagNaN | kSiteLngammaRound2;
     return 0.0;
 }
 
 // VP_gamma.c:1332-1379, 986-1007
 static __device__ __noinline__ double gammastar(double x, unsigned& flags)
 {
-    if (x <= 0.0) { flags |= kFlagNaN; return nan(""); }
+    if (x <= 0.0) { flags |= kFlagNaN | kSiteGammastar; return nan(""); }
     if (x < 0.5) {
         double sgn;
         const double lg = lngamma_sgn(x, sgn, flags, true);
@@ -409,8 +424,8 @@ static __device__ __noinline__ double gammastar(double x, unsigned& flags)
 // beta.c:38-47, 49-114, 161-164
 static __device__ __noinline__ double lnbeta_gsl(double x, double y, unsigned& flags)
 {
-    if (x == 0.0 || y == 0.0) { flags |= kFlagNaN; return nan(""); }
-    if ((x < 0 && x == floor(x)) || (y < 0 && y == floor(y))) { flags |= kFlagNaN; return nan(""); }
+    if (x == 0.0 || y == 0.0) { flags |= kFlagNaN | kSiteBetaZero; return nan(""); }
+    if ((x < 0 && x == floor(x)) || (y < 0 && y == floor(y))) { flags |= kFlagNaN | kSiteBetaNegInt; return nan(""); }
     if (x > 0 && y > 0) {
         const double mx = fmax(x, y), mn = fmin(x, y);
         const double rat = mn / mx;
@@ -428,7 +443,7 @@ static __device__ __noinline__ double lnbeta_gsl(double x, double y, unsigned& f
     const double lx = gsl::lngamma_sgn(x, sx, flags);
     const double ly = gsl::lngamma_sgn(y, sy, flags);
     const double lxy = gsl::lngamma_sgn(x + y, sxy, flags);
-    if (sx * sy * sxy == -1.0) { flags |= kFlagNaN; return nan(""); }
+    if (sx * sy * sxy == -1.0) { flags |= kFlagNaN | kSiteBetaSign; return nan(""); }
     return lx + ly - lxy;
 }
 
@@ -444,6 +459,20 @@ __device__ __forceinline__ double cell_loglik(const StateConst& sc, int total, i
         return __dsub_rn(__dadd_rn(gdiff(sc.g1, x), gdiff(sc.g2, y)), gdiff(sc.g12, z));
     }
     return lnbeta_gsl(x, y, flags) - lnbeta_gsl(sc.a1, sc.a2, flags);
+}
+
+// the same cell with the error sites of its two gsl_sf_lnbeta calls reported apart (sites[0]: the data term, sites[1]: the
+// normalising term) — the `.Call`-shaped entry point logs them per cell like the reference prints them
+__device__ __forceinline__ double cell_loglik_sites(const StateConst& sc, int total, int observed, unsigned& flags, unsigned* sites)
+{
+    double x, y, z;
+    data_args(sc.a1, sc.a2, total, observed, x, y, z);
+    sites[0] = sites[1] = 0u;
+    if (sc.ok && observed >= 0 && total >= observed)
+        return __dsub_rn(__dadd_rn(gdiff(sc.g1, x), gdiff(sc.g2, y)), gdiff(sc.g12, z));
+    const double t = lnbeta_gsl(x, y, sites[0]), n = lnbeta_gsl(sc.a1, sc.a2, sites[1]);
+    flags |= (sites[0] | sites[1]) & kFlagNaN;
+    return t - n;
 }
 
 }  // namespace edb

@@ -43,7 +43,7 @@ void launch_state_setup(int n_samples, int n_states, const double* phi, const do
 __global__ void __launch_bounds__(128)
 emission_bins_kernel(const double* __restrict__ phi, const double* __restrict__ expected,
                      const int32_t* __restrict__ total, const int32_t* __restrict__ observed, int64_t n_bins,
-                     int n_states, const double* __restrict__ odds, LLView out, unsigned* __restrict__ flags)
+                     int n_states, const double* __restrict__ odds, LLView out, unsigned* __restrict__ flags, GslEventLog log)
 {
     unsigned f = 0;
     for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < n_bins; b += (int64_t)gridDim.x * blockDim.x) {
@@ -52,7 +52,12 @@ emission_bins_kernel(const double* __restrict__ phi, const double* __restrict__ 
         const int tot = total[b], obs = observed[b];
         for (int s = 0; s < n_states; s++) {
             const StateConst sc = make_state_const(state_expected(e, odds[s]), sd);
-            out.ptr[s * out.state_stride + b] = cell_loglik(sc, tot, obs, f);
+            unsigned sites[2];
+            out.ptr[s * out.state_stride + b] = cell_loglik_sites(sc, tot, obs, f, sites);
+            if ((sites[0] | sites[1]) && log.count) {          // src/error.c:35-52: every failing call is reported
+                const unsigned q = atomicAdd(log.count, 1u);
+                if (q < log.cap) log.events[q] = make_uint4((unsigned)b, (unsigned)(b >> 32) << 8 | (unsigned)s, sites[0] >> kSiteShift, sites[1] >> kSiteShift);
+            }
         }
     }
     if (f) atomicOr(flags, f);
@@ -60,12 +65,12 @@ emission_bins_kernel(const double* __restrict__ phi, const double* __restrict__ 
 
 void launch_emission_bins(const double* phi, const double* expected, const int32_t* total,
                           const int32_t* observed, int64_t n_bins, int n_states, const double* odds,
-                          LLView out, unsigned* flags, cudaStream_t st)
+                          LLView out, unsigned* flags, GslEventLog log, cudaStream_t st)
 {
     if (n_bins == 0) return;
     int64_t blocks = (n_bins + 127) / 128;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    emission_bins_kernel<<<(int)blocks, 128, 0, st>>>(phi, expected, total, observed, n_bins, n_states, odds, out, flags);
+    emission_bins_kernel<<<(int)blocks, 128, 0, st>>>(phi, expected, total, observed, n_bins, n_states, odds, out, flags, log);
 }
 
 // per-bin phi / expected for every sample of a cohort (phi.bins > 1 and covariate formulas give per-bin fits,

@@ -54,10 +54,17 @@ struct LLView {                   // ll[sample*sample_stride + state*state_strid
 void launch_state_setup(int n_samples, int n_states, const double* phi, const double* expected,
                         const double* odds, StateConst* consts, cudaStream_t st);
 
+// Per-cell log of the GSL errors of a `.Call`-shaped emission (src/error.c:35-52 prints every failing call and carries on):
+// event = (bin low word, bin high word << 8 | state, sites of the data term's gsl_sf_lnbeta, sites of the normalising term's)
+struct GslEventLog {
+    unsigned* count;              // events raised (may exceed cap); null: no log
+    uint4* events;
+    unsigned cap;
+};
 // reference-API shaped: per-bin phi / expected vectors of ONE sample (src/CNV_estimate.cpp:52-85)
 void launch_emission_bins(const double* phi, const double* expected, const int32_t* total,
                           const int32_t* observed, int64_t n_bins, int n_states, const double* odds,
-                          LLView out, unsigned* flags, cudaStream_t st);
+                          LLView out, unsigned* flags, GslEventLog log, cudaStream_t st);
 
 // gsl_sf_lnbeta (src/beta.c:161-164) through the device's faithful GSL restatement; parity tests only
 void launch_lnbeta(const double* x, const double* y, int64_t n, double* out, unsigned* flags, cudaStream_t st);
@@ -242,6 +249,9 @@ size_t betabin_fit_smem_bytes(TableDims d);
 // overflow: device scratch of n_samples * ovf_cap int2 for the bins whose counts exceed the caps
 void launch_betabin_fit(CountsView c, int n_samples, int64_t n_bins, TableDims dims, int max_iter, void* overflow, int ovf_cap,
                         double* mu, double* phi, double* loglik, int32_t* info, cudaStream_t st);
+
+// expected Bayes factor of get.power.betabinom (R/tools.R:128-166, the deterministic beta-binomial branch), one CTA per problem
+void launch_power_betabinom(const int32_t* size, const double* phi, const double* p, const double* alt_p, int n, double* out, cudaStream_t st);
 
 // ---- forward pass / transition-probability grid (extension, forward.cu) -------------------------------
 struct ForwardArgs {

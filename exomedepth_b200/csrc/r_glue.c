@@ -25,12 +25,24 @@ static void raise_if_failed(int rc, const char *what)
         error("%s: %s (exomedepth_b200 status %d; this build has no CPU fallback)", what, edb200_last_error(), rc);
 }
 
-/* src/error.c:45-48: a GSL domain error prints and evaluation continues (abort is commented out, :51) */
+/* src/error.c:45-48: every failing GSL call prints its file, line and reason, and evaluation continues (abort is commented
+ * out, :51).  The device logs the failing cells with their error sites; the text is the reference's, cell by cell. */
 static void report_domain_errors(int rc)
 {
     if (rc & EDB200_WARN_NAN) {
-        Rprintf("ERROR %s %i %s\n", "beta.c", 44, "domain error");
-        Rprintf("Default GSL error handler invoked.\n");
+        char buf[4096];
+        int64_t next = 0, shown = 0;
+        const int64_t raised = edb200_gsl_error_log(buf, sizeof buf, 0, &next);
+        while (next > shown) {
+            Rprintf("%s", buf);
+            shown = next;
+            edb200_gsl_error_log(buf, sizeof buf, shown, &next);
+        }
+        if (raised > shown) Rprintf("... and %ld more cells with GSL errors (not listed)\n", (long)(raised - shown));
+        if (raised == 0) {      /* (a status without a log: should not happen) */
+            Rprintf("ERROR %s %i %s\n", "beta.c", 44, "domain error");
+            Rprintf("Default GSL error handler invoked.\n");
+        }
     }
 }
 

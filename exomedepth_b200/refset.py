@@ -104,6 +104,15 @@ def select_reference_set(test_counts, reference_counts, bin_length=None, n_bins_
         prefix = running[None, :] + np.cumsum(r_sel[:, i0:i1].T, axis=0)      # :115  reference <- reference + reference.counts[, i]
         running = prefix[-1]
         fit = betabin.fit(np.tile(t_sel, (i1 - i0, 1)), prefix.astype(np.int32))
+        # the expected Bayes factors of the whole chunk in one launch (R/optimize_reference_set.R:133-140); prefixes behind
+        # the loop's break are simply not used
+        med = np.median(prefix, axis=1)
+        p_all = np.clip(fit["expected"], 1e-300, 1 - 1e-16)
+        odds = p_all / (1 - p_all) * 0.5
+        ok = (fit["info"] != -1) & (fit["info"] != -2) & (fit["phi"] > 0) & (fit["phi"] < 1)
+        bf = np.full(i1 - i0, np.nan)
+        if ok.any():
+            bf[ok] = betabin.get_power_betabinom_batch(np.rint(med[ok]).astype(np.int32), fit["phi"][ok], p_all[ok], (odds / (1 + odds))[ok])
         for j in range(i1 - i0):
             i = i0 + j
             if fit["info"][j] == -1 or fit["info"][j] == -2:
@@ -115,8 +124,7 @@ def select_reference_set(test_counts, reference_counts, bin_length=None, n_bins_
             if i + 1 > 2 and p < 0.05:                                          # :130
                 done = True
                 break
-            alt_odds = p / (1 - p) * 0.5                                        # :133-134
-            cols["expected_BF"][i] = betabin.get_power_betabinom(round(cols["median_depth"][i]), phi, p, alt_odds / (1 + alt_odds))
+            cols["expected_BF"][i] = bf[j]                                      # :133-140
         if done:
             break
     best = int(np.nanargmax(cols["expected_BF"]))                              # :143 which.max

@@ -79,6 +79,15 @@ EDB200_API int edb200_lnbeta(const double *x, const double *y, int64_t n, double
 EDB200_API int edb200_emission(const double *phi, const double *expected, const int32_t *total,
                     const int32_t *observed, int64_t n, int32_t n_states, const double *odds, double *ll_out);
 
+/* The GSL error messages of the last edb200_get_loglike_matrix / edb200_emission call, as the reference prints them while it
+ * computes (src/error.c:45-48: "ERROR <file> <line> <reason>" + "Default GSL error handler invoked." for every failing call,
+ * then evaluation continues): per failing cell, in the reference's order (bin, then state), the error site(s) inside
+ * gsl_sf_lnbeta (src/beta.c:44, 56, 59; src/VP_gamma.c:803, 1239, 1253, 1261, 1283) and the value wrapper's report
+ * (src/beta.c:163).  Writes the text of events first_event, first_event + 1, ... as far as buflen allows (NUL-terminated),
+ * sets *next_event to the first event not written, returns the number of failing cells the call had (the log keeps the
+ * first 65,536).  csrc/r_glue.c prints it through Rprintf. */
+EDB200_API int64_t edb200_gsl_error_log(char *buf, size_t buflen, int64_t first_event, int64_t *next_event);
+
 /* Replaces C_hmm(nstates, nobs, transitions, probabilities, positions, expectedLength)  src/hmm.cpp:18-167.
  * transitions: double[S*S] column-major (R matrix; [k + S*j] = P(k -> j)); probabilities: double[nobs*S]
  * column-major in HMM state order (0 = normal); positions: int32[nobs].
@@ -284,6 +293,12 @@ EDB200_API int edb200_betabin_fit(const int32_t *observed, int64_t obs_stride, c
 EDB200_API int edb200_betabin_fit_device(const int32_t *observed, int64_t obs_stride, const int32_t *reference, int64_t ref_stride,
                                          int32_t n_samples, int64_t n_bins, double *mu, double *phi, double *loglik,
                                          int32_t *info, void *cuda_stream);
+
+/* get.power.betabinom(size, my.phi, my.p, my.alt.p) for n problems at once (R/tools.R:128-166, theory = FALSE, limit = FALSE:
+ * the expected log10 Bayes factor of the alternative proportion over one beta-binomial draw of `size` reads) — the inner step
+ * of select.reference.set's greedy loop (R/optimize_reference_set.R:136-140), one CTA per problem.  Host pointers. */
+EDB200_API int edb200_power_betabinom(const int32_t *size, const double *phi, const double *p, const double *alt_p, int32_t n,
+                                      double *expected_bf);
 
 /* sticky status word of device-side warnings since the last call with reset != 0 (EDB200_WARN_*) */
 EDB200_API int edb200_status(int reset);

@@ -65,3 +65,24 @@ def test_cuda_fit_reports_degenerate_samples():
     assert r["info"][0] == -1 and np.isnan(r["expected"][0])
     assert r["info"][2] == -2
     assert r["info"][1] in (-4, -3) or r["phi"][1] < 1e-6    # constant proportion: no over-dispersion to find
+
+
+@pytest.mark.gpu
+def test_cuda_expected_bf_batch_matches_the_oracle():
+    """edb200_power_betabinom (one CTA per problem) against the scipy restatement of get.power.betabinom
+    (R/tools.R:128-166, theory = FALSE, limit = FALSE), over the sizes and over-dispersions select.reference.set visits:
+    median depths from a handful of reads to tens of thousands, phi from 1e-4 to 0.3."""
+    from exomedepth_b200 import betabin
+    rng = np.random.default_rng(5)
+    size = np.concatenate([[0, 1, 2, 200, 200, 731, 40, 255, 256, 257], rng.integers(3, 40000, 40)]).astype(np.int32)
+    phi = np.concatenate([[0.1] * 3, [0.1, 0.1, 0.0045, 0.02, 0.01, 0.01, 0.01], np.exp(rng.uniform(np.log(1e-4), np.log(0.3), 40))])
+    p = np.concatenate([[0.2] * 3, [0.2, 0.2, 0.2176, 0.1, 0.3, 0.3, 0.3], rng.uniform(0.03, 0.6, 40)])
+    odds = p / (1 - p) * 0.5
+    alt = odds / (1 + odds)
+    alt[3], alt[4] = 0.6, 0.2                                    # the two examples of R/tools.R:122-123
+    got = betabin.get_power_betabinom_batch(size, phi, p, alt)
+    for i in range(size.size):
+        want = obb.get_power_betabinom(int(size[i]), float(phi[i]), float(p[i]), float(alt[i]))
+        assert got[i] == pytest.approx(want, rel=2e-9, abs=1e-11), (i, size[i], phi[i], p[i], alt[i])
+    assert abs(got[4]) < 1e-11 and got[3] > 1.0
+    assert np.isnan(betabin.get_power_betabinom_batch([10], [0.0], [0.2], [0.1])[0])      # phi = 0: a / b are not finite

@@ -950,6 +950,45 @@ def test_sample_chunk_pipeline_matches_single_pass(edb):
     co.close()
 
 
+def test_gsl_error_log_matches_the_reference(edb):
+    """src/error.c:45-48 prints file, line and reason of EVERY failing GSL call and carries on.  The device logs the failing
+    cells with their error sites; edb200_gsl_error_log renders them.  The text must be, line for line, what the compiled
+    reference printed for the same rows (tests/golden/gsl_errors.json, tools/make_golden_gsl_errors.py): per-bin vectors and
+    the single (phi, expected) pair that new('ExomeDepth') hands over; and through the `.Call` glue (Rprintf)."""
+    import ctypes as C
+    import json
+    import os
+    from conftest import ROOT
+    from exomedepth_b200 import _lib
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "gsl_errors.json")))
+    L = _lib.load()
+
+    def log_text(small=False):
+        buf = C.create_string_buffer(300 if small else 1 << 16)
+        nxt, first, out = C.c_int64(0), 0, ""
+        while True:
+            raised = L.edb200_gsl_error_log(buf, len(buf), first, C.byref(nxt))
+            if nxt.value == first:
+                break
+            out += buf.value.decode()
+            first = nxt.value
+        return out, raised
+
+    for name, g in gold.items():
+        i = g["inputs"]
+        ll = edb.get_loglike_matrix(np.array(i["phi"]), np.array(i["expected"]), np.array(i["total"], np.int32), np.array(i["observed"], np.int32), 1.0)
+        want = np.array([[np.nan if v is None else v for v in row] for row in g["ll"]])
+        assert np.array_equal(np.isnan(ll), np.isnan(want)), name
+        assert_ll_close(ll, want)
+        text, raised = log_text()
+        assert text == g["printed"], (name, text[:400], g["printed"][:400])
+        assert raised == int(np.isnan(want).sum()), (name, raised)
+        assert log_text(small=True)[0] == g["printed"], "paging through a small buffer"
+    # a healthy call leaves an empty log
+    edb.get_loglike_matrix(np.full(4, 0.01), np.full(4, 0.2), np.full(4, 50, np.int32), np.full(4, 10, np.int32), 1.0)
+    assert log_text() == ("", 0)
+
+
 def test_cohort_call_glue_on_exomecount(edb, exomecount, refvec2):
     """r_glue_cohort.c (`.Call("edb_cohort_callcnvs", ...)`, one call per COHORT) driven with fake SEXPs like R: the four
     leave-one-out ExomeCount samples as the columns of one count matrix, each with its own reference column — the
