@@ -116,65 +116,90 @@ refset_standardize_kernel(const int32_t* __restrict__ counts, int64_t stride, co
 // peer memory).  The all-gather of the sharded sweep is thereby fused into the contraction: tiles are fetched from
 // their owners while other tiles are being multiplied, and no rank ever holds a copy of the whole matrix Z.
 constexpr int kGT = 128, kGK = 16;
-__global__ void __launch_bounds__(256)
+constexpr int kGS = kGT + 4;           // shared-memory row stride in doubles: the four k-rows of a fragment load fall on distinct banks
+// FP64 tensor-core contraction (mma.sync m8n8k4, DMMA): a warp forms a 64 x 32 block of the 128 x 128 tile as 8 x 4
+// fragments of 8 x 8; per 4 values of k it loads 8 + 4 operand fragments (one double per lane each) for 32 DMMAs, where
+// the FMA form read 16 doubles per lane for 64 FMAs and stalled on its register operands (19 of 34 TFLOP/s, with or
+// without double buffering).  Two shared-memory stages: the next K-chunk's global loads (this rank's rows, and the peers'
+// over NVLink) are issued before the current chunk's DMMAs and stashed into the other stage behind them: one barrier per
+// chunk.  The sum over k runs in the tensor unit's order inside a group of 4 and in ascending groups — fixed, so the
+// sharded forms of the sweep still agree bit for bit.
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 1)
 refset_gram_kernel(const double* __restrict__ za, int m, const __grid_constant__ PeerRows zb, int n, int64_t k_pad, int64_t k_slice,
                    double* __restrict__ partial)
 {
-    __shared__ __align__(16) double sa[kGK][kGT], sb[kGK][kGT];       // k-major
+    extern __shared__ __align__(16) double gram_smem[];     // [stage][a | b][kGK][kGS], k-major
+    auto sa = [&](int st, int k, int r) -> double& { return gram_smem[((st * 2 + 0) * kGK + k) * kGS + r]; };
+    auto sb = [&](int st, int k, int r) -> double& { return gram_smem[((st * 2 + 1) * kGK + k) * kGS + r]; };
     const int ti = blockIdx.y * kGT, tj = blockIdx.x * kGT;
     const int64_t k0 = (int64_t)blockIdx.z * k_slice, k1 = k0 + k_slice < k_pad ? k0 + k_slice : k_pad;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;            // 16 x 16 threads
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wy = (warp >> 2) * 64, wx = (warp & 3) * 32;             // this warp's block of the tile
+    const int fr = lane >> 2, fk = lane & 3;                           // fragment row / k of this lane
     // loads: thread t brings 8 consecutive k of one row of each operand tile (128 rows x 16 k = 256 threads x 8)
     const int lr = threadIdx.x >> 1, lk = (threadIdx.x & 1) * 8;
-    double acc[8][8] = {};
-    for (int64_t k = k0; k < k1; k += kGK) {
-        double2 av[4], bv[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) av[q] = bv[q] = make_double2(0, 0);
-        if (ti + lr < m) {
-            const double2* p = reinterpret_cast<const double2*>(za + (int64_t)(ti + lr) * k_pad + k + lk);
-#pragma unroll
-            for (int q = 0; q < 4; q++) av[q] = p[q];
-        }
-        if (tj + lr < n) {
-            const int row = tj + lr, owner = row / zb.rows_per_rank;
-            const double2* p = reinterpret_cast<const double2*>(zb.base[owner] + (int64_t)(row - owner * zb.rows_per_rank) * k_pad + k + lk);
-#pragma unroll
-            for (int q = 0; q < 4; q++) bv[q] = p[q];
-        }
-        __syncthreads();                                    // the previous chunk's products are done
+    const double2* pa = ti + lr < m ? reinterpret_cast<const double2*>(za + (int64_t)(ti + lr) * k_pad + lk) : nullptr;
+    const double2* pb = nullptr;
+    if (tj + lr < n) {
+        const int row = tj + lr, owner = row / zb.rows_per_rank;
+        pb = reinterpret_cast<const double2*>(zb.base[owner] + (int64_t)(row - owner * zb.rows_per_rank) * k_pad + lk);
+    }
+    double2 av[4], bv[4];
+    auto fetch = [&](int64_t k) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            sa[lk + 2 * q][lr] = av[q].x; sa[lk + 2 * q + 1][lr] = av[q].y;
-            sb[lk + 2 * q][lr] = bv[q].x; sb[lk + 2 * q + 1][lr] = bv[q].y;
+            av[q] = pa ? __ldg(pa + k / 2 + q) : make_double2(0, 0);
+            bv[q] = pb ? pb[k / 2 + q] : make_double2(0, 0);
         }
+    };
+    auto stash = [&](int st) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            sa(st, lk + 2 * q, lr) = av[q].x; sa(st, lk + 2 * q + 1, lr) = av[q].y;
+            sb(st, lk + 2 * q, lr) = bv[q].x; sb(st, lk + 2 * q + 1, lr) = bv[q].y;
+        }
+    };
+    double acc[8][4][2] = {};
+    int cur = 0;
+    if (k0 < k1) {
+        fetch(k0);
+        stash(0);
+    }
+    __syncthreads();
+    for (int64_t k = k0; k < k1; k += kGK) {
+        const bool more = k + kGK < k1;
+        if (more) fetch(k + kGK);
+#pragma unroll
+        for (int k4 = 0; k4 < kGK; k4 += 4) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = sa(cur, k4 + fk, wy + i * 8 + fr);
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = sb(cur, k4 + fk, wx + j * 8 + fr);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        if (more) stash(cur ^ 1);       // (the other stage: nobody reads it during this chunk)
         __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < kGK; kk++) {
-            double ar[8], br[8];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const double2 a01 = *reinterpret_cast<const double2*>(&sa[kk][h * 64 + ty * 4]);
-                const double2 a23 = *reinterpret_cast<const double2*>(&sa[kk][h * 64 + ty * 4 + 2]);
-                const double2 b01 = *reinterpret_cast<const double2*>(&sb[kk][h * 64 + tx * 4]);
-                const double2 b23 = *reinterpret_cast<const double2*>(&sb[kk][h * 64 + tx * 4 + 2]);
-                ar[4 * h] = a01.x; ar[4 * h + 1] = a01.y; ar[4 * h + 2] = a23.x; ar[4 * h + 3] = a23.y;
-                br[4 * h] = b01.x; br[4 * h + 1] = b01.y; br[4 * h + 2] = b23.x; br[4 * h + 3] = b23.y;
-            }
-#pragma unroll
-            for (int r = 0; r < 8; r++)
-#pragma unroll
-                for (int c = 0; c < 8; c++) acc[r][c] = fma(ar[r], br[c], acc[r][c]);
-        }
+        cur ^= 1;
     }
     double* __restrict__ out = partial + (int64_t)blockIdx.z * m * n;
 #pragma unroll
-    for (int r = 0; r < 8; r++)
+    for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const int i = ti + (r >> 2) * 64 + ty * 4 + (r & 3), j = tj + (c >> 2) * 64 + tx * 4 + (c & 3);
-            if (i < m && j < n) out[(int64_t)i * n + j] = acc[r][c];
-        }
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int r = ti + wy + i * 8 + fr, c = tj + wx + j * 8 + 2 * fk + e;
+                if (r < m && c < n) out[(int64_t)r * n + c] = acc[i][j][e];
+            }
 }
 
 __global__ void __launch_bounds__(256)
@@ -216,7 +241,10 @@ void launch_refset_gram(const double* za, int m, const PeerRows& zb, int n, int6
     if (k_slice < 1024) k_slice = 1024;
     k_slice = (k_slice + kGK - 1) / kGK * kGK;
     prof_mark("refset_gram", st);
-    refset_gram_kernel<<<dim3((n + kGT - 1) / kGT, (m + kGT - 1) / kGT, n_slices), 256, 0, st>>>(za, m, zb, n, k_pad, k_slice, partial);
+    constexpr size_t kGramSmem = 2 * 2 * kGK * kGS * sizeof(double);      // 66 KB
+    static PerDevice configured;
+    if (configured.raise(kGramSmem)) cudaFuncSetAttribute(refset_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramSmem);
+    refset_gram_kernel<<<dim3((n + kGT - 1) / kGT, (m + kGT - 1) / kGT, n_slices), 256, kGramSmem, st>>>(za, m, zb, n, k_pad, k_slice, partial);
     prof_mark("refset_reduce", st);
     const int64_t mn = (int64_t)m * n;
     refset_reduce_kernel<<<(unsigned)((mn + 255) / 256), 256, 0, st>>>(partial, n_slices, mn, c);
