@@ -334,7 +334,11 @@ def gpu_arm(a, rank, world):
     launches_per_step = {k: v[0] / a.steps for k, v in prof.items()}
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    per_rank_ms = [ms / a.steps]
     if dist:
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        per_rank_ms = [float(x[0]) / a.steps for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
     total_calls = int(ncalls.sum())
@@ -575,7 +579,8 @@ def gpu_arm(a, rank, world):
                            if world > 1 else "single rank", table_build_s=table_s, total_calls=total_calls, status=status, nproc=os.cpu_count()),
                clocks=clocks, e2e=e2e, gpu_launches=int(launches), parity=parity, segmented_sweep=segments, roofline=roof(dom),
                roofline_other=roof("emission" if dom != "emission" else "viterbi_sweep"),
-               kernel_ms_per_step={k: round(v, 5) for k, v in sorted(kt.items(), key=lambda kv: -kv[1])}, aux=aux)
+               kernel_ms_per_step={k: round(v, 5) for k, v in sorted(kt.items(), key=lambda kv: -kv[1])},
+               ms_per_step_per_rank=[round(v, 4) for v in per_rank_ms], aux=aux)
     if world == 1 and not a.no_cpu:
         from oracle import ref as oref
         cores = os.cpu_count() or 1
@@ -725,7 +730,7 @@ def refset_arm(a, rank, world):
                         clocks=clocks, e2e=e2e, gpu_launches=int(launches),
                         roofline=dict(kernel="refset_gram", bound="fp64", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
                                       ms_per_launch=gram_ms, flops_per_step_all_ranks=flops, peak_source=src,
-                                      note="FP64 FMA contraction (no FP64 tcgen05 kind); achieved = this rank's 2*m*n*k flops / its Gram kernel time"),
+                                      note="FP64 tensor-core contraction (mma.sync m8n8k4; there is no FP64 tcgen05 kind); achieved = this rank's 2*m*n*k flops / its Gram kernel time"),
                         kernel_ms_per_step={k: round(v[1] / a.steps, 5) for k, v in prof.items()})
         if world == 1 and not a.no_cpu:
             from oracle import refset as oref

@@ -155,7 +155,7 @@ struct ViterbiArgs {
     double* seam_in;              // [n_pieces][S][32] V of a piece after its warm-up
     double* seam_out;             // [n_pieces][S][32] V of a piece after its last observation
     unsigned* seam_mag;           // [n_pieces][kSeamWords][32] magnitudes and error multipliers of a piece (viterbi_seam.h: PieceErr)
-    int4* seg_close;              // [seg_close_cap] decisions with a lead below kSegTau: (chain, sample, observation, destination)
+    int4* seg_close;              // [seg_close_cap] decisions with a lead below kSegTau: (piece, sample, observation, destination | lead)
     int seg_close_cap;
     // repair flags, zeroed per run (layout: seg_off_* below)
     int32_t* seg_flags;

@@ -15,8 +15,9 @@
 // rc_k - xc_k = C_i + err_i[k] + rho_k, |rho_k| <= rho = 2^-52 (M_X + M_R).  Hence:
 //  (1) for two candidates of one destination, (rc_k - rc_k') - (xc_k - xc_k') lies within D_i + 2 rho: a decision whose
 //      winner leads the other candidates by more than D_i + 2 rho in X arithmetic has the same (unique) winner in R
-//      arithmetic.  The sweep lists every decision with a lead below kSegTau (viterbi_step.h); seam_advance() refuses a
-//      segment unless D_i + 2 rho <= kSegTau / 4 at every step.
+//      arithmetic.  The sweep lists every decision with a lead below kSegTau (viterbi_step.h) together with its lead;
+//      seam_check() refuses a segment unless D_i + 2 rho <= kSegTau / 4 at every step, and returns the bound the segment
+//      actually reached: a listed decision whose lead exceeds it is certified after all.
 //  (2) with the winners w(j) equal in both arithmetics,  err_{i+1}[j] = err_i[w(j)] + rho_j - (err_i[w(0)] + rho_0).  When
 //      every destination has the same winner — the normal case away from CNV regions, where every state is reached from
 //      state 0, and inside a called region, where every state is reached from the called one — the old deviations
@@ -24,8 +25,9 @@
 //      step; they never enter a decision.)  In every other case, including a listed decision whose winner may differ
 //      (max is 1-Lipschitz), D grows by at most 2 rho.  The sweep keeps the two multipliers of viterbi_step.h:
 //      seg_err_step per lane; the check needs their maxima and their values at the segment's end.
-// A listed decision matters only when the traceback reads it, i.e. when the final path — built from certified decisions
-// alone as long as it meets no listed one — is in that destination state at that observation (viterbi_seg_check_kernel);
+// An uncertified decision matters only when the traceback reads it, i.e. when the final path — built from certified
+// decisions alone as long as it meets no uncertified one — is in that destination state at that observation
+// (viterbi_seg_check_kernel);
 // then, and when a seam cannot be certified, the whole chain goes to the repair pass.
 //
 // The seam itself: segment s - 1, certified up to its end with spread D', hands over X'_end[k]; segment s arrives from
@@ -85,9 +87,11 @@ EDB_STEP_HD double piece_rho(const PieceErr& pe, double cabs)
 
 // One seam.  x_in: the piece's V after its warm-up; x_prev: the previous piece's V after its last observation; pe / prev:
 // what the two pieces reported (prev = null: the previous piece starts the chain, its values are the reference's own);
-// cabs: the line's bound of |C|.  Returns 0 when every decision the piece did not list is certified, else the reason.
+// cabs: the line's bound of |C|.  Returns 0 when every decision the piece did not list is certified, else the reason;
+// *certified: the lead above which a decision of this piece is certified.
 template <int S>
-EDB_STEP_HD int seam_check(const double* x_in, const double* x_prev, const PieceErr& pe, const PieceErr* prev, double cabs)
+EDB_STEP_HD int seam_check(const double* x_in, const double* x_prev, const PieceErr& pe, const PieceErr* prev, double cabs,
+                           double* certified = nullptr)
 {
     double m = 0.0, big = 0.0;
     bool finite = true;
@@ -112,6 +116,9 @@ EDB_STEP_HD int seam_check(const double* x_in, const double* x_prev, const Piece
     const double rho = piece_rho(pe, cabs);
     const double worst = (double)pe.max_a * e0 + ((double)pe.max_b + 2.0) * 2.0 * rho;
     if (!(worst <= kSegEpsMax) || !(bv + cabs < kSegMagMax)) return kBadSeamError;
+    // every decision of the piece whose lead exceeds `worst` (>= D_i + 2 rho at every step) is certified — also a LISTED one:
+    // the list holds the leads below kSegTau, most of which are far above the bound the piece actually reached
+    if (certified) *certified = worst;
     return 0;
 }
 

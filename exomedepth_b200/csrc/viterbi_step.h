@@ -347,10 +347,11 @@ EDB_STEP_HD unsigned viterbi_step_spec_m(double* V, const double* em, double c0,
 
 // The plain scan of src/hmm.cpp:66-88 over the structured row, keeping the runner-up: arg[j] is the reference's first
 // maximum (in the arithmetic of the V given), and bit j of the result is set when destination j's winner leads the best
-// other candidate by less than kSegTau (ties included).  Preconditions (caller): every V and emission finite, c0 and c1
+// other candidate by less than kSegTau (ties included); lead[j], if asked for, is that lead.  Preconditions (caller): every V and emission finite, c0 and c1
 // finite — so a finite candidate from k = 0 exists, no "from = -1", no forced 0.
 template <int S>
-EDB_STEP_HD unsigned viterbi_step_margin(double* V, const double* em, double c0, double c1, const StructRow& row, unsigned* arg)
+EDB_STEP_HD unsigned viterbi_step_margin(double* V, const double* em, double c0, double c1, const StructRow& row, unsigned* arg,
+                                         double* lead = nullptr)
 {
     const double ninf = -HUGE_VAL;
     double nv[S];
@@ -369,7 +370,9 @@ EDB_STEP_HD unsigned viterbi_step_margin(double* V, const double* em, double c0,
             best = win ? c : best;
             a = win ? (unsigned)k : a;
         }
-        if (!(EDB_ADD(best, -second) >= kSegTau)) close |= 1u << j;
+        const double ld = EDB_ADD(best, -second);
+        if (!(ld >= kSegTau)) close |= 1u << j;
+        if (lead) lead[j] = ld;                             // (NaN when every candidate is -Inf: listed, lead unknown)
         nv[j] = best;
         arg[j] = a;
     }

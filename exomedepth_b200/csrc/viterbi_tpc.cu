@@ -49,7 +49,7 @@ struct PairArgs {
     double c0, c1;
     // segmented sweep only (tpc_pair_margin): where to report, and which decisions these are
     const ViterbiArgs* va;
-    int chain, smp, obs;        // obs: the first observation of the pair
+    int chain, piece, smp, obs; // obs: the first observation of the pair
     int rec;                    // 0: warm-up (decisions are not recorded, hence not listed)
 };
 template <int S>
@@ -115,7 +115,7 @@ __device__ __forceinline__ void seg_mark_bad(int32_t* flags, int n_chains, int n
 // Returns the step's kind for the error multipliers.
 template <int S>
 __device__ __forceinline__ int seg_step_margin(double* V, const double* em, const StructRow& row, double c0, double c1, unsigned* arg,
-                                               const ViterbiArgs* va, int chain, int smp, int obs, int rec)
+                                               const ViterbiArgs* va, int chain, int piece, int smp, int obs, int rec)
 {
     unsigned worst = 0;
 #pragma unroll
@@ -125,13 +125,16 @@ __device__ __forceinline__ int seg_step_margin(double* V, const double* em, cons
         if (rec) seg_mark_bad(va->seg_flags, va->n_chains, va->n_samples, chain, smp, kBadNonFinite);
         return 1;
     }
-    const unsigned close = viterbi_step_margin<S>(V, em, c0, c1, row, arg);
+    double lead[S];
+    const unsigned close = viterbi_step_margin<S>(V, em, c0, c1, row, arg, lead);
     if (close && rec) {
 #pragma unroll 1
         for (int j = 0; j < S; j++)
             if (close >> j & 1u) {
+                // (piece, sample, observation, destination | the lead as a float rounded towards zero, low three bits dropped)
+                const double ld = lead[j] > 0.0 ? lead[j] : 0.0;
                 const int q = atomicAdd(va->seg_flags, 1);
-                if (q < va->seg_close_cap) va->seg_close[q] = make_int4(chain, smp, obs, j);
+                if (q < va->seg_close_cap) va->seg_close[q] = make_int4(piece, smp, obs, (int)((__float_as_uint(__double2float_rz(ld)) & ~7u) | (unsigned)j));
                 else seg_mark_bad(va->seg_flags, va->n_chains, va->n_samples, chain, smp, kBadListFull);
             }
     }
@@ -154,8 +157,8 @@ __device__ __noinline__ PairRes<S> tpc_pair_margin(const PairArgs<S> a)
     const double2 r0a = lds_f64x2(a.rows), r1a = lds_f64x2(a.rows + 32);
     const StructRow rowA{r0a.x, r0a.y, lds_f64(a.rows + 16), 0.0}, rowB{r1a.x, r1a.y, lds_f64(a.rows + 48), 0.0};
     unsigned argB[S];
-    const int ka = seg_step_margin<S>(V, ea, rowA, a.c0, a.c1, r.acc, a.va, a.chain, a.smp, a.obs, a.rec);
-    const int kb = seg_step_margin<S>(V, eb, rowB, a.c0, a.c1, argB, a.va, a.chain, a.smp, a.obs + 1, a.rec);
+    const int ka = seg_step_margin<S>(V, ea, rowA, a.c0, a.c1, r.acc, a.va, a.chain, a.piece, a.smp, a.obs, a.rec);
+    const int kb = seg_step_margin<S>(V, eb, rowB, a.c0, a.c1, argB, a.va, a.chain, a.piece, a.smp, a.obs + 1, a.rec);
 #pragma unroll
     for (int j = 0; j < S; j++) {
         r.acc[j] |= argB[j] << 4;
@@ -171,7 +174,7 @@ struct MStepArgs {
     double v[S], em[S];
     double b0, sf, ot, c0, c1;
     const ViterbiArgs* va;
-    int chain, smp, obs;
+    int chain, piece, smp, obs;
     int rec;
 };
 template <int S>
@@ -191,7 +194,7 @@ __device__ __noinline__ MStepRes<S> tpc_step_margin(const MStepArgs<S> a)
         em[j] = a.em[j];
     }
     const StructRow row{a.b0, a.sf, a.ot, 0.0};
-    r.kind = seg_step_margin<S>(V, em, row, a.c0, a.c1, r.arg, a.va, a.chain, a.smp, a.obs, a.rec);
+    r.kind = seg_step_margin<S>(V, em, row, a.c0, a.c1, r.arg, a.va, a.chain, a.piece, a.smp, a.obs, a.rec);
 #pragma unroll
     for (int j = 0; j < S; j++) r.v[j] = V[j];
     return r;
@@ -477,7 +480,7 @@ viterbi_tpc_kernel(const __grid_constant__ ViterbiArgs a, const __grid_constant_
                             pa.c0 = c0;
                             pa.c1 = c1;
                             pa.va = &a;
-                            pa.chain = chain, pa.smp = smp, pa.obs = ih + 2 * pp, pa.rec = rec ? 1 : 0;
+                            pa.chain = chain, pa.piece = wi.piece, pa.smp = smp, pa.obs = ih + 2 * pp, pa.rec = rec ? 1 : 0;
                             PairRes<S> pr;
                             if (kSeg && mseg) {
                                 pr = tpc_pair_margin<S>(pa);
@@ -538,7 +541,7 @@ viterbi_tpc_kernel(const __grid_constant__ ViterbiArgs a, const __grid_constant_
                                     }
                                     ma.b0 = row.b0, ma.sf = row.sf, ma.ot = row.ot, ma.c0 = c0, ma.c1 = c1;
                                     ma.va = &a;
-                                    ma.chain = chain, ma.smp = smp, ma.obs = i, ma.rec = rec ? 1 : 0;
+                                    ma.chain = chain, ma.piece = wi.piece, ma.smp = smp, ma.obs = i, ma.rec = rec ? 1 : 0;
                                     const MStepRes<S> rm = tpc_step_margin<S>(ma);
                                     seg_err_step(err_a, err_b, rm.kind);
                                     max_b = max(max_b, err_b);
@@ -592,8 +595,10 @@ viterbi_tpc_kernel(const __grid_constant__ ViterbiArgs a, const __grid_constant_
 // ---- check kernel of the segmented sweep (after expand: it reads the path) --------------------------------------------
 // Part 1, one thread per (piece, sample): the seam in front of the piece (viterbi_seam.h: seam_check) — the chain is
 // refused when the seam does not close or the certified deviation outgrows kSegEpsMax.  Part 2, one thread per listed
-// decision (lead below kSegTau): the decision (observation i, destination j) is read by the traceback only if the path is
-// in state j at observation i; then the chain is refused too.  Refused chains are swept again by the repair pass.
+// decision (lead below kSegTau): certified after all when its lead exceeds the deviation its piece actually reached
+// (typically 1e-7 against leads spread over 0 .. 6e-5); otherwise the decision (observation i, destination j) is read by
+// the traceback only if the path is in state j at observation i — then the chain is refused too.  Refused chains are swept
+// again by the repair pass.
 template <int S>
 __global__ void __launch_bounds__(128)
 viterbi_seg_check_kernel(ViterbiArgs a, int n_pieces)
@@ -601,36 +606,45 @@ viterbi_seg_check_kernel(ViterbiArgs a, int n_pieces)
     const int n_g32 = seg_n_g32(a.n_samples);
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, n_thr = (int64_t)gridDim.x * blockDim.x;
     const double* cabs = reinterpret_cast<const double*>(a.seg_flags + seg_off_cabs(a.n_chains, a.n_samples));
+    // the seam in front of piece pc for lane `lane`: 0 / the reason it is refused; *certified: the lead above which the
+    // piece's decisions are certified
+    auto seam = [&](int pc, int lane, const int4& d, double* certified) -> int {
+        double x_in[S], x_prev[S];
+#pragma unroll
+        for (int j = 0; j < S; j++) {
+            x_in[j] = a.seam_in[((int64_t)pc * S + j) * 32 + lane];
+            x_prev[j] = a.seam_out[((int64_t)(pc - 1) * S + j) * 32 + lane];
+        }
+        const unsigned* w = a.seam_mag + (int64_t)pc * (kSeamWords * 32) + lane;
+        const PieceErr pe{w[0], w[32], w[64], w[96], w[128], w[160]};
+        const unsigned* v = w - kSeamWords * 32;
+        const PieceErr prev{v[0], v[32], v[64], v[96], v[128], v[160]};
+        const bool prev_exact = a.seg_desc[pc - 1].z == 0;          // piece pc - 1 is the one before it on its line
+        return seam_check<S>(x_in, x_prev, pe, prev_exact ? nullptr : &prev, cabs[((int64_t)d.x * n_g32 + d.y) * 32 + lane], certified);
+    };
     for (int64_t q = tid; q < (int64_t)n_pieces * 32; q += n_thr) {
         const int pc = (int)(q >> 5), lane = (int)(q & 31);
         const int4 d = a.seg_desc[pc];
         const int smp = d.y * 32 + lane;
         if (smp >= a.n_samples) continue;
         int bad = a.seg_force_repair ? kBadForced : 0;
-        if (d.z > 0) {                                      // a piece behind a seam; piece pc - 1 is the one before it on its line
-            double x_in[S], x_prev[S];
-#pragma unroll
-            for (int j = 0; j < S; j++) {
-                x_in[j] = a.seam_in[((int64_t)pc * S + j) * 32 + lane];
-                x_prev[j] = a.seam_out[((int64_t)(pc - 1) * S + j) * 32 + lane];
-            }
-            const unsigned* w = a.seam_mag + (int64_t)pc * (kSeamWords * 32) + lane;
-            const PieceErr pe{w[0], w[32], w[64], w[96], w[128], w[160]};
-            const unsigned* v = w - kSeamWords * 32;
-            const PieceErr prev{v[0], v[32], v[64], v[96], v[128], v[160]};
-            const bool prev_exact = a.seg_desc[pc - 1].z == 0;
-            bad |= seam_check<S>(x_in, x_prev, pe, prev_exact ? nullptr : &prev, cabs[((int64_t)d.x * n_g32 + d.y) * 32 + lane]);
-        }
+        if (d.z > 0) bad |= seam(pc, lane, d, nullptr);     // a piece behind a seam
         if (bad) seg_mark_bad(a.seg_flags, a.n_chains, a.n_samples, d.x, smp, bad);
     }
     const int n_close = min(a.seg_flags[0], a.seg_close_cap);
     for (int64_t q = tid; q < n_close; q += n_thr) {
-        const int4 e = a.seg_close[q];
-        const ChainDesc cd = a.chains[e.x];
+        const int4 e = a.seg_close[q];                      // (piece, sample, observation, destination | lead)
+        const int4 d = a.seg_desc[e.x];
+        const int dest = e.w & 7;
+        const double lead = (double)__uint_as_float((unsigned)e.w & ~7u);
+        double certified = 0.0;
+        if (seam(e.x, e.y & 31, d, &certified)) continue;   // a refused seam: part 1 has refused the chain already
+        if (lead > certified) continue;                     // listed, yet far enough above what the piece's deviation reached
+        const ChainDesc cd = a.chains[d.x];
         bool on = true;                                     // an observation whose state is not on record: assume the worst
-        if (e.z == cd.nobs - 1) on = e.w == 0;              // the chain ends in state 0 (hmm.cpp:96)
-        else if (e.z >= cd.out_first && e.z <= cd.out_last) on = (int)a.path[e.y * a.path_stride + cd.out_off + e.z] == e.w;
-        if (on) seg_mark_bad(a.seg_flags, a.n_chains, a.n_samples, e.x, e.y, kBadOnPath);
+        if (e.z == cd.nobs - 1) on = dest == 0;             // the chain ends in state 0 (hmm.cpp:96)
+        else if (e.z >= cd.out_first && e.z <= cd.out_last) on = (int)a.path[e.y * a.path_stride + cd.out_off + e.z] == dest;
+        if (on) seg_mark_bad(a.seg_flags, a.n_chains, a.n_samples, d.x, e.y, kBadOnPath);
     }
 }
 

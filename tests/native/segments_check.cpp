@@ -100,7 +100,7 @@ struct Model {
 };
 
 template <int S>
-static Model<S> make_model(uint64_t seed, int n, double scale, int flat_from, int flat_len, bool near_ties)
+static Model<S> make_model(uint64_t seed, int n, double scale, int flat_from, int flat_len, double near_ties)
 {
     std::mt19937_64 rng(seed);
     std::uniform_real_distribution<double> U(0.0, 1.0);
@@ -130,8 +130,8 @@ static Model<S> make_model(uint64_t seed, int n, double scale, int flat_from, in
             if (U(rng) < 0.08) llr = 0.5 + 3.0 * U(rng);   // noisy bin: a CNV state beats normal for one observation
             if (cnv_left > 0 && j == cnv_state) llr = 3.0 + 20.0 * U(rng);
             // after a step won from k = 0, V[j] - V[0] = llr + c1 - c0, so at the NEXT observation self - cand0 = llr + sf' - c0:
-            // this llr puts that lead within ~1e-4 of zero (listed when below 2^-14)
-            if (near_ties && i + 1 < n && U(rng) < 0.01) llr = m.c0 - m.rows[i + 1].sf + (U(rng) - 0.5) * 4e-4;
+            // this llr puts that lead within near_ties / 2 of zero (listed when below 2^-14)
+            if (near_ties > 0 && i + 1 < n && U(rng) < 0.01) llr = m.c0 - m.rows[i + 1].sf + (U(rng) - 0.5) * near_ties;
             m.em[(size_t)i * S + j] = j == 0 ? base : base + llr;
         }
         if (i >= flat_from && i < flat_from + flat_len)
@@ -151,7 +151,7 @@ static void expand_row(double c0, double c1, const edb::StructRow& r, double* lt
 template <int S>
 static void check_steps(uint64_t seed)
 {
-    Model<S> m = make_model<S>(seed, 4000, 400.0, -1, 0, true);
+    Model<S> m = make_model<S>(seed, 4000, 400.0, -1, 0, 4e-4);
     double Va[S], Vb[S], Vc[S], Vd[S];
     for (int j = 0; j < S; j++) Va[j] = Vb[j] = j == 0 ? 0.0 : -1.0 - j;
     long long close_seen = 0, spec_ok = 0;
@@ -201,7 +201,7 @@ static void check_steps(uint64_t seed)
 
 // sequential sweep (reference arithmetic) vs pieces + certification, as the kernel and the check kernel do it
 template <int S>
-static void check_scheme(uint64_t seed, int n, double scale, int piece, int warm, int flat_from, int flat_len, bool near_ties, bool expect_refusal)
+static void check_scheme(uint64_t seed, int n, double scale, int piece, int warm, int flat_from, int flat_len, double near_ties, bool expect_uncertified)
 {
     Model<S> m = make_model<S>(seed, n, scale, flat_from, flat_len, near_ties);
     // reference
@@ -232,9 +232,11 @@ static void check_scheme(uint64_t seed, int n, double scale, int piece, int warm
         double x_in[S], x_end[S];
         edb::PieceErr pe;
         std::vector<unsigned> arg, closev;
+        std::vector<float> lead;        // per decision, as the kernel lists it: a float rounded towards zero, low three bits dropped
+        double certified = 0.0;         // the lead above which the piece's decisions are certified (seam_check)
     };
     std::vector<Piece> pieces;
-    long long certified = 0, listed = 0, listed_on_path = 0, wrong_certified = 0, refused_pieces = 0;
+    long long certified = 0, listed = 0, listed_on_path = 0, listed_certified = 0, wrong_certified = 0, refused_pieces = 0;
     const double c0m = m.c0 - edb::kSpecMargin;
     double cabs = 0.0;
     for (int p0 = 0; p0 < n; p0 += piece) {
@@ -256,6 +258,7 @@ static void check_scheme(uint64_t seed, int n, double scale, int piece, int warm
         unsigned err_a = mseg ? 1u : 0u, err_b = 0;
         pc.arg.assign((size_t)(p1 - p0) * S, 0);
         pc.closev.assign(p1 - p0, 0);
+        pc.lead.assign((size_t)(p1 - p0) * S, 0.0f);
         for (int i = p0; i < p1; i++) {
             for (int j = 0; j < S; j++) {
                 pe.mag_v = std::max(pe.mag_v, edb::f64_hi(X[j]) << 1);
@@ -279,8 +282,18 @@ static void check_scheme(uint64_t seed, int n, double scale, int piece, int warm
                     for (int j = 1; j < S; j++) a[j] = (b >> (j - 1) & 1u) ? (unsigned)j : 0u;
                     edb::seg_err_step(err_a, err_b, b ? 1 : 0);
                 } else {
-                    const unsigned close = edb::viterbi_step_margin<S>(X, &m.em[(size_t)i * S], m.c0, m.c1, m.rows[i], a);
+                    double ld[S];
+                    const unsigned close = edb::viterbi_step_margin<S>(X, &m.em[(size_t)i * S], m.c0, m.c1, m.rows[i], a, ld);
                     pc.closev[i - p0] = close;
+                    for (int j = 0; j < S; j++) {
+                        float f = (float)(ld[j] > 0.0 ? ld[j] : 0.0);
+                        if ((double)f > ld[j]) f = std::nextafterf(f, 0.0f);           // round towards zero
+                        uint32_t u;
+                        memcpy(&u, &f, 4);
+                        u &= ~7u;
+                        memcpy(&f, &u, 4);
+                        pc.lead[(size_t)(i - p0) * S + j] = f;
+                    }
                     edb::seg_err_step(err_a, err_b, edb::seg_err_kind<S>(a, close));
                 }
                 pe.max_b = std::max(pe.max_b, err_b);
@@ -308,8 +321,8 @@ static void check_scheme(uint64_t seed, int n, double scale, int piece, int warm
     }
     std::vector<int> refused(pieces.size(), 0);
     for (size_t q = 1; q < pieces.size(); q++) {
-        const Piece& pc = pieces[q];
-        const int bad = edb::seam_check<S>(pc.x_in, pieces[q - 1].x_end, pc.pe, q == 1 ? nullptr : &pieces[q - 1].pe, cabs);
+        Piece& pc = pieces[q];
+        const int bad = edb::seam_check<S>(pc.x_in, pieces[q - 1].x_end, pc.pe, q == 1 ? nullptr : &pieces[q - 1].pe, cabs, &pc.certified);
         if (bad && getenv("SEG_DEBUG"))
             printf("  seam %zu bad %d: cabs %g mag_v %x mag_e %x max_b %u end_a %u end_b %u prev(end_a %u end_b %u) rho %g\n", q, bad, cabs, pc.pe.mag_v, pc.pe.mag_e,
                    pc.pe.max_b, pc.pe.end_a, pc.pe.end_b, pieces[q - 1].pe.end_a, pieces[q - 1].pe.end_b, edb::piece_rho(pc.pe, cabs));
@@ -326,21 +339,23 @@ static void check_scheme(uint64_t seed, int n, double scale, int piece, int warm
         for (int i = pc.p0; i < pc.p1; i++)
             for (int j = 0; j < S; j++) {
                 const bool is_listed = pc.closev[i - pc.p0] >> j & 1u;
-                if (is_listed) {
+                // a listed decision is certified after all when its lead exceeds what the piece's deviation reached
+                if (is_listed && !((double)pc.lead[(size_t)(i - pc.p0) * S + j] > pc.certified)) {
                     listed++;
                     listed_on_path += path[i] == j;
                     continue;
                 }
+                listed_certified += is_listed;
                 certified++;
                 if (pc.arg[(size_t)(i - pc.p0) * S + j] != ref_arg[(size_t)i * S + j]) wrong_certified++;
             }
     }
     CHECK(wrong_certified == 0, "S=%d seed %llu: %lld certified decisions differ from the sequential sweep", S, (unsigned long long)seed, wrong_certified);
     CHECK(certified > 0, "nothing certified");
-    if (expect_refusal) CHECK(refused_pieces > 0, "S=%d: a seam inside an uninformative stretch longer than the warm-up was certified", S);
-    else CHECK(refused_pieces == 0, "S=%d seed %llu scale %.0f: %lld pieces refused", S, (unsigned long long)seed, scale, refused_pieces);
-    printf("scheme S=%d scale %.0f piece %d warm %d: certified %lld, listed %lld (%lld on the path), refused pieces %lld\n", S, scale, piece, warm,
-           certified, listed, listed_on_path, refused_pieces);
+    CHECK(refused_pieces == 0, "S=%d seed %llu scale %.0f: %lld pieces refused", S, (unsigned long long)seed, scale, refused_pieces);
+    if (expect_uncertified) CHECK(listed > 0, "S=%d: leads planted inside the rounding noise were all certified", S);
+    printf("scheme S=%d scale %.0f piece %d warm %d: certified %lld (%lld of them listed, lead above the piece's bound), uncertified %lld (%lld on the path), "
+           "refused pieces %lld\n", S, scale, piece, warm, certified, listed_certified, listed, listed_on_path, refused_pieces);
 }
 
 int main()
@@ -364,15 +379,18 @@ int main()
     check_steps<7>(13);
     // (3) magnitudes of the reference's likelihood (no binomial coefficient: hundreds per bin, |V| ~ 1e7 per chromosome)
     for (uint64_t seed = 1; seed <= 6; seed++) {
-        check_scheme<5>(seed, 12000, 650.0, 1500, 64, -1, 0, false, false);
-        check_scheme<5>(seed + 10, 12000, 5.0, 700, 32, -1, 0, true, false);
-        check_scheme<3>(seed + 20, 8000, 650.0, 333, 32, -1, 0, true, false);
-        check_scheme<7>(seed + 30, 8000, 100.0, 1000, 64, -1, 0, false, false);
+        check_scheme<5>(seed, 12000, 650.0, 1500, 64, -1, 0, 0.0, false);
+        check_scheme<5>(seed + 10, 12000, 5.0, 700, 32, -1, 0, 4e-4, false);
+        check_scheme<3>(seed + 20, 8000, 650.0, 333, 32, -1, 0, 4e-4, false);
+        // leads planted INSIDE the rounding noise of |V| ~ 1e7 (one ulp is 2e-9): they stay uncertified — and may well differ from
+        // the sequential sweep, which is what the repair pass is for — while everything certified must still agree
+        check_scheme<5>(seed + 40, 12000, 650.0, 1500, 32, -1, 0, 2e-8, true);
+        check_scheme<7>(seed + 30, 8000, 100.0, 1000, 64, -1, 0, 0.0, false);
     }
     // an uninformative stretch that swallows a whole warm-up: the piece starts from (0, -Inf, ...) one observation before...
     // no — from the stationary vector of the flat stretch, which the previous piece also reaches: certified; and a warm-up
     // that starts INSIDE a called region which extends to the seam: refused or certified, never wrong
-    check_scheme<5>(99, 6000, 650.0, 1000, 16, 900, 200, false, false);
+    check_scheme<5>(99, 6000, 650.0, 1000, 16, 900, 200, 0.0, false);
     if (fails) {
         printf("%d failures\n", fails);
         return 1;

@@ -1,8 +1,3 @@
 mkdir -p gpurun_out
-timeout 500 python bench.py > gpurun_out/r2h_bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -2 gpurun_out/bench.err
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2h_bench_reference.json 2>> gpurun_out/bench.err; echo "ref rc=$?"
-timeout 300 python bench.py --workload small_panel > gpurun_out/r2h_bench_panel.json 2>> gpurun_out/bench.err; echo "panel rc=$?"
-timeout 300 python bench.py --workload refset --steps 5 > gpurun_out/r2h_bench_refset.json 2>> gpurun_out/bench.err; echo "refset rc=$?"
-timeout 300 python bench.py --states 3 --no-aux --no-ll > gpurun_out/r2h_bench_s3.json 2>> gpurun_out/bench.err; echo "s3 rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2h_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-aux --no-parity > /dev/null 2>&1; echo "ncu list rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:viterbi_tpc_kernel.*\(bool\)1|emission_table_kernel' -s 2 -c 2 -o gpurun_out/r2h_full python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-aux --no-parity > /dev/null 2>&1; echo "ncu full rc=$?"
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/all_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/all_pytest.log
+for f in 256 512 768 1024 1280 1536 1792; do timeout 300 python tools/perf_probe.py --first $f --gen 256 --reps 2 2>&1 | grep "^segments\|emission+viterbi" | cut -c1-330; done

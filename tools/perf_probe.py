@@ -24,12 +24,13 @@ ap.add_argument("--seg", type=int, default=-1, help="segmented sweep: -1 auto, 0
 ap.add_argument("--seg-min", type=int, default=0)
 ap.add_argument("--seg-warm", type=int, default=0)
 ap.add_argument("--warps", type=int, default=0)
+ap.add_argument("--first", type=int, default=0, help="index of the first synthetic sample")
 a = ap.parse_args()
 
 edb.init(0)
 print(edb.device_info())
 t0 = time.time()
-d = synth.cohort(min(a.gen, a.samples), n_bins=a.bins)
+d = synth.cohort(min(a.gen, a.samples), n_bins=a.bins, first_sample=a.first)
 print("synth", time.time() - t0)
 reps = (a.samples + d["observed"].shape[0] - 1) // d["observed"].shape[0]
 obs = np.tile(d["observed"], (reps, 1))[:a.samples]
