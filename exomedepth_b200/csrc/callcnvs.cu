@@ -105,9 +105,6 @@ count_cor_kernel(CountsView c, int n_samples, int64_t n_bins, double* __restrict
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
     const int32_t* __restrict__ obs = c.observed + sample * c.obs_stride;
     const int32_t* __restrict__ oth = c.other + sample * c.other_stride;
-    auto ref_at = [&](int64_t b, int o) -> double {
-        return c.other_is_total ? __dadd_rn((double)oth[b], -(double)o) : (double)oth[b];
-    };
     // the CTA-wide total of up to three compensated sums, combined in warp order
     auto cta_total = [&](Comp* v, int nv, double* out) {
         for (int q = 0; q < nv; q++) {
@@ -133,12 +130,27 @@ count_cor_kernel(CountsView c, int n_samples, int64_t n_bins, double* __restrict
         }
         __syncthreads();
     };
+    // 128-bit loads, four bins per thread and trip (with one 4-byte load per trip the kernel is bound by the latency of
+    // 2 x 391 dependent trips: 0.2 ms for 64 samples x 200k bins, during which its CTAs keep the emission kernel of the next
+    // chunk off their SMs)
+    const bool vec = ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(oth)) & 15) == 0;
+    const int64_t n4 = vec ? n_bins & ~(int64_t)3 : 0;
+    auto each = [&](auto&& f) {
+        for (int64_t b = (int64_t)threadIdx.x * 4; b < n4; b += (int64_t)blockDim.x * 4) {
+            const int4 o = __ldg(reinterpret_cast<const int4*>(obs + b)), r = __ldg(reinterpret_cast<const int4*>(oth + b));
+            f(o.x, r.x);
+            f(o.y, r.y);
+            f(o.z, r.z);
+            f(o.w, r.w);
+        }
+        for (int64_t b = n4 + threadIdx.x; b < n_bins; b += blockDim.x) f(obs[b], oth[b]);
+    };
+    const int is_total = c.other_is_total;
     Comp v[3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int64_t b = threadIdx.x; b < n_bins; b += blockDim.x) {
-        const int o = obs[b];
+    each([&](int o, int r) {
         comp_add(v[0], (double)o);
-        comp_add(v[1], ref_at(b, o));
-    }
+        comp_add(v[1], is_total ? __dadd_rn((double)r, -(double)o) : (double)r);
+    });
     __shared__ double tot[3];
     cta_total(v, 2, tot);
     if (threadIdx.x == 0) {
@@ -148,13 +160,12 @@ count_cor_kernel(CountsView c, int n_samples, int64_t n_bins, double* __restrict
     __syncthreads();
     const double mx = mean[0], my = mean[1];
     v[0] = v[1] = v[2] = Comp{0, 0, 0};
-    for (int64_t b = threadIdx.x; b < n_bins; b += blockDim.x) {
-        const int o = obs[b];
-        const double dx = __dadd_rn((double)o, -mx), dy = __dadd_rn(ref_at(b, o), -my);
+    each([&](int o, int r) {
+        const double dx = __dadd_rn((double)o, -mx), dy = __dadd_rn(is_total ? __dadd_rn((double)r, -(double)o) : (double)r, -my);
         comp_add(v[0], __dmul_rn(dx, dy));
         comp_add(v[1], __dmul_rn(dx, dx));
         comp_add(v[2], __dmul_rn(dy, dy));
-    }
+    });
     cta_total(v, 3, tot);
     if (threadIdx.x == 0) {
         double r = tot[0] / (sqrt(tot[1]) * sqrt(tot[2]));       // NaN for a constant vector, like R (with its warning)

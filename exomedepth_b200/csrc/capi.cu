@@ -260,6 +260,7 @@ struct edb200_cohort {
     // segmented sweep (viterbi_seam.h); seg_ok: the transition terms are small enough for the error bound (ensure_struct)
     int seg_ok = 0;
     int seg_slot = 0;                    // which sample chunk of a host call is being processed (its pieces and flags are its own)
+    int emission_sms = 0;                // SMs the emission launch of the current chunk may take (0 = all)
     bool in_host_call = false;
     // the pieces of one chromosome group for `key` (samples, warps, warm-up, shortest piece), its scratch and flags
     struct SegPlan {
@@ -1301,6 +1302,7 @@ static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiA
 // Defaults: a warm-up of 2 tiles (32 observations; 8 already close every seam of the synthetic cohorts, and a seam that does
 // not close only costs its chain the repair pass), pieces of at least 12 tiles.
 constexpr int kSegWarm = 2, kSegMinPiece = 12;
+constexpr int kChunkReserve = 56;        // SMs the emission of a middle chunk leaves to the Viterbi kernels of the chunk before it
 // Whether to cut the chains: when an even share of all tiles per sweep warp (plus its warm-up) is well below what bounds
 // the plain sweeps — the longest chain, or the whole lines packed onto the warps.
 static bool use_segments(const edb200_cohort* c, int n_samples)
@@ -1474,7 +1476,7 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
             all.n = 1;
             all.b0[0] = 0;
             all.b1[0] = c->n_bins;
-            if (int rc = emission_part(c, b, all, true, emission_mode, 0, st)) return rc;
+            if (int rc = emission_part(c, b, all, true, emission_mode, 0, st, c->emission_sms)) return rc;
         }
         if (what & 2) {
             // 0: one pass (tests, experiments).  The thread-per-chain sweep is split only while there are fewer work items than
@@ -1738,13 +1740,13 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     // ---- sample-chunk pipeline (segmented sweeps).  With the chains cut into pieces no chromosome is a critical path any
     // more, so the batch goes through in chunks of SAMPLES: chunk k+1 uploads (contiguous rows) while chunk k runs emission,
     // then its segmented sweep, on ONE compute stream — both kernels fill every SM; side by side they only trade SMs.
-    // T ~ U / k + G + k * o  (U upload, G device time of the batch, o ~ 0.25 ms of launches, tails and partly filled rounds per
-    // chunk): k ~ sqrt(U / o).
+    // T ~ U / k + G + k * o  (U upload, G device time of the batch, o ~ 0.1-0.25 ms of launches, tails and partly filled rounds
+    // per chunk): k ~ sqrt(U / o).
     int seg_k = 0, seg_per = 0;
     if (want_vit && !b->per_bin_stride && use_table(c, emission_mode) && c->opt_parts == 0) {
         if ((rc = ensure_struct(c))) return rc;
-        const double upload_ms = (double)ns * nb * (u16 ? 2.0 : 4.0) / 53e6, per_chunk_ms = 0.25;
-        int k = c->opt_chunks > 0 ? c->opt_chunks : (int)std::lround(std::sqrt(upload_ms / per_chunk_ms));       // (3 at 256 x 200k, 16-bit)
+        const double upload_ms = (double)ns * nb * (u16 ? 2.0 : 4.0) / 53e6, per_chunk_ms = 0.12;
+        int k = c->opt_chunks > 0 ? c->opt_chunks : (int)std::lround(std::sqrt(upload_ms / per_chunk_ms));       // (4 at 256 x 200k, 16-bit: measured best with 56 SMs reserved)
         k = std::max(1, std::min({k, Context::kMaxParts, ns / 24}));
         // chunk size: a whole number of rounds of the emission kernel's (sample, state) items over the SMs (64 samples x 5
         // states on 148 SMs are 2.16 rounds and cost 3)
@@ -1762,7 +1764,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         }
     }
     if (seg_k > 0) {
-        cudaStream_t sc = g.s_copy, sx = g.s_em, sv = g.s_vit[0];
+        cudaStream_t sc = g.s_copy, sx = g.s_em, sv = g.s_vit[0], sw = g.s_vit[2];
         if (shared_ref) CU(cudaMemcpyAsync(c->h_ref.p, b->reference, nb * 4, cudaMemcpyHostToDevice, sc));
         CU(cudaMemcpyAsync(c->h_phi.p, b->phi, ns * 8, cudaMemcpyHostToDevice, sc));
         CU(cudaMemcpyAsync(c->h_exp.p, b->expected, ns * 8, cudaMemcpyHostToDevice, sc));
@@ -1787,13 +1789,17 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
                 CU(cudaMemcpy2DAsync((int32_t*)c->h_ref.p + (size_t)s0 * nb, nb * 4, b->reference + (size_t)s0 * b->ref_stride, b->ref_stride * 4,
                                      nb * 4, cnt, cudaMemcpyHostToDevice, sc));
             edb::prof_mark(nullptr, sc);
-            if (u16) {
-                g_launches += edb::launch_widen_counts((const uint16_t*)c->h_obs16.p + (size_t)s0 * nb, nb, (int32_t*)c->h_obs.p + (size_t)s0 * nb, nb, cnt, nb,
-                                                       all, nullptr, nullptr, 0, sc);
-                g_launches += edb::launch_patch_overflow((int32_t*)c->h_obs.p, nb, nb, all, (const int64_t*)c->h_ovf_i.p, (const int32_t*)c->h_ovf_v.p,
-                                                         b->n_overflow, sc, s0, s0 + cnt);
-            }
             CU(cudaEventRecord(g.ev_copy[k], sc));
+            if (u16) {
+                // widened on a stream of its own: on the copy stream the kernel — whose blocks wait for an SM while an emission
+                // grid is resident — would hold up the next chunk's upload (0.1 ms per chunk)
+                CU(cudaStreamWaitEvent(sw, g.ev_copy[k], 0));
+                g_launches += edb::launch_widen_counts((const uint16_t*)c->h_obs16.p + (size_t)s0 * nb, nb, (int32_t*)c->h_obs.p + (size_t)s0 * nb, nb, cnt, nb,
+                                                       all, nullptr, nullptr, 0, sw);
+                g_launches += edb::launch_patch_overflow((int32_t*)c->h_obs.p, nb, nb, all, (const int64_t*)c->h_ovf_i.p, (const int32_t*)c->h_ovf_v.p,
+                                                         b->n_overflow, sw, s0, s0 + cnt);
+                CU(cudaEventRecord(g.ev_copy[k], sw));
+            }
             CU(cudaStreamWaitEvent(sx, g.ev_copy[k], 0));
             edb200_batch e = d;
             e.n_samples = cnt;
@@ -1818,7 +1824,14 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
             // two compute streams: the emission of chunk k+1 behind the emission of chunk k, the Viterbi of chunk k behind its
             // emission and behind the Viterbi of chunk k-1 (they share the back-pointer scratch) — the SMs a sweep's last CTAs
             // and the small kernels behind it leave idle go to the next emission
-            if ((rc = edb200_cohort_run_device(c, &e, 1, emission_mode, sx))) return rc;
+            // every chunk but the last leaves `reserve` SMs to the Viterbi kernels of the chunk before it: an emission CTA owns its
+            // SM (208 KB of shared memory, 1,024 threads) for the whole launch, so behind a full-width emission grid the sweep, the
+            // tile maps, ... of the previous chunk simply wait
+            const bool last = s0 + cnt >= ns;
+            c->emission_sms = last || k == 0 ? 0 : g.n_sms - (c->opt_reserve > 0 ? std::min(c->opt_reserve, g.n_sms / 2) : kChunkReserve);
+            rc = edb200_cohort_run_device(c, &e, 1, emission_mode, sx);
+            c->emission_sms = 0;
+            if (rc) return rc;
             CU(cudaEventRecord(g.ev_em[k], sx));
             CU(cudaStreamWaitEvent(sv, g.ev_em[k], 0));
             if ((rc = edb200_cohort_run_device(c, &e, 2 | (d.call_stats ? 4 : 0), emission_mode, sv))) return rc;
