@@ -648,7 +648,13 @@ def refset_arm(a, rank, world):
     z_local = torch.zeros((per, kp), dtype=torch.float64, device=dev)
     z_all = torch.empty((world * per, kp), dtype=torch.float64, device=dev) if dist else z_local
     out = torch.empty((max(n_local, 1), n_total), dtype=torch.float64, device=dev)
-    fused = dist is not None and per <= 256 and world <= 4 and not a.no_fused
+    fused = dist is not None and per <= 256 and world <= 4 and not a.no_fused and a.exchange in ("auto", "fused")
+    by_blocks = dist is not None and not fused and (a.exchange == "blocks" or (a.exchange == "auto" and world > 2))
+    blk_bufs = blk_outs = None
+    if by_blocks:
+        rows = [max(0, min(per, n_total - j * per)) for j in range(world)]
+        blk_bufs = [z_local if j == rank else torch.empty_like(z_local) for j in range(world)]
+        blk_outs = [torch.empty((n_local, rows[j]), dtype=torch.float64, device=dev) for j in range(world)]
     if fused:
         z_ptr, handle = refset.block_alloc(per, sel.size)
         handles = [None] * world
@@ -661,6 +667,9 @@ def refset_arm(a, rank, world):
             torch.cuda.synchronize()
             dist.barrier()                                  # every block complete before any rank reads it over NVLink
             refset.gram_peers_device(n_local, per, n_total, sel.size, out)
+        elif by_blocks:
+            refset.standardize_device(c_t, sel_t, bl_t, z_local[:n_local])
+            shard.exchange_and_gram(z_local, n_local, per, n_total, sel.size, dist, dev, bufs=blk_bufs, outs=blk_outs)
         else:
             refset.standardize_device(c_t, sel_t, bl_t, z_local[:n_local])
             if dist:
@@ -725,6 +734,7 @@ def refset_arm(a, rank, world):
                         vs_baseline=None, dtype="f64", data="synthetic",
                         config=dict(workload=f"select.reference.set sweep, {n_total} samples x {nb} bins ({sel.size} selected), leave-one-out over the "
                                              "cohort (BASELINE.json configs[4])", exchange="CUDA-IPC peer-memory Gram (no all-gather)" if fused else
+                                             "one NCCL broadcast per rank's block, block j's Gram while block j + 1 is in flight" if by_blocks else
                                              ("NCCL all-gather of standardised rows, then Gram" if dist else "single rank"),
                                     all_gather_bytes_per_rank=int((world - 1) * per * kp * 8), cache="Z (2.2 GB) exceeds the 126 MB L2", nproc=os.cpu_count()),
                         clocks=clocks, e2e=e2e, gpu_launches=int(launches),
@@ -825,6 +835,8 @@ def main():
                          "refset = configs[4], the select.reference.set correlation sweep of 2,000 samples sharded over the ranks")
     ap.add_argument("--states", type=int, default=N_STATES, help="copy-number states of the cohort workload (3 = the reference's own model)")
     ap.add_argument("--no-fused", action="store_true", help="refset: NCCL all-gather + Gram instead of the peer-memory Gram")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "fused", "blocks"],
+                    help="refset: how the standardised rows reach the other ranks (auto: fused up to 4 ranks, block-wise broadcasts beyond)")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     a.warmup = max(a.warmup, 3) if a.impl == "graft" else a.warmup

@@ -108,7 +108,28 @@ def make_cohort(shared, dist=None, device=None, **cohort_kwargs):
     return co
 
 
-def refset_sweep(counts_local, n_total, bin_length=None, n_bins_reduced=0, dist=None, device=None, backend=None, fused=None):
+def exchange_and_gram(z_local, n_local, per, n_total, n_selected, dist, dev, bufs=None, outs=None):
+    """The exchange of the sharded reference-set sweep overlapped with its contraction: one asynchronous NCCL broadcast
+    per rank's block of standardised rows (z_local: [per, k_pad], this rank's block, zero-padded), and this rank's first
+    n_local rows against block j as soon as it has arrived.  Returns the list of [n_local, rows of block j] correlation
+    blocks (bufs / outs: reusable receive buffers and outputs)."""
+    import torch
+    from . import refset
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if bufs is None:
+        bufs = [z_local if j == rank else torch.empty_like(z_local) for j in range(world)]
+    rows = [max(0, min(per, n_total - j * per)) for j in range(world)]
+    if outs is None:
+        outs = [torch.empty((n_local, rows[j]), dtype=torch.float64, device=dev) for j in range(world)]
+    works = [dist.broadcast(bufs[j], src=j, async_op=True) for j in range(world)]
+    for j in range(world):
+        works[j].wait()                                     # the compute stream waits for block j, not the host
+        if n_local and rows[j]:
+            refset.gram_device(z_local[:n_local], bufs[j][:rows[j]], n_selected, outs[j])
+    return outs
+
+
+def refset_sweep(counts_local, n_total, bin_length=None, n_bins_reduced=0, dist=None, device=None, backend=None, fused=None, blocks=None):
     """Sharded leave-one-out correlation sweep.  counts_local: int32[n_local, n_bins] — this rank's samples
     (contiguous blocks as shard_range deals them); n_total: samples over all ranks.
     Returns (selected bins, float64[n_local, n_total] correlations of this rank's samples against every sample).
@@ -120,7 +141,8 @@ def refset_sweep(counts_local, n_total, bin_length=None, n_bins_reduced=0, dist=
     fused=None picks it when a rank forms at most 256 rows AND there are at most 4 ranks (two row tiles: every remote tile
     then crosses NVLink at most twice; measured: 2 GPUs 2.6 vs 2.9 ms at 256 rows per rank and 35 vs 33 ms at 1,000; 4 GPUs
     5.2 vs 5.4 ms at 250 rows; 8 GPUs 11.7 vs 11.3 ms at 250 rows — with seven peers the remote reads of the Gram kernel
-    cost more than NCCL's all-gather, profiles/r2f_bench_refset_n8*.json)."""
+    cost more than NCCL's all-gather, profiles/r2f_bench_refset_n8*.json).  blocks=True (default beyond two ranks when not
+    fused): the exchange as one broadcast per block, overlapped with the Gram kernel block by block (exchange_and_gram)."""
     from . import refset
     multi = dist is not None and dist.is_initialized() and dist.get_world_size() > 1
     world = dist.get_world_size() if multi else 1
@@ -135,7 +157,9 @@ def refset_sweep(counts_local, n_total, bin_length=None, n_bins_reduced=0, dist=
     sel = refset.select_bins(total.cpu().numpy(), bin_length, n_bins_reduced)
     per = -(-n_total // world)                              # every rank contributes a block of `per` rows (zero padded)
     if fused is None:
-        fused = per <= 256 and world <= 4
+        fused = per <= 256 and world <= 4 and not blocks
+    if blocks is None:
+        blocks = not fused and world > 2                    # (two ranks: one remote block, nothing to overlap it with but the local one)
     if fused and multi and backend is None:
         c_t = torch.from_numpy(counts_local).to(dev)
         sel_t = torch.from_numpy(sel).to(dev)
@@ -168,6 +192,14 @@ def refset_sweep(counts_local, n_total, bin_length=None, n_bins_reduced=0, dist=
         z_local = torch.zeros((per, z.shape[1] if n_local else backend.kpad(sel.size)), dtype=torch.float64, device=dev)
         if n_local:
             z_local[:n_local] = torch.from_numpy(z).to(dev)
+    if multi and backend is None and blocks:
+        # block by block: every rank's block is broadcast in turn (NCCL, asynchronous) and this rank's rows are contracted
+        # with block j while block j + 1 is still crossing NVLink — the all-gather no longer stands in front of the Gram
+        # kernel.  Same bits as the other forms: an entry's K-slices do not depend on how the columns are grouped.
+        out_blocks = exchange_and_gram(z_local, n_local, per, n_total, sel.size, dist, dev)
+        out = torch.cat(out_blocks, dim=1) if n_local else torch.empty((0, n_total), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        return sel, out.cpu().numpy()
     if multi:
         z_all = torch.empty((world * per, z_local.shape[1]), dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(z_all, z_local)

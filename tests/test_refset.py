@@ -217,9 +217,13 @@ def _gpu_worker(rank, world, port_no, n_total, nccl, q):
     bl = (d["end"] - d["start"] + 1).astype(float)
     lo, hi = shard.shard_range(n_total, rank, world)
     out = {}
-    for fused in ((True, False) if nccl else (True,)):        # the all-gather form needs NCCL (one GPU per rank)
-        sel, cor = shard.refset_sweep(counts[lo:hi], n_total, bl, 0, dist, device=dev if nccl or fused else None, fused=fused)
-        out[fused] = cor
+    # the all-gather form and the block-wise broadcasts need NCCL (one GPU per rank)
+    forms = dict(fused=dict(fused=True))
+    if nccl:
+        forms.update(all_gather=dict(fused=False, blocks=False), blocks=dict(fused=False, blocks=True))
+    for name, kw in forms.items():
+        sel, cor = shard.refset_sweep(counts[lo:hi], n_total, bl, 0, dist, device=dev, **kw)
+        out[name] = cor
     blocks = [None] * world
     dist.all_gather_object(blocks, (lo, out))
     if rank == 0:
@@ -231,7 +235,8 @@ def _gpu_worker(rank, world, port_no, n_total, nccl, q):
 @pytest.mark.gpu
 def test_cuda_sharded_sweep_two_ranks_fused_exchange():
     """The multi-GPU form of the sweep inside `pytest -m gpu`: two processes, every rank standardises its block, the Gram
-    kernel reads the other rank's rows through CUDA IPC (no all-gather pass); with two GPUs also the NCCL all-gather form.
+    kernel reads the other rank's rows through CUDA IPC (no all-gather pass); with two GPUs also the NCCL all-gather form
+    and the block-wise broadcasts overlapped with the Gram kernel.
     Either way the assembled matrix equals the single-process matrix bit for bit (K-slices depend on K only)."""
     import torch
     import torch.multiprocessing as mp
