@@ -174,6 +174,7 @@ int check_kernel(const char* what)
 
 void release_refset_scratch();
 void release_fit_scratch();
+void release_hmm_cache();
 
 // scratch used by the single-call (reference-shaped) entry points
 struct CallScratch {
@@ -209,18 +210,6 @@ int make_ll_map(const double* ll, int64_t rows, int64_t cols, int64_t pitch, int
     return 0;
 }
 
-// build and upload the sweep schedule (host_tables.cpp: viterbi_schedule)
-int upload_schedule(const std::vector<int32_t>& nobs, int groups, int n_ctas, int warps_per_cta, DevBuf& d_begin, DevBuf& d_items, cudaStream_t st)
-{
-    std::vector<int32_t> begin, items;
-    edb::viterbi_schedule(nobs.data(), (int)nobs.size(), groups, n_ctas, warps_per_cta, begin, items);
-    if (int rc = ensure(d_begin, begin.size() * 4)) return rc;
-    if (int rc = ensure(d_items, items.size() * 4 + 8)) return rc;
-    CU(cudaMemcpyAsync(d_begin.p, begin.data(), begin.size() * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_items.p, items.data(), items.size() * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));          // the vectors go out of scope
-    return 0;
-}
 
 }  // namespace
 
@@ -357,6 +346,7 @@ void edb200_shutdown(void)
     DevBuf* all[] = {&cs.phi, &cs.expected, &cs.total, &cs.observed, &cs.odds, &cs.ll, &cs.consts, &cs.lt,
                      &cs.chains, &cs.bp, &cs.path, &cs.ccalls, &cs.cncalls, &cs.calls, &cs.ncalls, &cs.sched_begin, &cs.sched_items};
     for (DevBuf* b : all) release(*b);
+    release_hmm_cache();
     release_refset_scratch();            // also releases the fit scratch
     if (g.d_flags) cudaFree(g.d_flags);
     g.d_flags = nullptr;
@@ -685,99 +675,6 @@ int edb200_get_loglike_matrix(const double* phi, const double* expected, const i
     return edb200_emission(phi, expected, total, observed, n, 3, odds, ll_out);
 }
 
-int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const double* probabilities,
-               const int32_t* positions, double expected_length, int32_t* path_out, int32_t* calls_out,
-               int32_t call_cap, int32_t* ncalls_out)
-{
-    if (int rc = need_ctx()) return rc;
-    if (nstates < 2 || nstates > EDB200_MAX_STATES) return fail(EDB200_ERR_NSTATES, "nstates=%d not in [2,%d]", nstates, EDB200_MAX_STATES);
-    if (nobs < 1 || !transitions || !probabilities || !positions || !path_out || !ncalls_out || call_cap < 0 || (call_cap && !calls_out))
-        return fail(EDB200_ERR_ARG, "bad argument");
-    std::lock_guard<std::mutex> lk(g_mu);
-    cudaStream_t st = g.stream;
-    const int S = nstates;
-    const int cap = call_cap > 0 ? call_cap : 1;
-
-    const int pitch = edb::viterbi_lt_pitch(S);
-    std::vector<double> lt(((size_t)nobs + edb::viterbi_tile()) * pitch, 0.0);
-    edb::build_log_transition_rows(S, transitions, positions, nobs, expected_length, lt.data(), pitch);
-    edb::ChainDesc cd{};
-    cd.lt_row0 = 0;
-    cd.em_off = 0;
-    cd.out_off = 0;
-    cd.nobs = nobs;
-    cd.n_em = nobs - 1;
-    cd.out_first = 0;
-    cd.out_last = nobs - 1;
-    cd.call_shift = 0;
-    const int n_tiles = edb::viterbi_chain_tiles(cd);
-    const int32_t tile_base0 = 0;
-    const int64_t nobs_p = ((int64_t)nobs + 15) & ~(int64_t)15;     // emission rows padded to whole 128-byte lines
-
-    if (int rc = ensure(cs.lt, lt.size() * 8)) return rc;
-    if (int rc = ensure(cs.chains, sizeof cd + 16)) return rc;
-    if (int rc = ensure(cs.ll, (size_t)nobs_p * S * 8)) return rc;
-    if (int rc = ensure(cs.bp, (size_t)(n_tiles + 1) * edb::viterbi_record_bytes())) return rc;
-    if (int rc = ensure(cs.path, (size_t)nobs)) return rc;
-    if (int rc = ensure(cs.ccalls, (size_t)cap * 16)) return rc;
-    if (int rc = ensure(cs.cncalls, 4)) return rc;
-    if (int rc = ensure(cs.calls, (size_t)cap * 16)) return rc;
-    if (int rc = ensure(cs.ncalls, 4)) return rc;
-    edb::nan_to_neg_inf(lt.data(), lt.size());     // device copy only: a NaN term is "never selected", like -Inf (hmm.cpp:81)
-    CU(cudaMemcpyAsync(cs.lt.p, lt.data(), lt.size() * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(cs.chains.p, &cd, sizeof cd, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync((char*)cs.chains.p + sizeof cd, &tile_base0, 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpy2DAsync(cs.ll.p, nobs_p * 8, probabilities, (size_t)nobs * 8, (size_t)nobs * 8, S, cudaMemcpyHostToDevice, st));
-
-    edb::ViterbiArgs a{};
-    a.chains = (const edb::ChainDesc*)cs.chains.p;
-    a.n_chains = 1;
-    a.n_samples = 1;
-    a.n_states = S;
-    a.ll = (const double*)cs.ll.p;
-    a.ll_sample_stride = 0;
-    a.ll_state_stride = nobs_p;
-    alignas(64) CUtensorMap ll_map;
-    if (int rc = make_ll_map(a.ll, S, nobs_p, nobs_p, (32 / S) * S, &ll_map)) return rc;
-    a.ll_map = &ll_map;
-    for (int j = 0; j < S; j++) a.perm[j] = j;
-    if (int rc = upload_schedule(std::vector<int32_t>{nobs}, 1, 1, 4, cs.sched_begin, cs.sched_items, st)) return rc;
-    a.groups = 1;
-    a.warps_per_cta = 4;
-    a.n_slots = 4;
-    a.sched_begin = (const int32_t*)cs.sched_begin.p;
-    a.sched_items = (const int32_t*)cs.sched_items.p;
-    a.lt = (const double*)cs.lt.p;
-    a.bp = (uint32_t*)cs.bp.p;
-    a.bp_tile_base = (const int32_t*)((char*)cs.chains.p + sizeof cd);
-    a.tail_other = -100.0;
-    a.path = (int8_t*)cs.path.p;
-    a.path_stride = nobs;
-    a.chain_calls = (int32_t*)cs.ccalls.p;
-    a.chain_ncalls = (int32_t*)cs.cncalls.p;
-    a.chain_call_cap = cap;
-    a.calls = (int32_t*)cs.calls.p;
-    a.ncalls = (int32_t*)cs.ncalls.p;
-    a.call_cap = cap;
-    a.flags = g.d_flags;
-    a.chain_list = nullptr;
-    a.n_list = 1;
-    a.max_list_tiles = n_tiles;
-    g_launches += edb::launch_viterbi(a, st);
-    g_launches += edb::launch_viterbi_compact(a, st);
-    if (int rc = check_kernel("viterbi")) return rc;
-
-    std::vector<int8_t> p8(nobs);
-    int32_t nc = 0;
-    CU(cudaMemcpyAsync(p8.data(), cs.path.p, nobs, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&nc, cs.ncalls.p, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    for (int i = 0; i < nobs; i++) path_out[i] = p8[i];
-    *ncalls_out = nc;
-    const int have = nc < call_cap ? nc : call_cap;
-    if (have > 0) CU(cudaMemcpy(calls_out, cs.calls.p, (size_t)have * 16, cudaMemcpyDeviceToHost));
-    return nc > call_cap ? EDB200_WARN_CALLCAP : 0;
-}
 
 // ------------------------------------------------------------------------------------------------ cohort
 int edb200_cohort_create(const edb200_cohort_spec* sp, edb200_cohort** out)
@@ -870,10 +767,15 @@ int edb200_cohort_create(const edb200_cohort_spec* sp, edb200_cohort** out)
     return 0;
 }
 
+static void destroy_cohort_locked(edb200_cohort* c);
 void edb200_cohort_destroy(edb200_cohort* c)
 {
     if (!c) return;
     std::lock_guard<std::mutex> lk(g_mu);
+    destroy_cohort_locked(c);
+}
+static void destroy_cohort_locked(edb200_cohort* c)
+{
     cudaDeviceSynchronize();
     for (edb200_graph* gr : c->graphs) {
         if (gr->exec) cudaGraphExecDestroy(gr->exec);
@@ -1534,6 +1436,135 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
     if (what & 4)
         if (int rc = call_summary(c, b, true, true, st)) return rc;
     return 0;
+}
+
+// ---- C_hmm-shaped entry point ------------------------------------------------------------------------------------
+// R calls C_hmm once per sample and chromosome with the SAME positions, transition matrix and expected length for every
+// sample of a run (R/class_definition.R:354-369).  The host-libm log-transition table of a (positions, T, L) triple, its
+// structured view and everything sized by the chain live in a one-chain cohort that is kept — most recently used first, 64
+// of them — so a repeat costs an emission upload, the kernels and a path download; and the call goes through the cohort's
+// own Viterbi pass: for the CallCNVs matrix and a genome-scale chromosome that is the segmented sweep (section 4.2b of
+// DESIGN.md), ~0.1 ms instead of 19,803 dependent steps (1.5 ms) for chromosome 1.
+}  // extern "C"
+namespace {
+struct HmmEntry {
+    int S = 0, nobs = 0;
+    double L = 0;
+    std::vector<double> T;
+    std::vector<int32_t> pos;
+    edb200_cohort* co = nullptr;
+};
+std::vector<HmmEntry> g_hmm_cache;           // most recently used first
+constexpr size_t kHmmCacheCap = 64;
+
+int hmm_entry(int S, int nobs, const double* T, const int32_t* pos, double L, edb200_cohort** out)
+{
+    for (size_t i = 0; i < g_hmm_cache.size(); i++) {
+        HmmEntry& e = g_hmm_cache[i];
+        if (e.S == S && e.nobs == nobs && e.L == L && memcmp(e.T.data(), T, (size_t)S * S * 8) == 0 && memcmp(e.pos.data(), pos, (size_t)nobs * 4) == 0) {
+            if (i) std::rotate(g_hmm_cache.begin(), g_hmm_cache.begin() + i, g_hmm_cache.begin() + i + 1);
+            *out = g_hmm_cache[0].co;
+            return 0;
+        }
+    }
+    edb200_cohort* c = new edb200_cohort();
+    auto bail = [&](int rc) {
+        destroy_cohort_locked(c);
+        return rc;
+    };
+    c->n_bins = nobs;                                        // (the path row: one byte per observation)
+    c->n_chains = 1;
+    c->S = S;
+    c->L = L;
+    memcpy(c->T, T, (size_t)S * S * 8);
+    for (int j = 0; j < S; j++) c->perm[j] = j;              // C_hmm's columns are the HMM's states as they are
+    edb::ChainDesc cd{};
+    cd.nobs = nobs;
+    cd.n_em = nobs - 1;
+    cd.out_first = 0;
+    cd.out_last = nobs - 1;
+    c->chains_h.assign(1, cd);
+    c->total_rows = nobs;
+    c->total_tiles = edb::viterbi_chain_tiles(cd);
+    const int pitch = edb::viterbi_lt_pitch(S);
+    c->lt_pitch = pitch;
+    const size_t n_rows = (size_t)nobs + edb::viterbi_tile();
+    std::vector<double> lt(n_rows * pitch, 0.0);
+    edb::build_log_transition_rows(S, T, pos, nobs, L, lt.data(), pitch);
+    edb::nan_to_neg_inf(lt.data(), lt.size());               // device copy only: a NaN term is "never selected", like -Inf (hmm.cpp:81)
+    const int32_t tile_base0 = 0;
+    if (int rc = ensure(c->lt, lt.size() * 8)) return bail(rc);
+    if (int rc = ensure(c->chains, sizeof cd)) return bail(rc);
+    if (int rc = ensure(c->tile_base, 4)) return bail(rc);
+    if (cudaMemcpy(c->lt.p, lt.data(), lt.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(c->chains.p, &cd, sizeof cd, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->tile_base.p, &tile_base0, 4, cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail(fail(EDB200_ERR_CUDA, "edb200_hmm: uploading the log-transition table failed"));
+    if (int rc = ensure_struct(c)) return bail(rc);          // structured rows when the matrix has the CallCNVs form (else the general sweep)
+    if (g_hmm_cache.size() >= kHmmCacheCap) {
+        destroy_cohort_locked(g_hmm_cache.back().co);
+        g_hmm_cache.pop_back();
+    }
+    HmmEntry e;
+    e.S = S, e.nobs = nobs, e.L = L, e.co = c;
+    e.T.assign(T, T + (size_t)S * S);
+    e.pos.assign(pos, pos + nobs);
+    g_hmm_cache.insert(g_hmm_cache.begin(), std::move(e));
+    *out = c;
+    return 0;
+}
+void release_hmm_cache()
+{
+    for (HmmEntry& e : g_hmm_cache) destroy_cohort_locked(e.co);
+    g_hmm_cache.clear();
+}
+}  // namespace
+extern "C" {
+
+int edb200_hmm(int32_t nstates, int32_t nobs, const double* transitions, const double* probabilities,
+               const int32_t* positions, double expected_length, int32_t* path_out, int32_t* calls_out,
+               int32_t call_cap, int32_t* ncalls_out)
+{
+    if (int rc = need_ctx()) return rc;
+    if (nstates < 2 || nstates > EDB200_MAX_STATES) return fail(EDB200_ERR_NSTATES, "nstates=%d not in [2,%d]", nstates, EDB200_MAX_STATES);
+    if (nobs < 1 || !transitions || !probabilities || !positions || !path_out || !ncalls_out || call_cap < 0 || (call_cap && !calls_out))
+        return fail(EDB200_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaStream_t st = g.stream;
+    const int S = nstates;
+    const int cap = call_cap > 0 ? call_cap : 1;
+    edb200_cohort* co = nullptr;
+    if (int rc = hmm_entry(S, nobs, transitions, positions, expected_length, &co)) return rc;
+    const int64_t nobs_p = ((int64_t)nobs + 15) & ~(int64_t)15;     // emission rows padded to whole 128-byte lines
+    if (int rc = ensure(cs.ll, (size_t)nobs_p * S * 8)) return rc;
+    if (int rc = ensure(cs.path, (size_t)nobs_p)) return rc;
+    if (int rc = ensure(cs.calls, (size_t)cap * 16)) return rc;
+    if (int rc = ensure(cs.ncalls, 4)) return rc;
+    CU(cudaMemcpy2DAsync(cs.ll.p, nobs_p * 8, probabilities, (size_t)nobs * 8, (size_t)nobs * 8, S, cudaMemcpyHostToDevice, st));
+    edb200_batch b{};
+    b.n_samples = 1;
+    // (the Viterbi pass reads the likelihood rows only; the count / fit slots of the batch are not touched)
+    b.observed = b.reference = (const int32_t*)cs.ll.p;
+    b.phi = b.expected = (const double*)cs.ll.p;
+    b.obs_stride = nobs;
+    b.ll = (double*)cs.ll.p;
+    b.ll_stride = nobs_p;
+    b.path = (int8_t*)cs.path.p;
+    b.path_stride = nobs_p;
+    b.calls = (int32_t*)cs.calls.p;
+    b.ncalls = (int32_t*)cs.ncalls.p;
+    b.call_cap = cap;
+    if (int rc = edb200_cohort_run_device(co, &b, 2, EDB200_EMISSION_AUTO, st)) return rc;
+
+    std::vector<int8_t> p8(nobs);
+    int32_t nc = 0;
+    CU(cudaMemcpyAsync(p8.data(), cs.path.p, nobs, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&nc, cs.ncalls.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < nobs; i++) path_out[i] = p8[i];
+    *ncalls_out = nc;
+    const int have = nc < call_cap ? nc : call_cap;
+    if (have > 0) CU(cudaMemcpy(calls_out, cs.calls.p, (size_t)have * 16, cudaMemcpyDeviceToHost));
+    return nc > call_cap ? EDB200_WARN_CALLCAP : 0;
 }
 
 // ---- CUDA-graph replay of a device-resident batch (small panels: the step is bound by its ~10 launches) ----
