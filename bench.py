@@ -139,6 +139,13 @@ def reference_arm(a, rank):
             vals.append(v)
             per_core.append(pc)
     value = float(np.mean(vals))
+    # the like-for-like denominator of the 5-state GPU arm: the C restatement (oracle port) at 5 states on the same cores —
+    # the compiled reference cannot run it (src/hmm.cpp:37-40)
+    port5 = None
+    if kind == "reference" and not a.no_aux:
+        v5, pc5, _ = cpu_throughput("port", N_STATES, per_step, cores)
+        port5 = dict(value=v5, unit=UNIT, cores=cores, per_core=pc5, kind="port", states=N_STATES,
+                     note="oracle port (plain-C restatement, bit-identical to the compiled reference at 3 states) at the GPU arm's 5 states")
     sample = (f"{per_step} samples x {N_BINS} bins per step, {states} states, one sample per worker process, "
               f"get_loglike_matrix + per-chromosome C_hmm with CallCNVs framing")
     out = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
@@ -151,7 +158,7 @@ def reference_arm(a, rank):
                                  if kind == "reference" else "compiled reference unavailable: oracle port at 5 states")),
                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=kind, sample=sample,
                                  per_core=float(np.mean(per_core))),
-               e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+               e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), port_5_states=port5)
     emit(out)
 
 
