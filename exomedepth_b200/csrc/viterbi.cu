@@ -367,6 +367,12 @@ viterbi_tilemap_kernel(ViterbiArgs a)
     }
     if (q >= 0) {                                           // all end states share one walk from here
         unsigned st1 = cur & 0xFu;
+        // the usual case away from CNV regions: the walk has reached state 0 and state 0's own back-pointers are 0 for the
+        // rest of the tile — it stays there (the 15 remaining steps were 3/4 of this kernel's instructions)
+        if (st1 == 0u) {
+            const unsigned long long w0 = ((unsigned long long)w[0].y << 32) | w[0].x;
+            if ((w0 & (q >= 15 ? ~0ull : (1ull << (4 * (q + 1))) - 1ull)) == 0ull) q = -1;
+        }
         for (; q >= 0; q--) {
             uint2 ws = w[0];
 #pragma unroll
@@ -381,7 +387,7 @@ viterbi_tilemap_kernel(ViterbiArgs a)
 
 // =========================================================================================== trace
 // One warp per chain: e = state at the tile's last observation; the chain ends in state 0 (hmm.cpp:96).
-// The lanes fetch 32 map words at a time (the next 32 are already in flight), the walk itself passes
+// The lanes fetch 128 map words at a time (the next 128 are already in flight), the walk itself passes
 // through them with one shuffle per tile, and every word is replaced by its e.
 __global__ void __launch_bounds__(128)
 viterbi_trace_kernel(ViterbiArgs a, int G)
@@ -397,21 +403,48 @@ viterbi_trace_kernel(ViterbiArgs a, int G)
     const ChainDesc cd = a.chains[chain];
     const int n_tiles = chain_tiles(cd);
     unsigned* __restrict__ tmap = reinterpret_cast<unsigned*>(a.bp) + record_base(a, chain, grp, n_tiles) * kRecU32 + kMapOff + gg;
+    // 128 tiles per trip: lane l holds the maps of tiles top - 4l .. top - 4l - 3.  One trip costs a round trip to memory
+    // (load the maps, store the states), and chromosome 1's 1,238 tiles took 39 of them with 32 tiles per trip: the latency
+    // of the longest chain was the kernel's duration.
+    constexpr int K = 4;
     unsigned e = 0;
-    int top = n_tiles - 1;                                  // lane l holds tile top - l
-    unsigned nxt = top - lane >= 0 ? tmap[(int64_t)(top - lane) * kRecU32] : 0u;
-    while (top >= 0) {
-        const unsigned w = nxt;
-        if (top - 32 - lane >= 0) nxt = tmap[(int64_t)(top - 32 - lane) * kRecU32];
-        unsigned mine = 0;
-        const int n = top + 1 < 32 ? top + 1 : 32;
-        for (int l = 0; l < n; l++) {                       // warp-uniform
-            const unsigned wl = __shfl_sync(kFull, w, l);
-            if (lane == l) mine = e;
-            e = (wl >> (4 * e)) & 0xFu;
+    int top = n_tiles - 1;
+    auto fetch = [&](int first, unsigned* w) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int t = first - (lane * K + k);
+            w[k] = t >= 0 ? tmap[(int64_t)t * kRecU32] : 0u;
         }
-        if (lane < n) tmap[(int64_t)(top - lane) * kRecU32] = mine;
-        top -= 32;
+    };
+    unsigned nxt[K];
+    fetch(top, nxt);
+    while (top >= 0) {
+        unsigned w[K], mine[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            w[k] = nxt[k];
+            mine[k] = 0u;
+        }
+        if (top - 32 * K >= 0) fetch(top - 32 * K, nxt);
+        const int n = top + 1 < 32 * K ? top + 1 : 32 * K;
+        if (__all_sync(kFull, (w[0] | w[1] | w[2] | w[3]) == 0u)) {        // the usual case: every end state of these tiles came from state 0
+            if (lane == 0) mine[0] = e;
+            e = 0u;
+        } else
+            for (int l = 0; l * K < n; l++) {               // warp-uniform
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const unsigned wl = __shfl_sync(kFull, w[k], l);
+                    if (l * K + k < n) {
+                        if (lane == l) mine[k] = e;
+                        e = (wl >> (4 * e)) & 0xFu;
+                    }
+                }
+            }
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            if (lane * K + k < n) tmap[(int64_t)(top - (lane * K + k)) * kRecU32] = mine[k];
+        top -= 32 * K;
     }
 }
 
@@ -452,10 +485,16 @@ viterbi_expand_kernel(ViterbiArgs a)
         if (have) {
             st = tmap[(int64_t)t * kRecU32 + gg] & 0xFu;
             uint2 w[S];
+            w[0] = bp[(int64_t)t * kRecU2 + gg * S];
+            // the usual case: the tile ends in state 0 and state 0's back-pointers are 0 throughout — sixteen zeros, no change
+            // (and the other states' back-pointers are not even read)
+            const bool quiet = st == 0u && (w[0].x | w[0].y) == 0u;
+            if (!quiet) {
 #pragma unroll
-            for (int s = 0; s < S; s++) w[s] = bp[(int64_t)t * kRecU2 + gg * S + s];
+                for (int s = 1; s < S; s++) w[s] = bp[(int64_t)t * kRecU2 + gg * S + s];
+            }
 #pragma unroll
-            for (int q = kTile - 1; q >= 0; q--) {
+            for (int q = kTile - 1; q >= 0 && !quiet; q--) {
                 pw[q >> 2] |= st << (8 * (q & 3));
                 unsigned word = q < 8 ? w[0].x : w[0].y;
 #pragma unroll
