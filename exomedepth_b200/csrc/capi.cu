@@ -42,6 +42,7 @@ struct Context {
     cudaStream_t s_copy = nullptr, s_em = nullptr, s_vit[kMaxParts] = {};
     cudaEvent_t ev_fork = nullptr, ev_copy[kMaxParts] = {}, ev_em[kMaxParts] = {}, ev_vit[kMaxParts] = {}, ev_setup = nullptr;
     int* d_queue = nullptr;              // work-item counter of the emission lattice kernel
+    DevBuf cold_spill;                   // lattice kernel: parking list of out-of-lattice bins beyond the shared-memory list (per CTA)
     unsigned* d_flags = nullptr;         // sticky device warning word
     unsigned* d_gsl_count = nullptr;     // per-cell GSL error log of the `.Call`-shaped emission (kernels.cuh: GslEventLog)
     uint4* d_gsl_events = nullptr;
@@ -277,7 +278,7 @@ struct edb200_cohort {
     std::map<std::pair<int, int>, Part> seg_parts;
     std::vector<std::pair<Part*, int>> seg_used;       // (group, samples) of the segmented passes since the last top-level call
     // per-batch scratch
-    DevBuf consts, bp, ccalls, cncalls, fw_grid, fw_chain, fw_out, fw_best, lattices;
+    DevBuf consts, bp, ccalls, cncalls, fw_grid, fw_chain, fw_out, fw_best, lattices, cold_spill;
     std::vector<edb200_graph*> graphs;   // captured replays of this cohort (invalidated when the cohort goes)
     int last_host_samples = 0;           // samples whose likelihoods the last host-pointer run left in h_ll
     // host-mode staging
@@ -373,6 +374,7 @@ void edb200_shutdown(void)
             cudaEventDestroy(g.ev_vit[p]);
         }
         cudaFree(g.d_queue);
+        release(g.cold_spill);
     }
     g.s_em = nullptr;
     g.ready = false;
@@ -530,7 +532,8 @@ int run_emission_scalar(edb::CountsView cv, const double* d_phi, const double* d
         all.n = 1;
         all.b0[0] = 0;
         all.b1[0] = n_bins;
-        edb::launch_emission_table(cv, d_consts, n_samples, S, all, d, out, g.d_flags, g.d_queue, g.n_sms, nullptr, 0, st);
+        if (int rc = ensure(g.cold_spill, (size_t)edb::emission_table_max_ctas(g.n_sms) * n_bins * 4)) return rc;
+        edb::launch_emission_table(cv, d_consts, n_samples, S, all, d, out, g.d_flags, g.d_queue, g.n_sms, nullptr, 0, (int*)g.cold_spill.p, n_bins, st);
     } else {
         edb::launch_emission_direct(cv, d_consts, n_samples, S, n_bins, out, g.d_flags, st);
     }
@@ -797,7 +800,7 @@ static void destroy_cohort_locked(edb200_cohort* c)
                           &part.seg.seam_in, &part.seg.seam_out, &part.seg.seam_mag, &part.seg.close, &part.seg.flags})
             release(*b);
     }
-    DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->tile_base, &c->decay, &c->srows, &c->fw_grid, &c->fw_chain, &c->fw_out, &c->fw_best, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->lattices,
+    DevBuf* all[] = {&c->chains, &c->lt, &c->odds_d, &c->tile_base, &c->decay, &c->srows, &c->fw_grid, &c->fw_chain, &c->fw_out, &c->fw_best, &c->consts, &c->bp, &c->ccalls, &c->cncalls, &c->lattices, &c->cold_spill,
                      &c->h_obs, &c->h_ref, &c->h_phi, &c->h_exp, &c->h_ll, &c->h_path, &c->h_calls, &c->h_ncalls, &c->h_stats, &c->h_cor,
                      &c->h_obs16, &c->h_ovf_i, &c->h_ovf_v};
     for (DevBuf* b : all) release(*b);
@@ -1035,7 +1038,10 @@ static int emission_part(edb200_cohort* c, const edb200_batch* b, const edb::Bin
         if (lattice_mode)
             if (int rc = ensure(c->lattices, (size_t)ns * S * (kTableK + 2 * kTableRN) * 8)) return rc;
         edb::prof_mark(panel ? "emission_panel" : "emission", st);
-        edb::launch_emission_table(cv, consts, ns, S, rg, d, out, g.d_flags, g.d_queue, n_sms, (double*)c->lattices.p, lattice_mode, st);
+        int64_t span = 0;
+        for (int q = 0; q < rg.n; q++) span += rg.b1[q] - rg.b0[q];
+        if (int rc = ensure(c->cold_spill, (size_t)edb::emission_table_max_ctas(g.n_sms) * span * 4)) return rc;
+        edb::launch_emission_table(cv, consts, ns, S, rg, d, out, g.d_flags, g.d_queue, n_sms, (double*)c->lattices.p, lattice_mode, (int*)c->cold_spill.p, span, st);
     } else {
         if (!whole) return fail(EDB200_ERR_ARG, "internal: the in-register emission kernel covers whole rows only");
         edb::prof_mark("emission_direct", st);

@@ -190,32 +190,39 @@ size_t emission_table_smem_bytes(TableDims d)
 // Out-of-lattice cells (counts beyond the lattice, inconsistent counts) and whole pathological
 // (sample, state) items are evaluated here, outside the gather loop, so that loop carries no call
 // and stays within the 64 registers a 1024-thread CTA allows.
-__device__ __noinline__ void drain_cold(const StateConst* sc, const CountsView& c, int sample, const int* list, int n,
-                                        double* o, unsigned* flags)
+// The parking list is compacted — every lane of a draining warp has a cell — and never full: past the kColdCap entries in
+// shared memory it continues in the CTA's spill area in HBM, one int per bin of the launch at most.  (Evaluating the cells
+// in place, where a warp meets them, costs a full evaluation per warp and trip as soon as one lane in 32 is out of the
+// lattice: counts twice as deep as the lattices were sized for took 3.95 ms instead of 0.89.)
+// A parked cell usually has ONE count beyond its lattice (the test count of a deeply covered bin, or the total and the
+// other count together): the terms that are in the lattice are gathered, only the others are evaluated (the lattice
+// entries and gdiff are the same quantity, each to the last bit or two: DESIGN.md "emission_table").
+struct LatticeView {
+    const double *G1, *G2, *G3;
+    TableDims dims;
+};
+__device__ __forceinline__ double cold_cell(const StateConst* sc, const LatticeView& lv, int tot, int obs, unsigned& f)
+{
+    if (obs < 0 || tot < obs) return cell_loglik(*sc, tot, obs, f);          // inconsistent counts: the reference's own NaN / error path
+    double x, y, z;
+    data_args(sc->a1, sc->a2, tot, obs, x, y, z);
+    const int r = tot - obs;
+    const double t1 = obs < lv.dims.K ? lv.G1[obs] : gdiff(sc->g1, x);
+    const double t2 = r < lv.dims.R ? lv.G2[r] : gdiff(sc->g2, y);
+    const double t3 = tot < lv.dims.N ? lv.G3[tot] : gdiff(sc->g12, z);
+    return __dsub_rn(__dadd_rn(t1, t2), t3);
+}
+
+__device__ __noinline__ void drain_cold(const StateConst* sc, const CountsView& c, int sample, const LatticeView lv, const int* list,
+                                        const int* spill, int n, double* o, unsigned* flags)
 {
     unsigned f = 0;
     for (int q = threadIdx.x; q < n; q += blockDim.x) {
-        const int64_t b = list[q];
+        const int64_t b = q < kColdCap ? list[q] : __ldcg(spill + (q - kColdCap));      // (written by this CTA: read from L2)
         int tot, obs;
         load_counts(c, sample, b, tot, obs);
-        o[b] = cell_loglik(*sc, tot, obs, f);
+        o[b] = cold_cell(sc, lv, tot, obs, f);
     }
-    if (f) atomicOr(flags, f);
-}
-
-// more out-of-lattice cells than the parking list holds: walk the sample again and evaluate exactly those
-__device__ __noinline__ void rescan_cold(const StateConst* sc, const CountsView& c, int sample, const BinRanges& rg,
-                                         TableDims dims, double* o, unsigned* flags)
-{
-    unsigned f = 0;
-    for (int q = 0; q < rg.n; q++)
-        for (int64_t b = rg.b0[q] + threadIdx.x; b < rg.b1[q]; b += blockDim.x) {
-            int tot, obs;
-            load_counts(c, sample, b, tot, obs);
-            const int r = tot - obs;
-            if (!((unsigned)obs < (unsigned)dims.K && (unsigned)r < (unsigned)dims.R && (unsigned)tot < (unsigned)dims.N))
-                o[b] = cell_loglik(*sc, tot, obs, f);
-        }
     if (f) atomicOr(flags, f);
 }
 
@@ -247,7 +254,7 @@ template <bool kPanel, bool kWarpRows>
 __global__ void __launch_bounds__(kTableThreads, 1)
 emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n_states, int n_items,
                       const __grid_constant__ BinRanges rg, TableDims dims, LLView out, unsigned* __restrict__ flags,
-                      int* __restrict__ queue, double* __restrict__ lattices, int lattice_mode)
+                      int* __restrict__ queue, double* __restrict__ lattices, int lattice_mode, int* __restrict__ spill_all, int64_t spill_stride)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StateConst* scp = reinterpret_cast<StateConst*>(smem_raw);
@@ -257,6 +264,7 @@ emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n
     int* cold_n = reinterpret_cast<int*>(G3 + dims.N);
     int* next_item = cold_n + 1;
     int* cold = cold_n + 4;
+    int* __restrict__ spill = spill_all + (int64_t)blockIdx.x * spill_stride;
     // lattice reloads (lattice_mode 2) arrive as ONE bulk copy per item, completing on this barrier
     const uint32_t reload_bar = smem_u32(cold + kColdCap) + ((16u - (smem_u32(cold + kColdCap) & 15u)) & 15u);
     unsigned reload_phase = 0;
@@ -383,6 +391,7 @@ emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n
         auto park = [&](int64_t b) {
             const int q = atomicAdd(cold_n, 1);
             if (q < kColdCap) cold[q] = (int)b;
+            else spill[q - kColdCap] = (int)b;
         };
 
         for (int q = 0; q < rg.n; q++) {
@@ -481,14 +490,16 @@ emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n
         }
         __syncthreads();
         const int n_cold = *cold_n;
-        if (n_cold > kColdCap) rescan_cold(scp, c, sample, rg, dims, o, flags);     // lattice far too small for this sample
-        else if (n_cold > 0) drain_cold(scp, c, sample, cold, n_cold, o, flags);
+        const LatticeView lv{G1, G2, G3, dims};
+        if (n_cold > 0) drain_cold(scp, c, sample, lv, cold, spill, n_cold, o, flags);
     }
 }
 
+int emission_table_max_ctas(int n_sms) { return 2 * n_sms; }      // panels: two 512-thread CTAs per SM
+
 void launch_emission_table(CountsView c, const StateConst* consts, int n_samples, int n_states,
                            const BinRanges& rg, TableDims dims, LLView out, unsigned* flags, int* queue, int n_sms,
-                           double* lattices, int lattice_mode, cudaStream_t st)
+                           double* lattices, int lattice_mode, int* spill, int64_t spill_stride, cudaStream_t st)
 {
     const int n_items = n_samples * n_states;
     if (n_items == 0 || rg.n == 0) return;
@@ -509,13 +520,13 @@ void launch_emission_table(CountsView c, const StateConst* consts, int n_samples
         const int threads = two ? kTableThreads / 2 : kTableThreads;
         const int ctas = two ? 2 * n_sms : n_sms;
         emission_table_kernel<true, false><<<n_items < ctas ? n_items : ctas, threads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices,
-                                                                                          lattices ? lattice_mode : 0);
+                                                                                          lattices ? lattice_mode : 0, spill, spill_stride);
         return;
     }
     static PerDevice configured;
     if (configured.raise(smem)) cudaFuncSetAttribute(emission_table_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     // warp-row bin mapping (full-sector 128-bit stores): measured 0.967 -> 0.895 ms per launch at 256 x 200k x 5 (profiles/r2a_knob_ab.log)
-    emission_table_kernel<false, true><<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices, lattices ? lattice_mode : 0);
+    emission_table_kernel<false, true><<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices, lattices ? lattice_mode : 0, spill, spill_stride);
 }
 
 }  // namespace edb

@@ -90,7 +90,10 @@ size_t emission_table_smem_bytes(TableDims d);
 // lattice_mode 0 = build only, 1 = build and save, 2 = reload (the same items' later bin ranges).
 void launch_emission_table(CountsView c, const StateConst* consts, int n_samples, int n_states,
                            const BinRanges& ranges, TableDims dims, LLView out, unsigned* flags, int* queue, int n_sms,
-                           double* lattices, int lattice_mode, cudaStream_t st);
+                           double* lattices, int lattice_mode, int* spill, int64_t spill_stride, cudaStream_t st);
+// `spill`: parking list of out-of-lattice bins beyond the shared-memory list, emission_table_spill_ctas(...) * spill_stride ints,
+// spill_stride >= the bins the ranges cover
+int emission_table_max_ctas(int n_sms);
 
 // ---- Viterbi ------------------------------------------------------------------------------------
 // One chain template per chromosome; shared by every sample of the batch.

@@ -24,6 +24,9 @@ ap.add_argument("--seg", type=int, default=-1, help="segmented sweep: -1 auto, 0
 ap.add_argument("--seg-min", type=int, default=0)
 ap.add_argument("--seg-warm", type=int, default=0)
 ap.add_argument("--warps", type=int, default=0)
+ap.add_argument("--lattice", type=int, default=0)
+ap.add_argument("--ref-scale", type=float, default=1.0, help="scale the synthetic counts (test and reference) by this factor")
+ap.add_argument("--emission-only", action="store_true")
 ap.add_argument("--first", type=int, default=0, help="index of the first synthetic sample")
 a = ap.parse_args()
 
@@ -33,6 +36,9 @@ t0 = time.time()
 d = synth.cohort(min(a.gen, a.samples), n_bins=a.bins, first_sample=a.first)
 print("synth", time.time() - t0)
 reps = (a.samples + d["observed"].shape[0] - 1) // d["observed"].shape[0]
+if a.ref_scale != 1.0:
+    d["observed"] = (d["observed"] * a.ref_scale).astype(np.int32)
+    d["reference"] = (d["reference"] * a.ref_scale).astype(np.int32)
 obs = np.tile(d["observed"], (reps, 1))[:a.samples]
 phi = np.tile(d["phi"], reps)[:a.samples]
 exp = np.tile(d["expected"], reps)[:a.samples]
@@ -76,6 +82,9 @@ def timeit(fn, name, bytes_per_cell):
 B = 4 + 8 * S
 timeit(lambda: co.run_device(obs_t, ref_t, phi_t, exp_t, ll, path, calls, ncalls, what=1, mode=_lib.EMISSION_TABLE), "emission_table", B)
 ll_tab = ll.clone()
+print("ll checksum", float(ll.nan_to_num().sum()), "nan", int(ll.isnan().sum()))
+if a.emission_only:
+    sys.exit(0)
 if a.direct:
     timeit(lambda: co.run_device(obs_t, ref_t, phi_t, exp_t, ll, path, calls, ncalls, what=1, mode=_lib.EMISSION_DIRECT), "emission_direct", B)
     diff = (ll - ll_tab).abs()
