@@ -455,7 +455,10 @@ int edb200_status(int reset)
 namespace {
 
 constexpr int kHostChunks = 8;                     // sample chunks of the host-pointer cohort call (<= 16 events)
-constexpr int kTableK = 2048, kTableRN = 12288;   // lattice caps: (2048 + 2*12288) * 8 B = 208 KB of shared memory
+// lattice caps: (3072 + 2 * 11776) * 8 B = 208 KB of shared memory.  The split follows the counts: the test count is the
+// fraction e (0.08 .. 0.3, more inside a duplication) of the total, so K ~ N / 4 leaves the fewest cells outside — on the
+// synthetic cohort 0.01 % (0.08 % with 2048 + 2 * 12288), 0.5 % instead of 1.9 % at counts twice as deep
+constexpr int kTableK = 3072, kTableRN = 11776;
 
 // ---- per-cell GSL error log (src/error.c:35-52) -------------------------------------------------------------
 constexpr unsigned kGslLogCap = 1u << 16;

@@ -157,12 +157,22 @@ def test_cohort_callcnvs_columns_vs_oracle(edb, port, S):
     assert n_rows > 100
 
 
-def test_table_and_direct_paths_agree(edb):
+@pytest.mark.parametrize("n_bins,scale", [(20000, 1), (60000, 4)])
+def test_table_and_direct_paths_agree(edb, port, n_bins, scale):
+    """scale = 4: counts four times as deep as the lattices were sized for — a tenth of the cells are parked, more than the
+    shared-memory list holds (it continues in HBM), and evaluated with the terms their lattices hold gathered."""
     from exomedepth_b200 import _lib, synth
-    d = synth.cohort(5, n_bins=20000)
+    d = synth.cohort(5, n_bins=n_bins)
+    d["observed"], d["reference"] = d["observed"] * scale, d["reference"] * scale
     co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=5)
     a = co.run_host(d["observed"], d["reference"], d["phi"], d["expected"], want_path=False, mode=_lib.EMISSION_DIRECT)["ll"]
     b = co.run_host(d["observed"], d["reference"], d["phi"], d["expected"], want_path=False, mode=_lib.EMISSION_TABLE)["ll"]
+    if scale > 1:
+        out = (d["observed"] >= 3072) | (d["observed"] + d["reference"] >= 11776)
+        assert out.sum(axis=1).min() > 2048                             # every item spills past the shared-memory list
+        odds = port.state_odds(5)
+        for s in (0, 3):
+            assert_ll_close(b[s].T, port.emission(d["phi"][s], d["expected"][s], d["observed"][s] + d["reference"], d["observed"][s], odds))
     # the lattice entries come from a recurrence anchored on the in-register evaluation: same arguments, last-bit
     # differences in the entries, amplified by the cancellation in G1 + G2 - G3
     assert_ll_close(b, a, rtol=2e-11, atol=0)
@@ -173,8 +183,8 @@ def test_table_and_direct_paths_agree(edb):
 @pytest.mark.parametrize("n_bins,scale", [(9000, 1), (20000, 1), (9000, 12)])
 def test_panel_lattice_vs_oracle(edb, port, n_bins, scale):
     """The panel-sized lattices (2048 + 2 x 4096 entries below 16,384 bins, 2048 + 2 x 8192 from there) against the oracle,
-    cell by cell; scale = 12 multiplies the counts so that most cells leave the lattice (more than the parking list holds:
-    the kernel walks the sample again and evaluates exactly those cells in registers)."""
+    cell by cell; scale = 12 multiplies the counts so that most cells leave the lattice (more than the shared-memory parking list
+    holds: it continues in HBM)."""
     from exomedepth_b200 import _lib, synth
     d = synth.cohort(4, n_bins=n_bins)
     obs, ref = d["observed"] * scale, d["reference"] * scale
@@ -1070,7 +1080,7 @@ def test_per_bin_phi_and_expected_through_the_cohort_path(edb, port):
 def test_pipelined_groups_do_not_touch_each_others_bins(edb):
     """Regression: the chromosome groups of a host-pointer call run concurrently (upload | emission | sweeps), so a group's
     emission launch must write the bins of ITS chromosomes only.  With ranges rounded out to 16-bin tiles it rewrote the
-    first / last bins of the neighbouring chromosomes, and for out-of-lattice counts (>= 2048 reads) the lattice kernel's
+    first / last bins of the neighbouring chromosomes, and for out-of-lattice counts (>= 3072 reads) the lattice kernel's
     store of a clamped-gather value — corrected by its cold pass a moment later — was visible to the neighbour's running
     sweep: one extra call in one sample every few calls, only with pinned buffers (truly asynchronous copies).  Here the
     bins around every chromosome boundary carry such counts; 12 pipelined calls must all equal the single-pass result."""
@@ -1081,7 +1091,7 @@ def test_pipelined_groups_do_not_touch_each_others_bins(edb):
     rng = np.random.default_rng(4)
     for b in d["offsets"][1:-1]:
         for s in range(ns):
-            obs[s, b - 6:b + 6] = rng.integers(2100, 9000, 12)          # beyond the observed-count lattice (2047)
+            obs[s, b - 6:b + 6] = rng.integers(3100, 9000, 12)          # beyond the observed-count lattice (3071)
     phi, ex = np.tile(d["phi"], ns // 16), np.tile(d["expected"], ns // 16)
     hb = _lib.PinnedPool()
     obs_p = hb.empty(obs.shape, np.int32)
