@@ -94,81 +94,89 @@ call_summary_kernel(CallSummaryArgs a)
     }
 }
 
-// One CTA per sample: Pearson correlation of the test and the reference counts over all bins, two passes like R's
-// cor() (means first, then centred sums), every sum compensated.
+// One CTA per sample: Pearson correlation of the test and the reference counts over all bins (R/class_definition.R:338).
+// The counts are integers, so the five sums n, Sx, Sy, Sxx, Syy, Sxy are accumulated EXACTLY (64-bit sums of the counts,
+// 128-bit sums of their products) in ONE pass, and n*Sxy - Sx*Sy, n*Sxx - Sx^2, n*Syy - Sy^2 are exact 128-bit integers: the
+// only roundings are their conversion to double, two square roots, a product and a quotient (R's two-pass long-double
+// cor() agrees to the last bits).  The sums do not depend on the order of the terms.  (The two-pass compensated form this
+// replaces waited 2 x 98 times on a pair of loads per thread — 0.15-0.35 ms per 64-sample chunk on SMs the emission and
+// Viterbi kernels of the host pipeline were waiting for.)
+struct CorSums {
+    long long sx, sy;
+    __int128 sxx, syy, sxy;
+};
+__device__ __forceinline__ double i128_to_double(__int128 v)
+{
+    const bool neg = v < 0;
+    const unsigned __int128 u = neg ? (unsigned __int128)(-v) : (unsigned __int128)v;
+    const unsigned long long hi = (unsigned long long)(u >> 64), lo = (unsigned long long)u;
+    // hi * 2^64 is exact; the sum rounds once when hi < 2^53 (sums of products of 32-bit counts: hi < 2^40)
+    const double d = fma((double)hi, 18446744073709551616.0, (double)lo);
+    return neg ? -d : d;
+}
 __global__ void __launch_bounds__(512)
 count_cor_kernel(CountsView c, int n_samples, int64_t n_bins, double* __restrict__ cor)
 {
-    __shared__ double red[16][3][3];
-    __shared__ double mean[2];
+    __shared__ CorSums red[16];
     const int sample = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
     const int32_t* __restrict__ obs = c.observed + sample * c.obs_stride;
     const int32_t* __restrict__ oth = c.other + sample * c.other_stride;
-    // the CTA-wide total of up to three compensated sums, combined in warp order
-    auto cta_total = [&](Comp* v, int nv, double* out) {
-        for (int q = 0; q < nv; q++) {
-            Comp t = v[q];
-#pragma unroll
-            for (int d = 16; d; d >>= 1) {
-                const double s2 = __shfl_xor_sync(0xffffffffu, t.s, d), c2 = __shfl_xor_sync(0xffffffffu, t.c, d);
-                const double p2 = __shfl_xor_sync(0xffffffffu, t.plain, d);
-                Comp lo = t, hi{s2, c2, p2};
-                if (threadIdx.x & d) { lo = hi; hi = t; }
-                comp_merge(lo, hi.s, hi.c, hi.plain);
-                t = lo;
-            }
-            if (lane == 0) { red[warp][q][0] = t.s; red[warp][q][1] = t.c; red[warp][q][2] = t.plain; }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int q = 0; q < nv; q++) {
-                Comp t{0, 0, 0};
-                for (int w = 0; w < n_warps; w++) comp_merge(t, red[w][q][0], red[w][q][1], red[w][q][2]);
-                out[q] = __dadd_rn(t.s, t.c);
-            }
-        }
-        __syncthreads();
+    const int is_total = c.other_is_total;
+    CorSums v{0, 0, 0, 0, 0};
+    auto add = [&](int o, int r) {
+        const long long x = o, y = is_total ? (long long)r - o : (long long)r;
+        v.sx += x;
+        v.sy += y;
+        v.sxx += (__int128)(x * x);          // |x| <= 2^31: x * x fits 64 bits; y = total - test can reach 2^32 in magnitude,
+        v.syy += (__int128)y * y;            // so the products with y are formed in 128 bits
+        v.sxy += (__int128)x * y;
     };
-    // 128-bit loads, four bins per thread and trip (with one 4-byte load per trip the kernel is bound by the latency of
-    // 2 x 391 dependent trips: 0.2 ms for 64 samples x 200k bins, during which its CTAs keep the emission kernel of the next
-    // chunk off their SMs)
+    // 128-bit loads, four bins per thread and trip, two trips in flight
     const bool vec = ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(oth)) & 15) == 0;
     const int64_t n4 = vec ? n_bins & ~(int64_t)3 : 0;
-    auto each = [&](auto&& f) {
-        for (int64_t b = (int64_t)threadIdx.x * 4; b < n4; b += (int64_t)blockDim.x * 4) {
-            const int4 o = __ldg(reinterpret_cast<const int4*>(obs + b)), r = __ldg(reinterpret_cast<const int4*>(oth + b));
-            f(o.x, r.x);
-            f(o.y, r.y);
-            f(o.z, r.z);
-            f(o.w, r.w);
-        }
-        for (int64_t b = n4 + threadIdx.x; b < n_bins; b += blockDim.x) f(obs[b], oth[b]);
-    };
-    const int is_total = c.other_is_total;
-    Comp v[3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    each([&](int o, int r) {
-        comp_add(v[0], (double)o);
-        comp_add(v[1], is_total ? __dadd_rn((double)r, -(double)o) : (double)r);
-    });
-    __shared__ double tot[3];
-    cta_total(v, 2, tot);
-    if (threadIdx.x == 0) {
-        mean[0] = tot[0] / (double)n_bins;
-        mean[1] = tot[1] / (double)n_bins;
+    const int64_t stride = (int64_t)blockDim.x * 4;
+    int64_t b = (int64_t)threadIdx.x * 4;
+    for (; b + stride < n4; b += 2 * stride) {
+        const int4 o0 = __ldg(reinterpret_cast<const int4*>(obs + b)), r0 = __ldg(reinterpret_cast<const int4*>(oth + b));
+        const int4 o1 = __ldg(reinterpret_cast<const int4*>(obs + b + stride)), r1 = __ldg(reinterpret_cast<const int4*>(oth + b + stride));
+        add(o0.x, r0.x); add(o0.y, r0.y); add(o0.z, r0.z); add(o0.w, r0.w);
+        add(o1.x, r1.x); add(o1.y, r1.y); add(o1.z, r1.z); add(o1.w, r1.w);
     }
+    for (; b < n4; b += stride) {
+        const int4 o0 = __ldg(reinterpret_cast<const int4*>(obs + b)), r0 = __ldg(reinterpret_cast<const int4*>(oth + b));
+        add(o0.x, r0.x); add(o0.y, r0.y); add(o0.z, r0.z); add(o0.w, r0.w);
+    }
+    for (int64_t t = n4 + threadIdx.x; t < n_bins; t += blockDim.x) add(obs[t], oth[t]);
+    // CTA total: integer sums, any order
+    auto shfl128 = [&](__int128 x, int d) {
+        const unsigned long long lo = __shfl_xor_sync(0xffffffffu, (unsigned long long)x, d);
+        const unsigned long long hi = __shfl_xor_sync(0xffffffffu, (unsigned long long)((unsigned __int128)x >> 64), d);
+        return (__int128)(((unsigned __int128)hi << 64) | lo);
+    };
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        v.sx += __shfl_xor_sync(0xffffffffu, v.sx, d);
+        v.sy += __shfl_xor_sync(0xffffffffu, v.sy, d);
+        v.sxx += shfl128(v.sxx, d);
+        v.syy += shfl128(v.syy, d);
+        v.sxy += shfl128(v.sxy, d);
+    }
+    if (lane == 0) red[warp] = v;
     __syncthreads();
-    const double mx = mean[0], my = mean[1];
-    v[0] = v[1] = v[2] = Comp{0, 0, 0};
-    each([&](int o, int r) {
-        const double dx = __dadd_rn((double)o, -mx), dy = __dadd_rn(is_total ? __dadd_rn((double)r, -(double)o) : (double)r, -my);
-        comp_add(v[0], __dmul_rn(dx, dy));
-        comp_add(v[1], __dmul_rn(dx, dx));
-        comp_add(v[2], __dmul_rn(dy, dy));
-    });
-    cta_total(v, 3, tot);
     if (threadIdx.x == 0) {
-        double r = tot[0] / (sqrt(tot[1]) * sqrt(tot[2]));       // NaN for a constant vector, like R (with its warning)
+        CorSums t = red[0];
+        for (int w = 1; w < n_warps; w++) {
+            t.sx += red[w].sx;
+            t.sy += red[w].sy;
+            t.sxx += red[w].sxx;
+            t.syy += red[w].syy;
+            t.sxy += red[w].sxy;
+        }
+        const __int128 n = n_bins;
+        const double num = i128_to_double(n * t.sxy - (__int128)t.sx * t.sy);
+        const double dx = i128_to_double(n * t.sxx - (__int128)t.sx * t.sx), dy = i128_to_double(n * t.syy - (__int128)t.sy * t.sy);
+        double r = num / (sqrt(dx) * sqrt(dy));                    // NaN for a constant vector, like R (with its warning)
         if (r > 1.0) r = 1.0;
         if (r < -1.0) r = -1.0;
         cor[sample] = n_bins > 1 ? r : __longlong_as_double(0x7ff8000000000000ll);

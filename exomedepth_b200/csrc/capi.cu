@@ -40,6 +40,7 @@ struct Context {
     // chromosome-group pipeline: copy-in, emission and one Viterbi stream per group, forked from / joined to the caller's stream
     static constexpr int kMaxParts = 6;
     cudaStream_t s_copy = nullptr, s_em = nullptr, s_vit[kMaxParts] = {};
+    cudaStream_t s_widen = nullptr, s_cor = nullptr;      // sample-chunk pipeline: widening gates a chunk's emission (highest priority), cor(test, reference) is only needed at the end (lowest)
     cudaEvent_t ev_fork = nullptr, ev_copy[kMaxParts] = {}, ev_em[kMaxParts] = {}, ev_vit[kMaxParts] = {}, ev_setup = nullptr;
     int* d_queue = nullptr;              // work-item counter of the emission lattice kernel
     DevBuf cold_spill;                   // lattice kernel: parking list of out-of-lattice bins beyond the shared-memory list (per CTA)
@@ -333,6 +334,10 @@ int edb200_init(int device)
             CU(cudaEventCreateWithFlags(&g.ev_em[p], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&g.ev_vit[p], cudaEventDisableTiming));
         }
+        int prio_lo = 0, prio_hi = 0;                       // (numerically lower = served first)
+        CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CU(cudaStreamCreateWithPriority(&g.s_widen, cudaStreamNonBlocking, prio_hi));
+        CU(cudaStreamCreateWithPriority(&g.s_cor, cudaStreamNonBlocking, prio_lo));
         CU(cudaMalloc(&g.d_queue, sizeof(int)));
     }
     g.ready = true;
@@ -365,6 +370,8 @@ void edb200_shutdown(void)
     if (g.s_em) {
         cudaStreamDestroy(g.s_copy);
         cudaStreamDestroy(g.s_em);
+        cudaStreamDestroy(g.s_widen);
+        cudaStreamDestroy(g.s_cor);
         cudaEventDestroy(g.ev_fork);
         cudaEventDestroy(g.ev_setup);
         for (int p = 0; p < Context::kMaxParts; p++) {
@@ -1804,7 +1811,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         }
     }
     if (seg_k > 0) {
-        cudaStream_t sc = g.s_copy, sx = g.s_em, sv = g.s_vit[0], sw = g.s_vit[2];
+        cudaStream_t sc = g.s_copy, sx = g.s_em, sv = g.s_vit[0], sw = g.s_widen, sr = g.s_cor;
         if (shared_ref) CU(cudaMemcpyAsync(c->h_ref.p, b->reference, nb * 4, cudaMemcpyHostToDevice, sc));
         CU(cudaMemcpyAsync(c->h_phi.p, b->phi, ns * 8, cudaMemcpyHostToDevice, sc));
         CU(cudaMemcpyAsync(c->h_exp.p, b->expected, ns * 8, cudaMemcpyHostToDevice, sc));
@@ -1857,8 +1864,8 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
             // cor(test, reference) needs the counts only: on a stream of its own behind the chunk's upload (one CTA per sample:
             // 0.18 ms for 64 samples if it ran in line, and on the copy stream it would hold up the next upload)
             if (d.cor) {
-                CU(cudaStreamWaitEvent(g.s_vit[1], g.ev_copy[k], 0));
-                if ((rc = call_summary(c, &e, false, true, g.s_vit[1]))) return rc;
+                CU(cudaStreamWaitEvent(sr, g.ev_copy[k], 0));
+                if ((rc = call_summary(c, &e, false, true, sr))) return rc;
             }
             e.cor = nullptr;
             // two compute streams: the emission of chunk k+1 behind the emission of chunk k, the Viterbi of chunk k behind its
@@ -1885,7 +1892,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
                     CU(cudaMemcpy2DAsync(b->path + (size_t)s0 * b->path_stride, b->path_stride, e.path, nb, nb, cnt, cudaMemcpyDeviceToHost, g.stream2));
             }
         }
-        CU(cudaEventRecord(g.ev_setup, g.s_vit[1]));
+        CU(cudaEventRecord(g.ev_setup, sr));
         CU(cudaStreamWaitEvent(st, g.ev_setup, 0));
         CU(cudaStreamWaitEvent(st, g.ev_vit[seg_k - 1], 0));
     } else if (plan.size() > 1) {
