@@ -251,6 +251,8 @@ struct edb200_cohort {
     // segmented sweep (viterbi_seam.h); seg_ok: the transition terms are small enough for the error bound (ensure_struct)
     int seg_ok = 0;
     int seg_slot = 0;                    // which sample chunk of a host call is being processed (its pieces and flags are its own)
+    int vit_slots = 1, vit_slot = 0, vit_slot_samples = 0;     // (slots sized for vit_slot_samples, the largest chunk)
+    // sample-chunk pipeline: two sets of Viterbi scratch (back-pointers, per-chain call tables), chunk k uses set k & 1
     int emission_sms = 0;                // SMs the emission launch of the current chunk may take (0 = all)
     bool in_host_call = false;
     // the pieces of one chromosome group for `key` (samples, warps, warm-up, shortest piece), its scratch and flags
@@ -1108,9 +1110,13 @@ static int viterbi_prepare(edb200_cohort* c, const edb200_batch* b, edb::Viterbi
     const int ccap = b->call_cap;
     const int G = 32 / S;
     const int64_t groups = (ns + G - 1) / G;
-    if (int rc = ensure(c->bp, (size_t)groups * (c->total_tiles + 1) * edb::viterbi_record_bytes())) return rc;
-    if (int rc = ensure(c->ccalls, (size_t)ns * c->n_chains * ccap * 16)) return rc;
-    if (int rc = ensure(c->cncalls, (size_t)ns * c->n_chains * 4)) return rc;
+    // (slot sizes rounded up to 256 bytes; a later, smaller chunk of the same call fits the slots of the first)
+    const int slot_ns = std::max(ns, c->vit_slots > 1 ? c->vit_slot_samples : 0);
+    const size_t bp_bytes = ((size_t)((slot_ns + G - 1) / G) * (c->total_tiles + 1) * edb::viterbi_record_bytes() + 255) & ~(size_t)255;
+    const size_t cc_bytes = ((size_t)slot_ns * c->n_chains * ccap * 16 + 255) & ~(size_t)255, cn_bytes = ((size_t)slot_ns * c->n_chains * 4 + 255) & ~(size_t)255;
+    if (int rc = ensure(c->bp, c->vit_slots * bp_bytes)) return rc;
+    if (int rc = ensure(c->ccalls, c->vit_slots * cc_bytes)) return rc;
+    if (int rc = ensure(c->cncalls, c->vit_slots * cn_bytes)) return rc;
     a = edb::ViterbiArgs{};
     a.chains = (const edb::ChainDesc*)c->chains.p;
     a.n_chains = c->n_chains;
@@ -1132,13 +1138,13 @@ static int viterbi_prepare(edb200_cohort* c, const edb200_batch* b, edb::Viterbi
     for (int j = 0; j < S; j++) a.perm[j] = c->perm[j];
     a.groups = (int)groups;
     a.lt = (const double*)c->lt.p;
-    a.bp = (uint32_t*)c->bp.p;
+    a.bp = (uint32_t*)((char*)c->bp.p + c->vit_slot * bp_bytes);
     a.bp_tile_base = (const int32_t*)c->tile_base.p;
     a.tail_other = -100.0;                                 // R/class_definition.R:364
     a.path = b->path;
     a.path_stride = b->path_stride;
-    a.chain_calls = (int32_t*)c->ccalls.p;
-    a.chain_ncalls = (int32_t*)c->cncalls.p;
+    a.chain_calls = (int32_t*)((char*)c->ccalls.p + c->vit_slot * cc_bytes);
+    a.chain_ncalls = (int32_t*)((char*)c->cncalls.p + c->vit_slot * cn_bytes);
     a.chain_call_cap = ccap;
     a.calls = b->calls;
     a.ncalls = b->ncalls;
@@ -1733,7 +1739,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     struct HostCall {
         edb200_cohort* c;
         explicit HostCall(edb200_cohort* c_) : c(c_) { c->in_host_call = true; c->seg_used.clear(); }
-        ~HostCall() { c->in_host_call = false; c->seg_slot = 0; }
+        ~HostCall() { c->in_host_call = false; c->seg_slot = 0; c->vit_slots = 1; c->vit_slot = 0; c->vit_slot_samples = 0; }
     } host_call(c);
     cudaStream_t st = g.stream;
     const int S = c->S, ns = b->n_samples;
@@ -1811,7 +1817,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         }
     }
     if (seg_k > 0) {
-        cudaStream_t sc = g.s_copy, sx = g.s_em, sv = g.s_vit[0], sw = g.s_widen, sr = g.s_cor;
+        cudaStream_t sc = g.s_copy, sx = g.s_em, sw = g.s_widen, sr = g.s_cor;
         if (shared_ref) CU(cudaMemcpyAsync(c->h_ref.p, b->reference, nb * 4, cudaMemcpyHostToDevice, sc));
         CU(cudaMemcpyAsync(c->h_phi.p, b->phi, ns * 8, cudaMemcpyHostToDevice, sc));
         CU(cudaMemcpyAsync(c->h_exp.p, b->expected, ns * 8, cudaMemcpyHostToDevice, sc));
@@ -1880,6 +1886,12 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
             c->emission_sms = 0;
             if (rc) return rc;
             CU(cudaEventRecord(g.ev_em[k], sx));
+            // two Viterbi streams with a scratch set each: the sweep of chunk k fills the SMs while the small, latency-bound kernels
+            // behind the sweep of chunk k-1 (tile maps, trace, expand, check, repair, compaction, call sums) are still running
+            cudaStream_t sv = g.s_vit[k & 1];
+            c->vit_slots = 2;
+            c->vit_slot = k & 1;
+            c->vit_slot_samples = seg_per;
             CU(cudaStreamWaitEvent(sv, g.ev_em[k], 0));
             if ((rc = edb200_cohort_run_device(c, &e, 2 | (d.call_stats ? 4 : 0), emission_mode, sv))) return rc;
             CU(cudaEventRecord(g.ev_vit[k], sv));
@@ -1895,6 +1907,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         CU(cudaEventRecord(g.ev_setup, sr));
         CU(cudaStreamWaitEvent(st, g.ev_setup, 0));
         CU(cudaStreamWaitEvent(st, g.ev_vit[seg_k - 1], 0));
+        if (seg_k > 1) CU(cudaStreamWaitEvent(st, g.ev_vit[seg_k - 2], 0));
     } else if (plan.size() > 1) {
         // ---- chromosome-group pipeline over PCIe: the counts of the long chromosomes go up first; their emission and
         // sweep (the critical path) run while the other groups are still uploading; results drain per group.

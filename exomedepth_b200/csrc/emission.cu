@@ -226,12 +226,12 @@ __device__ __noinline__ void drain_cold(const StateConst* sc, const CountsView& 
     if (f) atomicOr(flags, f);
 }
 
-__device__ __noinline__ void whole_item_cold(const StateConst* sc, const CountsView& c, int sample, const BinRanges& rg,
-                                             double* o, unsigned* flags)
+__device__ __noinline__ void whole_item_cold(const StateConst* sc, const CountsView& c, int sample, const BinRanges& rg, int64_t sub_lo,
+                                             int64_t sub_hi, double* o, unsigned* flags)
 {
     unsigned f = 0;
     for (int q = 0; q < rg.n; q++)
-        for (int64_t b = rg.b0[q] + threadIdx.x; b < rg.b1[q]; b += blockDim.x) {
+        for (int64_t b = max(rg.b0[q], sub_lo) + threadIdx.x; b < min(rg.b1[q], sub_hi); b += blockDim.x) {
             int tot, obs;
             load_counts(c, sample, b, tot, obs);
             o[b] = cell_loglik(*sc, tot, obs, f);
@@ -254,7 +254,8 @@ template <bool kPanel, bool kWarpRows>
 __global__ void __launch_bounds__(kTableThreads, 1)
 emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n_states, int n_items,
                       const __grid_constant__ BinRanges rg, TableDims dims, LLView out, unsigned* __restrict__ flags,
-                      int* __restrict__ queue, double* __restrict__ lattices, int lattice_mode, int* __restrict__ spill_all, int64_t spill_stride)
+                      int* __restrict__ queue, double* __restrict__ lattices, int lattice_mode, int* __restrict__ spill_all, int64_t spill_stride,
+                      int n_whole, int split)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StateConst* scp = reinterpret_cast<StateConst*>(smem_raw);
@@ -283,15 +284,26 @@ emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n
             *cold_n = 0;
         }
         __syncthreads();
-        const int item = *next_item;
-        if (item >= n_items) break;
+        // work units: the first n_whole items whole, every later item as `split` units of consecutive bins (each builds the
+        // item's lattices again): a last, partly filled round of items over the CTAs is dealt out in pieces that fill it
+        const int unit = *next_item;
+        if (unit >= n_whole + (n_items - n_whole) * split) break;
+        int item = unit;
+        int64_t sub_lo = 0, sub_hi = INT64_MAX;
+        if (unit >= n_whole && split > 1) {                       // (one bin range per launch when split > 1: launch_emission_table)
+            const int j = unit - n_whole, part = j % split;
+            item = n_whole + j / split;
+            const int64_t len = rg.b1[0] - rg.b0[0];
+            sub_lo = part == 0 ? rg.b0[0] : rg.b0[0] + ((len * part / split) & ~(int64_t)127);
+            sub_hi = part + 1 == split ? rg.b1[0] : rg.b0[0] + ((len * (part + 1) / split) & ~(int64_t)127);
+        }
         const int sample = item / n_states, s = item - sample * n_states;
         for (int i = threadIdx.x; i < (int)(sizeof(StateConst) / 8); i += blockDim.x)
             reinterpret_cast<double*>(scp)[i] = reinterpret_cast<const double*>(consts + item)[i];
         __syncthreads();
         double* __restrict__ o = out.ptr + sample * out.sample_stride + s * out.state_stride;
         if (!scp->ok) {      // pathological shape parameters: reference NaN/sign semantics, cell by cell
-            whole_item_cold(scp, c, sample, rg, o, flags);
+            whole_item_cold(scp, c, sample, rg, sub_lo, sub_hi, o, flags);
             continue;
         }
         // lattice_mode 0: build; 1: build and keep a copy in HBM (first chromosome group of a pipelined batch);
@@ -396,8 +408,9 @@ emission_table_kernel(CountsView c, const StateConst* __restrict__ consts, int n
 
         for (int q = 0; q < rg.n; q++) {
             // a range may start anywhere (a chromosome's first bin): scalar head up to the next multiple of 4 bins
-            const int64_t r1 = rg.b1[q], r0 = min(r1, (rg.b0[q] + 3) & ~(int64_t)3);
-            for (int64_t bt = rg.b0[q] + threadIdx.x; bt < r0; bt += blockDim.x) {
+            const int64_t rb = max(rg.b0[q], sub_lo), r1 = min(rg.b1[q], sub_hi), r0 = min(r1, (rb + 3) & ~(int64_t)3);
+            if (rb >= r1) continue;
+            for (int64_t bt = rb + threadIdx.x; bt < r0; bt += blockDim.x) {
                 bool in;
                 o[bt] = cell(obs_row[bt], oth_row[bt], in);
                 if (!in) park(bt);
@@ -505,7 +518,6 @@ void launch_emission_table(CountsView c, const StateConst* consts, int n_samples
     if (n_items == 0 || rg.n == 0) return;
     cudaMemsetAsync(queue, 0, sizeof(int), st);
     const size_t smem = emission_table_smem_bytes(dims);
-    const int grid = n_items < n_sms ? n_items : n_sms;
     if (dims.K + dims.R + dims.N < kPanelEntries) {
         static PerDevice configured;
         if (configured.raise(smem)) {
@@ -520,13 +532,33 @@ void launch_emission_table(CountsView c, const StateConst* consts, int n_samples
         const int threads = two ? kTableThreads / 2 : kTableThreads;
         const int ctas = two ? 2 * n_sms : n_sms;
         emission_table_kernel<true, false><<<n_items < ctas ? n_items : ctas, threads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices,
-                                                                                          lattices ? lattice_mode : 0, spill, spill_stride);
+                                                                                          lattices ? lattice_mode : 0, spill, spill_stride, n_items, 1);
         return;
     }
     static PerDevice configured;
     if (configured.raise(smem)) cudaFuncSetAttribute(emission_table_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     // warp-row bin mapping (full-sector 128-bit stores): measured 0.967 -> 0.895 ms per launch at 256 x 200k x 5 (profiles/r2a_knob_ab.log)
-    emission_table_kernel<false, true><<<grid, kTableThreads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices, lattices ? lattice_mode : 0, spill, spill_stride);
+    // The items left over after the whole rounds over the CTAs (64 samples x 5 states on 148 SMs: 2 rounds and 24 items) go out
+    // as `split` units of consecutive bins each, every unit building the item's lattices again (~13 % of an item): the split
+    // that minimises rounds x (build + gathers / split) — 24 items as 6 x 24 units cost 0.28 of a round instead of a whole one.
+    int n_whole = n_items, split = 1;
+    if ((!lattices || lattice_mode == 0) && rg.n == 1 && n_items % n_sms != 0) {
+        const int rest = n_items % n_sms;
+        const int64_t bins = rg.b1[0] - rg.b0[0];
+        constexpr double kBuild = 0.13;
+        double best = 1.0;
+        for (int f = 2; f <= 8 && bins / f >= 16384; f++) {
+            const double cost = (double)((rest * f + n_sms - 1) / n_sms) * (kBuild + (1.0 - kBuild) / f);
+            if (cost < best - 0.05) {
+                best = cost;
+                split = f;
+            }
+        }
+        if (split > 1) n_whole = n_items - rest;
+    }
+    const int n_units = n_whole + (n_items - n_whole) * split;
+    emission_table_kernel<false, true><<<n_units < n_sms ? n_units : n_sms, kTableThreads, smem, st>>>(c, consts, n_states, n_items, rg, dims, out, flags, queue, lattices,
+                                                                                                      lattices ? lattice_mode : 0, spill, spill_stride, n_whole, split);
 }
 
 }  // namespace edb
