@@ -252,7 +252,7 @@ struct edb200_cohort {
     int seg_ok = 0;
     int seg_slot = 0;                    // which sample chunk of a host call is being processed (its pieces and flags are its own)
     int vit_slots = 1, vit_slot = 0, vit_slot_samples = 0;     // (slots sized for vit_slot_samples, the largest chunk)
-    // sample-chunk pipeline: two sets of Viterbi scratch (back-pointers, per-chain call tables), chunk k uses set k & 1
+    // sample-chunk pipeline: a set of Viterbi scratch (back-pointers, per-chain call tables) per chunk
     int emission_sms = 0;                // SMs the emission launch of the current chunk may take (0 = all)
     bool in_host_call = false;
     // the pieces of one chromosome group for `key` (samples, warps, warm-up, shortest piece), its scratch and flags
@@ -1226,7 +1226,7 @@ static int viterbi_part(edb200_cohort* c, edb200_cohort::Part& pt, edb::ViterbiA
 // Defaults: a warm-up of 2 tiles (32 observations; 8 already close every seam of the synthetic cohorts, and a seam that does
 // not close only costs its chain the repair pass), pieces of at least 12 tiles.
 constexpr int kSegWarm = 2, kSegMinPiece = 12;
-constexpr int kChunkReserve = 56;        // SMs the emission of a middle chunk leaves to the Viterbi kernels of the chunk before it
+constexpr int kChunkReserve = 40;        // SMs the emission of a middle chunk leaves to the Viterbi kernels of the chunk before it
 // Whether to cut the chains: when an even share of all tiles per sweep warp (plus its warm-up) is well below what bounds
 // the plain sweeps — the longest chain, or the whole lines packed onto the warps.
 static bool use_segments(const edb200_cohort* c, int n_samples)
@@ -1886,11 +1886,13 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
             c->emission_sms = 0;
             if (rc) return rc;
             CU(cudaEventRecord(g.ev_em[k], sx));
-            // two Viterbi streams with a scratch set each: the sweep of chunk k fills the SMs while the small, latency-bound kernels
-            // behind the sweep of chunk k-1 (tile maps, trace, expand, check, repair, compaction, call sums) are still running
-            cudaStream_t sv = g.s_vit[k & 1];
-            c->vit_slots = 2;
-            c->vit_slot = k & 1;
+            // a Viterbi stream and a scratch set per chunk: the sweep of chunk k fills the SMs while the small, latency-bound kernels
+            // behind the sweeps of the chunks before it (tile maps, trace, expand, check, repair, compaction, call sums) are still
+            // running — or still waiting for an SM beside the emission grid of chunk k+1 (with two alternating sets the sweep of the
+            // last chunk sat 0.2 ms behind the starved expand kernel of the chunk two before it, profiles/r2j_e2e_timeline.txt)
+            cudaStream_t sv = g.s_vit[k];
+            c->vit_slots = seg_k;
+            c->vit_slot = k;
             c->vit_slot_samples = seg_per;
             CU(cudaStreamWaitEvent(sv, g.ev_em[k], 0));
             if ((rc = edb200_cohort_run_device(c, &e, 2 | (d.call_stats ? 4 : 0), emission_mode, sv))) return rc;
@@ -1906,8 +1908,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         }
         CU(cudaEventRecord(g.ev_setup, sr));
         CU(cudaStreamWaitEvent(st, g.ev_setup, 0));
-        CU(cudaStreamWaitEvent(st, g.ev_vit[seg_k - 1], 0));
-        if (seg_k > 1) CU(cudaStreamWaitEvent(st, g.ev_vit[seg_k - 2], 0));
+        for (int k = 0; k < seg_k; k++) CU(cudaStreamWaitEvent(st, g.ev_vit[k], 0));
     } else if (plan.size() > 1) {
         // ---- chromosome-group pipeline over PCIe: the counts of the long chromosomes go up first; their emission and
         // sweep (the critical path) run while the other groups are still uploading; results drain per group.
