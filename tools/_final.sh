@@ -24,3 +24,11 @@ for name in ("bench", "bench_s3", "bench_panel", "bench_refset", "bench_referenc
         print(name, "parse failed", ex)
 PY
 tail -5 gpurun_out/bench.err
+if [ "${2:-}" = "ncu" ]; then
+# one --set full capture of each kernel of the device-resident step (first launch after the warm-up launches)
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"emission_table|viterbi_tpc|viterbi_tilemap|viterbi_trace|viterbi_expand" --launch-skip 10 --launch-count 5 \
+    -o gpurun_out/${tag}_full -f python tools/perf_probe.py --reps 1 > gpurun_out/${tag}_ncu.log 2>&1; echo "ncu full rc=$? $(( $(date +%s) - t0 ))s"
+timeout 200 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/${tag}_memcheck.log \
+    python -m pytest tests/test_gpu_parity.py -x -q -k "table_and_direct or panel_lattice or sample_chunk or kat1 or ragged" \
+    > gpurun_out/${tag}_memcheck_pytest.log 2>&1; echo "memcheck rc=$? $(( $(date +%s) - t0 ))s"; tail -2 gpurun_out/${tag}_memcheck_pytest.log; tail -2 gpurun_out/${tag}_memcheck.log
+fi
