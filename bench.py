@@ -397,9 +397,12 @@ def gpu_arm(a, rank, world):
         n_e2e = max(2, min(a.steps, 10))
         h2d = obs16_p.nbytes + ovf_i.nbytes + ovf_v.nbytes + ref.nbytes + phi_h.nbytes + exp_h.nbytes
 
+        pairs12 = (nb + 1) // 2
+        obs12_p, ovf12_i, ovf12_v = edb.pack_counts12(obs_h, out=hb.empty((ns, (3 * pairs12 + 3) // 4 * 4), np.uint8))
+
         def timed(out, counts=None, **kw):
             counts = obs16_p if counts is None else counts
-            ovf = (ovf_i, ovf_v) if counts is obs16_p else None
+            ovf = (ovf_i, ovf_v) if counts is obs16_p else (ovf12_i, ovf12_v) if counts is obs12_p else None
             co.run_host(counts, ref, phi_h, exp_h, call_cap=cap, out=out, want_stats=True, overflow=ovf, **kw)     # warm-up (allocations)
             barrier()
             t0 = time.perf_counter()
@@ -422,6 +425,10 @@ def gpu_arm(a, rank, world):
                    segmented_sweep=co.segment_stats())
         e2e["int32_counts"] = dict(timed(base, counts=obs_p, want_ll=False, want_path=False), h2d_bytes_per_step=int(obs_p.nbytes + ref.nbytes + phi_h.nbytes + exp_h.nbytes),
                                    note="the same call with the counts as int32 [sample][bin] (edb200_batch.observed)")
+        e2e["counts12"] = dict(timed(base, counts=obs12_p, want_ll=False, want_path=False),
+                               h2d_bytes_per_step=int(obs12_p.nbytes + ovf12_i.nbytes + ovf12_v.nbytes + ref.nbytes + phi_h.nbytes + exp_h.nbytes),
+                               note=f"the same call with the counts as rows of 12-bit fields + overflow list ({int(ovf12_i.size)} entries) — "
+                                    "edb200_batch.observed12: a quarter fewer bytes over PCIe, what several ranks uploading at once are bound by")
         with_path = dict(base, path=hb.empty((ns, nb), np.int8))
         e2e["with_path"] = dict(timed(with_path, want_ll=False, want_path=True), note="+ per-bin Viterbi path (int8) copied back")
         if not a.no_ll:

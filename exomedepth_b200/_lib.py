@@ -47,7 +47,8 @@ class Batch(C.Structure):
                 ("path_stride", C.c_int64), ("calls", C.c_void_p), ("ncalls", C.c_void_p), ("call_cap", C.c_int32),
                 ("call_stats", C.c_void_p), ("cor", C.c_void_p),
                 ("per_bin_stride", C.c_int64), ("observed16", C.c_void_p), ("obs16_stride", C.c_int64), ("n_overflow", C.c_int64),
-                ("overflow_index", C.c_void_p), ("overflow_value", C.c_void_p)]
+                ("overflow_index", C.c_void_p), ("overflow_value", C.c_void_p),
+                ("observed12", C.c_void_p), ("obs12_stride", C.c_int64)]
 
 
 _lib = None

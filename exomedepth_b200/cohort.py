@@ -29,6 +29,31 @@ def pack_counts(observed, out=None):
     return u16, idx, val
 
 
+def pack_counts12(observed, out=None):
+    """The 12-bit ingestion layout (edb200_batch.observed12): returns (uint8[n_samples, stride] — every row a little-endian
+    bit stream of 12 bits per bin, 4095 = "see the overflow list", stride = 3 * ceil(n_bins / 2) rounded up to 4 —, int64 flat
+    indices sample * n_bins + bin, int32 values).  `out`: an existing uint8 array of that shape (e.g. pinned) to fill.  A
+    quarter fewer bytes per call over PCIe than pack_counts."""
+    observed = np.asarray(observed)
+    if observed.min(initial=0) < 0:
+        raise ValueError("negative read count")
+    ns, nb = observed.shape
+    big = observed >= 4095
+    idx = np.flatnonzero(big.ravel()).astype(np.int64)
+    val = observed.ravel()[idx].astype(np.int32)
+    pairs = (nb + 1) // 2
+    stride = (pairs * 3 + 3) // 4 * 4
+    u8 = out if out is not None else np.zeros((ns, stride), np.uint8)
+    assert u8.shape == (ns, stride) and u8.dtype == np.uint8
+    v = np.zeros((ns, 2 * pairs), np.uint16)
+    np.minimum(observed, 4095, out=v[:, :nb], casting="unsafe")
+    v0, v1 = v[:, 0::2], v[:, 1::2]
+    u8[:, 0:3 * pairs:3] = v0 & 0xFF
+    u8[:, 1:3 * pairs:3] = (v0 >> 8) | ((v1 & 0xF) << 4)
+    u8[:, 2:3 * pairs:3] = v1 >> 4
+    return u8, idx, val
+
+
 class DeviceGraph:
     """A captured device-resident batch (Cohort.capture_device).  Holds the tensors it was captured over."""
 
@@ -117,18 +142,21 @@ class Cohort:
     # ---- host buffers ---------------------------------------------------------------------------
     def run_host(self, observed, reference, phi, expected, want_ll=True, want_path=True, call_cap=512,
                  mode=_lib.EMISSION_AUTO, out=None, want_stats=False, overflow=None):
-        """observed int32[n_samples, n_bins] — or uint16 in the ingestion layout of pack_counts, with overflow = (flat indices,
+        """observed int32[n_samples, n_bins] — or uint16 / uint8 in the ingestion layouts of pack_counts / pack_counts12, with overflow = (flat indices,
         values) of the counts that do not fit 16 bits; reference int32[n_bins] (shared) or [n_samples, n_bins];
         phi, expected float64[n_samples].  Returns dict(ll [n,S,bins], path int8 [n,bins], calls, ncalls, status);
         with want_stats also call_stats float64[n, call_cap, 3] (per call: sum of ll[,type] - ll[,normal],
         sum of total*expected, sum of test; R/class_definition.R:393-400) and cor float64[n] (:338), both computed
         on the device — the likelihood matrix then only crosses PCIe if want_ll is set."""
         u16 = np.asarray(observed).dtype == np.uint16
-        observed = np.ascontiguousarray(np.asarray(observed, np.uint16 if u16 else np.int32))
+        p12 = np.asarray(observed).dtype == np.uint8          # rows of 12-bit fields (pack_counts12)
+        observed = np.asarray(observed, np.uint8 if p12 else np.uint16 if u16 else np.int32)
+        if not (p12 and observed.ndim == 2 and observed.strides[1] == 1 and observed.strides[0] % 4 == 0):   # (12-bit rows may sit further apart than they are long)
+            observed = np.ascontiguousarray(observed)
         reference = np.ascontiguousarray(np.asarray(reference, np.int32))
         ns = observed.shape[0]
         ovf_i = ovf_v = None
-        if u16 and overflow is not None and len(overflow[0]):
+        if (u16 or p12) and overflow is not None and len(overflow[0]):
             ovf_i = np.ascontiguousarray(np.asarray(overflow[0], np.int64))
             ovf_v = np.ascontiguousarray(np.asarray(overflow[1], np.int32))
         S, nb = self.n_states, self.n_bins
@@ -136,7 +164,7 @@ class Cohort:
         shape = (ns, nb) if per_bin else (ns,)
         phi = np.ascontiguousarray(np.broadcast_to(np.asarray(phi, np.float64), shape))
         expected = np.ascontiguousarray(np.broadcast_to(np.asarray(expected, np.float64), shape))
-        assert observed.shape == (ns, nb)
+        assert observed.shape == ((ns, ((nb + 1) // 2 * 3 + 3) // 4 * 4) if p12 else (ns, nb))
         out = out or {}
         ll = out.get("ll") if want_ll else None
         if want_ll and ll is None:
@@ -158,10 +186,10 @@ class Cohort:
             cor = out.get("cor")
             if cor is None:
                 cor = np.zeros(ns)
-        b = _lib.Batch(ns, None if u16 else _ptr(observed), nb, _ptr(reference), 0 if reference.ndim == 1 else nb, _ptr(phi),
+        b = _lib.Batch(ns, None if (u16 or p12) else _ptr(observed), nb, _ptr(reference), 0 if reference.ndim == 1 else nb, _ptr(phi),
                        _ptr(expected), _ptr(ll), nb, _ptr(path), nb, _ptr(calls), _ptr(ncalls), call_cap,
                        _ptr(stats), _ptr(cor), nb if per_bin else 0, _ptr(observed) if u16 else None, nb, 0 if ovf_i is None else ovf_i.size,
-                       _ptr(ovf_i), _ptr(ovf_v))
+                       _ptr(ovf_i), _ptr(ovf_v), _ptr(observed) if p12 else None, observed.strides[0] if p12 else 0)
         rc = _lib.check(self.lib.edb200_cohort_run_host(self.handle, C.byref(b), mode), "edb200_cohort_run_host")
         self._last_ns = ns
         return dict(ll=ll, path=path, calls=calls, ncalls=ncalls, status=rc, call_stats=stats, cor=cor)

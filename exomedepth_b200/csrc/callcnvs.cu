@@ -229,6 +229,28 @@ widen_counts_kernel(const uint16_t* __restrict__ src, int64_t src_stride, int32_
     }
 }
 
+// 12-bit layout (edb200_batch.observed12): a row is a little-endian bit stream of 12 bits per bin; a thread takes eight bins =
+// 12 bytes = three 32-bit words and writes two 128-bit words.
+__global__ void __launch_bounds__(256)
+unpack12_counts_kernel(const uint8_t* __restrict__ src, int64_t src_stride, int32_t* __restrict__ dst, int64_t dst_stride, int64_t n_bins)
+{
+    const int sample = blockIdx.y;
+    const uint8_t* __restrict__ s = src + sample * src_stride;
+    int32_t* __restrict__ d = dst + sample * dst_stride;
+    const bool vec = ((reinterpret_cast<uintptr_t>(s) | (uintptr_t)src_stride) & 3) == 0 && ((reinterpret_cast<uintptr_t>(d) | (uintptr_t)(dst_stride * 4)) & 15) == 0;
+    const int64_t n8 = vec ? n_bins / 8 : 0;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n8; g += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(s + 12 * g);
+        const uint32_t w0 = __ldcs(w), w1 = __ldcs(w + 1), w2 = __ldcs(w + 2);
+        reinterpret_cast<int4*>(d + 8 * g)[0] = make_int4((int)(w0 & 0xFFFu), (int)((w0 >> 12) & 0xFFFu), (int)((w0 >> 24) | ((w1 & 0xFu) << 8)), (int)((w1 >> 4) & 0xFFFu));
+        reinterpret_cast<int4*>(d + 8 * g)[1] = make_int4((int)((w1 >> 16) & 0xFFFu), (int)((w1 >> 28) | ((w2 & 0xFFu) << 4)), (int)((w2 >> 8) & 0xFFFu), (int)(w2 >> 20));
+    }
+    for (int64_t b = n8 * 8 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < n_bins; b += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t at = (3 * b) >> 1;                                   // byte of bit 12 b
+        d[b] = (b & 1) ? (int)(s[at] >> 4) | ((int)s[at + 1] << 4) : (int)s[at] | (((int)s[at + 1] & 0xF) << 8);
+    }
+}
+
 __global__ void patch_overflow_kernel(const int64_t* __restrict__ index, const int32_t* __restrict__ value, int64_t n_overflow, int64_t n_bins,
                                       int32_t* __restrict__ dst, int64_t dst_stride, const __grid_constant__ BinRanges rg, int64_t s_lo, int64_t s_hi)
 {
@@ -238,6 +260,17 @@ __global__ void patch_overflow_kernel(const int64_t* __restrict__ index, const i
     if (sample < s_lo || sample >= s_hi) return;
     for (int q = 0; q < rg.n; q++)
         if (b >= rg.b0[q] && b < rg.b1[q]) dst[sample * dst_stride + b] = value[i];
+}
+
+int launch_unpack12_counts(const uint8_t* src, int64_t src_stride, int32_t* dst, int64_t dst_stride, int n_samples, int64_t n_bins, cudaStream_t st)
+{
+    if (n_samples == 0 || n_bins == 0) return 0;
+    int bx = (int)((n_bins / 8 + 255) / 256);
+    bx = bx < 1 ? 1 : bx > 64 ? 64 : bx;
+    prof_mark("widen_counts", st);
+    unpack12_counts_kernel<<<dim3((unsigned)bx, (unsigned)n_samples), 256, 0, st>>>(src, src_stride, dst, dst_stride, n_bins);
+    prof_mark(nullptr, st);
+    return 1;
 }
 
 int launch_widen_counts(const uint16_t* src, int64_t src_stride, int32_t* dst, int64_t dst_stride, int n_samples, int64_t n_bins,

@@ -1775,20 +1775,30 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     const bool want_vit = b->path || b->calls || b->ncalls || b->call_stats;
     c->last_host_samples = ns;
 
-    const int n_parts = want_vit && !b->per_bin_stride ? pick_parts(c, emission_mode, Context::kMaxParts) : 1;
+    // (the 12-bit layout goes up in whole rows: sample chunks, not chromosome groups)
+    const int n_parts = want_vit && !b->per_bin_stride && !b->observed12 ? pick_parts(c, emission_mode, Context::kMaxParts) : 1;
     if ((rc = build_plan(c, n_parts))) return rc;
     std::vector<edb200_cohort::Part>& plan = c->plans[n_parts];
 
     // 16-bit ingestion layout: the overflow list goes up once, every group's columns are widened behind their upload
-    const bool u16 = b->observed16 != nullptr;
-    if (u16) {
+    const bool p12 = b->observed12 != nullptr;
+    const bool u16 = !p12 && b->observed16 != nullptr;
+    const int64_t row12 = (nb + 1) / 2 * 3, r12 = (row12 + 3) & ~(int64_t)3;         // bytes of a 12-bit row; its pitch on the device
+    if (p12) {
+        if (b->obs12_stride < row12 || (b->obs12_stride & 3) || (reinterpret_cast<uintptr_t>(b->observed12) & 3) || b->n_overflow < 0 ||
+            (b->n_overflow > 0 && (!b->overflow_index || !b->overflow_value)))
+            return fail(EDB200_ERR_ARG, "bad 12-bit count layout (stride: a multiple of 4, >= 3 * ceil(n_bins / 2); rows 4-byte aligned; overflow list)");
+        if ((rc = ensure(c->h_obs16, (size_t)ns * r12)) || (rc = ensure(c->h_ovf_i, (size_t)b->n_overflow * 8 + 8)) ||
+            (rc = ensure(c->h_ovf_v, (size_t)b->n_overflow * 4 + 8)))
+            return rc;
+    } else if (u16) {
         if (b->obs16_stride < nb || b->n_overflow < 0 || (b->n_overflow > 0 && (!b->overflow_index || !b->overflow_value)))
             return fail(EDB200_ERR_ARG, "bad 16-bit count layout (stride / overflow list)");
         if ((rc = ensure(c->h_obs16, (size_t)ns * nb * 2)) || (rc = ensure(c->h_ovf_i, (size_t)b->n_overflow * 8 + 8)) ||
             (rc = ensure(c->h_ovf_v, (size_t)b->n_overflow * 4 + 8)))
             return rc;
     } else if (!b->observed)
-        return fail(EDB200_ERR_ARG, "no test counts in batch (observed or observed16)");
+        return fail(EDB200_ERR_ARG, "no test counts in batch (observed, observed16 or observed12)");
 
     // ---- sample-chunk pipeline (segmented sweeps).  With the chains cut into pieces no chromosome is a critical path any
     // more, so the batch goes through in chunks of SAMPLES: chunk k+1 uploads (contiguous rows) while chunk k runs emission,
@@ -1798,7 +1808,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     int seg_k = 0, seg_per = 0;
     if (want_vit && !b->per_bin_stride && use_table(c, emission_mode) && c->opt_parts == 0) {
         if ((rc = ensure_struct(c))) return rc;
-        const double upload_ms = (double)ns * nb * (u16 ? 2.0 : 4.0) / 53e6, per_chunk_ms = 0.12;
+        const double upload_ms = (double)ns * nb * (p12 ? 1.5 : u16 ? 2.0 : 4.0) / 53e6, per_chunk_ms = 0.12;
         int k = c->opt_chunks > 0 ? c->opt_chunks : (int)std::lround(std::sqrt(upload_ms / per_chunk_ms));       // (4 at 256 x 200k, 16-bit: measured best with 56 SMs reserved)
         k = std::max(1, std::min({k, Context::kMaxParts, ns / 24}));
         // chunk size: a whole number of rounds of the emission kernel's (sample, state) items over the SMs (64 samples x 5
@@ -1821,7 +1831,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         if (shared_ref) CU(cudaMemcpyAsync(c->h_ref.p, b->reference, nb * 4, cudaMemcpyHostToDevice, sc));
         CU(cudaMemcpyAsync(c->h_phi.p, b->phi, ns * 8, cudaMemcpyHostToDevice, sc));
         CU(cudaMemcpyAsync(c->h_exp.p, b->expected, ns * 8, cudaMemcpyHostToDevice, sc));
-        if (u16 && b->n_overflow > 0) {
+        if ((u16 || p12) && b->n_overflow > 0) {
             CU(cudaMemcpyAsync(c->h_ovf_i.p, b->overflow_index, (size_t)b->n_overflow * 8, cudaMemcpyHostToDevice, sc));
             CU(cudaMemcpyAsync(c->h_ovf_v.p, b->overflow_value, (size_t)b->n_overflow * 4, cudaMemcpyHostToDevice, sc));
         }
@@ -1832,7 +1842,10 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         for (int k = 0, s0 = 0; s0 < ns; k++, s0 += seg_per) {
             const int cnt = std::min(seg_per, ns - s0);
             edb::prof_mark("h2d_counts", sc);
-            if (u16)
+            if (p12)
+                CU(cudaMemcpy2DAsync((uint8_t*)c->h_obs16.p + (size_t)s0 * r12, r12, b->observed12 + (size_t)s0 * b->obs12_stride, b->obs12_stride,
+                                     row12, cnt, cudaMemcpyHostToDevice, sc));
+            else if (u16)
                 CU(cudaMemcpy2DAsync((uint16_t*)c->h_obs16.p + (size_t)s0 * nb, nb * 2, b->observed16 + (size_t)s0 * b->obs16_stride, b->obs16_stride * 2,
                                      nb * 2, cnt, cudaMemcpyHostToDevice, sc));
             else
@@ -1843,12 +1856,15 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
                                      nb * 4, cnt, cudaMemcpyHostToDevice, sc));
             edb::prof_mark(nullptr, sc);
             CU(cudaEventRecord(g.ev_copy[k], sc));
-            if (u16) {
+            if (u16 || p12) {
                 // widened on a stream of its own: on the copy stream the kernel — whose blocks wait for an SM while an emission
                 // grid is resident — would hold up the next chunk's upload (0.1 ms per chunk)
                 CU(cudaStreamWaitEvent(sw, g.ev_copy[k], 0));
-                g_launches += edb::launch_widen_counts((const uint16_t*)c->h_obs16.p + (size_t)s0 * nb, nb, (int32_t*)c->h_obs.p + (size_t)s0 * nb, nb, cnt, nb,
-                                                       all, nullptr, nullptr, 0, sw);
+                if (p12)
+                    g_launches += edb::launch_unpack12_counts((const uint8_t*)c->h_obs16.p + (size_t)s0 * r12, r12, (int32_t*)c->h_obs.p + (size_t)s0 * nb, nb, cnt, nb, sw);
+                else
+                    g_launches += edb::launch_widen_counts((const uint16_t*)c->h_obs16.p + (size_t)s0 * nb, nb, (int32_t*)c->h_obs.p + (size_t)s0 * nb, nb, cnt, nb,
+                                                           all, nullptr, nullptr, 0, sw);
                 g_launches += edb::launch_patch_overflow((int32_t*)c->h_obs.p, nb, nb, all, (const int64_t*)c->h_ovf_i.p, (const int32_t*)c->h_ovf_v.p,
                                                          b->n_overflow, sw, s0, s0 + cnt);
                 CU(cudaEventRecord(g.ev_copy[k], sw));
@@ -2017,9 +2033,13 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         }
         for (int k = 0, s0 = 0; s0 < ns; k++, s0 += per) {
             const int cnt = ns - s0 < per ? ns - s0 : per;
-            if (u16) {
-                CU(cudaMemcpy2DAsync((uint16_t*)c->h_obs16.p + (size_t)s0 * nb, nb * 2, b->observed16 + (size_t)s0 * b->obs16_stride, b->obs16_stride * 2,
-                                     nb * 2, cnt, cudaMemcpyHostToDevice, st));
+            if (u16 || p12) {
+                if (p12)
+                    CU(cudaMemcpy2DAsync((uint8_t*)c->h_obs16.p + (size_t)s0 * r12, r12, b->observed12 + (size_t)s0 * b->obs12_stride, b->obs12_stride,
+                                         row12, cnt, cudaMemcpyHostToDevice, st));
+                else
+                    CU(cudaMemcpy2DAsync((uint16_t*)c->h_obs16.p + (size_t)s0 * nb, nb * 2, b->observed16 + (size_t)s0 * b->obs16_stride, b->obs16_stride * 2,
+                                         nb * 2, cnt, cudaMemcpyHostToDevice, st));
                 if (k == 0 && b->n_overflow > 0) {
                     CU(cudaMemcpyAsync(c->h_ovf_i.p, b->overflow_index, (size_t)b->n_overflow * 8, cudaMemcpyHostToDevice, st));
                     CU(cudaMemcpyAsync(c->h_ovf_v.p, b->overflow_value, (size_t)b->n_overflow * 4, cudaMemcpyHostToDevice, st));
@@ -2028,8 +2048,11 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
                 all.n = 1;
                 all.b0[0] = 0;
                 all.b1[0] = nb;
-                g_launches += edb::launch_widen_counts((const uint16_t*)c->h_obs16.p + (size_t)s0 * nb, nb, (int32_t*)c->h_obs.p + (size_t)s0 * nb, nb, cnt, nb, all,
-                                                       nullptr, nullptr, 0, st);
+                if (p12)
+                    g_launches += edb::launch_unpack12_counts((const uint8_t*)c->h_obs16.p + (size_t)s0 * r12, r12, (int32_t*)c->h_obs.p + (size_t)s0 * nb, nb, cnt, nb, st);
+                else
+                    g_launches += edb::launch_widen_counts((const uint16_t*)c->h_obs16.p + (size_t)s0 * nb, nb, (int32_t*)c->h_obs.p + (size_t)s0 * nb, nb, cnt, nb, all,
+                                                           nullptr, nullptr, 0, st);
                 // the overflow entries of every sample, after every chunk: rows not yet uploaded are overwritten by their own widen
                 // pass and patched again then (the entries are idempotent)
                 g_launches += edb::launch_patch_overflow((int32_t*)c->h_obs.p, nb, nb, all, (const int64_t*)c->h_ovf_i.p, (const int32_t*)c->h_ovf_v.p, b->n_overflow, st);

@@ -227,6 +227,9 @@ int launch_call_summary(const CallSummaryArgs& a, cudaStream_t st);   // returns
 int launch_widen_counts(const uint16_t* src, int64_t src_stride, int32_t* dst, int64_t dst_stride, int n_samples, int64_t n_bins,
                         const BinRanges& rg, const int64_t* ovf_index, const int32_t* ovf_value, int64_t n_overflow, cudaStream_t st);
 
+// 12-bit counts (rows of little-endian 12-bit fields, 4095 = see the overflow list) -> int32 rows, whole rows
+int launch_unpack12_counts(const uint8_t* src, int64_t src_stride, int32_t* dst, int64_t dst_stride, int n_samples, int64_t n_bins, cudaStream_t st);
+
 int launch_patch_overflow(int32_t* dst, int64_t dst_stride, int64_t n_bins, const BinRanges& rg, const int64_t* ovf_index,
                           const int32_t* ovf_value, int64_t n_overflow, cudaStream_t st, int64_t s_lo = 0, int64_t s_hi = INT64_MAX);
 

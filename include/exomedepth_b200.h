@@ -190,6 +190,13 @@ typedef struct edb200_batch {
     int64_t        n_overflow;
     const int64_t *overflow_index;
     const int32_t *overflow_value;
+    /* 12-bit ingestion layout (HOST mode only, used instead of `observed` / `observed16` when non-NULL): every row a
+     * little-endian bit stream of 12 bits per bin — bins 2i and 2i+1 in bytes 3i .. 3i+2: v0 | v1 << 12 — with 4095 standing for
+     * "see the overflow list" (the same list as above: counts of 4095 and beyond).  obs12_stride: bytes from one sample's row
+     * to the next, a multiple of 4 and >= 3 * ceil(n_bins / 2); rows 4-byte aligned.  A quarter fewer bytes over PCIe than the
+     * 16-bit layout — what a host with eight GPUs uploading at once is bound by.  exomedepth_b200/cohort.py:pack_counts12. */
+    const uint8_t *observed12;
+    int64_t        obs12_stride;
 } edb200_batch;
 
 /* mode: 0 = auto (full lattice from 106,496 bins; panel lattice from 4,096 bins when samples x states >= 2 x SMs;

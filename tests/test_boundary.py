@@ -109,3 +109,54 @@ def test_glue_rejects_other_state_counts_without_touching_the_gpu():
     import numpy as np
     assert api.c_hmm(np.full((5, 5), 0.2), np.zeros((4, 5)), np.arange(4), 1.0) is None
     assert api.rprintf_count() == 1
+
+
+def test_batch_struct_layout_matches_the_header(tmp_path):
+    """exomedepth_b200/_lib.py:Batch is a hand-written ctypes image of include/exomedepth_b200.h:edb200_batch — size and
+    every field offset must be what the C compiler lays out."""
+    from exomedepth_b200 import _lib
+    fields = [n for n, _ in _lib.Batch._fields_]
+    src = tmp_path / "layout.c"
+    lines = "\n".join(f'    printf("{n} %zu\\n", offsetof(edb200_batch, {n}));' for n in fields)
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "exomedepth_b200.h"\nint main(void) {\n'
+                   '    printf("sizeof %zu\\n", sizeof(edb200_batch));\n' + lines + "\n    return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert int(out.pop("sizeof")) == C.sizeof(_lib.Batch)
+    for n in fields:
+        assert int(out[n]) == getattr(_lib.Batch, n).offset, n
+    # and the header has no field the ctypes image lacks
+    body = re.search(r"typedef struct edb200_batch \{(.*?)\} edb200_batch;", re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S), flags=re.S).group(1)
+    declared = re.findall(r"\b([a-z_0-9]+)\s*;", body)
+    assert declared == fields, (declared, fields)
+
+
+def test_ingestion_layouts_round_trip():
+    """pack_counts (edb200_batch.observed16) and pack_counts12 (observed12): decoding the packed rows as the header
+    describes them and applying the overflow list gives the counts back; sentinels themselves go to the list; odd bin
+    counts and row strides as documented."""
+    import numpy as np
+
+    from exomedepth_b200 import pack_counts, pack_counts12
+    rng = np.random.default_rng(5)
+    for nb in (1, 2, 7, 8, 4097, 4098):
+        obs = rng.integers(0, 5000, (5, nb)).astype(np.int32)
+        obs[rng.integers(5), rng.integers(nb)] = 70000
+        obs[0, 0], obs[4, nb - 1] = 4095, 65535
+        u16, i16, v16 = pack_counts(obs)
+        dec = u16.astype(np.int32)
+        assert np.all(dec.ravel()[i16] == 65535) and np.all(v16 >= 65535)
+        dec.ravel()[i16] = v16
+        assert np.array_equal(dec, obs)
+        u8, i12, v12 = pack_counts12(obs)
+        pairs = (nb + 1) // 2
+        assert u8.dtype == np.uint8 and u8.shape == (5, (3 * pairs + 3) // 4 * 4)
+        trip = u8[:, :3 * pairs].reshape(5, pairs, 3).astype(np.int32)
+        word = trip[:, :, 0] | trip[:, :, 1] << 8 | trip[:, :, 2] << 16               # v0 | v1 << 12
+        dec = np.stack([word & 0xFFF, word >> 12], axis=2).reshape(5, 2 * pairs)[:, :nb].copy()
+        assert np.array_equal(np.flatnonzero(dec.ravel() == 4095), i12) and np.all(v12 >= 4095)
+        dec.ravel()[i12] = v12
+        assert np.array_equal(dec, obs)
+    with pytest.raises(ValueError):
+        pack_counts12(np.array([[1, -1]]))

@@ -917,6 +917,42 @@ def test_16_bit_count_layout_matches_32_bit(edb):
         co.close()
 
 
+def test_12_bit_count_layout_matches_32_bit(edb):
+    """edb200_batch.observed12: rows of 12-bit fields + overflow list (counts of 4095 and beyond, incl. exactly 4095) give
+    the same likelihoods, paths, calls and per-call sums as the int32 matrix — through the sample-chunk pipeline, through the
+    sample-chunked single pass, with bin counts that are not a multiple of 8 / 4 / 2 (vector body + scalar tail, all-scalar
+    rows, a last byte pair holding one bin), a padded row stride and a per-sample reference."""
+    from exomedepth_b200 import _lib, synth
+    for ns, nb, mode, S in ((60, 20000, _lib.EMISSION_TABLE, 5), (9, 3000, _lib.EMISSION_AUTO, 5), (7, 3004, _lib.EMISSION_AUTO, 3),
+                            (5, 3001, _lib.EMISSION_AUTO, 3), (40, 20006, _lib.EMISSION_TABLE, 3)):
+        d = synth.cohort(ns, n_bins=nb)
+        obs = d["observed"].copy()
+        assert obs.shape[1] == nb
+        rng = np.random.default_rng(nb)
+        for _ in range(12):
+            obs[rng.integers(ns), rng.integers(nb)] = int(rng.integers(4096, 300000))
+        obs[ns // 2, 17], obs[ns - 1, nb - 1], obs[0, nb - 2] = 4095, 4094, 5000
+        ref = d["reference"] if ns != 7 else np.tile(d["reference"], (ns, 1)) + np.arange(ns, dtype=np.int32)[:, None]
+        co = edb.Cohort(d["offsets"], d["start"], d["end"], n_states=S)
+        want = co.run_host(obs, ref, d["phi"], d["expected"], call_cap=256, mode=mode, want_stats=True)
+        u8, idx, val = edb.pack_counts12(obs)
+        assert u8.dtype == np.uint8 and idx.size >= 14 and (obs >= 4095).sum() == idx.size
+        if ns == 9:                                            # rows further apart than they are long
+            wide = np.full((ns, u8.shape[1] + 8), 0xAB, np.uint8)
+            wide[:, :u8.shape[1]] = u8
+            u8 = wide[:, :u8.shape[1]]
+        for chunks in ((0, 2) if ns >= 40 else (0,)):
+            co.set_option("chunks", chunks)
+            got = co.run_host(u8, ref, d["phi"], d["expected"], call_cap=256, mode=mode, want_stats=True, overflow=(idx, val))
+            for k in ("ll", "path", "calls", "ncalls", "call_stats", "cor"):
+                assert np.array_equal(got[k], want[k], equal_nan=True), (ns, nb, chunks, k)
+        got = co.run_host(u8, ref, d["phi"], d["expected"], call_cap=256, mode=mode, want_ll=False, want_path=False, want_stats=True,
+                          overflow=(idx, val))
+        for k in ("calls", "ncalls", "call_stats", "cor"):
+            assert np.array_equal(got[k], want[k], equal_nan=True), (ns, nb, k)
+        co.close()
+
+
 def test_sample_chunk_pipeline_matches_single_pass(edb):
     """The host call with segmented sweeps moves the batch through in chunks of samples (upload k+1 | emission and sweep of
     chunk k): every output — likelihoods, paths, call tables, per-call sums, correlations — must equal the unsegmented

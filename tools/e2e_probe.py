@@ -19,6 +19,7 @@ ap.add_argument("--states", type=int, default=5)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--ll", action="store_true")
 ap.add_argument("--i32", action="store_true", help="int32 counts instead of the 16-bit ingestion layout")
+ap.add_argument("--p12", action="store_true", help="12-bit ingestion layout")
 ap.add_argument("--timeline", action="store_true")
 ap.add_argument("--opts", default="", help="cohort options, e.g. parts=4,sweep=1; several sets separated by ';' are timed in turn")
 ap.add_argument("--calls-only", action="store_true")
@@ -32,7 +33,10 @@ hb = _lib.PinnedPool()
 obs = hb.empty((ns, nb), np.int32)
 obs[:] = np.tile(d["observed"], (reps, 1))[:ns]
 ovf = None
-if not a.i32:
+if a.p12:
+    obs, oi, ov = edb.pack_counts12(obs, out=hb.empty((ns, ((nb + 1) // 2 * 3 + 3) // 4 * 4), np.uint8))
+    ovf = (oi, ov)
+elif not a.i32:
     obs, oi, ov = edb.pack_counts(obs, out=hb.empty((ns, nb), np.uint16))
     ovf = (oi, ov)
 phi = np.tile(d["phi"], reps)[:ns]
@@ -65,5 +69,5 @@ for opts in a.opts.split(";"):
             co.run_host(obs, d["reference"], phi, ex, call_cap=cap, out=out, **kw)
             _lib.profile_read()
             _lib.profile(0)
-        print(f"{name:22s} opts={opts or 'default'} {'i32' if a.i32 else 'u16'}: best {min(ts):.3f} ms  median {sorted(ts)[len(ts) // 2]:.3f}  "
+        print(f"{name:22s} opts={opts or 'default'} {'p12' if a.p12 else 'i32' if a.i32 else 'u16'}: best {min(ts):.3f} ms  median {sorted(ts)[len(ts) // 2]:.3f}  "
               f"{ns * nb / min(ts) / 1e6:.2f} G bin*samples/s  calls {int(r['ncalls'].sum())}", flush=True)
