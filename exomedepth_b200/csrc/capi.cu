@@ -250,6 +250,7 @@ struct edb200_cohort {
     int opt_segments = -1, opt_seg_warm = 0, opt_seg_min = 0, opt_seg_repair = 0, opt_reserve = 0, opt_chunks = 0;
     // segmented sweep (viterbi_seam.h); seg_ok: the transition terms are small enough for the error bound (ensure_struct)
     int seg_ok = 0;
+    int consts_first = -1;               // >= 0: the per-state constants of the whole host batch are built; a chunk's start at this sample
     int seg_slot = 0;                    // which sample chunk of a host call is being processed (its pieces and flags are its own)
     int vit_slots = 1, vit_slot = 0, vit_slot_samples = 0;     // (slots sized for vit_slot_samples, the largest chunk)
     // sample-chunk pipeline: a set of Viterbi scratch (back-pointers, per-chain call tables) per chunk
@@ -1040,7 +1041,7 @@ static int emission_part(edb200_cohort* c, const edb200_batch* b, const edb::Bin
     }
     edb::CountsView cv{b->observed, b->obs_stride, b->reference, b->ref_stride, 0};
     edb::LLView out{b->ll, (int64_t)S * b->ll_stride, b->ll_stride};
-    edb::StateConst* consts = (edb::StateConst*)c->consts.p;
+    edb::StateConst* consts = (edb::StateConst*)c->consts.p + (c->consts_first > 0 ? (size_t)c->consts_first * S : 0);
     edb::TableDims d{kTableK, kTableRN, kTableRN};
     const bool panel = !use_table(c, mode) && whole && lattice_mode == 0 && panel_table(c, (int64_t)ns * S, mode, &d);
     if (panel || use_table(c, mode)) {
@@ -1395,7 +1396,8 @@ int edb200_cohort_run_device(edb200_cohort* c, const edb200_batch* b, int what, 
     if (plan.size() <= 1) {
         // ---- one pass: emission, then Viterbi, on the caller's stream
         if (what & 1) {
-            if (int rc = state_setup(c, b, st)) return rc;
+            if (c->consts_first < 0)
+                if (int rc = state_setup(c, b, st)) return rc;
             edb::BinRanges all{};
             all.n = 1;
             all.b0[0] = 0;
@@ -1739,7 +1741,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     struct HostCall {
         edb200_cohort* c;
         explicit HostCall(edb200_cohort* c_) : c(c_) { c->in_host_call = true; c->seg_used.clear(); }
-        ~HostCall() { c->in_host_call = false; c->seg_slot = 0; c->vit_slots = 1; c->vit_slot = 0; c->vit_slot_samples = 0; }
+        ~HostCall() { c->in_host_call = false; c->consts_first = -1; c->seg_slot = 0; c->vit_slots = 1; c->vit_slot = 0; c->vit_slot_samples = 0; }
     } host_call(c);
     cudaStream_t st = g.stream;
     const int S = c->S, ns = b->n_samples;
@@ -1808,7 +1810,8 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     int seg_k = 0, seg_per = 0;
     if (want_vit && !b->per_bin_stride && use_table(c, emission_mode) && c->opt_parts == 0) {
         if ((rc = ensure_struct(c))) return rc;
-        const double upload_ms = (double)ns * nb * (p12 ? 1.5 : u16 ? 2.0 : 4.0) / 53e6, per_chunk_ms = 0.12;
+        // (the 12-bit layout is counted like the 16-bit one: measured best is 4 chunks for both at 256 x 200k — the call is GPU-bound)
+        const double upload_ms = (double)ns * nb * (p12 || u16 ? 2.0 : 4.0) / 53e6, per_chunk_ms = 0.12;
         int k = c->opt_chunks > 0 ? c->opt_chunks : (int)std::lround(std::sqrt(upload_ms / per_chunk_ms));       // (4 at 256 x 200k, 16-bit: measured best with 56 SMs reserved)
         k = std::max(1, std::min({k, Context::kMaxParts, ns / 24}));
         // chunk size: a whole number of rounds of the emission kernel's (sample, state) items over the SMs (64 samples x 5
@@ -1835,12 +1838,16 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
             CU(cudaMemcpyAsync(c->h_ovf_i.p, b->overflow_index, (size_t)b->n_overflow * 8, cudaMemcpyHostToDevice, sc));
             CU(cudaMemcpyAsync(c->h_ovf_v.p, b->overflow_value, (size_t)b->n_overflow * 4, cudaMemcpyHostToDevice, sc));
         }
+        // the per-state constants of every sample need phi and expected only: built once, ahead of the counts (a setup launch
+        // per chunk in front of its emission kernel waits for an SM beside the running kernels; worth ~1 % of the call)
+        if ((rc = state_setup(c, &d, sc))) return rc;
         edb::BinRanges all{};
         all.n = 1;
         all.b0[0] = 0;
         all.b1[0] = nb;
         for (int k = 0, s0 = 0; s0 < ns; k++, s0 += seg_per) {
             const int cnt = std::min(seg_per, ns - s0);
+            c->consts_first = s0;
             edb::prof_mark("h2d_counts", sc);
             if (p12)
                 CU(cudaMemcpy2DAsync((uint8_t*)c->h_obs16.p + (size_t)s0 * r12, r12, b->observed12 + (size_t)s0 * b->obs12_stride, b->obs12_stride,
