@@ -131,7 +131,7 @@ def reference_arm(a, rank):
     if kind == "reference":
         ref.api()            # dlopen oracle/_ref/libexomedepth_ref.so in THIS process too (the workers are forked from it)
     states = 3 if kind == "reference" else N_STATES
-    per_step = max(2 * cores, 16)
+    per_step = max(6 * cores, 16)
     vals, per_core = [], []
     for it in range(a.warmup + a.steps):
         v, pc, wall = cpu_throughput(kind, states, per_step, cores)
@@ -610,7 +610,7 @@ def gpu_arm(a, rank, world):
         if kind == "reference":
             oref.api()       # the library is then mapped in this process as well as in the forked workers
         states = 3 if kind == "reference" else S
-        nsamp = max(2 * cores, 16)
+        nsamp = max(6 * cores, 16)
         v, pc, wall = cpu_throughput(kind, states, nsamp, cores)
         out["cpu_baseline"] = dict(value=v, unit=UNIT, cores=cores, kind=kind, per_core=pc, wall_s=wall,
                                    sample=f"{nsamp} of the same synthetic samples x {nb} bins, {states} states "
