@@ -152,7 +152,7 @@ def reference_arm(a, rank):
                ms_per_step=1e3 * per_step * N_BINS / value, higher_is_better=True, scaling="weak", vs_baseline=None,
                dtype="f64", data="synthetic",
                config=dict(workload=f"synthetic {N_SAMPLES} samples x {N_BINS} bins x {N_STATES} CN states per GPU "
-                                    f"(BASELINE.json configs[1])", nproc=cores, reference_states=states,
+                                    f"(BASELINE.json configs[1]); CallCNVs framing, tp=1e-4, L=50000", nproc=cores, reference_states=states,
                            note=("the reference implements 3 states only (src/hmm.cpp:37-40, src/CNV_estimate.cpp:69); it is timed "
                                  "at 3 states on the same synthetic samples, which is LESS work per bin*sample than the 5-state GPU arm"
                                  if kind == "reference" else "compiled reference unavailable: oracle port at 5 states")),
