@@ -1808,6 +1808,7 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
     // T ~ U / k + G + k * o  (U upload, G device time of the batch, o ~ 0.1-0.25 ms of launches, tails and partly filled rounds
     // per chunk): k ~ sqrt(U / o).
     int seg_k = 0, seg_per = 0;
+    bool tables_copied = false;                              // call tables / per-call columns already went back chunk by chunk
     if (want_vit && !b->per_bin_stride && use_table(c, emission_mode) && c->opt_parts == 0) {
         if ((rc = ensure_struct(c))) return rc;
         // (the 12-bit layout is counted like the 16-bit one: measured best is 4 chunks for both at 256 x 200k — the call is GPU-bound)
@@ -1920,14 +1921,21 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
             CU(cudaStreamWaitEvent(sv, g.ev_em[k], 0));
             if ((rc = edb200_cohort_run_device(c, &e, 2 | (d.call_stats ? 4 : 0), emission_mode, sv))) return rc;
             CU(cudaEventRecord(g.ev_vit[k], sv));
-            if (b->ll || b->path) {
-                CU(cudaStreamWaitEvent(g.stream2, g.ev_vit[k], 0));
-                if (b->ll)
-                    CU(cudaMemcpy2DAsync(b->ll + (size_t)s0 * S * b->ll_stride, b->ll_stride * 8, e.ll, nbp * 8, nb * 8, (size_t)cnt * S,
-                                         cudaMemcpyDeviceToHost, g.stream2));
-                if (b->path)
-                    CU(cudaMemcpy2DAsync(b->path + (size_t)s0 * b->path_stride, b->path_stride, e.path, nb, nb, cnt, cudaMemcpyDeviceToHost, g.stream2));
-            }
+            // results drain per chunk on the copy-back stream, behind the chunk's Viterbi pass and call sums: the call tables and
+            // per-call columns too (cap x 40 bytes per sample — 10.5 MB at 256 samples and a capacity of 1,024 calls: 0.19 ms if
+            // they all went back behind the last chunk's kernels)
+            CU(cudaStreamWaitEvent(g.stream2, g.ev_vit[k], 0));
+            if (b->ll)
+                CU(cudaMemcpy2DAsync(b->ll + (size_t)s0 * S * b->ll_stride, b->ll_stride * 8, e.ll, nbp * 8, nb * 8, (size_t)cnt * S,
+                                     cudaMemcpyDeviceToHost, g.stream2));
+            if (b->path)
+                CU(cudaMemcpy2DAsync(b->path + (size_t)s0 * b->path_stride, b->path_stride, e.path, nb, nb, cnt, cudaMemcpyDeviceToHost, g.stream2));
+            if (b->calls && b->call_cap > 0)
+                CU(cudaMemcpyAsync(b->calls + (size_t)s0 * cap * 4, e.calls, (size_t)cnt * cap * 16, cudaMemcpyDeviceToHost, g.stream2));
+            if (b->ncalls) CU(cudaMemcpyAsync(b->ncalls + s0, e.ncalls, (size_t)cnt * 4, cudaMemcpyDeviceToHost, g.stream2));
+            if (b->call_stats && b->call_cap > 0)
+                CU(cudaMemcpyAsync(b->call_stats + (size_t)s0 * cap * 3, e.call_stats, (size_t)cnt * cap * 24, cudaMemcpyDeviceToHost, g.stream2));
+            tables_copied = true;
         }
         CU(cudaEventRecord(g.ev_setup, sr));
         CU(cudaStreamWaitEvent(st, g.ev_setup, 0));
@@ -2086,9 +2094,11 @@ int edb200_cohort_run_host(edb200_cohort* c, const edb200_batch* b, int emission
         if (b->path) CU(cudaMemcpy2DAsync(b->path, b->path_stride, c->h_path.p, nb, nb, ns, cudaMemcpyDeviceToHost, st));
     }
 
-    if (b->calls && b->call_cap > 0) CU(cudaMemcpyAsync(b->calls, c->h_calls.p, (size_t)ns * cap * 16, cudaMemcpyDeviceToHost, st));
-    if (b->ncalls) CU(cudaMemcpyAsync(b->ncalls, c->h_ncalls.p, ns * 4, cudaMemcpyDeviceToHost, st));
-    if (b->call_stats && b->call_cap > 0) CU(cudaMemcpyAsync(b->call_stats, c->h_stats.p, (size_t)ns * cap * 24, cudaMemcpyDeviceToHost, st));
+    if (!tables_copied) {
+        if (b->calls && b->call_cap > 0) CU(cudaMemcpyAsync(b->calls, c->h_calls.p, (size_t)ns * cap * 16, cudaMemcpyDeviceToHost, st));
+        if (b->ncalls) CU(cudaMemcpyAsync(b->ncalls, c->h_ncalls.p, ns * 4, cudaMemcpyDeviceToHost, st));
+        if (b->call_stats && b->call_cap > 0) CU(cudaMemcpyAsync(b->call_stats, c->h_stats.p, (size_t)ns * cap * 24, cudaMemcpyDeviceToHost, st));
+    }
     if (b->cor) CU(cudaMemcpyAsync(b->cor, c->h_cor.p, ns * 8, cudaMemcpyDeviceToHost, st));
     int warn = 0;
     if ((rc = pull_flags(st, &warn))) return rc;
