@@ -398,7 +398,11 @@ def gpu_arm(a, rank, world):
         n_e2e = max(2, min(a.steps, 10))
 
         pairs12 = (nb + 1) // 2
-        obs12_p, ovf12_i, ovf12_v = edb.pack_counts12(obs_h, out=hb.empty((ns, (3 * pairs12 + 3) // 4 * 4), np.uint8))
+        out12 = hb.empty((ns, (3 * pairs12 + 3) // 4 * 4), np.uint8)
+        obs12_p, ovf12_i, ovf12_v = edb.pack_counts12(obs_h, out=out12)
+        t0 = time.perf_counter()
+        edb.pack_counts12(obs_h, out=out12)
+        pack_ms = 1e3 * (time.perf_counter() - t0)
 
         h2d = obs12_p.nbytes + ovf12_i.nbytes + ovf12_v.nbytes + ref.nbytes + phi_h.nbytes + exp_h.nbytes
 
@@ -420,6 +424,9 @@ def gpu_arm(a, rank, world):
 
         e2e = timed(base, want_ll=False, want_path=False)
         e2e.update(h2d_bytes_per_step=int(h2d), steps=n_e2e,
+                   pack_ms_once_per_cohort=pack_ms, pack_note="edb200_pack_counts12 on the host's threads: int32 count matrix -> the 12-bit layout; run "
+                                                              "once per cohort by the loader, NOT inside the timed call (e2e.int32_counts is the call on the "
+                                                              "unpacked matrix)",
                    counts_layout=f"rows of 12-bit fields [sample][bin] + overflow list ({int(ovf12_i.size)} entries of 4095 reads and more) — "
                                  "edb200_batch.observed12",
                    api="edb200_cohort_run_host (C ABI, pinned host buffers): counts in; CNV call table, per-call BF / reads.expected / "

@@ -18,5 +18,5 @@ There is no CPU fallback.
 """
 from ._lib import EDB200Error, device_info, init, launch_count  # noqa: F401
 from .api import C_hmm, CallCNVs, ExomeDepth, TestCNV, emission, get_loglike_matrix, lnbeta, somatic_CNV_call, viterbi_hmm  # noqa: F401
-from .cohort import Cohort, pack_counts, pack_counts12  # noqa: F401
+from .cohort import Cohort, pack_counts, pack_counts12, pack_counts12_numpy, pack_counts_numpy  # noqa: F401
 from . import betabin, refset  # noqa: F401

@@ -18,7 +18,7 @@ SWEEP_AUTO, SWEEP_LANE_PER_STATE, SWEEP_THREAD_PER_CHAIN = 0, 1, 2
 
 EXPORTS = (
     "edb200_init", "edb200_shutdown", "edb200_last_error", "edb200_device_info", "edb200_launch_count",
-    "edb200_host_alloc", "edb200_host_free", "edb200_get_loglike_matrix", "edb200_emission", "edb200_lnbeta", "edb200_hmm",
+    "edb200_host_alloc", "edb200_host_free", "edb200_pack_counts16", "edb200_pack_counts12", "edb200_get_loglike_matrix", "edb200_emission", "edb200_lnbeta", "edb200_hmm",
     "edb200_cohort_create", "edb200_cohort_destroy", "edb200_cohort_set_option", "edb200_cohort_segment_stats", "edb200_cohort_table", "edb200_cohort_table_copy",
     "edb200_cohort_run_device", "edb200_cohort_capture_device", "edb200_graph_launch", "edb200_graph_destroy",
     "edb200_cohort_run_host", "edb200_status", "edb200_profile", "edb200_profile_read",
@@ -76,6 +76,9 @@ def load():
     L.edb200_host_alloc.argtypes = [C.c_size_t]
     L.edb200_host_free.restype = None
     L.edb200_host_free.argtypes = [vp]
+    for fn in (L.edb200_pack_counts16, L.edb200_pack_counts12):
+        fn.restype = i64
+        fn.argtypes = [vp, i64, i32, i64, vp, i64, vp, vp, i64]
     L.edb200_get_loglike_matrix.restype = C.c_int
     L.edb200_get_loglike_matrix.argtypes = [vp, vp, vp, vp, dbl, i64, vp]
     L.edb200_lnbeta.restype = C.c_int

@@ -13,19 +13,43 @@ def _ptr(a):
     return a.ctypes.data if a is not None else None
 
 
+def _pack_native(bits, observed, out, out_stride):
+    """edb200_pack_counts16 / edb200_pack_counts12 (host threads, include/exomedepth_b200.h) over an int32 matrix."""
+    lib = _lib.load()
+    fn = lib.edb200_pack_counts12 if bits == 12 else lib.edb200_pack_counts16
+    ns, nb = observed.shape
+    cap = 1 << 16
+    while True:
+        idx, val = np.empty(cap, np.int64), np.empty(cap, np.int32)
+        n = fn(_ptr(observed), observed.strides[0] // 4, ns, nb, _ptr(out), out_stride, _ptr(idx), _ptr(val), cap)
+        if n < 0:
+            raise ValueError(lib.edb200_last_error().decode() or "pack_counts failed")
+        if n <= cap:
+            return idx[:n].copy(), val[:n].copy()
+        cap = int(n)
+
+
+def _as_count_matrix(observed):
+    observed = np.asarray(observed)
+    if observed.ndim != 2:
+        raise ValueError("count matrix must be [n_samples, n_bins]")
+    if observed.dtype != np.int32 or observed.strides[1] != 4 or observed.strides[0] % 4 or observed.strides[0] < 4 * observed.shape[1]:
+        if observed.size and (observed.min() < 0 or observed.max() > np.iinfo(np.int32).max):
+            raise ValueError("negative read count" if observed.min() < 0 else "read count beyond int32")
+        observed = np.ascontiguousarray(observed, np.int32)
+    return observed
+
+
 def pack_counts(observed, out=None):
     """The 16-bit ingestion layout of a count matrix (include/exomedepth_b200.h, edb200_batch.observed16): returns
     (uint16[n_samples, n_bins] with 65535 = "see the overflow list", int64 flat indices sample * n_bins + bin, int32 values).
     `out`: an existing uint16 array (e.g. pinned) to fill.  This is the layout a loader writes ONCE per cohort
-    (R/countBamInGranges.R:356-369 produces the counts); it halves the bytes every later call moves over PCIe."""
-    observed = np.asarray(observed)
-    if observed.min(initial=0) < 0:
-        raise ValueError("negative read count")
-    big = observed >= 65535
-    idx = np.flatnonzero(big.ravel()).astype(np.int64)
-    val = observed.ravel()[idx].astype(np.int32)
+    (R/countBamInGranges.R:356-369 produces the counts); it halves the bytes every later call moves over PCIe.
+    Encoded by the library's host-side encoder (edb200_pack_counts16); pack_counts_numpy is the same thing in numpy."""
+    observed = _as_count_matrix(observed)
     u16 = out if out is not None else np.empty(observed.shape, np.uint16)
-    np.minimum(observed, 65535, out=u16, casting="unsafe")
+    assert u16.shape == observed.shape and u16.dtype == np.uint16 and u16.flags.c_contiguous
+    idx, val = _pack_native(16, observed, u16, observed.shape[1])
     return u16, idx, val
 
 
@@ -33,7 +57,30 @@ def pack_counts12(observed, out=None):
     """The 12-bit ingestion layout (edb200_batch.observed12): returns (uint8[n_samples, stride] — every row a little-endian
     bit stream of 12 bits per bin, 4095 = "see the overflow list", stride = 3 * ceil(n_bins / 2) rounded up to 4 —, int64 flat
     indices sample * n_bins + bin, int32 values).  `out`: an existing uint8 array of that shape (e.g. pinned) to fill.  A
-    quarter fewer bytes per call over PCIe than pack_counts."""
+    quarter fewer bytes per call over PCIe than pack_counts.  Encoded by edb200_pack_counts12; pack_counts12_numpy is the same
+    thing in numpy."""
+    observed = _as_count_matrix(observed)
+    ns, nb = observed.shape
+    stride = ((nb + 1) // 2 * 3 + 3) // 4 * 4
+    u8 = out if out is not None else np.zeros((ns, stride), np.uint8)
+    assert u8.shape == (ns, stride) and u8.dtype == np.uint8 and u8.flags.c_contiguous
+    idx, val = _pack_native(12, observed, u8, stride)
+    return u8, idx, val
+
+
+def pack_counts_numpy(observed):
+    """pack_counts, written out in numpy (the definition the encoder is tested against)."""
+    observed = np.asarray(observed)
+    if observed.min(initial=0) < 0:
+        raise ValueError("negative read count")
+    big = observed >= 65535
+    idx = np.flatnonzero(big.ravel()).astype(np.int64)
+    val = observed.ravel()[idx].astype(np.int32)
+    return np.minimum(observed, 65535).astype(np.uint16), idx, val
+
+
+def pack_counts12_numpy(observed):
+    """pack_counts12, written out in numpy (the definition the encoder is tested against)."""
     observed = np.asarray(observed)
     if observed.min(initial=0) < 0:
         raise ValueError("negative read count")
@@ -42,9 +89,7 @@ def pack_counts12(observed, out=None):
     idx = np.flatnonzero(big.ravel()).astype(np.int64)
     val = observed.ravel()[idx].astype(np.int32)
     pairs = (nb + 1) // 2
-    stride = (pairs * 3 + 3) // 4 * 4
-    u8 = out if out is not None else np.zeros((ns, stride), np.uint8)
-    assert u8.shape == (ns, stride) and u8.dtype == np.uint8
+    u8 = np.zeros((ns, (pairs * 3 + 3) // 4 * 4), np.uint8)
     v = np.zeros((ns, 2 * pairs), np.uint16)
     np.minimum(observed, 4095, out=v[:, :nb], casting="unsafe")
     v0, v1 = v[:, 0::2], v[:, 1::2]

@@ -425,6 +425,30 @@ void edb200_host_free(void* p)
     if (p) cudaFreeHost(p);
 }
 
+// host-side encoders of the ingestion layouts (host_tables.cpp:pack_counts); no device involved
+static int64_t pack_checked(int bits, const int32_t* counts, int64_t stride, int32_t n_samples, int64_t n_bins, void* out, int64_t out_stride,
+                            int64_t min_stride, int64_t* ovf_index, int32_t* ovf_value, int64_t cap)
+{
+    if (n_samples < 0 || n_bins < 0 || cap < 0 || (cap > 0 && (!ovf_index || !ovf_value))) return fail(EDB200_ERR_ARG, "pack_counts: bad size or overflow list"), -1;
+    if (n_samples == 0 || n_bins == 0) return 0;
+    if (!counts || !out || stride < n_bins || out_stride < min_stride) return fail(EDB200_ERR_ARG, "pack_counts: null matrix or stride smaller than a row"), -1;
+    const int64_t n = edb::pack_counts(bits, counts, stride, n_samples, n_bins, out, out_stride, ovf_index, ovf_value, cap);
+    if (n < 0) fail(EDB200_ERR_ARG, "pack_counts: negative read count");
+    return n;
+}
+
+int64_t edb200_pack_counts16(const int32_t* counts, int64_t stride, int32_t n_samples, int64_t n_bins, uint16_t* out16, int64_t out_stride,
+                             int64_t* overflow_index, int32_t* overflow_value, int64_t overflow_cap)
+{
+    return pack_checked(16, counts, stride, n_samples, n_bins, out16, out_stride, n_bins, overflow_index, overflow_value, overflow_cap);
+}
+
+int64_t edb200_pack_counts12(const int32_t* counts, int64_t stride, int32_t n_samples, int64_t n_bins, uint8_t* out12, int64_t out_stride,
+                             int64_t* overflow_index, int32_t* overflow_value, int64_t overflow_cap)
+{
+    return pack_checked(12, counts, stride, n_samples, n_bins, out12, out_stride, (n_bins + 1) / 2 * 3, overflow_index, overflow_value, overflow_cap);
+}
+
 int edb200_profile(int enable)
 {
     if (int rc = need_ctx()) return rc;

@@ -247,6 +247,72 @@ void viterbi_cut_pieces(const int32_t* chain_tiles, int n_chains, int n_g32, int
     begin[n_slots] = (int32_t)(items.size() / 2);
 }
 
+int64_t pack_counts(int bits, const int32_t* counts, int64_t stride, int32_t n_samples, int64_t n_bins, void* out, int64_t out_stride,
+                    int64_t* ovf_index, int32_t* ovf_value, int64_t cap)
+{
+    struct Entry { int64_t index; int32_t value; };
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)std::min<int64_t>(hw ? (hw > 16 ? 16 : hw) : 1, n_samples);
+    if ((int64_t)n_samples * n_bins < (1 << 20)) nt = 1;
+    if (nt < 1) nt = 1;
+    std::vector<std::vector<Entry>> found(nt);
+    std::vector<int> bad(nt, 0);
+    const int32_t sentinel = bits == 12 ? 4095 : 65535;
+    // a block of consecutive samples per thread: the per-thread lists, concatenated in thread order, are sorted by flat index
+    auto work = [&](int t) {
+        const int32_t s0 = (int32_t)((int64_t)n_samples * t / nt), s1 = (int32_t)((int64_t)n_samples * (t + 1) / nt);
+        for (int32_t s = s0; s < s1; s++) {
+            const int32_t* row = counts + (int64_t)s * stride;
+            auto field = [&](int64_t b) -> uint32_t {
+                const int32_t v = row[b];
+                if (v < 0) bad[t] = 1;
+                if (v >= sentinel) {
+                    found[t].push_back(Entry{(int64_t)s * n_bins + b, v});
+                    return (uint32_t)sentinel;
+                }
+                return (uint32_t)v;
+            };
+            if (bits == 16) {
+                uint16_t* o = (uint16_t*)out + (int64_t)s * out_stride;
+                for (int64_t b = 0; b < n_bins; b++) o[b] = (uint16_t)field(b);
+            } else {
+                uint8_t* o = (uint8_t*)out + (int64_t)s * out_stride;
+                int64_t b = 0;
+                for (; b + 1 < n_bins; b += 2, o += 3) {
+                    const uint32_t w = field(b) | field(b + 1) << 12;             // bins 2i, 2i+1 in bytes 3i .. 3i+2
+                    o[0] = (uint8_t)w;
+                    o[1] = (uint8_t)(w >> 8);
+                    o[2] = (uint8_t)(w >> 16);
+                }
+                if (b < n_bins) {
+                    const uint32_t w = field(b);
+                    o[0] = (uint8_t)w;
+                    o[1] = (uint8_t)(w >> 8);
+                    o[2] = 0;
+                }
+            }
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    int64_t n = 0;
+    for (int t = 0; t < nt; t++) {
+        if (bad[t]) return -1;
+        for (const Entry& e : found[t]) {
+            if (n < cap) {
+                ovf_index[n] = e.index;
+                ovf_value[n] = e.value;
+            }
+            n++;
+        }
+    }
+    return n;
+}
+
 int frame_positions(int64_t nb, const int32_t* start, const int32_t* end, double L, int32_t* pos)
 {
     // R/class_definition.R:368: as.integer(c(start[1] - 2*L, start, end[last] + 2*L))

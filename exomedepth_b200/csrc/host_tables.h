@@ -26,6 +26,12 @@ void build_log_transition_rows(int S, const double* T, const int32_t* pos, int32
 void build_decay_rows(const int32_t* pos, int32_t nobs, double L, double* decay);
 // CallCNVs framing of one chromosome's positions (R/class_definition.R:368); pos has nb+2 entries. 0 = ok
 int frame_positions(int64_t nb, const int32_t* start, const int32_t* end, double L, int32_t* pos);
+
+// Encoders of the count-matrix ingestion layouts (include/exomedepth_b200.h: edb200_batch.observed16 / observed12), on the
+// host's threads.  bits = 16: out = uint16 rows, out_stride in elements; bits = 12: out = rows of 12-bit fields, out_stride in
+// bytes.  Returns the number of overflow entries the matrix has (only the first `cap` are written), -1 for a negative count.
+int64_t pack_counts(int bits, const int32_t* counts, int64_t stride, int32_t n_samples, int64_t n_bins, void* out, int64_t out_stride,
+                    int64_t* ovf_index, int32_t* ovf_value, int64_t cap);
 // in-place NaN -> -Inf for the device copy of the table: in the recurrence a NaN candidate and a -Inf candidate
 // behave identically (neither can satisfy the strict '>' of src/hmm.cpp:81)
 void nan_to_neg_inf(double* v, size_t n);

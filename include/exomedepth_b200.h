@@ -58,6 +58,16 @@ EDB200_API int         edb200_profile_read(char *buf, int buflen);
 /* page-locked host buffers for the host-pointer entry points (optional, speeds up the copies) */
 EDB200_API void       *edb200_host_alloc(size_t bytes);
 EDB200_API void        edb200_host_free(void *p);
+/* Encoders of the count-matrix ingestion layouts of edb200_batch (observed16 / observed12, below) — what a loader runs once per
+ * cohort over the integer matrix getBamCounts produced (R/countBamInGranges.R:356-369).  Host code on the host's threads; no
+ * GPU involved.  counts: int32 [n_samples][stride]; out16: uint16 [n_samples][out_stride] (elements), out12: rows out_stride
+ * BYTES apart, >= 3 * ceil(n_bins / 2).  Counts at or beyond the layout's sentinel (65535 / 4095) go to the overflow list,
+ * sorted by flat index sample * n_bins + bin; the first overflow_cap entries are written.  Returns the number of entries the
+ * matrix has (call again with larger lists if it exceeds overflow_cap), -1 for a bad argument or a negative count. */
+EDB200_API int64_t     edb200_pack_counts16(const int32_t *counts, int64_t stride, int32_t n_samples, int64_t n_bins, uint16_t *out16,
+                                            int64_t out_stride, int64_t *overflow_index, int32_t *overflow_value, int64_t overflow_cap);
+EDB200_API int64_t     edb200_pack_counts12(const int32_t *counts, int64_t stride, int32_t n_samples, int64_t n_bins, uint8_t *out12,
+                                            int64_t out_stride, int64_t *overflow_index, int32_t *overflow_value, int64_t overflow_cap);
 
 /* ---- the two .Call routines, argument for argument --------------------------------------------- */
 

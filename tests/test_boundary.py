@@ -160,3 +160,40 @@ def test_ingestion_layouts_round_trip():
         assert np.array_equal(dec, obs)
     with pytest.raises(ValueError):
         pack_counts12(np.array([[1, -1]]))
+    with pytest.raises(ValueError):
+        pack_counts(np.array([[1, -1]], np.int32))
+
+
+def test_native_encoders_match_the_numpy_definition():
+    """edb200_pack_counts16 / edb200_pack_counts12 (host threads, no GPU) against cohort.pack_counts_numpy / pack_counts12_numpy:
+    a matrix large enough for several threads, more overflow entries than the first guess of the list capacity, a strided
+    input, int64 input, a pinned-style preallocated output, and the C entry points' argument checks."""
+    import numpy as np
+
+    from exomedepth_b200 import _lib, pack_counts, pack_counts12
+    from exomedepth_b200.cohort import pack_counts12_numpy, pack_counts_numpy
+    rng = np.random.default_rng(9)
+    big = rng.integers(0, 4200, (37, 40001)).astype(np.int32)                 # ~2.5 % at or beyond 4095: > 65,536 entries? no: ~37k
+    big[:, ::3] = rng.integers(4095, 90000, big[:, ::3].shape)                 # a third of the bins overflow: ~493k entries
+    wide = np.zeros((37, 40100), np.int32)
+    wide[:, :40001] = big
+    for obs in (big, wide[:, :40001], big.astype(np.int64), big[:1, :1], big[:3, :2]):
+        for native, ref in ((pack_counts, pack_counts_numpy), (pack_counts12, pack_counts12_numpy)):
+            got, want = native(obs), ref(obs)
+            for g, w in zip(got, want):
+                assert g.dtype == w.dtype and np.array_equal(g, w), (native.__name__, obs.shape)
+    assert pack_counts12(big)[1].size > (1 << 16)
+    out = np.full((37, (40001 + 1) // 2 * 3 + 3 & ~3), 0xEE, np.uint8)
+    u8, idx, val = pack_counts12(big, out=out)
+    assert u8 is out and np.array_equal(u8[:, :60003], pack_counts12_numpy(big)[0][:, :60003])
+    L = _lib.load()
+    i64, i32 = np.zeros(4, np.int64), np.zeros(4, np.int32)
+    small = np.arange(6, dtype=np.int32).reshape(2, 3)
+    o8 = np.zeros((2, 8), np.uint8)
+    assert L.edb200_pack_counts12(small.ctypes.data, 3, 2, 3, o8.ctypes.data, 8, i64.ctypes.data, i32.ctypes.data, 4) == 0
+    assert L.edb200_pack_counts12(small.ctypes.data, 3, 2, 3, o8.ctypes.data, 5, i64.ctypes.data, i32.ctypes.data, 4) == -1      # row of 6 bytes
+    assert L.edb200_pack_counts12(small.ctypes.data, 2, 2, 3, o8.ctypes.data, 8, i64.ctypes.data, i32.ctypes.data, 4) == -1      # stride < n_bins
+    assert L.edb200_pack_counts16(None, 3, 2, 3, o8.ctypes.data, 3, i64.ctypes.data, i32.ctypes.data, 4) == -1
+    assert L.edb200_pack_counts16(small.ctypes.data, 3, 0, 3, None, 3, None, None, 0) == 0
+    small[1, 1] = 70000
+    assert L.edb200_pack_counts16(small.ctypes.data, 3, 2, 3, o8.ctypes.data, 3, None, None, 0) == 1           # counted, nothing written
